@@ -1,0 +1,165 @@
+/*
+ * mmla_b200.h — C-ABI of libmmla_b200.so: the B200 (sm_100a) implementation of the
+ * mmla-audio analytics hot path.
+ *
+ * The reference (lizaibeim/mmla-audio) has no FFI: its boundary is the set of Python call
+ * signatures its entry scripts use.  Each entry point below names the reference
+ * call it replaces (paths relative to the reference root); the Python layer in
+ * mmla_audio_b200/ binds these with ctypes and re-exposes the reference's own signatures
+ * (INTEGRATION.md shows the stub a maintainer would add).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch / C++ types.
+ *   - All data pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *     enqueue work; they never synchronise the device.
+ *   - Return value: 0 on success, negative MMLA_E* on failure; mmla_last_error() returns a
+ *     thread-local message for the last failing call on the calling thread.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     MMLA_ECUDA.
+ */
+#ifndef MMLA_B200_H
+#define MMLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMLA_OK        0
+#define MMLA_EINVAL   -1   /* bad argument                         */
+#define MMLA_ECUDA    -2   /* CUDA runtime error / no device       */
+#define MMLA_ENOMEM   -3   /* allocation failed                    */
+#define MMLA_EUNSUP   -4   /* parameter combination not supported  */
+
+#define MMLA_WINDOW_RECT    0   /* python_speech_features default (what the reference uses) */
+#define MMLA_WINDOW_HANN    1
+#define MMLA_WINDOW_HAMMING 2
+
+const char* mmla_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int mmla_abi_version(void);
+/* CRC-32C (Castagnoli) of a HOST buffer, as stored in TF tensor-bundle entries. Host only. */
+uint32_t mmla_crc32c_host(const void* data_host, size_t n);
+
+/* ------------------------------------------------------------------------------------------
+ * Speaker-ID features.
+ * Replaces python_speech_features.mfcc(sig, rate, winlen=0.025, winstep=0.01, nfft=512)
+ *   SpeakerIdentification/scripts/speaker_identification.py:89,285,341,386
+ *   SpeakerIdentification/scripts/speaker_identification_post_processing.py:256
+ * and, when with_deltas=1, the reference's delta(feat,2) twice + concatenate
+ *   speaker_identification.py:141-151,387-389
+ * and, when pad_frames>0, the zero-pad / truncate to 256 rows of input_feature_gen
+ *   speaker_identification.py:391-395  (or to a multiple of 256 rows for whole files, :347-349)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct MmlaMfccParams {
+    int32_t samplerate;     /* 16000 */
+    int32_t frame_len;      /* 400  = round_half_up(winlen*samplerate); must be <= nfft */
+    int32_t frame_step;     /* 160  = round_half_up(winstep*samplerate) */
+    int32_t nfft;           /* 512 (the warp FFT is sized for exactly 512) */
+    int32_t nfilt;          /* 26 = reference; 40 = BASELINE config 3; <= 64 */
+    int32_t numcep;         /* 13; <= 16 and <= nfilt */
+    int32_t ceplifter;      /* 22 */
+    int32_t append_energy;  /* 1: c0 := ln(frame energy) */
+    int32_t window;         /* MMLA_WINDOW_* */
+    int32_t with_deltas;    /* 0: rows are [numcep]; 1: rows are [numcep | delta | delta-delta] */
+    int32_t pad_frames;     /* 0: write T rows per clip; >0: write exactly pad_frames rows
+                               (first min(T,pad_frames) real, remainder zero) */
+    float   preemph;        /* 0.97 */
+    float   lowfreq;        /* 0 */
+    float   highfreq;       /* samplerate/2 */
+} MmlaMfccParams;
+
+/* Number of frames python_speech_features produces for a clip of n samples. */
+int32_t mmla_psf_num_frames(int64_t n_samples, const MmlaMfccParams* p);
+
+/*
+ * pcm            int16 mono samples at int16 scale (as scipy.io.wavfile.read returns them),
+ *                16-byte aligned, readable up to the next 16-byte boundary past the last sample.
+ * clip_off_host  [n_clips] start sample of each clip in `pcm`, or NULL for uniform clips at
+ *                clip i -> i*clip_stride.
+ * clip_len_host  [n_clips] samples per clip, or NULL for uniform length `clip_len`.
+ * out            float32 [n_clips][rows][dim] with clip i at out + i*out_clip_stride floats;
+ *                dim = numcep*(with_deltas?3:1); rows = pad_frames>0 ? pad_frames : T(clip).
+ */
+int mmla_psf_mfcc(const int16_t* pcm, int64_t pcm_total_samples,
+                  const int64_t* clip_off_host, const int32_t* clip_len_host,
+                  int64_t n_clips, int32_t clip_len, int64_t clip_stride,
+                  const MmlaMfccParams* p,
+                  float* out, int64_t out_clip_stride, void* stream);
+
+/* Replaces delta(feat, N): SpeakerIdentification/scripts/speaker_identification.py:141-151.
+ * feat/out float32 [n_frames][dim]; out[t] = sum_{k=-N..N} k*feat[clamp(t+k)] / (2*sum k^2). */
+int mmla_delta(const float* feat, int64_t n_frames, int32_t dim, int32_t N, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Overlap-detection features.
+ * Replaces OverlapFeaturesGenerator.generate_mels / generate_zcr / generate_zcr_image +
+ * plt.imsave(origin='lower') + tf.image.decode_png(.,3)
+ *   OverlapDetection/scripts/overlap_features_generator.py:65-151
+ *   OverlapDetection/scripts/record_on_pc.py:139,156-158
+ * Every clip is zero-padded / truncated to hop*150 = 24000 samples (…generator.py:73-80).
+ * Any of the four outputs may be NULL.
+ *   s_db      float32 [n_clips][n_mels][151]   power_to_db(ref=max, top_db=80)
+ *   s_db_norm float32 [n_clips][n_mels][151]   min-max normalised
+ *   zcr       float32 [n_clips][151]
+ *   image     uint8   [n_clips][n_mels][151][3] row 0 = highest mel band, trunc(v*255)
+ * ---------------------------------------------------------------------------------------- */
+int mmla_overlap_features(const int16_t* pcm, int64_t pcm_total_samples,
+                          const int64_t* clip_off_host, const int32_t* clip_len_host,
+                          int64_t n_clips, int32_t clip_len, int64_t clip_stride,
+                          int32_t n_mels,
+                          float* s_db, float* s_db_norm, float* zcr, uint8_t* image,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Classifier forward pass.
+ * Replaces tf.keras.models.load_model(dir) / model.predict(x)
+ *   OverlapDetection/scripts/record_on_pc.py:87-88,159
+ *   SpeakerIdentification/scripts/record_on_pc.py:76-77,136
+ * Weights are passed as one float32 HOST blob laid out by mmla_audio_b200/models.py
+ * (TF layouts kept: HWIO / WIO kernels, LSTM [in,4u] i,f,c,o, Dense [in,out]).
+ * ---------------------------------------------------------------------------------------- */
+#define MMLA_NET_OVERLAP 0   /* x: uint8 [B,128,151,3] (or float32 0..255)  -> prob [B,2]   */
+#define MMLA_NET_SPEAKER 1   /* x: float32 [B,256,39]                       -> prob [B,n]   */
+#define MMLA_HEAD_SOFTMAX 0
+#define MMLA_HEAD_SIGMOID 1
+
+typedef struct MmlaNet MmlaNet;   /* opaque */
+
+int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head_activation,
+                    const float* weights_host, int64_t n_weights, MmlaNet** out_net);
+void mmla_net_destroy(MmlaNet* net);
+/* Bytes of device workspace needed for a forward pass over `batch` clips. */
+int64_t mmla_net_workspace_bytes(const MmlaNet* net, int64_t batch);
+/*
+ * x_is_u8: 1 when x is the uint8 image tensor (overlap net only), 0 for float32 input.
+ * prob    float32 [batch][n_classes]; labels int32 [batch] = argmax (first max wins), may be NULL.
+ */
+int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch,
+                     void* workspace, int64_t workspace_bytes,
+                     float* prob, int32_t* labels, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Label tallies.  Replaces the counting loops of
+ *   OverlapDetection/scripts/overlap_degree_distribution.py:49-61
+ *   SpeakerIdentification/scripts/speaker_time_distribution.py:52-80
+ * labels int32 [n]; entries outside [0,n_classes) (e.g. the 'silent' sentinel -1) are counted
+ * in counts[n_classes].  counts int64 [n_classes+1] is ADDED to (zero it first).
+ * ---------------------------------------------------------------------------------------- */
+int mmla_tally(const int32_t* labels, int64_t n, int32_t n_classes, int64_t* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic PCM (stands in for PyAudio capture, OverlapDetection/scripts/record_on_pc.py:115-124).
+ * Integer-only generator: clip i depends only on (seed, first_clip+i); bit-identical to
+ * oracle/synth.py.  sine_table is int16[1024] on the device.
+ * ---------------------------------------------------------------------------------------- */
+int mmla_synth_pcm(int16_t* pcm, int64_t first_clip, int64_t n_clips, int32_t clip_len,
+                   int64_t clip_stride, uint32_t seed, const int16_t* sine_table, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMLA_B200_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of libmmla_b200.so (the C-ABI declared in include/mmla_b200.h).
+
+Fails loudly: a missing library raises ImportError with the build command; a failing call
+raises MmlaError carrying mmla_last_error().  No fallback path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmmla_b200.so")
+
+# every symbol include/mmla_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = (
+    "mmla_last_error", "mmla_abi_version", "mmla_crc32c_host",
+    "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_delta", "mmla_overlap_features",
+    "mmla_net_create", "mmla_net_destroy", "mmla_net_workspace_bytes", "mmla_net_forward",
+    "mmla_tally", "mmla_synth_pcm",
+)
+
+
+class MmlaError(RuntimeError):
+    pass
+
+
+class MfccParams(C.Structure):
+    """Mirror of ``MmlaMfccParams``; defaults = the reference call
+    ``mfcc(sig, rate, winlen=0.025, winstep=0.01, nfft=512)``."""
+    _fields_ = [
+        ("samplerate", C.c_int32), ("frame_len", C.c_int32), ("frame_step", C.c_int32),
+        ("nfft", C.c_int32), ("nfilt", C.c_int32), ("numcep", C.c_int32),
+        ("ceplifter", C.c_int32), ("append_energy", C.c_int32), ("window", C.c_int32),
+        ("with_deltas", C.c_int32), ("pad_frames", C.c_int32),
+        ("preemph", C.c_float), ("lowfreq", C.c_float), ("highfreq", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m mmla_audio_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    mp = C.POINTER(MfccParams)
+    sigs = {
+        "mmla_last_error": (C.c_char_p, []),
+        "mmla_abi_version": (C.c_int, []),
+        "mmla_crc32c_host": (u32, [vp, C.c_size_t]),
+        "mmla_psf_num_frames": (i32, [i64, mp]),
+        "mmla_psf_mfcc": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, mp, vp, i64, vp]),
+        "mmla_delta": (C.c_int, [vp, i64, i32, i32, vp, vp]),
+        "mmla_overlap_features": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, i32, vp, vp, vp, vp, vp]),
+        "mmla_net_create": (C.c_int, [i32, i32, i32, vp, i64, C.POINTER(vp)]),
+        "mmla_net_destroy": (None, [vp]),
+        "mmla_net_workspace_bytes": (i64, [vp, i64]),
+        "mmla_net_forward": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, vp, vp]),
+        "mmla_tally": (C.c_int, [vp, i64, i32, vp, vp]),
+        "mmla_synth_pcm": (C.c_int, [vp, i64, i64, i32, i64, u32, vp, vp]),
+    }
+    assert set(sigs) == set(SYMBOLS)
+    for name, (res, args) in sigs.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:     # a stale / partial build: fail loudly, never fall back
+            raise ImportError(f"{LIB_PATH} does not export {name}; rebuild with "
+                              "`python -m mmla_audio_b200.build --force`") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mmla_last_error().decode("utf-8", "replace")
+        raise MmlaError(f"{what} failed (code {rc}): {msg}")
+
+
+def require_cuda():
+    """Import torch and insist on a CUDA device — the product path never runs on the CPU."""
+    import torch
+    if not torch.cuda.is_available():
+        raise MmlaError("mmla_audio_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr(torch) -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
