@@ -1,0 +1,657 @@
+// Classifier forward passes for sm_100a (fp32 path, bit-faithful layer semantics):
+//   overlap net  — Conv2D 1x1 -> 9 pre-activation residual blocks (BN-ELU-Conv3x3-BN-ELU-Conv(4,1),
+//                  three with stride-2 1x1 shortcut + MaxPool2x2 'same') -> mean over mel axis ->
+//                  BiLSTM(256) -> LeakyReLU(0.3) -> Dense(2) softmax
+//                  (OverlapDetection/scripts/overlap_detector_temp.py:253-303)
+//   speaker net  — Conv1D k4 -> 9 res units (MaxPool1D + stride-2 1x1 shortcut on three) ->
+//                  BN-ReLU-AvgPool1D(4) -> BiLSTM(256) -> Dense(n) softmax | sigmoid
+//                  (SpeakerIdentification/scripts/speaker_identification.py:168-218,401-410)
+// replacing model.predict(x) at OverlapDetection/scripts/record_on_pc.py:159 and
+// SpeakerIdentification/scripts/record_on_pc.py:136.
+//
+// Every convolution / dense projection / LSTM matmul runs through ONE implicit-GEMM kernel
+// (NHWC activations, TF HWIO weights = row-major [K][N]) whose A-operand gather applies the
+// preceding BatchNorm + activation on the fly and whose epilogue adds bias and the residual.
+// Keras 'same' padding (extra element at the end) is handled by explicit pad_top/pad_left.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr float kBnEps = 1e-3f;
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// implicit-GEMM convolution: Y[M,N] = gather(X)[M,K] * W[K,N] + bias (+ residual)
+// ---------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const void* x;            // NHWC float32, or uint8 when x_is_u8
+    const float* w;           // [K][N]
+    const float* bias;        // [N]
+    const float* pre_scale;   // per input channel BN scale (null: no BN/activation prologue)
+    const float* pre_shift;
+    const float* res;         // residual rows (null: none)
+    float* y;                 // [M][N]
+    long long res_row_stride; // floats between residual rows
+    long long M;
+    int x_is_u8, pre_act;
+    int H, W, Cin, Ho, Wo, N, K, kh, kw, stride, pad_t, pad_l;
+};
+
+constexpr int kBM = 128, kBK = 16;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_ELU) return v > 0.f ? v : expm1f(v);
+    return v;
+}
+
+template <int TN>
+__global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs a) {
+    constexpr int BN = 16 * TN;
+    constexpr int B_LOADS = (kBK * BN / 4 + 255) / 256;          // float4 per thread for the W tile
+    __shared__ __align__(16) float As[2][kBK][kBM];
+    __shared__ __align__(16) float Bs[2][kBK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long m0 = static_cast<long long>(blockIdx.x) * kBM;
+    const int n0 = blockIdx.y * BN;
+
+    // A-gather bookkeeping: this thread always fills row `arow` of the tile
+    const int arow = tid & 127, ahalf = tid >> 7;
+    const long long am = m0 + arow;
+    const bool avalid = am < a.M;
+    int hi0 = 0, wi0 = 0;
+    long long xbase = 0;
+    if (avalid) {
+        const int hw = a.Ho * a.Wo;
+        const long long b = am / hw;
+        const int r = static_cast<int>(am - b * hw);
+        const int ho = r / a.Wo, wo = r - ho * a.Wo;
+        hi0 = ho * a.stride - a.pad_t;
+        wi0 = wo * a.stride - a.pad_l;
+        xbase = b * a.H * a.W * a.Cin;
+    }
+    const bool fast = (a.Cin % kBK == 0) && !a.x_is_u8;
+    const float* xf = static_cast<const float*>(a.x);
+    const unsigned char* xu = static_cast<const unsigned char*>(a.x);
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float ra[8];
+    float4 rb[B_LOADS];
+
+    auto load_tiles = [&](int k0) {
+        if (fast) {
+            const int tap = k0 / a.Cin, c0 = k0 - tap * a.Cin;
+            const int ki = tap / a.kw, kj = tap - ki * a.kw;
+            const int hi = hi0 + ki, wi = wi0 + kj;
+            const bool inb = avalid && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+            const float* src = xf + xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c0 + ahalf * 8;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inb) {
+                    v = *reinterpret_cast<const float4*>(src + 4 * q);
+                    if (a.pre_scale) {
+                        const int c = c0 + ahalf * 8 + 4 * q;
+                        const float4 sc = *reinterpret_cast<const float4*>(a.pre_scale + c);
+                        const float4 sh = *reinterpret_cast<const float4*>(a.pre_shift + c);
+                        v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
+                        v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
+                        v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
+                        v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
+                    }
+                }
+                ra[4 * q + 0] = v.x; ra[4 * q + 1] = v.y; ra[4 * q + 2] = v.z; ra[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = k0 + ahalf * 8 + e;
+                float v = 0.f;
+                if (avalid && k < a.K) {
+                    const int tap = k / a.Cin, c = k - tap * a.Cin;
+                    const int ki = tap / a.kw, kj = tap - ki * a.kw;
+                    const int hi = hi0 + ki, wi = wi0 + kj;
+                    if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+                        const long long idx = xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c;
+                        v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
+                        if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
+                    }
+                }
+                ra[e] = v;
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < B_LOADS; ++l) {
+            const int idx = tid + 256 * l;                          // float4 index in [kBK][BN/4]
+            const int kr = idx / (BN / 4), c4 = idx - kr * (BN / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kr < kBK) {
+                const int k = k0 + kr, n = n0 + 4 * c4;
+                if (k < a.K) {
+                    const float* src = a.w + static_cast<long long>(k) * a.N + n;
+                    if (n + 3 < a.N && (a.N & 3) == 0) {
+                        v = *reinterpret_cast<const float4*>(src);
+                    } else {
+                        if (n + 0 < a.N) v.x = src[0];
+                        if (n + 1 < a.N) v.y = src[1];
+                        if (n + 2 < a.N) v.z = src[2];
+                        if (n + 3 < a.N) v.w = src[3];
+                    }
+                }
+            }
+            rb[l] = v;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) As[buf][ahalf * 8 + e][arow] = ra[e];
+#pragma unroll
+        for (int l = 0; l < B_LOADS; ++l) {
+            const int idx = tid + 256 * l;
+            const int kr = idx / (BN / 4), c4 = idx - kr * (BN / 4);
+            if (kr < kBK) *reinterpret_cast<float4*>(&Bs[buf][kr][4 * c4]) = rb[l];
+        }
+    };
+
+    const int nk = (a.K + kBK - 1) / kBK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kc = 0; kc < nk; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < nk) load_tiles((kc + 1) * kBK);
+#pragma unroll
+        for (int k = 0; k < kBK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kc + 1 < nk) store_tiles(buf ^ 1);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long m = m0 + ty * 8 + i;
+        if (m >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n < a.N) {
+                float v = acc[i][j] + a.bias[n];
+                if (a.res) v += a.res[m * a.res_row_stride + n];
+                a.y[m * a.N + n] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small layer kernels
+// ---------------------------------------------------------------------------------------------
+// MaxPool 'same' with window (ph, pw), stride = window, NHWC; out-of-range taps are -inf.
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, long long B,
+                                                      int H, int W, int C, int ph, int pw, int Ho, int Wo) {
+    const long long total = B * Ho * Wo * C;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int c = static_cast<int>(e % C);
+        long long r = e / C;
+        const int wo = static_cast<int>(r % Wo);
+        r /= Wo;
+        const int ho = static_cast<int>(r % Ho);
+        const long long b = r / Ho;
+        float m = -INFINITY;
+        for (int i = 0; i < ph; ++i)
+            for (int j = 0; j < pw; ++j) {
+                const int hi = ho * ph + i, wi = wo * pw + j;
+                if (hi < H && wi < W) m = fmaxf(m, x[((b * H + hi) * W + wi) * C + c]);
+            }
+        y[e] = m;
+    }
+}
+
+// overlap: Lambda(mean over axis 1 = H): [B,H,W,C] -> [B,W,C]
+__global__ void __launch_bounds__(256) mean_h_kernel(const float* __restrict__ x, float* __restrict__ y, long long B,
+                                                     int H, int W, int C) {
+    const long long total = B * W * C;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int c = static_cast<int>(e % C);
+        const long long r = e / C;
+        const int w = static_cast<int>(r % W);
+        const long long b = r / W;
+        float s = 0.f;
+        for (int h = 0; h < H; ++h) s += x[((b * H + h) * W + w) * C + c];
+        y[e] = s / static_cast<float>(H);
+    }
+}
+
+// speaker: BN -> ReLU -> AveragePooling1D(4): [B,T,C] -> [B,T/4,C]
+__global__ void __launch_bounds__(256) bn_relu_avgpool4_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               const float* __restrict__ sc, const float* __restrict__ sh,
+                                                               long long B, int T, int C) {
+    const int To = T / 4;
+    const long long total = B * To * C;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int c = static_cast<int>(e % C);
+        const long long r = e / C;
+        const int to = static_cast<int>(r % To);
+        const long long b = r / To;
+        float s = 0.f;
+        for (int i = 0; i < 4; ++i) s += fmaxf(fmaf(x[((b * T + 4 * to + i)) * C + c], sc[c], sh[c]), 0.f);
+        y[e] = s * 0.25f;
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// LSTM pointwise step: z [B,4u] (i,f,c,o pre-activations) -> c, h  (Keras gate order)
+__global__ void __launch_bounds__(256) lstm_gates_kernel(const float* __restrict__ z, long long z_row_stride,
+                                                         float* __restrict__ c, float* __restrict__ h, long long B,
+                                                         int u, int first_step) {
+    const long long total = B * u;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const long long b = e / u;
+        const int j = static_cast<int>(e - b * u);
+        const float* zr = z + b * z_row_stride;
+        const float ig = sigmoidf_(zr[j]);
+        const float fg = sigmoidf_(zr[u + j]);
+        const float gg = tanhf(zr[2 * u + j]);
+        const float og = sigmoidf_(zr[3 * u + j]);
+        const float cprev = first_step ? 0.f : c[e];
+        const float cn = fg * cprev + ig * gg;
+        c[e] = cn;
+        h[e] = og * tanhf(cn);
+    }
+}
+
+// head: z [B,512] (fwd|bwd) -> optional LeakyReLU -> Dense -> softmax|sigmoid -> prob, argmax
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ hf, const float* __restrict__ hb,
+                                                   const float* __restrict__ wk, const float* __restrict__ wb,
+                                                   float leaky, int use_leaky, int n_classes, int sigmoid_head,
+                                                   long long B, float* __restrict__ prob, int* __restrict__ labels) {
+    extern __shared__ float zs[];                                   // [warps][512]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* z = zs + warp * 512;
+    for (long long b = static_cast<long long>(blockIdx.x) * nw + warp; b < B; b += static_cast<long long>(gridDim.x) * nw) {
+        for (int i = lane; i < 512; i += 32) {
+            float v = i < 256 ? hf[b * 256 + i] : hb[b * 256 + i - 256];
+            if (use_leaky) v = v > 0.f ? v : leaky * v;
+            z[i] = v;
+        }
+        __syncwarp();
+        float* pr = prob + b * n_classes;
+        float vmax = -INFINITY;
+        for (int n = lane; n < n_classes; n += 32) {
+            float acc = 0.f;
+            for (int i = 0; i < 512; ++i) acc = fmaf(z[i], wk[static_cast<long long>(i) * n_classes + n], acc);
+            acc += wb[n];
+            pr[n] = acc;                                            // logits for now
+            vmax = fmaxf(vmax, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        float denom = 0.f;
+        if (!sigmoid_head) {
+            for (int n = lane; n < n_classes; n += 32) denom += expf(pr[n] - vmax);
+            for (int o = 16; o > 0; o >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, o);
+        }
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        for (int n = lane; n < n_classes; n += 32) {
+            const float l = pr[n];
+            const float pv = sigmoid_head ? sigmoidf_(l) : expf(l - vmax) / denom;
+            pr[n] = pv;
+            if (pv > best) { best = pv; besti = n; }               // first maximum within the lane
+        }
+        for (int o = 16; o > 0; o >>= 1) {                          // np.argmax: first max wins
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (labels && lane == 0) labels[b] = besti;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// network description + executor
+// ---------------------------------------------------------------------------------------------
+struct ConvW {
+    const float* k = nullptr;
+    const float* b = nullptr;
+    int kh = 1, kw = 1, cin = 0, cout = 0, stride = 1;
+};
+struct BnW {
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+};
+struct BlockW {
+    BnW bn1, bn2;
+    ConvW conv1, conv2, shortcut;
+    bool pool = false;
+};
+struct MmlaNet {
+    int kind = 0, n_classes = 0, head = 0;
+    float* dev = nullptr;                 // device blob (weights + folded BN)
+    ConvW stem;
+    std::vector<BlockW> blocks;
+    BnW final_bn;
+    ConvW lstm_in[2];                     // [feat,1024] projection (bias = LSTM bias)
+    ConvW lstm_rec[2];                    // [256,1024] recurrent (bias = zeros)
+    const float* dense_k = nullptr;
+    const float* dense_b = nullptr;
+    int in_h = 0, in_w = 0, in_c = 0;     // per-clip input geometry
+    int seq_len = 0, feat = 0;
+    long long per_clip_floats = 0;        // workspace floats per clip
+    int micro = 0;                        // clips per micro-batch
+};
+
+namespace {
+
+int same_out(int n, int s) { return (n + s - 1) / s; }
+int same_pad_before(int n, int k, int s) {
+    const int out = same_out(n, s);
+    int total = (out - 1) * s + k - n;
+    if (total < 0) total = 0;
+    return total / 2;
+}
+
+int launch_conv(const ConvW& c, const void* x, int x_is_u8, long long B, int H, int W, const BnW* pre, int pre_act,
+                const float* res, long long res_row_stride, float* y, cudaStream_t st) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.x_is_u8 = x_is_u8; a.w = c.k; a.bias = c.b;
+    a.pre_scale = pre ? pre->scale : nullptr;
+    a.pre_shift = pre ? pre->shift : nullptr;
+    a.pre_act = pre_act;
+    a.res = res; a.res_row_stride = res_row_stride; a.y = y;
+    a.H = H; a.W = W; a.Cin = c.cin;
+    a.Ho = same_out(H, c.stride); a.Wo = same_out(W, c.stride);
+    a.N = c.cout; a.K = c.kh * c.kw * c.cin;
+    a.kh = c.kh; a.kw = c.kw; a.stride = c.stride;
+    a.pad_t = same_pad_before(H, c.kh, c.stride);
+    a.pad_l = same_pad_before(W, c.kw, c.stride);
+    a.M = B * a.Ho * a.Wo;
+    if (a.M == 0) return MMLA_OK;
+    const unsigned gx = static_cast<unsigned>((a.M + kBM - 1) / kBM);
+    if (c.cout <= 16) {
+        conv_igemm_kernel<1><<<dim3(gx, (c.cout + 15) / 16), 256, 0, st>>>(a);
+    } else if (c.cout <= 32) {
+        conv_igemm_kernel<2><<<dim3(gx, (c.cout + 31) / 32), 256, 0, st>>>(a);
+    } else if (c.cout <= 64) {
+        conv_igemm_kernel<4><<<dim3(gx, (c.cout + 63) / 64), 256, 0, st>>>(a);
+    } else {
+        conv_igemm_kernel<8><<<dim3(gx, (c.cout + 127) / 128), 256, 0, st>>>(a);
+    }
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
+unsigned ew_grid(long long total) {
+    long long g = (total + 255) / 256;
+    const long long cap = 32LL * (mmla_num_sms() > 0 ? mmla_num_sms() : 148);
+    return static_cast<unsigned>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// host-side blob reader (spec traversal order, see mmla_audio_b200/models.py::pack_weights)
+struct BlobReader {
+    const float* p;
+    long long n, pos = 0;
+    bool ok = true;
+    const float* take(long long cnt) {
+        if (pos + cnt > n) { ok = false; return p; }
+        const float* r = p + pos;
+        pos += cnt;
+        return r;
+    }
+};
+
+}  // namespace
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const float* w_host, int64_t n_weights,
+                           MmlaNet** out_net) {
+    MMLA_REQUIRE(out_net && w_host, MMLA_EINVAL, "net_create: null argument");
+    MMLA_REQUIRE(kind == MMLA_NET_OVERLAP || kind == MMLA_NET_SPEAKER, MMLA_EINVAL, "net_create: bad kind %d", kind);
+    MMLA_REQUIRE(n_classes >= 1 && n_classes <= 4096, MMLA_EINVAL, "net_create: bad n_classes %d", n_classes);
+    MMLA_REQUIRE(head == MMLA_HEAD_SOFTMAX || head == MMLA_HEAD_SIGMOID, MMLA_EINVAL, "net_create: bad head %d", head);
+    MMLA_REQUIRE(mmla_num_sms() > 0, MMLA_ECUDA, "net_create: no CUDA device");
+    const bool ov = kind == MMLA_NET_OVERLAP;
+    // host staging blob: [weights as given][folded BN scale/shift][zero recurrent bias]
+    std::vector<float> stage(w_host, w_host + n_weights);
+    struct Fix { const float** dst; long long off; };
+    std::vector<Fix> fixes;
+    MmlaNet* net = new MmlaNet;
+    net->kind = kind; net->n_classes = n_classes; net->head = head;
+    BlobReader rd{w_host, n_weights};
+    auto take_ptr = [&](const float** dst, long long cnt) {
+        const long long off = rd.pos;
+        rd.take(cnt);
+        fixes.push_back({dst, off});
+    };
+    auto take_conv = [&](ConvW& c, int kh, int kw, int cin, int cout, int stride) {
+        c.kh = kh; c.kw = kw; c.cin = cin; c.cout = cout; c.stride = stride;
+        take_ptr(&c.k, static_cast<long long>(kh) * kw * cin * cout);
+        take_ptr(&c.b, cout);
+    };
+    auto take_bn = [&](BnW& bn, int ch) {
+        const float* g = rd.take(ch);
+        const float* be = rd.take(ch);
+        const float* mu = rd.take(ch);
+        const float* var = rd.take(ch);
+        if (!rd.ok) return;
+        while (stage.size() % 4) stage.push_back(0.f);             // float4-aligned scale/shift
+        const long long off = static_cast<long long>(stage.size());
+        for (int i = 0; i < ch; ++i) stage.push_back(static_cast<float>(g[i] / sqrt(static_cast<double>(var[i]) + kBnEps)));
+        for (int i = 0; i < ch; ++i) {
+            const double sc = g[i] / sqrt(static_cast<double>(var[i]) + kBnEps);
+            stage.push_back(static_cast<float>(be[i] - mu[i] * sc));
+        }
+        fixes.push_back({&bn.scale, off});
+        fixes.push_back({&bn.shift, off + ch});
+    };
+    const int chans[3] = {32, 64, 128};
+    if (ov) {
+        net->in_h = 128; net->in_w = 151; net->in_c = 3;
+        take_conv(net->stem, 1, 1, 3, 16, 1);
+    } else {
+        net->in_h = 1; net->in_w = 256; net->in_c = 39;
+        take_conv(net->stem, 1, 4, 39, 32, 1);
+    }
+    int cin = ov ? 16 : 32;
+    net->blocks.resize(9);
+    for (int s = 0; s < 3; ++s)
+        for (int r = 0; r < 3; ++r) {
+            BlockW& b = net->blocks[3 * s + r];
+            const int cout = chans[s];
+            b.pool = (r == 0);
+            take_bn(b.bn1, cin);
+            take_conv(b.conv1, ov ? 3 : 1, 3, cin, cout, 1);
+            take_bn(b.bn2, cout);
+            take_conv(b.conv2, ov ? 4 : 1, ov ? 1 : 3, cout, cout, 1);
+            if (b.pool) take_conv(b.shortcut, 1, 1, cin, cout, 2);
+            cin = cout;
+        }
+    if (!ov) take_bn(net->final_bn, 128);
+    net->feat = 128;
+    net->seq_len = ov ? 19 : 8;
+    long long zero_bias_off = -1;
+    for (int d = 0; d < 2; ++d) {
+        ConvW& pi = net->lstm_in[d];
+        ConvW& pr = net->lstm_rec[d];
+        pi.kh = pi.kw = 1; pi.cin = 128; pi.cout = 1024; pi.stride = 1;
+        pr.kh = pr.kw = 1; pr.cin = 256; pr.cout = 1024; pr.stride = 1;
+        take_ptr(&pi.k, 128LL * 1024);
+        take_ptr(&pr.k, 256LL * 1024);
+        take_ptr(&pi.b, 1024);
+        if (zero_bias_off < 0) {
+            while (stage.size() % 4) stage.push_back(0.f);
+            zero_bias_off = static_cast<long long>(stage.size());
+            stage.insert(stage.end(), 1024, 0.f);
+        }
+        fixes.push_back({&pr.b, zero_bias_off});
+    }
+    take_ptr(&net->dense_k, 512LL * n_classes);
+    take_ptr(&net->dense_b, n_classes);
+    if (!rd.ok || rd.pos != n_weights) {
+        mmla_set_error("net_create: weight blob has %lld floats, the %s net with %d classes needs %lld",
+                       static_cast<long long>(n_weights), ov ? "overlap" : "speaker", n_classes, rd.pos);
+        delete net;
+        return MMLA_EINVAL;
+    }
+    while (stage.size() % 4) stage.push_back(0.f);
+    cudaError_t e = cudaMalloc(&net->dev, stage.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(net->dev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        mmla_set_error("net_create: device upload failed: %s", cudaGetErrorString(e));
+        if (net->dev) cudaFree(net->dev);
+        delete net;
+        return MMLA_ECUDA;
+    }
+    for (const Fix& f : fixes) *f.dst = net->dev + f.off;
+
+    // workspace plan (floats per clip): three rotating activation buffers + LSTM scratch
+    const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
+    const long long T = net->seq_len;
+    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 3 * 256;
+    net->micro = ov ? 32 : 4096;
+    *out_net = net;
+    return MMLA_OK;
+}
+
+EXPORT void mmla_net_destroy(MmlaNet* net) {
+    if (!net) return;
+    if (net->dev) cudaFree(net->dev);
+    delete net;
+}
+
+EXPORT int64_t mmla_net_workspace_bytes(const MmlaNet* net, int64_t batch) {
+    if (!net || batch < 0) return -1;
+    const long long mb = batch < net->micro ? batch : net->micro;
+    return (mb < 1 ? 1 : mb) * net->per_clip_floats * static_cast<long long>(sizeof(float)) + 256;
+}
+
+EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch, void* workspace,
+                            int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
+    MMLA_REQUIRE(net && x && prob && workspace, MMLA_EINVAL, "net_forward: null argument");
+    MMLA_REQUIRE(batch >= 0, MMLA_EINVAL, "net_forward: negative batch");
+    MMLA_REQUIRE(!x_is_u8 || net->kind == MMLA_NET_OVERLAP, MMLA_EINVAL, "net_forward: uint8 input is for the overlap net");
+    MMLA_REQUIRE(workspace_bytes >= mmla_net_workspace_bytes(net, batch), MMLA_EINVAL,
+                 "net_forward: workspace too small (%lld < %lld bytes)", static_cast<long long>(workspace_bytes),
+                 static_cast<long long>(mmla_net_workspace_bytes(net, batch)));
+    MMLA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, MMLA_EINVAL, "net_forward: workspace must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool ov = net->kind == MMLA_NET_OVERLAP;
+    const long long in_elems = static_cast<long long>(net->in_h) * net->in_w * net->in_c;
+    const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
+    const int T = net->seq_len;
+
+    for (long long b0 = 0; b0 < batch; b0 += net->micro) {
+        const long long B = (batch - b0 < net->micro) ? batch - b0 : net->micro;
+        float* ws = static_cast<float*>(workspace);
+        float* buf[3] = {ws, ws + B * act, ws + 2 * B * act};
+        float* seq = ws + 3 * B * act;                    // [B,T,128]
+        float* xp[2] = {seq + B * T * 128, seq + B * T * 128 + B * T * 1024};   // [B,T,1024] per direction
+        float* z = xp[1] + B * T * 1024;                  // [B,1024] gate pre-activations
+        float* hdir[2] = {z + B * 1024, z + B * 1024 + B * 256};   // final h of the fwd / bwd layer
+        float* cst = hdir[1] + B * 256;                   // [B,256] cell state
+
+        const void* xin = x_is_u8 ? static_cast<const void*>(static_cast<const unsigned char*>(x) + b0 * in_elems)
+                                  : static_cast<const void*>(static_cast<const float*>(x) + b0 * in_elems);
+        int H = net->in_h, W = net->in_w;
+        int cur = 0;
+        int rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st);
+        if (rc) return rc;
+        const int act_kind = ov ? ACT_ELU : ACT_RELU;
+        for (const BlockW& blk : net->blocks) {
+            float* X = buf[cur];
+            float* A = buf[(cur + 1) % 3];
+            float* Bf = buf[(cur + 2) % 3];
+            if (!blk.pool) {
+                // out = conv2(act(bn2(conv1(act(bn1(x)))))) + x
+                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st))) return rc;
+                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, X, blk.conv2.cout, Bf, st))) return rc;
+                cur = (cur + 2) % 3;
+            } else if (ov) {
+                // full-resolution convs, MaxPool2x2 'same', then shortcut conv (stride 2) + pooled
+                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st))) return rc;
+                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st))) return rc;
+                const int Ho = same_out(H, 2), Wo = same_out(W, 2), C = blk.conv2.cout;
+                maxpool_kernel<<<ew_grid(B * Ho * Wo * C), 256, 0, st>>>(Bf, A, B, H, W, C, 2, 2, Ho, Wo);
+                MMLA_CUDA_CHECK(cudaGetLastError());
+                if ((rc = launch_conv(blk.shortcut, X, 0, B, H, W, nullptr, ACT_NONE, A, C, Bf, st))) return rc;
+                H = Ho; W = Wo;
+                cur = (cur + 2) % 3;
+            } else {
+                // speaker: x' = MaxPool1D(x); res = conv_k1_s2(x); out = conv2(..conv1(..x'..)) + res
+                const int Wo = same_out(W, 2), Cin = blk.conv1.cin;
+                maxpool_kernel<<<ew_grid(B * Wo * Cin), 256, 0, st>>>(X, A, B, 1, W, Cin, 1, 2, 1, Wo);
+                MMLA_CUDA_CHECK(cudaGetLastError());
+                if ((rc = launch_conv(blk.conv1, A, 0, B, 1, Wo, &blk.bn1, act_kind, nullptr, 0, Bf, st))) return rc;
+                if ((rc = launch_conv(blk.shortcut, X, 0, B, 1, W, nullptr, ACT_NONE, nullptr, 0, A, st))) return rc;
+                // conv2 reads Bf, adds A (shortcut), writes X's buffer (X is dead now)
+                if ((rc = launch_conv(blk.conv2, Bf, 0, B, 1, Wo, &blk.bn2, act_kind, A, blk.conv2.cout, X, st))) return rc;
+                W = Wo;
+            }
+        }
+        // sequence features [B,T,128]
+        if (ov) {
+            mean_h_kernel<<<ew_grid(B * W * 128), 256, 0, st>>>(buf[cur], seq, B, H, W, 128);
+        } else {
+            bn_relu_avgpool4_kernel<<<ew_grid(B * (W / 4) * 128), 256, 0, st>>>(buf[cur], seq, net->final_bn.scale,
+                                                                               net->final_bn.shift, B, W, 128);
+        }
+        MMLA_CUDA_CHECK(cudaGetLastError());
+        // BiLSTM(256): input projections for all steps, then the recurrence
+        for (int d = 0; d < 2; ++d)
+            if ((rc = launch_conv(net->lstm_in[d], seq, 0, B * T, 1, 1, nullptr, ACT_NONE, nullptr, 0, xp[d], st))) return rc;
+        for (int d = 0; d < 2; ++d) {
+            float* h = hdir[d];                            // updated in place: the recurrent GEMM of a
+            for (int s = 0; s < T; ++s) {                  // step finishes before its gate kernel writes h
+                const int t = d == 0 ? s : T - 1 - s;     // backward layer walks t = T-1 .. 0
+                const float* xpt = xp[d] + static_cast<long long>(t) * 1024;
+                if (s == 0) {                              // h0 = 0: pre-activations are xp[:, t, :]
+                    lstm_gates_kernel<<<ew_grid(B * 256), 256, 0, st>>>(xpt, static_cast<long long>(T) * 1024, cst, h, B, 256, 1);
+                } else {
+                    if ((rc = launch_conv(net->lstm_rec[d], h, 0, B, 1, 1, nullptr, ACT_NONE, xpt,
+                                          static_cast<long long>(T) * 1024, z, st)))
+                        return rc;
+                    lstm_gates_kernel<<<ew_grid(B * 256), 256, 0, st>>>(z, 1024, cst, h, B, 256, 0);
+                }
+                MMLA_CUDA_CHECK(cudaGetLastError());
+            }
+        }
+        const int warps = 8;
+        long long hgrid = (B + warps - 1) / warps;
+        if (hgrid > 8LL * mmla_num_sms()) hgrid = 8LL * mmla_num_sms();
+        head_kernel<<<static_cast<unsigned>(hgrid), warps * 32, warps * 512 * sizeof(float), st>>>(
+            hdir[0], hdir[1], net->dense_k, net->dense_b, 0.3f, ov ? 1 : 0, net->n_classes, net->head == MMLA_HEAD_SIGMOID, B,
+            prob + b0 * net->n_classes, labels ? labels + b0 : nullptr);
+        MMLA_CUDA_CHECK(cudaGetLastError());
+    }
+    return MMLA_OK;
+}

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) overlap_features_kernel(const __g
                 __syncthreads();                                     // buffer may be restaged
             }
             // |X|^2 tile S[f][k], overlaid on Ae (all reads of Ae/Ao are behind the barrier above)
-            float* S = &s.Ae[0][0];                                  // [kTileF][kBinsPad] = 6656 <= 201*32
+            float* S = &s.Ae[0][0];                                  // [kTileF][kBinsPad]: spans Ae and the head of Ao (both dead)
             if (active) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -350,9 +350,9 @@ int build_tables(int n_mels, OverlapTables& t) {
         }
     for (int n = 0; n < kNfft; ++n) t.window[n] = static_cast<float>(0.5 - 0.5 * cos(2.0 * PI * n / kNfft));
     // librosa.filters.mel(sr=16000, n_fft=400, n_mels, fmin=0, fmax=8000, htk=False, norm='slaney')
-    const double sr = 16000.0, fmax = sr / 2;
+    const double sr = 16000.0, f_hi = sr / 2;
     std::vector<double> mel_f(n_mels + 2);
-    const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(fmax);
+    const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(f_hi);
     for (int i = 0; i < n_mels + 2; ++i) {
         const double m = (i == n_mels + 1) ? m_hi : m_lo + i * ((m_hi - m_lo) / (n_mels + 1));
         mel_f[i] = mel_to_hz(m);

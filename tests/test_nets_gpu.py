@@ -1,0 +1,91 @@
+"""GPU parity: classifier forward passes (C-ABI mmla_net_*) vs the torch-CPU fp32 oracle, on
+seeded synthetic weights with the reference's exact tensor names and shapes.
+
+Tolerance: both sides are fp32 with different summation orders; probabilities must agree to
+2e-4 absolute and arg-max labels must be identical wherever the oracle's top-2 margin exceeds
+1e-3 (closer calls are reported, and overall agreement must be >= 99 %; BASELINE target >= 90 %).
+"""
+import numpy as np
+import pytest
+
+from oracle import librosa_mel as lm, nets as onets, psf, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _labels_agree(prob_gpu, prob_ref, min_agree=0.99):
+    lg, lr = prob_gpu.argmax(1), prob_ref.argmax(1)
+    srt = np.sort(prob_ref, axis=1)
+    margin = srt[:, -1] - srt[:, -2]
+    clear = margin > 1e-3
+    assert (lg[clear] == lr[clear]).all(), "label mismatch on a clear-margin clip"
+    assert (lg == lr).mean() >= min_agree
+
+
+def test_speaker_net_matches_oracle(cuda, tmp_path):
+    from mmla_audio_b200 import models, weights as W
+    spec = W.speaker_spec(10, "sigmoid")                  # 10 registered speakers, transfer head
+    w = models.save_synthetic_model(str(tmp_path / "model"), spec, seed=4321)
+    model = models.load_model(str(tmp_path / "model"))
+    assert model.spec.n_classes == 10 and model.spec.head_activation == "sigmoid"
+    pcm = synth.synth_clips(0, 48, 24000)
+    x = np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(48)]).astype(np.float32)
+    got = model.predict(x)
+    ref = onets.speaker_forward(x, w, spec)
+    assert got.shape == ref.shape == (48, 10) and got.dtype == np.float32
+    np.testing.assert_allclose(got, ref, atol=2e-4, rtol=0)
+    _labels_agree(got, ref)
+
+
+def test_speaker_base_630_softmax(cuda):
+    from mmla_audio_b200 import models, weights as W
+    spec = W.SPEAKER_BASE
+    w = W.synthetic_weights(spec, 99)
+    model = models.Model(spec, w)
+    pcm = synth.synth_clips(300, 8, 40960)
+    x = np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(8)]).astype(np.float32)
+    got = model.predict(x)
+    ref = onets.speaker_forward(x, w, spec)
+    np.testing.assert_allclose(got, ref, atol=2e-5, rtol=1e-3)
+    np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-5)
+    _labels_agree(got, ref)
+
+
+def test_overlap_net_matches_oracle(cuda, tmp_path):
+    from mmla_audio_b200 import models, weights as W
+    spec = W.OVERLAP
+    w = models.save_synthetic_model(str(tmp_path / "timit2.0"), spec, seed=1234)
+    model = models.load_model(str(tmp_path / "timit2.0"))
+    assert model.spec.ndim == 2 and model.spec.n_classes == 2
+    pcm = synth.synth_clips(40, 12, 24000)
+    x = np.stack([lm.classifier_input(pcm[i]) for i in range(12)])       # float32 0..255
+    ref = onets.overlap_forward(x, w, spec)
+    got_f32 = model.predict(x)
+    got_u8 = model.predict(x.astype(np.uint8))                            # decode_png dtype
+    np.testing.assert_array_equal(got_f32, got_u8)
+    np.testing.assert_allclose(got_f32, ref, atol=2e-4, rtol=0)
+    _labels_agree(got_f32, ref)
+
+
+def test_micro_batching_consistent(cuda):
+    """A batch larger than the executor's micro-batch equals the same clips run separately."""
+    from mmla_audio_b200 import models, weights as W
+    torch = cuda
+    spec = W.OVERLAP
+    model = models.Model(spec, W.synthetic_weights(spec, 7))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randint(0, 256, (40, 128, 151, 3), dtype=torch.uint8, device="cuda", generator=g)
+    p_all, l_all = model.predict_device(x)
+    p_a, l_a = model.predict_device(x[:7].contiguous())
+    p_b, l_b = model.predict_device(x[33:].contiguous())
+    assert torch.equal(p_all[:7], p_a) and torch.equal(p_all[33:], p_b)
+    assert torch.equal(l_all[:7], l_a) and torch.equal(l_all[33:], l_b)
+
+
+def test_bad_weight_blob_fails_loudly(cuda):
+    from mmla_audio_b200 import models, weights as W, _lib
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 1)
+    w.pop(next(iter(w)))
+    with pytest.raises(KeyError):
+        models.Model(spec, w)
