@@ -647,7 +647,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
 
     void* dev_tmp = nullptr;
     if (clip_off_host == nullptr) {
-        MMLA_REQUIRE(clip_len >= 0 && clip_stride >= clip_len, MMLA_EINVAL, "mfcc: bad uniform clip geometry");
+        MMLA_REQUIRE(clip_len >= 0 && clip_stride >= 0, MMLA_EINVAL, "mfcc: bad uniform clip geometry");   // stride < len = overlapping windows
         MMLA_REQUIRE((n_clips - 1) * clip_stride + clip_len <= pcm_total, MMLA_EINVAL, "mfcc: clips exceed pcm_total_samples");
         const int T = mmla_psf_num_frames(clip_len, &p);
         const int n_real = p.pad_frames > 0 ? (T < p.pad_frames ? T : p.pad_frames) : T;

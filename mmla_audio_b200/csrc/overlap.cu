@@ -466,7 +466,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_overlap_features(
         kp.clip_off = reinterpret_cast<const long long*>(base);
         kp.clip_len_arr = reinterpret_cast<const int*>(base + b_off);
     } else {
-        MMLA_REQUIRE(clip_len >= 0 && clip_stride >= clip_len, MMLA_EINVAL, "overlap: bad uniform clip geometry");
+        MMLA_REQUIRE(clip_len >= 0 && clip_stride >= 0, MMLA_EINVAL, "overlap: bad uniform clip geometry");   // stride < len = overlapping windows
         MMLA_REQUIRE((n_clips - 1) * clip_stride + clip_len <= pcm_total, MMLA_EINVAL, "overlap: clips exceed pcm_total_samples");
     }
     const int sms = mmla_num_sms();

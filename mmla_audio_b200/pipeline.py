@@ -1,0 +1,102 @@
+"""End-to-end hot path, batched: PCM → features → classifier → arg-max labels → tallies.
+
+These are the loops of the reference's entry scripts with the microphone / WAV / PNG plumbing
+removed (BASELINE.json north_star: "audio fed from synthetic buffers instead of PyAudio"):
+  * ``SpeakerPipeline``  — SpeakerIdentification/scripts/record_on_pc.py:97-151 (per clip) and
+    speaker_identification_post_processing.py:253-312 (whole session)
+  * ``OverlapPipeline``  — OverlapDetection/scripts/record_on_pc.py:114-173 (per clip) and
+    overlap_detection_post_processing.py:189-226 (whole session)
+"""
+from __future__ import annotations
+
+from datetime import datetime
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib, tally
+from .models import Model
+from .overlap_features_generator import OverlapFeaturesGenerator
+from .params import (MfccConfig, OVERLAP_CLIP_SAMPLES, SILENT_MIN_SAMPLES, SPEAKER_FRAMES)
+from .speaker_identification import speaker_features_batch, whole_file_chunks, _to_device_pcm
+
+
+def segmentation_windows(n_samples: int, win: int, step: int) -> int:
+    """``cut_num = int((nframes - win)/step + 1)`` (overlap_detection_post_processing.py:55-59)."""
+    return int(((n_samples - win) / step) + 1)
+
+
+def window_view(pcm_1d, win: int, step: int):
+    """Zero-copy [cut_num, win] strided view of a long recording (window j = [j*step, j*step+win))."""
+    n = segmentation_windows(pcm_1d.numel(), win, step)
+    return pcm_1d.as_strided((max(n, 0), win), (step, 1))
+
+
+class SpeakerPipeline:
+    def __init__(self, model: Model, cfg: MfccConfig = MfccConfig()):
+        if model.spec.ndim != 1:
+            raise ValueError("SpeakerPipeline needs the speaker net")
+        self.model = model
+        self.cfg = cfg
+        self._feat = None
+
+    def run_device(self, pcm_dev):
+        """pcm_dev: int16 CUDA [B, L] (L >= 4000).  → (labels int32 [B], prob [B,n])."""
+        torch = _lib.require_cuda()
+        B = pcm_dev.shape[0]
+        if pcm_dev.shape[1] < SILENT_MIN_SAMPLES:          # every clip is 'silent'
+            return (torch.full((B,), tally.SILENT, dtype=torch.int32, device=pcm_dev.device), None)
+        if self._feat is None or self._feat.shape[0] != B or self._feat.device != pcm_dev.device:
+            self._feat = torch.empty((B, SPEAKER_FRAMES, 3 * self.cfg.numcep), dtype=torch.float32,
+                                     device=pcm_dev.device)
+        speaker_features_batch(pcm_dev, self.cfg, out=self._feat)
+        prob, labels = self.model.predict_device(self._feat)
+        return labels, prob
+
+    def run_session(self, pcm_long, speaker_names: Dict[int, str], t0: Optional[datetime] = None,
+                    silent_index=()):
+        """Offline session: MFCC-39 over the whole recording, 256-frame chunks, one predict,
+        rows every 2.56 s (speaker_identification_post_processing.py:253-312)."""
+        torch = _lib.require_cuda()
+        chunks = whole_file_chunks(pcm_long, self.cfg)
+        prob, labels = self.model.predict_device(chunks)
+        if len(silent_index):
+            idx = torch.as_tensor(list(silent_index), dtype=torch.long, device=labels.device)
+            labels[idx] = tally.SILENT
+        t0 = t0 or datetime.today()
+        return labels, tally.tally_session(labels, speaker_names, t0, 2.56, add_before_first=True)
+
+
+class OverlapPipeline:
+    def __init__(self, model: Model):
+        if model.spec.ndim != 2:
+            raise ValueError("OverlapPipeline needs the overlap net")
+        self.model = model
+        self.ofg = OverlapFeaturesGenerator(wl=25, hl=10)
+
+    def run_device(self, pcm_dev):
+        """pcm_dev: int16 CUDA [B, L].  → (labels int32 [B], prob [B,2]); label -1 = 'silent'
+        when L < 4000 (record_on_pc.py:141-154)."""
+        torch = _lib.require_cuda()
+        B = pcm_dev.shape[0]
+        if pcm_dev.shape[1] < SILENT_MIN_SAMPLES:
+            return (torch.full((B,), tally.SILENT, dtype=torch.int32, device=pcm_dev.device), None)
+        img = self.ofg.classifier_input_batch(pcm_dev)
+        prob, labels = self.model.predict_device(img)
+        return labels, prob
+
+    def run_session(self, pcm_long, t0: Optional[datetime] = None, win_s: float = 1.5, step_s: float = 1.5,
+                    sr: int = 16000, chunk: int = 4096):
+        """Offline session: cut 1.5 s windows (zero-copy), features + predict per window, rows every
+        1.5 s (overlap_detection_post_processing.py:189-226)."""
+        torch = _lib.require_cuda()
+        x = _to_device_pcm(torch, pcm_long).reshape(-1)
+        wins = window_view(x, int(sr * win_s), int(sr * step_s))
+        labels = torch.empty((wins.shape[0],), dtype=torch.int32, device=x.device)
+        for i in range(0, wins.shape[0], chunk):
+            l, _ = self.run_device(wins[i:i + chunk])
+            labels[i:i + chunk] = l
+        t0 = t0 or datetime.today()
+        names = {int(k): v for k, v in tally.OVERLAP_DEGREE_DICT.items()}
+        return labels, tally.tally_session(labels, names, t0, win_s, add_before_first=False,
+                                           initial_order=list(tally.OVERLAP_DEGREE_DICT.values()))

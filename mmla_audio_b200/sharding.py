@@ -1,0 +1,40 @@
+"""Clip sharding across the GPUs of one box (one process per GPU) and the single exchange step
+of the path: gather per-clip labels, sum tallies.  No collective touches the
+data path — clips are independent — so scaling is weak and communication is a few KB..MB.
+
+Works with any initialised ``torch.distributed`` backend: NCCL on GPUs (the product), gloo on
+CPU ranks (the unit tests of this host logic).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rank r of R owns [floor(r*N/R), floor((r+1)*N/R))."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    return (n_items * rank) // world, (n_items * (rank + 1)) // world
+
+
+def gather_labels(labels_local, n_total: int, rank: int, world: int):
+    """all_gather of int32 labels sharded with shard_range → full [n_total] tensor on every rank."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return labels_local
+    sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    pad = torch.full((mx,), -2, dtype=torch.int32, device=labels_local.device)
+    pad[: labels_local.numel()] = labels_local.to(torch.int32)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)])
+
+
+def allreduce_counts(counts, world: int):
+    """all_reduce(SUM) of the int64 tally vector."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts
