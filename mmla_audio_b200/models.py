@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib
 from . import tf_bundle
 from .weights import (NetSpec, OVERLAP, SPEAKER_BASE, speaker_spec, weight_shapes, check_weights,
-                      synthetic_weights, dense_keys, lw)
+                      synthetic_weights, dense_keys, lw, resolve_lstm_keys)
 
 KIND_OVERLAP, KIND_SPEAKER = 0, 1
 HEAD_IDS = {"softmax": 0, "sigmoid": 1}
@@ -156,6 +156,7 @@ def load_model(model_dir: str, kind: Optional[str] = None, n_classes: Optional[i
         else:
             n = shapes[lw(42, "kernel")][1] if n_classes is None else n_classes
             spec = speaker_spec(n, head or "softmax")
+    spec = resolve_lstm_keys(spec, shapes)
     return Model(spec, _read_model_weights(model_dir, spec))
 
 

@@ -104,6 +104,31 @@ def speaker_spec(n_classes: int = 630, head: str = "softmax") -> NetSpec:
     return _speaker_spec(n_classes, head)
 
 
+def resolve_lstm_keys(spec: NetSpec, index_shapes: Dict[str, Tuple[int, ...]]) -> NetSpec:
+    """The Bidirectional layer's six tensors are stored under checkpoint-dependent names
+    (``variables/116..121`` in timit2.0, ``trainable_variables/80..85`` in timit1.0,
+    ``trainable_variables/82..87`` in the speaker model).  Find them by shape: the first run of
+    six consecutively numbered entries shaped [feat,1024],[256,1024],[1024] twice."""
+    import re
+    from dataclasses import replace
+    if all(k in index_shapes for k in spec.lstm_keys):
+        return spec
+    feat = spec.blocks[-1].conv2.cout
+    want = [(feat, 1024), (256, 1024), (1024,)] * 2
+    groups: Dict[str, Dict[int, str]] = {}
+    for k in index_shapes:
+        m = re.match(r"^(trainable_variables|variables)/(\d+)/\.ATTRIBUTES/VARIABLE_VALUE$", k)
+        if m:
+            groups.setdefault(m.group(1), {})[int(m.group(2))] = k
+    for prefix in ("variables", "trainable_variables"):
+        nums = groups.get(prefix, {})
+        for n0 in sorted(nums):
+            keys = [nums.get(n0 + i) for i in range(6)]
+            if all(keys) and [tuple(index_shapes[k]) for k in keys] == want:
+                return replace(spec, lstm_keys=tuple(keys))
+    raise KeyError(f"{spec.name}: no Bidirectional(LSTM(256)) tensors found in the checkpoint index")
+
+
 def dense_keys(spec: NetSpec) -> Tuple[str, str]:
     if spec.dense_key_prefix:
         return (f"{spec.dense_key_prefix}/kernel{_SUFFIX}", f"{spec.dense_key_prefix}/bias{_SUFFIX}")
