@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the mmla-audio hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload speaker_id|bulk_mfcc|overlap]
+
+Metric (BASELINE.json): audio-seconds per second, MFCC + classifier, whole job over N GPUs.
+Default workload = BASELINE.json configs[1]: speaker identification, 1.5 s windows, 4096
+synthetic clips per GPU, 10 registered speakers.  One step = one pass of the hot path over the
+rank's clips: fused MFCC-39 features -> speaker classifier forward -> arg-max labels -> label
+tally (+ label all_gather / tally all_reduce when N > 1).  Clips are sharded across ranks with
+no data-path collective (weak scaling).
+
+Printed JSON line (rank 0): the driver contract plus `roofline`, `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches`, and an `extra` object with per-stage timings and the bulk MFCC-only number
+(configs[2] shape: 2.5 s clips, nfilt 40) on the same GPU.
+
+`--impl reference` times the reference-equivalent CPU path (oracle/ port: numpy float64
+python_speech_features restatement + torch-CPU classifier — the upstream libraries cannot be
+installed here) on the host cores over a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+WORKLOADS = {
+    "speaker_id": dict(name="speaker_id_1.5s_x4096_10spk", clips=4096, clip_len=24000, nfilt=26),
+    "bulk_mfcc": dict(name="bulk_mfcc13_2.5s_nfilt40", clips=65536, clip_len=40000, nfilt=40),
+    "overlap": dict(name="overlap_1.5s_x512", clips=512, clip_len=24000, nfilt=0),
+}
+SPEAKER_FLOP_PER_CLIP = 46.9e6
+OVERLAP_FLOP_PER_CLIP = 1.838e9
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt, self.active = threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            if self.active:
+                try:
+                    self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference-equivalent path (oracle port) — cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------
+def _cpu_features_speaker(args):
+    first, n, clip_len = args
+    from oracle import psf, synth
+    pcm = synth.synth_clips(first, n, clip_len)
+    return np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(n)]).astype(np.float32)
+
+
+def cpu_step(workload: str, first_clip: int, n_clips: int, clip_len: int, state: dict, pool=None):
+    """One bounded CPU pass of the same hot path on `n_clips` synthetic clips."""
+    from oracle import librosa_mel as lm, nets as onets, psf, synth
+    if workload == "speaker_id":
+        if pool is not None:
+            per = max(1, n_clips // pool._processes)
+            jobs = [(first_clip + i, min(per, n_clips - i), clip_len) for i in range(0, n_clips, per)]
+            x = np.concatenate(pool.map(_cpu_features_speaker, jobs))
+        else:
+            x = _cpu_features_speaker((first_clip, n_clips, clip_len))
+        prob = onets.speaker_forward(x, state["w"], state["spec"])
+        labels = np.argmax(prob, axis=1)
+    elif workload == "bulk_mfcc":
+        pcm = synth.synth_clips(first_clip, n_clips, clip_len)
+        for i in range(n_clips):
+            psf.mfcc(pcm[i], SR, winlen=0.025, winstep=0.01, nfft=512, nfilt=40)
+        labels = np.zeros(n_clips, np.int64)
+    else:
+        pcm = synth.synth_clips(first_clip, n_clips, clip_len)
+        x = np.stack([lm.classifier_input(pcm[i]) for i in range(n_clips)])
+        prob = onets.overlap_forward(x, state["w"], state["spec"])
+        labels = np.argmax(prob, axis=1)
+    return np.bincount(labels, minlength=2)
+
+
+def cpu_state(workload: str):
+    from mmla_audio_b200 import weights as W
+    if workload == "speaker_id":
+        spec = W.speaker_spec(10, "sigmoid")
+        return {"spec": spec, "w": W.synthetic_weights(spec, 4321)}
+    if workload == "overlap":
+        return {"spec": W.OVERLAP, "w": W.synthetic_weights(W.OVERLAP, 1234)}
+    return {}
+
+
+def time_cpu(workload: str, clip_len: int, sample_clips: int, steps: int, warmup: int, all_cores: bool):
+    import torch
+    state = cpu_state(workload)
+    pool = None
+    cores = torch.get_num_threads()
+    if all_cores and workload == "speaker_id":
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        pool = mp.get_context("spawn").Pool(min(cores, 32))
+        pool.map(_cpu_features_speaker, [(0, 1, clip_len)] * pool._processes)   # import warm-up
+    for i in range(warmup):
+        cpu_step(workload, i * sample_clips, sample_clips, clip_len, state, pool)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        cpu_step(workload, (warmup + i) * sample_clips, sample_clips, clip_len, state, pool)
+    dt = (time.perf_counter() - t0) / steps
+    if pool is not None:
+        pool.close()
+    return sample_clips * clip_len / SR / dt, dt, cores
+
+
+def run_reference_arm(a, wl):
+    """`--impl reference`: the reference-equivalent CPU path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = {"speaker_id": 128, "bulk_mfcc": 256, "overlap": 8}[a.workload]
+    steps, warmup = max(1, min(a.steps, 5)), max(1, min(a.warmup, 1))
+    value, dt, cores = time_cpu(a.workload, wl["clip_len"], sample, steps, warmup, all_cores=True)
+    desc = f"{sample} synthetic clips of {wl['clip_len'] / SR:.2f} s per step (oracle port, numpy float64 + torch-CPU fp32)"
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "clips_per_step": sample, "clip_seconds": wl["clip_len"] / SR,
+                   "note": "CPU baseline does not scale with --gpus; rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="speaker_id", choices=sorted(WORKLOADS))
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    a = ap.parse_args()
+    wl = dict(WORKLOADS[a.workload])
+    if a.clips:
+        wl["clips"] = a.clips
+    if a.impl == "reference":
+        run_reference_arm(a, wl)
+        return
+    if a.warmup < 3:
+        a.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from mmla_audio_b200 import _lib, models, synth, tally, weights as W
+    from mmla_audio_b200 import speaker_identification as si
+    from mmla_audio_b200.pipeline import OverlapPipeline, SpeakerPipeline
+    from mmla_audio_b200.sharding import allreduce_counts, gather_labels, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for --impl ours")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    B, L = wl["clips"], wl["clip_len"]
+    n_total = B * world
+    lo, hi = shard_range(n_total, rank, world)
+    pcm = synth.synth_clips(lo, hi - lo, L)                       # this rank's shard, resident in HBM
+    pcm_host = torch.empty((B, L), dtype=torch.int16).pin_memory()
+    pcm_host.copy_(pcm.cpu())
+    pcm_dev2 = torch.empty_like(pcm)                              # e2e staging target
+
+    if a.workload == "speaker_id":
+        spec = W.speaker_spec(10, "sigmoid")
+        pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321)))
+        n_classes = 10
+    elif a.workload == "overlap":
+        pipe = OverlapPipeline(models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234)))
+        n_classes = 2
+    else:
+        pipe, n_classes = None, 1
+        cfg40 = si.MfccConfig(nfilt=40)
+        out_bulk = torch.empty((B, cfg40.num_frames(L), 13), dtype=torch.float32, device="cuda")
+
+    def step(x):
+        if pipe is None:
+            si.mfcc_batch(x, cfg40, out=out_bulk)
+            return None, None
+        labels, _ = pipe.run_device(x)
+        counts = tally.device_counts(labels, n_classes)
+        if world > 1:
+            labels = gather_labels(labels, n_total, rank, world)
+            counts = allreduce_counts(counts, world)
+        return labels, counts
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    for _ in range(a.warmup):
+        step(pcm)
+    launches0 = lib.mmla_launch_count()
+    sampler.active = True
+    ms_step = timed(lambda: step(pcm), a.steps)
+    sampler.active = False
+    gpu_launches = int(lib.mmla_launch_count() - launches0)
+    audio_s = n_total * L / SR
+    value = audio_s / (ms_step / 1e3)
+
+    # ---- e2e: host buffers in, labels + tallies out, copies inside the timed region -----------
+    def e2e_step():
+        pcm_dev2.copy_(pcm_host, non_blocking=True)
+        labels, counts = step(pcm_dev2)
+        if labels is None:
+            return out_bulk[:, 0, 0].sum().item()
+        return labels.cpu(), counts.cpu()
+    for _ in range(3):
+        e2e_step()
+    sampler.active = True
+    ms_e2e = timed(e2e_step, max(3, a.steps // 2))
+    sampler.active = False
+    h2d = B * L * 2
+    d2h = (n_total * 4 + (n_classes + 1) * 8) if pipe is not None else 4
+
+    # ---- per-stage timing + roofline of the dominant kernel -----------------------------------
+    extra = {}
+    if a.workload == "speaker_id":
+        feat = torch.empty((B, 256, 39), dtype=torch.float32, device="cuda")
+        ms_feat = timed(lambda: si.speaker_features_batch(pcm, out=feat), a.steps)
+        l0 = lib.mmla_launch_count()
+        ms_cls = timed(lambda: pipe.model.predict_device(feat), a.steps)
+        cls_launches = int((lib.mmla_launch_count() - l0) // (a.steps))
+        feat_bytes = B * (L * 2 + 256 * 39 * 4)
+        feat_gbs = feat_bytes / (ms_feat * 1e-3) / 1e9
+        cls_tflops = B * SPEAKER_FLOP_PER_CLIP / (ms_cls * 1e-3) / 1e12
+        extra["stages_ms"] = {"mfcc39_fused_kernel": ms_feat, "speaker_classifier_%d_launches" % cls_launches: ms_cls}
+        extra["mfcc39_roofline"] = {"bound": "hbm", "achieved": feat_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": feat_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": feat_bytes}
+        if ms_cls >= ms_feat:
+            roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (speaker classifier, fp32 CUDA-core path)",
+                        "achieved": cls_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": cls_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "peak_source": peaks["source"] + " cuBLAS bf16 sustained"}
+        else:
+            roofline = dict(extra["mfcc39_roofline"], kernel="mfcc_fused_kernel", traffic=None,
+                            peak_source=peaks["source"] + " HBM copy")
+    elif a.workload == "overlap":
+        img = pipe.ofg.classifier_input_batch(pcm)
+        ms_feat = timed(lambda: pipe.ofg.classifier_input_batch(pcm), a.steps)
+        ms_cls = timed(lambda: pipe.model.predict_device(img), a.steps)
+        cls_tflops = B * OVERLAP_FLOP_PER_CLIP / (ms_cls * 1e-3) / 1e12
+        extra["stages_ms"] = {"overlap_features_kernel": ms_feat, "overlap_classifier": ms_cls}
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (overlap classifier, fp32 CUDA-core path)",
+                    "achieved": cls_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": cls_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "peak_source": peaks["source"] + " cuBLAS bf16 sustained"}
+    else:
+        nbytes = B * (L * 2 + out_bulk.shape[1] * 13 * 4)
+        gbs = nbytes / (ms_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "mfcc_fused_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": nbytes,
+                    "peak_source": peaks["source"] + " HBM copy"}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            roofline["traffic"] = json.load(open(traffic_path)).get(a.workload, {}).get(roofline.get("kernel", "").split(" ")[0])
+        except Exception:
+            pass
+
+    # ---- bulk MFCC-only (configs[2] shape) on the same GPU, reported as extra -------------------
+    if a.workload == "speaker_id" and not a.no_extra:
+        Bb, Lb = 32768, 40000
+        cfgb = si.MfccConfig(nfilt=40)
+        del pcm_dev2
+        pb = synth.synth_clips(10_000_000 + lo, Bb, Lb)
+        ob = torch.empty((Bb, cfgb.num_frames(Lb), 13), dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            si.mfcc_batch(pb, cfgb, out=ob)
+        ms_b = timed(lambda: si.mfcc_batch(pb, cfgb, out=ob), max(5, a.steps // 3))
+        nb = Bb * (Lb * 2 + ob.shape[1] * 13 * 4)
+        extra["bulk_mfcc13_nfilt40_2.5s"] = {
+            "clips_per_gpu": Bb, "ms": ms_b, "audio_s_per_s": world * Bb * Lb / SR / (ms_b * 1e-3),
+            "hbm_gbs": nb / (ms_b * 1e-3) / 1e9, "frac_of_hbm_peak": nb / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        del pb, ob
+    sampler.stop()
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) -----------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        sample = {"speaker_id": 96, "bulk_mfcc": 192, "overlap": 6}[a.workload]
+        v, dt, cores = time_cpu(a.workload, L, sample, steps=2, warmup=1, all_cores=False)
+        cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                        "sample": f"{sample} clips x 2 steps of the same workload through oracle/ "
+                                  f"(numpy float64 psf/librosa restatement + torch-CPU fp32 classifier, "
+                                  f"torch threads={cores}); upstream libs not installable here"}
+
+    if rank == 0:
+        line = {
+            "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "clips_per_gpu": B, "clip_seconds": L / SR, "global_clips": n_total,
+                       "sharding": f"clips x{world}, no data-path collective; labels all_gather + tally all_reduce",
+                       "l2": "inputs larger than L2 (%.0f MB int16 PCM per GPU per step)" % (B * L * 2 / 1e6),
+                       "weights": "seeded synthetic, reference shapes (real .data shards stripped from the mount)"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": audio_s / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": gpu_launches, "clocks": sampler.summary(), "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

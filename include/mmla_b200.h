@@ -41,6 +41,8 @@ extern "C" {
 const char* mmla_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
 int mmla_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+int64_t mmla_launch_count(void);
 /* CRC-32C (Castagnoli) of a HOST buffer, as stored in TF tensor-bundle entries. Host only. */
 uint32_t mmla_crc32c_host(const void* data_host, size_t n);
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libmmla_b200.so")
 
 # every symbol include/mmla_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = (
-    "mmla_last_error", "mmla_abi_version", "mmla_crc32c_host",
+    "mmla_last_error", "mmla_abi_version", "mmla_launch_count", "mmla_crc32c_host",
     "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_delta", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_workspace_bytes", "mmla_net_forward",
     "mmla_tally", "mmla_synth_pcm",
@@ -53,6 +53,7 @@ def load() -> C.CDLL:
     sigs = {
         "mmla_last_error": (C.c_char_p, []),
         "mmla_abi_version": (C.c_int, []),
+        "mmla_launch_count": (i64, []),
         "mmla_crc32c_host": (u32, [vp, C.c_size_t]),
         "mmla_psf_num_frames": (i32, [i64, mp]),
         "mmla_psf_mfcc": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, mp, vp, i64, vp]),

@@ -26,6 +26,7 @@ void mmla_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+void mmla_count_launch();                 // bumps the counter mmla_launch_count() reports
 int mmla_num_sms();   // SM count of the current device (cached), <0 on error
 
 // ---------------------------------------------------------------------------------------------

@@ -3,11 +3,16 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 }
+
+void mmla_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void mmla_set_error(const char* fmt, ...) {
     va_list ap;
@@ -54,4 +59,8 @@ extern "C" __attribute__((visibility("default"))) uint32_t mmla_crc32c_host(cons
     uint32_t c = 0xFFFFFFFFu;
     for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
     return c ^ 0xFFFFFFFFu;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t mmla_launch_count(void) {
+    return g_launches.load(std::memory_order_relaxed);
 }
