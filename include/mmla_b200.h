@@ -62,7 +62,7 @@ typedef struct MmlaMfccParams {
     int32_t frame_step;     /* 160  = round_half_up(winstep*samplerate) */
     int32_t nfft;           /* 512 (the warp FFT is sized for exactly 512) */
     int32_t nfilt;          /* 26 = reference; 40 = BASELINE config 3; <= 64 */
-    int32_t numcep;         /* 13; <= 16 and <= nfilt */
+    int32_t numcep;         /* 13; <= 14 and <= nfilt */
     int32_t ceplifter;      /* 22 */
     int32_t append_energy;  /* 1: c0 := ln(frame energy) */
     int32_t window;         /* MMLA_WINDOW_* */

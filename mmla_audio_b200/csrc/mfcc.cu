@@ -38,23 +38,23 @@ constexpr int kE1Stride = 72;         // complex stride of exchange-1 rows  [k0]
 constexpr int kE2Stride = 66;         // complex stride of exchange-2 rows  [n0][q]
 constexpr int kScratchC = 8 * kE1Stride;   // complex elements of FFT scratch per warp
 constexpr int kPsStride = 258;        // float stride of one frame's power spectrum
-constexpr int kLmStride = 65;         // float stride of one frame's log-mel row
 constexpr int kMaxFilt = 64;
-constexpr int kMaxCep = 16;
-constexpr int kMaxNnz = 640;
+constexpr int kMaxCep = 16;          // smem row stride of cepstra; numcep itself is limited to 14
+constexpr int kMaxNnz = 896;          // zero-padded filter halves
 constexpr int kTileOut = 256;         // output frames per tile
 constexpr int kHalo = 4;              // delta-delta context
 constexpr int kTileFrames = kTileOut + 2 * kHalo;
 constexpr int kMaxBatchSamples = 2816;     // (kBatch-1)*step + frame_len, padded
 constexpr int kPcmBufSamples = kMaxBatchSamples + 16;
+constexpr int kYpre = kPcmBufSamples;      // pre-emphasised floats, same indexing as the PCM buffer
 constexpr float kEps = 2.220446049250313e-16f;
 
 struct MfccTables {
-    int4 fmeta[kMaxFilt];             // start bin, length, weight offset, split point a
+    int4 fmeta[kMaxFilt];             // start bin, split point a, iterations per half, weight offset
     int warp_cnt[kWarps];
     unsigned char warp_list[kWarps][kMaxFilt];
-    float fbw[kMaxNnz];
-    float dct[kMaxCep][kMaxFilt];     // scale, cos and lifter folded in
+    float fbw[kMaxNnz];               // per filter: [half 0 | half 1], each `iters` long, zero padded
+    float dct[kMaxFilt][2][8];        // [filter][half][7 cepstra (+pad)]: half 0 = c0..c6, half 1 = c7..c13
     float window[kNfft];
 };
 
@@ -78,9 +78,9 @@ struct MfccKernelParams {
 struct Smem {
     float2 scratch[kWarps][kScratchC];            // FFT exchanges; reused as delta tile
     float pspec[kBatch][kPsStride];
-    float ypre[kMaxBatchSamples];
+    alignas(16) float ypre[kYpre];                // ypre[i] = y at PCM-buffer sample i
     float feat[kTileFrames * kMaxCep];            // stride = numcep
-    float logmel[kBatch][kLmStride];
+    float cpart[kWarps][kBatch][kMaxCep];         // per-warp partial cepstra of the batch
     float energy[kBatch];
     alignas(16) int16_t pcm[2][kPcmBufSamples];
     alignas(8) uint64_t full_bar[2];
@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(kThreads, 2) mfcc_fused_kernel(const __grid_co
         int4* dst = reinterpret_cast<int4*>(&s.tab);
         for (int i = tid; i < static_cast<int>(sizeof(MfccTables) / 16); i += kThreads) dst[i] = src[i];
     }
+    for (int i = tid; i < kBatch * kPsStride; i += kThreads) (&s.pspec[0][0])[i] = 0.f;   // finite everywhere
     if (tid == 0) {
         mbar_init(&s.full_bar[0], 1);
         mbar_init(&s.full_bar[1], 1);
@@ -226,22 +227,37 @@ __global__ void __launch_bounds__(kThreads, 2) mfcc_fused_kernel(const __grid_co
             mbar_wait(&s.full_bar[buf], phase[buf]);
             phase[buf] ^= 1u;
 
-            // ---- P0: int16 -> float, pre-emphasis; ypre[i] = y[f0*step + i] ---------------------
+            // ---- P0: int16 -> float + pre-emphasis, 8 samples per thread -------------------------
+            // ypre uses the PCM buffer's own (16-byte aligned) indexing, so loads and stores are
+            // 128-bit; `yoff` is where the batch's first sample sits.
+            const long long a0 = batch_pcm_base(un, f0, step);
+            const int shift = static_cast<int>(un.clip_off - a0);       // buffer index of clip sample 0
+            const int yoff = shift + f0 * step;                         // buffer index of y[f0*step]
             {
-                const long long a0 = batch_pcm_base(un, f0, step);
-                const int sb = f0 * step;
-                const int shift = static_cast<int>(un.clip_off - a0);   // smem index of clip sample 0
-                const int nsamp = (kBatch - 1) * step + flen;
+                const uint4* px4 = reinterpret_cast<const uint4*>(&s.pcm[buf][0]);
                 const unsigned short* px = reinterpret_cast<const unsigned short*>(&s.pcm[buf][0]);
-                for (int i = tid; i < nsamp; i += kThreads) {
-                    const int sidx = sb + i;
-                    float v = 0.0f;
-                    if (sidx < un.len) {
-                        const float x = s16_bits_to_float(px[shift + sidx]);
-                        const float xp = sidx > 0 ? s16_bits_to_float(px[shift + sidx - 1]) : 0.0f;
-                        v = fmaf(-p.preemph, xp, x);
+                const int ngroups = (yoff + (kBatch - 1) * step + flen + 7) >> 3;
+                const float pre = p.preemph;
+                for (int g = tid; g < ngroups; g += kThreads) {
+                    const uint4 w = px4[g];
+                    const uint32_t prev16 = g > 0 ? px[8 * g - 1] : 0u;
+                    const int s0 = 8 * g - shift;                       // clip sample index of element 0
+                    float x[9];
+                    x[0] = s16_bits_to_float(prev16);
+                    x[1] = s16_bits_to_float(w.x & 0xffffu); x[2] = s16_bits_to_float(w.x >> 16);
+                    x[3] = s16_bits_to_float(w.y & 0xffffu); x[4] = s16_bits_to_float(w.y >> 16);
+                    x[5] = s16_bits_to_float(w.z & 0xffffu); x[6] = s16_bits_to_float(w.z >> 16);
+                    x[7] = s16_bits_to_float(w.w & 0xffffu); x[8] = s16_bits_to_float(w.w >> 16);
+                    float y[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int si = s0 + j;
+                        const float xp = si > 0 ? x[j] : 0.f;           // y[0] = x[0]
+                        y[j] = (si >= 0 && si < un.len) ? fmaf(-pre, xp, x[j + 1]) : 0.f;   // zero padded tail
                     }
-                    s.ypre[i] = v;
+                    float4* dst = reinterpret_cast<float4*>(&s.ypre[8 * g]);
+                    dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+                    dst[1] = make_float4(y[4], y[5], y[6], y[7]);
                 }
             }
             __syncthreads();                                            // S0
@@ -250,29 +266,38 @@ __global__ void __launch_bounds__(kThreads, 2) mfcc_fused_kernel(const __grid_co
             {
                 const int fa = f0 + 2 * warp;                           // frame A (B = A+1)
                 if (fa < un.c1) {
-                    const bool b_valid = (fa + 1 < un.c1);
-                    const float* ya = &s.ypre[(2 * warp) * step];
+                    const float* ya = &s.ypre[yoff + (2 * warp) * step];
                     const float* yb = ya + step;
                     float2* sc = &s.scratch[warp][0];
                     float2 v0[8], v1[8];
                     // stage 1: butterflies m = lane, lane+32 over n2 (stride 64)
+                    if (flen == 400 && !p.windowed) {
+                        // the reference configuration: samples 0..383 always present, 384..399 only
+                        // for m < 16, everything above is the FFT's zero padding
 #pragma unroll
-                    for (int n2 = 0; n2 < 8; ++n2) {
-                        const int n_a = 64 * n2 + lane;
-                        const int n_b = n_a + 32;
-                        float2 za = make_float2(0.f, 0.f), zb = make_float2(0.f, 0.f);
-                        if (n_a < flen) {
-                            za.x = ya[n_a];
-                            za.y = b_valid ? yb[n_a] : 0.f;
-                            if (p.windowed) { za.x *= s.tab.window[n_a]; za.y *= s.tab.window[n_a]; }
+                        for (int n2 = 0; n2 < 6; ++n2) {
+                            v0[n2] = make_float2(ya[64 * n2 + lane], yb[64 * n2 + lane]);
+                            v1[n2] = make_float2(ya[64 * n2 + 32 + lane], yb[64 * n2 + 32 + lane]);
                         }
-                        if (n_b < flen) {
-                            zb.x = ya[n_b];
-                            zb.y = b_valid ? yb[n_b] : 0.f;
-                            if (p.windowed) { zb.x *= s.tab.window[n_b]; zb.y *= s.tab.window[n_b]; }
+                        v0[6] = lane < 16 ? make_float2(ya[384 + lane], yb[384 + lane]) : make_float2(0.f, 0.f);
+                        v0[7] = v1[6] = v1[7] = make_float2(0.f, 0.f);
+                    } else {
+#pragma unroll
+                        for (int n2 = 0; n2 < 8; ++n2) {
+                            const int n_a = 64 * n2 + lane;
+                            const int n_b = n_a + 32;
+                            float2 za = make_float2(0.f, 0.f), zb = make_float2(0.f, 0.f);
+                            if (n_a < flen) {
+                                const float wv = p.windowed ? s.tab.window[n_a] : 1.f;
+                                za = make_float2(ya[n_a] * wv, yb[n_a] * wv);
+                            }
+                            if (n_b < flen) {
+                                const float wv = p.windowed ? s.tab.window[n_b] : 1.f;
+                                zb = make_float2(ya[n_b] * wv, yb[n_b] * wv);
+                            }
+                            v0[n2] = za;
+                            v1[n2] = zb;
                         }
-                        v0[n2] = za;
-                        v1[n2] = zb;
                     }
                     fft8(v0);
                     fft8(v1);
@@ -374,61 +399,63 @@ __global__ void __launch_bounds__(kThreads, 2) mfcc_fused_kernel(const __grid_co
             }
             __syncthreads();                                            // S1
 
-            // ---- P2: mel filterbank + log; lane = (frame f, half h) -----------------------------
+            // ---- P2: mel filterbank + log + this warp's share of the DCT ------------------------
+            // lane = (frame f, half h): the two halves split each filter's bins, then split the
+            // cepstra (h=0: c0..c6, h=1: c7..c13) of the DCT-II partial sums.
             {
                 const int f = lane & 15;
                 const int h = lane >> 4;
                 const float* ps = &s.pspec[f][0];
                 const int cnt = s.tab.warp_cnt[warp];
+                float cp[7];
+#pragma unroll
+                for (int c = 0; c < 7; ++c) cp[c] = 0.f;
                 for (int li = 0; li < cnt; ++li) {
                     const int j = s.tab.warp_list[warp][li];
-                    const int4 m = s.tab.fmeta[j];                      // start, len, woff, a
-                    const int my_off = h ? m.w : 0;
-                    const int my_len = h ? m.y - m.w : m.w;
-                    const int iters = max(m.w, m.y - m.w);
-                    const float* w = &s.tab.fbw[m.z + my_off];
-                    const float* x = ps + m.x + my_off;
-                    float acc = 0.f;
-                    for (int i = 0; i < iters; ++i)
-                        if (i < my_len) acc = fmaf(w[i], x[i], acc);
+                    const int4 m = s.tab.fmeta[j];                      // start, a, iters, woff
+                    const float* w = &s.tab.fbw[m.w + h * m.z];
+                    const float* x = ps + m.x + h * m.y;
+                    float acc0 = 0.f, acc1 = 0.f;
+                    for (int i = 0; i < m.z; i += 4) {                  // zero-padded: no bounds tests
+                        const float4 wv = *reinterpret_cast<const float4*>(w + i);
+                        acc0 = fmaf(wv.x, x[i], acc0);
+                        acc1 = fmaf(wv.y, x[i + 1], acc1);
+                        acc0 = fmaf(wv.z, x[i + 2], acc0);
+                        acc1 = fmaf(wv.w, x[i + 3], acc1);
+                    }
+                    float acc = acc0 + acc1;
                     acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                    if (h == 0) s.logmel[f][j] = logf(acc == 0.f ? kEps : acc);
+                    const float lm = __logf(acc == 0.f ? kEps : acc);
+                    const float4 d0 = *reinterpret_cast<const float4*>(&s.tab.dct[j][h][0]);
+                    const float4 d1 = *reinterpret_cast<const float4*>(&s.tab.dct[j][h][4]);
+                    cp[0] = fmaf(lm, d0.x, cp[0]); cp[1] = fmaf(lm, d0.y, cp[1]);
+                    cp[2] = fmaf(lm, d0.z, cp[2]); cp[3] = fmaf(lm, d0.w, cp[3]);
+                    cp[4] = fmaf(lm, d1.x, cp[4]); cp[5] = fmaf(lm, d1.y, cp[5]);
+                    cp[6] = fmaf(lm, d1.z, cp[6]);
                 }
+                float* dst = &s.cpart[warp][f][7 * h];
+#pragma unroll
+                for (int c = 0; c < 7; ++c) dst[c] = cp[c];
             }
             __syncthreads();                                            // S2
 
-            // ---- P3: DCT-II + lifter (+ c0 := ln energy); warp -> cepstra {w, w+8} --------------
+            // ---- P3: sum the 8 warps' partial cepstra; c0 := ln(energy) -------------------------
             {
-                const int f = lane & 15;
-                const int h = lane >> 4;
-                const int ca = warp, cb = warp + 8;
-                const int nh = (p.nfilt + 1) >> 1;
-                const float* lm = &s.logmel[f][0];
-                float acc_a = 0.f, acc_b = 0.f;
-                if (ca < ncep) {
-                    for (int i = 0; i < nh; ++i) {
-                        const int j = h * nh + i;
-                        if (j < p.nfilt) {
-                            const float v = lm[j];
-                            acc_a = fmaf(v, s.tab.dct[ca][j], acc_a);
-                            if (cb < ncep) acc_b = fmaf(v, s.tab.dct[cb][j], acc_b);
-                        }
-                    }
-                }
-                acc_a += __shfl_xor_sync(0xffffffffu, acc_a, 16);
-                acc_b += __shfl_xor_sync(0xffffffffu, acc_b, 16);
+                const int f = tid >> 4, c = tid & 15;
                 const int fr = f0 + f;
-                if (h == 0 && fr < un.c1 && ca < ncep) {
-                    float* row = &s.feat[(fr - un.c0) * ncep];
-                    if (ca == 0 && p.append_energy) {
+                if (c < ncep && fr < un.c1) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) v += s.cpart[w][f][c];
+                    if (c == 0 && p.append_energy) {
                         const float e = s.energy[f];
-                        acc_a = logf(e == 0.f ? kEps : e);
+                        v = logf(e == 0.f ? kEps : e);
                     }
-                    row[ca] = acc_a;
-                    if (cb < ncep) row[cb] = acc_b;
+                    s.feat[(fr - un.c0) * ncep + c] = v;
                 }
             }
-            // no barrier needed here: the next batch's P0 only writes ypre (last read before S1)
+            // no barrier needed here: the next batch's P0 only writes ypre (last read before S1), and
+            // cpart / energy are next written after the next S0 / S1
         }
         __syncthreads();
 
@@ -523,17 +550,21 @@ int build_tables(const MmlaMfccParams& p, MfccTables& t) {
                 if (first < 0) first = i;
                 last = i;
             }
-        int len = first < 0 ? 0 : last - first + 1;
-        if (nnz_total + len > kMaxNnz) {
-            mmla_set_error("mfcc: filterbank has more than %d non-zeros", kMaxNnz);
-            return MMLA_EUNSUP;
-        }
+        const int len = first < 0 ? 0 : last - first + 1;
         int a = len >= 2 ? ((len / 2) | 1) : len;          // odd split point (bank-friendly)
         if (a > len) a = len;
-        t.fmeta[j] = make_int4(first < 0 ? 0 : first, len, nnz_total, a);
-        for (int i = 0; i < len; ++i) t.fbw[nnz_total + i] = static_cast<float>(row[first + i]);
-        nnz_total += len;
-        cost[j] = (len - a > a ? len - a : a) + 12;        // loop trips + fixed per-filter overhead
+        int iters = (len - a > a ? len - a : a);
+        iters = (iters + 3) & ~3;                          // float4 weight loads, no bounds tests
+        if (nnz_total + 2 * iters > kMaxNnz) {
+            mmla_set_error("mfcc: filterbank needs more than %d padded weights", kMaxNnz);
+            return MMLA_EUNSUP;
+        }
+        const int start = first < 0 ? 0 : first;
+        t.fmeta[j] = make_int4(start, a, iters, nnz_total);
+        for (int i = 0; i < a; ++i) t.fbw[nnz_total + i] = static_cast<float>(row[start + i]);
+        for (int i = a; i < len; ++i) t.fbw[nnz_total + iters + (i - a)] = static_cast<float>(row[start + i]);
+        nnz_total += 2 * iters;
+        cost[j] = (iters / 4) * 6 + 28;                    // loop trips + fixed per-filter work
     }
     // longest-processing-time partition of filters over the 8 warps
     std::vector<int> order(p.nfilt);
@@ -547,13 +578,14 @@ int build_tables(const MmlaMfccParams& p, MfccTables& t) {
         t.warp_list[w][t.warp_cnt[w]++] = static_cast<unsigned char>(j);
         load[w] += cost[j];
     }
-    // DCT-II ortho (scipy.fftpack.dct norm='ortho') with the psf lifter folded in
+    // DCT-II ortho (scipy.fftpack.dct norm='ortho') with the psf lifter folded in, laid out per
+    // filter as [half][7]: half 0 holds c0..c6, half 1 holds c7..c13
     const double PI = 3.14159265358979323846;
     for (int c = 0; c < p.numcep; ++c) {
         double scale = c == 0 ? sqrt(1.0 / p.nfilt) : sqrt(2.0 / p.nfilt);
         double lift = p.ceplifter > 0 ? 1.0 + (p.ceplifter / 2.0) * sin(PI * c / p.ceplifter) : 1.0;
         for (int j = 0; j < p.nfilt; ++j)
-            t.dct[c][j] = static_cast<float>(lift * scale * cos(PI * c * (2 * j + 1) / (2.0 * p.nfilt)));
+            t.dct[j][c / 7][c % 7] = static_cast<float>(lift * scale * cos(PI * c * (2 * j + 1) / (2.0 * p.nfilt)));
     }
     for (int n = 0; n < kNfft; ++n) {
         double w = 1.0;
@@ -620,8 +652,8 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
     MMLA_REQUIRE(p.frame_step >= 1 && (kBatch - 1) * p.frame_step + p.frame_len <= kMaxBatchSamples, MMLA_EUNSUP,
                  "mfcc: frame_step=%d too large for the %d-sample batch buffer", p.frame_step, kMaxBatchSamples);
     MMLA_REQUIRE(p.nfilt >= 1 && p.nfilt <= kMaxFilt, MMLA_EUNSUP, "mfcc: nfilt=%d must be in [1,%d]", p.nfilt, kMaxFilt);
-    MMLA_REQUIRE(p.numcep >= 1 && p.numcep <= kMaxCep && p.numcep <= p.nfilt, MMLA_EUNSUP,
-                 "mfcc: numcep=%d must be in [1,%d] and <= nfilt", p.numcep, kMaxCep);
+    MMLA_REQUIRE(p.numcep >= 1 && p.numcep <= 14 && p.numcep <= p.nfilt, MMLA_EUNSUP,
+                 "mfcc: numcep=%d must be in [1,14] and <= nfilt", p.numcep);
     MMLA_REQUIRE(p.window >= 0 && p.window <= 2, MMLA_EINVAL, "mfcc: bad window id %d", p.window);
     MMLA_REQUIRE((reinterpret_cast<uintptr_t>(pcm) & 15) == 0, MMLA_EINVAL, "mfcc: pcm must be 16-byte aligned");
     MMLA_REQUIRE((clip_off_host == nullptr) == (clip_len_host == nullptr), MMLA_EINVAL,
