@@ -128,12 +128,18 @@ int mmla_overlap_features(const int16_t* pcm, int64_t pcm_total_samples,
 #define MMLA_NET_SPEAKER 1   /* x: float32 [B,256,39]                       -> prob [B,n]   */
 #define MMLA_HEAD_SOFTMAX 0
 #define MMLA_HEAD_SIGMOID 1
+/* Arithmetic of the conv / LSTM matrix products (features are always fp32):
+ *   FP32: CUDA-core implicit GEMM, fp32 operands and accumulation (bit-faithful layer semantics);
+ *   TF32: tcgen05 tensor cores, TF32 operands (10-bit mantissa), fp32 accumulation in TMEM. */
+#define MMLA_PRECISION_FP32 0
+#define MMLA_PRECISION_TF32 1
 
 typedef struct MmlaNet MmlaNet;   /* opaque */
 
 int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head_activation,
                     const float* weights_host, int64_t n_weights, MmlaNet** out_net);
 void mmla_net_destroy(MmlaNet* net);
+int mmla_net_set_precision(MmlaNet* net, int32_t mode);
 /* Bytes of device workspace needed for a forward pass over `batch` clips. */
 int64_t mmla_net_workspace_bytes(const MmlaNet* net, int64_t batch);
 /*

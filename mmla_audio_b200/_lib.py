@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "libmmla_b200.so")
 SYMBOLS = (
     "mmla_last_error", "mmla_abi_version", "mmla_launch_count", "mmla_crc32c_host",
     "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_delta", "mmla_overlap_features",
-    "mmla_net_create", "mmla_net_destroy", "mmla_net_workspace_bytes", "mmla_net_forward",
+    "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
+    "mmla_net_forward",
     "mmla_tally", "mmla_synth_pcm",
 )
 
@@ -61,6 +62,7 @@ def load() -> C.CDLL:
         "mmla_overlap_features": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, i32, vp, vp, vp, vp, vp]),
         "mmla_net_create": (C.c_int, [i32, i32, i32, vp, i64, C.POINTER(vp)]),
         "mmla_net_destroy": (None, [vp]),
+        "mmla_net_set_precision": (C.c_int, [vp, i32]),
         "mmla_net_workspace_bytes": (i64, [vp, i64]),
         "mmla_net_forward": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, vp, vp]),
         "mmla_tally": (C.c_int, [vp, i64, i32, vp, vp]),

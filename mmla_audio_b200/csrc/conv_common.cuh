@@ -1,0 +1,32 @@
+// Shared between the fp32 CUDA-core conv kernel (nets.cu) and the tcgen05 TF32 kernel (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+
+constexpr float kBnEps = 1e-3f;
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// implicit-GEMM convolution: Y[M,N] = gather(X)[M,K] * W[K,N] + bias (+ residual)
+// ---------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const void* x;            // NHWC float32, or uint8 when x_is_u8
+    const float* w;           // [K][N]
+    const float* bias;        // [N]
+    const float* pre_scale;   // per input channel BN scale (null: no BN/activation prologue)
+    const float* pre_shift;
+    const float* res;         // residual rows (null: none)
+    float* y;                 // [M][N]
+    long long res_row_stride; // floats between residual rows
+    long long M;
+    int x_is_u8, pre_act;
+    int H, W, Cin, Ho, Wo, N, K, kh, kw, stride, pad_t, pad_l;
+};
+
+constexpr int kBM = 128, kBK = 16;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_ELU) return v > 0.f ? v : expm1f(v);
+    return v;
+}
+

@@ -1,0 +1,328 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a, TF32 operands, FP32
+// accumulation in tensor memory (TMEM).
+//
+//   Y[M, N] = gather(X)[M, K] * W[K, N] + bias (+ residual)          M = B*Ho*Wo, K = kh*kw*Cin
+//
+// One CTA computes a 128 x NT output tile:
+//   * A operand (activations): all 256 threads gather the im2col tile from NHWC global memory,
+//     apply the preceding BatchNorm + ELU/ReLU on the fly, round to TF32 and store it to shared
+//     memory in the UMMA canonical K-major / no-swizzle layout
+//         [K-slab of 4 floats][row 0..127][16 bytes]          (LBO = 2048 B, SBO = 128 B)
+//     — a layout in which consecutive rows are consecutive 16-byte words, so the STS.128 stores are
+//     bank-conflict free.
+//   * B operand (weights): pre-arranged on the host in the same slab layout and pre-rounded to
+//     TF32, so one TMA bulk copy (cp.async.bulk + mbarrier complete_tx) lands a whole
+//     [32 x NT] K-chunk, ready for the tensor core.
+//   * One elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=NT, K=8) four
+//     times per 32-wide K chunk; tcgen05.commit releases the smem stage (2-stage ring) and, after
+//     the last chunk, signals the epilogue.
+//   * Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) TMEM -> registers, + bias, + residual,
+//     128-bit stores.
+// Used for every conv / LSTM projection of both classifiers when the net runs in TF32 mode
+// (mmla_net_set_precision); the fp32 CUDA-core kernel in nets.cu is the bit-faithful path.
+#include <math.h>
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int kTcBK = 32;                  // K elements per pipeline stage (4 MMAs of K=8)
+constexpr int kTcStages = 2;
+constexpr int kAStageBytes = 8 * 128 * 16;  // 8 slabs x 128 rows x 16 B
+
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return u;
+}
+// mbarrier wait that traps instead of hanging the GPU if a barrier is never satisfied (a wrong
+// descriptor / byte count would otherwise spin forever); ~seconds of polling before giving up.
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE, Blackwell version bit set.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;                       // descriptor version (sm_100)
+    return d;                              // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int NT>
+struct TcSmem {
+    alignas(128) unsigned char A[kTcStages][kAStageBytes];
+    alignas(128) unsigned char B[kTcStages][8 * NT * 16];
+    alignas(8) uint64_t full_b[kTcStages];
+    alignas(8) uint64_t empty[kTcStages];
+    alignas(8) uint64_t accum;
+    uint32_t tmem_base;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const float* __restrict__ wg) {
+    constexpr int kCols = NT < 32 ? 32 : NT;                       // TMEM columns (power of two >= 32)
+    constexpr uint32_t kBStage = 8 * NT * 16;
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcSmem<NT>& s = *reinterpret_cast<TcSmem<NT>*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long m0 = static_cast<long long>(blockIdx.x) * 128;
+    const int ntile = blockIdx.y;
+    const int n0 = ntile * NT;
+    const int nk = (a.K + kTcBK - 1) / kTcBK;
+
+    if (tid == 0) {
+        for (int i = 0; i < kTcStages; ++i) {
+            mbar_init(&s.full_b[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
+        mbar_init(&s.accum, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
+                     "r"(static_cast<uint32_t>(kCols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+
+    // A-gather bookkeeping: this thread always fills row `arow`, K offsets [ahalf*16, ahalf*16+16)
+    const int arow = tid & 127, ahalf = tid >> 7;
+    const long long am = m0 + arow;
+    const bool avalid = am < a.M;
+    int hi0 = 0, wi0 = 0;
+    long long xbase = 0;
+    if (avalid) {
+        const int hw = a.Ho * a.Wo;
+        const long long b = am / hw;
+        const int r = static_cast<int>(am - b * hw);
+        const int ho = r / a.Wo, wo = r - ho * a.Wo;
+        hi0 = ho * a.stride - a.pad_t;
+        wi0 = wo * a.stride - a.pad_l;
+        xbase = b * a.H * a.W * a.Cin;
+    }
+    const bool fast = (a.Cin % 16 == 0) && !a.x_is_u8;
+    const float* xf = static_cast<const float*>(a.x);
+    const unsigned char* xu = static_cast<const unsigned char*>(a.x);
+
+    for (int kc = 0; kc < nk; ++kc) {
+        const int st = kc & 1;
+        const int use = kc >> 1;
+        if (kc >= kTcStages) mbar_wait_or_trap(&s.empty[st], static_cast<uint32_t>((use - 1) & 1));   // MMAs of kc-2 done
+        if (tid == 0) {
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(&s.full_b[st], kBStage);
+            tma_bulk_g2s(&s.B[st][0], wg + (static_cast<long long>(ntile) * nk + kc) * (NT * kTcBK), kBStage,
+                         &s.full_b[st]);
+        }
+        // ---- gather 16 K-elements of this thread's row, BN + activation, TF32, STS.128 x4 --------
+        {
+            const int kb = kc * kTcBK + ahalf * 16;
+            uint4 q[4];
+            if (fast) {
+                const int tap = kb / a.Cin, c0 = kb - tap * a.Cin;
+                const int ki = tap / a.kw, kj = tap - ki * a.kw;
+                const int hi = hi0 + ki, wi = wi0 + kj;
+                const bool inb = avalid && kb < a.K && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+                const float* src = xf + xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inb) {
+                        v = *reinterpret_cast<const float4*>(src + 4 * j);
+                        if (a.pre_scale) {
+                            const float4 sc = *reinterpret_cast<const float4*>(a.pre_scale + c0 + 4 * j);
+                            const float4 sh = *reinterpret_cast<const float4*>(a.pre_shift + c0 + 4 * j);
+                            v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
+                            v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
+                            v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
+                            v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
+                        }
+                    }
+                    q[j] = make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
+                }
+            } else {
+                uint32_t e[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = kb + i;
+                    float v = 0.f;
+                    if (avalid && k < a.K) {
+                        const int tap = k / a.Cin, c = k - tap * a.Cin;
+                        const int ki = tap / a.kw, kj = tap - ki * a.kw;
+                        const int hi = hi0 + ki, wi = wi0 + kj;
+                        if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+                            const long long idx = xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c;
+                            v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
+                            if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
+                        }
+                    }
+                    e[i] = f32_to_tf32(v);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+            }
+            unsigned char* abase = &s.A[st][0] + (ahalf * 4) * 2048 + arow * 16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(abase + j * 2048) = q[j];
+        }
+        fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait_or_trap(&s.full_b[st], static_cast<uint32_t>(use & 1));
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(&s.A[st][0]);
+            const uint32_t b_addr = smem_u32(&s.B[st][0]);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = umma_desc(a_addr + kk * 2 * 2048, 2048, 128);
+                const uint64_t bd = umma_desc(b_addr + kk * 2 * (NT * 16), NT * 16, 128);
+                umma_tf32(tmem, ad, bd, kIdesc, (kc | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&s.empty[st]);                       // frees this smem stage when the MMAs retire
+            if (kc == nk - 1) umma_commit(&s.accum);         // accumulator complete
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> (+bias, +residual) -> global ---------------------------
+    mbar_wait_or_trap(&s.accum, 0u);
+    tc_fence_after();
+    {
+        constexpr int kColsPerWarp = NT >= 64 ? NT / 2 : NT;      // warps 4..7 take the upper half when NT >= 64
+        const int quarter = warp & 3;
+        const int chalf = warp >> 2;
+        const bool active = NT >= 64 || chalf == 0;
+        const long long m = m0 + quarter * 32 + lane;
+        if (active) {
+#pragma unroll
+            for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
+                const int col = chalf * kColsPerWarp + c0;
+                uint32_t r[16];
+                const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(col);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                    "%14, %15}, [%16];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < a.M) {
+                    const int n = n0 + col;
+                    float* dst = a.y + m * a.N + n;
+                    const float* bias = a.bias + n;
+                    const float* res = a.res ? a.res + m * a.res_row_stride + n : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 v;
+                        const float4 bv = *reinterpret_cast<const float4*>(bias + j);
+                        v.x = __uint_as_float(r[j + 0]) + bv.x;
+                        v.y = __uint_as_float(r[j + 1]) + bv.y;
+                        v.z = __uint_as_float(r[j + 2]) + bv.z;
+                        v.w = __uint_as_float(r[j + 3]) + bv.w;
+                        if (res) {
+                            const float4 rv = *reinterpret_cast<const float4*>(res + j);
+                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = v;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(static_cast<uint32_t>(kCols))
+                     : "memory");
+    }
+}
+
+template <int NT>
+int launch_nt(const ConvArgs& a, const float* wg, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(TcSmem<NT>))));
+        attr_set = true;
+    }
+    const dim3 grid(static_cast<unsigned>((a.M + 127) / 128), static_cast<unsigned>(a.N / NT));
+    conv_tc_kernel<NT><<<grid, 256, sizeof(TcSmem<NT>), st>>>(a, wg);
+    mmla_count_launch();
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
+}  // namespace
+
+// N tile used for an output width N (0: this layer is not eligible for the tensor-core path).
+int mmla_tc_ntile(int n) {
+    if (n == 16 || n == 32 || n == 64 || n == 128) return n;
+    if (n > 128 && n % 128 == 0) return 128;
+    return 0;
+}
+
+// Host: arrange W[K][N] (row-major, TF layout) for the TMA-fed B operand:
+//   out[ntile][kchunk][slab 0..7][n 0..NT-1][4]  = W[kchunk*32 + slab*4 + j][ntile*NT + n], zero padded in K,
+// rounded to TF32 (round-to-nearest, ties away — what cvt.rna.tf32.f32 does on the A side).
+long long mmla_tc_arranged_floats(int K, int N) {
+    const int nk = (K + kTcBK - 1) / kTcBK;
+    return static_cast<long long>(nk) * kTcBK * N;
+}
+void mmla_tc_arrange_weights(const float* w, int K, int N, float* out) {
+    const int NT = mmla_tc_ntile(N);
+    const int nk = (K + kTcBK - 1) / kTcBK;
+    const int ntiles = N / NT;
+    for (int t = 0; t < ntiles; ++t)
+        for (int kc = 0; kc < nk; ++kc)
+            for (int slab = 0; slab < 8; ++slab)
+                for (int n = 0; n < NT; ++n)
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = kc * kTcBK + slab * 4 + j;
+                        float v = k < K ? w[static_cast<long long>(k) * N + t * NT + n] : 0.f;
+                        uint32_t u;
+                        memcpy(&u, &v, 4);
+                        if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & ~0x1FFFu;
+                        memcpy(&v, &u, 4);
+                        out[((((static_cast<long long>(t) * nk + kc) * 8 + slab) * NT + n) * 4) + j] = v;
+                    }
+}
+
+int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st) {
+    switch (mmla_tc_ntile(a.N)) {
+        case 16: return launch_nt<16>(a, wg, st);
+        case 32: return launch_nt<32>(a, wg, st);
+        case 64: return launch_nt<64>(a, wg, st);
+        case 128: return launch_nt<128>(a, wg, st);
+        default:
+            mmla_set_error("conv_tc: N=%d is not eligible for the tensor-core path", a.N);
+            return MMLA_EUNSUP;
+    }
+}

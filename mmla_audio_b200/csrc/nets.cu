@@ -19,36 +19,11 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_common.cuh"
 
 namespace {
 
-constexpr float kBnEps = 1e-3f;
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2 };
-
-// ---------------------------------------------------------------------------------------------
-// implicit-GEMM convolution: Y[M,N] = gather(X)[M,K] * W[K,N] + bias (+ residual)
-// ---------------------------------------------------------------------------------------------
-struct ConvArgs {
-    const void* x;            // NHWC float32, or uint8 when x_is_u8
-    const float* w;           // [K][N]
-    const float* bias;        // [N]
-    const float* pre_scale;   // per input channel BN scale (null: no BN/activation prologue)
-    const float* pre_shift;
-    const float* res;         // residual rows (null: none)
-    float* y;                 // [M][N]
-    long long res_row_stride; // floats between residual rows
-    long long M;
-    int x_is_u8, pre_act;
-    int H, W, Cin, Ho, Wo, N, K, kh, kw, stride, pad_t, pad_l;
-};
-
-constexpr int kBM = 128, kBK = 16;
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == ACT_RELU) return fmaxf(v, 0.f);
-    if (act == ACT_ELU) return v > 0.f ? v : expm1f(v);
-    return v;
-}
+// (ConvArgs, activation ids and apply_act live in conv_common.cuh)
 
 template <int TN>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs a) {
@@ -341,6 +316,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ hf,
 // ---------------------------------------------------------------------------------------------
 struct ConvW {
     const float* k = nullptr;
+    const float* k_tc = nullptr;          // same weights arranged + TF32-rounded for conv_tc.cu (or null)
     const float* b = nullptr;
     int kh = 1, kw = 1, cin = 0, cout = 0, stride = 1;
 };
@@ -355,6 +331,7 @@ struct BlockW {
 };
 struct MmlaNet {
     int kind = 0, n_classes = 0, head = 0;
+    int precision = MMLA_PRECISION_FP32;  // MMLA_PRECISION_*
     float* dev = nullptr;                 // device blob (weights + folded BN)
     ConvW stem;
     std::vector<BlockW> blocks;
@@ -369,6 +346,12 @@ struct MmlaNet {
     int micro = 0;                        // clips per micro-batch
 };
 
+// conv_tc.cu
+int mmla_tc_ntile(int n);
+long long mmla_tc_arranged_floats(int K, int N);
+void mmla_tc_arrange_weights(const float* w, int K, int N, float* out);
+int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st);
+
 namespace {
 
 int same_out(int n, int s) { return (n + s - 1) / s; }
@@ -380,7 +363,7 @@ int same_pad_before(int n, int k, int s) {
 }
 
 int launch_conv(const ConvW& c, const void* x, int x_is_u8, long long B, int H, int W, const BnW* pre, int pre_act,
-                const float* res, long long res_row_stride, float* y, cudaStream_t st) {
+                const float* res, long long res_row_stride, float* y, cudaStream_t st, bool tc = false) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x; a.x_is_u8 = x_is_u8; a.w = c.k; a.bias = c.b;
@@ -396,6 +379,7 @@ int launch_conv(const ConvW& c, const void* x, int x_is_u8, long long B, int H, 
     a.pad_l = same_pad_before(W, c.kw, c.stride);
     a.M = B * a.Ho * a.Wo;
     if (a.M == 0) return MMLA_OK;
+    if (tc && c.k_tc) return mmla_launch_conv_tc(a, c.k_tc, st);
     const unsigned gx = static_cast<unsigned>((a.M + kBM - 1) / kBM);
     if (c.cout <= 16) {
         conv_igemm_kernel<1><<<dim3(gx, (c.cout + 15) / 16), 256, 0, st>>>(a);
@@ -457,10 +441,21 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
         rd.take(cnt);
         fixes.push_back({dst, off});
     };
+    auto add_tc = [&](ConvW& c, const float* wsrc) {     // tensor-core copy of the weights (if eligible)
+        const int K = c.kh * c.kw * c.cin;
+        if (!rd.ok || mmla_tc_ntile(c.cout) == 0) return;
+        while (stage.size() % 4) stage.push_back(0.f);
+        const long long off = static_cast<long long>(stage.size());
+        stage.resize(stage.size() + mmla_tc_arranged_floats(K, c.cout));
+        mmla_tc_arrange_weights(wsrc, K, c.cout, stage.data() + off);
+        fixes.push_back({&c.k_tc, off});
+    };
     auto take_conv = [&](ConvW& c, int kh, int kw, int cin, int cout, int stride) {
         c.kh = kh; c.kw = kw; c.cin = cin; c.cout = cout; c.stride = stride;
+        const float* wsrc = rd.p + rd.pos;
         take_ptr(&c.k, static_cast<long long>(kh) * kw * cin * cout);
         take_ptr(&c.b, cout);
+        add_tc(c, wsrc);
     };
     auto take_bn = [&](BnW& bn, int ch) {
         const float* g = rd.take(ch);
@@ -509,9 +504,13 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
         ConvW& pr = net->lstm_rec[d];
         pi.kh = pi.kw = 1; pi.cin = 128; pi.cout = 1024; pi.stride = 1;
         pr.kh = pr.kw = 1; pr.cin = 256; pr.cout = 1024; pr.stride = 1;
+        const float* wi_src = rd.p + rd.pos;
         take_ptr(&pi.k, 128LL * 1024);
+        const float* wr_src = rd.p + rd.pos;
         take_ptr(&pr.k, 256LL * 1024);
         take_ptr(&pi.b, 1024);
+        add_tc(pi, wi_src);
+        add_tc(pr, wr_src);
         if (zero_bias_off < 0) {
             while (stage.size() % 4) stage.push_back(0.f);
             zero_bias_off = static_cast<long long>(stage.size());
@@ -570,6 +569,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
     MMLA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, MMLA_EINVAL, "net_forward: workspace must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ov = net->kind == MMLA_NET_OVERLAP;
+    const bool tc = net->precision == MMLA_PRECISION_TF32;
     const long long in_elems = static_cast<long long>(net->in_h) * net->in_w * net->in_c;
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const int T = net->seq_len;
@@ -588,7 +588,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                                   : static_cast<const void*>(static_cast<const float*>(x) + b0 * in_elems);
         int H = net->in_h, W = net->in_w;
         int cur = 0;
-        int rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st);
+        int rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
         if (rc) return rc;
         const int act_kind = ov ? ACT_ELU : ACT_RELU;
         for (const BlockW& blk : net->blocks) {
@@ -597,18 +597,18 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
             float* Bf = buf[(cur + 2) % 3];
             if (!blk.pool) {
                 // out = conv2(act(bn2(conv1(act(bn1(x)))))) + x
-                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st))) return rc;
-                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, X, blk.conv2.cout, Bf, st))) return rc;
+                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
+                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, X, blk.conv2.cout, Bf, st, tc))) return rc;
                 cur = (cur + 2) % 3;
             } else if (ov) {
                 // full-resolution convs, MaxPool2x2 'same', then shortcut conv (stride 2) + pooled
-                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st))) return rc;
-                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st))) return rc;
+                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
+                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st, tc))) return rc;
                 const int Ho = same_out(H, 2), Wo = same_out(W, 2), C = blk.conv2.cout;
                 maxpool_kernel<<<ew_grid(B * Ho * Wo * C), 256, 0, st>>>(Bf, A, B, H, W, C, 2, 2, Ho, Wo);
                 mmla_count_launch();
                 MMLA_CUDA_CHECK(cudaGetLastError());
-                if ((rc = launch_conv(blk.shortcut, X, 0, B, H, W, nullptr, ACT_NONE, A, C, Bf, st))) return rc;
+                if ((rc = launch_conv(blk.shortcut, X, 0, B, H, W, nullptr, ACT_NONE, A, C, Bf, st, tc))) return rc;
                 H = Ho; W = Wo;
                 cur = (cur + 2) % 3;
             } else {
@@ -617,10 +617,10 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                 maxpool_kernel<<<ew_grid(B * Wo * Cin), 256, 0, st>>>(X, A, B, 1, W, Cin, 1, 2, 1, Wo);
                 mmla_count_launch();
                 MMLA_CUDA_CHECK(cudaGetLastError());
-                if ((rc = launch_conv(blk.conv1, A, 0, B, 1, Wo, &blk.bn1, act_kind, nullptr, 0, Bf, st))) return rc;
-                if ((rc = launch_conv(blk.shortcut, X, 0, B, 1, W, nullptr, ACT_NONE, nullptr, 0, A, st))) return rc;
+                if ((rc = launch_conv(blk.conv1, A, 0, B, 1, Wo, &blk.bn1, act_kind, nullptr, 0, Bf, st, tc))) return rc;
+                if ((rc = launch_conv(blk.shortcut, X, 0, B, 1, W, nullptr, ACT_NONE, nullptr, 0, A, st, tc))) return rc;
                 // conv2 reads Bf, adds A (shortcut), writes X's buffer (X is dead now)
-                if ((rc = launch_conv(blk.conv2, Bf, 0, B, 1, Wo, &blk.bn2, act_kind, A, blk.conv2.cout, X, st))) return rc;
+                if ((rc = launch_conv(blk.conv2, Bf, 0, B, 1, Wo, &blk.bn2, act_kind, A, blk.conv2.cout, X, st, tc))) return rc;
                 W = Wo;
             }
         }
@@ -636,7 +636,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         MMLA_CUDA_CHECK(cudaGetLastError());
         // BiLSTM(256): input projections for all steps, then the recurrence
         for (int d = 0; d < 2; ++d)
-            if ((rc = launch_conv(net->lstm_in[d], seq, 0, B * T, 1, 1, nullptr, ACT_NONE, nullptr, 0, xp[d], st))) return rc;
+            if ((rc = launch_conv(net->lstm_in[d], seq, 0, B * T, 1, 1, nullptr, ACT_NONE, nullptr, 0, xp[d], st, tc))) return rc;
         for (int d = 0; d < 2; ++d) {
             float* h = hdir[d];                            // updated in place: the recurrent GEMM of a
             for (int s = 0; s < T; ++s) {                  // step finishes before its gate kernel writes h
@@ -647,7 +647,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                     mmla_count_launch();
                 } else {
                     if ((rc = launch_conv(net->lstm_rec[d], h, 0, B, 1, 1, nullptr, ACT_NONE, xpt,
-                                          static_cast<long long>(T) * 1024, z, st)))
+                                          static_cast<long long>(T) * 1024, z, st, tc)))
                         return rc;
                     lstm_gates_kernel<<<ew_grid(B * 256), 256, 0, st>>>(z, 1024, cst, h, B, 256, 0);
                     mmla_count_launch();
@@ -664,5 +664,13 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         mmla_count_launch();
         MMLA_CUDA_CHECK(cudaGetLastError());
     }
+    return MMLA_OK;
+}
+
+EXPORT int mmla_net_set_precision(MmlaNet* net, int32_t mode) {
+    MMLA_REQUIRE(net != nullptr, MMLA_EINVAL, "net_set_precision: null net");
+    MMLA_REQUIRE(mode == MMLA_PRECISION_FP32 || mode == MMLA_PRECISION_TF32, MMLA_EINVAL,
+                 "net_set_precision: unknown mode %d", mode);
+    net->precision = mode;
     return MMLA_OK;
 }

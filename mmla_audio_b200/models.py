@@ -24,6 +24,7 @@ from .weights import (NetSpec, OVERLAP, SPEAKER_BASE, speaker_spec, weight_shape
 
 KIND_OVERLAP, KIND_SPEAKER = 0, 1
 HEAD_IDS = {"softmax": 0, "sigmoid": 1}
+PRECISION_IDS = {"fp32": 0, "tf32": 1}
 
 
 def pack_weights(spec: NetSpec, w: Dict[str, np.ndarray]) -> np.ndarray:
@@ -63,7 +64,9 @@ class Model:
     """Object returned by ``load_model``; ``predict(x)`` mirrors Keras: numpy in, float32
     ``[B, n_classes]`` numpy out.  ``predict_device`` keeps everything on the GPU."""
 
-    def __init__(self, spec: NetSpec, weights: Dict[str, np.ndarray]):
+    def __init__(self, spec: NetSpec, weights: Dict[str, np.ndarray], precision: str = "fp32"):
+        """precision: 'fp32' (CUDA-core implicit GEMM, bit-faithful layer semantics) or 'tf32'
+        (tcgen05 tensor cores, TF32 operands, fp32 accumulation)."""
         self.spec = spec
         self.weights = weights
         self._handle = None
@@ -78,6 +81,14 @@ class Model:
         self._handle = handle
         self._lib = lib
         self._torch = torch
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str) -> None:
+        if precision not in PRECISION_IDS:
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        _lib.check(self._lib.mmla_net_set_precision(self._handle, PRECISION_IDS[precision]),
+                   "mmla_net_set_precision")
+        self.precision = precision
 
     def __del__(self):
         try:
@@ -138,7 +149,7 @@ def _read_model_weights(model_dir: str, spec: NetSpec) -> Dict[str, np.ndarray]:
 
 
 def load_model(model_dir: str, kind: Optional[str] = None, n_classes: Optional[int] = None,
-               head: Optional[str] = None) -> Model:
+               head: Optional[str] = None, precision: str = "fp32") -> Model:
     """``tf.keras.models.load_model(dir)`` stand-in.  The network family is inferred from the
     bundle's tensor names/shapes unless ``kind`` ('overlap' | 'speaker') is given."""
     prefix = os.path.join(model_dir, "variables", "variables")
@@ -157,7 +168,7 @@ def load_model(model_dir: str, kind: Optional[str] = None, n_classes: Optional[i
             n = shapes[lw(42, "kernel")][1] if n_classes is None else n_classes
             spec = speaker_spec(n, head or "softmax")
     spec = resolve_lstm_keys(spec, shapes)
-    return Model(spec, _read_model_weights(model_dir, spec))
+    return Model(spec, _read_model_weights(model_dir, spec), precision=precision)
 
 
 def save_synthetic_model(model_dir: str, spec: NetSpec, seed: int = 1234) -> Dict[str, np.ndarray]:

@@ -89,3 +89,65 @@ def test_bad_weight_blob_fails_loudly(cuda):
     w.pop(next(iter(w)))
     with pytest.raises(KeyError):
         models.Model(spec, w)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, TF32 operands, fp32 accumulation) path
+# ---------------------------------------------------------------------------------------------
+# Tolerance: TF32 rounds every operand to a 10-bit mantissa (relative 2^-11), so probabilities
+# agree with the fp32 oracle to ~1e-3; stated bound 5e-3 absolute.  Labels must match wherever the
+# oracle's top-2 margin exceeds 1e-2, and overall agreement must be >= 95 % (BASELINE target >= 90 %).
+def _labels_agree_tf32(prob_gpu, prob_ref):
+    lg, lr = prob_gpu.argmax(1), prob_ref.argmax(1)
+    srt = np.sort(prob_ref, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 1e-2
+    assert (lg[clear] == lr[clear]).all(), "TF32 label mismatch on a clear-margin clip"
+    assert (lg == lr).mean() >= 0.95
+
+
+def test_speaker_net_tf32_tensor_cores(cuda):
+    from mmla_audio_b200 import models, weights as W
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 4321)
+    model = models.Model(spec, w, precision="tf32")
+    pcm = synth.synth_clips(0, 64, 24000)
+    x = np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(64)]).astype(np.float32)
+    got = model.predict(x)
+    ref = onets.speaker_forward(x, w, spec)
+    print("tf32 speaker max |dprob|", np.abs(got - ref).max())
+    np.testing.assert_allclose(got, ref, atol=5e-3, rtol=0)
+    _labels_agree_tf32(got, ref)
+    model.set_precision("fp32")                                  # same object, CUDA-core path again
+    np.testing.assert_allclose(model.predict(x), ref, atol=2e-4, rtol=0)
+
+
+def test_overlap_net_tf32_tensor_cores(cuda):
+    from mmla_audio_b200 import models, weights as W
+    spec = W.OVERLAP
+    w = W.synthetic_weights(spec, 1234)
+    model = models.Model(spec, w, precision="tf32")
+    pcm = synth.synth_clips(40, 12, 24000)
+    x = np.stack([lm.classifier_input(pcm[i]) for i in range(12)])
+    ref = onets.overlap_forward(x, w, spec)
+    got = model.predict(x.astype(np.uint8))
+    print("tf32 overlap max |dprob|", np.abs(got - ref).max())
+    np.testing.assert_allclose(got, ref, atol=5e-3, rtol=0)
+    _labels_agree_tf32(got, ref)
+
+
+def test_tf32_vs_fp32_large_batch_label_agreement(cuda):
+    """Bench-sized batch (4096 clips): tensor-core labels vs the fp32 CUDA-core labels."""
+    from mmla_audio_b200 import models, synth as dsynth, weights as W
+    from mmla_audio_b200 import speaker_identification as si
+    torch = cuda
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 4321)
+    feat = si.speaker_features_batch(dsynth.synth_clips(0, 4096, 24000))
+    m32 = models.Model(spec, w, precision="fp32")
+    mtc = models.Model(spec, w, precision="tf32")
+    p32, l32 = m32.predict_device(feat)
+    ptc, ltc = mtc.predict_device(feat)
+    agree = (l32 == ltc).float().mean().item()
+    print("tf32 vs fp32 label agreement on 4096 clips:", agree, "max |dprob|", (p32 - ptc).abs().max().item())
+    assert agree >= 0.95
+    assert (p32 - ptc).abs().max().item() <= 5e-3
