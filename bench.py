@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="speaker_id", choices=sorted(WORKLOADS))
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: workload's)")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+                    help="classifier matmul arithmetic: tf32 = tcgen05 tensor cores, fp32 = CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     a = ap.parse_args()
@@ -244,10 +246,10 @@ def main():
 
     if a.workload == "speaker_id":
         spec = W.speaker_spec(10, "sigmoid")
-        pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321)))
+        pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321), precision=a.precision))
         n_classes = 10
     elif a.workload == "overlap":
-        pipe = OverlapPipeline(models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234)))
+        pipe = OverlapPipeline(models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234), precision=a.precision))
         n_classes = 2
     else:
         pipe, n_classes = None, 1
@@ -312,6 +314,7 @@ def main():
 
     # ---- per-stage timing + roofline of the dominant kernel -----------------------------------
     extra = {}
+    conv_name = "conv_tc_kernel [tcgen05 tf32]" if a.precision == "tf32" else "conv_igemm_kernel [fp32 CUDA cores]"
     if a.workload == "speaker_id":
         feat = torch.empty((B, 256, 39), dtype=torch.float32, device="cuda")
         ms_feat = timed(lambda: si.speaker_features_batch(pcm, out=feat), a.steps)
@@ -325,7 +328,7 @@ def main():
         extra["mfcc39_roofline"] = {"bound": "hbm", "achieved": feat_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": feat_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": feat_bytes}
         if ms_cls >= ms_feat:
-            roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (speaker classifier, fp32 CUDA-core path)",
+            roofline = {"bound": "tensor", "kernel": conv_name + " (speaker classifier)",
                         "achieved": cls_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": cls_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
                         "peak_source": peaks["source"] + " cuBLAS bf16 sustained"}
@@ -338,7 +341,7 @@ def main():
         ms_cls = timed(lambda: pipe.model.predict_device(img), a.steps)
         cls_tflops = B * OVERLAP_FLOP_PER_CLIP / (ms_cls * 1e-3) / 1e12
         extra["stages_ms"] = {"overlap_features_kernel": ms_feat, "overlap_classifier": ms_cls}
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (overlap classifier, fp32 CUDA-core path)",
+        roofline = {"bound": "tensor", "kernel": conv_name + " (overlap classifier)",
                     "achieved": cls_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": cls_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
                     "peak_source": peaks["source"] + " cuBLAS bf16 sustained"}
@@ -386,8 +389,10 @@ def main():
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "clips_per_gpu": B, "clip_seconds": L / SR, "global_clips": n_total,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if (pipe is None or a.precision == "fp32") else "tf32", "data": "synthetic",
+            "config": {"workload": wl["name"], "classifier_precision": a.precision if pipe is not None else None,
+                       "clips_per_gpu": B, "clip_seconds": L / SR, "global_clips": n_total,
                        "sharding": f"clips x{world}, no data-path collective; labels all_gather + tally all_reduce",
                        "l2": "inputs larger than L2 (%.0f MB int16 PCM per GPU per step)" % (B * L * 2 / 1e6),
                        "weights": "seeded synthetic, reference shapes (real .data shards stripped from the mount)"},
