@@ -133,6 +133,78 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
     const float* xf = static_cast<const float*>(a.x);
     const unsigned char* xu = static_cast<const unsigned char*>(a.x);
 
+    // kh == 1 convolutions (every Conv1D, and 1x1 Conv2D): the im2col row of a pixel is one
+    // contiguous run of the NHWC input, valid for k in [k_lo, k_hi) — no div/mod per element.
+    const bool rowrun = !fast && a.kh == 1 && a.stride == 1;
+    long long run_base = 0;
+    int k_lo = 0, k_hi = 0;
+    if (rowrun && avalid) {
+        run_base = xbase + (static_cast<long long>(hi0) * a.W + wi0) * a.Cin;
+        k_lo = max(0, -wi0) * a.Cin;
+        k_hi = min(min(a.kw, a.W - wi0) * a.Cin, a.K);
+    }
+
+    // gather 16 K-elements of this thread's row for chunk kc: BN + activation, TF32
+    auto gather = [&](int kc, uint4 (&q)[4]) {
+        const int kb = kc * kTcBK + ahalf * 16;
+        if (fast) {
+            const int tap = kb / a.Cin, c0 = kb - tap * a.Cin;
+            const int ki = tap / a.kw, kj = tap - ki * a.kw;
+            const int hi = hi0 + ki, wi = wi0 + kj;
+            const bool inb = avalid && kb < a.K && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+            const float* src = xf + xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inb) {
+                    v = *reinterpret_cast<const float4*>(src + 4 * j);
+                    if (a.pre_scale) {
+                        const float4 sc = *reinterpret_cast<const float4*>(a.pre_scale + c0 + 4 * j);
+                        const float4 sh = *reinterpret_cast<const float4*>(a.pre_shift + c0 + 4 * j);
+                        v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
+                        v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
+                        v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
+                        v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
+                    }
+                }
+                q[j] = make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
+            }
+        } else if (rowrun && !a.pre_scale) {
+            uint32_t e[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = kb + i;
+                float v = 0.f;
+                if (k >= k_lo && k < k_hi) v = a.x_is_u8 ? static_cast<float>(xu[run_base + k]) : xf[run_base + k];
+                e[i] = f32_to_tf32(v);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+        } else {
+            uint32_t e[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = kb + i;
+                float v = 0.f;
+                if (avalid && k < a.K) {
+                    const int tap = k / a.Cin, c = k - tap * a.Cin;
+                    const int ki = tap / a.kw, kj = tap - ki * a.kw;
+                    const int hi = hi0 + ki, wi = wi0 + kj;
+                    if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+                        const long long idx = xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c;
+                        v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
+                        if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
+                    }
+                }
+                e[i] = f32_to_tf32(v);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+        }
+    };
+
+    uint4 q[4];
+    gather(0, q);
     for (int kc = 0; kc < nk; ++kc) {
         const int st = kc & 1;
         const int use = kc >> 1;
@@ -143,58 +215,13 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
             tma_bulk_g2s(&s.B[st][0], wg + (static_cast<long long>(ntile) * nk + kc) * (NT * kTcBK), kBStage,
                          &s.full_b[st]);
         }
-        // ---- gather 16 K-elements of this thread's row, BN + activation, TF32, STS.128 x4 --------
         {
-            const int kb = kc * kTcBK + ahalf * 16;
-            uint4 q[4];
-            if (fast) {
-                const int tap = kb / a.Cin, c0 = kb - tap * a.Cin;
-                const int ki = tap / a.kw, kj = tap - ki * a.kw;
-                const int hi = hi0 + ki, wi = wi0 + kj;
-                const bool inb = avalid && kb < a.K && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
-                const float* src = xf + xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inb) {
-                        v = *reinterpret_cast<const float4*>(src + 4 * j);
-                        if (a.pre_scale) {
-                            const float4 sc = *reinterpret_cast<const float4*>(a.pre_scale + c0 + 4 * j);
-                            const float4 sh = *reinterpret_cast<const float4*>(a.pre_shift + c0 + 4 * j);
-                            v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
-                            v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
-                            v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
-                            v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
-                        }
-                    }
-                    q[j] = make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
-                }
-            } else {
-                uint32_t e[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k = kb + i;
-                    float v = 0.f;
-                    if (avalid && k < a.K) {
-                        const int tap = k / a.Cin, c = k - tap * a.Cin;
-                        const int ki = tap / a.kw, kj = tap - ki * a.kw;
-                        const int hi = hi0 + ki, wi = wi0 + kj;
-                        if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
-                            const long long idx = xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c;
-                            v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
-                            if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
-                        }
-                    }
-                    e[i] = f32_to_tf32(v);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
-            }
             unsigned char* abase = &s.A[st][0] + (ahalf * 4) * 2048 + arow * 16;
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(abase + j * 2048) = q[j];
         }
         fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
+        if (kc + 1 < nk) gather(kc + 1, q);  // next chunk's global loads fly during the barrier + MMAs
         __syncthreads();
         if (tid == 0) {
             mbar_wait_or_trap(&s.full_b[st], static_cast<uint32_t>(use & 1));

@@ -14,6 +14,7 @@
 // preceding BatchNorm + activation on the fly and whose epilogue adds bias and the residual.
 // Keras 'same' padding (extra element at the end) is handled by explicit pad_top/pad_left.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -541,7 +542,11 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const long long T = net->seq_len;
     net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 3 * 256;
-    net->micro = ov ? 32 : 4096;
+    net->micro = ov ? 32 : 1024;          // speaker: 17 MB activation tensors stay L2-resident between layers
+    if (const char* e = getenv("MMLA_NET_MICRO")) {
+        const int v = atoi(e);
+        if (v > 0) net->micro = v;
+    }
     *out_net = net;
     return MMLA_OK;
 }
