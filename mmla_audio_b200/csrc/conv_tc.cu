@@ -31,11 +31,10 @@ constexpr int kTcBK = 32;                  // K elements per pipeline stage (4 M
 constexpr int kTcStages = 2;
 constexpr int kAStageBytes = 8 * 128 * 16;  // 8 slabs x 128 rows x 16 B
 
-__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return u;
-}
+// Round-to-nearest (ties away) to TF32's 10-bit mantissa with two integer ops — what
+// cvt.rna.tf32.f32 does for finite inputs, without its multi-instruction special-case handling
+// (activations here are finite; an Inf/NaN would propagate as a huge/NaN value either way).
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 // mbarrier wait that traps instead of hanging the GPU if a barrier is never satisfied (a wrong
 // descriptor / byte count would otherwise spin forever); ~seconds of polling before giving up.
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
@@ -144,44 +143,37 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
         k_hi = min(min(a.kw, a.W - wi0) * a.Cin, a.K);
     }
 
-    // gather 16 K-elements of this thread's row for chunk kc: BN + activation, TF32
-    auto gather = [&](int kc, uint4 (&q)[4]) {
+    // The gather is split in two so the global loads of chunk kc+1 are in flight across the
+    // barrier + MMA issue of chunk kc: load_raw() only issues loads, finish() (BN + activation +
+    // TF32 rounding) runs one iteration later, just before the tile is stored to smem.
+    auto load_raw = [&](int kc, float4 (&raw)[4], int& meta) {
         const int kb = kc * kTcBK + ahalf * 16;
+        meta = -1;                                            // -1: nothing to post-process (zeros / final)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fast) {
             const int tap = kb / a.Cin, c0 = kb - tap * a.Cin;
             const int ki = tap / a.kw, kj = tap - ki * a.kw;
             const int hi = hi0 + ki, wi = wi0 + kj;
             const bool inb = avalid && kb < a.K && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
-            const float* src = xf + xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c0;
+            if (inb) {
+                const float* src = xf + xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (inb) {
-                    v = *reinterpret_cast<const float4*>(src + 4 * j);
-                    if (a.pre_scale) {
-                        const float4 sc = *reinterpret_cast<const float4*>(a.pre_scale + c0 + 4 * j);
-                        const float4 sh = *reinterpret_cast<const float4*>(a.pre_shift + c0 + 4 * j);
-                        v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
-                        v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
-                        v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
-                        v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
-                    }
-                }
-                q[j] = make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
+                for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const float4*>(src + 4 * j);
+                meta = c0;                                    // channel offset for the BN prologue
             }
         } else if (rowrun && !a.pre_scale) {
-            uint32_t e[16];
+            float e[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int k = kb + i;
-                float v = 0.f;
-                if (k >= k_lo && k < k_hi) v = a.x_is_u8 ? static_cast<float>(xu[run_base + k]) : xf[run_base + k];
-                e[i] = f32_to_tf32(v);
+                e[i] = 0.f;
+                if (k >= k_lo && k < k_hi) e[i] = a.x_is_u8 ? static_cast<float>(xu[run_base + k]) : xf[run_base + k];
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) q[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) raw[j] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
         } else {
-            uint32_t e[16];
+            float e[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int k = kb + i;
@@ -196,15 +188,31 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                         if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
                     }
                 }
-                e[i] = f32_to_tf32(v);
+                e[i] = v;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) q[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) raw[j] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+        }
+    };
+    auto finish = [&](const float4 (&raw)[4], int meta, uint4 (&q)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 v = raw[j];
+            if (meta >= 0 && a.pre_scale) {
+                const float4 sc = *reinterpret_cast<const float4*>(a.pre_scale + meta + 4 * j);
+                const float4 sh = *reinterpret_cast<const float4*>(a.pre_shift + meta + 4 * j);
+                v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
+                v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
+                v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
+                v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
+            }
+            q[j] = make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
         }
     };
 
-    uint4 q[4];
-    gather(0, q);
+    float4 raw[4];
+    int meta;
+    load_raw(0, raw, meta);
     for (int kc = 0; kc < nk; ++kc) {
         const int st = kc & 1;
         const int use = kc >> 1;
@@ -216,12 +224,14 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                          &s.full_b[st]);
         }
         {
+            uint4 q[4];
+            finish(raw, meta, q);
             unsigned char* abase = &s.A[st][0] + (ahalf * 4) * 2048 + arow * 16;
 #pragma unroll
             for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(abase + j * 2048) = q[j];
         }
         fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
-        if (kc + 1 < nk) gather(kc + 1, q);  // next chunk's global loads fly during the barrier + MMAs
+        if (kc + 1 < nk) load_raw(kc + 1, raw, meta);   // next chunk's loads fly across the barrier + MMAs
         __syncthreads();
         if (tid == 0) {
             mbar_wait_or_trap(&s.full_b[st], static_cast<uint32_t>(use & 1));
@@ -240,18 +250,34 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
     }
 
     // ---- epilogue: TMEM -> registers -> (+bias, +residual) -> global ---------------------------
-    mbar_wait_or_trap(&s.accum, 0u);
-    tc_fence_after();
+    // Residual / bias loads for a 16-column chunk are issued before the accumulator is read (the
+    // first chunk's even before the MMAs have finished), so their latency hides behind the wait.
     {
         constexpr int kColsPerWarp = NT >= 64 ? NT / 2 : NT;      // warps 4..7 take the upper half when NT >= 64
+        constexpr int kChunks = kColsPerWarp / 16;
         const int quarter = warp & 3;
         const int chalf = warp >> 2;
-        const bool active = NT >= 64 || chalf == 0;
+        const bool active = (NT >= 64 || chalf == 0);
         const long long m = m0 + quarter * 32 + lane;
+        const bool mvalid = active && m < a.M;
+        const int colbase = chalf * kColsPerWarp;
+        float4 rres[4], rbias[4];
+        auto load_rb = [&](int c) {
+            const int n = n0 + colbase + 16 * c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rbias[j] = *reinterpret_cast<const float4*>(a.bias + n + 4 * j);
+                rres[j] = (mvalid && a.res) ? *reinterpret_cast<const float4*>(a.res + m * a.res_row_stride + n + 4 * j)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        if (active) load_rb(0);
+        mbar_wait_or_trap(&s.accum, 0u);
+        tc_fence_after();
         if (active) {
 #pragma unroll
-            for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
-                const int col = chalf * kColsPerWarp + c0;
+            for (int c = 0; c < kChunks; ++c) {
+                const int col = colbase + 16 * c;
                 uint32_t r[16];
                 const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(col);
                 asm volatile(
@@ -261,25 +287,19 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (m < a.M) {
-                    const int n = n0 + col;
-                    float* dst = a.y + m * a.N + n;
-                    const float* bias = a.bias + n;
-                    const float* res = a.res ? a.res + m * a.res_row_stride + n : nullptr;
+                float4 v[4];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 v;
-                        const float4 bv = *reinterpret_cast<const float4*>(bias + j);
-                        v.x = __uint_as_float(r[j + 0]) + bv.x;
-                        v.y = __uint_as_float(r[j + 1]) + bv.y;
-                        v.z = __uint_as_float(r[j + 2]) + bv.z;
-                        v.w = __uint_as_float(r[j + 3]) + bv.w;
-                        if (res) {
-                            const float4 rv = *reinterpret_cast<const float4*>(res + j);
-                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                        }
-                        *reinterpret_cast<float4*>(dst + j) = v;
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    v[j].x = __uint_as_float(r[4 * j + 0]) + rbias[j].x + rres[j].x;
+                    v[j].y = __uint_as_float(r[4 * j + 1]) + rbias[j].y + rres[j].y;
+                    v[j].z = __uint_as_float(r[4 * j + 2]) + rbias[j].z + rres[j].z;
+                    v[j].w = __uint_as_float(r[4 * j + 3]) + rbias[j].w + rres[j].w;
+                }
+                if (c + 1 < kChunks) load_rb(c + 1);             // next chunk's loads overlap these stores
+                if (mvalid) {
+                    float* dst = a.y + m * a.N + n0 + col;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = v[j];
                 }
             }
         }
