@@ -542,7 +542,7 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const long long T = net->seq_len;
     net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 3 * 256;
-    net->micro = ov ? 32 : 1024;          // speaker: 17 MB activation tensors stay L2-resident between layers
+    net->micro = ov ? 128 : 4096;         // measured on B200: larger micro-batches win (launch/latency-bound layers)
     if (const char* e = getenv("MMLA_NET_MICRO")) {
         const int v = atoi(e);
         if (v > 0) net->micro = v;

@@ -1,0 +1,116 @@
+"""GPU parity for the end-to-end pipelines: BASELINE configs 1, 4 and 5 (scaled so the CPU
+oracle finishes in seconds) — labels and tallies must equal the oracle's."""
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+from oracle import librosa_mel as lm, nets as onets, psf, synth, tally as otally
+
+pytestmark = pytest.mark.gpu
+
+
+def _clear(prob, margin=1e-3):
+    s = np.sort(prob, axis=1)
+    return (s[:, -1] - s[:, -2]) > margin
+
+
+def test_config1_overlap_single_clip(cuda):
+    """One 2.5 s clip: features (first 24000 samples) + classifier forward, label vs oracle."""
+    from mmla_audio_b200 import models, weights as W
+    from mmla_audio_b200.pipeline import OverlapPipeline
+    w = W.synthetic_weights(W.OVERLAP, 1234)
+    pipe = OverlapPipeline(models.Model(W.OVERLAP, w))
+    sig = synth.synth_clips(77, 1, 40000)
+    labels, prob = pipe.run_device(cuda.from_numpy(sig).cuda())
+    ref = onets.overlap_forward(lm.classifier_input(sig[0])[None], w, W.OVERLAP)
+    assert np.abs(prob.cpu().numpy() - ref).max() <= 1e-3        # image may differ by 1 LSB on <1% pixels
+    if _clear(ref)[0]:
+        assert labels.cpu().numpy()[0] == ref.argmax(1)[0]
+    short = synth.synth_clips(78, 2, 3999)                        # < 4000 samples => 'silent'
+    l2, _ = pipe.run_device(cuda.from_numpy(short).cuda())
+    assert l2.cpu().tolist() == [-1, -1]
+
+
+def test_config4_long_session_overlap(cuda):
+    """A 60 s recording cut into 1.5 s windows (segmentation index math), labels + tallies."""
+    from mmla_audio_b200 import models, tally, weights as W
+    from mmla_audio_b200.pipeline import OverlapPipeline, segmentation_windows
+    w = W.synthetic_weights(W.OVERLAP, 1234)
+    pipe = OverlapPipeline(models.Model(W.OVERLAP, w))
+    rec = synth.synth_clips(500, 40, 24000).reshape(-1)[: 40 * 24000 - 5000]   # ragged tail is dropped
+    n = segmentation_windows(len(rec), 24000, 24000)
+    assert n == otally.num_windows(len(rec), 24000, 24000) == 39
+    t0 = datetime(2021, 6, 1, 12, 0, 0, 654321)
+    labels, (counts, secs, total) = pipe.run_session(rec, t0=t0)
+    assert labels.numel() == n
+    x = np.stack([lm.classifier_input(rec[i * 24000:(i + 1) * 24000]) for i in range(n)])
+    ref = onets.overlap_forward(x, w, W.OVERLAP)
+    got = labels.cpu().numpy()
+    clear = _clear(ref, 5e-3)
+    assert (got[clear] == ref.argmax(1)[clear]).all() and (got == ref.argmax(1)).mean() >= 0.9
+    names = [tally.OVERLAP_DEGREE_DICT[str(int(l))] for l in got]
+    lines = otally.log_rows(names, t0, 1.5, "overlapped degree", add_before_first=False)
+    rc, rs, rt = otally.tally_from_log(lines, list(tally.OVERLAP_DEGREE_DICT.values()))
+    assert (counts, secs, total) == (rc, rs, rt)                  # integer tallies: bit exact
+
+
+def test_config4_long_session_speaker(cuda):
+    """Whole-file MFCC-39 -> 256-frame chunks -> one predict -> rows every 2.56 s."""
+    from mmla_audio_b200 import models, weights as W
+    from mmla_audio_b200.pipeline import SpeakerPipeline
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 4321)
+    pipe = SpeakerPipeline(models.Model(spec, w))
+    rec = synth.synth_clips(700, 30, 40960).reshape(-1)           # 76.8 s -> 30 chunks
+    names = {i: f"spk{i}" for i in range(10)}
+    t0 = datetime(2022, 3, 3, 8, 30, 0, 111111)
+    labels, (counts, secs, total) = pipe.run_session(rec, names, t0=t0, silent_index=(2, 7))
+    chunks = psf.chunked_features(rec).astype(np.float32)
+    ref = onets.speaker_forward(chunks, w, spec)
+    assert labels.numel() == ref.shape[0] == 30
+    got = labels.cpu().numpy()
+    assert got[2] == -1 and got[7] == -1
+    keep = np.ones(30, bool)
+    keep[[2, 7]] = False
+    clear = _clear(ref) & keep
+    assert (got[clear] == ref.argmax(1)[clear]).all()
+    lab_names = [names.get(int(l), "silent") for l in got]
+    lines = otally.log_rows(lab_names, t0, 2.56, "speaker", add_before_first=True)
+    rc, rs, rt = otally.tally_from_log(lines)
+    assert (counts, secs, total) == (rc, rs, rt)
+
+
+def test_config5_enrollment_features(cuda):
+    """make_feature_experiment: per-speaker corpora -> [M,256,39] chunks, one-hot labels, id dict."""
+    from mmla_audio_b200 import speaker_identification as si
+    corpora = [(f"spk{i}", synth.synth_clips(900 + 10 * i, 4, 40000).reshape(-1)) for i in range(3)]   # 10 s each
+    x, y, ids = si.make_feature_experiment(corpora)
+    ref = np.concatenate([psf.chunked_features(sig) for _, sig in corpora])
+    assert x.shape == ref.shape == (12, 256, 39) and y.shape == (12, 3)
+    tol = 1e-4 * np.abs(ref).max()
+    assert np.all(np.abs(x - ref) <= 1e-4 * np.abs(ref) + tol)
+    assert ids == {"0": "spk0", "1": "spk1", "2": "spk2"}
+    assert (y.argmax(1) == np.repeat(np.arange(3), 4)).all()
+
+
+def test_config2_speaker_batch_labels_bit_exact_on_clear_margins(cuda):
+    """256 clips of 1.5 s, 10 speakers: labels vs oracle (fp32 path) and tf32 agreement."""
+    from mmla_audio_b200 import models, tally, weights as W
+    from mmla_audio_b200.pipeline import SpeakerPipeline
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 4321)
+    pcm = synth.synth_clips(0, 256, 24000)
+    x = np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(256)]).astype(np.float32)
+    ref = onets.speaker_forward(x, w, spec)
+    dev = cuda.from_numpy(pcm).cuda()
+    for prec, min_agree in (("fp32", 0.99), ("tf32", 0.95)):
+        pipe = SpeakerPipeline(models.Model(spec, w, precision=prec))
+        labels, prob = pipe.run_device(dev)
+        got = labels.cpu().numpy()
+        assert (got == ref.argmax(1)).mean() >= min_agree, prec
+        if prec == "fp32":
+            clear = _clear(ref)
+            assert (got[clear] == ref.argmax(1)[clear]).all()
+        counts = tally.device_counts(labels, 10).cpu().numpy()
+        np.testing.assert_array_equal(counts[:10], np.bincount(got, minlength=10))
