@@ -155,6 +155,9 @@ def time_cpu(workload: str, clip_len: int, sample_clips: int, steps: int, warmup
     state = cpu_state(workload)
     pool = None
     cores = torch.get_num_threads()
+    if all_cores:
+        torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1
+        cores = torch.get_num_threads()
     if all_cores and workload == "speaker_id":
         import multiprocessing as mp
         cores = os.cpu_count() or 1
