@@ -6,18 +6,17 @@
 // One CTA computes a 128 x NT output tile:
 //   * A operand (activations): all 256 threads gather the im2col tile from NHWC global memory,
 //     apply the preceding BatchNorm + ELU/ReLU on the fly, round to TF32 and store it to shared
-//     memory in the UMMA canonical K-major / no-swizzle layout
-//         [K-slab of 4 floats][row 0..127][16 bytes]          (LBO = 2048 B, SBO = 128 B)
-//     — a layout in which consecutive rows are consecutive 16-byte words, so the STS.128 stores are
-//     bank-conflict free.
+//     memory in the UMMA canonical K-major SWIZZLE_128B layout (128-byte rows, 16-byte chunks
+//     XORed with row%8).  A warp load covers 4 rows x 128 contiguous bytes (coalesced) and each
+//     quarter-warp STS.128 covers the eight swizzled chunks of one row (conflict free).
 //   * B operand (weights): pre-arranged on the host in the same slab layout and pre-rounded to
 //     TF32, so one TMA bulk copy (cp.async.bulk + mbarrier complete_tx) lands a whole
 //     [32 x NT] K-chunk, ready for the tensor core.
 //   * One elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=NT, K=8) four
 //     times per 32-wide K chunk; tcgen05.commit releases the smem stage (2-stage ring) and, after
 //     the last chunk, signals the epilogue.
-//   * Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) TMEM -> registers, + bias, + residual,
-//     128-bit stores.
+//   * Epilogue: tcgen05.ld TMEM -> registers, + bias, staged through the (now dead) operand
+//     buffers so the final stores (and residual loads) are fully coalesced 128-bit accesses.
 // Used for every conv / LSTM projection of both classifiers when the net runs in TF32 mode
 // (mmla_net_set_precision); the fp32 CUDA-core kernel in nets.cu is the bit-faithful path.
 #include <math.h>
@@ -72,7 +71,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 template <int NT>
 struct TcSmem {
-    alignas(128) unsigned char A[kTcStages][kAStageBytes];
+    // A stages: 128 rows x 128 B in the UMMA K-major SWIZZLE_128B layout (8-row x 128 B atoms, the
+    // 16-byte chunk index XORed with row%8).  B stages: no-swizzle slab layout as arranged on the
+    // host.  After the last MMA the A|B region is reused as the epilogue staging tile.
+    alignas(1024) unsigned char A[kTcStages][kAStageBytes];
     alignas(128) unsigned char B[kTcStages][8 * NT * 16];
     alignas(8) uint64_t full_b[kTcStages];
     alignas(8) uint64_t empty[kTcStages];
@@ -80,14 +82,27 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
+// UMMA descriptor for the SWIZZLE_128B K-major A tile (LBO unused = 1, SBO = 1024 B between 8-row atoms).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(1u) << 16;
+    d |= static_cast<uint64_t>((1024u >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;                       // descriptor version (sm_100)
+    d |= 2ull << 61;                       // layout type: SWIZZLE_128B
+    return d;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const float* __restrict__ wg) {
     constexpr int kCols = NT < 32 ? 32 : NT;                       // TMEM columns (power of two >= 32)
     constexpr uint32_t kBStage = 8 * NT * 16;
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TcSmem<NT>& s = *reinterpret_cast<TcSmem<NT>*>(smem_raw);
+    extern __shared__ unsigned char smem_dyn[];
+    // SWIZZLE_128B atoms need a 1024-byte aligned base; the launch reserves 1 KB of slack for this
+    TcSmem<NT>& s = *reinterpret_cast<TcSmem<NT>*>(
+        (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long m0 = static_cast<long long>(blockIdx.x) * 128;
     const int ntile = blockIdx.y;
@@ -113,106 +128,118 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
 
-    // A-gather bookkeeping: this thread always fills row `arow`, K offsets [ahalf*16, ahalf*16+16)
-    const int arow = tid & 127, ahalf = tid >> 7;
-    const long long am = m0 + arow;
-    const bool avalid = am < a.M;
-    int hi0 = 0, wi0 = 0;
-    long long xbase = 0;
-    if (avalid) {
-        const int hw = a.Ho * a.Wo;
-        const long long b = am / hw;
-        const int r = static_cast<int>(am - b * hw);
-        const int ho = r / a.Wo, wo = r - ho * a.Wo;
-        hi0 = ho * a.stride - a.pad_t;
-        wi0 = wo * a.stride - a.pad_l;
-        xbase = b * a.H * a.W * a.Cin;
+    // ---- A-gather bookkeeping -------------------------------------------------------------------
+    // Thread t owns the 16-byte chunk q = t&7 (4 consecutive K elements) of rows rb+32i, i = 0..3,
+    // so one warp load instruction covers 4 rows x 128 contiguous bytes (coalesced) and one warp
+    // STS.128 covers, per quarter-warp, the eight swizzled chunks of one row (conflict free).
+    const int q = tid & 7, rb = tid >> 3;
+    int hi0[4], wi0[4];
+    long long xb[4];
+    bool rv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long am = m0 + rb + 32 * i;
+        rv[i] = am < a.M;
+        hi0[i] = wi0[i] = 0;
+        xb[i] = 0;
+        if (rv[i]) {
+            const int hw = a.Ho * a.Wo;
+            const long long b = am / hw;
+            const int r = static_cast<int>(am - b * hw);
+            const int ho = r / a.Wo, wo = r - ho * a.Wo;
+            hi0[i] = ho * a.stride - a.pad_t;
+            wi0[i] = wo * a.stride - a.pad_l;
+            xb[i] = b * a.H * a.W * a.Cin;
+        }
     }
-    const bool fast = (a.Cin % 16 == 0) && !a.x_is_u8;
+    const bool fast = (a.Cin % 4 == 0) && !a.x_is_u8;             // a K-quad never straddles a filter tap
+    const bool rowrun = !fast && a.kh == 1 && a.stride == 1 && !a.pre_scale;   // stems: contiguous im2col rows
     const float* xf = static_cast<const float*>(a.x);
     const unsigned char* xu = static_cast<const unsigned char*>(a.x);
 
-    // kh == 1 convolutions (every Conv1D, and 1x1 Conv2D): the im2col row of a pixel is one
-    // contiguous run of the NHWC input, valid for k in [k_lo, k_hi) — no div/mod per element.
-    const bool rowrun = !fast && a.kh == 1 && a.stride == 1;
-    long long run_base = 0;
-    int k_lo = 0, k_hi = 0;
-    if (rowrun && avalid) {
-        run_base = xbase + (static_cast<long long>(hi0) * a.W + wi0) * a.Cin;
-        k_lo = max(0, -wi0) * a.Cin;
-        k_hi = min(min(a.kw, a.W - wi0) * a.Cin, a.K);
-    }
-
-    // The gather is split in two so the global loads of chunk kc+1 are in flight across the
-    // barrier + MMA issue of chunk kc: load_raw() only issues loads, finish() (BN + activation +
-    // TF32 rounding) runs one iteration later, just before the tile is stored to smem.
-    auto load_raw = [&](int kc, float4 (&raw)[4], int& meta) {
-        const int kb = kc * kTcBK + ahalf * 16;
-        meta = -1;                                            // -1: nothing to post-process (zeros / final)
+    // load_raw() only issues the global loads of a chunk; finish() (BN + activation + TF32
+    // rounding) runs one iteration later, so the loads fly across the barrier + MMA issue.
+    auto load_raw = [&](int kc, float4 (&raw)[4], int& chan) {
+        const int k = kc * kTcBK + 4 * q;
+        chan = -1;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) raw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fast) {
-            const int tap = kb / a.Cin, c0 = kb - tap * a.Cin;
-            const int ki = tap / a.kw, kj = tap - ki * a.kw;
-            const int hi = hi0 + ki, wi = wi0 + kj;
-            const bool inb = avalid && kb < a.K && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
-            if (inb) {
-                const float* src = xf + xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c0;
+            if (k < a.K) {
+                const int tap = k / a.Cin, c = k - tap * a.Cin;
+                const int ki = tap / a.kw, kj = tap - ki * a.kw;
+                chan = c;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const float4*>(src + 4 * j);
-                meta = c0;                                    // channel offset for the BN prologue
-            }
-        } else if (rowrun && !a.pre_scale) {
-            float e[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = kb + i;
-                e[i] = 0.f;
-                if (k >= k_lo && k < k_hi) e[i] = a.x_is_u8 ? static_cast<float>(xu[run_base + k]) : xf[run_base + k];
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) raw[j] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
-        } else {
-            float e[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int k = kb + i;
-                float v = 0.f;
-                if (avalid && k < a.K) {
-                    const int tap = k / a.Cin, c = k - tap * a.Cin;
-                    const int ki = tap / a.kw, kj = tap - ki * a.kw;
-                    const int hi = hi0 + ki, wi = wi0 + kj;
-                    if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
-                        const long long idx = xbase + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c;
-                        v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
-                        if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const int hi = hi0[i] + ki, wi = wi0[i] + kj;
+                    if (rv[i] && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
+                        raw[i] = *reinterpret_cast<const float4*>(xf + xb[i] + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c);
+                    else
+                        raw[i].x = __int_as_float(0x7fc00000);   // NaN marks "padding": stays zero after BN
                 }
-                e[i] = v;
             }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) raw[j] = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+            for (int i = 0; i < 4; ++i) {
+                float e[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = k + j;
+                    float v = 0.f;
+                    if (rv[i] && kk < a.K) {
+                        if (rowrun) {
+                            // kh == 1, stride 1: the im2col row is one contiguous run of the input
+                            const int wi = wi0[i] + kk / a.Cin;
+                            if (wi >= 0 && wi < a.W) {
+                                const long long idx = xb[i] + (static_cast<long long>(hi0[i]) * a.W + wi0[i]) * a.Cin + kk;
+                                v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
+                            }
+                        } else {
+                            const int tap = kk / a.Cin, c = kk - tap * a.Cin;
+                            const int ki = tap / a.kw, kj = tap - ki * a.kw;
+                            const int hi = hi0[i] + ki, wi = wi0[i] + kj;
+                            if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+                                const long long idx = xb[i] + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c;
+                                v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
+                                if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
+                            }
+                        }
+                    }
+                    e[j] = v;
+                }
+                raw[i] = make_float4(e[0], e[1], e[2], e[3]);
+            }
         }
     };
-    auto finish = [&](const float4 (&raw)[4], int meta, uint4 (&q)[4]) {
+    auto finish_store = [&](const float4 (&raw)[4], int chan, unsigned char* abase) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool bn = chan >= 0 && a.pre_scale;
+        if (bn) {
+            sc = *reinterpret_cast<const float4*>(a.pre_scale + chan);
+            sh = *reinterpret_cast<const float4*>(a.pre_shift + chan);
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 v = raw[j];
-            if (meta >= 0 && a.pre_scale) {
-                const float4 sc = *reinterpret_cast<const float4*>(a.pre_scale + meta + 4 * j);
-                const float4 sh = *reinterpret_cast<const float4*>(a.pre_shift + meta + 4 * j);
-                v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
-                v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
-                v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
-                v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
+        for (int i = 0; i < 4; ++i) {
+            float4 v = raw[i];
+            if (chan >= 0) {
+                if (__float_as_uint(v.x) == 0x7fc00000u) {
+                    v = make_float4(0.f, 0.f, 0.f, 0.f);                     // padding pixel
+                } else if (bn) {
+                    v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
+                    v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
+                    v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
+                    v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
+                }
             }
-            q[j] = make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
+            const int r = rb + 32 * i;
+            *reinterpret_cast<uint4*>(abase + r * 128 + ((q ^ (r & 7)) << 4)) =
+                make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
         }
     };
 
     float4 raw[4];
-    int meta;
-    load_raw(0, raw, meta);
+    int chan;
+    load_raw(0, raw, chan);
     for (int kc = 0; kc < nk; ++kc) {
         const int st = kc & 1;
         const int use = kc >> 1;
@@ -223,15 +250,9 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
             tma_bulk_g2s(&s.B[st][0], wg + (static_cast<long long>(ntile) * nk + kc) * (NT * kTcBK), kBStage,
                          &s.full_b[st]);
         }
-        {
-            uint4 q[4];
-            finish(raw, meta, q);
-            unsigned char* abase = &s.A[st][0] + (ahalf * 4) * 2048 + arow * 16;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(abase + j * 2048) = q[j];
-        }
+        finish_store(raw, chan, &s.A[st][0]);
         fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
-        if (kc + 1 < nk) load_raw(kc + 1, raw, meta);   // next chunk's loads fly across the barrier + MMAs
+        if (kc + 1 < nk) load_raw(kc + 1, raw, chan);   // next chunk's loads fly across the barrier + MMAs
         __syncthreads();
         if (tid == 0) {
             mbar_wait_or_trap(&s.full_b[st], static_cast<uint32_t>(use & 1));
@@ -240,7 +261,7 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
             const uint32_t b_addr = smem_u32(&s.B[st][0]);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = umma_desc(a_addr + kk * 2 * 2048, 2048, 128);
+                const uint64_t ad = umma_desc_sw128(a_addr + kk * 32);          // K advances 32 B inside the atom row
                 const uint64_t bd = umma_desc(b_addr + kk * 2 * (NT * 16), NT * 16, 128);
                 umma_tf32(tmem, ad, bd, kIdesc, (kc | kk) != 0 ? 1u : 0u);
             }
@@ -249,59 +270,68 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
         }
     }
 
-    // ---- epilogue: TMEM -> registers -> (+bias, +residual) -> global ---------------------------
-    // Residual / bias loads for a 16-column chunk are issued before the accumulator is read (the
-    // first chunk's even before the MMAs have finished), so their latency hides behind the wait.
+    // ---- epilogue: TMEM -> registers (+bias) -> smem staging -> coalesced (+residual) stores ----
+    // The operand stages are dead once the accumulator barrier fires, so they become a
+    // [128][HC+4] float staging tile (HC = columns per pass; +4 floats of padding keep the
+    // per-row STS.128 conflict free).  The write-out then moves whole 16-byte words with
+    // consecutive lanes on consecutive addresses; the residual is read the same way.
     {
-        constexpr int kColsPerWarp = NT >= 64 ? NT / 2 : NT;      // warps 4..7 take the upper half when NT >= 64
-        constexpr int kChunks = kColsPerWarp / 16;
+        constexpr int HC = NT > 64 ? 64 : NT;                     // columns staged per pass
+        constexpr int kPasses = NT / HC;
+        constexpr int kStride = HC + 4;                           // floats
+        static_assert(kStride * 128 * 4 <= kTcStages * (kAStageBytes + 8 * NT * 16), "staging tile must fit");
+        float* stg = reinterpret_cast<float*>(&s.A[0][0]);
         const int quarter = warp & 3;
-        const int chalf = warp >> 2;
-        const bool active = (NT >= 64 || chalf == 0);
-        const long long m = m0 + quarter * 32 + lane;
-        const bool mvalid = active && m < a.M;
-        const int colbase = chalf * kColsPerWarp;
-        float4 rres[4], rbias[4];
-        auto load_rb = [&](int c) {
-            const int n = n0 + colbase + 16 * c;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                rbias[j] = *reinterpret_cast<const float4*>(a.bias + n + 4 * j);
-                rres[j] = (mvalid && a.res) ? *reinterpret_cast<const float4*>(a.res + m * a.res_row_stride + n + 4 * j)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        if (active) load_rb(0);
+        const int chalf = warp >> 2;                              // warps 4..7 take the upper half of a pass
+        const int row = quarter * 32 + lane;
         mbar_wait_or_trap(&s.accum, 0u);
         tc_fence_after();
-        if (active) {
 #pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                const int col = colbase + 16 * c;
-                uint32_t r[16];
-                const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(col);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-                    "%14, %15}, [%16];\n"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float4 v[4];
+        for (int pass = 0; pass < kPasses; ++pass) {
+            constexpr int kColsPerWarp = HC >= 32 ? HC / 2 : HC;  // HC=16: only warps 0..3 read TMEM
+            const bool active = HC >= 32 || chalf == 0;
+            if (active) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    v[j].x = __uint_as_float(r[4 * j + 0]) + rbias[j].x + rres[j].x;
-                    v[j].y = __uint_as_float(r[4 * j + 1]) + rbias[j].y + rres[j].y;
-                    v[j].z = __uint_as_float(r[4 * j + 2]) + rbias[j].z + rres[j].z;
-                    v[j].w = __uint_as_float(r[4 * j + 3]) + rbias[j].w + rres[j].w;
-                }
-                if (c + 1 < kChunks) load_rb(c + 1);             // next chunk's loads overlap these stores
-                if (mvalid) {
-                    float* dst = a.y + m * a.N + n0 + col;
+                for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
+                    const int col = chalf * kColsPerWarp + c0;    // column within the pass
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                           static_cast<uint32_t>(pass * HC + col);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                        "%13, %14, %15}, [%16];\n"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                          "=r"(r[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const float* bias = a.bias + n0 + pass * HC + col;
+                    float* dst = stg + row * kStride + col;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = v[j];
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(bias + j);
+                        *reinterpret_cast<float4*>(dst + j) =
+                            make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                                        __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                    }
                 }
             }
+            __syncthreads();
+            constexpr int kQuadsPerRow = HC / 4;
+            for (int idx = tid; idx < 128 * kQuadsPerRow; idx += 256) {
+                const int r = idx / kQuadsPerRow, c4 = idx - r * kQuadsPerRow;
+                const long long m = m0 + r;
+                if (m < a.M) {
+                    float4 v = *reinterpret_cast<const float4*>(stg + r * kStride + 4 * c4);
+                    const int n = n0 + pass * HC + 4 * c4;
+                    if (a.res) {
+                        const float4 rr = *reinterpret_cast<const float4*>(a.res + m * a.res_row_stride + n);
+                        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+                    }
+                    *reinterpret_cast<float4*>(a.y + m * a.N + n) = v;
+                }
+            }
+            if (pass + 1 < kPasses) __syncthreads();              // staging tile is rewritten by the next pass
         }
     }
     tc_fence_before();
@@ -317,11 +347,11 @@ int launch_nt(const ConvArgs& a, const float* wg, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(sizeof(TcSmem<NT>))));
+                                             static_cast<int>(sizeof(TcSmem<NT>) + 1024)));
         attr_set = true;
     }
     const dim3 grid(static_cast<unsigned>((a.M + 127) / 128), static_cast<unsigned>(a.N / NT));
-    conv_tc_kernel<NT><<<grid, 256, sizeof(TcSmem<NT>), st>>>(a, wg);
+    conv_tc_kernel<NT><<<grid, 256, sizeof(TcSmem<NT>) + 1024, st>>>(a, wg);
     mmla_count_launch();
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
