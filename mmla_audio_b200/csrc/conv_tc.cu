@@ -133,23 +133,26 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
     // so one warp load instruction covers 4 rows x 128 contiguous bytes (coalesced) and one warp
     // STS.128 covers, per quarter-warp, the eight swizzled chunks of one row (conflict free).
     const int q = tid & 7, rb = tid >> 3;
-    int hi0[4], wi0[4];
-    long long xb[4];
+    // (the launcher guarantees M and the input element count fit in 31 bits: 32-bit index math)
+    int hi0[4], wi0[4], xb[4], klo[4], khi[4];
     bool rv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const long long am = m0 + rb + 32 * i;
-        rv[i] = am < a.M;
-        hi0[i] = wi0[i] = 0;
-        xb[i] = 0;
+        const int am = static_cast<int>(m0) + rb + 32 * i;
+        rv[i] = am < static_cast<int>(a.M);
+        hi0[i] = wi0[i] = xb[i] = klo[i] = khi[i] = 0;
         if (rv[i]) {
             const int hw = a.Ho * a.Wo;
-            const long long b = am / hw;
-            const int r = static_cast<int>(am - b * hw);
+            const int b = am / hw;
+            const int r = am - b * hw;
             const int ho = r / a.Wo, wo = r - ho * a.Wo;
             hi0[i] = ho * a.stride - a.pad_t;
             wi0[i] = wo * a.stride - a.pad_l;
             xb[i] = b * a.H * a.W * a.Cin;
+            // kh == 1, stride 1 convs: the im2col row is the contiguous input run
+            // [xb + (hi0*W + wi0)*Cin + k], valid for k in [klo, khi) (columns inside the image)
+            klo[i] = max(0, -wi0[i]) * a.Cin;
+            khi[i] = min(min(a.kw, a.W - wi0[i]) * a.Cin, a.K);
         }
     }
     const bool fast = (a.Cin % 4 == 0) && !a.x_is_u8;             // a K-quad never straddles a filter tap
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                 for (int i = 0; i < 4; ++i) {
                     const int hi = hi0[i] + ki, wi = wi0[i] + kj;
                     if (rv[i] && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
-                        raw[i] = *reinterpret_cast<const float4*>(xf + xb[i] + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c);
+                        raw[i] = *reinterpret_cast<const float4*>(xf + (xb[i] + (hi * a.W + wi) * a.Cin + c));
                     else
                         raw[i].x = __int_as_float(0x7fc00000);   // NaN marks "padding": stays zero after BN
                 }
@@ -186,20 +189,18 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                 for (int j = 0; j < 4; ++j) {
                     const int kk = k + j;
                     float v = 0.f;
-                    if (rv[i] && kk < a.K) {
-                        if (rowrun) {
-                            // kh == 1, stride 1: the im2col row is one contiguous run of the input
-                            const int wi = wi0[i] + kk / a.Cin;
-                            if (wi >= 0 && wi < a.W) {
-                                const long long idx = xb[i] + (static_cast<long long>(hi0[i]) * a.W + wi0[i]) * a.Cin + kk;
-                                v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
-                            }
-                        } else {
+                    if (rowrun) {
+                        if (kk >= klo[i] && kk < khi[i]) {
+                            const int idx = xb[i] + (hi0[i] * a.W + wi0[i]) * a.Cin + kk;
+                            v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
+                        }
+                    } else if (rv[i] && kk < a.K) {
+                        {
                             const int tap = kk / a.Cin, c = kk - tap * a.Cin;
                             const int ki = tap / a.kw, kj = tap - ki * a.kw;
                             const int hi = hi0[i] + ki, wi = wi0[i] + kj;
                             if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
-                                const long long idx = xb[i] + (static_cast<long long>(hi) * a.W + wi) * a.Cin + c;
+                                const int idx = xb[i] + (hi * a.W + wi) * a.Cin + c;
                                 v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
                                 if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
                             }
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
             for (int idx = tid; idx < 128 * kQuadsPerRow; idx += 256) {
                 const int r = idx / kQuadsPerRow, c4 = idx - r * kQuadsPerRow;
                 const long long m = m0 + r;
-                if (m < a.M) {
+                if (m < a.M) {   // (64-bit only for the final byte offsets)
                     float4 v = *reinterpret_cast<const float4*>(stg + r * kStride + 4 * c4);
                     const int n = n0 + pass * HC + 4 * c4;
                     if (a.res) {
@@ -393,6 +394,8 @@ void mmla_tc_arrange_weights(const float* w, int K, int N, float* out) {
 }
 
 int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st) {
+    MMLA_REQUIRE(a.M < (1LL << 31) - 256 && (a.M / (a.Ho * a.Wo) + 1) * a.H * a.W * a.Cin < (1LL << 31), MMLA_EUNSUP,
+                 "conv_tc: tensor too large for 32-bit indexing (reduce the micro-batch)");
     switch (mmla_tc_ntile(a.N)) {
         case 16: return launch_nt<16>(a, wg, st);
         case 32: return launch_nt<32>(a, wg, st);

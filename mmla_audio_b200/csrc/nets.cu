@@ -184,24 +184,28 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs a) {
 // small layer kernels
 // ---------------------------------------------------------------------------------------------
 // MaxPool 'same' with window (ph, pw), stride = window, NHWC; out-of-range taps are -inf.
-__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, long long B,
-                                                      int H, int W, int C, int ph, int pw, int Ho, int Wo) {
-    const long long total = B * Ho * Wo * C;
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int c = static_cast<int>(e % C);
-        long long r = e / C;
-        const int wo = static_cast<int>(r % Wo);
+// One thread per (output pixel, channel quad): 128-bit loads/stores, 32-bit index math.
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H,
+                                                      int W, int C, int ph, int pw, int Ho, int Wo) {
+    const int C4 = C >> 2;
+    const int total = B * Ho * Wo * C4;                              // < 2^31 (launcher checks)
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int c4 = e % C4;
+        int r = e / C4;
+        const int wo = r % Wo;
         r /= Wo;
-        const int ho = static_cast<int>(r % Ho);
-        const long long b = r / Ho;
-        float m = -INFINITY;
+        const int ho = r % Ho;
+        const int b = r / Ho;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         for (int i = 0; i < ph; ++i)
             for (int j = 0; j < pw; ++j) {
                 const int hi = ho * ph + i, wi = wo * pw + j;
-                if (hi < H && wi < W) m = fmaxf(m, x[((b * H + hi) * W + wi) * C + c]);
+                if (hi < H && wi < W) {
+                    const float4 v = *reinterpret_cast<const float4*>(x + (static_cast<long long>((b * H + hi) * W + wi) * C + 4 * c4));
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
             }
-        y[e] = m;
+        *reinterpret_cast<float4*>(y + static_cast<long long>(e) * 4) = m;
     }
 }
 
@@ -610,7 +614,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                 if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
                 if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st, tc))) return rc;
                 const int Ho = same_out(H, 2), Wo = same_out(W, 2), C = blk.conv2.cout;
-                maxpool_kernel<<<ew_grid(B * Ho * Wo * C), 256, 0, st>>>(Bf, A, B, H, W, C, 2, 2, Ho, Wo);
+                maxpool_kernel<<<ew_grid(B * Ho * Wo * C / 4), 256, 0, st>>>(Bf, A, static_cast<int>(B), H, W, C, 2, 2, Ho, Wo);
                 mmla_count_launch();
                 MMLA_CUDA_CHECK(cudaGetLastError());
                 if ((rc = launch_conv(blk.shortcut, X, 0, B, H, W, nullptr, ACT_NONE, A, C, Bf, st, tc))) return rc;
@@ -619,7 +623,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
             } else {
                 // speaker: x' = MaxPool1D(x); res = conv_k1_s2(x); out = conv2(..conv1(..x'..)) + res
                 const int Wo = same_out(W, 2), Cin = blk.conv1.cin;
-                maxpool_kernel<<<ew_grid(B * Wo * Cin), 256, 0, st>>>(X, A, B, 1, W, Cin, 1, 2, 1, Wo);
+                maxpool_kernel<<<ew_grid(B * Wo * Cin / 4), 256, 0, st>>>(X, A, static_cast<int>(B), 1, W, Cin, 1, 2, 1, Wo);
                 mmla_count_launch();
                 MMLA_CUDA_CHECK(cudaGetLastError());
                 if ((rc = launch_conv(blk.conv1, A, 0, B, 1, Wo, &blk.bn1, act_kind, nullptr, 0, Bf, st, tc))) return rc;
