@@ -343,6 +343,7 @@ struct MmlaNet {
     BnW final_bn;
     ConvW lstm_in[2];                     // [feat,1024] projection (bias = LSTM bias)
     ConvW lstm_rec[2];                    // [256,1024] recurrent (bias = zeros)
+    const float* lstm_rec_fused[2] = {nullptr, nullptr};   // chunk stream for lstm_fused_kernel
     const float* dense_k = nullptr;
     const float* dense_b = nullptr;
     int in_h = 0, in_w = 0, in_c = 0;     // per-clip input geometry
@@ -356,6 +357,11 @@ int mmla_tc_ntile(int n);
 long long mmla_tc_arranged_floats(int K, int N);
 void mmla_tc_arrange_weights(const float* w, int K, int N, float* out);
 int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st);
+// lstm_fused.cu
+long long mmla_lstm_arranged_floats();
+void mmla_lstm_arrange_weights(const float* U, float* out);
+int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
+                           float* h_b, float* c_f, float* c_b, long long B, int T, cudaStream_t st);
 
 namespace {
 
@@ -516,6 +522,13 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
         take_ptr(&pi.b, 1024);
         add_tc(pi, wi_src);
         add_tc(pr, wr_src);
+        if (rd.ok) {
+            while (stage.size() % 4) stage.push_back(0.f);
+            const long long off = static_cast<long long>(stage.size());
+            stage.resize(stage.size() + mmla_lstm_arranged_floats());
+            mmla_lstm_arrange_weights(wr_src, stage.data() + off);
+            fixes.push_back({&net->lstm_rec_fused[d], off});
+        }
         if (zero_bias_off < 0) {
             while (stage.size() % 4) stage.push_back(0.f);
             zero_bias_off = static_cast<long long>(stage.size());
@@ -545,7 +558,7 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
     // workspace plan (floats per clip): three rotating activation buffers + LSTM scratch
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const long long T = net->seq_len;
-    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 3 * 256;
+    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 4 * 256;
     net->micro = ov ? 128 : 4096;         // measured on B200: larger micro-batches win (launch/latency-bound layers)
     if (const char* e = getenv("MMLA_NET_MICRO")) {
         const int v = atoi(e);
@@ -591,7 +604,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         float* xp[2] = {seq + B * T * 128, seq + B * T * 128 + B * T * 1024};   // [B,T,1024] per direction
         float* z = xp[1] + B * T * 1024;                  // [B,1024] gate pre-activations
         float* hdir[2] = {z + B * 1024, z + B * 1024 + B * 256};   // final h of the fwd / bwd layer
-        float* cst = hdir[1] + B * 256;                   // [B,256] cell state
+        float* cst = hdir[1] + B * 256;                   // [B,256] cell state (x2 for the fused kernel)
 
         const void* xin = x_is_u8 ? static_cast<const void*>(static_cast<const unsigned char*>(x) + b0 * in_elems)
                                   : static_cast<const void*>(static_cast<const float*>(x) + b0 * in_elems);
@@ -646,7 +659,13 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         // BiLSTM(256): input projections for all steps, then the recurrence
         for (int d = 0; d < 2; ++d)
             if ((rc = launch_conv(net->lstm_in[d], seq, 0, B * T, 1, 1, nullptr, ACT_NONE, nullptr, 0, xp[d], st, tc))) return rc;
-        for (int d = 0; d < 2; ++d) {
+        if (tc) {
+            // one persistent launch: both directions, all time steps (lstm_fused.cu)
+            if ((rc = mmla_launch_lstm_fused(xp[0], xp[1], net->lstm_rec_fused[0], net->lstm_rec_fused[1], hdir[0], hdir[1],
+                                             cst, cst + B * 256, B, T, st)))
+                return rc;
+        }
+        for (int d = 0; d < 2 && !tc; ++d) {
             float* h = hdir[d];                            // updated in place: the recurrent GEMM of a
             for (int s = 0; s < T; ++s) {                  // step finishes before its gate kernel writes h
                 const int t = d == 0 ? s : T - 1 - s;     // backward layer walks t = T-1 .. 0
