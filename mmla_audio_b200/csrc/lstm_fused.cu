@@ -9,7 +9,7 @@
 //   * h_{t-1} [128 x 256] lives in shared memory as the tcgen05 A operand (eight 128x32 TF32
 //     sub-tiles, UMMA K-major SWIZZLE_128B);
 //   * the recurrent weights U [256 x 1024] are streamed every step from L2 by the TMA bulk-copy
-//     engine through a 2-stage ring of 32 KB chunks (host pre-arranged: gate columns regrouped so a
+//     engine through an 8-stage ring of 8 KB chunks, one per MMA (host pre-arranged: gate columns regrouped so a
 //     512-column accumulator pass holds i|f|c~|o for the same 128 units, TF32 pre-rounded);
 //   * z = h U accumulates in TMEM (512 fp32 columns = the whole tensor memory of the SM), two
 //     passes of 128 units per step, tcgen05.mma M=128 N=256 K=8;
@@ -28,15 +28,16 @@ namespace {
 constexpr int kU = 256;                     // LSTM units
 constexpr int kRows = 128;                  // clips per CTA
 constexpr int kSubTile = 128 * 128;         // bytes of one 128x32 TF32 sub-tile
-constexpr int kBChunkFloats = 8 * 256 * 4;  // one weight chunk: 8 K-slabs x 256 columns x 4
-constexpr int kBChunkBytes = kBChunkFloats * 4;
-constexpr int kChunksPerStep = 32;          // 2 halves x 2 N-tiles x 8 K-chunks
+constexpr int kBChunkFloats = 2 * 256 * 4;  // one weight chunk = one MMA: 2 K-slabs (K=8) x 256 columns x 4
+constexpr int kBChunkBytes = kBChunkFloats * 4;   // 8 KB
+constexpr int kChunksPerStep = 128;         // 2 halves x 2 N-tiles x 8 K-sub-tiles x 4 MMAs
+constexpr int kStages = 8;                  // deep ring of small chunks: 7 TMA copies in flight hide L2 latency
 
 struct LstmSmem {
     alignas(1024) unsigned char H[8][kSubTile];          // h_{t-1}, SWIZZLE_128B K-major
-    alignas(128) unsigned char Bst[2][kBChunkBytes];     // weight ring (no-swizzle slab layout)
-    alignas(8) uint64_t full[2];
-    alignas(8) uint64_t empty[2];
+    alignas(128) unsigned char Bst[kStages][kBChunkBytes];   // weight ring (no-swizzle slab layout)
+    alignas(8) uint64_t full[kStages];
+    alignas(8) uint64_t empty[kStages];
     alignas(8) uint64_t accum;
     uint32_t tmem_base;
 };
@@ -82,8 +83,10 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // f32 += tf32 x tf32, M=128, N=256
 
     if (tid == 0) {
-        mbar_init(&s.full[0], 1); mbar_init(&s.full[1], 1);
-        mbar_init(&s.empty[0], 1); mbar_init(&s.empty[1], 1);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
         mbar_init(&s.accum, 1);
         mbar_fence_init();
     }
@@ -106,36 +109,57 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
     long long produced = 0, consumed = 0;            // weight chunks issued / used (thread 0 only)
     const long long total_chunks = static_cast<long long>(T > 1 ? T - 1 : 0) * kChunksPerStep;
 
-    // gate math for 8 units starting at `u` (absolute unit index) given recurrent pre-activations z*
-    auto cell8 = [&](int t, int u, const float (&zi)[8], const float (&zf)[8], const float (&zc)[8], const float (&zo)[8],
-                     bool first) {
-        if (!row_ok) return;
-        const float* xr = xp + (static_cast<long long>(brow) * T + t) * 1024 + u;
-        float* cp = cg + static_cast<long long>(brow) * kU + u;
-        float* hp = hg + static_cast<long long>(brow) * kU + u;
-        float xi[8], xf[8], xc[8], xo[8], cv[8], hv[8];
+    // One 16-unit slice of the cell update for this thread's row.  All global loads (four gate
+    // slices of xp and the old cell state: 20 x 128-bit per thread) are issued before the first
+    // TMEM read, so their latency overlaps; gates are then consumed one TMEM slice at a time.
+    auto ld16 = [&](uint32_t taddr, float (&z)[16]) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+            "[%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-            *reinterpret_cast<float4*>(&xi[j]) = *reinterpret_cast<const float4*>(xr + j);
-            *reinterpret_cast<float4*>(&xf[j]) = *reinterpret_cast<const float4*>(xr + 256 + j);
-            *reinterpret_cast<float4*>(&xc[j]) = *reinterpret_cast<const float4*>(xr + 512 + j);
-            *reinterpret_cast<float4*>(&xo[j]) = *reinterpret_cast<const float4*>(xr + 768 + j);
-            if (first) *reinterpret_cast<float4*>(&cv[j]) = make_float4(0.f, 0.f, 0.f, 0.f);
-            else *reinterpret_cast<float4*>(&cv[j]) = __ldcg(reinterpret_cast<const float4*>(cp + j));
+        for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(r[j]);
+    };
+    auto cell16 = [&](int t, int half, int uoff, bool first) {      // uoff: unit offset inside the half
+        const int u = 128 * half + uoff;
+        const long long rrow = row_ok ? brow : 0;                     // masked rows read row 0, never write
+        const float* xr = xp + (rrow * T + t) * 1024 + u;
+        float* cp = cg + rrow * kU + u;
+        float* hp = hg + rrow * kU + u;
+        float xi[16], xf[16], xc[16], xo[16], cv[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            *reinterpret_cast<float4*>(&xi[j]) = __ldcg(reinterpret_cast<const float4*>(xr + j));
+            *reinterpret_cast<float4*>(&xc[j]) = __ldcg(reinterpret_cast<const float4*>(xr + 512 + j));
+            *reinterpret_cast<float4*>(&xf[j]) = __ldcg(reinterpret_cast<const float4*>(xr + 256 + j));
+            *reinterpret_cast<float4*>(&xo[j]) = __ldcg(reinterpret_cast<const float4*>(xr + 768 + j));
+            *reinterpret_cast<float4*>(&cv[j]) =
+                first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(cp + j));
         }
+        const uint32_t tbase = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(uoff);
+        float z[16], pr[16];
+        if (!first) ld16(tbase, z);                                   // i
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float ig = fast_sigmoid(zi[j] + xi[j]);
-            const float fg = fast_sigmoid(zf[j] + xf[j]);
-            const float gg = fast_tanh(zc[j] + xc[j]);
-            const float og = fast_sigmoid(zo[j] + xo[j]);
-            cv[j] = fg * cv[j] + ig * gg;
-            hv[j] = og * fast_tanh(cv[j]);
-        }
+        for (int j = 0; j < 16; ++j) pr[j] = fast_sigmoid((first ? 0.f : z[j]) + xi[j]);
+        if (!first) ld16(tbase + 256, z);                             // c~
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-            *reinterpret_cast<float4*>(cp + j) = *reinterpret_cast<float4*>(&cv[j]);
-            *reinterpret_cast<float4*>(hp + j) = *reinterpret_cast<float4*>(&hv[j]);
+        for (int j = 0; j < 16; ++j) pr[j] *= fast_tanh((first ? 0.f : z[j]) + xc[j]);
+        if (!first) ld16(tbase + 128, z);                             // f
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cv[j] = fast_sigmoid((first ? 0.f : z[j]) + xf[j]) * cv[j] + pr[j];
+        if (!first) ld16(tbase + 384, z);                             // o
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pr[j] = fast_sigmoid((first ? 0.f : z[j]) + xo[j]) * fast_tanh(cv[j]);
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                *reinterpret_cast<float4*>(cp + j) = *reinterpret_cast<float4*>(&cv[j]);
+                *reinterpret_cast<float4*>(hp + j) = *reinterpret_cast<float4*>(&pr[j]);
+            }
         }
     };
 
@@ -156,8 +180,8 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
     };
 
     auto issue_weight_chunk = [&]() {                 // thread 0: next chunk of the (periodic) weight stream
-        const int stg = static_cast<int>(produced & 1);
-        const long long use = produced >> 1;
+        const int stg = static_cast<int>(produced % kStages);
+        const long long use = produced / kStages;
         if (use > 0) wait_or_trap(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(&s.full[stg], kBChunkBytes);
@@ -165,73 +189,49 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
         ++produced;
     };
 
-    if (tid == 0 && total_chunks > 0) issue_weight_chunk();      // weights start flowing during step 0
+    if (tid == 0)                                                 // weights start flowing during step 0
+        while (produced < total_chunks && produced < kStages) issue_weight_chunk();
 
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? step : T - 1 - step;
         if (step == 0) {
             // h0 = c0 = 0: pre-activations are the input projection alone
-            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int half = 0; half < 2; ++half)
-                for (int u = 0; u < 64; u += 8) cell8(t, 128 * half + ubase + u, zero, zero, zero, zero, true);
+                for (int uo = 0; uo < 64; uo += 16) cell16(t, half, ubase + uo, true);
         } else {
             for (int half = 0; half < 2; ++half) {
                 if (tid == 0) {
-                    // 16 chunks: N-tile j (0: i|f, 1: c~|o) x K-chunk kc
+                    // 64 MMAs: N-tile j (0: i|f, 1: c~|o) x K sub-tile kc x 4 K-steps, one 8 KB chunk each
                     for (int j = 0; j < 2; ++j)
-                        for (int kc = 0; kc < 8; ++kc) {
-                            if (produced < total_chunks) issue_weight_chunk();      // stay one chunk ahead
-                            const int stg = static_cast<int>(consumed & 1);
-                            wait_or_trap(&s.full[stg], static_cast<uint32_t>((consumed >> 1) & 1));
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t a_addr = smem_u32(&s.H[kc][0]);
-                            const uint32_t b_addr = smem_u32(&s.Bst[stg][0]);
-#pragma unroll
+                        for (int kc = 0; kc < 8; ++kc)
                             for (int kk = 0; kk < 4; ++kk) {
-                                const uint64_t ad = desc_sw128(a_addr + kk * 32);
-                                const uint64_t bd = desc_noswz(b_addr + kk * 2 * (256 * 16), 256 * 16, 128);
+                                while (produced < total_chunks && produced - consumed < kStages) issue_weight_chunk();
+                                const int stg = static_cast<int>(consumed % kStages);
+                                wait_or_trap(&s.full[stg], static_cast<uint32_t>((consumed / kStages) & 1));
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                const uint64_t ad = desc_sw128(smem_u32(&s.H[kc][0]) + kk * 32);
+                                const uint64_t bd = desc_noswz(smem_u32(&s.Bst[stg][0]), 256 * 16, 128);
                                 const uint32_t acc = (kc | kk) != 0 ? 1u : 0u;
                                 asm volatile(
                                     "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + j * 256),
                                     "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
                                     : "memory");
+                                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                                 smem_u32(&s.empty[stg]))
+                                             : "memory");
+                                ++consumed;
                             }
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                                             smem_u32(&s.empty[stg]))
-                                         : "memory");
-                            ++consumed;
-                        }
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      smem_u32(&s.accum))
                                  : "memory");
+                    while (produced < total_chunks && produced - consumed < kStages) issue_weight_chunk();   // refill
                 }
                 wait_or_trap(&s.accum, accum_phase);
                 accum_phase ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // epilogue of this half: TMEM columns [0,128) i, [128,256) f, [256,384) c~, [384,512) o
-                for (int u = 0; u < 64; u += 8) {
-                    uint32_t ri[8], rf[8], rc[8], ro[8];
-                    const uint32_t tbase = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(ubase + u);
-#define LD8(dst, col)                                                                                              \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"                  \
-                 : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]), "=r"(dst[4]), "=r"(dst[5]), "=r"(dst[6]), \
-                   "=r"(dst[7])                                                                                     \
-                 : "r"(tbase + (col)))
-                    LD8(ri, 0);
-                    LD8(rf, 128);
-                    LD8(rc, 256);
-                    LD8(ro, 384);
-#undef LD8
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float zi[8], zf[8], zc[8], zo[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        zi[j] = __uint_as_float(ri[j]); zf[j] = __uint_as_float(rf[j]);
-                        zc[j] = __uint_as_float(rc[j]); zo[j] = __uint_as_float(ro[j]);
-                    }
-                    cell8(t, 128 * half + ubase + u, zi, zf, zc, zo, false);
-                }
+                for (int uo = 0; uo < 64; uo += 16) cell16(t, half, ubase + uo, false);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();                       // TMEM drained before the next half's MMAs overwrite it
             }
@@ -251,27 +251,28 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
 
 // Host: arrange U [256][1024] (Keras recurrent kernel, columns i|f|c|o) into the chunk stream the
 // kernel consumes: chunk (half, j, kc) -> [8 slabs][256 n][4], n<128: gate 2j, else gate 2j+1,
-// unit = 128*half + (n&127); TF32-rounded.  out: 32 x 8192 floats.
+// unit = 128*half + (n&127); TF32-rounded.  out: 128 chunks x 2048 floats (one MMA each).
 long long mmla_lstm_arranged_floats() { return static_cast<long long>(kChunksPerStep) * kBChunkFloats; }
 void mmla_lstm_arrange_weights(const float* U, float* out) {
     for (int half = 0; half < 2; ++half)
         for (int j = 0; j < 2; ++j)
-            for (int kc = 0; kc < 8; ++kc) {
-                float* chunk = out + (static_cast<long long>((half * 2 + j) * 8 + kc)) * kBChunkFloats;
-                for (int slab = 0; slab < 8; ++slab)
-                    for (int n = 0; n < 256; ++n)
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = kc * 32 + slab * 4 + e;
-                            const int gate = 2 * j + (n >= 128 ? 1 : 0);
-                            const int unit = 128 * half + (n & 127);
-                            float v = U[static_cast<long long>(k) * 1024 + gate * 256 + unit];
-                            uint32_t u;
-                            memcpy(&u, &v, 4);
-                            if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & ~0x1FFFu;
-                            memcpy(&v, &u, 4);
-                            chunk[(slab * 256 + n) * 4 + e] = v;
-                        }
-            }
+            for (int kc = 0; kc < 8; ++kc)
+                for (int kk = 0; kk < 4; ++kk) {
+                    float* chunk = out + (static_cast<long long>(((half * 2 + j) * 8 + kc) * 4 + kk)) * kBChunkFloats;
+                    for (int slab = 0; slab < 2; ++slab)
+                        for (int n = 0; n < 256; ++n)
+                            for (int e = 0; e < 4; ++e) {
+                                const int k = kc * 32 + kk * 8 + slab * 4 + e;
+                                const int gate = 2 * j + (n >= 128 ? 1 : 0);
+                                const int unit = 128 * half + (n & 127);
+                                float v = U[static_cast<long long>(k) * 1024 + gate * 256 + unit];
+                                uint32_t u;
+                                memcpy(&u, &v, 4);
+                                if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & ~0x1FFFu;
+                                memcpy(&v, &u, 4);
+                                chunk[(slab * 256 + n) * 4 + e] = v;
+                            }
+                }
 }
 
 int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
