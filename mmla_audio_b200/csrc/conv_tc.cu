@@ -245,8 +245,7 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
         const int st = kc & 1;
         const int use = kc >> 1;
         if (kc >= kTcStages) mbar_wait_or_trap(&s.empty[st], static_cast<uint32_t>((use - 1) & 1));   // MMAs of kc-2 done
-        if (tid == 0) {
-            fence_proxy_async_smem();
+        if (tid == 0) {   // (no proxy fence: B stages are only ever touched by the async proxy)
             mbar_arrive_expect_tx(&s.full_b[st], kBStage);
             tma_bulk_g2s(&s.B[st][0], wg + (static_cast<long long>(ntile) * nk + kc) * (NT * kTcBK), kBStage,
                          &s.full_b[st]);

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
         const int stg = static_cast<int>(produced % kStages);
         const long long use = produced / kStages;
         if (use > 0) wait_or_trap(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
-        fence_proxy_async_smem();
+        // (no proxy fence: the ring is written by TMA and read by the tensor core — async proxy only)
         mbar_arrive_expect_tx(&s.full[stg], kBChunkBytes);
         tma_bulk_g2s(&s.Bst[stg][0], wr + (produced % kChunksPerStep) * kBChunkFloats, kBChunkBytes, &s.full[stg]);
         ++produced;
