@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
             tma_bulk_g2s(&s.B[st][0], wg + (static_cast<long long>(ntile) * nk + kc) * (NT * kTcBK), kBStage,
                          &s.full_b[st]);
         }
+        if (warp == 0) __syncwarp();
         finish_store(raw, chan, &s.A[st][0]);
         fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
         if (kc + 1 < nk) load_raw(kc + 1, raw, chan);   // next chunk's loads fly across the barrier + MMAs
@@ -268,6 +269,9 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
             umma_commit(&s.empty[st]);                       // frees this smem stage when the MMAs retire
             if (kc == nk - 1) umma_commit(&s.accum);         // accumulator complete
         }
+        // keep warp 0 converged: lanes 1..31 must not run ahead into the next blocking mbarrier
+        // wait while lane 0 is still issuing (a suspended warp stalls its own issuing lane)
+        if (warp == 0) __syncwarp();
     }
 
     // ---- epilogue: TMEM -> registers (+bias) -> smem staging -> coalesced (+residual) stores ----

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
 
     if (tid == 0)                                                 // weights start flowing during step 0
         while (produced < total_chunks && produced < kStages) issue_weight_chunk();
+    if (warp == 0) __syncwarp();
 
     for (int step = 0; step < T; ++step) {
         const int t = dir == 0 ? step : T - 1 - step;
@@ -200,6 +201,8 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
                 for (int uo = 0; uo < 64; uo += 16) cell16(t, half, ubase + uo, true);
         } else {
             for (int half = 0; half < 2; ++half) {
+                // Warp 0 stays converged around its issuing lane: if lanes 1..31 ran ahead into the
+                // blocking mbarrier wait below, the suspended warp would stall lane 0's issue loop.
                 if (tid == 0) {
                     // 64 MMAs: N-tile j (0: i|f, 1: c~|o) x K sub-tile kc x 4 K-steps, one 8 KB chunk each
                     for (int j = 0; j < 2; ++j)
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
                                  : "memory");
                     while (produced < total_chunks && produced - consumed < kStages) issue_weight_chunk();   // refill
                 }
+                if (warp == 0) __syncwarp();
                 wait_or_trap(&s.accum, accum_phase);
                 accum_phase ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
