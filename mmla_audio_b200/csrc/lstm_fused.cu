@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
     };
 
     if (tid == 0)                                                 // weights start flowing during step 0
-        while (produced < total_chunks && produced < kStages) issue_weight_chunk();
+        while (produced < total_chunks && produced < kStages - 2) issue_weight_chunk();
     if (warp == 0) __syncwarp();
 
     for (int step = 0; step < T; ++step) {
@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
                     for (int j = 0; j < 2; ++j)
                         for (int kc = 0; kc < 8; ++kc)
                             for (int kk = 0; kk < 4; ++kk) {
-                                while (produced < total_chunks && produced - consumed < kStages) issue_weight_chunk();
+                                // refill lags two slots behind the ring size so the slot being re-armed
+                                // belongs to an MMA committed two iterations ago (never blocks on a fresh one)
+                                while (produced < total_chunks && produced - consumed < kStages - 2) issue_weight_chunk();
                                 const int stg = static_cast<int>(consumed % kStages);
                                 wait_or_trap(&s.full[stg], static_cast<uint32_t>((consumed / kStages) & 1));
                                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -228,7 +230,6 @@ __global__ void __launch_bounds__(256, 1) lstm_fused_kernel(const LstmArgs a) {
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                                      smem_u32(&s.accum))
                                  : "memory");
-                    while (produced < total_chunks && produced - consumed < kStages) issue_weight_chunk();   // refill
                 }
                 if (warp == 0) __syncwarp();
                 wait_or_trap(&s.accum, accum_phase);
