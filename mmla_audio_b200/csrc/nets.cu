@@ -357,6 +357,10 @@ int mmla_tc_ntile(int n);
 long long mmla_tc_arranged_floats(int K, int N);
 void mmla_tc_arrange_weights(const float* w, int K, int N, float* out);
 int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st);
+// resunit_fused.cu
+int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int C, const float* bn1_scale,
+                              const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
+                              const float* bn2_shift, const float* w2, const float* b2, cudaStream_t st);
 // lstm_fused.cu
 long long mmla_lstm_arranged_floats();
 void mmla_lstm_arrange_weights(const float* U, float* out);
@@ -617,7 +621,13 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
             float* X = buf[cur];
             float* A = buf[(cur + 1) % 3];
             float* Bf = buf[(cur + 2) % 3];
-            if (!blk.pool) {
+            if (!blk.pool && tc && !ov && blk.conv1.k_tc && blk.conv2.k_tc) {
+                // speaker plain unit, tensor-core mode: one fused kernel (resunit_fused.cu)
+                if ((rc = mmla_launch_resunit_fused(X, A, B, W, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift, blk.conv1.k_tc,
+                                                    blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc, blk.conv2.b, st)))
+                    return rc;
+                cur = (cur + 1) % 3;
+            } else if (!blk.pool) {
                 // out = conv2(act(bn2(conv1(act(bn1(x)))))) + x
                 if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
                 if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, X, blk.conv2.cout, Bf, st, tc))) return rc;

@@ -1,0 +1,309 @@
+// Fused 1-D residual unit for sm_100a (speaker classifier, TF32 tensor-core mode):
+//
+//     y = x + Conv1D_k3( ReLU(BN2( Conv1D_k3( ReLU(BN1(x)) ) )) )        (no pooling, Cin == Cout == C)
+//
+// — `res_unit(x, filters)` of SpeakerIdentification/scripts/speaker_identification.py:168-190.
+//
+// The im2col expansion never exists.  One CTA owns a 128-row tile = G = 128/T whole clips with rows
+// interleaved time-major (row = t*G + g), so that a filter tap is a UNIFORM shift of G rows:
+//   1. x is read once (coalesced), BN1 + ReLU + TF32 rounding applied once per element, and stored
+//      as the tcgen05 A operand in the UMMA K-major no-swizzle "slab" layout
+//          [channel quad][row][16 B]      (rows 16 B apart, G zero halo rows at both ends);
+//   2. conv1 = 3 taps x C/8 tcgen05.mma (M=128, N=C, K=8): the A descriptor of tap j simply starts
+//      G*j rows further down the same buffer — Keras 'same' zero padding is the halo rows;
+//   3. epilogue 1 (TMEM -> +bias -> BN2 -> ReLU -> TF32) writes the intermediate straight into a
+//      second slab buffer; conv2 runs from it the same way;
+//   4. epilogue 2 stages the accumulator through shared memory and writes y = acc + bias + x with
+//      coalesced 128-bit accesses (x re-read from L2).
+// Weights stream through a 4-stage TMA ring (dedicated producer warp), MMAs are issued by a
+// dedicated warp, warps 0..7 load / transform / run the epilogues.  HBM traffic per unit: x in,
+// y out — versus five activation tensors and two 3x im2col gathers for the unfused pair.
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int kRtot = 137;                 // rows per slab: 128 + 2*G halo (G <= 4), == 1 mod 8 (bank-friendly)
+constexpr int kStagesRU = 4;
+constexpr int kEpi = 256;
+constexpr int kThreadsRU = kEpi + 64;
+
+struct ResUnitArgs {
+    const float* x;
+    float* y;
+    const float* bn1_scale; const float* bn1_shift;
+    const float* bn2_scale; const float* bn2_shift;
+    const float* w1; const float* w2;      // conv_tc-arranged K-chunk streams ([K/32][8 slabs][C][4])
+    const float* b1; const float* b2;
+    int B, T, G;
+};
+
+template <int C>
+struct RuSmem {
+    alignas(128) unsigned char a1[(C / 4) * kRtot * 16];       // ReLU(BN1(x)), later the output staging tile
+    alignas(128) unsigned char a2[(C / 4) * kRtot * 16];       // ReLU(BN2(conv1))
+    alignas(128) unsigned char ring[kStagesRU][8 * C * 16];    // weight chunks: 32 K x C
+    alignas(8) uint64_t full[kStagesRU];
+    alignas(8) uint64_t empty[kStagesRU];
+    alignas(8) uint64_t a_ready[2];                            // operand buffer written   (epilogue -> MMA)
+    alignas(8) uint64_t tfull[2];                              // accumulator complete     (MMA -> epilogue)
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t ru_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void ru_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void ru_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ru_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint64_t ru_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void ru_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnitArgs a) {
+    constexpr int kQuads = C / 4;
+    constexpr int kChunks = 3 * C / 32;                          // K-chunks per conv (K = 3*C)
+    constexpr uint32_t kChunkBytes = 8 * C * 16;
+    constexpr int kCols = 2 * C < 32 ? 32 : 2 * C;               // two accumulators side by side
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(C >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);
+    extern __shared__ unsigned char smem_dyn[];
+    RuSmem<C>& s = *reinterpret_cast<RuSmem<C>*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~static_cast<uintptr_t>(127));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = a.G, T = a.T;
+    const int clip0 = blockIdx.x * G;
+
+    if (tid == 0) {
+        for (int i = 0; i < kStagesRU; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s.a_ready[i], 1);
+            mbar_init(&s.tfull[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
+                     "r"(static_cast<uint32_t>(kCols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s.tmem_base;
+
+    if (warp == 8) {
+        // ================= TMA producer: conv1 then conv2 weight chunks =================
+        if (lane == 0) {
+            for (int g = 0; g < 2 * kChunks; ++g) {
+                const int stg = g % kStagesRU, use = g / kStagesRU;
+                if (use > 0) ru_wait(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
+                const float* src = (g < kChunks ? a.w1 + static_cast<long long>(g) * (8 * C * 4)
+                                                : a.w2 + static_cast<long long>(g - kChunks) * (8 * C * 4));
+                mbar_arrive_expect_tx(&s.full[stg], kChunkBytes);
+                tma_bulk_g2s(&s.ring[stg][0], src, kChunkBytes, &s.full[stg]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int g = 0;
+            for (int conv = 0; conv < 2; ++conv) {
+                ru_wait(&s.a_ready[conv], 0u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t abuf = smem_u32(conv == 0 ? &s.a1[0] : &s.a2[0]);
+                for (int ch = 0; ch < kChunks; ++ch, ++g) {
+                    const int stg = g % kStagesRU;
+                    ru_wait(&s.full[stg], static_cast<uint32_t>((g / kStagesRU) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int k0 = ch * 32;                      // K index = tap*C + channel
+                    const int tap = k0 / C, c0 = k0 - tap * C;
+                    const uint32_t b_addr = smem_u32(&s.ring[stg][0]);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        // A: slabs (c0/4 + 2kk, +1), rows shifted by tap*G (row G*1 = first real row)
+                        const uint32_t a_addr = abuf + (((c0 >> 2) + 2 * kk) * kRtot + tap * G) * 16;
+                        const uint64_t ad = ru_desc(a_addr, kRtot * 16, 128);
+                        const uint64_t bd = ru_desc(b_addr + kk * 2 * (C * 16), C * 16, 128);
+                        const uint32_t acc = (ch | kk) != 0 ? 1u : 0u;
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + conv * C),
+                            "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                            : "memory");
+                    }
+                    ru_commit(&s.empty[stg]);
+                }
+                ru_commit(&s.tfull[conv]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= warps 0..7: load/transform, epilogues =================
+        // zero the halo rows (rows [0,G) and [G+128, G+128+G)) of both operand buffers
+        for (int i = tid; i < 2 * kQuads * 2 * G; i += kEpi) {
+            const int buf = i / (kQuads * 2 * G), r = i % (kQuads * 2 * G);
+            const int qd = r / (2 * G), h = r % (2 * G);
+            const int row = h < G ? h : 128 + h;                 // h-G+G+128
+            unsigned char* base = buf == 0 ? &s.a1[0] : &s.a2[0];
+            *reinterpret_cast<uint4*>(base + (qd * kRtot + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // ---- x -> ReLU(BN1(x)) -> TF32 -> a1 (lanes run over channel quads: coalesced loads) ----
+        {
+            constexpr int kRowsPerPass = kEpi / kQuads;           // rows covered by 256 threads at once
+            const int qd = tid % kQuads, rsub = tid / kQuads;
+            const float4 sc = *reinterpret_cast<const float4*>(a.bn1_scale + 4 * qd);
+            const float4 sh = *reinterpret_cast<const float4*>(a.bn1_shift + 4 * qd);
+#pragma unroll 4
+            for (int r = rsub; r < 128; r += kRowsPerPass) {
+                const int t = r / G, g = r - t * G;              // row = t*G + g
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (clip0 + g < a.B) {
+                    v = *reinterpret_cast<const float4*>(a.x + (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd);
+                    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+                    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+                    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+                    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+                }
+                *reinterpret_cast<uint4*>(&s.a1[0] + (qd * kRtot + G + r) * 16) =
+                    make_uint4(ru_tf32(v.x), ru_tf32(v.y), ru_tf32(v.z), ru_tf32(v.w));
+            }
+        }
+        fence_proxy_async_smem();
+        ru_epi_sync();
+        if (tid == 0) ru_arrive(&s.a_ready[0]);
+
+        // TMEM lane = tile row; warps 0..3 take the lower half of the columns, warps 4..7 the upper
+        const int row = 32 * (warp & 3) + lane;
+        constexpr int kColsPerWarp = C / 2;
+        const int cbase = (warp >> 2) * kColsPerWarp;
+        auto ld16 = [&](uint32_t taddr, float (&z)[16]) {
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                "%15}, [%16];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(r[j]);
+        };
+
+        // ---- epilogue 1: conv1 accumulator -> +b1 -> BN2 -> ReLU -> TF32 -> a2 -------------------
+        ru_wait(&s.tfull[0], 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
+            const int col = cbase + c0;
+            float z[16];
+            ld16(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(col), z);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(a.b1 + col + j);
+                const float4 sc = *reinterpret_cast<const float4*>(a.bn2_scale + col + j);
+                const float4 sh = *reinterpret_cast<const float4*>(a.bn2_shift + col + j);
+                const float v0 = fmaxf(fmaf(z[j + 0] + bv.x, sc.x, sh.x), 0.f);
+                const float v1 = fmaxf(fmaf(z[j + 1] + bv.y, sc.y, sh.y), 0.f);
+                const float v2 = fmaxf(fmaf(z[j + 2] + bv.z, sc.z, sh.z), 0.f);
+                const float v3 = fmaxf(fmaf(z[j + 3] + bv.w, sc.w, sh.w), 0.f);
+                *reinterpret_cast<uint4*>(&s.a2[0] + (((col + j) >> 2) * kRtot + G + row) * 16) =
+                    make_uint4(ru_tf32(v0), ru_tf32(v1), ru_tf32(v2), ru_tf32(v3));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        fence_proxy_async_smem();
+        ru_epi_sync();
+        if (tid == 0) ru_arrive(&s.a_ready[1]);
+
+        // ---- epilogue 2: conv2 accumulator + b2 -> staging (operand buffers are dead) -> y = . + x ----
+        constexpr int kStride = C + 4;                            // floats per staged row (conflict-free STS.128)
+        static_assert(kStride * 128 * 4 <= 2 * (C / 4) * kRtot * 16, "staging tile must fit in a1|a2");
+        float* stg = reinterpret_cast<float*>(&s.a1[0]);          // spans a1 and (contiguous) a2: both are dead now
+        ru_wait(&s.tfull[1], 0u);                                 // every MMA reading a1 / a2 has retired
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
+            const int col = cbase + c0;
+            float z[16];
+            ld16(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(C + col), z);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(a.b2 + col + j);
+                *reinterpret_cast<float4*>(stg + row * kStride + col + j) =
+                    make_float4(z[j] + bv.x, z[j + 1] + bv.y, z[j + 2] + bv.z, z[j + 3] + bv.w);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        ru_epi_sync();
+        for (int idx = tid; idx < 128 * kQuads; idx += kEpi) {
+            const int r = idx / kQuads, qd = idx - r * kQuads;
+            const int t = r / G, g = r - t * G;
+            if (clip0 + g < a.B) {
+                const long long off = (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd;
+                float4 v = *reinterpret_cast<const float4*>(stg + r * kStride + 4 * qd);
+                const float4 xr = *reinterpret_cast<const float4*>(a.x + off);
+                v.x += xr.x; v.y += xr.y; v.z += xr.z; v.w += xr.w;
+                *reinterpret_cast<float4*>(a.y + off) = v;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(static_cast<uint32_t>(kCols))
+                     : "memory");
+}
+
+template <int C>
+int launch_ru(const ResUnitArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    const int smem = static_cast<int>(sizeof(RuSmem<C>) + 128);
+    if (!attr_set) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resunit_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const unsigned grid = static_cast<unsigned>((a.B + a.G - 1) / a.G);
+    resunit_fused_kernel<C><<<grid, kThreadsRU, smem, st>>>(a);
+    mmla_count_launch();
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
+}  // namespace
+
+// x, y: [B][T][C] fp32 NHWC (H = 1).  T in {128, 64, 32} with C in {32, 64, 128}; weights are the
+// conv_tc-arranged streams of the two k=3 convolutions.
+int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int C, const float* bn1_scale,
+                              const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
+                              const float* bn2_shift, const float* w2, const float* b2, cudaStream_t st) {
+    MMLA_REQUIRE(T >= 32 && T <= 128 && 128 % T == 0, MMLA_EUNSUP, "resunit_fused: T=%d unsupported", T);
+    MMLA_REQUIRE(B > 0 && B < (1LL << 24), MMLA_EINVAL, "resunit_fused: bad batch");
+    ResUnitArgs a;
+    a.x = x; a.y = y;
+    a.bn1_scale = bn1_scale; a.bn1_shift = bn1_shift; a.bn2_scale = bn2_scale; a.bn2_shift = bn2_shift;
+    a.w1 = w1; a.w2 = w2; a.b1 = b1; a.b2 = b2;
+    a.B = static_cast<int>(B); a.T = T; a.G = 128 / T;
+    switch (C) {
+        case 32: return launch_ru<32>(a, st);
+        case 64: return launch_ru<64>(a, st);
+        case 128: return launch_ru<128>(a, st);
+        default:
+            mmla_set_error("resunit_fused: C=%d unsupported", C);
+            return MMLA_EUNSUP;
+    }
+}
