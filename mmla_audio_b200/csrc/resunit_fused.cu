@@ -41,9 +41,10 @@ struct ResUnitArgs {
 
 template <int C>
 struct RuSmem {
-    alignas(128) unsigned char a1[(C / 4) * kRtot * 16];       // ReLU(BN1(x)), later the output staging tile
-    alignas(128) unsigned char a2[(C / 4) * kRtot * 16];       // ReLU(BN2(conv1))
-    alignas(128) unsigned char ring[kStagesRU][8 * C * 16];    // weight chunks: 32 K x C
+    // ONE operand buffer, used three times: ReLU(BN1(x)) for conv1; then (conv1's MMAs have retired
+    // before epilogue 1 runs) ReLU(BN2(conv1)) for conv2; then the output staging tile.
+    alignas(128) unsigned char ab[(C / 4) * kRtot * 16];
+    alignas(128) unsigned char ring[kStagesRU][(C == 128 ? 4 : 8) * C * 16];   // weight chunks: 16|32 K x C
     alignas(8) uint64_t full[kStagesRU];
     alignas(8) uint64_t empty[kStagesRU];
     alignas(8) uint64_t a_ready[2];                            // operand buffer written   (epilogue -> MMA)
@@ -72,8 +73,9 @@ __device__ __forceinline__ void ru_commit(uint64_t* bar) {
 template <int C>
 __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnitArgs a) {
     constexpr int kQuads = C / 4;
-    constexpr int kChunks = 3 * C / 32;                          // K-chunks per conv (K = 3*C)
-    constexpr uint32_t kChunkBytes = 8 * C * 16;
+    constexpr int kChunkK = C == 128 ? 16 : 32;                  // K per ring chunk (8 KB chunks keep 2 CTAs/SM at C=128)
+    constexpr int kChunks = 3 * C / kChunkK;                     // K-chunks per conv (K = 3*C)
+    constexpr uint32_t kChunkBytes = (kChunkK / 4) * C * 16;
     constexpr int kCols = 2 * C < 32 ? 32 : 2 * C;               // two accumulators side by side
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(C >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);
@@ -111,8 +113,10 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
             for (int g = 0; g < 2 * kChunks; ++g) {
                 const int stg = g % kStagesRU, use = g / kStagesRU;
                 if (use > 0) ru_wait(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
-                const float* src = (g < kChunks ? a.w1 + static_cast<long long>(g) * (8 * C * 4)
-                                                : a.w2 + static_cast<long long>(g - kChunks) * (8 * C * 4));
+                // the conv_tc arrangement is a plain sequence of K-slabs ([K/4][C][4]), so any
+                // multiple-of-4 K granularity is a contiguous slice of it
+                const float* src = (g < kChunks ? a.w1 + static_cast<long long>(g) * (kChunkK * C)
+                                                : a.w2 + static_cast<long long>(g - kChunks) * (kChunkK * C));
                 mbar_arrive_expect_tx(&s.full[stg], kChunkBytes);
                 tma_bulk_g2s(&s.ring[stg][0], src, kChunkBytes, &s.full[stg]);
             }
@@ -125,16 +129,16 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
             for (int conv = 0; conv < 2; ++conv) {
                 ru_wait(&s.a_ready[conv], 0u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t abuf = smem_u32(conv == 0 ? &s.a1[0] : &s.a2[0]);
+                const uint32_t abuf = smem_u32(&s.ab[0]);
                 for (int ch = 0; ch < kChunks; ++ch, ++g) {
                     const int stg = g % kStagesRU;
                     ru_wait(&s.full[stg], static_cast<uint32_t>((g / kStagesRU) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int k0 = ch * 32;                      // K index = tap*C + channel
+                    const int k0 = ch * kChunkK;                 // K index = tap*C + channel
                     const int tap = k0 / C, c0 = k0 - tap * C;
                     const uint32_t b_addr = smem_u32(&s.ring[stg][0]);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
+                    for (int kk = 0; kk < kChunkK / 8; ++kk) {
                         // A: slabs (c0/4 + 2kk, +1), rows shifted by tap*G (row G*1 = first real row)
                         const uint32_t a_addr = abuf + (((c0 >> 2) + 2 * kk) * kRtot + tap * G) * 16;
                         const uint64_t ad = ru_desc(a_addr, kRtot * 16, 128);
@@ -154,33 +158,42 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
         __syncwarp();
     } else {
         // ================= warps 0..7: load/transform, epilogues =================
-        // zero the halo rows (rows [0,G) and [G+128, G+128+G)) of both operand buffers
-        for (int i = tid; i < 2 * kQuads * 2 * G; i += kEpi) {
-            const int buf = i / (kQuads * 2 * G), r = i % (kQuads * 2 * G);
-            const int qd = r / (2 * G), h = r % (2 * G);
-            const int row = h < G ? h : 128 + h;                 // h-G+G+128
-            unsigned char* base = buf == 0 ? &s.a1[0] : &s.a2[0];
-            *reinterpret_cast<uint4*>(base + (qd * kRtot + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        // zero the halo rows (rows [0,G) and [G+128, G+128+G)); epilogue 1 never touches them
+        for (int i = tid; i < kQuads * 2 * G; i += kEpi) {
+            const int qd = i / (2 * G), h = i % (2 * G);
+            const int row = h < G ? h : 128 + h;
+            *reinterpret_cast<uint4*>(&s.ab[0] + (qd * kRtot + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        // ---- x -> ReLU(BN1(x)) -> TF32 -> a1 (lanes run over channel quads: coalesced loads) ----
+        // ---- x -> ReLU(BN1(x)) -> TF32 -> operand buffer (lanes run over channel quads: coalesced;
+        //      all loads are issued before the first use so their latencies overlap) ----
         {
             constexpr int kRowsPerPass = kEpi / kQuads;           // rows covered by 256 threads at once
+            constexpr int kIters = 128 / kRowsPerPass;            // 4 | 8 | 16 float4 per thread
             const int qd = tid % kQuads, rsub = tid / kQuads;
             const float4 sc = *reinterpret_cast<const float4*>(a.bn1_scale + 4 * qd);
             const float4 sh = *reinterpret_cast<const float4*>(a.bn1_shift + 4 * qd);
-#pragma unroll 4
-            for (int r = rsub; r < 128; r += kRowsPerPass) {
+            float4 v[kIters];
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+                const int r = rsub + i * kRowsPerPass;
                 const int t = r / G, g = r - t * G;              // row = t*G + g
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (clip0 + g < a.B)
+                    v[i] = *reinterpret_cast<const float4*>(a.x + (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd);
+            }
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+                const int r = rsub + i * kRowsPerPass;
+                const int g = r % G;
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);       // clips past the batch end stay zero
                 if (clip0 + g < a.B) {
-                    v = *reinterpret_cast<const float4*>(a.x + (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd);
-                    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
-                    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-                    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
-                    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+                    w.x = fmaxf(fmaf(v[i].x, sc.x, sh.x), 0.f);
+                    w.y = fmaxf(fmaf(v[i].y, sc.y, sh.y), 0.f);
+                    w.z = fmaxf(fmaf(v[i].z, sc.z, sh.z), 0.f);
+                    w.w = fmaxf(fmaf(v[i].w, sc.w, sh.w), 0.f);
                 }
-                *reinterpret_cast<uint4*>(&s.a1[0] + (qd * kRtot + G + r) * 16) =
-                    make_uint4(ru_tf32(v.x), ru_tf32(v.y), ru_tf32(v.z), ru_tf32(v.w));
+                *reinterpret_cast<uint4*>(&s.ab[0] + (qd * kRtot + G + r) * 16) =
+                    make_uint4(ru_tf32(w.x), ru_tf32(w.y), ru_tf32(w.z), ru_tf32(w.w));
             }
         }
         fence_proxy_async_smem();
@@ -204,8 +217,8 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
             for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(r[j]);
         };
 
-        // ---- epilogue 1: conv1 accumulator -> +b1 -> BN2 -> ReLU -> TF32 -> a2 -------------------
-        ru_wait(&s.tfull[0], 0u);
+        // ---- epilogue 1: conv1 accumulator -> +b1 -> BN2 -> ReLU -> TF32 -> operand buffer -------
+        ru_wait(&s.tfull[0], 0u);                                 // conv1's MMAs (readers of the buffer) have retired
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
                 const float v1 = fmaxf(fmaf(z[j + 1] + bv.y, sc.y, sh.y), 0.f);
                 const float v2 = fmaxf(fmaf(z[j + 2] + bv.z, sc.z, sh.z), 0.f);
                 const float v3 = fmaxf(fmaf(z[j + 3] + bv.w, sc.w, sh.w), 0.f);
-                *reinterpret_cast<uint4*>(&s.a2[0] + (((col + j) >> 2) * kRtot + G + row) * 16) =
+                *reinterpret_cast<uint4*>(&s.ab[0] + (((col + j) >> 2) * kRtot + G + row) * 16) =
                     make_uint4(ru_tf32(v0), ru_tf32(v1), ru_tf32(v2), ru_tf32(v3));
             }
         }
@@ -232,9 +245,10 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
 
         // ---- epilogue 2: conv2 accumulator + b2 -> staging (operand buffers are dead) -> y = . + x ----
         constexpr int kStride = C + 4;                            // floats per staged row (conflict-free STS.128)
-        static_assert(kStride * 128 * 4 <= 2 * (C / 4) * kRtot * 16, "staging tile must fit in a1|a2");
-        float* stg = reinterpret_cast<float*>(&s.a1[0]);          // spans a1 and (contiguous) a2: both are dead now
-        ru_wait(&s.tfull[1], 0u);                                 // every MMA reading a1 / a2 has retired
+        static_assert(kStride * 128 * 4 <= (C / 4) * kRtot * 16 + kStagesRU * (C == 128 ? 4 : 8) * C * 16,
+                      "staging tile must fit in the operand buffer (+ the idle weight ring)");
+        float* stg = reinterpret_cast<float*>(&s.ab[0]);          // may run over into the (idle) weight ring
+        ru_wait(&s.tfull[1], 0u);                                 // every MMA has retired, every weight chunk consumed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
@@ -250,15 +264,28 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         ru_epi_sync();
-        for (int idx = tid; idx < 128 * kQuads; idx += kEpi) {
-            const int r = idx / kQuads, qd = idx - r * kQuads;
-            const int t = r / G, g = r - t * G;
-            if (clip0 + g < a.B) {
-                const long long off = (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd;
-                float4 v = *reinterpret_cast<const float4*>(stg + r * kStride + 4 * qd);
-                const float4 xr = *reinterpret_cast<const float4*>(a.x + off);
-                v.x += xr.x; v.y += xr.y; v.z += xr.z; v.w += xr.w;
-                *reinterpret_cast<float4*>(a.y + off) = v;
+        {
+            constexpr int kIters = 128 * kQuads / kEpi;           // float4 per thread
+            float4 xr[kIters];
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {                    // all residual loads first
+                const int idx = tid + i * kEpi;
+                const int r = idx / kQuads, qd = idx - r * kQuads;
+                const int t = r / G, g = r - t * G;
+                xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (clip0 + g < a.B)
+                    xr[i] = *reinterpret_cast<const float4*>(a.x + (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd);
+            }
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+                const int idx = tid + i * kEpi;
+                const int r = idx / kQuads, qd = idx - r * kQuads;
+                const int t = r / G, g = r - t * G;
+                if (clip0 + g < a.B) {
+                    float4 v = *reinterpret_cast<const float4*>(stg + r * kStride + 4 * qd);
+                    v.x += xr[i].x; v.y += xr[i].y; v.z += xr[i].z; v.w += xr[i].w;
+                    *reinterpret_cast<float4*>(a.y + (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd) = v;
+                }
             }
         }
     }
