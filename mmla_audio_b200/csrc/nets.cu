@@ -209,6 +209,26 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
     }
 }
 
+// speaker stem input [rows][39] -> [rows][40] (zero column) so the stem conv takes the vectorised
+// Cin % 4 == 0 gather path of conv_tc_kernel
+__global__ void __launch_bounds__(256) pad_channels_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows,
+                                                           int cin, int cpad) {
+    const int quads = cpad >> 2;
+    const long long total = rows * quads;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const long long r = e / quads;
+        const int c = 4 * static_cast<int>(e - r * quads);
+        const float* src = x + r * cin + c;
+        float4 v;
+        v.x = c + 0 < cin ? src[0] : 0.f;
+        v.y = c + 1 < cin ? src[1] : 0.f;
+        v.z = c + 2 < cin ? src[2] : 0.f;
+        v.w = c + 3 < cin ? src[3] : 0.f;
+        *reinterpret_cast<float4*>(y + e * 4) = v;
+    }
+}
+
 // overlap: Lambda(mean over axis 1 = H): [B,H,W,C] -> [B,W,C]
 __global__ void __launch_bounds__(256) mean_h_kernel(const float* __restrict__ x, float* __restrict__ y, long long B,
                                                      int H, int W, int C) {
@@ -339,6 +359,7 @@ struct MmlaNet {
     int precision = MMLA_PRECISION_FP32;  // MMLA_PRECISION_*
     float* dev = nullptr;                 // device blob (weights + folded BN)
     ConvW stem;
+    ConvW stem_pad;                       // speaker stem with Cin padded 39 -> 40 (tensor-core path only)
     std::vector<BlockW> blocks;
     BnW final_bn;
     ConvW lstm_in[2];                     // [feat,1024] projection (bias = LSTM bias)
@@ -358,9 +379,10 @@ long long mmla_tc_arranged_floats(int K, int N);
 void mmla_tc_arrange_weights(const float* w, int K, int N, float* out);
 int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st);
 // resunit_fused.cu
-int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int C, const float* bn1_scale,
+int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* bn1_scale,
                               const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
-                              const float* bn2_shift, const float* w2, const float* b2, cudaStream_t st);
+                              const float* bn2_shift, const float* w2, const float* b2, const float* ws, const float* bs,
+                              cudaStream_t st);
 // lstm_fused.cu
 long long mmla_lstm_arranged_floats();
 void mmla_lstm_arrange_weights(const float* U, float* out);
@@ -494,7 +516,22 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
         take_conv(net->stem, 1, 1, 3, 16, 1);
     } else {
         net->in_h = 1; net->in_w = 256; net->in_c = 39;
+        const float* stem_src = rd.p + rd.pos;
         take_conv(net->stem, 1, 4, 39, 32, 1);
+        if (rd.ok) {                      // zero-padded copy [4][40][32] for the vectorised gather
+            std::vector<float> wpad(4 * 40 * 32, 0.f);
+            for (int k = 0; k < 4; ++k)
+                for (int c = 0; c < 39; ++c) memcpy(&wpad[(k * 40 + c) * 32], stem_src + (k * 39 + c) * 32, 32 * sizeof(float));
+            net->stem_pad = net->stem;
+            net->stem_pad.cin = 40;
+            net->stem_pad.k = nullptr;
+            while (stage.size() % 4) stage.push_back(0.f);
+            const long long off = static_cast<long long>(stage.size());
+            stage.resize(stage.size() + mmla_tc_arranged_floats(160, 32));
+            mmla_tc_arrange_weights(wpad.data(), 160, 32, stage.data() + off);
+            fixes.push_back({&net->stem_pad.k_tc, off});
+            fixes.push_back({&net->stem_pad.b, static_cast<long long>((stem_src + 4 * 39 * 32) - w_host)});
+        }
     }
     int cin = ov ? 16 : 32;
     net->blocks.resize(9);
@@ -562,7 +599,7 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
     // workspace plan (floats per clip): three rotating activation buffers + LSTM scratch
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const long long T = net->seq_len;
-    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 4 * 256;
+    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 4 * 256 + (ov ? 0 : 256 * 40);
     net->micro = ov ? 128 : 4096;         // measured on B200: larger micro-batches win (launch/latency-bound layers)
     if (const char* e = getenv("MMLA_NET_MICRO")) {
         const int v = atoi(e);
@@ -609,23 +646,37 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         float* z = xp[1] + B * T * 1024;                  // [B,1024] gate pre-activations
         float* hdir[2] = {z + B * 1024, z + B * 1024 + B * 256};   // final h of the fwd / bwd layer
         float* cst = hdir[1] + B * 256;                   // [B,256] cell state (x2 for the fused kernel)
+        float* xpad = cst + 2 * B * 256;                  // speaker: [B,256,40] channel-padded input
 
         const void* xin = x_is_u8 ? static_cast<const void*>(static_cast<const unsigned char*>(x) + b0 * in_elems)
                                   : static_cast<const void*>(static_cast<const float*>(x) + b0 * in_elems);
         int H = net->in_h, W = net->in_w;
         int cur = 0;
-        int rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
+        int rc;
+        if (tc && !ov && net->stem_pad.k_tc) {
+            pad_channels_kernel<<<ew_grid(B * 256 * 10), 256, 0, st>>>(static_cast<const float*>(xin), xpad, B * 256, 39, 40);
+            mmla_count_launch();
+            MMLA_CUDA_CHECK(cudaGetLastError());
+            rc = launch_conv(net->stem_pad, xpad, 0, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
+        } else {
+            rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
+        }
         if (rc) return rc;
         const int act_kind = ov ? ACT_ELU : ACT_RELU;
         for (const BlockW& blk : net->blocks) {
             float* X = buf[cur];
             float* A = buf[(cur + 1) % 3];
             float* Bf = buf[(cur + 2) % 3];
-            if (!blk.pool && tc && !ov && blk.conv1.k_tc && blk.conv2.k_tc) {
-                // speaker plain unit, tensor-core mode: one fused kernel (resunit_fused.cu)
-                if ((rc = mmla_launch_resunit_fused(X, A, B, W, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift, blk.conv1.k_tc,
-                                                    blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc, blk.conv2.b, st)))
+            if (tc && !ov && blk.conv1.k_tc && blk.conv2.k_tc && (!blk.pool || blk.shortcut.k_tc)) {
+                // speaker res_unit, tensor-core mode: ONE fused kernel per unit (resunit_fused.cu) —
+                // pooled units max-pool on load and fold the stride-2 shortcut into the accumulator
+                const int Wo = blk.pool ? same_out(W, 2) : W;
+                if ((rc = mmla_launch_resunit_fused(X, A, B, Wo, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
+                                                    blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift,
+                                                    blk.conv2.k_tc, blk.conv2.b, blk.pool ? blk.shortcut.k_tc : nullptr,
+                                                    blk.pool ? blk.shortcut.b : nullptr, st)))
                     return rc;
+                W = Wo;
                 cur = (cur + 1) % 3;
             } else if (!blk.pool) {
                 // out = conv2(act(bn2(conv1(act(bn1(x)))))) + x

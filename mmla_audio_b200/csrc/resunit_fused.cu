@@ -1,8 +1,11 @@
 // Fused 1-D residual unit for sm_100a (speaker classifier, TF32 tensor-core mode):
 //
-//     y = x + Conv1D_k3( ReLU(BN2( Conv1D_k3( ReLU(BN1(x)) ) )) )        (no pooling, Cin == Cout == C)
+//   plain :  y = x + Conv1D_k3( ReLU(BN2( Conv1D_k3( ReLU(BN1(x)) ) )) )               (Cin == Cout)
+//   pooled:  y = Conv1D_k1_s2(x) + Conv1D_k3( ReLU(BN2( Conv1D_k3( ReLU(BN1( MaxPool1D_2(x) )) ) )) )
 //
-// — `res_unit(x, filters)` of SpeakerIdentification/scripts/speaker_identification.py:168-190.
+// — `res_unit(x, filters, pool)` of SpeakerIdentification/scripts/speaker_identification.py:168-190.
+// In the pooled unit the max-pool happens while x is loaded, and the stride-2 1x1 shortcut is
+// simply extra K-chunks (A = raw even rows of x) accumulated into conv2's TMEM accumulator.
 //
 // The im2col expansion never exists.  One CTA owns a 128-row tile = G = 128/T whole clips with rows
 // interleaved time-major (row = t*G + g), so that a filter tap is a UNIFORM shift of G rows:
@@ -35,15 +38,17 @@ struct ResUnitArgs {
     const float* bn1_scale; const float* bn1_shift;
     const float* bn2_scale; const float* bn2_shift;
     const float* w1; const float* w2;      // conv_tc-arranged K-chunk streams ([K/32][8 slabs][C][4])
-    const float* b1; const float* b2;
-    int B, T, G;
+    const float* ws;                       // shortcut weights (pooled unit), same arrangement
+    const float* b1; const float* b2; const float* bs;
+    int B, T, G;                           // T = OUTPUT time steps (input has 2T when pooled)
 };
 
-template <int C>
+template <int CIN, int C, bool POOL>
 struct RuSmem {
     // ONE operand buffer, used three times: ReLU(BN1(x)) for conv1; then (conv1's MMAs have retired
     // before epilogue 1 runs) ReLU(BN2(conv1)) for conv2; then the output staging tile.
     alignas(128) unsigned char ab[(C / 4) * kRtot * 16];
+    alignas(128) unsigned char a0[POOL ? (CIN / 4) * 128 * 16 : 16];   // raw x[2t] for the shortcut GEMM
     alignas(128) unsigned char ring[kStagesRU][(C == 128 ? 4 : 8) * C * 16];   // weight chunks: 16|32 K x C
     alignas(8) uint64_t full[kStagesRU];
     alignas(8) uint64_t empty[kStagesRU];
@@ -70,17 +75,21 @@ __device__ __forceinline__ void ru_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int C>
+template <int CIN, int C, bool POOL>
 __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnitArgs a) {
+    static_assert(POOL || CIN == C, "plain units keep the channel count");
     constexpr int kQuads = C / 4;
+    constexpr int kQuadsIn = CIN / 4;
     constexpr int kChunkK = C == 128 ? 16 : 32;                  // K per ring chunk (8 KB chunks keep 2 CTAs/SM at C=128)
-    constexpr int kChunks = 3 * C / kChunkK;                     // K-chunks per conv (K = 3*C)
+    constexpr int kChunks1 = 3 * CIN / kChunkK;                  // conv1: K = 3*CIN
+    constexpr int kChunksS = POOL ? CIN / kChunkK : 0;           // shortcut: K = CIN
+    constexpr int kChunks2 = 3 * C / kChunkK;                    // conv2: K = 3*C
     constexpr uint32_t kChunkBytes = (kChunkK / 4) * C * 16;
     constexpr int kCols = 2 * C < 32 ? 32 : 2 * C;               // two accumulators side by side
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(C >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);
     extern __shared__ unsigned char smem_dyn[];
-    RuSmem<C>& s = *reinterpret_cast<RuSmem<C>*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~static_cast<uintptr_t>(127));
+    RuSmem<CIN, C, POOL>& s = *reinterpret_cast<RuSmem<CIN, C, POOL>*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~static_cast<uintptr_t>(127));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = a.G, T = a.T;
     const int clip0 = blockIdx.x * G;
@@ -110,13 +119,14 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
     if (warp == 8) {
         // ================= TMA producer: conv1 then conv2 weight chunks =================
         if (lane == 0) {
-            for (int g = 0; g < 2 * kChunks; ++g) {
+            for (int g = 0; g < kChunks1 + kChunksS + kChunks2; ++g) {
                 const int stg = g % kStagesRU, use = g / kStagesRU;
                 if (use > 0) ru_wait(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
                 // the conv_tc arrangement is a plain sequence of K-slabs ([K/4][C][4]), so any
-                // multiple-of-4 K granularity is a contiguous slice of it
-                const float* src = (g < kChunks ? a.w1 + static_cast<long long>(g) * (kChunkK * C)
-                                                : a.w2 + static_cast<long long>(g - kChunks) * (kChunkK * C));
+                // multiple-of-4 K granularity is a contiguous slice of it.  Order: conv1, shortcut, conv2.
+                const float* src = g < kChunks1              ? a.w1 + static_cast<long long>(g) * (kChunkK * C)
+                                   : g < kChunks1 + kChunksS ? a.ws + static_cast<long long>(g - kChunks1) * (kChunkK * C)
+                                                             : a.w2 + static_cast<long long>(g - kChunks1 - kChunksS) * (kChunkK * C);
                 mbar_arrive_expect_tx(&s.full[stg], kChunkBytes);
                 tma_bulk_g2s(&s.ring[stg][0], src, kChunkBytes, &s.full[stg]);
             }
@@ -126,34 +136,47 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
         // ================= MMA issuer =================
         if (lane == 0) {
             int g = 0;
-            for (int conv = 0; conv < 2; ++conv) {
-                ru_wait(&s.a_ready[conv], 0u);
+            const uint32_t abuf = smem_u32(&s.ab[0]);
+            // one K-chunk of MMAs: A slabs start at (slab0 + 2kk) in a buffer with `rows` rows per slab,
+            // shifted down by `shift` rows; accumulates into TMEM column block `dcol`
+            auto chunk_mma = [&](uint32_t a_base, int rows, int slab0, int shift, uint32_t dcol, bool first) {
+                const int stg = g % kStagesRU;
+                ru_wait(&s.full[stg], static_cast<uint32_t>((g / kStagesRU) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t abuf = smem_u32(&s.ab[0]);
-                for (int ch = 0; ch < kChunks; ++ch, ++g) {
-                    const int stg = g % kStagesRU;
-                    ru_wait(&s.full[stg], static_cast<uint32_t>((g / kStagesRU) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int k0 = ch * kChunkK;                 // K index = tap*C + channel
-                    const int tap = k0 / C, c0 = k0 - tap * C;
-                    const uint32_t b_addr = smem_u32(&s.ring[stg][0]);
+                const uint32_t b_addr = smem_u32(&s.ring[stg][0]);
 #pragma unroll
-                    for (int kk = 0; kk < kChunkK / 8; ++kk) {
-                        // A: slabs (c0/4 + 2kk, +1), rows shifted by tap*G (row G*1 = first real row)
-                        const uint32_t a_addr = abuf + (((c0 >> 2) + 2 * kk) * kRtot + tap * G) * 16;
-                        const uint64_t ad = ru_desc(a_addr, kRtot * 16, 128);
-                        const uint64_t bd = ru_desc(b_addr + kk * 2 * (C * 16), C * 16, 128);
-                        const uint32_t acc = (ch | kk) != 0 ? 1u : 0u;
-                        asm volatile(
-                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + conv * C),
-                            "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
-                            : "memory");
-                    }
-                    ru_commit(&s.empty[stg]);
+                for (int kk = 0; kk < kChunkK / 8; ++kk) {
+                    const uint32_t a_addr = a_base + ((slab0 + 2 * kk) * rows + shift) * 16;
+                    const uint64_t ad = ru_desc(a_addr, rows * 16, 128);
+                    const uint64_t bd = ru_desc(b_addr + kk * 2 * (C * 16), C * 16, 128);
+                    const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + dcol),
+                        "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                        : "memory");
                 }
-                ru_commit(&s.tfull[conv]);
+                ru_commit(&s.empty[stg]);
+                ++g;
+            };
+            // conv1: K index = tap*CIN + channel; tap j reads rows shifted by j*G (halo rows = zero padding)
+            ru_wait(&s.a_ready[0], 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int ch = 0; ch < kChunks1; ++ch) {
+                const int k0 = ch * kChunkK, tap = k0 / CIN, c0 = k0 - tap * CIN;
+                chunk_mma(abuf, kRtot, c0 >> 2, tap * G, 0u, ch == 0);
             }
+            ru_commit(&s.tfull[0]);
+            // shortcut (pooled unit): raw x[2t] x Ws starts conv2's accumulator while epilogue 1 runs
+            for (int ch = 0; ch < kChunksS; ++ch) chunk_mma(smem_u32(&s.a0[0]), 128, (ch * kChunkK) >> 2, 0, C, ch == 0);
+            // conv2
+            ru_wait(&s.a_ready[1], 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int ch = 0; ch < kChunks2; ++ch) {
+                const int k0 = ch * kChunkK, tap = k0 / C, c0 = k0 - tap * C;
+                chunk_mma(abuf, kRtot, c0 >> 2, tap * G, C, ch == 0 && !POOL);
+            }
+            ru_commit(&s.tfull[1]);
         }
         __syncwarp();
     } else {
@@ -164,22 +187,27 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
             const int row = h < G ? h : 128 + h;
             *reinterpret_cast<uint4*>(&s.ab[0] + (qd * kRtot + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        // ---- x -> ReLU(BN1(x)) -> TF32 -> operand buffer (lanes run over channel quads: coalesced;
-        //      all loads are issued before the first use so their latencies overlap) ----
+        // ---- x -> [MaxPool2] -> ReLU(BN1(.)) -> TF32 -> operand buffer (lanes run over channel quads:
+        //      coalesced; all loads are issued before the first use so their latencies overlap) ----
         {
-            constexpr int kRowsPerPass = kEpi / kQuads;           // rows covered by 256 threads at once
-            constexpr int kIters = 128 / kRowsPerPass;            // 4 | 8 | 16 float4 per thread
-            const int qd = tid % kQuads, rsub = tid / kQuads;
+            constexpr int kRowsPerPass = kEpi / kQuadsIn;         // rows covered by 256 threads at once
+            constexpr int kIters = 128 / kRowsPerPass;
+            const int qd = tid % kQuadsIn, rsub = tid / kQuadsIn;
             const float4 sc = *reinterpret_cast<const float4*>(a.bn1_scale + 4 * qd);
             const float4 sh = *reinterpret_cast<const float4*>(a.bn1_shift + 4 * qd);
-            float4 v[kIters];
+            const int Tin = POOL ? 2 * T : T;
+            float4 v[kIters], v2[POOL ? kIters : 1];
 #pragma unroll
             for (int i = 0; i < kIters; ++i) {
                 const int r = rsub + i * kRowsPerPass;
                 const int t = r / G, g = r - t * G;              // row = t*G + g
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (clip0 + g < a.B)
-                    v[i] = *reinterpret_cast<const float4*>(a.x + (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd);
+                if (POOL) v2[i] = v[i];
+                if (clip0 + g < a.B) {
+                    const float* src = a.x + (static_cast<long long>(clip0 + g) * Tin + (POOL ? 2 * t : t)) * CIN + 4 * qd;
+                    v[i] = *reinterpret_cast<const float4*>(src);
+                    if (POOL) v2[i] = *reinterpret_cast<const float4*>(src + CIN);
+                }
             }
 #pragma unroll
             for (int i = 0; i < kIters; ++i) {
@@ -187,10 +215,20 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
                 const int g = r % G;
                 float4 w = make_float4(0.f, 0.f, 0.f, 0.f);       // clips past the batch end stay zero
                 if (clip0 + g < a.B) {
-                    w.x = fmaxf(fmaf(v[i].x, sc.x, sh.x), 0.f);
-                    w.y = fmaxf(fmaf(v[i].y, sc.y, sh.y), 0.f);
-                    w.z = fmaxf(fmaf(v[i].z, sc.z, sh.z), 0.f);
-                    w.w = fmaxf(fmaf(v[i].w, sc.w, sh.w), 0.f);
+                    float4 p = v[i];
+                    if (POOL) {
+                        // shortcut operand: the raw even row; conv path: max over the pair
+                        *reinterpret_cast<uint4*>(&s.a0[0] + (qd * 128 + r) * 16) =
+                            make_uint4(ru_tf32(p.x), ru_tf32(p.y), ru_tf32(p.z), ru_tf32(p.w));
+                        p.x = fmaxf(p.x, v2[i].x); p.y = fmaxf(p.y, v2[i].y);
+                        p.z = fmaxf(p.z, v2[i].z); p.w = fmaxf(p.w, v2[i].w);
+                    }
+                    w.x = fmaxf(fmaf(p.x, sc.x, sh.x), 0.f);
+                    w.y = fmaxf(fmaf(p.y, sc.y, sh.y), 0.f);
+                    w.z = fmaxf(fmaf(p.z, sc.z, sh.z), 0.f);
+                    w.w = fmaxf(fmaf(p.w, sc.w, sh.w), 0.f);
+                } else if (POOL) {
+                    *reinterpret_cast<uint4*>(&s.a0[0] + (qd * 128 + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 *reinterpret_cast<uint4*>(&s.ab[0] + (qd * kRtot + G + r) * 16) =
                     make_uint4(ru_tf32(w.x), ru_tf32(w.y), ru_tf32(w.z), ru_tf32(w.w));
@@ -245,9 +283,9 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
 
         // ---- epilogue 2: conv2 accumulator + b2 -> staging (operand buffers are dead) -> y = . + x ----
         constexpr int kStride = C + 4;                            // floats per staged row (conflict-free STS.128)
-        static_assert(kStride * 128 * 4 <= (C / 4) * kRtot * 16 + kStagesRU * (C == 128 ? 4 : 8) * C * 16,
-                      "staging tile must fit in the operand buffer (+ the idle weight ring)");
-        float* stg = reinterpret_cast<float*>(&s.ab[0]);          // may run over into the (idle) weight ring
+        static_assert(kStride * 128 * 4 <= sizeof(s.ab) + sizeof(s.a0) + sizeof(s.ring),
+                      "staging tile must fit in the (now idle) operand buffers + weight ring");
+        float* stg = reinterpret_cast<float*>(&s.ab[0]);          // may run over into a0 / the ring head (all idle now)
         ru_wait(&s.tfull[1], 0u);                                 // every MMA has retired, every weight chunk consumed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -257,7 +295,11 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
             ld16(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(C + col), z);
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                const float4 bv = *reinterpret_cast<const float4*>(a.b2 + col + j);
+                float4 bv = *reinterpret_cast<const float4*>(a.b2 + col + j);
+                if (POOL) {
+                    const float4 b3 = *reinterpret_cast<const float4*>(a.bs + col + j);
+                    bv.x += b3.x; bv.y += b3.y; bv.z += b3.z; bv.w += b3.w;
+                }
                 *reinterpret_cast<float4*>(stg + row * kStride + col + j) =
                     make_float4(z[j] + bv.x, z[j + 1] + bv.y, z[j + 2] + bv.z, z[j + 3] + bv.w);
             }
@@ -273,7 +315,7 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
                 const int r = idx / kQuads, qd = idx - r * kQuads;
                 const int t = r / G, g = r - t * G;
                 xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (clip0 + g < a.B)
+                if (!POOL && clip0 + g < a.B)                    // pooled units got their residual from the shortcut GEMM
                     xr[i] = *reinterpret_cast<const float4*>(a.x + (static_cast<long long>(clip0 + g) * T + t) * C + 4 * qd);
             }
 #pragma unroll
@@ -296,16 +338,16 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
                      : "memory");
 }
 
-template <int C>
+template <int CIN, int C, bool POOL>
 int launch_ru(const ResUnitArgs& a, cudaStream_t st) {
     static bool attr_set = false;
-    const int smem = static_cast<int>(sizeof(RuSmem<C>) + 128);
+    const int smem = static_cast<int>(sizeof(RuSmem<CIN, C, POOL>) + 128);
     if (!attr_set) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resunit_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resunit_fused_kernel<CIN, C, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const unsigned grid = static_cast<unsigned>((a.B + a.G - 1) / a.G);
-    resunit_fused_kernel<C><<<grid, kThreadsRU, smem, st>>>(a);
+    resunit_fused_kernel<CIN, C, POOL><<<grid, kThreadsRU, smem, st>>>(a);
     mmla_count_launch();
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
@@ -313,24 +355,30 @@ int launch_ru(const ResUnitArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-// x, y: [B][T][C] fp32 NHWC (H = 1).  T in {128, 64, 32} with C in {32, 64, 128}; weights are the
-// conv_tc-arranged streams of the two k=3 convolutions.
-int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int C, const float* bn1_scale,
+// x: [B][Tin][Cin], y: [B][T][C] fp32 NHWC (H = 1); T = output steps in {128, 64, 32}, Tin = T (plain,
+// Cin == C) or 2T (pooled).  Weights are the conv_tc-arranged streams of the k=3 convolutions (and of
+// the 1x1 stride-2 shortcut when pooled: ws/bs non-null).
+int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* bn1_scale,
                               const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
-                              const float* bn2_shift, const float* w2, const float* b2, cudaStream_t st) {
+                              const float* bn2_shift, const float* w2, const float* b2, const float* ws, const float* bs,
+                              cudaStream_t st) {
     MMLA_REQUIRE(T >= 32 && T <= 128 && 128 % T == 0, MMLA_EUNSUP, "resunit_fused: T=%d unsupported", T);
     MMLA_REQUIRE(B > 0 && B < (1LL << 24), MMLA_EINVAL, "resunit_fused: bad batch");
     ResUnitArgs a;
     a.x = x; a.y = y;
     a.bn1_scale = bn1_scale; a.bn1_shift = bn1_shift; a.bn2_scale = bn2_scale; a.bn2_shift = bn2_shift;
-    a.w1 = w1; a.w2 = w2; a.b1 = b1; a.b2 = b2;
+    a.w1 = w1; a.w2 = w2; a.ws = ws; a.b1 = b1; a.b2 = b2; a.bs = bs;
     a.B = static_cast<int>(B); a.T = T; a.G = 128 / T;
-    switch (C) {
-        case 32: return launch_ru<32>(a, st);
-        case 64: return launch_ru<64>(a, st);
-        case 128: return launch_ru<128>(a, st);
-        default:
-            mmla_set_error("resunit_fused: C=%d unsupported", C);
-            return MMLA_EUNSUP;
+    const bool pool = ws != nullptr;
+    if (!pool && Cin == C) {
+        if (C == 32) return launch_ru<32, 32, false>(a, st);
+        if (C == 64) return launch_ru<64, 64, false>(a, st);
+        if (C == 128) return launch_ru<128, 128, false>(a, st);
+    } else if (pool) {
+        if (Cin == 32 && C == 32) return launch_ru<32, 32, true>(a, st);
+        if (Cin == 32 && C == 64) return launch_ru<32, 64, true>(a, st);
+        if (Cin == 64 && C == 128) return launch_ru<64, 128, true>(a, st);
     }
+    mmla_set_error("resunit_fused: Cin=%d C=%d pool=%d unsupported", Cin, C, pool ? 1 : 0);
+    return MMLA_EUNSUP;
 }
