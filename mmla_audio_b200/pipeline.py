@@ -53,6 +53,41 @@ class SpeakerPipeline:
         prob, labels = self.model.predict_device(self._feat)
         return labels, prob
 
+    def run_host(self, pcm_host, n_classes: int, n_chunks: int = 4):
+        """End-to-end from HOST memory: ``pcm_host`` int16 [B, L] (pinned for full speed).  The batch
+        is cut into ``n_chunks`` slices; a copy stream uploads slice i+1 while slice i runs
+        features + classifier on the compute stream (two device staging buffers).  Returns
+        (labels int32 numpy [B], counts int64 numpy [n_classes+1])."""
+        torch = _lib.require_cuda()
+        B, L = pcm_host.shape
+        n_chunks = max(1, min(n_chunks, B))
+        bounds = [(B * i) // n_chunks for i in range(n_chunks + 1)]
+        cmax = max(bounds[i + 1] - bounds[i] for i in range(n_chunks))
+        key = (cmax, L)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = [torch.empty((cmax, L), dtype=torch.int16, device="cuda") for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_key = key
+        labels = torch.empty((B,), dtype=torch.int32, device="cuda")
+        compute = torch.cuda.current_stream()
+        copied = [torch.cuda.Event() for _ in range(n_chunks)]
+        consumed = [torch.cuda.Event() for _ in range(n_chunks)]
+        self._copy_stream.wait_stream(compute)
+        for i in range(n_chunks):
+            lo, hi = bounds[i], bounds[i + 1]
+            buf = self._stage[i & 1][: hi - lo]
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(consumed[i - 2])       # staging buffer is free again
+                buf.copy_(pcm_host[lo:hi], non_blocking=True)
+                copied[i].record(self._copy_stream)
+            compute.wait_event(copied[i])
+            lab, _ = self.run_device(buf)
+            labels[lo:hi] = lab
+            consumed[i].record(compute)
+        counts = tally.device_counts(labels, n_classes)
+        return labels.cpu().numpy(), counts.cpu().numpy()
+
     def run_session(self, pcm_long, speaker_names: Dict[int, str], t0: Optional[datetime] = None,
                     silent_index=()):
         """Offline session: MFCC-39 over the whole recording, 256-frame chunks, one predict,
