@@ -209,7 +209,7 @@ def main():
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: workload's)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
                     help="classifier matmul arithmetic: tf32 = tcgen05 tensor cores, fp32 = CUDA cores")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="host pipeline: upload/compute overlap slices")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="host pipeline: upload/compute overlap slices")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     a = ap.parse_args()

@@ -53,7 +53,7 @@ class SpeakerPipeline:
         prob, labels = self.model.predict_device(self._feat)
         return labels, prob
 
-    def run_host(self, pcm_host, n_classes: int, n_chunks: int = 4):
+    def run_host(self, pcm_host, n_classes: int, n_chunks: int = 2):
         """End-to-end from HOST memory: ``pcm_host`` int16 [B, L] (pinned for full speed).  The batch
         is cut into ``n_chunks`` slices; a copy stream uploads slice i+1 while slice i runs
         features + classifier on the compute stream (two device staging buffers).  Returns
