@@ -57,8 +57,14 @@ struct LstmArgs {
 };
 
 __device__ __forceinline__ uint32_t tf32_round(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 2.f * fast_sigmoid(2.f * x) - 1.f; }
+// Gate non-linearities on the MUFU pipe: tanh.approx.f32 (max relative error ~2^-11, the same
+// order as the TF32 operand rounding of this mode) and sigmoid(x) = 0.5 + 0.5 tanh(x/2).
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
 
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
     for (uint32_t i = 0; i < (1u << 24); ++i)
