@@ -235,24 +235,44 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                 }
             }
         };
-        // re-stage h (global, fp32) into the SWIZZLE_128B TF32 operand tiles
+        // re-stage h (global, fp32) into the SWIZZLE_128B TF32 operand tiles; loads are issued
+        // 16 at a time before their first use
         auto restage_h = [&]() {
             const int q = tid & 7, rb = tid >> 3;
-#pragma unroll 2
-            for (int kc = 0; kc < 8; ++kc)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = rb + 32 * i;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b0 + r < a.B) v = __ldcg(reinterpret_cast<const float4*>(hg + static_cast<long long>(b0 + r) * kU + 32 * kc + 4 * q));
-                    *reinterpret_cast<uint4*>(&s.H[kc][0] + r * 128 + ((q ^ (r & 7)) << 4)) =
-                        make_uint4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+            for (int kc0 = 0; kc0 < 8; kc0 += 4) {
+                float4 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int kc = kc0 + (j >> 2), r = rb + 32 * (j & 3);
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + r < a.B) v[j] = __ldcg(reinterpret_cast<const float4*>(hg + static_cast<long long>(b0 + r) * kU + 32 * kc + 4 * q));
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int kc = kc0 + (j >> 2), r = rb + 32 * (j & 3);
+                    *reinterpret_cast<uint4*>(&s.H[kc][0] + r * 128 + ((q ^ (r & 7)) << 4)) =
+                        make_uint4(tf32_round(v[j].x), tf32_round(v[j].y), tf32_round(v[j].z), tf32_round(v[j].w));
+                }
+            }
             fence_proxy_async_smem();
+        };
+        // pull the xp rows of time step t into L2 one step ahead (they stream from HBM otherwise):
+        // 128 rows x 4 KB = 4096 lines, 16 per thread
+        auto prefetch_xp = [&](int t) {
+#pragma unroll 4
+            for (int i = tid; i < kRows * 32; i += kEpiThreads) {
+                const int r = i >> 5, line = i & 31;
+                if (b0 + r < a.B) {
+                    const float* ptr = xp + (static_cast<long long>(b0 + r) * T + t) * 1024 + line * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                }
+            }
         };
 
         for (int step = 0; step < T; ++step) {
             const int t = dir == 0 ? step : T - 1 - step;
+            if (step + 1 < T) prefetch_xp(dir == 0 ? t + 1 : t - 1);
             if (step == 0) {
                 for (int pass = 0; pass < 4; ++pass)                   // h0 = c0 = 0: z is the input projection alone
                     for (int uo = 0; uo < 32; uo += 16) cell16(t, 64 * pass + usub + uo, 0u, true);
