@@ -32,6 +32,19 @@ def window_view(pcm_1d, win: int, step: int):
     return pcm_1d.as_strided((max(n, 0), win), (step, 1))
 
 
+class PendingResult:
+    """Handle of one in-flight :meth:`SpeakerPipeline.submit_host` batch."""
+
+    def __init__(self, slot, done):
+        self._slot, self._done = slot, done
+        self.labels_dev = slot["labels"]       # int32 CUDA [B]; valid until `depth` more submissions
+
+    def result(self):
+        """Block until this batch's labels and tallies are on the host; returns numpy copies."""
+        self._done.synchronize()
+        return self._slot["labels_h"].numpy().copy(), self._slot["counts_h"].numpy().copy()
+
+
 class SpeakerPipeline:
     def __init__(self, model: Model, cfg: MfccConfig = MfccConfig()):
         if model.spec.ndim != 1:
@@ -53,40 +66,67 @@ class SpeakerPipeline:
         prob, labels = self.model.predict_device(self._feat)
         return labels, prob
 
-    def run_host(self, pcm_host, n_classes: int, n_chunks: int = 2):
-        """End-to-end from HOST memory: ``pcm_host`` int16 [B, L] (pinned for full speed).  The batch
-        is cut into ``n_chunks`` slices; a copy stream uploads slice i+1 while slice i runs
-        features + classifier on the compute stream (two device staging buffers).  Returns
-        (labels int32 numpy [B], counts int64 numpy [n_classes+1])."""
+    def submit_host(self, pcm_host, n_classes: int, n_chunks: int = 2, depth: int = 3):
+        """Asynchronous end-to-end pass from HOST memory: ``pcm_host`` int16 [B, L] (pinned for
+        full speed).  The batch is cut into ``n_chunks`` slices; a copy stream uploads slice i+1
+        while slice i runs features + classifier on the compute stream, and the labels + tallies
+        are read back into pinned host buffers behind the last slice.  Nothing blocks the host:
+        the call returns a :class:`PendingResult`; up to ``depth`` submissions may be in flight, so
+        the upload of batch k+1 overlaps the compute of batch k (the recording loop of the
+        reference scripts, pipelined).  ``PendingResult.result()`` waits for that batch only."""
         torch = _lib.require_cuda()
         B, L = pcm_host.shape
         n_chunks = max(1, min(n_chunks, B))
         bounds = [(B * i) // n_chunks for i in range(n_chunks + 1)]
         cmax = max(bounds[i + 1] - bounds[i] for i in range(n_chunks))
-        key = (cmax, L)
+        key = (B, cmax, L, n_classes, depth)
         if getattr(self, "_stage_key", None) != key:
-            self._stage = [torch.empty((cmax, L), dtype=torch.int16, device="cuda") for _ in range(2)]
+            nbuf = 3
+            self._stage = [torch.empty((cmax, L), dtype=torch.int16, device="cuda") for _ in range(nbuf)]
+            self._stage_free = [None] * nbuf            # event: last consumer of the buffer is done
+            self._stage_next = 0
             self._copy_stream = torch.cuda.Stream()
+            self._slots = [dict(labels=torch.empty((B,), dtype=torch.int32, device="cuda"),
+                                labels_h=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                                counts_h=torch.empty((n_classes + 1,), dtype=torch.int64).pin_memory(),
+                                done=None) for _ in range(depth)]
+            self._slot_next = 0
             self._stage_key = key
-        labels = torch.empty((B,), dtype=torch.int32, device="cuda")
+        slot = self._slots[self._slot_next]
+        self._slot_next = (self._slot_next + 1) % len(self._slots)
+        if slot["done"] is not None:
+            slot["done"].synchronize()                  # the slot's previous batch must be read out
         compute = torch.cuda.current_stream()
-        copied = [torch.cuda.Event() for _ in range(n_chunks)]
-        consumed = [torch.cuda.Event() for _ in range(n_chunks)]
-        self._copy_stream.wait_stream(compute)
+        labels = slot["labels"]
         for i in range(n_chunks):
             lo, hi = bounds[i], bounds[i + 1]
-            buf = self._stage[i & 1][: hi - lo]
+            k = self._stage_next
+            self._stage_next = (k + 1) % len(self._stage)
+            buf = self._stage[k][: hi - lo]
+            copied = torch.cuda.Event()
             with torch.cuda.stream(self._copy_stream):
-                if i >= 2:
-                    self._copy_stream.wait_event(consumed[i - 2])       # staging buffer is free again
+                if self._stage_free[k] is not None:
+                    self._copy_stream.wait_event(self._stage_free[k])
                 buf.copy_(pcm_host[lo:hi], non_blocking=True)
-                copied[i].record(self._copy_stream)
-            compute.wait_event(copied[i])
+                copied.record(self._copy_stream)
+            compute.wait_event(copied)
             lab, _ = self.run_device(buf)
             labels[lo:hi] = lab
-            consumed[i].record(compute)
+            free = torch.cuda.Event()
+            free.record(compute)
+            self._stage_free[k] = free
         counts = tally.device_counts(labels, n_classes)
-        return labels.cpu().numpy(), counts.cpu().numpy()
+        slot["labels_h"].copy_(labels, non_blocking=True)
+        slot["counts_h"].copy_(counts, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        slot["done"] = done
+        return PendingResult(slot, done)
+
+    def run_host(self, pcm_host, n_classes: int, n_chunks: int = 2):
+        """Synchronous form of :meth:`submit_host`: returns (labels int32 numpy [B], counts int64
+        numpy [n_classes+1])."""
+        return self.submit_host(pcm_host, n_classes, n_chunks).result()
 
     def run_session(self, pcm_long, speaker_names: Dict[int, str], t0: Optional[datetime] = None,
                     silent_index=()):
