@@ -46,6 +46,10 @@ int64_t mmla_launch_count(void);
 /* CRC-32C (Castagnoli) of a HOST buffer, as stored in TF tensor-bundle entries. Host only. */
 uint32_t mmla_crc32c_host(const void* data_host, size_t n);
 
+/* Diagnostics: when non-NULL, the tensor-core MFCC kernel also writes its raw stage-1 / stage-2
+ * accumulators (per 64-frame tile: 2 x 128 x 256 float32) to this DEVICE buffer.  NULL disables. */
+void mmla_debug_mfcc_tc_dump(float* dev_buffer);
+
 /* ------------------------------------------------------------------------------------------
  * Speaker-ID features.
  * Replaces python_speech_features.mfcc(sig, rate, winlen=0.025, winstep=0.01, nfft=512)
@@ -60,7 +64,7 @@ typedef struct MmlaMfccParams {
     int32_t samplerate;     /* 16000 */
     int32_t frame_len;      /* 400  = round_half_up(winlen*samplerate); must be <= nfft */
     int32_t frame_step;     /* 160  = round_half_up(winstep*samplerate) */
-    int32_t nfft;           /* 512 (the warp FFT is sized for exactly 512) */
+    int32_t nfft;           /* 512 (both DFT kernels are sized for exactly 512) */
     int32_t nfilt;          /* 26 = reference; 40 = BASELINE config 3; <= 64 */
     int32_t numcep;         /* 13; <= 14 and <= nfilt */
     int32_t ceplifter;      /* 22 */

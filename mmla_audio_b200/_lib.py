@@ -17,7 +17,7 @@ SYMBOLS = (
     "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_delta", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
     "mmla_net_forward",
-    "mmla_tally", "mmla_synth_pcm",
+    "mmla_tally", "mmla_synth_pcm", "mmla_debug_mfcc_tc_dump",
 )
 
 
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
         "mmla_net_forward": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, vp, vp]),
         "mmla_tally": (C.c_int, [vp, i64, i32, vp, vp]),
         "mmla_synth_pcm": (C.c_int, [vp, i64, i64, i32, i64, u32, vp, vp]),
+        "mmla_debug_mfcc_tc_dump": (None, [vp]),
     }
     assert set(sigs) == set(SYMBOLS)
     for name, (res, args) in sigs.items():

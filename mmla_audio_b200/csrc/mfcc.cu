@@ -632,6 +632,13 @@ int get_tables(const MmlaMfccParams& p, const MfccTables** out) {
 
 }  // namespace
 
+// csrc/mfcc_tc.cu: tensor-core path for the reference parameterisation
+int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_off_host, const int32_t* clip_len_host,
+                     int64_t n_clips, int32_t clip_len, int64_t clip_stride, const MmlaMfccParams& p, float* out,
+                     int64_t out_clip_stride, cudaStream_t st, float* dbg, int* handled);
+static float* g_tc_dump = nullptr;
+extern "C" __attribute__((visibility("default"))) void mmla_debug_mfcc_tc_dump(float* dev_buffer) { g_tc_dump = dev_buffer; }
+
 extern "C" __attribute__((visibility("default"))) int32_t mmla_psf_num_frames(int64_t n, const MmlaMfccParams* p) {
     if (!p || p->frame_step <= 0) return -1;
     if (n <= p->frame_len) return 1;
@@ -659,6 +666,22 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
     MMLA_REQUIRE((clip_off_host == nullptr) == (clip_len_host == nullptr), MMLA_EINVAL,
                  "mfcc: clip_off_host and clip_len_host must both be given or both be NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    if (clip_off_host == nullptr) {
+        MMLA_REQUIRE(clip_len >= 0 && clip_stride >= 0, MMLA_EINVAL, "mfcc: bad uniform clip geometry");
+        MMLA_REQUIRE((n_clips - 1) * clip_stride + clip_len <= pcm_total, MMLA_EINVAL, "mfcc: clips exceed pcm_total_samples");
+    } else {
+        for (int64_t c = 0; c < n_clips; ++c)
+            MMLA_REQUIRE(clip_len_host[c] >= 0 && clip_off_host[c] >= 0 && clip_off_host[c] + clip_len_host[c] <= pcm_total,
+                         MMLA_EINVAL, "mfcc: clip %lld exceeds pcm_total_samples", static_cast<long long>(c));
+    }
+    {
+        int handled = 0;
+        const int trc = mmla_mfcc_tc_try(pcm, pcm_total, clip_off_host, clip_len_host, n_clips, clip_len, clip_stride, p, out,
+                                         out_clip_stride, st, g_tc_dump, &handled);
+        if (trc != MMLA_OK) return trc;
+        if (handled) return MMLA_OK;
+    }
 
     const MfccTables* tab = nullptr;
     int rc = get_tables(p, &tab);
