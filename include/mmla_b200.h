@@ -46,9 +46,10 @@ int64_t mmla_launch_count(void);
 /* CRC-32C (Castagnoli) of a HOST buffer, as stored in TF tensor-bundle entries. Host only. */
 uint32_t mmla_crc32c_host(const void* data_host, size_t n);
 
-/* Diagnostics: when non-NULL, the tensor-core MFCC kernel also writes its raw stage-1 / stage-2
- * accumulators (per 64-frame tile: 2 x 128 x 256 float32) to this DEVICE buffer.  NULL disables. */
-void mmla_debug_mfcc_tc_dump(float* dev_buffer);
+/* Diagnostics of the tensor-core MFCC kernel (both DEVICE pointers, NULL disables each):
+ *   dev_buffer  receives the raw stage-1 / stage-2 accumulators, per 64-frame tile 2 x 128 x 256 float32;
+ *   dev_stamps  receives clock64 stamps of CTA 0's warp roles, 64 tiles x 32 int64 slots. */
+void mmla_debug_mfcc_tc_dump(float* dev_buffer, long long* dev_stamps);
 
 /* ------------------------------------------------------------------------------------------
  * Speaker-ID features.

@@ -67,7 +67,7 @@ def load() -> C.CDLL:
         "mmla_net_forward": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, vp, vp]),
         "mmla_tally": (C.c_int, [vp, i64, i32, vp, vp]),
         "mmla_synth_pcm": (C.c_int, [vp, i64, i64, i32, i64, u32, vp, vp]),
-        "mmla_debug_mfcc_tc_dump": (None, [vp]),
+        "mmla_debug_mfcc_tc_dump": (None, [vp, vp]),
     }
     assert set(sigs) == set(SYMBOLS)
     for name, (res, args) in sigs.items():

@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B atoms need a 1024-byte aligned base; the launch reserves 1 KB of slack for this
-    TcSmem<NT>& s = *reinterpret_cast<TcSmem<NT>*>(
-        (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+    // (offset added to the __shared__ array itself, not to an integer copy of its address, so the compiler keeps
+    // every access in the shared address space: LDS/STS instead of generic LD/ST)
+    TcSmem<NT>& s = *reinterpret_cast<TcSmem<NT>*>(smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long m0 = static_cast<long long>(blockIdx.x) * 128;
     const int ntile = blockIdx.y;

@@ -92,7 +92,8 @@ __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
 // columns); the two TMEM halves ping-pong so the MMAs of pass p+1 overlap the epilogue of pass p.
 __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs a) {
     extern __shared__ unsigned char smem_dyn[];
-    LstmSmem& s = *reinterpret_cast<LstmSmem*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~static_cast<uintptr_t>(1023));
+    // offset applied to the __shared__ array itself so accesses stay LDS/STS (an integer round-trip makes them generic)
+    LstmSmem& s = *reinterpret_cast<LstmSmem*>(smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
     const int b0 = blockIdx.x * kRows;

@@ -635,9 +635,13 @@ int get_tables(const MmlaMfccParams& p, const MfccTables** out) {
 // csrc/mfcc_tc.cu: tensor-core path for the reference parameterisation
 int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_off_host, const int32_t* clip_len_host,
                      int64_t n_clips, int32_t clip_len, int64_t clip_stride, const MmlaMfccParams& p, float* out,
-                     int64_t out_clip_stride, cudaStream_t st, float* dbg, int* handled);
+                     int64_t out_clip_stride, cudaStream_t st, float* dbg, long long* prof, int* handled);
 static float* g_tc_dump = nullptr;
-extern "C" __attribute__((visibility("default"))) void mmla_debug_mfcc_tc_dump(float* dev_buffer) { g_tc_dump = dev_buffer; }
+static long long* g_tc_prof = nullptr;
+extern "C" __attribute__((visibility("default"))) void mmla_debug_mfcc_tc_dump(float* dev_buffer, long long* dev_stamps) {
+    g_tc_dump = dev_buffer;
+    g_tc_prof = dev_stamps;
+}
 
 extern "C" __attribute__((visibility("default"))) int32_t mmla_psf_num_frames(int64_t n, const MmlaMfccParams* p) {
     if (!p || p->frame_step <= 0) return -1;
@@ -678,7 +682,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
     {
         int handled = 0;
         const int trc = mmla_mfcc_tc_try(pcm, pcm_total, clip_off_host, clip_len_host, n_clips, clip_len, clip_stride, p, out,
-                                         out_clip_stride, st, g_tc_dump, &handled);
+                                         out_clip_stride, st, g_tc_dump, g_tc_prof, &handled);
         if (trc != MMLA_OK) return trc;
         if (handled) return MMLA_OK;
     }

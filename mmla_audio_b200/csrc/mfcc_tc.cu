@@ -28,7 +28,7 @@
 //     them through the descriptor stride.  The frame's zero padding (n1 >= 25) is zero rows of B1.
 //   * MMA warp: stage 1 = per (group, h) a 128x32x32 product, rows (frame, r), K = n1, columns
 //     (k1, re/im), accumulators D1 in TMEM columns [0,256); stage 2 = per pair of k1 a 128x32x32
-//     product, rows (k1 parity, frame), K = (n2, re/im), columns (k2, re/im), D2 in [256,512).
+//     product, rows (k1 parity, frame), K = (n2, re/im), columns (k2 pair: re re im im), D2 in [256,512).
 //     Each product is hi*hi + lo*hi + hi*lo (three kind::f16 passes).
 //   * convert warps (4): read D1 (tcgen05.ld), apply the twiddle (fp32), scale by 2^-5, split to
 //     fp16 hi / lo and transpose into the stage-2 A operand (K-major, no swizzle) in smem.
@@ -65,7 +65,7 @@ constexpr float kS1 = 0.5f;                         // stage-1 operand scale (|y
 constexpr float kS2 = 0.03125f;                     // stage-2 operand scale (|S| <= 8.1e5 -> fp16 range)
 constexpr float kEps = 2.220446049250313e-16f;
 constexpr int kThreads = 448;                       // warps 0-3 epilogue, 4-7 convert, 8-11 signal, 12 TMA, 13 MMA
-constexpr int kXchStride = 41;
+constexpr int kXchStride = 44;                     // >= nfilt + 3; 176-byte rows: 128-bit accesses conflict-free
 
 struct TcSmem {
     alignas(128) unsigned char a2[8][2][kA2Bytes];
@@ -74,15 +74,17 @@ struct TcSmem {
     alignas(128) unsigned char b1[2][2048];          // hi, lo: B1[col][n1], K-major core matrices
     alignas(128) unsigned char b2[2][2048];          // hi, lo: B2[(k2,c')][(n2,c)]
     float2 tw[2][16][8];                             // [h][k1][r] = s2 * W512^((8h+r) k1)
+    float2 k16[8][16];                               // [k2][n2] = s2 * W512^(n2 (16 + 32 k2))
+    float dct[40][16];                               // [m][c] DCT-II(ortho) x lifter; c 0..6 | pad | 7..12 at 8..13
     float s16[2][kTileFrames][20];                   // S[n2][16] of the tile (k1 = 16 column), double buffered
-    float xch[kTileFrames][kXchStride];              // mel partial sums / log-mels between k1 parities
+    alignas(16) float xch[kTileFrames][kXchStride];  // mel partial sums / log-mels between k1 parities
     alignas(8) uint64_t raw_full[2], raw_empty[2];
     alignas(8) uint64_t plane_full[kTileGroups], plane_empty[kTileGroups];
     alignas(8) uint64_t d1_full[kTileGroups], d1_empty[kTileGroups];
     alignas(8) uint64_t s2_done, d2_empty;
     uint32_t tmem_base;
 };
-constexpr int kConstBytes = 4 * 2048 + 2048;         // b1 hi|lo, b2 hi|lo, tw
+constexpr int kConstBytes = 4 * 2048 + 2048 + 1024 + 2560;   // b1 hi|lo, b2 hi|lo, tw, k16, dct
 
 struct TcParams {
     const int16_t* pcm;
@@ -92,6 +94,7 @@ struct TcParams {
     const unsigned char* consts;
     float* out;
     float* dbg;
+    long long* prof;               // DBG builds: clock64 stamps of CTA 0, 32 slots per tile (after the dump area)
     long long n_groups;
     long long clip_stride;
     long long out_clip_stride;
@@ -109,9 +112,9 @@ struct Group {
     bool active;
 };
 
-__device__ __forceinline__ Group decode_group(const TcParams& p, long long G) {
+__device__ __forceinline__ Group decode_group(const TcParams& p, int G) {
     Group g;
-    g.active = G < p.n_groups;
+    g.active = G < static_cast<int>(p.n_groups);
     g.clip = 0; g.clip_off = 0; g.len = 0; g.f0 = 0; g.n_real = 0;
     if (!g.active) return g;
     if (p.groups) {
@@ -119,8 +122,9 @@ __device__ __forceinline__ Group decode_group(const TcParams& p, long long G) {
         g.clip = e.x;
         g.f0 = e.y;
     } else {
-        g.clip = G / p.groups_per_clip;
-        g.f0 = static_cast<int>(G - g.clip * p.groups_per_clip) * kGroupFrames;
+        const int c = static_cast<int>(static_cast<unsigned>(G) / static_cast<unsigned>(p.groups_per_clip));
+        g.clip = c;
+        g.f0 = (G - c * p.groups_per_clip) * kGroupFrames;
     }
     g.clip_off = p.clip_off ? p.clip_off[g.clip] : g.clip * p.clip_stride;
     g.len = p.clip_len_arr ? p.clip_len_arr[g.clip] : p.clip_len;
@@ -129,9 +133,25 @@ __device__ __forceinline__ Group decode_group(const TcParams& p, long long G) {
     return g;
 }
 
-__device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 26); ++i)
-        if (mbar_try_wait(bar, parity)) return;
+// mbarrier wait that parks the warp in hardware (suspend-time hint) instead of polling, so waiting
+// roles do not steal issue slots from working ones; traps instead of hanging the GPU on a logic error.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 22); ++i)
+        if (mbar_try_wait_hint(bar, parity, 100000u)) return;
     asm volatile("trap;");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -151,8 +171,8 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t ad, uint64_t 
         "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// tcgen05.ld of 32 consecutive columns of this thread's TMEM lane; asynchronous until tmem_wait32.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -161,9 +181,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+// Waits for the outstanding tcgen05.ld; the registers are in/out operands so no use can be hoisted above it.
+__device__ __forceinline__ void tmem_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // epilogue warps only
 
@@ -180,10 +207,11 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // Epilogue arithmetic with compile-time bin -> filter maps
 // ---------------------------------------------------------------------------------------------
 template <int NF, int B>
-__device__ __forceinline__ void mel_add(float q, float (&mel)[NF]) {
+__device__ __forceinline__ void mel_add(float q, float (&mel)[NF], float& edge) {
     using Tab = MfccTcTab<NF>;
     constexpr int fa = Tab::fa[B];
     constexpr int fb = Tab::fb[B];
+    constexpr float we = Tab::we[B];
     if constexpr (fa >= 0) {
         constexpr float w = Tab::wa[B];
         mel[fa] = fmaf(w, q, mel[fa]);
@@ -192,73 +220,60 @@ __device__ __forceinline__ void mel_add(float q, float (&mel)[NF]) {
         constexpr float w = Tab::wb[B];
         mel[fb] = fmaf(w, q, mel[fb]);
     }
+    if constexpr (we != 0.f) edge = fmaf(we, q, edge);     // first / last segment, bin 256: the energy remainder
 }
 
-// One D2 column pair: X[k1 + 32 k2] with k1 = 2 J + P.
+// |X|^2 of two bins at once with the packed fp32 pipe: q = re*re + im*im on (bin 2i, bin 2i+1).
+__device__ __forceinline__ void sq2(uint32_t re0, uint32_t re1, uint32_t im0, uint32_t im1, float& q0, float& q1) {
+    asm("{\n.reg .b64 a, b, c;\n"
+        "mov.b64 a, {%2, %3};\n"
+        "mov.b64 b, {%4, %5};\n"
+        "mul.rn.f32x2 c, b, b;\n"
+        "fma.rn.f32x2 c, a, a, c;\n"
+        "mov.b64 {%0, %1}, c;\n}\n"
+        : "=f"(q0), "=f"(q1)
+        : "r"(re0), "r"(re1), "r"(im0), "r"(im1));
+}
 template <int NF, int P, int J, int K2>
-__device__ __forceinline__ void bin_acc(const float (&v)[32], float (&mel)[NF], float& esum) {
+__device__ __forceinline__ void bin_add(float q, float (&mel)[NF], float& edge) {
     constexpr int k1 = 2 * J + P;
     constexpr bool valid = (k1 != 0) || (K2 <= 8);         // k1 = 0: k2 = 9..15 duplicate k2 = 7..1
     if constexpr (valid) {
         constexpr int b = (k1 == 0) ? 32 * K2 : (K2 < 8 ? k1 + 32 * K2 : 512 - k1 - 32 * K2);
-        const float re = v[2 * K2], im = v[2 * K2 + 1];
-        const float q = fmaf(re, re, im * im);
-        esum += q;
-        mel_add<NF, b>(q, mel);
+        mel_add<NF, b>(q, mel, edge);
     }
 }
-template <int NF, int P, int J, int... K2>
-__device__ __forceinline__ void block_acc(const float (&v)[32], float (&mel)[NF], float& esum,
-                                          std::integer_sequence<int, K2...>) {
-    (bin_acc<NF, P, J, K2>(v, mel, esum), ...);
+// D2 block J of this row: columns are grouped (re 2i, re 2i+1, im 2i, im 2i+1) so that both squares
+// of two neighbouring k2 are one packed multiply + one packed fma.
+template <int NF, int P, int J, int I>
+__device__ __forceinline__ void pair_acc(const uint32_t (&v)[32], float (&mel)[NF], float& edge) {
+    constexpr int k1 = 2 * J + P;
+    if constexpr (k1 != 0 || 2 * I <= 8) {
+        float q0, q1;
+        sq2(v[4 * I], v[4 * I + 1], v[4 * I + 2], v[4 * I + 3], q0, q1);
+        bin_add<NF, P, J, 2 * I>(q0, mel, edge);
+        bin_add<NF, P, J, 2 * I + 1>(q1, mel, edge);
+    }
 }
+template <int NF, int P, int J, int... I>
+__device__ __forceinline__ void block_acc(const uint32_t (&v)[32], float (&mel)[NF], float& edge,
+                                          std::integer_sequence<int, I...>) {
+    (pair_acc<NF, P, J, I>(v, mel, edge), ...);
+}
+// Two D2 blocks per step through two register buffers: the tcgen05.ld of the next block is in
+// flight while the current one is accumulated.
 template <int NF, int P, int J>
-__device__ __forceinline__ void d2_block(uint32_t tbase, float (&mel)[NF], float& esum, float* dbg_row) {
-    float v[32];
-    tmem_ld32(tbase + 32 * J, v);
-    if (dbg_row) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) dbg_row[32 * J + c] = v[c];
-    }
-    block_acc<NF, P, J>(v, mel, esum, std::make_integer_sequence<int, 16>{});
-}
-template <int NF, int P, int... J>
-__device__ __forceinline__ void d2_acc(uint32_t tbase, float (&mel)[NF], float& esum, float* dbg_row,
-                                       std::integer_sequence<int, J...>) {
-    (d2_block<NF, P, J>(tbase, mel, esum, dbg_row), ...);
+__device__ __forceinline__ void d2_pair(uint32_t tbase, uint32_t (&va)[32], uint32_t (&vb)[32], float (&mel)[NF],
+                                        float& edge) {
+    using Seq = std::make_integer_sequence<int, 8>;
+    tmem_wait32(va);                                       // block J landed
+    tmem_ld32_issue(tbase + 32 * (J + 1), vb);
+    block_acc<NF, P, J>(va, mel, edge, Seq{});
+    tmem_wait32(vb);                                       // block J+1 landed
+    if constexpr (J + 2 < 8) tmem_ld32_issue(tbase + 32 * (J + 2), va);
+    block_acc<NF, P, J + 1>(vb, mel, edge, Seq{});
 }
 
-// k1 = 16 column: X[16 + 32 k2] = sum_n2 S16[n2] W512^(n2 (16 + 32 k2)), four k2 per parity.
-template <int K2, int N2>
-__device__ __forceinline__ void k16_step(const float (&s)[16], float& re, float& im) {
-    constexpr float cr = MfccTcK16::re[K2 * 16 + N2];
-    constexpr float ci = MfccTcK16::im[K2 * 16 + N2];
-    re = fmaf(s[N2], cr, re);
-    im = fmaf(s[N2], ci, im);
-}
-template <int K2, int... N2>
-__device__ __forceinline__ void k16_dft(const float (&s)[16], float& re, float& im, std::integer_sequence<int, N2...>) {
-    (k16_step<K2, N2>(s, re, im), ...);
-}
-template <int NF, int K2>
-__device__ __forceinline__ void k16_bin(const float (&s)[16], float (&mel)[NF], float& esum) {
-    float re = 0.f, im = 0.f;
-    k16_dft<K2>(s, re, im, std::make_integer_sequence<int, 16>{});
-    const float q = fmaf(re, re, im * im);
-    esum += q;
-    mel_add<NF, 16 + 32 * K2>(q, mel);
-}
-template <int NF, int C, int M>
-__device__ __forceinline__ void dct_step(const float (&lm)[NF], float& acc) {
-    constexpr float w = MfccTcTab<NF>::dct[C * NF + M];
-    acc = fmaf(w, lm[M], acc);
-}
-template <int NF, int C, int... M>
-__device__ __forceinline__ float dct_row(const float (&lm)[NF], std::integer_sequence<int, M...>) {
-    float acc = 0.f;
-    (dct_step<NF, C, M>(lm, acc), ...);
-    return acc;
-}
 template <int NF, int P>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint32_t tmem, int q, int lane, int it,
                                               long long tile) {
@@ -266,82 +281,120 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
     float mel[NF];
 #pragma unroll
     for (int m = 0; m < NF; ++m) mel[m] = 0.f;
-    float esum = 0.f;
-    float* dbg_row = p.dbg ? p.dbg + (tile * 2 + 1) * 128 * 256 + (32 * q + lane) * 256 : nullptr;
-    d2_acc<NF, P>(tmem + (static_cast<uint32_t>(32 * q) << 16) + 256u, mel, esum, dbg_row,
-                  std::make_integer_sequence<int, 8>{});
+    float edge = 0.f;
+    {
+        const uint32_t tbase = tmem + (static_cast<uint32_t>(32 * q) << 16) + 256u;
+        uint32_t va[32], vb[32];
+        tmem_ld32_issue(tbase, va);
+        d2_pair<NF, P, 0>(tbase, va, vb, mel, edge);
+        d2_pair<NF, P, 2>(tbase, va, vb, mel, edge);
+        d2_pair<NF, P, 4>(tbase, va, vb, mel, edge);
+        d2_pair<NF, P, 6>(tbase, va, vb, mel, edge);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&s.d2_empty);                // D2 drained: stage 2 of the next tile may start
+    // ---- k1 = 16 column: X[16 + 32 k2] = sum_n2 S16[n2] W512^(n2 (16 + 32 k2)), k2 = 4P .. 4P+3 ----
     {
-        float sv[16];
-        const float4* src = reinterpret_cast<const float4*>(&s.s16[it & 1][f][0]);
+        const float4* sr = reinterpret_cast<const float4*>(&s.s16[it & 1][f][0]);
+        float q16[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(&sv[4 * i]) = src[i];
-        k16_bin<NF, 4 * P + 0>(sv, mel, esum);
-        k16_bin<NF, 4 * P + 1>(sv, mel, esum);
-        k16_bin<NF, 4 * P + 2>(sv, mel, esum);
-        k16_bin<NF, 4 * P + 3>(sv, mel, esum);
+        for (int i = 0; i < 4; ++i) {
+            const float4* cf = reinterpret_cast<const float4*>(&s.k16[4 * P + i][0]);
+            float re = 0.f, im = 0.f;
+#pragma unroll 1
+            for (int n4 = 0; n4 < 4; ++n4) {
+                const float4 sv = sr[n4];
+                const float4 c0 = cf[2 * n4], c1 = cf[2 * n4 + 1];
+                re = fmaf(sv.x, c0.x, re); im = fmaf(sv.x, c0.y, im);
+                re = fmaf(sv.y, c0.z, re); im = fmaf(sv.y, c0.w, im);
+                re = fmaf(sv.z, c1.x, re); im = fmaf(sv.z, c1.y, im);
+                re = fmaf(sv.w, c1.z, re); im = fmaf(sv.w, c1.w, im);
+            }
+            q16[i] = fmaf(re, re, im * im);
+        }
+        mel_add<NF, 16 + 32 * (4 * P + 0)>(q16[0], mel, edge);
+        mel_add<NF, 16 + 32 * (4 * P + 1)>(q16[1], mel, edge);
+        mel_add<NF, 16 + 32 * (4 * P + 2)>(q16[2], mel, edge);
+        mel_add<NF, 16 + 32 * (4 * P + 3)>(q16[3], mel, edge);
     }
-    // ---- combine the two k1 parities, log, DCT -----------------------------------------------
+    // ---- combine the two k1 parities in smem, then log + DCT as compact loops -------------------
     float* xr = &s.xch[f][0];
-    epi_bar();                                               // previous tile's readers are done
-    if (P == 1) {
+    {
+        float part[kXchStride];
 #pragma unroll
-        for (int m = 0; m < NF; ++m) xr[m] = mel[m];
-        xr[NF] = esum;
-    }
-    epi_bar();
-    if (P == 0) {
-        esum = (esum + xr[NF]) * 8.0f;                       // 1/(512 s1^2 s2^2) = 8
+        for (int m = 0; m < kXchStride; ++m) part[m] = 0.f;
 #pragma unroll
-        for (int m = 0; m < NF; ++m) {
-            float v = mel[m] + xr[m];
-            v = v == 0.f ? kEps : v;
-            mel[m] = __logf(v);
-            xr[m] = mel[m];
+        for (int m = 0; m < NF; ++m) part[m] = mel[m];
+        part[NF] = edge;
+        float4* x4 = reinterpret_cast<float4*>(xr);
+        epi_bar();                                           // previous tile's readers are done
+        if (P == 1) {
+#pragma unroll
+            for (int i = 0; i < kXchStride / 4; ++i) x4[i] = make_float4(part[4 * i], part[4 * i + 1], part[4 * i + 2], part[4 * i + 3]);
         }
+        epi_bar();
+        if (P == 0) {
+#pragma unroll
+            for (int i = 0; i < (NF + 1 + 3) / 4; ++i) {
+                float4 v = x4[i];
+                v.x += part[4 * i]; v.y += part[4 * i + 1]; v.z += part[4 * i + 2]; v.w += part[4 * i + 3];
+                x4[i] = v;
+            }
+        }
+        epi_bar();
+    }
+    {   // each parity takes half of the filters: energy share, zero guard, log
+        constexpr int m0 = P == 0 ? 0 : NF / 2, m1 = P == 0 ? NF / 2 : NF;
+        float esum = 0.f;
+#pragma unroll 2
+        for (int m = m0; m < m1; ++m) {
+            const float v = xr[m];
+            esum += v;
+            xr[m] = __logf(v == 0.f ? kEps : v);
+        }
+        xr[NF + 1 + P] = esum;
     }
     epi_bar();
-    if (P == 1) {
-#pragma unroll
-        for (int m = 0; m < NF; ++m) mel[m] = xr[m];
-    }
     const int g = f >> 4;
-    const Group gr = decode_group(p, tile * kTileGroups + g);
+    const Group gr = decode_group(p, static_cast<int>(tile) * kTileGroups + g);
     const int t = gr.f0 + (f & 15);
+    constexpr int nc = P == 0 ? 7 : 6;
+    float c[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) c[i] = 0.f;
+#pragma unroll 2
+    for (int m = 0; m < NF; ++m) {
+        const float lm = xr[m];
+        const float4* w4 = reinterpret_cast<const float4*>(&s.dct[m][8 * P]);
+        const float4 wa = w4[0], wb = w4[1];
+        c[0] = fmaf(wa.x, lm, c[0]); c[1] = fmaf(wa.y, lm, c[1]); c[2] = fmaf(wa.z, lm, c[2]); c[3] = fmaf(wa.w, lm, c[3]);
+        c[4] = fmaf(wb.x, lm, c[4]); c[5] = fmaf(wb.y, lm, c[5]); c[6] = fmaf(wb.z, lm, c[6]);
+    }
+    if (P == 0 && p.append_energy) {
+        const float e = xr[NF] + xr[NF + 1] + xr[NF + 2];    // = 8 * sum_b q_b = the psf frame energy
+        c[0] = __logf(e == 0.f ? kEps : e);
+    }
     if (gr.active && t < gr.n_real) {
-        float* o = p.out + gr.clip * p.out_clip_stride + static_cast<long long>(t) * p.row_stride;
-        if constexpr (P == 0) {
-            float c[7];
-            c[0] = dct_row<NF, 0>(mel, std::make_integer_sequence<int, NF>{});
-            c[1] = dct_row<NF, 1>(mel, std::make_integer_sequence<int, NF>{});
-            c[2] = dct_row<NF, 2>(mel, std::make_integer_sequence<int, NF>{});
-            c[3] = dct_row<NF, 3>(mel, std::make_integer_sequence<int, NF>{});
-            c[4] = dct_row<NF, 4>(mel, std::make_integer_sequence<int, NF>{});
-            c[5] = dct_row<NF, 5>(mel, std::make_integer_sequence<int, NF>{});
-            c[6] = dct_row<NF, 6>(mel, std::make_integer_sequence<int, NF>{});
-            if (p.append_energy) c[0] = __logf(esum == 0.f ? kEps : esum);
+        float* o = p.out + gr.clip * p.out_clip_stride + static_cast<long long>(t) * p.row_stride + 7 * P;
 #pragma unroll
-            for (int i = 0; i < 7; ++i) o[i] = c[i];
-        } else {
-            float c[6];
-            c[0] = dct_row<NF, 7>(mel, std::make_integer_sequence<int, NF>{});
-            c[1] = dct_row<NF, 8>(mel, std::make_integer_sequence<int, NF>{});
-            c[2] = dct_row<NF, 9>(mel, std::make_integer_sequence<int, NF>{});
-            c[3] = dct_row<NF, 10>(mel, std::make_integer_sequence<int, NF>{});
-            c[4] = dct_row<NF, 11>(mel, std::make_integer_sequence<int, NF>{});
-            c[5] = dct_row<NF, 12>(mel, std::make_integer_sequence<int, NF>{});
-#pragma unroll
-            for (int i = 0; i < 6; ++i) o[7 + i] = c[i];
-        }
+        for (int i = 0; i < nc; ++i) o[i] = c[i];
     }
 }
 
-template <int NF>
+#define TC_STAMP(slot)                                                                         \
+    do {                                                                                       \
+        if constexpr (DBG) {                                                                   \
+            if (p.prof && blockIdx.x == 0 && lane == 0 && it < 64) p.prof[it * 32 + (slot)] = clock64(); \
+        }                                                                                      \
+    } while (0)
+
+template <int NF, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_constant__ TcParams p) {
-    extern __shared__ unsigned char smem_dyn[];
-    TcSmem& s = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~static_cast<uintptr_t>(127));
+    // no static __shared__ in this kernel, so the dynamic window starts at the CTA's shared base (1 KB aligned);
+    // using the array directly keeps every access in the shared address space (LDS/STS, not generic LD/ST)
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    TcSmem& s = *reinterpret_cast<TcSmem*>(smem_dyn);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long n_tiles = (p.n_groups + kTileGroups - 1) / kTileGroups;
     const int my_tiles = blockIdx.x < n_tiles ? static_cast<int>((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
@@ -389,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                 for (int g = 0; g < kTileGroups; ++g) {
                     const int gi = it * kTileGroups + g, rs = gi & 1;
                     if (gi >= 2) wait_or_trap(&s.raw_empty[rs], static_cast<uint32_t>(((gi >> 1) - 1) & 1));
-                    const Group gr = decode_group(p, tile * kTileGroups + g);
+                    if (g == 0) TC_STAMP(0);
+                    const Group gr = decode_group(p, static_cast<int>(tile) * kTileGroups + g);
                     if (gr.active) {
                         const long long gs0 = gr.clip_off + static_cast<long long>(gr.f0) * kStep;
                         const long long gA = gs0 >= 8 ? gs0 - 8 : 0;
@@ -412,23 +466,34 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
             constexpr uint32_t kIdesc2 = (1u << 4) | (static_cast<uint32_t>(32 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
             constexpr uint32_t kIdesc1 = kIdesc2 | (1u << 15);     // A is MN-major in stage 1
             const uint32_t b1a = smem_u32(&s.b1[0][0]), b2a = smem_u32(&s.b2[0][0]);
+            // Base descriptors once; every MMA then adds a compile-time offset (>> 4) to the 14-bit address field
+            // (all operands live below 256 KB, so the field cannot carry).  Measured (scripts/microbench/umma_rate.cu):
+            // an M=128 K=16 SS-mode MMA costs max(N/2, (A+B bytes)/128) ~ 45 cycles at N=32 when issued like this,
+            // 80-200 cycles when the descriptors are rebuilt per instruction.
+            const uint64_t dA1 = desc_noswz(smem_u32(&s.planes[0][0]), 128, kStep);
+            const uint64_t dB1 = desc_noswz(b1a, 128, 512);
+            const uint64_t dA2 = desc_noswz(smem_u32(&s.a2[0][0][0]), kA2Lbo, 128);
+            const uint64_t dB2 = desc_noswz(b2a, 128, 512);
             auto stage1 = [&](int it) {
+#pragma unroll 1
                 for (int g = 0; g < kTileGroups; ++g) {
                     wait_or_trap(&s.plane_full[g], static_cast<uint32_t>(it & 1));
                     if (it >= 1) wait_or_trap(&s.d1_empty[g], static_cast<uint32_t>((it - 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t pl = smem_u32(&s.planes[g][0]);
+                    if (g == 0) TC_STAMP(1);
+                    if (g == 3) TC_STAMP(2);
+                    const uint64_t dAg = dA1 + static_cast<uint64_t>((g * kSlotBytes) >> 4);
+                    const uint32_t dcol = tmem + g * 64;
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
 #pragma unroll
                         for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint32_t a_addr = pl + ((pass == 1 ? 2 : 0) + h) * kPlaneBytes + ks * 256;
-                                const uint32_t b_addr = b1a + (pass == 2 ? 2048 : 0) + ks * 256;
-                                umma_f16(tmem + (2 * g + h) * 32, desc_noswz(a_addr, 128, kStep),
-                                         desc_noswz(b_addr, 128, 512), kIdesc1, (pass | ks) != 0 ? 1u : 0u);
-                            }
+                            for (int ks = 0; ks < 2; ++ks)
+                                umma_f16(dcol + h * 32,
+                                         dAg + static_cast<uint64_t>((((pass == 1 ? 2 : 0) + h) * kPlaneBytes + ks * 256) >> 4),
+                                         dB1 + static_cast<uint64_t>(((pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc1,
+                                         (pass | ks) != 0 ? 1u : 0u);
                     umma_commit_to(&s.plane_empty[g]);
                     umma_commit_to(&s.d1_full[g]);
                 }
@@ -437,18 +502,21 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                 wait_or_trap(&s.d1_empty[kTileGroups - 1], static_cast<uint32_t>(it & 1));   // conversion complete
                 if (it >= 1) wait_or_trap(&s.d2_empty, static_cast<uint32_t>((it - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
+                TC_STAMP(3);
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t dAj = dA2 + static_cast<uint64_t>((j * 2 * kA2Bytes) >> 4);
+                    const uint32_t dcol = tmem + 256 + j * 32;
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint32_t a_addr = smem_u32(&s.a2[j][pass == 1 ? 1 : 0][0]) + ks * 2 * kA2Lbo;
-                            const uint32_t b_addr = b2a + (pass == 2 ? 2048 : 0) + ks * 256;
-                            umma_f16(tmem + 256 + j * 32, desc_noswz(a_addr, kA2Lbo, 128), desc_noswz(b_addr, 128, 512),
-                                     kIdesc2, (pass | ks) != 0 ? 1u : 0u);
-                        }
+                        for (int ks = 0; ks < 2; ++ks)
+                            umma_f16(dcol, dAj + static_cast<uint64_t>(((pass == 1 ? kA2Bytes : 0) + ks * 2 * kA2Lbo) >> 4),
+                                     dB2 + static_cast<uint64_t>(((pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc2,
+                                     (pass | ks) != 0 ? 1u : 0u);
+                }
                 umma_commit_to(&s.s2_done);
+                TC_STAMP(4);
             };
             if (my_tiles > 0) stage1(0);
             for (int it = 0; it < my_tiles; ++it) {
@@ -465,9 +533,10 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
             const long long tile = blockIdx.x + static_cast<long long>(it) * gridDim.x;
             for (int g = 0; g < kTileGroups; ++g) {
                 const int gi = it * kTileGroups + g, rs = gi & 1;
-                const Group gr = decode_group(p, tile * kTileGroups + g);
+                const Group gr = decode_group(p, static_cast<int>(tile) * kTileGroups + g);
                 wait_or_trap(&s.raw_full[rs], static_cast<uint32_t>((gi >> 1) & 1));
                 if (it >= 1) wait_or_trap(&s.plane_empty[g], static_cast<uint32_t>((it - 1) & 1));
+                if (warp == 8) TC_STAMP(8 + 2 * g);
                 const long long gs0 = gr.clip_off + static_cast<long long>(gr.f0) * kStep;
                 const int delta = gs0 >= 8 ? 8 : 0;                      // raw index of the group's first sample
                 const int n_base = gr.f0 * kStep;
@@ -504,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
+                if (warp == 8) TC_STAMP(9 + 2 * g);
                 if (lane == 0) {
                     mbar_arrive(&s.plane_full[g]);
                     mbar_arrive(&s.raw_empty[rs]);
@@ -520,17 +590,27 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
             for (int g = 0; g < kTileGroups; ++g) {
                 wait_or_trap(&s.d1_full[g], static_cast<uint32_t>(it & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 4) TC_STAMP(16 + 2 * g);
                 const int frow = 16 * g + fl;                                 // frame of the tile
-#pragma unroll
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
+                    uint32_t vr[32];
+                    tmem_ld32_issue(tmem + (static_cast<uint32_t>(32 * q) << 16) + (2 * g + h) * 32, vr);
+                    tmem_wait32(vr);
                     float v[32];
-                    tmem_ld32(tmem + (static_cast<uint32_t>(32 * q) << 16) + (2 * g + h) * 32, v);
-                    if (p.dbg) {
-                        float* d = p.dbg + (tile * 2) * 128 * 256 + (32 * q + lane) * 256 + (2 * g + h) * 32;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) d[c] = v[c];
+                    for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vr[c]);
+                    if constexpr (DBG) {
+                        if (p.dbg) {
+                            float* d = p.dbg + (tile * 2) * 128 * 256 + (32 * q + lane) * 256 + (2 * g + h) * 32;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) d[c] = v[c];
+                        }
                     }
                     const int n2 = 8 * h + r;
+                    float2 tw[16];
+#pragma unroll
+                    for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s.tw[h][k1][r];   // all loads before the first store
                     s.s16[it & 1][frow][n2] = v[1];
                     const uint32_t koff = (n2 >> 2) * kA2Lbo + (n2 & 3) * 4;
 #pragma unroll
@@ -540,7 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                             tr = v[0] * kS2;
                             ti = 0.f;
                         } else {
-                            const float2 w = s.tw[h][k1][r];
+                            const float2 w = tw[k1];
                             const float a = v[2 * k1], b = v[2 * k1 + 1];
                             tr = fmaf(a, w.x, -b * w.y);
                             ti = fmaf(a, w.y, b * w.x);
@@ -556,6 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 fence_proxy_async_smem();
                 __syncwarp();
+                if (warp == 4) TC_STAMP(17 + 2 * g);
                 if (lane == 0) mbar_arrive(&s.d1_empty[g]);
             }
         }
@@ -567,8 +648,23 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
             // s2_done(it) also covers the convert warps' s16 stores: stage 2 was issued after d1_empty[3](it)
             wait_or_trap(&s.s2_done, static_cast<uint32_t>(it & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 0) TC_STAMP(24);
+            if constexpr (DBG) {
+                if (p.dbg) {
+                    float* d = p.dbg + (tile * 2 + 1) * 128 * 256 + (32 * q + lane) * 256;
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t vr[32];
+                        tmem_ld32_issue(tmem + (static_cast<uint32_t>(32 * q) << 16) + 256u + 32 * j, vr);
+                        tmem_wait32(vr);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) d[32 * j + c] = __uint_as_float(vr[c]);
+                    }
+                }
+            }
             if (q < 2) epilogue_tile<NF, 0>(p, s, tmem, q, lane, it, tile);
             else epilogue_tile<NF, 1>(p, s, tmem, q, lane, it, tile);
+            if (warp == 0) TC_STAMP(26);
+            if (warp == 3) TC_STAMP(27);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -649,7 +745,7 @@ __global__ void __launch_bounds__(256) mfcc_finish_kernel(const FinParams p) {
 // Host side
 // ---------------------------------------------------------------------------------------------
 std::mutex g_mu;
-std::map<int, unsigned char*> g_consts;      // per device
+std::map<std::pair<int, int>, unsigned char*> g_consts;      // per (device, nfilt)
 
 void put_split(unsigned char* hi, unsigned char* lo, int n, int k, double v) {
     // B[n][k] in the UMMA K-major no-swizzle layout: core matrix (n/8, k/8) = 8 rows x 16 B
@@ -660,11 +756,11 @@ void put_split(unsigned char* hi, unsigned char* lo, int n, int k, double v) {
     memcpy(lo + off, &l, 2);
 }
 
-int get_consts(const unsigned char** out) {
+int get_consts(int nfilt, const unsigned char** out) {
     int dev = 0;
     MMLA_CUDA_CHECK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_consts.find(dev);
+    auto it = g_consts.find(std::make_pair(dev, nfilt));
     if (it != g_consts.end()) {
         *out = it->second;
         return MMLA_OK;
@@ -692,10 +788,11 @@ int get_consts(const unsigned char** out) {
     for (int n2 = 0; n2 < 16; ++n2)
         for (int k2 = 0; k2 < 16; ++k2) {
             const double th = 2.0 * PI * ((n2 * k2) % 16) / 16.0;
-            put_split(b2h, b2l, 2 * k2, 2 * n2, cos(th));
-            put_split(b2h, b2l, 2 * k2, 2 * n2 + 1, sin(th));
-            put_split(b2h, b2l, 2 * k2 + 1, 2 * n2, -sin(th));
-            put_split(b2h, b2l, 2 * k2 + 1, 2 * n2 + 1, cos(th));
+            const int cre = 4 * (k2 >> 1) + (k2 & 1), cim = cre + 2;     // columns: re 2i, re 2i+1, im 2i, im 2i+1
+            put_split(b2h, b2l, cre, 2 * n2, cos(th));
+            put_split(b2h, b2l, cre, 2 * n2 + 1, sin(th));
+            put_split(b2h, b2l, cim, 2 * n2, -sin(th));
+            put_split(b2h, b2l, cim, 2 * n2 + 1, cos(th));
         }
     for (int h = 0; h < 2; ++h)
         for (int k1 = 0; k1 < 16; ++k1)
@@ -703,6 +800,20 @@ int get_consts(const unsigned char** out) {
                 const double th = 2.0 * PI * (((8 * h + r) * k1) % 512) / 512.0;
                 tw[(h * 16 + k1) * 8 + r] = make_float2(static_cast<float>(kS2 * cos(th)), static_cast<float>(-kS2 * sin(th)));
             }
+    float2* k16 = tw + 2 * 16 * 8;
+    for (int k2 = 0; k2 < 8; ++k2)
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const double th = 2.0 * PI * ((n2 * (16 + 32 * k2)) % 512) / 512.0;
+            k16[k2 * 16 + n2] = make_float2(static_cast<float>(kS2 * cos(th)), static_cast<float>(-kS2 * sin(th)));
+        }
+    // DCT-II ortho (scipy.fftpack.dct norm='ortho') with the psf lifter (L = 22) folded in
+    float* dct = reinterpret_cast<float*>(k16 + 8 * 16);
+    for (int c = 0; c < 13; ++c) {
+        const double scale = c == 0 ? sqrt(1.0 / nfilt) : sqrt(2.0 / nfilt);
+        const double lift = 1.0 + (22 / 2.0) * sin(PI * c / 22);
+        for (int m = 0; m < nfilt; ++m)
+            dct[m * 16 + (c < 7 ? c : c + 1)] = static_cast<float>(lift * scale * cos(PI * c * (2 * m + 1) / (2.0 * nfilt)));
+    }
     unsigned char* devp = nullptr;
     cudaError_t e = cudaMalloc(&devp, kConstBytes);
     if (e == cudaSuccess) e = cudaMemcpy(devp, host.data(), kConstBytes, cudaMemcpyHostToDevice);
@@ -710,20 +821,20 @@ int get_consts(const unsigned char** out) {
         mmla_set_error("mfcc_tc constants upload failed: %s", cudaGetErrorString(e));
         return MMLA_ECUDA;
     }
-    g_consts[dev] = devp;
+    g_consts[std::make_pair(dev, nfilt)] = devp;
     *out = devp;
     return MMLA_OK;
 }
 
-template <int NF>
+template <int NF, bool DBG>
 int launch_tc(const TcParams& kp, long long grid, cudaStream_t st) {
     static bool attr_set = false;
-    const int smem = static_cast<int>(sizeof(TcSmem) + 128);
+    const int smem = static_cast<int>(sizeof(TcSmem));
     if (!attr_set) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(mfcc_tc_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(mfcc_tc_kernel<NF, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    mfcc_tc_kernel<NF><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(kp);
+    mfcc_tc_kernel<NF, DBG><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(kp);
     mmla_count_launch();
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
@@ -734,9 +845,10 @@ int launch_tc(const TcParams& kp, long long grid, cudaStream_t st) {
 // Returns MMLA_OK and *handled = 1 when the tensor-core path ran; *handled = 0 when the
 // parameters are outside what it is specialised for (the caller then uses the general kernel).
 // `dbg` (device, or null): per tile [D1 | D2] raw accumulators, 2 x 128 x 256 floats.
+// `prof` (device, or null): clock64 stamps of CTA 0, 64 tiles x 32 slots.
 int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_off_host, const int32_t* clip_len_host,
                      int64_t n_clips, int32_t clip_len, int64_t clip_stride, const MmlaMfccParams& p, float* out,
-                     int64_t out_clip_stride, cudaStream_t st, float* dbg, int* handled) {
+                     int64_t out_clip_stride, cudaStream_t st, float* dbg, long long* prof, int* handled) {
     *handled = 0;
     const char* force = getenv("MMLA_MFCC_KERNEL");
     if (force && strcmp(force, "fft") == 0) return MMLA_OK;
@@ -775,7 +887,7 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     if (n_groups == 0) return MMLA_OK;
 
     const unsigned char* consts = nullptr;
-    int rc = get_consts(&consts);
+    int rc = get_consts(p.nfilt, &consts);
     if (rc != MMLA_OK) return rc;
 
     TcParams kp;
@@ -784,6 +896,7 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     kp.consts = consts;
     kp.out = out;
     kp.dbg = dbg;
+    kp.prof = prof;
     kp.n_groups = n_groups;
     kp.clip_stride = clip_stride;
     kp.out_clip_stride = out_clip_stride;
@@ -819,7 +932,8 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     MMLA_REQUIRE(sms > 0, MMLA_ECUDA, "mfcc_tc: no CUDA device");
     const long long n_tiles = (n_groups + kTileGroups - 1) / kTileGroups;
     const long long grid = n_tiles < sms ? n_tiles : sms;
-    rc = p.nfilt == 26 ? launch_tc<26>(kp, grid, st) : launch_tc<40>(kp, grid, st);
+    if (dbg || prof) rc = p.nfilt == 26 ? launch_tc<26, true>(kp, grid, st) : launch_tc<40, true>(kp, grid, st);
+    else rc = p.nfilt == 26 ? launch_tc<26, false>(kp, grid, st) : launch_tc<40, false>(kp, grid, st);
     if (rc != MMLA_OK) return rc;
 
     const bool need_finish = p.with_deltas || p.pad_frames > 0;

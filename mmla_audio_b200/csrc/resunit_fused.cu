@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(C >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);
     extern __shared__ unsigned char smem_dyn[];
-    RuSmem<CIN, C, POOL>& s = *reinterpret_cast<RuSmem<CIN, C, POOL>*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~static_cast<uintptr_t>(127));
+    // offset applied to the __shared__ array itself so accesses stay LDS/STS (an integer round-trip makes them generic)
+    RuSmem<CIN, C, POOL>& s = *reinterpret_cast<RuSmem<CIN, C, POOL>*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = a.G, T = a.T;
     const int clip0 = blockIdx.x * G;

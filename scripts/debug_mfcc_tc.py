@@ -19,11 +19,11 @@ gpc = (T + 15) // 16
 n_groups = n_clips * gpc
 n_tiles = (n_groups + 3) // 4
 dbg = torch.full((n_tiles, 2, 128, 256), float("nan"), dtype=torch.float32, device="cuda")
-lib.mmla_debug_mfcc_tc_dump(dbg.data_ptr())
+lib.mmla_debug_mfcc_tc_dump(dbg.data_ptr(), None)
 out = torch.empty((n_clips, T, 13), dtype=torch.float32, device="cuda")
 si.mfcc_batch(pcm, cfg, out=out)
 torch.cuda.synchronize()
-lib.mmla_debug_mfcc_tc_dump(None)
+lib.mmla_debug_mfcc_tc_dump(None, None)
 d = dbg.cpu().numpy().astype(np.float64)
 got = out.cpu().numpy()
 
@@ -66,7 +66,8 @@ for tile in range(n_tiles):
                     k1 = 2 * j + p
                     for k2 in range(16):
                         v = X[k1 + 32 * k2]
-                        gr_, gi_ = d[tile, 1, row, j * 32 + 2 * k2], d[tile, 1, row, j * 32 + 2 * k2 + 1]
+                        cre = 4 * (k2 >> 1) + (k2 & 1)
+                        gr_, gi_ = d[tile, 1, row, j * 32 + cre], d[tile, 1, row, j * 32 + cre + 2]
                         e2 = max(e2, abs(gr_ - v.real), abs(gi_ - v.imag))
                         s2max = max(s2max, abs(v))
 print(f"stage 1: max abs err {e1:.4g} (scale {s1max:.4g}, rel {e1 / max(s1max, 1e-30):.3g})")
