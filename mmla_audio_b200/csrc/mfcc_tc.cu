@@ -161,6 +161,13 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint
     return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
            (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+// One lane of the (converged) warp; the surrounding control flow stays warp-uniform so descriptors live in
+// uniform registers and UTCHMMA issues without a per-instruction R2UR waterfall.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -302,7 +309,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
         for (int i = 0; i < 4; ++i) {
             const float4* cf = reinterpret_cast<const float4*>(&s.k16[4 * P + i][0]);
             float re = 0.f, im = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int n4 = 0; n4 < 4; ++n4) {
                 const float4 sv = sr[n4];
                 const float4 c0 = cf[2 * n4], c1 = cf[2 * n4 + 1];
@@ -347,7 +354,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
     {   // each parity takes half of the filters: energy share, zero guard, log
         constexpr int m0 = P == 0 ? 0 : NF / 2, m1 = P == 0 ? NF / 2 : NF;
         float esum = 0.f;
-#pragma unroll 2
+#pragma unroll
         for (int m = m0; m < m1; ++m) {
             const float v = xr[m];
             esum += v;
@@ -363,7 +370,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
     float c[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) c[i] = 0.f;
-#pragma unroll 2
+#pragma unroll 5
     for (int m = 0; m < NF; ++m) {
         const float lm = xr[m];
         const float4* w4 = reinterpret_cast<const float4*>(&s.dct[m][8 * P]);
@@ -461,8 +468,8 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
         }
         __syncwarp();
     } else if (warp == 13) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+        {
             constexpr uint32_t kIdesc2 = (1u << 4) | (static_cast<uint32_t>(32 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
             constexpr uint32_t kIdesc1 = kIdesc2 | (1u << 15);     // A is MN-major in stage 1
             const uint32_t b1a = smem_u32(&s.b1[0][0]), b2a = smem_u32(&s.b2[0][0]);
@@ -484,18 +491,21 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                     if (g == 3) TC_STAMP(2);
                     const uint64_t dAg = dA1 + static_cast<uint64_t>((g * kSlotBytes) >> 4);
                     const uint32_t dcol = tmem + g * 64;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                        for (int h = 0; h < 2; ++h)
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass)
+                            for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks)
-                                umma_f16(dcol + h * 32,
-                                         dAg + static_cast<uint64_t>((((pass == 1 ? 2 : 0) + h) * kPlaneBytes + ks * 256) >> 4),
-                                         dB1 + static_cast<uint64_t>(((pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc1,
-                                         (pass | ks) != 0 ? 1u : 0u);
-                    umma_commit_to(&s.plane_empty[g]);
-                    umma_commit_to(&s.d1_full[g]);
+                                for (int ks = 0; ks < 2; ++ks)
+                                    umma_f16(dcol + h * 32,
+                                             dAg + static_cast<uint64_t>((((pass == 1 ? 2 : 0) + h) * kPlaneBytes + ks * 256) >> 4),
+                                             dB1 + static_cast<uint64_t>(((pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc1,
+                                             (pass | ks) != 0 ? 1u : 0u);
+                        umma_commit_to(&s.plane_empty[g]);
+                        umma_commit_to(&s.d1_full[g]);
+                    }
+                    __syncwarp();
                 }
             };
             auto stage2 = [&](int it) {
@@ -507,15 +517,18 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                 for (int j = 0; j < 8; ++j) {
                     const uint64_t dAj = dA2 + static_cast<uint64_t>((j * 2 * kA2Bytes) >> 4);
                     const uint32_t dcol = tmem + 256 + j * 32;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass)
+                        for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks)
-                            umma_f16(dcol, dAj + static_cast<uint64_t>(((pass == 1 ? kA2Bytes : 0) + ks * 2 * kA2Lbo) >> 4),
-                                     dB2 + static_cast<uint64_t>(((pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc2,
-                                     (pass | ks) != 0 ? 1u : 0u);
+                            for (int ks = 0; ks < 2; ++ks)
+                                umma_f16(dcol, dAj + static_cast<uint64_t>(((pass == 1 ? kA2Bytes : 0) + ks * 2 * kA2Lbo) >> 4),
+                                         dB2 + static_cast<uint64_t>(((pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc2,
+                                         (pass | ks) != 0 ? 1u : 0u);
+                        if (j == 7) umma_commit_to(&s.s2_done);
+                    }
+                    __syncwarp();
                 }
-                umma_commit_to(&s.s2_done);
                 TC_STAMP(4);
             };
             if (my_tiles > 0) stage1(0);
@@ -544,18 +557,33 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                 const uint4* raw4 = reinterpret_cast<const uint4*>(&s.raw[rs][0]);
                 const unsigned short* raw16 = reinterpret_cast<const unsigned short*>(&s.raw[rs][0]);
                 unsigned char* slot = &s.planes[g][0];
-                for (int c8 = ts; c8 < kChunks; c8 += 128) {
-                    const int m0 = 8 * c8, n0 = n_base + m0, r0 = delta + m0;
+                // chunks ts, ts+128, ts+256 of the group: all loads first, then three independent convert chains
+                uint4 w[3];
+                uint32_t prev16[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int c8 = ts + 128 * u;
+                    const int r0 = delta + 8 * c8;
+                    w[u] = make_uint4(0u, 0u, 0u, 0u);
+                    prev16[u] = 0u;
+                    if (c8 < kChunks && n_base + 8 * c8 < len) {
+                        w[u] = raw4[r0 >> 3];
+                        prev16[u] = r0 > 0 ? raw16[r0 - 1] : 0u;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int c8 = ts + 128 * u;
+                    if (c8 >= kChunks) break;
+                    const int n0 = n_base + 8 * c8;
                     uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
                     if (n0 < len) {
-                        const uint4 w = raw4[r0 >> 3];
-                        const uint32_t prev16 = r0 > 0 ? raw16[r0 - 1] : 0u;
                         float x[9];
-                        x[0] = n0 > 0 ? s16_bits_to_float(prev16) : 0.f;          // y[0] = x[0]
-                        x[1] = s16_bits_to_float(w.x & 0xffffu); x[2] = s16_bits_to_float(w.x >> 16);
-                        x[3] = s16_bits_to_float(w.y & 0xffffu); x[4] = s16_bits_to_float(w.y >> 16);
-                        x[5] = s16_bits_to_float(w.z & 0xffffu); x[6] = s16_bits_to_float(w.z >> 16);
-                        x[7] = s16_bits_to_float(w.w & 0xffffu); x[8] = s16_bits_to_float(w.w >> 16);
+                        x[0] = n0 > 0 ? s16_bits_to_float(prev16[u]) : 0.f;          // y[0] = x[0]
+                        x[1] = s16_bits_to_float(w[u].x & 0xffffu); x[2] = s16_bits_to_float(w[u].x >> 16);
+                        x[3] = s16_bits_to_float(w[u].y & 0xffffu); x[4] = s16_bits_to_float(w[u].y >> 16);
+                        x[5] = s16_bits_to_float(w[u].z & 0xffffu); x[6] = s16_bits_to_float(w[u].z >> 16);
+                        x[7] = s16_bits_to_float(w[u].w & 0xffffu); x[8] = s16_bits_to_float(w[u].w >> 16);
                         float y[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -587,57 +615,71 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
         for (int it = 0; it < my_tiles; ++it) {
             const long long tile = blockIdx.x + static_cast<long long>(it) * gridDim.x;
             if (it >= 1) wait_or_trap(&s.s2_done, static_cast<uint32_t>((it - 1) & 1));    // A2 free again
-            for (int g = 0; g < kTileGroups; ++g) {
-                wait_or_trap(&s.d1_full[g], static_cast<uint32_t>(it & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (warp == 4) TC_STAMP(16 + 2 * g);
+            // blocks b = 2 g + h; the tcgen05.ld of block b+1 is in flight while block b is converted
+            uint32_t va[32], vb[32];
+            const uint32_t tlane = tmem + (static_cast<uint32_t>(32 * q) << 16);
+            auto convert_block = [&](const uint32_t (&vr)[32], int g, int h) {
                 const int frow = 16 * g + fl;                                 // frame of the tile
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t vr[32];
-                    tmem_ld32_issue(tmem + (static_cast<uint32_t>(32 * q) << 16) + (2 * g + h) * 32, vr);
-                    tmem_wait32(vr);
-                    float v[32];
+                float v[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vr[c]);
-                    if constexpr (DBG) {
-                        if (p.dbg) {
-                            float* d = p.dbg + (tile * 2) * 128 * 256 + (32 * q + lane) * 256 + (2 * g + h) * 32;
+                for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(vr[c]);
+                if constexpr (DBG) {
+                    if (p.dbg) {
+                        float* d = p.dbg + (tile * 2) * 128 * 256 + (32 * q + lane) * 256 + (2 * g + h) * 32;
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) d[c] = v[c];
-                        }
-                    }
-                    const int n2 = 8 * h + r;
-                    float2 tw[16];
-#pragma unroll
-                    for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s.tw[h][k1][r];   // all loads before the first store
-                    s.s16[it & 1][frow][n2] = v[1];
-                    const uint32_t koff = (n2 >> 2) * kA2Lbo + (n2 & 3) * 4;
-#pragma unroll
-                    for (int k1 = 0; k1 < 16; ++k1) {
-                        float tr, ti;
-                        if (k1 == 0) {
-                            tr = v[0] * kS2;
-                            ti = 0.f;
-                        } else {
-                            const float2 w = tw[k1];
-                            const float a = v[2 * k1], b = v[2 * k1 + 1];
-                            tr = fmaf(a, w.x, -b * w.y);
-                            ti = fmaf(a, w.y, b * w.x);
-                        }
-                        uint32_t hi, lo;
-                        split2(tr, ti, hi, lo);
-                        const int row = (k1 & 1) * 64 + frow;
-                        const uint32_t off = koff + (row >> 3) * 128 + (row & 7) * 16;
-                        *reinterpret_cast<uint32_t*>(&s.a2[k1 >> 1][0][off]) = hi;
-                        *reinterpret_cast<uint32_t*>(&s.a2[k1 >> 1][1][off]) = lo;
+                        for (int c = 0; c < 32; ++c) d[c] = v[c];
                     }
                 }
+                const int n2 = 8 * h + r;
+                float2 tw[16];
+#pragma unroll
+                for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s.tw[h][k1][r];   // all loads before the first store
+                s.s16[it & 1][frow][n2] = v[1];
+                const uint32_t koff = (n2 >> 2) * kA2Lbo + (n2 & 3) * 4 + (frow >> 3) * 128 + (frow & 7) * 16;
+#pragma unroll
+                for (int k1 = 0; k1 < 16; ++k1) {
+                    float tr, ti;
+                    if (k1 == 0) {
+                        tr = v[0] * kS2;
+                        ti = 0.f;
+                    } else {
+                        const float2 w = tw[k1];
+                        const float a = v[2 * k1], b = v[2 * k1 + 1];
+                        tr = fmaf(a, w.x, -b * w.y);
+                        ti = fmaf(a, w.y, b * w.x);
+                    }
+                    uint32_t hi, lo;
+                    split2(tr, ti, hi, lo);
+                    const uint32_t off = koff + (k1 & 1) * 1024;               // rows 64.. of the pair: +8 row groups
+                    *reinterpret_cast<uint32_t*>(&s.a2[k1 >> 1][0][off]) = hi;
+                    *reinterpret_cast<uint32_t*>(&s.a2[k1 >> 1][1][off]) = lo;
+                }
+            };
+            auto block_done = [&](int g) {
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (warp == 4) TC_STAMP(17 + 2 * g);
                 if (lane == 0) mbar_arrive(&s.d1_empty[g]);
+            };
+            wait_or_trap(&s.d1_full[0], static_cast<uint32_t>(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 4) TC_STAMP(16);
+            tmem_ld32_issue(tlane, va);
+#pragma unroll 1
+            for (int g = 0; g < kTileGroups; ++g) {
+                tmem_wait32(va);                                              // block (g, 0)
+                tmem_ld32_issue(tlane + (2 * g + 1) * 32, vb);
+                convert_block(va, g, 0);
+                tmem_wait32(vb);                                              // block (g, 1)
+                if (g + 1 < kTileGroups) {
+                    wait_or_trap(&s.d1_full[g + 1], static_cast<uint32_t>(it & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (warp == 4) TC_STAMP(16 + 2 * (g + 1));
+                    tmem_ld32_issue(tlane + (2 * g + 2) * 32, va);
+                }
+                convert_block(vb, g, 1);
+                block_done(g);
             }
         }
     } else {
