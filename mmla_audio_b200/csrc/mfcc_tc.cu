@@ -326,15 +326,18 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
         mel_add<NF, 16 + 32 * (4 * P + 3)>(q16[3], mel, edge);
     }
     // ---- combine the two k1 parities in smem, then log + DCT as compact loops -------------------
-    float* xr = &s.xch[f][0];
+    // Row layout (176-byte rows, every access 128-bit => conflict-free): [0, NFP) mel sums (zero padded
+    // past NF), [NFP] energy remainder, [NFP + 1 + parity] energy share of that parity's filter half.
+    constexpr int NFP = (NF + 3) & ~3, NG = NFP / 4;
+    static_assert(NFP + 3 <= kXchStride, "xch row too short");
+    float4* x4 = reinterpret_cast<float4*>(&s.xch[f][0]);
     {
         float part[kXchStride];
 #pragma unroll
         for (int m = 0; m < kXchStride; ++m) part[m] = 0.f;
 #pragma unroll
         for (int m = 0; m < NF; ++m) part[m] = mel[m];
-        part[NF] = edge;
-        float4* x4 = reinterpret_cast<float4*>(xr);
+        part[NFP] = edge;
         epi_bar();                                           // previous tile's readers are done
         if (P == 1) {
 #pragma unroll
@@ -343,7 +346,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
         epi_bar();
         if (P == 0) {
 #pragma unroll
-            for (int i = 0; i < (NF + 1 + 3) / 4; ++i) {
+            for (int i = 0; i <= NG; ++i) {
                 float4 v = x4[i];
                 v.x += part[4 * i]; v.y += part[4 * i + 1]; v.z += part[4 * i + 2]; v.w += part[4 * i + 3];
                 x4[i] = v;
@@ -351,17 +354,25 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
         }
         epi_bar();
     }
-    {   // each parity takes half of the filters: energy share, zero guard, log
-        constexpr int m0 = P == 0 ? 0 : NF / 2, m1 = P == 0 ? NF / 2 : NF;
+    float e_tail;
+    {   // each parity takes half of the filter quads: energy share, zero guard, log
+        constexpr int g0 = P == 0 ? 0 : (NG + 1) / 2, g1 = P == 0 ? (NG + 1) / 2 : NG;
         float esum = 0.f;
+        float4 v[g1 - g0];
 #pragma unroll
-        for (int m = m0; m < m1; ++m) {
-            const float v = xr[m];
-            esum += v;
-            xr[m] = __logf(v == 0.f ? kEps : v);
+        for (int i = g0; i < g1; ++i) v[i - g0] = x4[i];
+#pragma unroll
+        for (int i = g0; i < g1; ++i) {
+            float4& q = v[i - g0];
+            esum += (q.x + q.y) + (q.z + q.w);                // padding entries are exact zeros
+            q.x = __logf(q.x == 0.f ? kEps : q.x); q.y = __logf(q.y == 0.f ? kEps : q.y);
+            q.z = __logf(q.z == 0.f ? kEps : q.z); q.w = __logf(q.w == 0.f ? kEps : q.w);
+            x4[i] = q;
         }
-        xr[NF + 1 + P] = esum;
+        e_tail = esum;
     }
+    // the two energy shares meet through one word each (different banks per lane: stride 44 words, +1)
+    s.xch[f][NFP + 1 + P] = e_tail;
     epi_bar();
     const int g = f >> 4;
     const Group gr = decode_group(p, static_cast<int>(tile) * kTileGroups + g);
@@ -370,16 +381,22 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
     float c[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) c[i] = 0.f;
-#pragma unroll 5
-    for (int m = 0; m < NF; ++m) {
-        const float lm = xr[m];
-        const float4* w4 = reinterpret_cast<const float4*>(&s.dct[m][8 * P]);
-        const float4 wa = w4[0], wb = w4[1];
-        c[0] = fmaf(wa.x, lm, c[0]); c[1] = fmaf(wa.y, lm, c[1]); c[2] = fmaf(wa.z, lm, c[2]); c[3] = fmaf(wa.w, lm, c[3]);
-        c[4] = fmaf(wb.x, lm, c[4]); c[5] = fmaf(wb.y, lm, c[5]); c[6] = fmaf(wb.z, lm, c[6]);
+#pragma unroll 2
+    for (int i = 0; i < NG; ++i) {
+        const float4 lm4 = x4[i];
+        const float lm[4] = {lm4.x, lm4.y, lm4.z, lm4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4* w4 = reinterpret_cast<const float4*>(&s.dct[4 * i + u][8 * P]);   // rows >= NF are zero
+            const float4 wa = w4[0], wb = w4[1];
+            c[0] = fmaf(wa.x, lm[u], c[0]); c[1] = fmaf(wa.y, lm[u], c[1]); c[2] = fmaf(wa.z, lm[u], c[2]);
+            c[3] = fmaf(wa.w, lm[u], c[3]); c[4] = fmaf(wb.x, lm[u], c[4]); c[5] = fmaf(wb.y, lm[u], c[5]);
+            c[6] = fmaf(wb.z, lm[u], c[6]);
+        }
     }
     if (P == 0 && p.append_energy) {
-        const float e = xr[NF] + xr[NF + 1] + xr[NF + 2];    // = 8 * sum_b q_b = the psf frame energy
+        const float4 tail = x4[NG];                          // [edge, share 0, share 1, -]
+        const float e = tail.x + tail.y + tail.z;            // = 8 * sum_b q_b = the psf frame energy
         c[0] = __logf(e == 0.f ? kEps : e);
     }
     if (gr.active && t < gr.n_real) {
@@ -566,10 +583,11 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                     const int r0 = delta + 8 * c8;
                     w[u] = make_uint4(0u, 0u, 0u, 0u);
                     prev16[u] = 0u;
-                    if (c8 < kChunks && n_base + 8 * c8 < len) {
-                        w[u] = raw4[r0 >> 3];
-                        prev16[u] = r0 > 0 ? raw16[r0 - 1] : 0u;
-                    }
+                    if (c8 < kChunks && n_base + 8 * c8 < len) w[u] = raw4[r0 >> 3];
+                    // the sample before this chunk is the last one of the neighbouring lane's chunk; only lane 0
+                    // reads it from shared memory (a 2-byte load per lane would be a 4-way bank conflict)
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, w[u].w, 1) >> 16;
+                    prev16[u] = lane > 0 ? up : ((c8 < kChunks && r0 > 0) ? raw16[r0 - 1] : 0u);
                 }
 #pragma unroll
                 for (int u = 0; u < 3; ++u) {
