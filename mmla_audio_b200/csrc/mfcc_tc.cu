@@ -55,9 +55,10 @@ constexpr int kFrameLen = 400, kStep = 160;
 constexpr int kGroupFrames = 16, kTileGroups = 4, kTileFrames = 64;
 constexpr int kGroupSamples = 2912;                 // 15*160 + 32*16: samples one group's MMAs touch
 constexpr int kChunks = kGroupSamples / 8;          // 364 8-sample chunks
-constexpr int kPlaneBytes = 3008;                   // 182 chunks x 16 B, padded; = 64 mod 128 so the
-                                                    // two chunk-parity planes sit 16 banks apart
-constexpr int kSlotBytes = 4 * kPlaneBytes;         // [hi|lo][h]
+constexpr int kPlaneBytes = 2944;                   // 184 chunks x 16 B
+constexpr int kPlaneH = kPlaneBytes + 64;           // h = 1 plane: = 64 mod 128 past h = 0, i.e. 16 banks apart
+constexpr int kPlaneLo = kPlaneH + kPlaneBytes;     // the fp16 "lo" pair of planes follows the "hi" pair
+constexpr int kSlotBytes = 2 * kPlaneLo;            // [hi|lo][h] = 11904 bytes
 constexpr int kRawBytes = 5888;                     // 8 + 2912 samples, padded
 constexpr int kA2Lbo = 2112;                        // K-group stride of the stage-2 A operand
 constexpr int kA2Bytes = 4 * kA2Lbo;                // one (k1 pair, hi|lo) operand: 128 rows x 32 halves
@@ -71,11 +72,11 @@ struct TcSmem {
     alignas(128) unsigned char a2[8][2][kA2Bytes];
     alignas(128) unsigned char planes[kTileGroups][kSlotBytes];
     alignas(128) unsigned char raw[2][kRawBytes];
-    alignas(128) unsigned char b1[2][2048];          // hi, lo: B1[col][n1], K-major core matrices
+    alignas(128) unsigned char b1[2][2][2048];       // [h][hi|lo]: B1[col][n1], K-major core matrices; the h = 1 copy
+                                                     // carries the W64^k1 half of the twiddle (angle (2 n1 + 1) k1 / 64)
     alignas(128) unsigned char b2[2][2048];          // hi, lo: B2[(k2,c')][(n2,c)]
-    float2 tw[2][16][8];                             // [h][k1][r] = s2 * W512^((8h+r) k1)
     float2 k16[8][16];                               // [k2][n2] = s2 * W512^(n2 (16 + 32 k2))
-    float dct[40][16];                               // [m][c] DCT-II(ortho) x lifter; c 0..6 | pad | 7..12 at 8..13
+    float dct[40][16];                               // [m][c] DCT-II(ortho) x lifter; c 0..6 at 0..6, 7..12 at 8..13
     float s16[2][kTileFrames][20];                   // S[n2][16] of the tile (k1 = 16 column), double buffered
     alignas(16) float xch[kTileFrames][kXchStride];  // mel partial sums / log-mels between k1 parities
     alignas(8) uint64_t raw_full[2], raw_empty[2];
@@ -84,7 +85,9 @@ struct TcSmem {
     alignas(8) uint64_t s2_done, d2_empty;
     uint32_t tmem_base;
 };
-constexpr int kConstBytes = 4 * 2048 + 2048 + 1024 + 2560;   // b1 hi|lo, b2 hi|lo, tw, k16, dct
+static_assert(sizeof(TcSmem) <= 227 * 1024, "TcSmem exceeds the 227 KB a CTA can own");
+constexpr int kConstSmemBytes = 6 * 2048 + 1024 + 2560;   // b1 [h][hi|lo], b2 hi|lo, k16, dct -> shared memory
+constexpr int kConstBytes = kConstSmemBytes + 1024;       // + twr [k1][r] (read once into registers)
 
 struct TcParams {
     const int16_t* pcm;
@@ -426,8 +429,8 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
     // ---- one-time setup -------------------------------------------------------------------------
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.consts);
-        uint4* dst = reinterpret_cast<uint4*>(&s.b1[0][0]);          // b1, b2, tw are contiguous
-        for (int i = tid; i < kConstBytes / 16; i += kThreads) dst[i] = src[i];
+        uint4* dst = reinterpret_cast<uint4*>(&s.b1[0][0][0]);       // b1, b2, k16 are contiguous
+        for (int i = tid; i < kConstSmemBytes / 16; i += kThreads) dst[i] = src[i];
         uint4* z = reinterpret_cast<uint4*>(&s.a2[0][0][0]);          // operand buffers: finite everywhere
         for (int i = tid; i < static_cast<int>(sizeof(s.a2) + sizeof(s.planes)) / 16; i += kThreads)
             z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
         {
             constexpr uint32_t kIdesc2 = (1u << 4) | (static_cast<uint32_t>(32 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
             constexpr uint32_t kIdesc1 = kIdesc2 | (1u << 15);     // A is MN-major in stage 1
-            const uint32_t b1a = smem_u32(&s.b1[0][0]), b2a = smem_u32(&s.b2[0][0]);
+            const uint32_t b1a = smem_u32(&s.b1[0][0][0]), b2a = smem_u32(&s.b2[0][0]);
             // Base descriptors once; every MMA then adds a compile-time offset (>> 4) to the 14-bit address field
             // (all operands live below 256 KB, so the field cannot carry).  Measured (scripts/microbench/umma_rate.cu):
             // an M=128 K=16 SS-mode MMA costs max(N/2, (A+B bytes)/128) ~ 45 cycles at N=32 when issued like this,
@@ -516,8 +519,8 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
 #pragma unroll
                                 for (int ks = 0; ks < 2; ++ks)
                                     umma_f16(dcol + h * 32,
-                                             dAg + static_cast<uint64_t>((((pass == 1 ? 2 : 0) + h) * kPlaneBytes + ks * 256) >> 4),
-                                             dB1 + static_cast<uint64_t>(((pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc1,
+                                             dAg + static_cast<uint64_t>(((pass == 1 ? kPlaneLo : 0) + h * kPlaneH + ks * 256) >> 4),
+                                             dB1 + static_cast<uint64_t>((h * 4096 + (pass == 2 ? 2048 : 0) + ks * 256) >> 4), kIdesc1,
                                              (pass | ks) != 0 ? 1u : 0u);
                         umma_commit_to(&s.plane_empty[g]);
                         umma_commit_to(&s.d1_full[g]);
@@ -614,8 +617,8 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                         split2(y[6], y[7], hi4.w, lo4.w);
                     }
                     const int h = c8 & 1, j16 = (c8 >> 1) * 16;
-                    *reinterpret_cast<uint4*>(slot + h * kPlaneBytes + j16) = hi4;
-                    *reinterpret_cast<uint4*>(slot + (2 + h) * kPlaneBytes + j16) = lo4;
+                    *reinterpret_cast<uint4*>(slot + h * kPlaneH + j16) = hi4;
+                    *reinterpret_cast<uint4*>(slot + kPlaneLo + h * kPlaneH + j16) = lo4;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -630,6 +633,14 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
         // ================= convert warps: D1 -> twiddle -> fp16 hi/lo stage-2 operand =================
         const int q = warp - 4;
         const int fl = 4 * q + (lane >> 3), r = lane & 7;
+        // s2 * W512^(r k1): the part of the twiddle W512^((8 h + r) k1) that depends on the lane; the W64^(h k1)
+        // part is folded into the h = 1 copy of B1, so the 15 factors stay in registers for the whole kernel
+        float2 tw[16];
+        {
+            const float2* twr = reinterpret_cast<const float2*>(p.consts + kConstSmemBytes);
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) tw[k1] = __ldg(&twr[k1 * 8 + r]);
+        }
         for (int it = 0; it < my_tiles; ++it) {
             const long long tile = blockIdx.x + static_cast<long long>(it) * gridDim.x;
             if (it >= 1) wait_or_trap(&s.s2_done, static_cast<uint32_t>((it - 1) & 1));    // A2 free again
@@ -649,9 +660,6 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
                     }
                 }
                 const int n2 = 8 * h + r;
-                float2 tw[16];
-#pragma unroll
-                for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s.tw[h][k1][r];   // all loads before the first store
                 s.s16[it & 1][frow][n2] = v[1];
                 const uint32_t koff = (n2 >> 2) * kA2Lbo + (n2 & 3) * 4 + (frow >> 3) * 128 + (frow & 7) * 16;
 #pragma unroll
@@ -826,22 +834,27 @@ int get_consts(int nfilt, const unsigned char** out) {
         return MMLA_OK;
     }
     std::vector<unsigned char> host(kConstBytes, 0);
-    unsigned char* b1h = host.data();
-    unsigned char* b1l = b1h + 2048;
-    unsigned char* b2h = b1l + 2048;
+    unsigned char* b1 = host.data();                 // [h][hi|lo][2048]
+    unsigned char* b2h = b1 + 4 * 2048;
     unsigned char* b2l = b2h + 2048;
-    float2* tw = reinterpret_cast<float2*>(b2l + 2048);
+    float2* k16 = reinterpret_cast<float2*>(b2l + 2048);
+    float* dct = reinterpret_cast<float*>(k16 + 8 * 16);
+    float2* twr = reinterpret_cast<float2*>(dct + 40 * 16);
     const double PI = 3.14159265358979323846;
-    // stage 1: column 0 = Re S[.][0], column 1 = Re S[.][16], columns 2j, 2j+1 = Re, Im S[.][j]; rows n1 >= 25 are the
-    // frame's zero padding
-    for (int n1 = 0; n1 < 32; ++n1) {
-        const double live = n1 < 25 ? 1.0 : 0.0;
-        put_split(b1h, b1l, 0, n1, live);
-        put_split(b1h, b1l, 1, n1, live * ((n1 & 1) ? -1.0 : 1.0));
-        for (int j = 1; j < 16; ++j) {
-            const double th = 2.0 * PI * ((n1 * j) % 32) / 32.0;
-            put_split(b1h, b1l, 2 * j, n1, live * cos(th));
-            put_split(b1h, b1l, 2 * j + 1, n1, -live * sin(th));
+    // stage 1: column 0 = Re S[.][0], column 1 = Re S[.][16], columns 2j, 2j+1 = Re, Im of S[.][j] W64^(h j); rows
+    // n1 >= 25 are the frame's zero padding
+    for (int h = 0; h < 2; ++h) {
+        unsigned char* bh = b1 + h * 4096;
+        unsigned char* bl = bh + 2048;
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const double live = n1 < 25 ? 1.0 : 0.0;
+            put_split(bh, bl, 0, n1, live);
+            put_split(bh, bl, 1, n1, live * ((n1 & 1) ? -1.0 : 1.0));
+            for (int j = 1; j < 16; ++j) {
+                const double th = 2.0 * PI * (((2 * n1 + h) * j) % 64) / 64.0;
+                put_split(bh, bl, 2 * j, n1, live * cos(th));
+                put_split(bh, bl, 2 * j + 1, n1, -live * sin(th));
+            }
         }
     }
     // stage 2: complex DFT-16 as a real 32 x 32 product, K = (n2, re/im), N = (k2, re/im)
@@ -854,20 +867,17 @@ int get_consts(int nfilt, const unsigned char** out) {
             put_split(b2h, b2l, cim, 2 * n2, -sin(th));
             put_split(b2h, b2l, cim, 2 * n2 + 1, cos(th));
         }
-    for (int h = 0; h < 2; ++h)
-        for (int k1 = 0; k1 < 16; ++k1)
-            for (int r = 0; r < 8; ++r) {
-                const double th = 2.0 * PI * (((8 * h + r) * k1) % 512) / 512.0;
-                tw[(h * 16 + k1) * 8 + r] = make_float2(static_cast<float>(kS2 * cos(th)), static_cast<float>(-kS2 * sin(th)));
-            }
-    float2* k16 = tw + 2 * 16 * 8;
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int r = 0; r < 8; ++r) {
+            const double th = 2.0 * PI * ((r * k1) % 512) / 512.0;
+            twr[k1 * 8 + r] = make_float2(static_cast<float>(kS2 * cos(th)), static_cast<float>(-kS2 * sin(th)));
+        }
     for (int k2 = 0; k2 < 8; ++k2)
         for (int n2 = 0; n2 < 16; ++n2) {
             const double th = 2.0 * PI * ((n2 * (16 + 32 * k2)) % 512) / 512.0;
             k16[k2 * 16 + n2] = make_float2(static_cast<float>(kS2 * cos(th)), static_cast<float>(-kS2 * sin(th)));
         }
-    // DCT-II ortho (scipy.fftpack.dct norm='ortho') with the psf lifter (L = 22) folded in
-    float* dct = reinterpret_cast<float*>(k16 + 8 * 16);
+    // DCT-II ortho (scipy.fftpack.dct norm='ortho') with the psf lifter (L = 22) folded in; rows >= nfilt stay zero
     for (int c = 0; c < 13; ++c) {
         const double scale = c == 0 ? sqrt(1.0 / nfilt) : sqrt(2.0 / nfilt);
         const double lift = 1.0 + (22 / 2.0) * sin(PI * c / 22);

@@ -55,6 +55,10 @@ for tile in range(n_tiles):
                 for r in range(8):
                     n2 = 8 * h + r
                     exp = B1 @ fr[16 * n1 + n2]
+                    if h == 1:          # the h = 1 copy of B1 carries W64^k1 (half of the twiddle)
+                        for j in range(1, 16):
+                            z = (exp[2 * j] + 1j * exp[2 * j + 1]) * np.exp(-2j * np.pi * j / 64)
+                            exp[2 * j], exp[2 * j + 1] = z.real, z.imag
                     lane = 8 * fl + r
                     gotv = d[tile, 0, lane, (2 * g + h) * 32:(2 * g + h) * 32 + 32]
                     e1 = max(e1, np.abs(gotv - exp).max())
