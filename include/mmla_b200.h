@@ -46,6 +46,14 @@ int64_t mmla_launch_count(void);
 /* CRC-32C (Castagnoli) of a HOST buffer, as stored in TF tensor-bundle entries. Host only. */
 uint32_t mmla_crc32c_host(const void* data_host, size_t n);
 
+/* Launch trace (measurement aid for bench.py's per-kernel roofline): between mmla_trace_begin(stream) and
+ * mmla_trace_end every kernel this library launches on `stream` is followed by a CUDA event.  mmla_trace_end
+ * waits for them and returns the number of records written: names_host receives the kernel names, one per
+ * line ('\n'-separated, NUL-terminated), ms_host[i] the device time between the previous event and record i
+ * (kernels of one stream run in order, so that is kernel i's duration plus any launch gap).  Negative = error. */
+int mmla_trace_begin(void* stream);
+int mmla_trace_end(char* names_host, int64_t names_bytes, float* ms_host, int32_t max_records);
+
 /* Diagnostics of the tensor-core MFCC kernel (both DEVICE pointers, NULL disables each):
  *   dev_buffer  receives the raw stage-1 / stage-2 accumulators, per 64-frame tile 2 x 128 x 256 float32;
  *   dev_stamps  receives clock64 stamps of CTA 0's warp roles, 64 tiles x 32 int64 slots. */

@@ -17,7 +17,7 @@ SYMBOLS = (
     "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_delta", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
     "mmla_net_forward",
-    "mmla_tally", "mmla_synth_pcm", "mmla_debug_mfcc_tc_dump",
+    "mmla_tally", "mmla_synth_pcm", "mmla_debug_mfcc_tc_dump", "mmla_trace_begin", "mmla_trace_end",
 )
 
 
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
         "mmla_tally": (C.c_int, [vp, i64, i32, vp, vp]),
         "mmla_synth_pcm": (C.c_int, [vp, i64, i64, i32, i64, u32, vp, vp]),
         "mmla_debug_mfcc_tc_dump": (None, [vp, vp]),
+        "mmla_trace_begin": (C.c_int, [vp]),
+        "mmla_trace_end": (C.c_int, [vp, i64, vp, i32]),
     }
     assert set(sigs) == set(SYMBOLS)
     for name, (res, args) in sigs.items():
@@ -98,3 +100,20 @@ def require_cuda():
 
 def stream_ptr(torch) -> int:
     return int(torch.cuda.current_stream().cuda_stream)
+
+
+def trace_launches(fn, torch):
+    """Run ``fn()`` with the library's launch trace open on the current stream; returns
+    ``[(kernel_name, ms), ...]`` in launch order (device time per launch, CUDA events)."""
+    lib = load()
+    check(lib.mmla_trace_begin(stream_ptr(torch)), "mmla_trace_begin")
+    try:
+        fn()
+    finally:
+        names = C.create_string_buffer(1 << 16)
+        ms = (C.c_float * 4096)()
+        n = lib.mmla_trace_end(names, len(names), ms, 4096)
+    if n < 0:
+        check(n, "mmla_trace_end")
+    nm = names.value.decode().split("\n")[:n]
+    return [(nm[i] if i < len(nm) else "?", float(ms[i])) for i in range(n)]

@@ -26,7 +26,9 @@ void mmla_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
-void mmla_count_launch();                 // bumps the counter mmla_launch_count() reports
+// Called right after every kernel launch: bumps the counter mmla_launch_count() reports and, while a launch
+// trace is open (mmla_trace_begin), records a CUDA event on `st` so the kernel's device time can be read back.
+void mmla_count_launch(const char* kernel_name, cudaStream_t st);
 int mmla_num_sms();   // SM count of the current device (cached), <0 on error
 
 // ---------------------------------------------------------------------------------------------

@@ -357,7 +357,7 @@ int launch_nt(const ConvArgs& a, const float* wg, cudaStream_t st) {
     }
     const dim3 grid(static_cast<unsigned>((a.M + 127) / 128), static_cast<unsigned>(a.N / NT));
     conv_tc_kernel<NT><<<grid, 256, sizeof(TcSmem<NT>) + 1024, st>>>(a, wg);
-    mmla_count_launch();
+    mmla_count_launch("conv_tc_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }

@@ -35,7 +35,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_delta(const float* fe
     long long grid = (n_frames * dim + 255) / 256;
     if (grid > 8LL * sms) grid = 8LL * sms;
     delta_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat, n_frames, dim, N, denom, out);
-    mmla_count_launch();
+    mmla_count_launch("delta_kernel", static_cast<cudaStream_t>(stream));
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }

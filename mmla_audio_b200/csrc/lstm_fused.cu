@@ -346,7 +346,7 @@ int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr
     a.B = static_cast<int>(B); a.T = T;
     const dim3 grid(static_cast<unsigned>((B + kRows - 1) / kRows), 2);
     lstm_fused_kernel<<<grid, kThreads, smem, st>>>(a);
-    mmla_count_launch();
+    mmla_count_launch("lstm_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }

@@ -754,7 +754,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
     long long grid = 2LL * sms;
     if (grid > kp.n_units) grid = kp.n_units;
     mfcc_fused_kernel<<<static_cast<unsigned>(grid), kThreads, sizeof(Smem), st>>>(kp);
-    mmla_count_launch();
+    mmla_count_launch("mfcc_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     if (dev_tmp) MMLA_CUDA_CHECK(cudaFreeAsync(dev_tmp, st));
     return MMLA_OK;

@@ -905,7 +905,7 @@ int launch_tc(const TcParams& kp, long long grid, cudaStream_t st) {
         attr_set = true;
     }
     mfcc_tc_kernel<NF, DBG><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(kp);
-    mmla_count_launch();
+    mmla_count_launch("mfcc_tc_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }
@@ -1020,7 +1020,7 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
         const long long fgrid = n_clips * fin_tiles_per_clip;
         MMLA_REQUIRE(fgrid < (1LL << 31), MMLA_EUNSUP, "mfcc_tc: too many finish tiles");
         mfcc_finish_kernel<<<static_cast<unsigned>(fgrid), 256, 0, st>>>(fp);
-        mmla_count_launch();
+        mmla_count_launch("mfcc_finish_kernel", st);
         MMLA_CUDA_CHECK(cudaGetLastError());
     }
     if (dev_tmp) MMLA_CUDA_CHECK(cudaFreeAsync(dev_tmp, st));

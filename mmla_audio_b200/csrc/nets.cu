@@ -420,16 +420,16 @@ int launch_conv(const ConvW& c, const void* x, int x_is_u8, long long B, int H, 
     const unsigned gx = static_cast<unsigned>((a.M + kBM - 1) / kBM);
     if (c.cout <= 16) {
         conv_igemm_kernel<1><<<dim3(gx, (c.cout + 15) / 16), 256, 0, st>>>(a);
-        mmla_count_launch();
+        mmla_count_launch("conv_igemm_kernel", st);
     } else if (c.cout <= 32) {
         conv_igemm_kernel<2><<<dim3(gx, (c.cout + 31) / 32), 256, 0, st>>>(a);
-        mmla_count_launch();
+        mmla_count_launch("conv_igemm_kernel", st);
     } else if (c.cout <= 64) {
         conv_igemm_kernel<4><<<dim3(gx, (c.cout + 63) / 64), 256, 0, st>>>(a);
-        mmla_count_launch();
+        mmla_count_launch("conv_igemm_kernel", st);
     } else {
         conv_igemm_kernel<8><<<dim3(gx, (c.cout + 127) / 128), 256, 0, st>>>(a);
-        mmla_count_launch();
+        mmla_count_launch("conv_igemm_kernel", st);
     }
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
@@ -655,7 +655,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         int rc;
         if (tc && !ov && net->stem_pad.k_tc) {
             pad_channels_kernel<<<ew_grid(B * 256 * 10), 256, 0, st>>>(static_cast<const float*>(xin), xpad, B * 256, 39, 40);
-            mmla_count_launch();
+            mmla_count_launch("pad_channels_kernel", st);
             MMLA_CUDA_CHECK(cudaGetLastError());
             rc = launch_conv(net->stem_pad, xpad, 0, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
         } else {
@@ -689,7 +689,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                 if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st, tc))) return rc;
                 const int Ho = same_out(H, 2), Wo = same_out(W, 2), C = blk.conv2.cout;
                 maxpool_kernel<<<ew_grid(B * Ho * Wo * C / 4), 256, 0, st>>>(Bf, A, static_cast<int>(B), H, W, C, 2, 2, Ho, Wo);
-                mmla_count_launch();
+                mmla_count_launch("maxpool_kernel", st);
                 MMLA_CUDA_CHECK(cudaGetLastError());
                 if ((rc = launch_conv(blk.shortcut, X, 0, B, H, W, nullptr, ACT_NONE, A, C, Bf, st, tc))) return rc;
                 H = Ho; W = Wo;
@@ -698,7 +698,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                 // speaker: x' = MaxPool1D(x); res = conv_k1_s2(x); out = conv2(..conv1(..x'..)) + res
                 const int Wo = same_out(W, 2), Cin = blk.conv1.cin;
                 maxpool_kernel<<<ew_grid(B * Wo * Cin / 4), 256, 0, st>>>(X, A, static_cast<int>(B), 1, W, Cin, 1, 2, 1, Wo);
-                mmla_count_launch();
+                mmla_count_launch("maxpool_kernel", st);
                 MMLA_CUDA_CHECK(cudaGetLastError());
                 if ((rc = launch_conv(blk.conv1, A, 0, B, 1, Wo, &blk.bn1, act_kind, nullptr, 0, Bf, st, tc))) return rc;
                 if ((rc = launch_conv(blk.shortcut, X, 0, B, 1, W, nullptr, ACT_NONE, nullptr, 0, A, st, tc))) return rc;
@@ -710,11 +710,11 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         // sequence features [B,T,128]
         if (ov) {
             mean_h_kernel<<<ew_grid(B * W * 128), 256, 0, st>>>(buf[cur], seq, B, H, W, 128);
-            mmla_count_launch();
+            mmla_count_launch("mean_h_kernel", st);
         } else {
             bn_relu_avgpool4_kernel<<<ew_grid(B * (W / 4) * 128), 256, 0, st>>>(buf[cur], seq, net->final_bn.scale,
                                                                                net->final_bn.shift, B, W, 128);
-            mmla_count_launch();
+            mmla_count_launch("bn_relu_avgpool4_kernel", st);
         }
         MMLA_CUDA_CHECK(cudaGetLastError());
         // BiLSTM(256): input projections for all steps, then the recurrence
@@ -733,13 +733,13 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                 const float* xpt = xp[d] + static_cast<long long>(t) * 1024;
                 if (s == 0) {                              // h0 = 0: pre-activations are xp[:, t, :]
                     lstm_gates_kernel<<<ew_grid(B * 256), 256, 0, st>>>(xpt, static_cast<long long>(T) * 1024, cst, h, B, 256, 1);
-                    mmla_count_launch();
+                    mmla_count_launch("lstm_gates_kernel", st);
                 } else {
                     if ((rc = launch_conv(net->lstm_rec[d], h, 0, B, 1, 1, nullptr, ACT_NONE, xpt,
                                           static_cast<long long>(T) * 1024, z, st, tc)))
                         return rc;
                     lstm_gates_kernel<<<ew_grid(B * 256), 256, 0, st>>>(z, 1024, cst, h, B, 256, 0);
-                    mmla_count_launch();
+                    mmla_count_launch("lstm_gates_kernel", st);
                 }
                 MMLA_CUDA_CHECK(cudaGetLastError());
             }
@@ -750,7 +750,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         head_kernel<<<static_cast<unsigned>(hgrid), warps * 32, warps * 512 * sizeof(float), st>>>(
             hdir[0], hdir[1], net->dense_k, net->dense_b, 0.3f, ov ? 1 : 0, net->n_classes, net->head == MMLA_HEAD_SIGMOID, B,
             prob + b0 * net->n_classes, labels ? labels + b0 : nullptr);
-        mmla_count_launch();
+        mmla_count_launch("head_kernel", st);
         MMLA_CUDA_CHECK(cudaGetLastError());
     }
     return MMLA_OK;

@@ -480,7 +480,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_overlap_features(
     long long grid = sms;
     if (grid > n_clips) grid = n_clips;
     overlap_features_kernel<<<static_cast<unsigned>(grid), kThreads, sizeof(Smem), st>>>(kp);
-    mmla_count_launch();
+    mmla_count_launch("overlap_features_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     if (dev_tmp) MMLA_CUDA_CHECK(cudaFreeAsync(dev_tmp, st));
     return MMLA_OK;

@@ -349,7 +349,7 @@ int launch_ru(const ResUnitArgs& a, cudaStream_t st) {
     }
     const unsigned grid = static_cast<unsigned>((a.B + a.G - 1) / a.G);
     resunit_fused_kernel<CIN, C, POOL><<<grid, kThreadsRU, smem, st>>>(a);
-    mmla_count_launch();
+    mmla_count_launch("resunit_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }

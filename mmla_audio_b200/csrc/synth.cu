@@ -88,7 +88,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_synth_pcm(int16_t* pc
     if (grid > n_clips) grid = n_clips;
     synth_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         pcm, first_clip, n_clips, clip_len, clip_stride, seed, sine_table);
-    mmla_count_launch();
+    mmla_count_launch("synth_kernel", static_cast<cudaStream_t>(stream));
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }

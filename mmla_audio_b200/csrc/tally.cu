@@ -35,7 +35,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_tally(const int32_t* 
     if (grid > 4LL * sms) grid = 4LL * sms;
     tally_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         labels, n, n_classes, reinterpret_cast<unsigned long long*>(counts));
-    mmla_count_launch();
+    mmla_count_launch("tally_kernel", static_cast<cudaStream_t>(stream));
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }
