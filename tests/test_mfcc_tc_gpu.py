@@ -1,0 +1,164 @@
+"""GPU parity of the tensor-core MFCC kernel (csrc/mfcc_tc.cu) and of the kernel dispatch.
+
+The reference parameterisation (mfcc(sig, rate, winlen=0.025, winstep=0.01, nfft=512), nfilt 26 or
+40) runs on the tcgen05 two-stage DFT kernel; anything else runs on the general fp32 FFT kernel
+(csrc/mfcc.cu).  Both must agree with the float64 oracle within the tolerance stated in
+test_mfcc_gpu.py, and with each other.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import psf, synth
+from test_mfcc_gpu import assert_mfcc_close, ref_mfcc
+
+pytestmark = pytest.mark.gpu
+
+
+def _with_kernel(kind, fn):
+    old = os.environ.get("MMLA_MFCC_KERNEL")
+    try:
+        if kind is None:
+            os.environ.pop("MMLA_MFCC_KERNEL", None)
+        else:
+            os.environ["MMLA_MFCC_KERNEL"] = kind
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("MMLA_MFCC_KERNEL", None)
+        else:
+            os.environ["MMLA_MFCC_KERNEL"] = old
+
+
+def _launch_names(fn):
+    from mmla_audio_b200 import _lib
+    import torch
+    return [n for n, _ in _lib.trace_launches(fn, torch)]
+
+
+@pytest.mark.parametrize("nfilt", [26, 40])
+def test_tc_and_fft_kernels_agree(cuda, nfilt):
+    from mmla_audio_b200 import speaker_identification as si
+    pcm = synth.synth_clips(300, 5, 40000)
+    cfg = si.MfccConfig(nfilt=nfilt)
+    names_tc = _launch_names(lambda: si.mfcc_batch(pcm, cfg))
+    names_fft = _with_kernel("fft", lambda: _launch_names(lambda: si.mfcc_batch(pcm, cfg)))
+    assert names_tc == ["mfcc_tc_kernel"] and names_fft == ["mfcc_fused_kernel"]
+    tc = si.mfcc_batch(pcm, cfg).cpu().numpy()
+    fft = _with_kernel("fft", lambda: si.mfcc_batch(pcm, cfg).cpu().numpy())
+    for i in range(pcm.shape[0]):
+        ref = ref_mfcc(pcm[i], nfilt=nfilt)
+        assert_mfcc_close(tc[i], ref)
+        assert_mfcc_close(fft[i], ref)
+        assert_mfcc_close(tc[i], fft[i])
+
+
+def test_non_reference_parameters_use_the_general_kernel(cuda):
+    """Hamming window / nfilt 30 are outside the tensor-core specialisation."""
+    from mmla_audio_b200 import speaker_identification as si
+    pcm = synth.synth_clips(310, 2, 24000)
+    cfg = si.MfccConfig(nfilt=30)
+    assert _launch_names(lambda: si.mfcc_batch(pcm, cfg)) == ["mfcc_fused_kernel"]
+    out = si.mfcc_batch(pcm, cfg).cpu().numpy()
+    for i in range(2):
+        assert_mfcc_close(out[i], psf.mfcc(pcm[i], 16000, 0.025, 0.01, 13, 30, 512))
+
+
+def test_tc_speaker_features_and_padding(cuda):
+    """MFCC || delta || delta-delta, zero rows up to 256: mfcc_tc_kernel + mfcc_finish_kernel."""
+    from mmla_audio_b200 import speaker_identification as si
+    for clip_len in (24000, 40000, 40960, 4000, 4321):
+        pcm = synth.synth_clips(320, 3, clip_len)
+        names = _launch_names(lambda: si.speaker_features_batch(pcm))
+        # clip starts must be 16-byte aligned for the TMA path: a 4321-sample stride is not
+        want = ["mfcc_tc_kernel", "mfcc_finish_kernel"] if clip_len % 8 == 0 else ["mfcc_fused_kernel"]
+        assert names == want, (clip_len, names)
+        out = si.speaker_features_batch(pcm).cpu().numpy()
+        assert out.shape == (3, 256, 39)
+        for i in range(3):
+            ref = psf.input_feature_gen(pcm[i])[0]
+            assert_mfcc_close(out[i], ref)
+            T = psf.num_frames(clip_len)
+            assert not out[i, T:].any()
+
+
+def test_tc_truncated_context_falls_back(cuda):
+    """Clips longer than 256 frames with deltas need frames past the cut for the delta context."""
+    from mmla_audio_b200 import speaker_identification as si
+    pcm = synth.synth_clips(330, 2, 48000)                     # 299 frames -> truncated to 256
+    names = _launch_names(lambda: si.speaker_features_batch(pcm))
+    assert names == ["mfcc_fused_kernel"]
+    out = si.speaker_features_batch(pcm).cpu().numpy()
+    for i in range(2):
+        assert_mfcc_close(out[i], psf.input_feature_gen(pcm[i])[0])
+
+
+def test_tc_overlapping_windows_zero_copy(cuda):
+    """segmentation() with step < win: a strided view of one recording (clip_stride < clip_len)."""
+    import torch
+    from mmla_audio_b200 import speaker_identification as si
+    from mmla_audio_b200.pipeline import window_view
+    rec = synth.synth_clips(340, 4, 40000).reshape(-1)
+    x = torch.from_numpy(rec).cuda()
+    wins = window_view(x, 24000, 8000)
+    assert wins.shape[0] == int((rec.size - 24000) / 8000 + 1)
+    out = si.mfcc_batch(wins).cpu().numpy()
+    for j in (0, 1, wins.shape[0] - 1):
+        assert_mfcc_close(out[j], ref_mfcc(rec[j * 8000:j * 8000 + 24000]))
+
+
+def test_tc_stage_accumulators_match_numpy(cuda):
+    """The raw tcgen05 accumulators of both DFT stages (diagnostic dump) against float64 numpy:
+    stage 1 = 32-point real DFTs over the stride-16 polyphase components (the h = 1 half carries
+    W64^k1), stage 2 = the 512-point spectrum scaled by 2^-6."""
+    import torch
+    from mmla_audio_b200 import _lib, speaker_identification as si
+    lib = _lib.load()
+    n_clips, L = 2, 24000
+    pcm = synth.synth_clips(350, n_clips, L)
+    cfg = si.MfccConfig()
+    T = cfg.num_frames(L)
+    gpc = (T + 15) // 16
+    n_tiles = (n_clips * gpc + 3) // 4
+    dbg = torch.full((n_tiles, 2, 128, 256), float("nan"), dtype=torch.float32, device="cuda")
+    lib.mmla_debug_mfcc_tc_dump(dbg.data_ptr(), None)
+    try:
+        si.mfcc_batch(torch.from_numpy(pcm).cuda(), cfg)
+        torch.cuda.synchronize()
+    finally:
+        lib.mmla_debug_mfcc_tc_dump(None, None)
+    d = dbg.cpu().numpy().astype(np.float64)
+    n1 = np.arange(32)
+    k = np.arange(16)
+    rng = np.random.default_rng(0)
+    worst1 = worst2 = 0.0
+    for _ in range(40):
+        G = int(rng.integers(0, n_clips * gpc))
+        fl, h, r = int(rng.integers(0, 16)), int(rng.integers(0, 2)), int(rng.integers(0, 8))
+        clip, f0 = G // gpc, (G % gpc) * 16
+        tile, g = G // 4, G % 4
+        y = np.concatenate([psf.preemphasis(pcm[clip], 0.97) * 0.5, np.zeros(4096)])
+        fr = y[(f0 + fl) * 160:(f0 + fl) * 160 + 512].copy()
+        fr[400:] = 0
+        if (f0 + fl) * 160 >= L:
+            continue
+        seq = fr[16 * n1 + 8 * h + r]
+        S = np.array([np.sum(seq * np.exp(-2j * np.pi * n1 * kk / 32)) for kk in range(17)])
+        S[1:16] *= np.exp(-2j * np.pi * k[1:] * h / 64)
+        got = d[tile, 0, 8 * fl + r, (2 * g + h) * 32:(2 * g + h) * 32 + 32]
+        exp = np.empty(32)
+        exp[0], exp[1] = S[0].real, S[16].real
+        exp[2::2], exp[3::2] = S[1:16].real, S[1:16].imag
+        scale = max(np.abs(exp).max(), 1.0)
+        worst1 = max(worst1, np.abs(got - exp).max() / scale)
+        X = np.fft.fft(fr, 512) * 2.0 ** -5
+        for p in range(2):
+            row = p * 64 + 16 * g + fl
+            for j in range(8):
+                k1 = 2 * j + p
+                for k2 in range(16):
+                    c = 4 * (k2 >> 1) + (k2 & 1)
+                    z = d[tile, 1, row, j * 32 + c] + 1j * d[tile, 1, row, j * 32 + c + 2]
+                    worst2 = max(worst2, abs(z - X[k1 + 32 * k2]) / max(np.abs(X).max(), 1.0))
+    assert worst1 < 2e-6 and worst2 < 4e-6, (worst1, worst2)
