@@ -363,12 +363,10 @@ def main():
 
     # ---- e2e: host buffers in, labels + tallies out, copies inside the timed region -----------
     def e2e_finish(pending):
-        labels_h, counts_h = pending.result()                    # host numpy: the step's result
-        if world > 1:
-            lt = gather_labels(pending.labels_dev, n_total, rank, world)
-            ct = allreduce_counts(torch.from_numpy(counts_h).cuda(), world)
-            return lt.cpu(), ct.cpu()
-        return labels_h, counts_h
+        return pending.result()                                  # host numpy: the step's (gathered) labels + tallies
+
+    def e2e_reduce(labels_dev, counts_dev):                      # device side, on the compute stream, before the read-back
+        return gather_labels(labels_dev, n_total, rank, world), allreduce_counts(counts_dev, world)
 
     def e2e_run(steps):
         """`steps` passes through the public host API.  Every pass uploads its own PCM from pinned
@@ -378,7 +376,8 @@ def main():
             from collections import deque
             pend = deque()
             for _ in range(steps):
-                pend.append(pipe.submit_host(pcm_host, n_classes, n_chunks=a.e2e_chunks, depth=a.e2e_depth + 1))
+                pend.append(pipe.submit_host(pcm_host, n_classes, n_chunks=a.e2e_chunks, depth=a.e2e_depth + 1,
+                                             reduce=e2e_reduce if world > 1 else None))
                 if len(pend) >= a.e2e_depth:
                     e2e_finish(pend.popleft())
             while pend:

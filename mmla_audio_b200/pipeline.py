@@ -66,14 +66,19 @@ class SpeakerPipeline:
         prob, labels = self.model.predict_device(self._feat)
         return labels, prob
 
-    def submit_host(self, pcm_host, n_classes: int, n_chunks: int = 2, depth: int = 3):
+    def submit_host(self, pcm_host, n_classes: int, n_chunks: int = 2, depth: int = 3, reduce=None):
         """Asynchronous end-to-end pass from HOST memory: ``pcm_host`` int16 [B, L] (pinned for
         full speed).  The batch is cut into ``n_chunks`` slices; a copy stream uploads slice i+1
         while slice i runs features + classifier on the compute stream, and the labels + tallies
         are read back into pinned host buffers behind the last slice.  Nothing blocks the host:
         the call returns a :class:`PendingResult`; up to ``depth`` submissions may be in flight, so
         the upload of batch k+1 overlaps the compute of batch k (the recording loop of the
-        reference scripts, pipelined).  ``PendingResult.result()`` waits for that batch only."""
+        reference scripts, pipelined).  ``PendingResult.result()`` waits for that batch only.
+
+        ``reduce(labels_dev, counts_dev) -> (labels_all, counts_all)``: optional device-side step run
+        on the compute stream before the read-back — the multi-GPU label all_gather / tally
+        all_reduce (``sharding.gather_labels`` / ``allreduce_counts``); its outputs are what is
+        copied to the host."""
         torch = _lib.require_cuda()
         B, L = pcm_host.shape
         n_chunks = max(1, min(n_chunks, B))
@@ -116,8 +121,11 @@ class SpeakerPipeline:
             free.record(compute)
             self._stage_free[k] = free
         counts = tally.device_counts(labels, n_classes)
-        slot["labels_h"].copy_(labels, non_blocking=True)
-        slot["counts_h"].copy_(counts, non_blocking=True)
+        labels_out, counts_out = (labels, counts) if reduce is None else reduce(labels, counts)
+        if slot["labels_h"].numel() != labels_out.numel():
+            slot["labels_h"] = torch.empty((labels_out.numel(),), dtype=torch.int32).pin_memory()
+        slot["labels_h"].copy_(labels_out.reshape(-1), non_blocking=True)
+        slot["counts_h"].copy_(counts_out, non_blocking=True)
         done = torch.cuda.Event()
         done.record(compute)
         slot["done"] = done
