@@ -137,9 +137,10 @@ class SpeakerPipeline:
         return self.submit_host(pcm_host, n_classes, n_chunks).result()
 
     def run_session(self, pcm_long, speaker_names: Dict[int, str], t0: Optional[datetime] = None,
-                    silent_index=()):
+                    silent_index=(), log_path: Optional[str] = None):
         """Offline session: MFCC-39 over the whole recording, 256-frame chunks, one predict,
-        rows every 2.56 s (speaker_identification_post_processing.py:253-312)."""
+        rows every 2.56 s (speaker_identification_post_processing.py:253-312).  With ``log_path`` the
+        TSV log the reference appends row by row (:278-312) is written for ``visualization()``."""
         torch = _lib.require_cuda()
         chunks = whole_file_chunks(pcm_long, self.cfg)
         prob, labels = self.model.predict_device(chunks)
@@ -147,6 +148,10 @@ class SpeakerPipeline:
             idx = torch.as_tensor(list(silent_index), dtype=torch.long, device=labels.device)
             labels[idx] = tally.SILENT
         t0 = t0 or datetime.today()
+        if log_path is not None:
+            from . import distributions
+            rows = [speaker_names.get(int(l), "silent") for l in labels.cpu().tolist()]
+            distributions.write_log(log_path, tally.log_rows(rows, t0, 2.56, "speaker", add_before_first=True))
         return labels, tally.tally_session(labels, speaker_names, t0, 2.56, add_before_first=True)
 
 
@@ -169,9 +174,10 @@ class OverlapPipeline:
         return labels, prob
 
     def run_session(self, pcm_long, t0: Optional[datetime] = None, win_s: float = 1.5, step_s: float = 1.5,
-                    sr: int = 16000, chunk: int = 4096):
+                    sr: int = 16000, chunk: int = 4096, log_path: Optional[str] = None):
         """Offline session: cut 1.5 s windows (zero-copy), features + predict per window, rows every
-        1.5 s (overlap_detection_post_processing.py:189-226)."""
+        1.5 s (overlap_detection_post_processing.py:189-226).  With ``log_path`` the TSV log of
+        :213-224 is written for ``visualization()``."""
         torch = _lib.require_cuda()
         x = _to_device_pcm(torch, pcm_long).reshape(-1)
         wins = window_view(x, int(sr * win_s), int(sr * step_s))
@@ -181,5 +187,9 @@ class OverlapPipeline:
             labels[i:i + chunk] = l
         t0 = t0 or datetime.today()
         names = {int(k): v for k, v in tally.OVERLAP_DEGREE_DICT.items()}
+        if log_path is not None:
+            from . import distributions
+            rows = [names.get(int(l), "silent") for l in labels.cpu().tolist()]
+            distributions.write_log(log_path, tally.log_rows(rows, t0, win_s, "overlapped degree", add_before_first=False))
         return labels, tally.tally_session(labels, names, t0, win_s, add_before_first=False,
                                            initial_order=list(tally.OVERLAP_DEGREE_DICT.values()))

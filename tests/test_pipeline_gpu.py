@@ -32,7 +32,7 @@ def test_config1_overlap_single_clip(cuda):
     assert l2.cpu().tolist() == [-1, -1]
 
 
-def test_config4_long_session_overlap(cuda):
+def test_config4_long_session_overlap(cuda, tmp_path):
     """A 60 s recording cut into 1.5 s windows (segmentation index math), labels + tallies."""
     from mmla_audio_b200 import models, tally, weights as W
     from mmla_audio_b200.pipeline import OverlapPipeline, segmentation_windows
@@ -42,7 +42,8 @@ def test_config4_long_session_overlap(cuda):
     n = segmentation_windows(len(rec), 24000, 24000)
     assert n == otally.num_windows(len(rec), 24000, 24000) == 39
     t0 = datetime(2021, 6, 1, 12, 0, 0, 654321)
-    labels, (counts, secs, total) = pipe.run_session(rec, t0=t0)
+    log = tmp_path / "experiment" / "logs" / "session.txt"
+    labels, (counts, secs, total) = pipe.run_session(rec, t0=t0, log_path=str(log))
     assert labels.numel() == n
     x = np.stack([lm.classifier_input(rec[i * 24000:(i + 1) * 24000]) for i in range(n)])
     ref = onets.overlap_forward(x, w, W.OVERLAP)
@@ -53,9 +54,16 @@ def test_config4_long_session_overlap(cuda):
     lines = otally.log_rows(names, t0, 1.5, "overlapped degree", add_before_first=False)
     rc, rs, rt = otally.tally_from_log(lines, list(tally.OVERLAP_DEGREE_DICT.values()))
     assert (counts, secs, total) == (rc, rs, rt)                  # integer tallies: bit exact
+    # the log file on disk is the one the reference would have written, and the file-based
+    # visualization() counts it to the same tallies (silent is pre-seeded there, :11)
+    assert log.read_text().splitlines() == lines
+    from mmla_audio_b200 import overlap_degree_distribution as odd
+    res = odd.visualization(str(log.parent))["session.txt"]
+    assert dict(zip(res["labels"], res["counts"])) == {**rc, "silent": 0}
+    assert res["total_seconds"] == rt
 
 
-def test_config4_long_session_speaker(cuda):
+def test_config4_long_session_speaker(cuda, tmp_path):
     """Whole-file MFCC-39 -> 256-frame chunks -> one predict -> rows every 2.56 s."""
     from mmla_audio_b200 import models, weights as W
     from mmla_audio_b200.pipeline import SpeakerPipeline
@@ -65,7 +73,8 @@ def test_config4_long_session_speaker(cuda):
     rec = synth.synth_clips(700, 30, 40960).reshape(-1)           # 76.8 s -> 30 chunks
     names = {i: f"spk{i}" for i in range(10)}
     t0 = datetime(2022, 3, 3, 8, 30, 0, 111111)
-    labels, (counts, secs, total) = pipe.run_session(rec, names, t0=t0, silent_index=(2, 7))
+    log = tmp_path / "experiment" / "logs" / "session.txt"
+    labels, (counts, secs, total) = pipe.run_session(rec, names, t0=t0, silent_index=(2, 7), log_path=str(log))
     chunks = psf.chunked_features(rec).astype(np.float32)
     ref = onets.speaker_forward(chunks, w, spec)
     assert labels.numel() == ref.shape[0] == 30
@@ -79,6 +88,10 @@ def test_config4_long_session_speaker(cuda):
     lines = otally.log_rows(lab_names, t0, 2.56, "speaker", add_before_first=True)
     rc, rs, rt = otally.tally_from_log(lines)
     assert (counts, secs, total) == (rc, rs, rt)
+    assert log.read_text().splitlines() == lines
+    from mmla_audio_b200 import speaker_time_distribution as std
+    res = std.visualization(str(log.parent))["session.txt"]
+    assert dict(zip(res["labels"], res["counts"])) == rc and dict(zip(res["labels"], res["seconds"])) == rs
 
 
 def test_config5_enrollment_features(cuda):

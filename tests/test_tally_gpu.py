@@ -54,3 +54,41 @@ def test_speaker_session_tally_with_silent(cuda):
     assert got_total == ref_total
     assert got_counts == ref_counts and list(got_counts) == list(ref_counts)
     assert got_secs == ref_secs
+
+
+def test_visualization_reads_log_files(cuda, tmp_path):
+    """File-based visualization() (overlap_degree_distribution.py:14-65, speaker_time_distribution.py:16-86):
+    logs written by the session drivers, counted on the device, equal to the oracle's line-by-line
+    restatement; the chart series are exported as JSON."""
+    import json
+    from datetime import datetime
+    import numpy as np
+    from mmla_audio_b200 import distributions, overlap_degree_distribution as odd, speaker_time_distribution as std, tally
+    from oracle import tally as otally
+
+    rng = np.random.default_rng(3)
+    t0 = datetime(2021, 11, 5, 10, 0, 0, 250000)
+    logs = tmp_path / "experiment" / "logs"
+    # overlap session: 1.5 s rows, first row at t0
+    ov = [["non-overlapped", "overlapped", "silent"][i] for i in rng.integers(0, 3, 257)]
+    lines_o = tally.log_rows(ov, t0, 1.5, "overlapped degree", add_before_first=False)
+    assert lines_o == otally.log_rows(ov, t0, 1.5, "overlapped degree", False)
+    distributions.write_log(str(logs / "ov" / "a.txt"), lines_o)
+    res = odd.visualization(str(logs / "ov"))["a.txt"]
+    dist, secs, total = otally.tally_from_log(lines_o, ["non-overlapped", "overlapped", "silent"])
+    assert res["labels"] == list(dist.keys()) and res["counts"] == list(dist.values())
+    assert res["seconds"] == list(secs.values()) and res["total_seconds"] == total
+    assert res["bars"]["overlapped"][:5] == [1 if l == "overlapped" else None for l in ov[:5]]
+    exported = json.load(open(logs / "ov" / "a.txt.tally.json"))
+    assert exported["counts"] == res["counts"] and len(exported["x_bar"]) == 257
+    # speaker session: 2.56 s added before every row, labels in order of first appearance
+    sp = [["amy", "bo", "silent", "cy"][i] for i in rng.integers(0, 4, 300)]
+    lines_s = tally.log_rows(sp, t0, 2.56, "speaker", add_before_first=True)
+    distributions.write_log(str(logs / "sp" / "b.txt"), lines_s)
+    res = std.visualization(str(logs / "sp"))["b.txt"]
+    dist, secs, total = otally.tally_from_log(lines_s)
+    assert res["labels"] == list(dist.keys()) and res["counts"] == list(dist.values())
+    assert res["seconds"] == list(secs.values()) and res["total_seconds"] == total
+    second = res["labels"][1]
+    f0 = sp.index(second)
+    assert res["bars"][second][:f0] == [None] * f0 and res["bars"][second][f0] == 1
