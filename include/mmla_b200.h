@@ -105,6 +105,15 @@ int mmla_psf_mfcc(const int16_t* pcm, int64_t pcm_total_samples,
                   const MmlaMfccParams* p,
                   float* out, int64_t out_clip_stride, void* stream);
 
+/* Same as mmla_psf_mfcc with rows `out_row_stride` floats apart (>= dim; 0 = dense).  Columns [dim, out_row_stride)
+ * of every row are written as zeros: out_row_stride = 40 with with_deltas = 1 is the channel-padded [256,40] layout the
+ * speaker classifier's tensor-core stem reads directly (MMLA_INPUT_F32_PAD40), saving a pad pass. */
+int mmla_psf_mfcc_rows(const int16_t* pcm, int64_t pcm_total_samples,
+                       const int64_t* clip_off_host, const int32_t* clip_len_host,
+                       int64_t n_clips, int32_t clip_len, int64_t clip_stride,
+                       const MmlaMfccParams* p,
+                       float* out, int64_t out_clip_stride, int32_t out_row_stride, void* stream);
+
 /* Replaces delta(feat, N): SpeakerIdentification/scripts/speaker_identification.py:141-151.
  * feat/out float32 [n_frames][dim]; out[t] = sum_{k=-N..N} k*feat[clamp(t+k)] / (2*sum k^2). */
 int mmla_delta(const float* feat, int64_t n_frames, int32_t dim, int32_t N, float* out, void* stream);
@@ -155,8 +164,11 @@ void mmla_net_destroy(MmlaNet* net);
 int mmla_net_set_precision(MmlaNet* net, int32_t mode);
 /* Bytes of device workspace needed for a forward pass over `batch` clips. */
 int64_t mmla_net_workspace_bytes(const MmlaNet* net, int64_t batch);
+#define MMLA_INPUT_F32       0   /* float32 in the net's own input shape                                   */
+#define MMLA_INPUT_U8        1   /* uint8 image tensor (overlap net only)                                  */
+#define MMLA_INPUT_F32_PAD40 2   /* speaker net, TF32 mode: float32 [B,256,40], channel 39 = 0             */
 /*
- * x_is_u8: 1 when x is the uint8 image tensor (overlap net only), 0 for float32 input.
+ * x_is_u8: one of MMLA_INPUT_* (historical name: 1 when x is the uint8 image tensor, 0 for float32 input).
  * prob    float32 [batch][n_classes]; labels int32 [batch] = argmax (first max wins), may be NULL.
  */
 int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch,

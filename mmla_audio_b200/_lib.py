@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmmla_b200.so")
 # every symbol include/mmla_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = (
     "mmla_last_error", "mmla_abi_version", "mmla_launch_count", "mmla_crc32c_host",
-    "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_delta", "mmla_overlap_features",
+    "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_psf_mfcc_rows", "mmla_delta", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
     "mmla_net_forward",
     "mmla_tally", "mmla_synth_pcm", "mmla_debug_mfcc_tc_dump", "mmla_trace_begin", "mmla_trace_end",
@@ -58,6 +58,7 @@ def load() -> C.CDLL:
         "mmla_crc32c_host": (u32, [vp, C.c_size_t]),
         "mmla_psf_num_frames": (i32, [i64, mp]),
         "mmla_psf_mfcc": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, mp, vp, i64, vp]),
+        "mmla_psf_mfcc_rows": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, mp, vp, i64, i32, vp]),
         "mmla_delta": (C.c_int, [vp, i64, i32, i32, vp, vp]),
         "mmla_overlap_features": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, i32, vp, vp, vp, vp, vp]),
         "mmla_net_create": (C.c_int, [i32, i32, i32, vp, i64, C.POINTER(vp)]),

@@ -68,6 +68,7 @@ struct MfccKernelParams {
     long long n_units;
     long long clip_stride;
     long long out_clip_stride;
+    int out_row_stride;               // floats between output rows (>= dim; extra columns are written as zeros)
     int tiles_per_clip;
     int clip_len;
     int frame_len, frame_step, nfilt, numcep;
@@ -461,11 +462,15 @@ __global__ void __launch_bounds__(kThreads, 2) mfcc_fused_kernel(const __grid_co
 
         // ---- epilogue: (delta, delta-delta), padding rows, coalesced store ---------------------
         float* out_clip = p.out + un.clip * p.out_clip_stride;
+        const int rs = p.out_row_stride;
         if (!p.with_deltas) {
-            const int n = (un.hi - un.lo) * ncep;
+            const int n = (un.hi - un.lo) * rs;
             const float* src = &s.feat[(un.lo - un.c0) * ncep];
-            float* dst = out_clip + static_cast<long long>(un.lo) * ncep;
-            for (int e = tid; e < n; e += kThreads) dst[e] = src[e];
+            float* dst = out_clip + static_cast<long long>(un.lo) * rs;
+            for (int e = tid; e < n; e += kThreads) {
+                const int r = e / rs, col = e - r * rs;
+                dst[e] = col < ncep ? src[r * ncep + col] : 0.f;
+            }
         } else {
             float* dt = reinterpret_cast<float*>(&s.scratch[0][0]);     // delta tile, same indexing as feat
             const int Tm1 = un.T - 1;
@@ -479,12 +484,14 @@ __global__ void __launch_bounds__(kThreads, 2) mfcc_fused_kernel(const __grid_co
                 dt[(t - un.c0) * ncep + c] = (-2.f * xm2 - xm1 + xp1 + 2.f * xp2) / 10.f;
             }
             __syncthreads();
-            const int n = (un.hi - un.lo) * dim;
-            float* dst = out_clip + static_cast<long long>(un.lo) * dim;
+            const int n = (un.hi - un.lo) * rs;
+            float* dst = out_clip + static_cast<long long>(un.lo) * rs;
             for (int e = tid; e < n; e += kThreads) {
-                const int t = un.lo + e / dim, col = e % dim;
+                const int t = un.lo + e / rs, col = e % rs;
                 float v;
-                if (col < ncep) {
+                if (col >= dim) {
+                    v = 0.f;
+                } else if (col < ncep) {
                     v = s.feat[(t - un.c0) * ncep + col];
                 } else if (col < 2 * ncep) {
                     v = dt[(t - un.c0) * ncep + col - ncep];
@@ -500,8 +507,8 @@ __global__ void __launch_bounds__(kThreads, 2) mfcc_fused_kernel(const __grid_co
             }
         }
         if (un.last_tile && p.pad_frames > un.n_real) {
-            const int n = (p.pad_frames - un.n_real) * dim;
-            float* dst = out_clip + static_cast<long long>(un.n_real) * dim;
+            const int n = (p.pad_frames - un.n_real) * p.out_row_stride;
+            float* dst = out_clip + static_cast<long long>(un.n_real) * p.out_row_stride;
             for (int e = tid; e < n; e += kThreads) dst[e] = 0.f;
         }
         __syncthreads();                                                // feat / scratch reuse
@@ -635,7 +642,7 @@ int get_tables(const MmlaMfccParams& p, const MfccTables** out) {
 // csrc/mfcc_tc.cu: tensor-core path for the reference parameterisation
 int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_off_host, const int32_t* clip_len_host,
                      int64_t n_clips, int32_t clip_len, int64_t clip_stride, const MmlaMfccParams& p, float* out,
-                     int64_t out_clip_stride, cudaStream_t st, float* dbg, long long* prof, int* handled);
+                     int64_t out_clip_stride, int32_t out_row_stride, cudaStream_t st, float* dbg, long long* prof, int* handled);
 static float* g_tc_dump = nullptr;
 static long long* g_tc_prof = nullptr;
 extern "C" __attribute__((visibility("default"))) void mmla_debug_mfcc_tc_dump(float* dev_buffer, long long* dev_stamps) {
@@ -654,8 +661,22 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
                              int64_t n_clips, int32_t clip_len, int64_t clip_stride,
                              const MmlaMfccParams* pp, float* out, int64_t out_clip_stride,
                              void* stream) {
+    return mmla_psf_mfcc_rows(pcm, pcm_total, clip_off_host, clip_len_host, n_clips, clip_len, clip_stride, pp, out,
+                              out_clip_stride, 0, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc_rows(const int16_t* pcm, int64_t pcm_total,
+                             const int64_t* clip_off_host, const int32_t* clip_len_host,
+                             int64_t n_clips, int32_t clip_len, int64_t clip_stride,
+                             const MmlaMfccParams* pp, float* out, int64_t out_clip_stride,
+                             int32_t out_row_stride, void* stream) {
     MMLA_REQUIRE(pp != nullptr && pcm != nullptr && out != nullptr, MMLA_EINVAL, "mfcc: null argument");
     const MmlaMfccParams& p = *pp;
+    {
+        const int dim = p.numcep * (p.with_deltas ? 3 : 1);
+        if (out_row_stride == 0) out_row_stride = dim;
+        MMLA_REQUIRE(out_row_stride >= dim, MMLA_EINVAL, "mfcc: out_row_stride %d < row width %d", out_row_stride, dim);
+    }
     MMLA_REQUIRE(n_clips >= 0, MMLA_EINVAL, "mfcc: negative n_clips");
     if (n_clips == 0) return MMLA_OK;
     MMLA_REQUIRE(p.nfft == kNfft, MMLA_EUNSUP, "mfcc: nfft=%d unsupported (the warp FFT is 512-point)", p.nfft);
@@ -682,7 +703,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
     {
         int handled = 0;
         const int trc = mmla_mfcc_tc_try(pcm, pcm_total, clip_off_host, clip_len_host, n_clips, clip_len, clip_stride, p, out,
-                                         out_clip_stride, st, g_tc_dump, g_tc_prof, &handled);
+                                         out_clip_stride, out_row_stride, st, g_tc_dump, g_tc_prof, &handled);
         if (trc != MMLA_OK) return trc;
         if (handled) return MMLA_OK;
     }
@@ -698,6 +719,7 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc(const int16_
     kp.out = out;
     kp.clip_stride = clip_stride;
     kp.out_clip_stride = out_clip_stride;
+    kp.out_row_stride = out_row_stride;
     kp.clip_len = clip_len;
     kp.frame_len = p.frame_len; kp.frame_step = p.frame_step; kp.nfilt = p.nfilt; kp.numcep = p.numcep;
     kp.append_energy = p.append_energy; kp.with_deltas = p.with_deltas; kp.pad_frames = p.pad_frames;

@@ -800,6 +800,16 @@ __global__ void __launch_bounds__(256) mfcc_finish_kernel(const FinParams p) {
             o[static_cast<long long>(t) * p.row_stride + 13 + cc] = v;
         }
     }
+    // zero the extra columns [dim, row_stride) of this tile's real rows
+    const int dim = p.with_deltas ? 39 : 13;
+    if (p.row_stride > dim) {
+        const int extra = p.row_stride - dim;
+        const int r1 = min(t0 + kFinRows, n_real);
+        for (int i = tid; i < (r1 - t0) * extra; i += 256) {
+            const int rr = i / extra, cc = i - rr * extra;
+            o[static_cast<long long>(t0 + rr) * p.row_stride + dim + cc] = 0.f;
+        }
+    }
     // zero rows [n_real, rows_total) of this tile
     const int z0 = max(t0, n_real), z1 = min(t0 + kFinRows, rows_total);
     if (z1 > z0) {
@@ -918,7 +928,8 @@ int launch_tc(const TcParams& kp, long long grid, cudaStream_t st) {
 // `prof` (device, or null): clock64 stamps of CTA 0, 64 tiles x 32 slots.
 int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_off_host, const int32_t* clip_len_host,
                      int64_t n_clips, int32_t clip_len, int64_t clip_stride, const MmlaMfccParams& p, float* out,
-                     int64_t out_clip_stride, cudaStream_t st, float* dbg, long long* prof, int* handled) {
+                     int64_t out_clip_stride, int32_t out_row_stride, cudaStream_t st, float* dbg, long long* prof,
+                     int* handled) {
     *handled = 0;
     const char* force = getenv("MMLA_MFCC_KERNEL");
     if (force && strcmp(force, "fft") == 0) return MMLA_OK;
@@ -972,7 +983,7 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     kp.out_clip_stride = out_clip_stride;
     kp.groups_per_clip = groups_per_clip;
     kp.clip_len = clip_len;
-    kp.row_stride = p.with_deltas ? 39 : 13;
+    kp.row_stride = out_row_stride;
     kp.pad_frames = p.pad_frames;
     kp.append_energy = p.append_energy;
     kp.preemph = p.preemph;
@@ -1006,7 +1017,8 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     else rc = p.nfilt == 26 ? launch_tc<26, false>(kp, grid, st) : launch_tc<40, false>(kp, grid, st);
     if (rc != MMLA_OK) return rc;
 
-    const bool need_finish = p.with_deltas || p.pad_frames > 0;
+    const int dim = p.with_deltas ? 39 : 13;
+    const bool need_finish = p.with_deltas || p.pad_frames > 0 || out_row_stride > dim;
     if (need_finish) {
         FinParams fp;
         fp.out = out;

@@ -625,7 +625,11 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                             int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
     MMLA_REQUIRE(net && x && prob && workspace, MMLA_EINVAL, "net_forward: null argument");
     MMLA_REQUIRE(batch >= 0, MMLA_EINVAL, "net_forward: negative batch");
-    MMLA_REQUIRE(!x_is_u8 || net->kind == MMLA_NET_OVERLAP, MMLA_EINVAL, "net_forward: uint8 input is for the overlap net");
+    MMLA_REQUIRE(x_is_u8 >= 0 && x_is_u8 <= 2, MMLA_EINVAL, "net_forward: bad input kind %d", x_is_u8);
+    MMLA_REQUIRE(x_is_u8 != 1 || net->kind == MMLA_NET_OVERLAP, MMLA_EINVAL, "net_forward: uint8 input is for the overlap net");
+    MMLA_REQUIRE(x_is_u8 != 2 || net->kind == MMLA_NET_SPEAKER, MMLA_EINVAL, "net_forward: 40-channel input is for the speaker net");
+    const bool pad40 = x_is_u8 == 2;          // speaker features already laid out [B,256,40] with channel 39 = 0
+    if (pad40) x_is_u8 = 0;
     MMLA_REQUIRE(workspace_bytes >= mmla_net_workspace_bytes(net, batch), MMLA_EINVAL,
                  "net_forward: workspace too small (%lld < %lld bytes)", static_cast<long long>(workspace_bytes),
                  static_cast<long long>(mmla_net_workspace_bytes(net, batch)));
@@ -633,7 +637,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ov = net->kind == MMLA_NET_OVERLAP;
     const bool tc = net->precision == MMLA_PRECISION_TF32;
-    const long long in_elems = static_cast<long long>(net->in_h) * net->in_w * net->in_c;
+    const long long in_elems = static_cast<long long>(net->in_h) * net->in_w * (pad40 ? 40 : net->in_c);
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const int T = net->seq_len;
 
@@ -654,10 +658,17 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         int cur = 0;
         int rc;
         if (tc && !ov && net->stem_pad.k_tc) {
-            pad_channels_kernel<<<ew_grid(B * 256 * 10), 256, 0, st>>>(static_cast<const float*>(xin), xpad, B * 256, 39, 40);
-            mmla_count_launch("pad_channels_kernel", st);
-            MMLA_CUDA_CHECK(cudaGetLastError());
-            rc = launch_conv(net->stem_pad, xpad, 0, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
+            const float* x40 = static_cast<const float*>(xin);
+            if (!pad40) {
+                pad_channels_kernel<<<ew_grid(B * 256 * 10), 256, 0, st>>>(static_cast<const float*>(xin), xpad, B * 256, 39, 40);
+                mmla_count_launch("pad_channels_kernel", st);
+                MMLA_CUDA_CHECK(cudaGetLastError());
+                x40 = xpad;
+            }
+            rc = launch_conv(net->stem_pad, x40, 0, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
+        } else if (pad40) {
+            mmla_set_error("net_forward: 40-channel input needs the TF32 tensor-core mode");
+            return MMLA_EUNSUP;
         } else {
             rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
         }

@@ -106,7 +106,9 @@ class Model:
         """x: CUDA tensor [B,128,151,3] uint8|float32 (overlap) or [B,256,39] float32 (speaker).
         Returns (prob float32 CUDA [B,n], labels int32 CUDA [B])."""
         torch, lib = self._torch, self._lib
-        if tuple(x.shape[1:]) != self.input_shape:
+        pad40 = (self.spec.ndim == 1 and self.precision == "tf32" and tuple(x.shape[1:]) == (256, 40)
+                 and x.dtype == torch.float32)      # channel-padded features (speaker_features_batch(row_stride=40))
+        if tuple(x.shape[1:]) != self.input_shape and not pad40:
             raise ValueError(f"expected input [B, {self.input_shape}], got {tuple(x.shape)}")
         is_u8 = x.dtype == torch.uint8
         if not is_u8 and x.dtype != torch.float32:
@@ -121,7 +123,7 @@ class Model:
             self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         prob = torch.empty((B, self.spec.n_classes), dtype=torch.float32, device=x.device)
         labels = torch.empty((B,), dtype=torch.int32, device=x.device)
-        _lib.check(lib.mmla_net_forward(self._handle, x.data_ptr(), 1 if is_u8 else 0, B,
+        _lib.check(lib.mmla_net_forward(self._handle, x.data_ptr(), 2 if pad40 else (1 if is_u8 else 0), B,
                                         self._ws.data_ptr(), self._ws.numel(), prob.data_ptr(),
                                         labels.data_ptr(), _lib.stream_ptr(torch)), "mmla_net_forward")
         return prob, labels

@@ -59,10 +59,12 @@ class SpeakerPipeline:
         B = pcm_dev.shape[0]
         if pcm_dev.shape[1] < SILENT_MIN_SAMPLES:          # every clip is 'silent'
             return (torch.full((B,), tally.SILENT, dtype=torch.int32, device=pcm_dev.device), None)
-        if self._feat is None or self._feat.shape[0] != B or self._feat.device != pcm_dev.device:
-            self._feat = torch.empty((B, SPEAKER_FRAMES, 3 * self.cfg.numcep), dtype=torch.float32,
-                                     device=pcm_dev.device)
-        speaker_features_batch(pcm_dev, self.cfg, out=self._feat)
+        # TF32 mode: features go straight into the channel-padded [B,256,40] layout the tcgen05 stem reads
+        width = 40 if (self.model.precision == "tf32" and self.cfg.numcep == 13) else 3 * self.cfg.numcep
+        if (self._feat is None or self._feat.shape[0] != B or self._feat.shape[2] != width
+                or self._feat.device != pcm_dev.device):
+            self._feat = torch.empty((B, SPEAKER_FRAMES, width), dtype=torch.float32, device=pcm_dev.device)
+        speaker_features_batch(pcm_dev, self.cfg, out=self._feat, row_stride=width)
         prob, labels = self.model.predict_device(self._feat)
         return labels, prob
 

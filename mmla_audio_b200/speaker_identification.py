@@ -61,9 +61,10 @@ def _to_device_pcm(torch, pcm):
 
 
 def mfcc_batch(pcm, cfg: MfccConfig = MfccConfig(), with_deltas: bool = False, pad_frames: int = 0,
-               out=None):
+               out=None, row_stride: int = 0):
     """Batched device path.  ``pcm``: int16 [B, L] (numpy or torch; CUDA tensors are used in
-    place).  Returns a float32 CUDA tensor [B, rows, dim] with rows = pad_frames or T(L)."""
+    place).  Returns a float32 CUDA tensor [B, rows, dim] with rows = pad_frames or T(L).
+    ``row_stride`` > dim widens the rows (zero filled): [B, rows, row_stride]."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     x = _to_device_pcm(torch, pcm)
@@ -75,14 +76,17 @@ def mfcc_batch(pcm, cfg: MfccConfig = MfccConfig(), with_deltas: bool = False, p
     T = cfg.num_frames(L)
     rows = pad_frames if pad_frames > 0 else T
     dim = cfg.numcep * (3 if with_deltas else 1)
+    width = row_stride if row_stride else dim
+    if width < dim:
+        raise ValueError(f"row_stride {row_stride} < row width {dim}")
     if out is None:
-        out = torch.empty((B, rows, dim), dtype=torch.float32, device=x.device)
-    elif tuple(out.shape) != (B, rows, dim) or out.dtype != torch.float32 or not out.is_contiguous():
-        raise ValueError(f"out must be a contiguous float32 tensor of shape {(B, rows, dim)}")
+        out = torch.empty((B, rows, width), dtype=torch.float32, device=x.device)
+    elif tuple(out.shape) != (B, rows, width) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float32 tensor of shape {(B, rows, width)}")
     p = _c_params(cfg, with_deltas, pad_frames)
     stride0 = x.stride(0) if B > 1 else L
-    _lib.check(lib.mmla_psf_mfcc(x.data_ptr(), (B - 1) * stride0 + L, None, None, B, L, stride0, C.byref(p),
-                                 out.data_ptr(), rows * dim, _lib.stream_ptr(torch)), "mmla_psf_mfcc")
+    _lib.check(lib.mmla_psf_mfcc_rows(x.data_ptr(), (B - 1) * stride0 + L, None, None, B, L, stride0, C.byref(p),
+                                      out.data_ptr(), rows * width, width, _lib.stream_ptr(torch)), "mmla_psf_mfcc_rows")
     return out
 
 
@@ -106,10 +110,12 @@ def mfcc_ragged(pcm_flat, clip_off: Sequence[int], clip_len: Sequence[int], cfg:
     return out, rows
 
 
-def speaker_features_batch(pcm, cfg: MfccConfig = MfccConfig(), out=None):
+def speaker_features_batch(pcm, cfg: MfccConfig = MfccConfig(), out=None, row_stride: int = 0):
     """[B, L] int16 → float32 CUDA [B, 256, 39]: MFCC ‖ Δ ‖ ΔΔ padded / truncated to 256 rows —
-    the batched equivalent of ``input_feature_gen`` (speaker_identification.py:386-395)."""
-    return mfcc_batch(pcm, cfg, with_deltas=True, pad_frames=SPEAKER_FRAMES, out=out)
+    the batched equivalent of ``input_feature_gen`` (speaker_identification.py:386-395).
+    ``row_stride=40`` gives the channel-padded [B, 256, 40] layout (column 39 = 0) the tensor-core
+    classifier stem consumes without a pad pass."""
+    return mfcc_batch(pcm, cfg, with_deltas=True, pad_frames=SPEAKER_FRAMES, out=out, row_stride=row_stride)
 
 
 # ---------------------------------------------------------------------------------------------

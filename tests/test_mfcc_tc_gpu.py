@@ -162,3 +162,29 @@ def test_tc_stage_accumulators_match_numpy(cuda):
                     z = d[tile, 1, row, j * 32 + c] + 1j * d[tile, 1, row, j * 32 + c + 2]
                     worst2 = max(worst2, abs(z - X[k1 + 32 * k2]) / max(np.abs(X).max(), 1.0))
     assert worst1 < 2e-6 and worst2 < 4e-6, (worst1, worst2)
+
+
+def test_row_stride_40_layout_and_pad40_classifier_input(cuda):
+    """speaker_features_batch(row_stride=40): columns 0..38 identical to the dense layout, column 39
+    zero, on both MFCC kernels; the TF32 speaker classifier gives identical probabilities from the
+    [B,256,40] layout (MMLA_INPUT_F32_PAD40, no pad pass) and from [B,256,39]."""
+    import torch
+    from mmla_audio_b200 import models, speaker_identification as si, weights as W
+    pcm = synth.synth_clips(360, 6, 24000)
+    dense = si.speaker_features_batch(pcm)
+    for kind in (None, "fft"):
+        wide = _with_kernel(kind, lambda: si.speaker_features_batch(pcm, row_stride=40))
+        ref = _with_kernel(kind, lambda: si.speaker_features_batch(pcm))
+        assert wide.shape == (6, 256, 40)
+        assert torch.equal(wide[:, :, :39], ref) and not wide[:, :, 39].any()
+    wide13 = si.mfcc_batch(pcm, row_stride=16)
+    assert wide13.shape[2] == 16 and torch.equal(wide13[:, :, :13], si.mfcc_batch(pcm)) and not wide13[:, :, 13:].any()
+    spec = W.speaker_spec(10, "sigmoid")
+    model = models.Model(spec, W.synthetic_weights(spec, 4321), precision="tf32")
+    wide = si.speaker_features_batch(pcm, row_stride=40)
+    names = _launch_names(lambda: model.predict_device(wide))
+    assert "pad_channels_kernel" not in names
+    assert "pad_channels_kernel" in _launch_names(lambda: model.predict_device(dense))
+    p40, l40 = model.predict_device(wide)
+    p39, l39 = model.predict_device(dense)
+    assert torch.equal(p40, p39) and torch.equal(l40, l39)
