@@ -64,6 +64,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -256,23 +261,24 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
         fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the tensor core
         if (kc + 1 < nk) load_raw(kc + 1, raw, chan);   // next chunk's loads fly across the barrier + MMAs
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
+            // the whole warp stays converged and ONE elected lane issues: warp-uniform descriptors live in uniform
+            // registers and the four UTCHMMA go out back to back (from a `tid == 0` branch each cost an R2UR
+            // waterfall of 80-200 cycles; scripts/microbench/umma_rate.cu)
             mbar_wait_or_trap(&s.full_b[st], static_cast<uint32_t>(use & 1));
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(&s.A[st][0]);
-            const uint32_t b_addr = smem_u32(&s.B[st][0]);
+            const uint64_t ad0 = umma_desc_sw128(smem_u32(&s.A[st][0]));
+            const uint64_t bd0 = umma_desc(smem_u32(&s.B[st][0]), NT * 16, 128);
+            if (tc_elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = umma_desc_sw128(a_addr + kk * 32);          // K advances 32 B inside the atom row
-                const uint64_t bd = umma_desc(b_addr + kk * 2 * (NT * 16), NT * 16, 128);
-                umma_tf32(tmem, ad, bd, kIdesc, (kc | kk) != 0 ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk)                // K advances 32 B inside the atom row / two slabs of B
+                    umma_tf32(tmem, ad0 + static_cast<uint64_t>(kk * 2), bd0 + static_cast<uint64_t>(kk * 2 * NT), kIdesc,
+                              (kc | kk) != 0 ? 1u : 0u);
+                umma_commit(&s.empty[st]);                   // frees this smem stage when the MMAs retire
+                if (kc == nk - 1) umma_commit(&s.accum);     // accumulator complete
             }
-            umma_commit(&s.empty[st]);                       // frees this smem stage when the MMAs retire
-            if (kc == nk - 1) umma_commit(&s.accum);         // accumulator complete
+            __syncwarp();
         }
-        // keep warp 0 converged: lanes 1..31 must not run ahead into the next blocking mbarrier
-        // wait while lane 0 is still issuing (a suspended warp stalls its own issuing lane)
-        if (warp == 0) __syncwarp();
     }
 
     // ---- epilogue: TMEM -> registers (+bias) -> smem staging -> coalesced (+residual) stores ----

@@ -83,6 +83,11 @@ __device__ __forceinline__ uint64_t desc_noswz(uint32_t addr, uint32_t lbo, uint
     return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
            (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+__device__ __forceinline__ bool lstm_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -142,9 +147,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
         }
         __syncwarp();
     } else if (warp == 9) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (warp-uniform loop, one elected lane issues; see resunit_fused.cu) =================
+        {
             long long g = 0;                                      // chunk counter
+            const uint64_t dB0 = desc_noswz(smem_u32(&s.Bst[0][0]), 256 * 16, 128);
+            constexpr uint32_t kStageUnits = kBChunkBytes / 16;
             for (int rs = 0; rs < n_rec; ++rs) {
                 wait_or_trap(&s.hready, static_cast<uint32_t>(rs & 1));        // h_{t-1} staged in smem
                 for (int pass = 0; pass < 4; ++pass) {
@@ -152,27 +159,31 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                     const int buf = static_cast<int>(P & 1);
                     if (P >= 2) wait_or_trap(&s.tempty[buf], static_cast<uint32_t>(((P >> 1) - 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int kc = 0; kc < 8; ++kc)
+                    for (int kc = 0; kc < 8; ++kc) {
+                        const uint64_t dA = desc_sw128(smem_u32(&s.H[kc][0]));
                         for (int kh = 0; kh < 2; ++kh, ++g) {
                             const int stg = static_cast<int>(g % kStages);
                             wait_or_trap(&s.full[stg], static_cast<uint32_t>((g / kStages) & 1));
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t a_addr = smem_u32(&s.H[kc][0]) + (2 * kh) * 32;
-                            const uint32_t b_addr = smem_u32(&s.Bst[stg][0]);
+                            const uint64_t bd0 = dB0 + static_cast<uint64_t>(stg * kStageUnits);
+                            if (lstm_elect_one()) {
 #pragma unroll
-                            for (int m = 0; m < 2; ++m) {
-                                const uint64_t ad = desc_sw128(a_addr + m * 32);
-                                const uint64_t bd = desc_noswz(b_addr + m * 2 * (256 * 16), 256 * 16, 128);
-                                const uint32_t acc = (kc | kh | m) != 0 ? 1u : 0u;
-                                asm volatile(
-                                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + buf * 256),
-                                    "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
-                                    : "memory");
+                                for (int m = 0; m < 2; ++m) {
+                                    const uint64_t ad = dA + static_cast<uint64_t>((2 * kh) * 2 + m * 2);   // 32 B per K=8 step
+                                    const uint64_t bd = bd0 + static_cast<uint64_t>(m * 2 * 256);
+                                    const uint32_t acc = (kc | kh | m) != 0 ? 1u : 0u;
+                                    asm volatile(
+                                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + buf * 256),
+                                        "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                                        : "memory");
+                                }
+                                umma_commit_to(&s.empty[stg]);
+                                if (kc == 7 && kh == 1) umma_commit_to(&s.tfull[buf]);
                             }
-                            umma_commit_to(&s.empty[stg]);
+                            __syncwarp();
                         }
-                    umma_commit_to(&s.tfull[buf]);
+                    }
                 }
             }
         }

@@ -71,6 +71,11 @@ __device__ __forceinline__ uint64_t ru_desc(uint32_t addr, uint32_t lbo, uint32_
     return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
            (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
+__device__ __forceinline__ bool ru_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void ru_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -135,29 +140,39 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
         __syncwarp();
     } else if (warp == 9) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp runs this loop with warp-uniform values and ONE elected lane issues: descriptors then live in
+        // uniform registers and UTCHMMA issues back to back.  (Issued from an `if (lane == 0)` branch with descriptors
+        // rebuilt per instruction, each MMA cost 80-200 cycles of R2UR waterfall instead of its ~45-64 cycle floor —
+        // measured with scripts/microbench/umma_rate.cu.)
+        {
             int g = 0;
-            const uint32_t abuf = smem_u32(&s.ab[0]);
+            const uint64_t dA_main = ru_desc(smem_u32(&s.ab[0]), kRtot * 16, 128);
+            const uint64_t dA_short = ru_desc(smem_u32(&s.a0[0]), 128 * 16, 128);
+            const uint64_t dB0 = ru_desc(smem_u32(&s.ring[0][0]), C * 16, 128);
+            constexpr uint32_t kStageUnits = sizeof(s.ring[0]) / 16;          // descriptor address units per ring stage
             // one K-chunk of MMAs: A slabs start at (slab0 + 2kk) in a buffer with `rows` rows per slab,
             // shifted down by `shift` rows; accumulates into TMEM column block `dcol`
-            auto chunk_mma = [&](uint32_t a_base, int rows, int slab0, int shift, uint32_t dcol, bool first) {
+            auto chunk_mma = [&](uint64_t dA, int rows, int slab0, int shift, uint32_t dcol, bool first) {
                 const int stg = g % kStagesRU;
                 ru_wait(&s.full[stg], static_cast<uint32_t>((g / kStagesRU) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t b_addr = smem_u32(&s.ring[stg][0]);
+                const uint64_t bd0 = dB0 + static_cast<uint64_t>(stg * kStageUnits);
+                const uint64_t ad0 = dA + static_cast<uint64_t>(slab0 * rows + shift);
+                if (ru_elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < kChunkK / 8; ++kk) {
-                    const uint32_t a_addr = a_base + ((slab0 + 2 * kk) * rows + shift) * 16;
-                    const uint64_t ad = ru_desc(a_addr, rows * 16, 128);
-                    const uint64_t bd = ru_desc(b_addr + kk * 2 * (C * 16), C * 16, 128);
-                    const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
-                    asm volatile(
-                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + dcol),
-                        "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
-                        : "memory");
+                    for (int kk = 0; kk < kChunkK / 8; ++kk) {
+                        const uint64_t ad = ad0 + static_cast<uint64_t>(2 * kk * rows);
+                        const uint64_t bd = bd0 + static_cast<uint64_t>(kk * 2 * C);
+                        const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + dcol),
+                            "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                            : "memory");
+                    }
+                    ru_commit(&s.empty[stg]);
                 }
-                ru_commit(&s.empty[stg]);
+                __syncwarp();
                 ++g;
             };
             // conv1: K index = tap*CIN + channel; tap j reads rows shifted by j*G (halo rows = zero padding)
@@ -165,19 +180,20 @@ __global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnit
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int ch = 0; ch < kChunks1; ++ch) {
                 const int k0 = ch * kChunkK, tap = k0 / CIN, c0 = k0 - tap * CIN;
-                chunk_mma(abuf, kRtot, c0 >> 2, tap * G, 0u, ch == 0);
+                chunk_mma(dA_main, kRtot, c0 >> 2, tap * G, 0u, ch == 0);
             }
-            ru_commit(&s.tfull[0]);
+            if (ru_elect_one()) ru_commit(&s.tfull[0]);
+            __syncwarp();
             // shortcut (pooled unit): raw x[2t] x Ws starts conv2's accumulator while epilogue 1 runs
-            for (int ch = 0; ch < kChunksS; ++ch) chunk_mma(smem_u32(&s.a0[0]), 128, (ch * kChunkK) >> 2, 0, C, ch == 0);
+            for (int ch = 0; ch < kChunksS; ++ch) chunk_mma(dA_short, 128, (ch * kChunkK) >> 2, 0, C, ch == 0);
             // conv2
             ru_wait(&s.a_ready[1], 0u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int ch = 0; ch < kChunks2; ++ch) {
                 const int k0 = ch * kChunkK, tap = k0 / C, c0 = k0 - tap * C;
-                chunk_mma(abuf, kRtot, c0 >> 2, tap * G, C, ch == 0 && !POOL);
+                chunk_mma(dA_main, kRtot, c0 >> 2, tap * G, C, ch == 0 && !POOL);
             }
-            ru_commit(&s.tfull[1]);
+            if (ru_elect_one()) ru_commit(&s.tfull[1]);
         }
         __syncwarp();
     } else {
