@@ -270,6 +270,8 @@ def main():
                     help="classifier matmul arithmetic: tf32 = tcgen05 tensor cores, fp32 = CUDA cores")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="host pipeline: upload/compute overlap slices per pass")
     ap.add_argument("--e2e-depth", type=int, default=2, help="host pipeline: passes in flight (1 = synchronous)")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="speaker_id: slices of a batch run on this many CUDA streams so under-filled kernels overlap")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     a = ap.parse_args()
@@ -310,7 +312,8 @@ def main():
 
     if a.workload == "speaker_id":
         spec = W.speaker_spec(10, "sigmoid")
-        pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321), precision=a.precision))
+        pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321), precision=a.precision),
+                               n_streams=a.streams)
         n_classes = 10
     elif a.workload == "overlap":
         pipe = OverlapPipeline(models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234), precision=a.precision))
@@ -403,8 +406,13 @@ def main():
     #      live over `steps` passes of the timed step) and the roofline of the dominant kernel ---------------------
     extra = {"h2d_only_ms": ms_h2d, "h2d_gbs": h2d / (ms_h2d * 1e-3) / 1e9}
     barrier()
+    streams_saved = getattr(pipe, "n_streams", 1)
+    if pipe is not None and streams_saved > 1:
+        pipe.n_streams = 1            # per-kernel durations need the launches serialised on one stream
     trace = _lib.trace_launches(lambda: [step(pcm) for _ in range(a.steps)], torch)
     barrier()
+    if pipe is not None and streams_saved > 1:
+        pipe.n_streams = streams_saved
     per = {}
     for name, ms in trace:
         d = per.setdefault(name, [0, 0.0])
@@ -416,6 +424,8 @@ def main():
     kernels.sort(key=lambda d: -d["ms_per_step"])
     extra["kernels"] = kernels
     extra["traced_ms_per_step"] = traced_ms
+    extra["kernels_note"] = ("per-kernel device times from a single-stream pass over the same steps (launch trace); "
+                             "the timed step runs %d stream slice(s), so shares are relative to ms_per_step" % streams_saved)
     work = kernel_work(a.workload, B, L, pipe, out_bulk.shape[1] if pipe is None else 0)
     dom = kernels[0]
     w = work.get(dom["kernel"])
@@ -499,6 +509,7 @@ def main():
             "dtype": "f32" if (pipe is None or a.precision == "fp32") else "tf32", "data": "synthetic",
             "config": {"workload": wl["name"], "classifier_precision": a.precision if pipe is not None else None,
                        "clips_per_gpu": B, "clip_seconds": L / SR, "global_clips": n_total,
+                       "stream_slices": getattr(pipe, "n_streams", 1) if pipe is not None else 1,
                        "sharding": f"clips x{world}, no data-path collective; labels all_gather + tally all_reduce",
                        "l2": "inputs larger than L2 (%.0f MB int16 PCM per GPU per step)" % (B * L * 2 / 1e6),
                        "weights": "seeded synthetic, reference shapes (real .data shards stripped from the mount)"},

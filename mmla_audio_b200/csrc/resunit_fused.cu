@@ -81,7 +81,7 @@ __device__ __forceinline__ void ru_commit(uint64_t* bar) {
 }
 
 template <int CIN, int C, bool POOL>
-__global__ void __launch_bounds__(kThreadsRU) resunit_fused_kernel(const ResUnitArgs a) {
+__global__ void __launch_bounds__(kThreadsRU, (C == 32 ? 4 : (C == 64 ? 3 : 2))) resunit_fused_kernel(const ResUnitArgs a) {
     static_assert(POOL || CIN == C, "plain units keep the channel count");
     constexpr int kQuads = C / 4;
     constexpr int kQuadsIn = CIN / 4;

@@ -119,12 +119,17 @@ class Model:
         x = x.contiguous()
         B = x.shape[0]
         need = lib.mmla_net_workspace_bytes(self._handle, B)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        # one workspace per CUDA stream: forwards issued on different streams may run concurrently
+        key = int(torch.cuda.current_stream().cuda_stream)
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need or ws.device != x.device:
+            ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=x.device)
         prob = torch.empty((B, self.spec.n_classes), dtype=torch.float32, device=x.device)
         labels = torch.empty((B,), dtype=torch.int32, device=x.device)
         _lib.check(lib.mmla_net_forward(self._handle, x.data_ptr(), 2 if pad40 else (1 if is_u8 else 0), B,
-                                        self._ws.data_ptr(), self._ws.numel(), prob.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), prob.data_ptr(),
                                         labels.data_ptr(), _lib.stream_ptr(torch)), "mmla_net_forward")
         return prob, labels
 
