@@ -20,6 +20,11 @@
 //     the shared-memory operand for the next step.
 // This replaces T x (GEMM launch + gate launch) per direction by ONE launch for both directions
 // and removes the [B,1024] pre-activation round trip through HBM.
+//
+// A 128-clip tile is shared by a CLUSTER OF TWO CTAs: CTA `half` computes the gate columns of units
+// [128 half, 128 half + 128) (two of the four 64-unit passes) for all 128 clips, so 4096 clips give
+// 128 CTAs instead of 64 (148 SMs) and each CTA streams half of U per step.  h(t) goes through global
+// memory as before; the two halves hand it over with one remote mbarrier arrive per step (DSMEM).
 #include <math.h>
 #include <string.h>
 
@@ -45,6 +50,7 @@ struct LstmSmem {
     alignas(8) uint64_t tfull[2];                            // accumulator pass ready   (MMA -> epilogue)
     alignas(8) uint64_t tempty[2];                           // accumulator pass drained (epilogue -> MMA)
     alignas(8) uint64_t hready;                              // h re-staged for the next step
+    alignas(8) uint64_t peer[2];                             // the other half's h(t) is in global memory (even / odd steps)
     uint32_t tmem_base;
 };
 
@@ -101,7 +107,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     LstmSmem& s = *reinterpret_cast<LstmSmem*>(smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
-    const int b0 = blockIdx.x * kRows;
+    const int half = blockIdx.x & 1;                          // rank in the 2-CTA cluster = which 128 units
+    const int b0 = (blockIdx.x >> 1) * kRows;
+    constexpr int kPasses = 2;                                // 64-unit passes per CTA and step
+    constexpr int kChunksCta = kChunksPerStep / 2;            // weight chunks per CTA and step
     const float* xp = a.xp[dir];
     const float* wr = a.wr[dir];
     float* hg = a.h[dir];
@@ -120,6 +129,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             mbar_init(&s.tempty[i], 8);           // one arrival per epilogue warp
         }
         mbar_init(&s.hready, 1);
+        mbar_init(&s.peer[0], 1);
+        mbar_init(&s.peer[1], 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -129,10 +140,12 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    // both CTAs' barriers must be initialised before either arrives remotely
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s.tmem_base;
     const int n_rec = T > 1 ? T - 1 : 0;                          // recurrent steps
-    const long long total_chunks = static_cast<long long>(n_rec) * kChunksPerStep;
+    const long long total_chunks = static_cast<long long>(n_rec) * kChunksCta;
 
     if (warp == 8) {
         // ================= TMA producer: the periodic weight stream =================
@@ -142,7 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                 const long long use = g / kStages;
                 if (use > 0) wait_or_trap(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
                 mbar_arrive_expect_tx(&s.full[stg], kBChunkBytes);
-                tma_bulk_g2s(&s.Bst[stg][0], wr + (g % kChunksPerStep) * kBChunkFloats, kBChunkBytes, &s.full[stg]);
+                tma_bulk_g2s(&s.Bst[stg][0], wr + (half * kChunksCta + g % kChunksCta) * kBChunkFloats, kBChunkBytes,
+                             &s.full[stg]);
             }
         }
         __syncwarp();
@@ -154,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             constexpr uint32_t kStageUnits = kBChunkBytes / 16;
             for (int rs = 0; rs < n_rec; ++rs) {
                 wait_or_trap(&s.hready, static_cast<uint32_t>(rs & 1));        // h_{t-1} staged in smem
-                for (int pass = 0; pass < 4; ++pass) {
-                    const long long P = static_cast<long long>(rs) * 4 + pass; // global pass index
+                for (int pass = 0; pass < kPasses; ++pass) {
+                    const long long P = static_cast<long long>(rs) * kPasses + pass; // this CTA's pass counter
                     const int buf = static_cast<int>(P & 1);
                     if (P >= 2) wait_or_trap(&s.tempty[buf], static_cast<uint32_t>(((P >> 1) - 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -275,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
 #pragma unroll 4
             for (int i = tid; i < kRows * 32; i += kEpiThreads) {
                 const int r = i >> 5, line = i & 31;
+                if (((line >> 2) & 1) != half) continue;               // this half's 128 units of every gate
                 if (b0 + r < a.B) {
                     const float* ptr = xp + (static_cast<long long>(b0 + r) * T + t) * 1024 + line * 32;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
@@ -286,24 +301,45 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             const int t = dir == 0 ? step : T - 1 - step;
             if (step + 1 < T) prefetch_xp(dir == 0 ? t + 1 : t - 1);
             if (step == 0) {
-                for (int pass = 0; pass < 4; ++pass)                   // h0 = c0 = 0: z is the input projection alone
-                    for (int uo = 0; uo < 32; uo += 16) cell16(t, 64 * pass + usub + uo, 0u, true);
+                for (int pass = 0; pass < kPasses; ++pass)             // h0 = c0 = 0: z is the input projection alone
+                    for (int uo = 0; uo < 32; uo += 16) cell16(t, 64 * (kPasses * half + pass) + usub + uo, 0u, true);
             } else {
-                for (int pass = 0; pass < 4; ++pass) {
-                    const long long P = static_cast<long long>(step - 1) * 4 + pass;
+                for (int pass = 0; pass < kPasses; ++pass) {
+                    const long long P = static_cast<long long>(step - 1) * kPasses + pass;
                     const int buf = static_cast<int>(P & 1);
                     wait_or_trap(&s.tfull[buf], static_cast<uint32_t>((P >> 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     // pass columns: [0,64) i, [64,128) f, [128,192) c~, [192,256) o
                     for (int uo = 0; uo < 32; uo += 16)
-                        cell16(t, 64 * pass + usub + uo, static_cast<uint32_t>(buf * 256 + usub + uo), false);
+                        cell16(t, 64 * (kPasses * half + pass) + usub + uo, static_cast<uint32_t>(buf * 256 + usub + uo), false);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s.tempty[buf]);        // this warp has drained the pass
                 }
             }
             if (step + 1 < T) {
-                epi_bar_sync();            // all h(t) written; every MMA of this step has completed (tfull of pass 3)
+                // hand this half of h(t) to the peer CTA and wait for the other half: global stores -> gpu-scope
+                // fence -> one remote mbarrier arrive (release.cluster) -> local wait (acquire.cluster)
+                __threadfence();
+                epi_bar_sync();            // all of this CTA's h(t) written; every MMA of this step has completed
+                if (tid == 0) {
+                    uint32_t remote;
+                    // two barriers used alternately: a barrier can then never run two phases ahead of its waiter
+                    // (the peer cannot pass step s+1's hand-over without this CTA's arrive for s+1)
+                    uint64_t* pb = &s.peer[step & 1];
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(pb)), "r"(half ^ 1));
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+                    const uint32_t parity = static_cast<uint32_t>((step >> 1) & 1);
+                    uint32_t ok = 0;
+                    for (uint32_t i = 0; i < (1u << 24) && !ok; ++i)
+                        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+                                     "selp.u32 %0, 1, 0, p;\n}\n"
+                                     : "=r"(ok)
+                                     : "r"(smem_u32(pb)), "r"(parity)
+                                     : "memory");
+                    if (!ok) asm volatile("trap;");
+                }
+                epi_bar_sync();
                 restage_h();
                 epi_bar_sync();
                 if (tid == 0) mbar_arrive(&s.hready);
@@ -313,6 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    // neither CTA leaves while the peer could still arrive on its barrier
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace
@@ -355,8 +393,20 @@ int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr
     a.xp[0] = xp_f; a.xp[1] = xp_b; a.wr[0] = wr_f; a.wr[1] = wr_b;
     a.h[0] = h_f; a.h[1] = h_b; a.c[0] = c_f; a.c[1] = c_b;
     a.B = static_cast<int>(B); a.T = T;
-    const dim3 grid(static_cast<unsigned>((B + kRows - 1) / kRows), 2);
-    lstm_fused_kernel<<<grid, kThreads, smem, st>>>(a);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2u * static_cast<unsigned>((B + kRows - 1) / kRows), 2, 1);   // two CTAs (unit halves) per 128-clip tile
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel, a));
     mmla_count_launch("lstm_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
