@@ -50,6 +50,8 @@ struct RuSmem {
     alignas(128) unsigned char ab[(C / 4) * kRtot * 16];
     alignas(128) unsigned char a0[POOL ? (CIN / 4) * 128 * 16 : 16];   // raw x[2t] for the shortcut GEMM
     alignas(128) unsigned char ring[kStagesRU][(C == 128 ? 4 : 8) * C * 16];   // weight chunks: 16|32 K x C
+    alignas(16) float prm[4][C];                               // b1, BN2 scale, BN2 shift, b2 (+ bs): fetched once at
+                                                               // kernel start so the epilogues never wait on L2
     alignas(8) uint64_t full[kStagesRU];
     alignas(8) uint64_t empty[kStagesRU];
     alignas(8) uint64_t a_ready[2];                            // operand buffer written   (epilogue -> MMA)
@@ -99,6 +101,31 @@ __global__ void __launch_bounds__(kThreadsRU, (C == 32 ? 4 : (C == 64 ? 3 : 2)))
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = a.G, T = a.T;
     const int clip0 = blockIdx.x * G;
+
+    // ---- warps 0..7 issue their x loads BEFORE the setup barrier (mbarrier init, TMEM allocation), so the HBM latency
+    //      overlaps it; lanes run over channel quads (coalesced), all loads are in flight before the first use ----
+    constexpr int kRowsPerPass = kEpi / kQuadsIn;             // rows covered by 256 threads at once
+    constexpr int kIters = 128 / kRowsPerPass;
+    const int qd = tid % kQuadsIn, rsub = (tid % kEpi) / kQuadsIn;
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+    float4 v[kIters], v2[POOL ? kIters : 1];
+    if (warp < 8) {
+        sc = *reinterpret_cast<const float4*>(a.bn1_scale + 4 * qd);
+        sh = *reinterpret_cast<const float4*>(a.bn1_shift + 4 * qd);
+        const int Tin = POOL ? 2 * T : T;
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) {
+            const int r = rsub + i * kRowsPerPass;
+            const int t = r / G, g = r - t * G;                  // row = t*G + g
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (POOL) v2[i] = v[i];
+            if (clip0 + g < a.B) {
+                const float* src = a.x + (static_cast<long long>(clip0 + g) * Tin + (POOL ? 2 * t : t)) * CIN + 4 * qd;
+                v[i] = *reinterpret_cast<const float4*>(src);
+                if (POOL) v2[i] = *reinterpret_cast<const float4*>(src + CIN);
+            }
+        }
+    }
 
     if (tid == 0) {
         for (int i = 0; i < kStagesRU; ++i) {
@@ -198,34 +225,20 @@ __global__ void __launch_bounds__(kThreadsRU, (C == 32 ? 4 : (C == 64 ? 3 : 2)))
         __syncwarp();
     } else {
         // ================= warps 0..7: load/transform, epilogues =================
+        for (int i = tid; i < C; i += kEpi) {
+            s.prm[0][i] = a.b1[i];
+            s.prm[1][i] = a.bn2_scale[i];
+            s.prm[2][i] = a.bn2_shift[i];
+            s.prm[3][i] = a.b2[i] + (POOL ? a.bs[i] : 0.f);
+        }
         // zero the halo rows (rows [0,G) and [G+128, G+128+G)); epilogue 1 never touches them
         for (int i = tid; i < kQuads * 2 * G; i += kEpi) {
             const int qd = i / (2 * G), h = i % (2 * G);
             const int row = h < G ? h : 128 + h;
             *reinterpret_cast<uint4*>(&s.ab[0] + (qd * kRtot + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        // ---- x -> [MaxPool2] -> ReLU(BN1(.)) -> TF32 -> operand buffer (lanes run over channel quads:
-        //      coalesced; all loads are issued before the first use so their latencies overlap) ----
+        // ---- [MaxPool2] -> ReLU(BN1(.)) -> TF32 -> operand buffer (x was loaded before the setup barrier) ----
         {
-            constexpr int kRowsPerPass = kEpi / kQuadsIn;         // rows covered by 256 threads at once
-            constexpr int kIters = 128 / kRowsPerPass;
-            const int qd = tid % kQuadsIn, rsub = tid / kQuadsIn;
-            const float4 sc = *reinterpret_cast<const float4*>(a.bn1_scale + 4 * qd);
-            const float4 sh = *reinterpret_cast<const float4*>(a.bn1_shift + 4 * qd);
-            const int Tin = POOL ? 2 * T : T;
-            float4 v[kIters], v2[POOL ? kIters : 1];
-#pragma unroll
-            for (int i = 0; i < kIters; ++i) {
-                const int r = rsub + i * kRowsPerPass;
-                const int t = r / G, g = r - t * G;              // row = t*G + g
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (POOL) v2[i] = v[i];
-                if (clip0 + g < a.B) {
-                    const float* src = a.x + (static_cast<long long>(clip0 + g) * Tin + (POOL ? 2 * t : t)) * CIN + 4 * qd;
-                    v[i] = *reinterpret_cast<const float4*>(src);
-                    if (POOL) v2[i] = *reinterpret_cast<const float4*>(src + CIN);
-                }
-            }
 #pragma unroll
             for (int i = 0; i < kIters; ++i) {
                 const int r = rsub + i * kRowsPerPass;
@@ -282,9 +295,9 @@ __global__ void __launch_bounds__(kThreadsRU, (C == 32 ? 4 : (C == 64 ? 3 : 2)))
             ld16(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(col), z);
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                const float4 bv = *reinterpret_cast<const float4*>(a.b1 + col + j);
-                const float4 sc = *reinterpret_cast<const float4*>(a.bn2_scale + col + j);
-                const float4 sh = *reinterpret_cast<const float4*>(a.bn2_shift + col + j);
+                const float4 bv = *reinterpret_cast<const float4*>(&s.prm[0][col + j]);
+                const float4 sc = *reinterpret_cast<const float4*>(&s.prm[1][col + j]);
+                const float4 sh = *reinterpret_cast<const float4*>(&s.prm[2][col + j]);
                 const float v0 = fmaxf(fmaf(z[j + 0] + bv.x, sc.x, sh.x), 0.f);
                 const float v1 = fmaxf(fmaf(z[j + 1] + bv.y, sc.y, sh.y), 0.f);
                 const float v2 = fmaxf(fmaf(z[j + 2] + bv.z, sc.z, sh.z), 0.f);
@@ -312,11 +325,7 @@ __global__ void __launch_bounds__(kThreadsRU, (C == 32 ? 4 : (C == 64 ? 3 : 2)))
             ld16(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(C + col), z);
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                float4 bv = *reinterpret_cast<const float4*>(a.b2 + col + j);
-                if (POOL) {
-                    const float4 b3 = *reinterpret_cast<const float4*>(a.bs + col + j);
-                    bv.x += b3.x; bv.y += b3.y; bv.z += b3.z; bv.w += b3.w;
-                }
+                const float4 bv = *reinterpret_cast<const float4*>(&s.prm[3][col + j]);
                 *reinterpret_cast<float4*>(stg + row * kStride + col + j) =
                     make_float4(z[j] + bv.x, z[j + 1] + bv.y, z[j + 2] + bv.z, z[j + 3] + bv.w);
             }
