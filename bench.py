@@ -247,7 +247,9 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     conv_flop = B * (stem + res + xproj)
     if spec.ndim == 1:
         work["resunit_fused_kernel"] = {"bound": "tensor", "per_step": B * res, "what": "the 9 residual units (18 convs + 3 shortcuts)"}
-        work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (stem + xproj), "what": "stem conv + both LSTM input projections"}
+        work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * xproj, "what": "both LSTM input projections"}
+        work["stem_fused_kernel"] = {"bound": "hbm", "per_step": B * 256 * (40 + 32) * 4,
+                                     "what": "[256,40] features in + [256,32] activations out (Conv1D k=4)"}
         work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
     else:
         for k in ("conv_tc_kernel", "conv_igemm_kernel"):

@@ -378,6 +378,7 @@ int mmla_tc_ntile(int n);
 long long mmla_tc_arranged_floats(int K, int N);
 void mmla_tc_arrange_weights(const float* w, int K, int N, float* out);
 int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st);
+int mmla_launch_stem_fused(const float* x, const float* wg, const float* bias, float* y, long long B, cudaStream_t st);
 // resunit_fused.cu
 int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* bn1_scale,
                               const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
@@ -665,7 +666,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
                 MMLA_CUDA_CHECK(cudaGetLastError());
                 x40 = xpad;
             }
-            rc = launch_conv(net->stem_pad, x40, 0, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
+            rc = mmla_launch_stem_fused(x40, net->stem_pad.k_tc, net->stem_pad.b, buf[cur], B, st);   // stem_fused.cu
         } else if (pad40) {
             mmla_set_error("net_forward: 40-channel input needs the TF32 tensor-core mode");
             return MMLA_EUNSUP;

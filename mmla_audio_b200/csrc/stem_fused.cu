@@ -1,0 +1,188 @@
+// Speaker-classifier stem on tcgen05 (TF32 mode): Conv1D(32, kernel 4, padding 'same') over the
+// channel-padded feature tensor — the first layer of `res_model`
+// (SpeakerIdentification/scripts/speaker_identification.py:196, `Conv1D(32, 4, padding='same')`).
+//
+//   x [B][256][40] fp32 (MFCC | delta | delta-delta | 0)  ->  y [B][256][32] fp32,
+//   y[t] = b + sum_{j=0..3} W[j] x[t + j - 1]        (Keras 'same' for k = 4: one zero row before, two after)
+//
+// Same operand scheme as resunit_fused.cu: one CTA owns 128 consecutive time steps of one clip, x is read
+// once (coalesced), rounded to TF32 and stored as the UMMA K-major no-swizzle "slab" operand
+// [channel quad][row][16 B] with the 3 halo rows, so filter tap j is the SAME buffer read j rows further
+// down — no im2col gather (the generic conv_tc kernel spent 0.18 ms per 4096 clips on this layer, 3x its
+// HBM time).  The 20 KB of weights land by one TMA bulk copy; 20 tcgen05.mma (M=128, N=32, K=8) accumulate
+// in 32 TMEM columns; the epilogue adds the bias and stores coalesced rows through a staging tile.
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int kT = 256, kCin = 40, kCout = 32;
+constexpr int kQuads = kCin / 4;                 // 10 channel quads
+constexpr int kRows = 137;                       // 128 + 3 halo rows, padded to == 1 mod 8 (bank-friendly slab stride)
+constexpr int kWBytes = 4 * kCin * kCout * 4;    // 20480: 40 K-slabs x [32][4] floats
+constexpr int kThreadsStem = 256 + 32;           // warps 0..7 load / epilogue, warp 8 issues TMA + MMA
+
+struct StemSmem {
+    alignas(128) unsigned char ab[kQuads * kRows * 16];     // operand slabs; later the output staging tile
+    alignas(128) unsigned char w[kWBytes];
+    alignas(16) float bias[kCout];
+    alignas(8) uint64_t wfull, aready, done;
+    uint32_t tmem_base;
+};
+static_assert(128 * (kCout + 4) * 4 <= kQuads * kRows * 16, "staging tile must fit in the operand buffer");
+
+__device__ __forceinline__ uint32_t st_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void st_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+__device__ __forceinline__ uint64_t st_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ bool st_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+__global__ void __launch_bounds__(kThreadsStem, 4) stem_fused_kernel(const float* __restrict__ x, const float* __restrict__ wg,
+                                                                    const float* __restrict__ bias, float* __restrict__ y,
+                                                                    int B) {
+    extern __shared__ unsigned char smem_dyn[];
+    StemSmem& s = *reinterpret_cast<StemSmem*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int clip = blockIdx.x >> 1, t0 = (blockIdx.x & 1) * 128;
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kCout >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);   // f32 += tf32 x tf32, M=128, N=32
+
+    // x rows t0-1 .. t0+129 (131 rows x 10 quads), issued before the setup barrier so HBM latency overlaps it
+    constexpr int kLoads = (131 * kQuads + 255) / 256;   // 6 float4 per thread
+    float4 v[kLoads];
+    if (warp < 8) {
+        const float* xc = x + static_cast<long long>(clip) * kT * kCin;
+#pragma unroll
+        for (int i = 0; i < kLoads; ++i) {
+            const int idx = tid + i * 256;
+            const int r = idx / kQuads, q = idx - r * kQuads;
+            const int t = t0 - 1 + r;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < 131 && t >= 0 && t < kT) v[i] = *reinterpret_cast<const float4*>(xc + t * kCin + 4 * q);
+        }
+        if (tid < kCout) s.bias[tid] = bias[tid];
+    }
+    if (tid == 0) {
+        mbar_init(&s.wfull, 1);
+        mbar_init(&s.aready, 1);
+        mbar_init(&s.done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(32u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s.tmem_base;
+
+    if (warp == 8) {
+        // ================= weights by TMA, then the 20 MMAs (whole warp converged, one elected lane issues) =========
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&s.wfull, kWBytes);
+            tma_bulk_g2s(&s.w[0], wg, kWBytes, &s.wfull);
+        }
+        __syncwarp();
+        st_wait(&s.wfull, 0u);
+        st_wait(&s.aready, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dA = st_desc(smem_u32(&s.ab[0]), kRows * 16, 128);
+        const uint64_t dB = st_desc(smem_u32(&s.w[0]), kCout * 16, 128);
+        if (st_elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap)
+#pragma unroll
+                for (int kq = 0; kq < kQuads / 2; ++kq) {
+                    // K = 8 channels = slabs 2kq, 2kq+1 of the tap: A rows shifted down by `tap`, B slab tap*10 + 2kq
+                    const uint64_t ad = dA + static_cast<uint64_t>(2 * kq * kRows + tap);
+                    const uint64_t bd = dB + static_cast<uint64_t>((tap * kQuads + 2 * kq) * kCout);
+                    const uint32_t acc = (tap | kq) != 0 ? 1u : 0u;
+                    asm volatile(
+                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
+                        "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                        : "memory");
+                }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s.done)) : "memory");
+        }
+        __syncwarp();
+    } else {
+        // ================= warps 0..7: operand slabs, epilogue =================
+#pragma unroll
+        for (int i = 0; i < kLoads; ++i) {
+            const int idx = tid + i * 256;
+            const int r = idx / kQuads, q = idx - r * kQuads;
+            if (r < 131)
+                *reinterpret_cast<uint4*>(&s.ab[0] + (q * kRows + r) * 16) =
+                    make_uint4(st_tf32(v[i].x), st_tf32(v[i].y), st_tf32(v[i].z), st_tf32(v[i].w));
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s.aready)) : "memory");
+
+        // epilogue: TMEM lane = output row; warps 0..3 take columns 0..15, warps 4..7 columns 16..31
+        const int row = 32 * (warp & 3) + lane;
+        const int col = (warp >> 2) * 16;
+        constexpr int kStride = kCout + 4;
+        float* stg = reinterpret_cast<float*>(&s.ab[0]);
+        st_wait(&s.done, 0u);                                   // all MMAs retired: the operand buffer is dead
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(col)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(&s.bias[col + j]);
+            *reinterpret_cast<float4*>(stg + row * kStride + col + j) =
+                make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y, __uint_as_float(r[j + 2]) + bv.z,
+                            __uint_as_float(r[j + 3]) + bv.w);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float* yc = y + (static_cast<long long>(clip) * kT + t0) * kCout;
+#pragma unroll
+        for (int i = 0; i < 128 * (kCout / 4) / 256; ++i) {      // 4 float4 per thread, coalesced rows
+            const int idx = tid + i * 256;
+            const int rr = idx >> 3, q = idx & 7;
+            *reinterpret_cast<float4*>(yc + rr * kCout + 4 * q) = *reinterpret_cast<const float4*>(stg + rr * kStride + 4 * q);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
+    (void)B;
+}
+
+}  // namespace
+
+// x: [B][256][40] fp32 (channel 39 = 0), wg: the conv_tc-arranged weights of the padded stem (K = 160, N = 32),
+// bias: [32], y: [B][256][32].
+int mmla_launch_stem_fused(const float* x, const float* wg, const float* bias, float* y, long long B, cudaStream_t st) {
+    MMLA_REQUIRE(B > 0 && B < (1LL << 22), MMLA_EINVAL, "stem_fused: bad batch");
+    static bool attr_set = false;
+    const int smem = static_cast<int>(sizeof(StemSmem) + 128);
+    if (!attr_set) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    stem_fused_kernel<<<static_cast<unsigned>(2 * B), kThreadsStem, smem, st>>>(x, wg, bias, y, static_cast<int>(B));
+    mmla_count_launch("stem_fused_kernel", st);
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
