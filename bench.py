@@ -291,7 +291,7 @@ def main():
     from mmla_audio_b200 import _lib, models, synth, tally, weights as W
     from mmla_audio_b200 import speaker_identification as si
     from mmla_audio_b200.pipeline import OverlapPipeline, SpeakerPipeline
-    from mmla_audio_b200.sharding import allreduce_counts, gather_labels, shard_range
+    from mmla_audio_b200.sharding import allreduce_counts, bind_host_thread_to_gpu, gather_labels, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -299,6 +299,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for --impl ours")
     torch.cuda.set_device(local_rank)
+    numa_bound = bind_host_thread_to_gpu(physical_gpu_index(local_rank)) if world > 1 else False
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
@@ -512,6 +513,7 @@ def main():
             "config": {"workload": wl["name"], "classifier_precision": a.precision if pipe is not None else None,
                        "clips_per_gpu": B, "clip_seconds": L / SR, "global_clips": n_total,
                        "stream_slices": getattr(pipe, "n_streams", 1) if pipe is not None else 1,
+                       "host_numa_binding": bool(numa_bound),
                        "sharding": f"clips x{world}, no data-path collective; labels all_gather + tally all_reduce",
                        "l2": "inputs larger than L2 (%.0f MB int16 PCM per GPU per step)" % (B * L * 2 / 1e6),
                        "weights": "seeded synthetic, reference shapes (real .data shards stripped from the mount)"},

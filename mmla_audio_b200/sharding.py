@@ -38,3 +38,18 @@ def allreduce_counts(counts, world: int):
     if world > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return counts
+
+
+def bind_host_thread_to_gpu(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores NVML reports as closest to ``device_index`` (same NUMA
+    node / PCIe root), so pinned staging buffers are first-touched next to the GPU that will read them.
+    With one process per GPU the eight uploads otherwise contend for one socket's memory controllers.
+    Returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
