@@ -365,6 +365,7 @@ struct MmlaNet {
     ConvW lstm_in[2];                     // [feat,1024] projection (bias = LSTM bias)
     ConvW lstm_rec[2];                    // [256,1024] recurrent (bias = zeros)
     const float* lstm_rec_fused[2] = {nullptr, nullptr};   // chunk stream for lstm_fused_kernel
+    const float* lstm_in_fused[2] = {nullptr, nullptr};    // chunk stream for xproj_fused_kernel
     const float* dense_k = nullptr;
     const float* dense_b = nullptr;
     int in_h = 0, in_w = 0, in_c = 0;     // per-clip input geometry
@@ -385,6 +386,10 @@ int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int 
                               const float* bn2_shift, const float* w2, const float* b2, const float* ws, const float* bs,
                               cudaStream_t st);
 // lstm_fused.cu
+long long mmla_xproj_arranged_floats();
+void mmla_xproj_arrange_weights(const float* W, float* out);
+int mmla_launch_xproj_fused(const float* seq, const float* w_f, const float* w_b, const float* b_f, const float* b_b,
+                            float* xp_f, float* xp_b, long long rows, cudaStream_t st);
 long long mmla_lstm_arranged_floats();
 void mmla_lstm_arrange_weights(const float* U, float* out);
 int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
@@ -570,6 +575,10 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
             stage.resize(stage.size() + mmla_lstm_arranged_floats());
             mmla_lstm_arrange_weights(wr_src, stage.data() + off);
             fixes.push_back({&net->lstm_rec_fused[d], off});
+            const long long off_in = static_cast<long long>(stage.size());
+            stage.resize(stage.size() + mmla_xproj_arranged_floats());
+            mmla_xproj_arrange_weights(wi_src, stage.data() + off_in);
+            fixes.push_back({&net->lstm_in_fused[d], off_in});
         }
         if (zero_bias_off < 0) {
             while (stage.size() % 4) stage.push_back(0.f);
@@ -730,8 +739,15 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         }
         MMLA_CUDA_CHECK(cudaGetLastError());
         // BiLSTM(256): input projections for all steps, then the recurrence
-        for (int d = 0; d < 2; ++d)
-            if ((rc = launch_conv(net->lstm_in[d], seq, 0, B * T, 1, 1, nullptr, ACT_NONE, nullptr, 0, xp[d], st, tc))) return rc;
+        if (tc && net->lstm_in_fused[0] && net->lstm_in_fused[1]) {
+            // both directions in one launch (xproj_fused.cu)
+            if ((rc = mmla_launch_xproj_fused(seq, net->lstm_in_fused[0], net->lstm_in_fused[1], net->lstm_in[0].b,
+                                              net->lstm_in[1].b, xp[0], xp[1], B * T, st)))
+                return rc;
+        } else {
+            for (int d = 0; d < 2; ++d)
+                if ((rc = launch_conv(net->lstm_in[d], seq, 0, B * T, 1, 1, nullptr, ACT_NONE, nullptr, 0, xp[d], st, tc))) return rc;
+        }
         if (tc) {
             // one persistent launch: both directions, all time steps (lstm_fused.cu)
             if ((rc = mmla_launch_lstm_fused(xp[0], xp[1], net->lstm_rec_fused[0], net->lstm_rec_fused[1], hdir[0], hdir[1],
