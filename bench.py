@@ -244,12 +244,13 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     xproj = 2.0 * 2 * t_lstm * feat * 1024
     work["lstm_fused_kernel"] = {"bound": "tensor", "per_step": B * 2.0 * 2 * (t_lstm - 1) * 256 * 1024,
                                  "what": "recurrent products h U of both directions, T-1 steps"}
+    work["xproj_fused_kernel"] = {"bound": "hbm", "per_step": B * t_lstm * (128 + 2 * 1024) * 4,
+                                  "what": "[B*T,128] features in + both directions' [B*T,1024] input projections out"}
     conv_flop = B * (stem + res + xproj)
     if spec.ndim == 1:
         work["resunit_fused_kernel"] = {"bound": "tensor", "per_step": B * res, "what": "the 9 residual units (18 convs + 3 shortcuts)"}
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * xproj, "what": "both LSTM input projections"}
-        work["xproj_fused_kernel"] = {"bound": "hbm", "per_step": B * t_lstm * (128 + 2 * 1024) * 4,
-                                      "what": "[B*T,128] features in + both directions' [B*T,1024] input projections out"}
+
         work["stem_fused_kernel"] = {"bound": "hbm", "per_step": B * 256 * (40 + 32) * 4,
                                      "what": "[256,40] features in + [256,32] activations out (Conv1D k=4)"}
         work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
