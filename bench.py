@@ -253,6 +253,8 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
 
         work["stem_fused_kernel"] = {"bound": "hbm", "per_step": B * 256 * (40 + 32) * 4,
                                      "what": "[256,40] features in + [256,32] activations out (Conv1D k=4)"}
+        work["stem_delta_fused_kernel"] = {"bound": "hbm", "per_step": B * (rows * 13 + 256 * 32) * 4,
+                                           "what": "[T,13] cepstra in + [256,32] activations out (delta, delta-delta, padding, Conv1D k=4)"}
         work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
     else:
         for k in ("conv_tc_kernel", "conv_igemm_kernel"):

@@ -175,6 +175,18 @@ int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch
                      void* workspace, int64_t workspace_bytes,
                      float* prob, int32_t* labels, void* stream);
 
+/*
+ * Speaker net, TF32 mode, straight from the MFCC-13 rows (the label pipeline of
+ * SpeakerIdentification/scripts/record_on_pc.py:120-137 when the [256,39] feature tensor itself is not wanted):
+ *   cepstra   float32, clip i at cepstra + i*cep_clip_stride floats, rows of 16 floats (13 cepstra + 3 ignored),
+ *             n_frames rows per clip (the psf frame count, 1..256) — what mmla_psf_mfcc_rows(with_deltas=0,
+ *             pad_frames=0, out_row_stride=16) writes.
+ * The stem kernel builds delta / delta-delta (speaker_identification.py:141-151,387-389) and the zero rows up to 256
+ * (:391-395) on the fly, so the feature tensor never exists in HBM.  Results equal mmla_net_forward on the features.
+ */
+int mmla_net_forward_cepstra(MmlaNet* net, const float* cepstra, int64_t cep_clip_stride, int32_t n_frames, int64_t batch,
+                             void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Label tallies.  Replaces the counting loops of
  *   OverlapDetection/scripts/overlap_degree_distribution.py:49-61

@@ -16,7 +16,7 @@ SYMBOLS = (
     "mmla_last_error", "mmla_abi_version", "mmla_launch_count", "mmla_crc32c_host",
     "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_psf_mfcc_rows", "mmla_delta", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
-    "mmla_net_forward",
+    "mmla_net_forward", "mmla_net_forward_cepstra",
     "mmla_tally", "mmla_synth_pcm", "mmla_debug_mfcc_tc_dump", "mmla_trace_begin", "mmla_trace_end",
 )
 
@@ -66,6 +66,7 @@ def load() -> C.CDLL:
         "mmla_net_set_precision": (C.c_int, [vp, i32]),
         "mmla_net_workspace_bytes": (i64, [vp, i64]),
         "mmla_net_forward": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, vp, vp]),
+        "mmla_net_forward_cepstra": (C.c_int, [vp, vp, i64, i32, i64, vp, i64, vp, vp, vp]),
         "mmla_tally": (C.c_int, [vp, i64, i32, vp, vp]),
         "mmla_synth_pcm": (C.c_int, [vp, i64, i64, i32, i64, u32, vp, vp]),
         "mmla_debug_mfcc_tc_dump": (None, [vp, vp]),

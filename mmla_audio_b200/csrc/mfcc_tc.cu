@@ -103,7 +103,8 @@ struct TcParams {
     long long out_clip_stride;
     int groups_per_clip;
     int clip_len;
-    int row_stride;                // floats between output rows (13 or 39)
+    int row_stride;                // floats between output rows (>= 13 or 39)
+    int zero_tail;                 // columns [13, 13 + zero_tail) of every row are zeroed by the epilogue (no finish pass)
     int pad_frames;
     int append_energy;
     float preemph;
@@ -406,6 +407,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, TcSmem& s, uint
         float* o = p.out + gr.clip * p.out_clip_stride + static_cast<long long>(t) * p.row_stride + 7 * P;
 #pragma unroll
         for (int i = 0; i < nc; ++i) o[i] = c[i];
+        if (P == 1)
+            for (int i = 0; i < p.zero_tail; ++i) o[6 + i] = 0.f;
     }
 }
 
@@ -984,6 +987,7 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     kp.groups_per_clip = groups_per_clip;
     kp.clip_len = clip_len;
     kp.row_stride = out_row_stride;
+    kp.zero_tail = (!p.with_deltas && p.pad_frames == 0 && out_row_stride > 13 && out_row_stride - 13 <= 3) ? out_row_stride - 13 : 0;
     kp.pad_frames = p.pad_frames;
     kp.append_energy = p.append_energy;
     kp.preemph = p.preemph;
@@ -1018,7 +1022,10 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     if (rc != MMLA_OK) return rc;
 
     const int dim = p.with_deltas ? 39 : 13;
-    const bool need_finish = p.with_deltas || p.pad_frames > 0 || out_row_stride > dim;
+    // plain cepstra with a few spare columns per row (e.g. the 16-float rows stem_fused.cu consumes): the epilogue zeroes
+    // them itself and no second pass is needed
+    const bool tail_in_epilogue = !p.with_deltas && p.pad_frames == 0 && out_row_stride > dim && out_row_stride - dim <= 3;
+    const bool need_finish = p.with_deltas || p.pad_frames > 0 || (out_row_stride > dim && !tail_in_epilogue);
     if (need_finish) {
         FinParams fp;
         fp.out = out;

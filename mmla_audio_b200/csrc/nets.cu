@@ -380,6 +380,8 @@ long long mmla_tc_arranged_floats(int K, int N);
 void mmla_tc_arrange_weights(const float* w, int K, int N, float* out);
 int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st);
 int mmla_launch_stem_fused(const float* x, const float* wg, const float* bias, float* y, long long B, cudaStream_t st);
+int mmla_launch_stem_from_cepstra(const float* cep, long long cep_clip_stride, int n_frames, const float* wg, const float* bias,
+                                  float* y, long long B, cudaStream_t st);
 // resunit_fused.cu
 int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* bn1_scale,
                               const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
@@ -631,10 +633,30 @@ EXPORT int64_t mmla_net_workspace_bytes(const MmlaNet* net, int64_t batch) {
     return (mb < 1 ? 1 : mb) * net->per_clip_floats * static_cast<long long>(sizeof(float)) + 256;
 }
 
+static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t cep_frames, int64_t cep_clip_stride, int64_t batch,
+                        void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream);
+
 EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch, void* workspace,
                             int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
+    return forward_impl(net, x, x_is_u8, 0, 0, batch, workspace, workspace_bytes, prob, labels, stream);
+}
+
+EXPORT int mmla_net_forward_cepstra(MmlaNet* net, const float* cepstra, int64_t cep_clip_stride, int32_t n_frames, int64_t batch,
+                                    void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
+    MMLA_REQUIRE(net && net->kind == MMLA_NET_SPEAKER && net->precision == MMLA_PRECISION_TF32 && net->stem_pad.k_tc, MMLA_EUNSUP,
+                 "net_forward_cepstra: needs the speaker net in TF32 tensor-core mode");
+    MMLA_REQUIRE(n_frames >= 1 && n_frames <= 256 && cep_clip_stride >= static_cast<int64_t>(n_frames) * 16, MMLA_EINVAL,
+                 "net_forward_cepstra: bad cepstra geometry (n_frames %d, clip stride %lld)", n_frames,
+                 static_cast<long long>(cep_clip_stride));
+    return forward_impl(net, cepstra, 3, n_frames, cep_clip_stride, batch, workspace, workspace_bytes, prob, labels, stream);
+}
+
+static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t cep_frames, int64_t cep_clip_stride, int64_t batch,
+                        void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
     MMLA_REQUIRE(net && x && prob && workspace, MMLA_EINVAL, "net_forward: null argument");
     MMLA_REQUIRE(batch >= 0, MMLA_EINVAL, "net_forward: negative batch");
+    const bool from_cep = x_is_u8 == 3;       // MFCC-13 rows; delta / delta-delta / padding happen inside the stem kernel
+    if (from_cep) x_is_u8 = 0;
     MMLA_REQUIRE(x_is_u8 >= 0 && x_is_u8 <= 2, MMLA_EINVAL, "net_forward: bad input kind %d", x_is_u8);
     MMLA_REQUIRE(x_is_u8 != 1 || net->kind == MMLA_NET_OVERLAP, MMLA_EINVAL, "net_forward: uint8 input is for the overlap net");
     MMLA_REQUIRE(x_is_u8 != 2 || net->kind == MMLA_NET_SPEAKER, MMLA_EINVAL, "net_forward: 40-channel input is for the speaker net");
@@ -647,7 +669,7 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ov = net->kind == MMLA_NET_OVERLAP;
     const bool tc = net->precision == MMLA_PRECISION_TF32;
-    const long long in_elems = static_cast<long long>(net->in_h) * net->in_w * (pad40 ? 40 : net->in_c);
+    const long long in_elems = from_cep ? cep_clip_stride : static_cast<long long>(net->in_h) * net->in_w * (pad40 ? 40 : net->in_c);
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const int T = net->seq_len;
 
@@ -667,7 +689,10 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
         int H = net->in_h, W = net->in_w;
         int cur = 0;
         int rc;
-        if (tc && !ov && net->stem_pad.k_tc) {
+        if (from_cep) {
+            rc = mmla_launch_stem_from_cepstra(static_cast<const float*>(xin), cep_clip_stride, cep_frames, net->stem_pad.k_tc,
+                                               net->stem_pad.b, buf[cur], B, st);                     // stem_fused.cu
+        } else if (tc && !ov && net->stem_pad.k_tc) {
             const float* x40 = static_cast<const float*>(xin);
             if (!pad40) {
                 pad_channels_kernel<<<ew_grid(B * 256 * 10), 256, 0, st>>>(static_cast<const float*>(xin), xpad, B * 256, 39, 40);

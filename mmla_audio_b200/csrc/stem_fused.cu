@@ -11,6 +11,12 @@
 // down — no im2col gather (the generic conv_tc kernel spent 0.18 ms per 4096 clips on this layer, 3x its
 // HBM time).  The 20 KB of weights land by one TMA bulk copy; 20 tcgen05.mma (M=128, N=32, K=8) accumulate
 // in 32 TMEM columns; the epilogue adds the bias and stores coalesced rows through a staging tile.
+//
+// FROM_CEP variant (the label pipeline, where the [256,39] feature tensor itself is not wanted): the input is the
+// MFCC-13 rows straight from the feature kernel ([B][rows >= T][16] fp32) and the CTA builds its feature rows on the
+// fly — delta and delta-delta exactly as the reference's `delta(feat, 2)` (speaker_identification.py:141-151, edge
+// replicated inside the clip's T frames), zero rows from T to 256 (:391-395) — so the feature tensor never exists in
+// HBM and the separate delta / padding pass disappears.
 #include <string.h>
 
 #include "conv_common.cuh"
@@ -27,6 +33,8 @@ struct StemSmem {
     alignas(128) unsigned char ab[kQuads * kRows * 16];     // operand slabs; later the output staging tile
     alignas(128) unsigned char w[kWBytes];
     alignas(16) float bias[kCout];
+    float cep[139][13];                                       // FROM_CEP: cepstra of times t0-5 .. t0+133 (clamped)
+    float dlt[135][13];                                       // FROM_CEP: delta   of times t0-3 .. t0+131 (clamped)
     alignas(8) uint64_t wfull, aready, done;
     uint32_t tmem_base;
 };
@@ -48,9 +56,10 @@ __device__ __forceinline__ bool st_elect_one() {
     return pred != 0;
 }
 
+template <bool FROM_CEP>
 __global__ void __launch_bounds__(kThreadsStem, 4) stem_fused_kernel(const float* __restrict__ x, const float* __restrict__ wg,
                                                                     const float* __restrict__ bias, float* __restrict__ y,
-                                                                    int B) {
+                                                                    int B, int n_frames, long long cep_clip_stride) {
     extern __shared__ unsigned char smem_dyn[];
     StemSmem& s = *reinterpret_cast<StemSmem*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -62,14 +71,31 @@ __global__ void __launch_bounds__(kThreadsStem, 4) stem_fused_kernel(const float
     constexpr int kLoads = (131 * kQuads + 255) / 256;   // 6 float4 per thread
     float4 v[kLoads];
     if (warp < 8) {
-        const float* xc = x + static_cast<long long>(clip) * kT * kCin;
+        if (!FROM_CEP) {
+            const float* xc = x + static_cast<long long>(clip) * kT * kCin;
 #pragma unroll
-        for (int i = 0; i < kLoads; ++i) {
-            const int idx = tid + i * 256;
-            const int r = idx / kQuads, q = idx - r * kQuads;
-            const int t = t0 - 1 + r;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < 131 && t >= 0 && t < kT) v[i] = *reinterpret_cast<const float4*>(xc + t * kCin + 4 * q);
+            for (int i = 0; i < kLoads; ++i) {
+                const int idx = tid + i * 256;
+                const int r = idx / kQuads, q = idx - r * kQuads;
+                const int t = t0 - 1 + r;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < 131 && t >= 0 && t < kT) v[i] = *reinterpret_cast<const float4*>(xc + t * kCin + 4 * q);
+            }
+        } else {
+            // cepstra rows of times t0-5 .. t0+133, clamped into the clip (the reference's edge replication); 16-float rows
+            const float* cc = x + static_cast<long long>(clip) * cep_clip_stride;
+            const int Tm1 = n_frames - 1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {                 // 139 rows x 4 float4 = 556 loads
+                const int idx = tid + i * 256;
+                const int rr = idx >> 2, q4 = idx & 3;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rr < 139) {
+                    int t = t0 - 5 + rr;
+                    t = t < 0 ? 0 : (t > Tm1 ? Tm1 : t);
+                    v[i] = *reinterpret_cast<const float4*>(cc + static_cast<long long>(t) * 16 + 4 * q4);
+                }
+            }
         }
         if (tid < kCout) s.bias[tid] = bias[tid];
     }
@@ -120,13 +146,74 @@ __global__ void __launch_bounds__(kThreadsStem, 4) stem_fused_kernel(const float
         __syncwarp();
     } else {
         // ================= warps 0..7: operand slabs, epilogue =================
+        if (!FROM_CEP) {
 #pragma unroll
-        for (int i = 0; i < kLoads; ++i) {
-            const int idx = tid + i * 256;
-            const int r = idx / kQuads, q = idx - r * kQuads;
-            if (r < 131)
+            for (int i = 0; i < kLoads; ++i) {
+                const int idx = tid + i * 256;
+                const int r = idx / kQuads, q = idx - r * kQuads;
+                if (r < 131)
+                    *reinterpret_cast<uint4*>(&s.ab[0] + (q * kRows + r) * 16) =
+                        make_uint4(st_tf32(v[i].x), st_tf32(v[i].y), st_tf32(v[i].z), st_tf32(v[i].w));
+            }
+        } else {
+            const int Tm1 = n_frames - 1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int idx = tid + i * 256;
+                const int rr = idx >> 2, q4 = idx & 3;
+                if (rr < 139) {
+                    const float vv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (4 * q4 + u < 13) s.cep[rr][4 * q4 + u] = vv[u];
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // delta of times t0-3 .. t0+131 that lie inside the clip: row dd <-> time t0 - 3 + dd; cep row of time t is
+            // t - (t0 - 5).  Every index below is a time already clamped into [0, T-1], and |clamped - requested| <= 2
+            // per level, so it stays inside the staged windows.
+            for (int i = tid; i < 135 * 13; i += 256) {
+                const int dd = i / 13, c = i - dd * 13;
+                const int td = t0 - 3 + dd;
+                if (td < 0 || td > Tm1) continue;         // never read: consumers index by times clamped into [0, T-1]
+                float acc = 0.f;
+#pragma unroll
+                for (int k = -2; k <= 2; ++k) {
+                    int tt = td + k;
+                    tt = tt < 0 ? 0 : (tt > Tm1 ? Tm1 : tt);
+                    acc = fmaf(static_cast<float>(k), s.cep[tt - (t0 - 5)][c], acc);
+                }
+                s.dlt[dd][c] = acc * 0.1f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // feature rows of times t0-1 .. t0+129 -> TF32 slabs; rows outside [0, T) are the zero padding
+            for (int idx = tid; idx < 131 * kQuads; idx += 256) {
+                const int r = idx / kQuads, q = idx - r * kQuads;
+                const int t = t0 - 1 + r;
+                float f[4] = {0.f, 0.f, 0.f, 0.f};
+                if (t >= 0 && t <= Tm1) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ch = 4 * q + u;
+                        if (ch < 13) {
+                            f[u] = s.cep[t - (t0 - 5)][ch];
+                        } else if (ch < 26) {
+                            f[u] = s.dlt[t - (t0 - 3)][ch - 13];
+                        } else if (ch < 39) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int k = -2; k <= 2; ++k) {
+                                int tt = t + k;
+                                tt = tt < 0 ? 0 : (tt > Tm1 ? Tm1 : tt);
+                                acc = fmaf(static_cast<float>(k), s.dlt[tt - (t0 - 3)][ch - 26], acc);
+                            }
+                            f[u] = acc * 0.1f;
+                        }
+                    }
+                }
                 *reinterpret_cast<uint4*>(&s.ab[0] + (q * kRows + r) * 16) =
-                    make_uint4(st_tf32(v[i].x), st_tf32(v[i].y), st_tf32(v[i].z), st_tf32(v[i].w));
+                    make_uint4(st_tf32(f[0]), st_tf32(f[1]), st_tf32(f[2]), st_tf32(f[3]));
+            }
         }
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -178,11 +265,32 @@ int mmla_launch_stem_fused(const float* x, const float* wg, const float* bias, f
     static bool attr_set = false;
     const int smem = static_cast<int>(sizeof(StemSmem) + 128);
     if (!attr_set) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    stem_fused_kernel<<<static_cast<unsigned>(2 * B), kThreadsStem, smem, st>>>(x, wg, bias, y, static_cast<int>(B));
+    stem_fused_kernel<false><<<static_cast<unsigned>(2 * B), kThreadsStem, smem, st>>>(x, wg, bias, y, static_cast<int>(B), kT, 0);
     mmla_count_launch("stem_fused_kernel", st);
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
+// cep: MFCC-13 rows [B][>= n_frames][16] fp32 (clip i at cep + i * cep_clip_stride), n_frames = psf frame count of every
+// clip (1..256); the delta / delta-delta / zero-padding of the feature tensor happen inside the kernel.
+int mmla_launch_stem_from_cepstra(const float* cep, long long cep_clip_stride, int n_frames, const float* wg, const float* bias,
+                                  float* y, long long B, cudaStream_t st) {
+    MMLA_REQUIRE(B > 0 && B < (1LL << 22), MMLA_EINVAL, "stem_fused: bad batch");
+    MMLA_REQUIRE(n_frames >= 1 && n_frames <= kT, MMLA_EINVAL, "stem_fused: n_frames=%d must be in [1,256]", n_frames);
+    MMLA_REQUIRE((cep_clip_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(cep) & 15) == 0, MMLA_EINVAL,
+                 "stem_fused: cepstra rows must be 16-byte aligned");
+    static bool attr_set = false;
+    const int smem = static_cast<int>(sizeof(StemSmem) + 128);
+    if (!attr_set) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    stem_fused_kernel<true><<<static_cast<unsigned>(2 * B), kThreadsStem, smem, st>>>(cep, wg, bias, y, static_cast<int>(B), n_frames,
+                                                                                        cep_clip_stride);
+    mmla_count_launch("stem_delta_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }

@@ -133,6 +133,29 @@ class Model:
                                         labels.data_ptr(), _lib.stream_ptr(torch)), "mmla_net_forward")
         return prob, labels
 
+    def predict_device_cepstra(self, cep):
+        """Speaker net, TF32 mode: ``cep`` float32 CUDA [B, T, 16] — the MFCC-13 rows of
+        ``mfcc_batch(pcm, row_stride=16)`` (T = psf frame count <= 256).  Delta, delta-delta and the
+        zero rows up to 256 are built inside the stem kernel; returns what ``predict_device`` returns
+        on ``speaker_features_batch(pcm)``."""
+        torch, lib = self._torch, self._lib
+        if cep.dim() != 3 or cep.shape[2] != 16 or cep.dtype != torch.float32 or not cep.is_contiguous():
+            raise ValueError("cepstra must be a contiguous float32 tensor [B, T, 16]")
+        B, T = cep.shape[0], cep.shape[1]
+        need = lib.mmla_net_workspace_bytes(self._handle, B)
+        key = int(torch.cuda.current_stream().cuda_stream)
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need or ws.device != cep.device:
+            ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=cep.device)
+        prob = torch.empty((B, self.spec.n_classes), dtype=torch.float32, device=cep.device)
+        labels = torch.empty((B,), dtype=torch.int32, device=cep.device)
+        _lib.check(lib.mmla_net_forward_cepstra(self._handle, cep.data_ptr(), T * 16, T, B, ws.data_ptr(), ws.numel(),
+                                                prob.data_ptr(), labels.data_ptr(), _lib.stream_ptr(torch)),
+                   "mmla_net_forward_cepstra")
+        return prob, labels
+
     def predict(self, x, batch_size=None, verbose=0):
         """Keras-style ``model.predict``: accepts numpy (any float dtype / uint8), returns numpy
         float32 probabilities.  Callers then do ``np.argmax(prob, axis=1)`` as in the reference."""

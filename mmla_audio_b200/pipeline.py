@@ -18,7 +18,7 @@ from . import _lib, tally
 from .models import Model
 from .overlap_features_generator import OverlapFeaturesGenerator
 from .params import (MfccConfig, OVERLAP_CLIP_SAMPLES, SILENT_MIN_SAMPLES, SPEAKER_FRAMES)
-from .speaker_identification import speaker_features_batch, whole_file_chunks, _to_device_pcm
+from .speaker_identification import mfcc_batch, speaker_features_batch, whole_file_chunks, _to_device_pcm
 
 
 def segmentation_windows(n_samples: int, win: int, step: int) -> int:
@@ -63,13 +63,22 @@ class SpeakerPipeline:
         self._side = None
 
     def _run_slice(self, torch, pcm_dev, slot: int):
-        B = pcm_dev.shape[0]
-        # TF32 mode: features go straight into the channel-padded [B,256,40] layout the tcgen05 stem reads
-        width = 40 if (self.model.precision == "tf32" and self.cfg.numcep == 13) else 3 * self.cfg.numcep
+        B, L = pcm_dev.shape
+        T = self.cfg.num_frames(L)
+        if self.model.precision == "tf32" and self.cfg.numcep == 13 and T <= SPEAKER_FRAMES:
+            # label pipeline: MFCC-13 rows only; delta / delta-delta / padding happen inside the classifier's stem
+            # kernel, so the [B,256,39] feature tensor never exists in HBM
+            cep = self._feat.get(slot)
+            if cep is None or tuple(cep.shape) != (B, T, 16) or cep.device != pcm_dev.device:
+                cep = self._feat[slot] = torch.empty((B, T, 16), dtype=torch.float32, device=pcm_dev.device)
+            mfcc_batch(pcm_dev, self.cfg, out=cep, row_stride=16)
+            prob, labels = self.model.predict_device_cepstra(cep)
+            return labels, prob
+        width = 3 * self.cfg.numcep
         feat = self._feat.get(slot)
-        if feat is None or feat.shape[0] != B or feat.shape[2] != width or feat.device != pcm_dev.device:
+        if feat is None or tuple(feat.shape) != (B, SPEAKER_FRAMES, width) or feat.device != pcm_dev.device:
             feat = self._feat[slot] = torch.empty((B, SPEAKER_FRAMES, width), dtype=torch.float32, device=pcm_dev.device)
-        speaker_features_batch(pcm_dev, self.cfg, out=feat, row_stride=width)
+        speaker_features_batch(pcm_dev, self.cfg, out=feat)
         prob, labels = self.model.predict_device(feat)
         return labels, prob
 

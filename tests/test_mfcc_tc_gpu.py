@@ -188,3 +188,28 @@ def test_row_stride_40_layout_and_pad40_classifier_input(cuda):
     p40, l40 = model.predict_device(wide)
     p39, l39 = model.predict_device(dense)
     assert torch.equal(p40, p39) and torch.equal(l40, l39)
+
+
+@pytest.mark.parametrize("clip_len", [24000, 40000, 40960, 4000, 8800])
+def test_classifier_from_cepstra_equals_classifier_from_features(cuda, clip_len):
+    """mmla_net_forward_cepstra (delta / delta-delta / zero rows built inside the stem kernel from the MFCC-13 rows)
+    must give what mmla_net_forward gives on the materialised [B,256,39] features, and both must match the oracle
+    features -> torch-CPU classifier within the TF32 bar of test_nets_gpu.py."""
+    import torch
+    from mmla_audio_b200 import models, speaker_identification as si, weights as W
+    from oracle import nets as onets
+    pcm = synth.synth_clips(370, 5, clip_len)
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 4321)
+    model = models.Model(spec, w, precision="tf32")
+    cep = si.mfcc_batch(pcm, row_stride=16)
+    assert cep.shape == (5, psf.num_frames(clip_len), 16) and not cep[:, :, 13:].any()
+    names = _launch_names(lambda: model.predict_device_cepstra(cep))
+    assert names[0] == "stem_delta_fused_kernel" and "mfcc_finish_kernel" not in names
+    p_cep, l_cep = model.predict_device_cepstra(cep)
+    p_feat, l_feat = model.predict_device(si.speaker_features_batch(pcm))
+    assert torch.allclose(p_cep, p_feat, rtol=0, atol=2e-6), float((p_cep - p_feat).abs().max())
+    assert torch.equal(l_cep, l_feat)
+    ref_feat = np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(5)]).astype(np.float32)
+    ref = onets.speaker_forward(ref_feat, w, spec)
+    assert np.abs(p_cep.cpu().numpy() - ref).max() <= 5e-3
