@@ -127,3 +127,27 @@ def test_config2_speaker_batch_labels_bit_exact_on_clear_margins(cuda):
             assert (got[clear] == ref.argmax(1)[clear]).all()
         counts = tally.device_counts(labels, 10).cpu().numpy()
         np.testing.assert_array_equal(counts[:10], np.bincount(got, minlength=10))
+
+
+def test_host_pipeline_sync_and_pipelined(cuda):
+    """run_host / submit_host (pinned host PCM in, labels + tallies out; uploads overlap compute, several
+    batches in flight) give exactly what the device-resident path gives, batch after batch."""
+    import torch
+    from mmla_audio_b200 import models, tally, weights as W
+    from mmla_audio_b200 import synth as dsynth
+    from mmla_audio_b200.pipeline import SpeakerPipeline
+    spec = W.speaker_spec(10, "sigmoid")
+    pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321), precision="tf32"))
+    batches = [dsynth.synth_clips(1000 + 300 * i, 300, 24000) for i in range(4)]
+    want = []
+    for b in batches:
+        labels, _ = pipe.run_device(b)
+        want.append((labels.cpu().numpy(), tally.device_counts(labels, 10).cpu().numpy()))
+    hosts = [b.cpu().pin_memory() for b in batches]
+    lab, cnt = pipe.run_host(hosts[0], 10, n_chunks=3)
+    assert np.array_equal(lab, want[0][0]) and np.array_equal(cnt, want[0][1]) and cnt.sum() == 300
+    pending = [pipe.submit_host(h, 10, n_chunks=2, depth=3) for h in hosts[:3]]      # three batches in flight
+    pending.append(pipe.submit_host(hosts[3], 10, n_chunks=2, depth=3))              # reuses the first slot: waits for it
+    for i in (1, 2, 3):
+        lab, cnt = pending[i].result()
+        assert np.array_equal(lab, want[i][0]) and np.array_equal(cnt, want[i][1])
