@@ -58,6 +58,9 @@ int mmla_trace_end(char* names_host, int64_t names_bytes, float* ms_host, int32_
  *   dev_buffer  receives the raw stage-1 / stage-2 accumulators, per 64-frame tile 2 x 128 x 256 float32;
  *   dev_stamps  receives clock64 stamps of CTA 0's warp roles, 64 tiles x 32 int64 slots. */
 void mmla_debug_mfcc_tc_dump(float* dev_buffer, long long* dev_stamps);
+/* Diagnostics of the fused ResNet-stage kernel: dev_stamps (DEVICE pointer, 3 x 64 int64, NULL = off) receives a
+ * clock64 timeline of the warp roles of CTA `cta` of each of the three stage launches (row = stage). */
+void mmla_debug_resstage_stamps(long long* dev_stamps, int32_t cta);
 
 /* ------------------------------------------------------------------------------------------
  * Speaker-ID features.

@@ -372,6 +372,7 @@ struct MmlaNet {
     int seq_len = 0, feat = 0;
     long long per_clip_floats = 0;        // workspace floats per clip
     int micro = 0;                        // clips per micro-batch
+    bool fuse_stages = true;              // speaker, TF32: one launch per ResNet stage (MMLA_NET_FUSE_STAGES=0: per unit)
 };
 
 // conv_tc.cu
@@ -383,6 +384,9 @@ int mmla_launch_stem_fused(const float* x, const float* wg, const float* bias, f
 int mmla_launch_stem_from_cepstra(const float* cep, long long cep_clip_stride, int n_frames, const float* wg, const float* bias,
                                   float* y, long long B, cudaStream_t st);
 // resunit_fused.cu
+int mmla_launch_resstage_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* const (*p)[8],
+                               const float* ws, const float* bs, const float* fin_scale, const float* fin_shift,
+                               float* pooled, cudaStream_t st);
 int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* bn1_scale,
                               const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                               const float* bn2_shift, const float* w2, const float* b2, const float* ws, const float* bs,
@@ -617,6 +621,7 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
         const int v = atoi(e);
         if (v > 0) net->micro = v;
     }
+    if (const char* e = getenv("MMLA_NET_FUSE_STAGES")) net->fuse_stages = atoi(e) != 0;
     *out_net = net;
     return MMLA_OK;
 }
@@ -689,6 +694,7 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         int H = net->in_h, W = net->in_w;
         int cur = 0;
         int rc;
+        bool seq_done = false;
         if (from_cep) {
             rc = mmla_launch_stem_from_cepstra(static_cast<const float*>(xin), cep_clip_stride, cep_frames, net->stem_pad.k_tc,
                                                net->stem_pad.b, buf[cur], B, st);                     // stem_fused.cu
@@ -709,11 +715,36 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         }
         if (rc) return rc;
         const int act_kind = ov ? ACT_ELU : ACT_RELU;
-        for (const BlockW& blk : net->blocks) {
+        for (size_t bi = 0; bi < net->blocks.size(); ++bi) {
+            const BlockW& blk = net->blocks[bi];
             float* X = buf[cur];
             float* A = buf[(cur + 1) % 3];
             float* Bf = buf[(cur + 2) % 3];
-            if (tc && !ov && blk.conv1.k_tc && blk.conv2.k_tc && (!blk.pool || blk.shortcut.k_tc)) {
+            auto fusable = [&](const BlockW& k) { return k.conv1.k_tc && k.conv2.k_tc && (!k.pool || k.shortcut.k_tc); };
+            if (tc && !ov && net->fuse_stages && blk.pool && bi + 2 < net->blocks.size() && fusable(blk) &&
+                fusable(net->blocks[bi + 1]) && fusable(net->blocks[bi + 2]) && !net->blocks[bi + 1].pool &&
+                !net->blocks[bi + 2].pool && net->blocks[bi + 1].conv1.cin == blk.conv1.cout &&
+                net->blocks[bi + 2].conv1.cin == blk.conv1.cout) {
+                // a whole ResNet stage (pooled unit + two plain units) in ONE launch: the activations between the
+                // units stay in shared memory (resunit_fused.cu, stage mode)
+                const int Wo = same_out(W, 2);
+                const float* prm[3][8];
+                for (int u = 0; u < 3; ++u) {
+                    const BlockW& k = net->blocks[bi + u];
+                    prm[u][0] = k.bn1.scale; prm[u][1] = k.bn1.shift; prm[u][2] = k.conv1.k_tc; prm[u][3] = k.conv1.b;
+                    prm[u][4] = k.bn2.scale; prm[u][5] = k.bn2.shift; prm[u][6] = k.conv2.k_tc; prm[u][7] = k.conv2.b;
+                }
+                // the last stage also applies the net's tail (BN -> ReLU -> AveragePooling1D(4)) and writes `seq` directly
+                const bool tail = bi + 3 == net->blocks.size() && Wo % 4 == 0 && blk.conv1.cout == 128;
+                if ((rc = mmla_launch_resstage_fused(X, A, B, Wo, blk.conv1.cin, blk.conv1.cout, prm, blk.shortcut.k_tc,
+                                                     blk.shortcut.b, tail ? net->final_bn.scale : nullptr,
+                                                     tail ? net->final_bn.shift : nullptr, tail ? seq : nullptr, st)))
+                    return rc;
+                seq_done = tail;
+                W = Wo;
+                cur = (cur + 1) % 3;
+                bi += 2;
+            } else if (tc && !ov && blk.conv1.k_tc && blk.conv2.k_tc && (!blk.pool || blk.shortcut.k_tc)) {
                 // speaker res_unit, tensor-core mode: ONE fused kernel per unit (resunit_fused.cu) —
                 // pooled units max-pool on load and fold the stride-2 shortcut into the accumulator
                 const int Wo = blk.pool ? same_out(W, 2) : W;
@@ -754,7 +785,9 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
             }
         }
         // sequence features [B,T,128]
-        if (ov) {
+        if (seq_done) {
+            // written by the last fused stage
+        } else if (ov) {
             mean_h_kernel<<<ew_grid(B * W * 128), 256, 0, st>>>(buf[cur], seq, B, H, W, 128);
             mmla_count_launch("mean_h_kernel", st);
         } else {

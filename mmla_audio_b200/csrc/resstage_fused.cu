@@ -1,0 +1,592 @@
+// One whole ResNet STAGE of the speaker classifier in a single launch (sm_100a, TF32 tensor-core mode):
+//
+//   y0 = Conv1D_k1_s2(x) + Conv_k3( ReLU(BN2( Conv_k3( ReLU(BN1( MaxPool1D_2(x) )) ) )) )        pooled unit
+//   y1 = y0 + Conv_k3( ReLU(BN2'( Conv_k3( ReLU(BN1'(y0)) ) )) )                                 plain unit
+//   y2 = y1 + Conv_k3( ReLU(BN2''( Conv_k3( ReLU(BN1''(y1)) ) )) )                               plain unit
+//
+// — three consecutive `res_unit(x, filters, pool)` calls of SpeakerIdentification/scripts/
+// speaker_identification.py:168-190, as the model builder stacks them (:205-216).
+//
+// Why a stage and not a unit (resunit_fused.cu): measured on B200, the per-unit kernel is bound by streaming
+// its conv weights from L2 — every 128-row tile pulls the whole K x C weight stream through a small TMA ring,
+// so each weight byte feeds only 128 rows of MMA (C = 128: 393 KB of weights per 64 KB tile; 1024 tiles x 3
+// units = 1.3 GB of L2 -> SM traffic per stage, ~110 us at the chip's L2 throughput before any math).  This
+// kernel changes the two ratios that matter:
+//   * a CTA owns TILES (2 or 4) 128-row tiles and every weight chunk that comes through the ring feeds the
+//     MMAs of all of them before the slot is released: L2 -> SM weight traffic / TILES;
+//   * a tile is G = 128/T WHOLE clips (rows interleaved time-major, row = t*G + g, so a filter tap is a uniform
+//     shift of G rows and 'same' padding is G zero halo rows), hence nothing a later unit needs lives in another
+//     tile: the three units run back to back on the tile and the activations between them never touch HBM —
+//     x in once, y out once per stage instead of per unit.
+//
+// The residual needs no buffer: conv2's TMEM accumulator is simply never cleared.  It starts as the shortcut
+// GEMM (raw x[2t] x Ws, pooled unit), every conv2 accumulates on top, and the biases are added on read:
+//      y_u = acc2 + (bs + b2_0 + .. + b2_u).
+// Epilogue 2 of unit u therefore only has to produce the next unit's operand ReLU(BN1'(y_u)) -> TF32, exactly
+// like epilogue 1 does for conv2; the last one stages y through shared memory for coalesced 128-bit stores.
+//
+// Operand scheme as in resunit_fused.cu: UMMA K-major no-swizzle slabs [channel quad][row][16 B], one buffer
+// per tile, reused for every operand of the stage (conv MMAs have retired before an epilogue rewrites it).
+// Warps 0..7 load / transform / run the epilogues, warp 8 streams weights (TMA bulk copies into an mbarrier
+// ring), warp 9 issues tcgen05.mma (warp-uniform loop, one elected lane, descriptors in uniform registers).
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int kRtotS = 137;                // rows per slab: 128 + 2*G halo (G <= 4), == 1 mod 8 (bank-friendly)
+constexpr int kEpiS = 256;
+constexpr int kThreadsS = kEpiS + 64;
+constexpr int kUnitsS = 3;
+
+struct StageUnit {
+    const float* bn1_scale; const float* bn1_shift;
+    const float* bn2_scale; const float* bn2_shift;
+    const float* w1; const float* w2;      // conv_tc-arranged K-slab streams ([K/4][C][4])
+    const float* b1; const float* b2;
+};
+
+struct StageArgs {
+    const float* x;                        // [B][2T][CIN]
+    float* y;                              // [B][T][C]
+    StageUnit u[kUnitsS];
+    const float* ws; const float* bs;      // stride-2 1x1 shortcut of the pooled unit
+    // optional tail (last stage of the net): instead of y, write AveragePooling1D(4)(ReLU(BN(y))) -> pooled [B][T/4][C]
+    const float* fin_scale; const float* fin_shift;
+    float* pooled;
+    int B, T, G;                           // T = OUTPUT time steps
+    long long* stamps;                     // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
+    int stamp_cta;
+};
+
+template <int CIN, int C>
+struct StageCfg {
+    static constexpr int kTiles = C == 64 ? 4 : 2;             // 128-row tiles per CTA
+    static constexpr int kChunkK = 32;                         // K per ring chunk
+    static constexpr int kStages = C == 32 ? 4 : (C == 64 ? 8 : 3);
+    static constexpr int kMinCtas = C == 32 ? 3 : 1;
+    static constexpr int kChunkBytes = kChunkK * C * 4;
+    // raw x[2t] of ONE tile (shortcut GEMM operand): slabs of 129 rows — with 128, the loader's lanes (which run over
+    // channel quads for coalesced global loads) would all hit the same banks (16-way conflict, measured 4k cycles/tile)
+    static constexpr int kA0Rows = 129;
+    static constexpr int kA0Bytes = ((CIN / 4) * kA0Rows * 16 + 127) / 128 * 128;
+    static constexpr int kExtra = kA0Bytes / kChunkBytes;      // ring stages that open up once the shortcut is done
+    static constexpr int kStagesTot = kStages + kExtra;
+    static constexpr int kSlabBytes = (C / 4) * kRtotS * 16;
+    static constexpr int kStageTileBytes = 128 * (C + 4) * 4;  // output staging, rows C + 4 floats apart
+    static constexpr int kTileBytes = ((kSlabBytes > kStageTileBytes ? kSlabBytes : kStageTileBytes) + 127) / 128 * 128;
+};
+
+template <int CIN, int C>
+struct StageSmem {
+    using Cfg = StageCfg<CIN, C>;
+    alignas(128) unsigned char ab[Cfg::kTiles][Cfg::kTileBytes];   // per tile: the current MMA A operand / output staging
+    // weight ring; its last kExtra stages double as `a0`, the shortcut GEMM's operand (raw x[2t] of one tile), and
+    // join the ring when the last shortcut MMA has retired (short_done)
+    alignas(128) unsigned char ring[Cfg::kStages * Cfg::kChunkBytes + Cfg::kA0Bytes];
+    // per unit: [0] BN2 scale, [1] BN2 shift + b1*scale  (epilogue 1: ReLU(BN2(acc1 + b1)) = ReLU(acc1*[0] + [1]));
+    //           [2] next BN1 scale, [3] next BN1 shift + run_u*scale, run_u = bs + b2_0 + .. + b2_u  (epilogue 2);
+    //           [4] run_u  (y_u = acc2 + run_u, used by the final store)
+    alignas(16) float prm[kUnitsS][5][C];
+    alignas(8) uint64_t full[Cfg::kStagesTot];
+    alignas(8) uint64_t empty[Cfg::kStagesTot];
+    alignas(8) uint64_t a0_ready, a0_free; // shortcut operand of tile j written / its MMAs retired
+    alignas(8) uint64_t short_done;        // every shortcut MMA retired: a0's bytes become ring stages
+    alignas(8) uint64_t a_ready[2];        // operand buffers written   (epilogue -> MMA): conv1, conv2
+    alignas(8) uint64_t tfull[2];          // accumulators complete     (MMA -> epilogue): conv1, conv2
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t rs_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void rs_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void rs_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void rs_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint64_t rs_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ bool rs_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void rs_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int CIN, int C>
+__global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstage_fused_kernel(const __grid_constant__ StageArgs a) {
+    using Cfg = StageCfg<CIN, C>;
+    using Smem = StageSmem<CIN, C>;
+    constexpr int kTiles = Cfg::kTiles;
+    constexpr int kQuads = C / 4;
+    constexpr int kQuadsIn = CIN / 4;
+    constexpr int kChunkK = Cfg::kChunkK;
+    constexpr int kStages = Cfg::kStages;          // ring stages available from the start
+    constexpr int kStagesTot = Cfg::kStagesTot;    // ... once the shortcut operand buffer has been released
+    constexpr int kChunksS = CIN / kChunkK;                      // shortcut: K = CIN
+    constexpr int kChunks1 = 3 * CIN / kChunkK;                  // conv1 of the pooled unit: K = 3*CIN
+    constexpr int kChunks2 = 3 * C / kChunkK;                    // every other conv: K = 3*C
+    static_assert(kChunksS >= 1 && kChunksS < kStages, "the shortcut weights stay in the ring while all tiles use them");
+    constexpr uint32_t kChunkBytes = Cfg::kChunkBytes;
+    constexpr int kCols = kTiles * 2 * C;                        // per tile: conv1 | running-y accumulator
+    static_assert(kCols <= 512 && (kCols & (kCols - 1)) == 0 && kCols >= 32, "TMEM allocation");
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(C >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);
+    extern __shared__ unsigned char smem_dyn[];
+    // offset applied to the __shared__ array itself so accesses stay LDS/STS (an integer round-trip makes them generic)
+    Smem& s = *reinterpret_cast<Smem*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = a.G, T = a.T;
+    const int clip_base = blockIdx.x * kTiles * G;               // tile j holds clips [clip_base + j*G, +G)
+
+    if (tid == 0) {
+        for (int i = 0; i < kStagesTot; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
+        mbar_init(&s.short_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s.a_ready[i], 1);
+            mbar_init(&s.tfull[i], 1);
+        }
+        mbar_init(&s.a0_ready, 1);
+        mbar_init(&s.a0_free, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)),
+                     "r"(static_cast<uint32_t>(kCols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s.tmem_base;
+    const bool stamping = a.stamps != nullptr && static_cast<int>(blockIdx.x) == a.stamp_cta;
+    auto stamp = [&](int slot) {
+        if (stamping) a.stamps[slot] = clock64();
+    };
+
+    if (warp == 8) {
+        // ================= TMA producer: shortcut, then per unit conv1 and conv2 weight chunks =================
+        if (lane == 0) {
+            int g = 0;
+            // the conv_tc arrangement is a plain sequence of K-slabs ([K/4][C][4]): any multiple-of-4 K
+            // granularity is a contiguous slice of it
+            auto stream = [&](const float* w, int chunks) {
+                for (int ch = 0; ch < chunks; ++ch, ++g) {
+                    const int stg = g % kStagesTot, use = g / kStagesTot;
+                    if (use > 0) rs_wait(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
+                    else if (stg >= kStages) rs_wait(&s.short_done, 0u);
+                    mbar_arrive_expect_tx(&s.full[stg], kChunkBytes);
+                    tma_bulk_g2s(&s.ring[stg * kChunkBytes], w + static_cast<long long>(ch) * (kChunkK * C), kChunkBytes, &s.full[stg]);
+                }
+            };
+            stream(a.ws, kChunksS);
+#pragma unroll 1
+            for (int u = 0; u < kUnitsS; ++u) {
+                stream(a.u[u].w1, u == 0 ? kChunks1 : kChunks2);
+                stream(a.u[u].w2, kChunks2);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        if (lane == 0) stamp(0);
+        const uint64_t dA_main = rs_desc(smem_u32(&s.ab[0][0]), kRtotS * 16, 128);
+        const uint64_t dA_short = rs_desc(smem_u32(&s.ring[kStages * kChunkBytes]), Cfg::kA0Rows * 16, 128);
+        const uint64_t dB0 = rs_desc(smem_u32(&s.ring[0]), C * 16, 128);
+        constexpr uint32_t kStageUnits = Cfg::kChunkBytes / 16;      // descriptor address units per ring stage
+        constexpr uint32_t kTileUnits = Cfg::kTileBytes / 16;        // ... per tile operand buffer
+        // ---- shortcut: raw x[2t] x Ws initialises the running-y accumulator of each tile as its operand arrives;
+        //      the Ws chunks (ring slots 0..kChunksS-1) are released after the last tile has used them ----
+#pragma unroll 1
+        for (int j = 0; j < kTiles; ++j) {
+            rs_wait(&s.a0_ready, static_cast<uint32_t>(j & 1));
+            if (j == 0)
+                for (int c = 0; c < kChunksS; ++c) rs_wait(&s.full[c], 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (rs_elect_one()) {
+                const uint32_t dcol = tmem + static_cast<uint32_t>(j * 2 * C + C);
+#pragma unroll
+                for (int c = 0; c < kChunksS; ++c) {
+#pragma unroll
+                    for (int kk = 0; kk < kChunkK / 8; ++kk) {
+                        const uint64_t ad = dA_short + static_cast<uint64_t>((c * (kChunkK / 4) + 2 * kk) * Cfg::kA0Rows);
+                        const uint64_t bd = dB0 + static_cast<uint64_t>(c * kStageUnits + kk * 2 * C);
+                        const uint32_t acc = (c != 0 || kk != 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol),
+                            "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                            : "memory");
+                    }
+                }
+                rs_commit(&s.a0_free);
+                if (j == kTiles - 1) {
+                    for (int c = 0; c < kChunksS; ++c) rs_commit(&s.empty[c]);
+                    rs_commit(&s.short_done);
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) stamp(1);
+        // Ring position kept as counters and descriptors advanced by adds: everything between the last MMA of a chunk
+        // and the first MMA of the next one is a bubble the tensor pipe sees once its short queue (~4 MMAs) has drained.
+        int stg = kChunksS;                                          // kChunksS < kStagesTot: no wrap yet
+        uint32_t par = 0;
+        uint64_t bd0 = dB0 + static_cast<uint64_t>(kChunksS * kStageUnits);
+        // one K-chunk of MMAs for EVERY tile: A slabs start at descriptor `ad0` (slab + tap shift already applied);
+        // accumulates into TMEM column block `dcol` of each tile
+        auto chunk_mma = [&](uint64_t ad0, uint32_t dcol, bool first) {
+            rs_wait(&s.full[stg], par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (rs_elect_one()) {
+#pragma unroll
+                for (int j = 0; j < kTiles; ++j) {
+#pragma unroll
+                    for (int kk = 0; kk < kChunkK / 8; ++kk) {
+                        const uint64_t ad = ad0 + static_cast<uint64_t>(j * kTileUnits + 2 * kk * kRtotS);
+                        const uint64_t bd = bd0 + static_cast<uint64_t>(kk * 2 * C);
+                        const uint32_t acc = (!first || kk != 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + dcol + j * 2 * C),
+                            "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                            : "memory");
+                    }
+                }
+                rs_commit(&s.empty[stg]);
+            }
+            ++stg;
+            bd0 += kStageUnits;
+            if (stg == kStagesTot) {
+                stg = 0;
+                par ^= 1u;
+                bd0 = dB0;
+            }
+        };
+        // a k=3 convolution over `cin` input channels: K index = tap*cin + channel; tap j reads rows shifted by j*G
+        // (halo rows = zero padding)
+        auto conv = [&](int cin, uint32_t dcol, bool clear) {
+            uint64_t tap0 = dA_main;
+            for (int tap = 0; tap < 3; ++tap, tap0 += static_cast<uint64_t>(G)) {
+                uint64_t ad = tap0;
+                for (int c0 = 0; c0 < cin; c0 += kChunkK, ad += static_cast<uint64_t>((kChunkK / 4) * kRtotS))
+                    chunk_mma(ad, dcol, clear && tap == 0 && c0 == 0);
+            }
+        };
+#pragma unroll 1
+        for (int u = 0; u < kUnitsS; ++u) {
+            const uint32_t upar = static_cast<uint32_t>(u & 1);
+            rs_wait(&s.a_ready[0], upar);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) stamp(2 + 4 * u);
+            conv(u == 0 ? CIN : C, 0u, true);
+            if (rs_elect_one()) rs_commit(&s.tfull[0]);
+            __syncwarp();
+            if (lane == 0) stamp(3 + 4 * u);
+            // conv2 accumulates on top of the shortcut (u = 0) / of y_{u-1}: that IS the residual add
+            rs_wait(&s.a_ready[1], upar);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) stamp(4 + 4 * u);
+            conv(C, static_cast<uint32_t>(C), false);
+            if (rs_elect_one()) rs_commit(&s.tfull[1]);
+            __syncwarp();
+            if (lane == 0) stamp(5 + 4 * u);
+        }
+    } else {
+        // ================= warps 0..7: load/transform, epilogues =================
+        constexpr int kRowsPerPass = kEpiS / kQuadsIn;            // rows covered by 256 threads at once
+        constexpr int kIters = 128 / kRowsPerPass;
+        const int qd = tid % kQuadsIn, rsub = tid / kQuadsIn;
+        // x loads: lanes run over channel quads (coalesced).  With one CTA per SM the registers are there to put the
+        // loads of EVERY tile in flight at once (one exposed HBM latency per CTA instead of one per tile); the C = 32
+        // stage (3 CTAs/SM, 64 registers) fetches tile j+1 while tile j's shortcut MMAs run.
+        constexpr int kPre = Cfg::kMinCtas == 1 ? kTiles : 1;
+        float4 v[kPre][kIters], v2[kPre][kIters];
+#define RS_LOAD_TILE(J)                                                                                                  \
+    {                                                                                                                    \
+        const int clip0_ = clip_base + (J) * G;                                                                          \
+        _Pragma("unroll") for (int i = 0; i < kIters; ++i) {                                                             \
+            const int r = rsub + i * kRowsPerPass;                                                                       \
+            const int t = r / G, gg = r - t * G; /* row = t*G + g */                                                     \
+            v[(J) % kPre][i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                          \
+            v2[(J) % kPre][i] = v[(J) % kPre][i];                                                                        \
+            if (clip0_ + gg < a.B) {                                                                                     \
+                const float* src = a.x + (static_cast<long long>(clip0_ + gg) * (2 * T) + 2 * t) * CIN + 4 * qd;         \
+                v[(J) % kPre][i] = *reinterpret_cast<const float4*>(src);                                                \
+                v2[(J) % kPre][i] = *reinterpret_cast<const float4*>(src + CIN);                                         \
+            }                                                                                                            \
+        }                                                                                                                \
+    }
+        if (tid == 0) stamp(16);
+#pragma unroll
+        for (int j = 0; j < kPre; ++j) RS_LOAD_TILE(j)
+        const float4 sc1 = *reinterpret_cast<const float4*>(a.u[0].bn1_scale + 4 * qd);
+        const float4 sh1 = *reinterpret_cast<const float4*>(a.u[0].bn1_shift + 4 * qd);
+        // Parameters: all global loads first, then the shared stores.  (Interleaved, every load has to wait for the
+        // store before it — the pointers are generic, so the compiler must assume they may alias shared memory —
+        // and ~17 serialised L2 round trips cost 10k cycles at the head of every CTA.)
+        for (int i = tid; i < C; i += kEpiS) {
+            float pb1[kUnitsS], pb2[kUnitsS], ps1[kUnitsS], ph1[kUnitsS], ps2[kUnitsS], ph2[kUnitsS];
+            const float pbs = __ldg(a.bs + i);
+#pragma unroll
+            for (int u = 0; u < kUnitsS; ++u) {
+                pb1[u] = __ldg(a.u[u].b1 + i); pb2[u] = __ldg(a.u[u].b2 + i);
+                ps1[u] = __ldg(a.u[u].bn1_scale + i); ph1[u] = __ldg(a.u[u].bn1_shift + i);
+                ps2[u] = __ldg(a.u[u].bn2_scale + i); ph2[u] = __ldg(a.u[u].bn2_shift + i);
+            }
+            float run = pbs;
+#pragma unroll
+            for (int u = 0; u < kUnitsS; ++u) {
+                run += pb2[u];
+                const float scn = u + 1 < kUnitsS ? ps1[u + 1 < kUnitsS ? u + 1 : u] : 0.f;
+                const float shn = u + 1 < kUnitsS ? ph1[u + 1 < kUnitsS ? u + 1 : u] : 0.f;
+                s.prm[u][0][i] = ps2[u];
+                s.prm[u][1][i] = fmaf(pb1[u], ps2[u], ph2[u]);
+                s.prm[u][2][i] = scn;
+                s.prm[u][3][i] = fmaf(run, scn, shn);
+                s.prm[u][4][i] = run;                             // y_u = acc2 + bs + b2_0 + .. + b2_u
+            }
+        }
+        // zero the halo rows (rows [0,G) and [G+128, G+128+G)) of every tile; the epilogues never touch them
+        for (int i = tid; i < kTiles * kQuads * 2 * G; i += kEpiS) {
+            const int j = i / (kQuads * 2 * G), rem = i - j * (kQuads * 2 * G);
+            const int q = rem / (2 * G), h = rem - q * (2 * G);
+            const int row = h < G ? h : 128 + h;
+            *reinterpret_cast<uint4*>(&s.ab[j][0] + (q * kRtotS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // ---- per tile: raw x[2t] -> shortcut operand; ReLU(BN1(max(x[2t], x[2t+1]))) -> conv1 operand ----
+        unsigned char* a0 = &s.ring[kStages * kChunkBytes];
+#pragma unroll
+        for (int j = 0; j < kTiles; ++j) {
+            if (j > 0) rs_wait(&s.a0_free, static_cast<uint32_t>((j - 1) & 1));   // shortcut MMAs of tile j-1 retired
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+                const int r = rsub + i * kRowsPerPass;
+                float4 p = v[j % kPre][i];
+                const float4 p2 = v2[j % kPre][i];
+                *reinterpret_cast<uint4*>(a0 + (qd * Cfg::kA0Rows + r) * 16) =
+                    make_uint4(rs_tf32(p.x), rs_tf32(p.y), rs_tf32(p.z), rs_tf32(p.w));
+                p.x = fmaxf(p.x, p2.x); p.y = fmaxf(p.y, p2.y);
+                p.z = fmaxf(p.z, p2.z); p.w = fmaxf(p.w, p2.w);
+                *reinterpret_cast<uint4*>(&s.ab[j][0] + (qd * kRtotS + G + r) * 16) =
+                    make_uint4(rs_tf32(fmaxf(fmaf(p.x, sc1.x, sh1.x), 0.f)), rs_tf32(fmaxf(fmaf(p.y, sc1.y, sh1.y), 0.f)),
+                               rs_tf32(fmaxf(fmaf(p.z, sc1.z, sh1.z), 0.f)), rs_tf32(fmaxf(fmaf(p.w, sc1.w, sh1.w), 0.f)));
+            }
+            if (kPre == 1 && j + 1 < kTiles) RS_LOAD_TILE(j + 1)  // latency overlaps the barrier round trip below
+            fence_proxy_async_smem();
+            rs_epi_sync();
+            if (tid == 0) rs_arrive(&s.a0_ready);
+            if (tid == 0) stamp(32 + j);
+        }
+        if (tid == 0) rs_arrive(&s.a_ready[0]);
+
+        // TMEM lane = tile row; warps 0..3 take the lower half of the columns, warps 4..7 the upper
+        const int row = 32 * (warp & 3) + lane;
+        constexpr int kColsPerWarp = C / 2;
+        const int cbase = (warp >> 2) * kColsPerWarp;
+        const uint32_t trow = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
+        // this warp's kColsPerWarp accumulator columns of one tile: every tcgen05.ld in flight before the single wait
+        auto ld_cols = [&](uint32_t taddr, uint32_t (&z)[kColsPerWarp]) {
+#pragma unroll
+            for (int c0 = 0; c0 < kColsPerWarp; c0 += 16)
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15}, [%16];\n"
+                    : "=r"(z[c0 + 0]), "=r"(z[c0 + 1]), "=r"(z[c0 + 2]), "=r"(z[c0 + 3]), "=r"(z[c0 + 4]), "=r"(z[c0 + 5]),
+                      "=r"(z[c0 + 6]), "=r"(z[c0 + 7]), "=r"(z[c0 + 8]), "=r"(z[c0 + 9]), "=r"(z[c0 + 10]), "=r"(z[c0 + 11]),
+                      "=r"(z[c0 + 12]), "=r"(z[c0 + 13]), "=r"(z[c0 + 14]), "=r"(z[c0 + 15])
+                    : "r"(taddr + static_cast<uint32_t>(c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        };
+        // accumulator block `dcol` of every tile -> * scale + shift -> ReLU -> TF32 -> that tile's operand buffer
+        auto to_operand = [&](uint32_t dcol, const float* scale, const float* shift) {
+#pragma unroll 1
+            for (int j = 0; j < kTiles; ++j) {
+                uint32_t z[kColsPerWarp];
+                ld_cols(trow + dcol + static_cast<uint32_t>(j * 2 * C + cbase), z);
+#pragma unroll
+                for (int k = 0; k < kColsPerWarp; k += 4) {
+                    const int col = cbase + k;
+                    const float4 sc = *reinterpret_cast<const float4*>(scale + col);
+                    const float4 sh = *reinterpret_cast<const float4*>(shift + col);
+                    const float w0 = fmaxf(fmaf(__uint_as_float(z[k + 0]), sc.x, sh.x), 0.f);
+                    const float w1 = fmaxf(fmaf(__uint_as_float(z[k + 1]), sc.y, sh.y), 0.f);
+                    const float w2 = fmaxf(fmaf(__uint_as_float(z[k + 2]), sc.z, sh.z), 0.f);
+                    const float w3 = fmaxf(fmaf(__uint_as_float(z[k + 3]), sc.w, sh.w), 0.f);
+                    *reinterpret_cast<uint4*>(&s.ab[j][0] + ((col >> 2) * kRtotS + G + row) * 16) =
+                        make_uint4(rs_tf32(w0), rs_tf32(w1), rs_tf32(w2), rs_tf32(w3));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            fence_proxy_async_smem();
+            rs_epi_sync();
+        };
+
+#pragma unroll 1
+        for (int u = 0; u < kUnitsS; ++u) {
+            const uint32_t par = static_cast<uint32_t>(u & 1);
+            // ---- epilogue 1: conv1 accumulator -> +b1 -> BN2 -> ReLU -> TF32 -> operand buffer ----
+            rs_wait(&s.tfull[0], par);                            // conv1's MMAs (readers of the buffers) have retired
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) stamp(18 + 4 * u);
+            to_operand(0u, &s.prm[u][0][0], &s.prm[u][1][0]);
+            if (tid == 0) rs_arrive(&s.a_ready[1]);
+            if (tid == 0) stamp(19 + 4 * u);
+            // ---- epilogue 2: y_u = running accumulator + running bias; next unit's operand = ReLU(BN1'(y_u)) ----
+            rs_wait(&s.tfull[1], par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) stamp(20 + 4 * u);
+            if (u + 1 < kUnitsS) {
+                to_operand(static_cast<uint32_t>(C), &s.prm[u][2][0], &s.prm[u][3][0]);
+                if (tid == 0) rs_arrive(&s.a_ready[0]);
+                if (tid == 0) stamp(21 + 4 * u);
+            }
+        }
+
+        // ---- last epilogue: y_2 -> staging (operand buffers are dead) -> coalesced 128-bit stores ----
+        constexpr int kStride = C + 4;                            // floats per staged row (conflict-free STS/LDS.128)
+#pragma unroll 1
+        for (int j = 0; j < kTiles; ++j) {
+            float* stg = reinterpret_cast<float*>(&s.ab[j][0]);
+            uint32_t z[kColsPerWarp];
+            ld_cols(trow + static_cast<uint32_t>(j * 2 * C + C + cbase), z);
+#pragma unroll
+            for (int k = 0; k < kColsPerWarp; k += 4) {
+                const int col = cbase + k;
+                const float4 bv = *reinterpret_cast<const float4*>(&s.prm[kUnitsS - 1][4][col]);
+                *reinterpret_cast<float4*>(stg + row * kStride + col) =
+                    make_float4(__uint_as_float(z[k]) + bv.x, __uint_as_float(z[k + 1]) + bv.y, __uint_as_float(z[k + 2]) + bv.z,
+                                __uint_as_float(z[k + 3]) + bv.w);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        fence_proxy_async_smem();                                 // staged rows are read by the bulk-copy engine
+        rs_epi_sync();
+        if (tid == 0) stamp(30);
+        if (a.pooled != nullptr) {
+            // tail of the net folded in: BN -> ReLU -> mean over 4 consecutive time steps, from the staged rows
+            // (row = t*G + g), summed in the order of the stand-alone bn_relu_avgpool4_kernel; y itself is never written
+            const int q = tid % kQuads;                           // constant per thread (kEpiS % kQuads == 0)
+            const float4 fsc = *reinterpret_cast<const float4*>(a.fin_scale + 4 * q);
+            const float4 fsh = *reinterpret_cast<const float4*>(a.fin_shift + 4 * q);
+            const int To = T / 4;
+#pragma unroll 1
+            for (int idx = tid; idx < kTiles * 32 * kQuads; idx += kEpiS) {
+                const int j = idx / (32 * kQuads), pr = (idx / kQuads) % 32;
+                const int to = pr / G, gg = pr - to * G;
+                const int clip = clip_base + j * G + gg;
+                if (clip >= a.B) continue;
+                const float* stg = reinterpret_cast<const float*>(&s.ab[j][0]);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 v = *reinterpret_cast<const float4*>(stg + ((4 * to + k) * G + gg) * kStride + 4 * q);
+                    acc.x += fmaxf(fmaf(v.x, fsc.x, fsh.x), 0.f);
+                    acc.y += fmaxf(fmaf(v.y, fsc.y, fsh.y), 0.f);
+                    acc.z += fmaxf(fmaf(v.z, fsc.z, fsh.z), 0.f);
+                    acc.w += fmaxf(fmaf(v.w, fsc.w, fsh.w), 0.f);
+                }
+                *reinterpret_cast<float4*>(a.pooled + (static_cast<long long>(clip) * To + to) * C + 4 * q) =
+                    make_float4(acc.x * 0.25f, acc.y * 0.25f, acc.z * 0.25f, acc.w * 0.25f);
+            }
+        } else {
+        // one bulk copy per output row (C floats, contiguous in y): asynchronous, so the warps are done once the
+        // copies are issued; they only wait for the shared-memory READS before the CTA (and its smem) goes away
+#pragma unroll
+        for (int i = 0; i < kTiles * 128 / kEpiS; ++i) {
+            const int idx = tid + i * kEpiS;
+            const int j = idx >> 7, r = idx & 127;
+            const int t = r / G, gg = r - t * G;
+            const int clip = clip_base + j * G + gg;
+            if (clip < a.B) {
+                float* dst = a.y + (static_cast<long long>(clip) * T + t) * C;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                             "r"(smem_u32(&s.ab[j][0] + r * kStride * 4)), "r"(static_cast<uint32_t>(C * 4))
+                             : "memory");
+            }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        if (tid == 0) stamp(31);
+#undef RS_LOAD_TILE
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(static_cast<uint32_t>(kCols))
+                     : "memory");
+}
+
+template <int CIN, int C>
+int launch_stage(const StageArgs& a, cudaStream_t st) {
+    static bool attr_set = false;
+    const int smem = static_cast<int>(sizeof(StageSmem<CIN, C>) + 128);
+    static_assert(sizeof(StageSmem<CIN, C>) + 128 <= 227 * 1024, "stage kernel shared memory");
+    static_assert(StageCfg<CIN, C>::kExtra >= 1, "the shortcut operand buffer becomes at least one ring stage");
+    if (!attr_set) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resstage_fused_kernel<CIN, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const long long tiles = (a.B + a.G - 1) / a.G;
+    const unsigned grid = static_cast<unsigned>((tiles + StageCfg<CIN, C>::kTiles - 1) / StageCfg<CIN, C>::kTiles);
+    resstage_fused_kernel<CIN, C><<<grid, kThreadsS, smem, st>>>(a);
+    mmla_count_launch("resstage_fused_kernel", st);
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
+}  // namespace
+
+static long long* g_stage_stamps = nullptr;
+static int g_stage_stamp_cta = 0;
+extern "C" __attribute__((visibility("default"))) void mmla_debug_resstage_stamps(long long* dev_stamps, int32_t cta) {
+    g_stage_stamps = dev_stamps;
+    g_stage_stamp_cta = cta;
+}
+
+// x: [B][2T][Cin], y: [B][T][C] fp32 NHWC (H = 1); T = output steps in {128, 64, 32}.
+// p[u] = {bn1_scale, bn1_shift, w1, b1, bn2_scale, bn2_shift, w2, b2} of unit u (u = 0: the pooled unit);
+// w* are the conv_tc-arranged streams of the k=3 convolutions, ws / bs the stride-2 1x1 shortcut of unit 0.
+// fin_scale / fin_shift / pooled (all or none): the net's tail BN -> ReLU -> AveragePooling1D(4) applied to the stage
+// output, written to pooled [B][T/4][C]; y is then not written (and may be null).
+int mmla_launch_resstage_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* const (*p)[8],
+                               const float* ws, const float* bs, const float* fin_scale, const float* fin_shift,
+                               float* pooled, cudaStream_t st) {
+    MMLA_REQUIRE(T >= 32 && T <= 128 && 128 % T == 0, MMLA_EUNSUP, "resstage_fused: T=%d unsupported", T);
+    MMLA_REQUIRE(B > 0 && B < (1LL << 24), MMLA_EINVAL, "resstage_fused: bad batch");
+    MMLA_REQUIRE(ws && bs, MMLA_EINVAL, "resstage_fused: the first unit of a stage is the pooled one");
+    StageArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.y = y;
+    for (int u = 0; u < kUnitsS; ++u) {
+        a.u[u].bn1_scale = p[u][0]; a.u[u].bn1_shift = p[u][1]; a.u[u].w1 = p[u][2]; a.u[u].b1 = p[u][3];
+        a.u[u].bn2_scale = p[u][4]; a.u[u].bn2_shift = p[u][5]; a.u[u].w2 = p[u][6]; a.u[u].b2 = p[u][7];
+    }
+    a.ws = ws; a.bs = bs;
+    MMLA_REQUIRE(pooled == nullptr || (fin_scale && fin_shift && T % 4 == 0), MMLA_EINVAL, "resstage_fused: bad pooled tail");
+    MMLA_REQUIRE(pooled != nullptr || y != nullptr, MMLA_EINVAL, "resstage_fused: no output");
+    a.fin_scale = fin_scale; a.fin_shift = fin_shift; a.pooled = pooled;
+    a.B = static_cast<int>(B); a.T = T; a.G = 128 / T;
+    if (g_stage_stamps) {                  // one 64-slot row per stage, keyed by C: 32 -> row 0, 64 -> 1, 128 -> 2
+        a.stamps = g_stage_stamps + 64 * (C == 32 ? 0 : (C == 64 ? 1 : 2));
+        a.stamp_cta = g_stage_stamp_cta;
+    }
+    if (Cin == 32 && C == 32) return launch_stage<32, 32>(a, st);
+    if (Cin == 32 && C == 64) return launch_stage<32, 64>(a, st);
+    if (Cin == 64 && C == 128) return launch_stage<64, 128>(a, st);
+    mmla_set_error("resstage_fused: Cin=%d C=%d unsupported", Cin, C);
+    return MMLA_EUNSUP;
+}

@@ -52,16 +52,22 @@ __global__ void __launch_bounds__(128, 1) bench(const Cfg* cfgs, int ncfg, int i
             uint64_t ad, bd;
             if (cf.a_mode == 0) ad = desc(a_base, 128, 256, 0);             // [rowgroup][2 kgroups][8 x 16 B]
             else if (cf.a_mode == 1) ad = desc(a_base, 16, 1024, 2);         // SW128: 8 rows x 128 B atoms
-            else ad = desc(a_base, 128, 160, 0);                             // MN-major, overlapping groups
+            else if (cf.a_mode == 2) ad = desc(a_base, 128, 160, 0);         // MN-major, overlapping groups
+            // "slab" layouts of the conv kernels: [k group][row][16 B], rows 16 B apart (SBO 128), slabs LBO apart;
+            // a_mode 3..8: slab of 137 rows (start +0 / +16 / +64 B), slab of 136 rows (start +0 / +16 / +64 B)
+            else if (cf.a_mode <= 5) ad = desc(a_base + (cf.a_mode == 3 ? 0 : (cf.a_mode == 4 ? 16 : 64)), 137 * 16, 128, 0);
+            else ad = desc(a_base + (cf.a_mode == 6 ? 0 : (cf.a_mode == 7 ? 16 : 64)), 136 * 16, 128, 0);
             if (cf.b_mode == 0) bd = desc(b_base, 128, 256, 0);
-            else bd = desc(b_base, 16, 1024, 2);
+            else if (cf.b_mode == 1) bd = desc(b_base, 16, 1024, 2);
+            else bd = desc(b_base, cf.N * 16, 128, 0);                       // weight slabs [k group][N][16 B]
+            const uint64_t astep = cf.a_mode >= 3 ? 0 : 2;   // slab modes keep their start alignment
             for (int rep = 0; rep < 2; ++rep) {
                 const long long t0 = clock64();
                 if (cf.same_d == 2) {
                     // fully unrolled groups of 16 with compile-time offsets: the pure issue rate
                     for (int i = 0; i < iters; i += 16) {
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) umma(tmem + (u & 7) * 32, ad + (u & 3) * 2, bd, idesc, 1u);
+                        for (int u = 0; u < 16; ++u) umma(tmem + (u & 7) * 32, ad + (u & 3) * astep, bd, idesc, 1u);
                     }
                 } else {
 #pragma unroll 1
@@ -87,14 +93,63 @@ __global__ void __launch_bounds__(128, 1) bench(const Cfg* cfgs, int ncfg, int i
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// Is the ~46-cycle issue floor per issuing thread or global?  `nwarps` warps (lane 0 of each) issue concurrently
+// into their own TMEM columns; reports cycles per MMA as seen by each issuer (same value as 1 warp => per thread).
+__global__ void __launch_bounds__(128, 1) bench_multi(int N, int nwarps, int iters, long long* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    const int w = tid >> 5;
+    if ((tid & 31) == 0 && w < nwarps) {
+        const uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+        const uint64_t ad = desc(smem_u32(smem), 128, 256, 0), bd = desc(smem_u32(smem + 96 * 1024), 128, 256, 0);
+        const uint32_t d0 = tmem + w * 128;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) umma(d0, ad + (u & 3) * 2, bd, idesc, 1u);
+        }
+        const long long t1 = clock64();
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[w])) : "memory");
+        while (!try_wait(&bar[w], 0)) {}
+        const long long t2 = clock64();
+        if (blockIdx.x == 0) {
+            out[w * 2] = t1 - t0;
+            out[w * 2 + 1] = t2 - t0;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 int main() {
     Cfg h[] = {{32, 0, 0, 0}, {32, 1, 0, 0}, {32, 2, 0, 0}, {32, 0, 0, 1}, {32, 0, 0, 2}, {32, 1, 0, 2}, {32, 2, 0, 2}, {16, 0, 0, 2},
-               {64, 0, 0, 2}, {64, 1, 0, 2}, {128, 0, 0, 2}, {128, 1, 0, 2}, {256, 0, 0, 2}, {256, 1, 0, 2}, {256, 1, 1, 2}};
+               {64, 0, 0, 2}, {64, 1, 0, 2}, {128, 0, 0, 2}, {128, 1, 0, 2}, {256, 0, 0, 2}, {256, 1, 0, 2}, {256, 1, 1, 2},
+               {128, 0, 2, 2}, {128, 3, 2, 2}, {128, 4, 2, 2}, {128, 5, 2, 2}, {128, 6, 2, 2}, {128, 7, 2, 2}, {128, 8, 2, 2},
+               {64, 0, 2, 2},  {64, 3, 2, 2},  {64, 4, 2, 2},  {64, 5, 2, 2},  {64, 6, 2, 2},  {64, 7, 2, 2},  {64, 8, 2, 2},
+               {32, 3, 2, 2},  {32, 4, 2, 2},  {32, 6, 2, 2},  {32, 7, 2, 2}};
     const int n = sizeof(h) / sizeof(h[0]);
     Cfg* d;
     long long* o;
     cudaMalloc(&d, sizeof(h));
     cudaMalloc(&o, n * 16);
+    static_assert(sizeof(h) / sizeof(h[0]) <= 64, "");
     cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 512;
@@ -102,12 +157,24 @@ int main() {
         bench<<<grid, 128, 200 * 1024>>>(d, n, iters, o);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-        long long r[64];
+        long long r[128];
         cudaMemcpy(r, o, n * 16, cudaMemcpyDeviceToHost);
         printf("grid %d\n", grid);
         for (int c = 0; c < n; ++c)
             printf("  N=%3d a_mode=%d b_mode=%d same_d=%d : issue %.1f cyc/mma, complete %.1f cyc/mma\n", h[c].N, h[c].a_mode, h[c].b_mode,
                    h[c].same_d, double(r[2 * c]) / iters, double(r[2 * c + 1]) / iters);
     }
+    cudaFuncSetAttribute(bench_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int N : {32, 128})
+        for (int nw : {1, 2, 4}) {
+            bench_multi<<<1, 128, 200 * 1024>>>(N, nw, iters, o);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+            long long r[8];
+            cudaMemcpy(r, o, 64, cudaMemcpyDeviceToHost);
+            printf("multi-issuer N=%d warps=%d:", N, nw);
+            for (int w = 0; w < nw; ++w) printf("  w%d issue %.1f complete %.1f", w, double(r[2 * w]) / iters, double(r[2 * w + 1]) / iters);
+            printf("  (cycles per MMA of that issuer)\n");
+        }
     return 0;
 }

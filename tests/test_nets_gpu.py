@@ -151,3 +151,26 @@ def test_tf32_vs_fp32_large_batch_label_agreement(cuda):
     print("tf32 vs fp32 label agreement on 4096 clips:", agree, "max |dprob|", (p32 - ptc).abs().max().item())
     assert agree >= 0.95
     assert (p32 - ptc).abs().max().item() <= 5e-3
+
+
+def test_fused_stages_match_per_unit_kernels(cuda, monkeypatch):
+    """One launch per ResNet stage (resstage_fused.cu) vs one launch per residual unit (resunit_fused.cu): same TF32
+    algorithm, but the bias is folded into the BN shift and the residual lives in the accumulator, so a few operands
+    round to the neighbouring TF32 value: probabilities agree to 5e-4 (a tenth of the TF32-vs-fp32 bound); ragged batches exercise partially filled tile groups (stage tiles hold 1, 2 and 4 clips, groups 2 or 4
+    tiles)."""
+    from mmla_audio_b200 import models, synth as dsynth, weights as W
+    from mmla_audio_b200 import speaker_identification as si
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 4321)
+    monkeypatch.setenv("MMLA_NET_FUSE_STAGES", "0")
+    per_unit = models.Model(spec, w, precision="tf32")
+    monkeypatch.setenv("MMLA_NET_FUSE_STAGES", "1")
+    staged = models.Model(spec, w, precision="tf32")
+    for n in (1, 7, 37, 300):
+        feat = si.speaker_features_batch(dsynth.synth_clips(5, n, 24000))
+        pu, lu = per_unit.predict_device(feat)
+        ps, ls = staged.predict_device(feat)
+        d = (pu - ps).abs().max().item()
+        print(f"stage-fused vs per-unit, {n} clips: max |dprob| {d:.2e}")
+        assert d <= 5e-4
+        assert (lu == ls).float().mean().item() >= 0.99
