@@ -249,6 +249,8 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     conv_flop = B * (stem + res + xproj)
     if spec.ndim == 1:
         work["resunit_fused_kernel"] = {"bound": "tensor", "per_step": B * res, "what": "the 9 residual units (18 convs + 3 shortcuts)"}
+        work["resstage_fused_kernel"] = {"bound": "tensor", "per_step": B * res,
+                                         "what": "the 3 ResNet stages = 9 residual units (18 convs + 3 shortcuts), TF32"}
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * xproj, "what": "both LSTM input projections"}
 
         work["stem_fused_kernel"] = {"bound": "hbm", "per_step": B * 256 * (40 + 32) * 4,

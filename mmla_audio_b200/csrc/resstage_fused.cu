@@ -76,6 +76,11 @@ struct StageCfg {
     static constexpr int kSlabBytes = (C / 4) * kRtotS * 16;
     static constexpr int kStageTileBytes = 128 * (C + 4) * 4;  // output staging, rows C + 4 floats apart
     static constexpr int kTileBytes = ((kSlabBytes > kStageTileBytes ? kSlabBytes : kStageTileBytes) + 127) / 128 * 128;
+    // With one CTA per SM the raw x tile ([G clips][2T rows][CIN] fp32, contiguous in HBM) is fetched by ONE bulk copy
+    // per tile into that tile's (still empty) operand buffer, all tiles in flight from the first cycle of the CTA.
+    static constexpr bool kTmaX = kMinCtas == 1;
+    static constexpr int kRawTileBytes = 256 * CIN * 4;
+    static_assert(!kTmaX || kRawTileBytes <= kTileBytes, "raw x tile is staged in the operand buffer");
 };
 
 template <int CIN, int C>
@@ -93,12 +98,19 @@ struct StageSmem {
     alignas(8) uint64_t empty[Cfg::kStagesTot];
     alignas(8) uint64_t a0_ready, a0_free; // shortcut operand of tile j written / its MMAs retired
     alignas(8) uint64_t short_done;        // every shortcut MMA retired: a0's bytes become ring stages
+    alignas(8) uint64_t x_full[Cfg::kTiles];   // raw x tile landed (kTmaX)
     alignas(8) uint64_t a_ready[2];        // operand buffers written   (epilogue -> MMA): conv1, conv2
     alignas(8) uint64_t tfull[2];          // accumulators complete     (MMA -> epilogue): conv1, conv2
     uint32_t tmem_base;
 };
 
 __device__ __forceinline__ uint32_t rs_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+// ReLU + round-to-nearest TF32 in one integer add/max (VIADDMNMX): a negative float is a negative int, and for x >= 0
+// adding half a TF32 ulp to the bit pattern rounds the 10-bit mantissa (carry into the exponent included).  The low 13
+// bits are left as they fall: kind::tf32 reads only the upper 19 bits of each operand word.
+__device__ __forceinline__ uint32_t rs_relu_tf32(float x) {
+    return static_cast<uint32_t>(max(static_cast<int>(__float_as_uint(x)) + 0x1000, 0));
+}
 __device__ __forceinline__ void rs_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t i = 0; i < (1u << 24); ++i)
         if (mbar_try_wait(bar, parity)) return;
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
             mbar_init(&s.empty[i], 1);
         }
         mbar_init(&s.short_done, 1);
+        for (int i = 0; i < kTiles; ++i) mbar_init(&s.x_full[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.a_ready[i], 1);
             mbar_init(&s.tfull[i], 1);
@@ -179,6 +192,20 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
     if (warp == 8) {
         // ================= TMA producer: shortcut, then per unit conv1 and conv2 weight chunks =================
         if (lane == 0) {
+            if (Cfg::kTmaX) {
+                const int clip_floats = 2 * T * CIN;
+                for (int j = 0; j < kTiles; ++j) {
+                    const int clip0 = clip_base + j * G;
+                    const int valid = a.B - clip0 < G ? (a.B - clip0 < 0 ? 0 : a.B - clip0) : G;
+                    if (valid > 0) {
+                        const uint32_t bytes = static_cast<uint32_t>(valid * clip_floats * 4);
+                        mbar_arrive_expect_tx(&s.x_full[j], bytes);
+                        tma_bulk_g2s(&s.ab[j][0], a.x + static_cast<long long>(clip0) * clip_floats, bytes, &s.x_full[j]);
+                    } else {
+                        rs_arrive(&s.x_full[j]);
+                    }
+                }
+            }
             int g = 0;
             // the conv_tc arrangement is a plain sequence of K-slabs ([K/4][C][4]): any multiple-of-4 K
             // granularity is a contiguous slice of it
@@ -309,10 +336,10 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         constexpr int kRowsPerPass = kEpiS / kQuadsIn;            // rows covered by 256 threads at once
         constexpr int kIters = 128 / kRowsPerPass;
         const int qd = tid % kQuadsIn, rsub = tid / kQuadsIn;
-        // x loads: lanes run over channel quads (coalesced).  With one CTA per SM the registers are there to put the
-        // loads of EVERY tile in flight at once (one exposed HBM latency per CTA instead of one per tile); the C = 32
-        // stage (3 CTAs/SM, 64 registers) fetches tile j+1 while tile j's shortcut MMAs run.
-        constexpr int kPre = Cfg::kMinCtas == 1 ? kTiles : 1;
+        // x loads of the C = 32 stage (3 CTAs/SM hide the latency; its raw tile does not fit the operand buffer): lanes
+        // run over channel quads (coalesced), tile j+1 is fetched while tile j's shortcut MMAs run.  The other stages
+        // read the tile the producer warp's bulk copy staged in shared memory (RS_READ_TILE).
+        constexpr int kPre = 1;
         float4 v[kPre][kIters], v2[kPre][kIters];
 #define RS_LOAD_TILE(J)                                                                                                  \
     {                                                                                                                    \
@@ -329,9 +356,24 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
             }                                                                                                            \
         }                                                                                                                \
     }
+#define RS_READ_TILE(J)                                                                                                  \
+    {                                                                                                                    \
+        const int clip0_ = clip_base + (J) * G;                                                                          \
+        const float* raw = reinterpret_cast<const float*>(&s.ab[J][0]);                                                  \
+        _Pragma("unroll") for (int i = 0; i < kIters; ++i) {                                                             \
+            const int r = rsub + i * kRowsPerPass;                                                                       \
+            const int t = r / G, gg = r - t * G;                                                                         \
+            v[0][i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                                   \
+            v2[0][i] = v[0][i];                                                                                          \
+            if (clip0_ + gg < a.B) {                                                                                     \
+                const float* src = raw + (gg * (2 * T) + 2 * t) * CIN + 4 * qd;                                          \
+                v[0][i] = *reinterpret_cast<const float4*>(src);                                                         \
+                v2[0][i] = *reinterpret_cast<const float4*>(src + CIN);                                                  \
+            }                                                                                                            \
+        }                                                                                                                \
+    }
         if (tid == 0) stamp(16);
-#pragma unroll
-        for (int j = 0; j < kPre; ++j) RS_LOAD_TILE(j)
+        if (!Cfg::kTmaX) RS_LOAD_TILE(0)
         const float4 sc1 = *reinterpret_cast<const float4*>(a.u[0].bn1_scale + 4 * qd);
         const float4 sh1 = *reinterpret_cast<const float4*>(a.u[0].bn1_shift + 4 * qd);
         // Parameters: all global loads first, then the shared stores.  (Interleaved, every load has to wait for the
@@ -359,17 +401,26 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                 s.prm[u][4][i] = run;                             // y_u = acc2 + bs + b2_0 + .. + b2_u
             }
         }
-        // zero the halo rows (rows [0,G) and [G+128, G+128+G)) of every tile; the epilogues never touch them
-        for (int i = tid; i < kTiles * kQuads * 2 * G; i += kEpiS) {
-            const int j = i / (kQuads * 2 * G), rem = i - j * (kQuads * 2 * G);
-            const int q = rem / (2 * G), h = rem - q * (2 * G);
-            const int row = h < G ? h : 128 + h;
-            *reinterpret_cast<uint4*>(&s.ab[j][0] + (q * kRtotS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
-        }
+        // zero the halo rows (rows [0,G) and [G+128, G+128+G)) of a tile; the epilogues never touch them
+        auto zero_halo = [&](int j) {
+            for (int i = tid; i < kQuads * 2 * G; i += kEpiS) {
+                const int q = i / (2 * G), h = i - q * (2 * G);
+                const int row = h < G ? h : 128 + h;
+                *reinterpret_cast<uint4*>(&s.ab[j][0] + (q * kRtotS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        if (!Cfg::kTmaX)
+            for (int j = 0; j < kTiles; ++j) zero_halo(j);
         // ---- per tile: raw x[2t] -> shortcut operand; ReLU(BN1(max(x[2t], x[2t+1]))) -> conv1 operand ----
         unsigned char* a0 = &s.ring[kStages * kChunkBytes];
 #pragma unroll
         for (int j = 0; j < kTiles; ++j) {
+            if (Cfg::kTmaX) {
+                rs_wait(&s.x_full[j], 0u);
+                RS_READ_TILE(j)
+                rs_epi_sync();                                    // everyone holds its part: the buffer may be rewritten
+                zero_halo(j);
+            }
             if (j > 0) rs_wait(&s.a0_free, static_cast<uint32_t>((j - 1) & 1));   // shortcut MMAs of tile j-1 retired
 #pragma unroll
             for (int i = 0; i < kIters; ++i) {
@@ -384,7 +435,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                     make_uint4(rs_tf32(fmaxf(fmaf(p.x, sc1.x, sh1.x), 0.f)), rs_tf32(fmaxf(fmaf(p.y, sc1.y, sh1.y), 0.f)),
                                rs_tf32(fmaxf(fmaf(p.z, sc1.z, sh1.z), 0.f)), rs_tf32(fmaxf(fmaf(p.w, sc1.w, sh1.w), 0.f)));
             }
-            if (kPre == 1 && j + 1 < kTiles) RS_LOAD_TILE(j + 1)  // latency overlaps the barrier round trip below
+            if (!Cfg::kTmaX && j + 1 < kTiles) RS_LOAD_TILE(j + 1)  // latency overlaps the barrier round trip below
             fence_proxy_async_smem();
             rs_epi_sync();
             if (tid == 0) rs_arrive(&s.a0_ready);
@@ -421,12 +472,11 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                     const int col = cbase + k;
                     const float4 sc = *reinterpret_cast<const float4*>(scale + col);
                     const float4 sh = *reinterpret_cast<const float4*>(shift + col);
-                    const float w0 = fmaxf(fmaf(__uint_as_float(z[k + 0]), sc.x, sh.x), 0.f);
-                    const float w1 = fmaxf(fmaf(__uint_as_float(z[k + 1]), sc.y, sh.y), 0.f);
-                    const float w2 = fmaxf(fmaf(__uint_as_float(z[k + 2]), sc.z, sh.z), 0.f);
-                    const float w3 = fmaxf(fmaf(__uint_as_float(z[k + 3]), sc.w, sh.w), 0.f);
                     *reinterpret_cast<uint4*>(&s.ab[j][0] + ((col >> 2) * kRtotS + G + row) * 16) =
-                        make_uint4(rs_tf32(w0), rs_tf32(w1), rs_tf32(w2), rs_tf32(w3));
+                        make_uint4(rs_relu_tf32(fmaf(__uint_as_float(z[k + 0]), sc.x, sh.x)),
+                                   rs_relu_tf32(fmaf(__uint_as_float(z[k + 1]), sc.y, sh.y)),
+                                   rs_relu_tf32(fmaf(__uint_as_float(z[k + 2]), sc.z, sh.z)),
+                                   rs_relu_tf32(fmaf(__uint_as_float(z[k + 3]), sc.w, sh.w)));
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -522,6 +572,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         }
         if (tid == 0) stamp(31);
 #undef RS_LOAD_TILE
+#undef RS_READ_TILE
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
