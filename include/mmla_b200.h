@@ -61,6 +61,9 @@ void mmla_debug_mfcc_tc_dump(float* dev_buffer, long long* dev_stamps);
 /* Diagnostics of the fused ResNet-stage kernel: dev_stamps (DEVICE pointer, 3 x 64 int64, NULL = off) receives a
  * clock64 timeline of the warp roles of CTA `cta` of each of the three stage launches (row = stage). */
 void mmla_debug_resstage_stamps(long long* dev_stamps, int32_t cta);
+/* Same for the fused BiLSTM kernel: dev_stamps (DEVICE pointer, T x 16 int64, NULL = off) receives, per time step,
+ * the clock64 timeline of CTA `cta` of the forward direction. */
+void mmla_debug_lstm_stamps(long long* dev_stamps, int32_t cta);
 
 /* ------------------------------------------------------------------------------------------
  * Speaker-ID features.

@@ -25,6 +25,14 @@
 // [128 half, 128 half + 128) (two of the four 64-unit passes) for all 128 clips, so 4096 clips give
 // 128 CTAs instead of 64 (148 SMs) and each CTA streams half of U per step.  h(t) goes through global
 // memory as before; the two halves hand it over with one remote mbarrier arrive per step (DSMEM).
+//
+// Global layouts.  The gate epilogue holds one clip per thread (TMEM lane = row), so everything it touches every step
+// is "row-tiled": [clip tile][column quad][row 0..127][4 floats] — a warp's 128-bit access is then 512 contiguous
+// bytes.  That is the layout of xp (written that way by xproj_fused.cu: [tile][t][256 quads][128][4]), of the cell
+// state c ([tile][64 quads][128][4]) and of the h exchange buffer hx (same shape, two copies used alternately so a
+// CTA never overwrites the h its peer may still be re-staging).  In the natural [b][..] layouts every lane touched
+// its own 128-byte line: 17k of the 60k cycles of a step went into those loads (scripts/prof_lstm.py).  Only the
+// final h is written in the caller's [B][256] layout.
 #include <math.h>
 #include <string.h>
 
@@ -55,11 +63,14 @@ struct LstmSmem {
 };
 
 struct LstmArgs {
-    const float* xp[2];     // [B][T][1024] input projections (+bias), Keras column order i|f|c|o
+    const float* xp[2];     // row-tiled input projections (+bias), columns in Keras order i|f|c|o
     const float* wr[2];     // arranged recurrent weights, kChunksPerStep x kBChunkFloats
-    float* h[2];            // [B][256] running / final hidden state
-    float* c[2];            // [B][256] cell state
+    float* h[2];            // [B][256] final hidden state
+    float* c[2];            // row-tiled cell state, ceil(B/128) x 64 x 128 x 4 floats
+    float* hx[2];           // row-tiled h exchange, 2 x the size of c
     int B, T;
+    long long* stamps;      // diagnostics: clock64 timeline of CTA (stamp_cta, dir 0), 16 slots per step (null = off)
+    int stamp_cta;
 };
 
 __device__ __forceinline__ uint32_t tf32_round(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
@@ -114,7 +125,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     const float* xp = a.xp[dir];
     const float* wr = a.wr[dir];
     float* hg = a.h[dir];
-    float* cg = a.c[dir];
+    const long long tile = blockIdx.x >> 1;
+    const long long tile_floats = 64LL * 512;                  // one row-tiled [64 quads][128 rows][4] block
+    float* cg = a.c[dir] + tile * tile_floats;
+    float* hx0 = a.hx[dir] + tile * tile_floats;                // buffer of even steps; odd steps: + hx_stride
+    const long long hx_stride = ((a.B + kRows - 1) / kRows) * tile_floats;
     const int T = a.T;
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // f32 += tf32 x tf32, M=128, N=256
@@ -144,6 +159,10 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s.tmem_base;
+    const bool stamping = a.stamps != nullptr && static_cast<int>(blockIdx.x) == a.stamp_cta && dir == 0;
+    auto stamp = [&](int step, int slot) {
+        if (stamping) a.stamps[step * 16 + slot] = clock64();
+    };
     const int n_rec = T > 1 ? T - 1 : 0;                          // recurrent steps
     const long long total_chunks = static_cast<long long>(n_rec) * kChunksCta;
 
@@ -168,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             constexpr uint32_t kStageUnits = kBChunkBytes / 16;
             for (int rs = 0; rs < n_rec; ++rs) {
                 wait_or_trap(&s.hready, static_cast<uint32_t>(rs & 1));        // h_{t-1} staged in smem
+                if (lane == 0) stamp(rs + 1, 8);
                 for (int pass = 0; pass < kPasses; ++pass) {
                     const long long P = static_cast<long long>(rs) * kPasses + pass; // this CTA's pass counter
                     const int buf = static_cast<int>(P & 1);
@@ -198,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                             __syncwarp();
                         }
                     }
+                    if (lane == 0) stamp(rs + 1, 9 + pass);
                 }
             }
         }
@@ -224,20 +245,19 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
         };
         // 16 units of the cell update for this thread's row.  All global loads (four gate slices of
         // xp + the old cell state, 20 x 128-bit) are issued before the first TMEM read.
-        auto cell16 = [&](int t, int u, uint32_t tcol, bool first) {  // u: absolute unit; tcol: TMEM column of gate i
-            const long long rrow = row_ok ? brow : 0;                  // masked rows read row 0, never write
-            const float* xr = xp + (rrow * T + t) * 1024 + u;
-            float* cp = cg + rrow * kU + u;
-            float* hp = hg + rrow * kU + u;
+        auto cell16 = [&](int step, int t, int u, uint32_t tcol, bool first) {  // u: absolute unit; tcol: TMEM column of gate i
+            const float* xr = xp + ((tile * T + t) * 256 + (u >> 2)) * 512 + row * 4;   // gate g: + 64 g quads
+            float* cp = cg + (u >> 2) * 512 + row * 4;
+            float* hp = hx0 + (step & 1) * hx_stride + (u >> 2) * 512 + row * 4;
             float xi[16], xf[16], xc[16], xo[16], cv[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<float4*>(&xi[j]) = __ldcg(reinterpret_cast<const float4*>(xr + j));
-                *reinterpret_cast<float4*>(&xc[j]) = __ldcg(reinterpret_cast<const float4*>(xr + 512 + j));
-                *reinterpret_cast<float4*>(&xf[j]) = __ldcg(reinterpret_cast<const float4*>(xr + 256 + j));
-                *reinterpret_cast<float4*>(&xo[j]) = __ldcg(reinterpret_cast<const float4*>(xr + 768 + j));
+                *reinterpret_cast<float4*>(&xi[j]) = __ldcg(reinterpret_cast<const float4*>(xr + (j >> 2) * 512));
+                *reinterpret_cast<float4*>(&xc[j]) = __ldcg(reinterpret_cast<const float4*>(xr + (128 + (j >> 2)) * 512));
+                *reinterpret_cast<float4*>(&xf[j]) = __ldcg(reinterpret_cast<const float4*>(xr + (64 + (j >> 2)) * 512));
+                *reinterpret_cast<float4*>(&xo[j]) = __ldcg(reinterpret_cast<const float4*>(xr + (192 + (j >> 2)) * 512));
                 *reinterpret_cast<float4*>(&cv[j]) =
-                    first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(cp + j));
+                    first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(cp + (j >> 2) * 512));
             }
             const uint32_t tbase = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + tcol;
             float z[16], pr[16];
@@ -253,30 +273,39 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             if (!first) ld16(tbase + 192, z);                          // o
 #pragma unroll
             for (int j = 0; j < 16; ++j) pr[j] = fast_sigmoid((first ? 0.f : z[j]) + xo[j]) * fast_tanh(cv[j]);
-            if (row_ok) {
+            if (step + 1 < T) {                                        // padded rows live in the tile too: no masking
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    *reinterpret_cast<float4*>(cp + j) = *reinterpret_cast<float4*>(&cv[j]);
-                    *reinterpret_cast<float4*>(hp + j) = *reinterpret_cast<float4*>(&pr[j]);
+                    *reinterpret_cast<float4*>(cp + (j >> 2) * 512) = *reinterpret_cast<float4*>(&cv[j]);
+                    *reinterpret_cast<float4*>(hp + (j >> 2) * 512) = *reinterpret_cast<float4*>(&pr[j]);
                 }
+            } else if (row_ok) {                                       // last step: the caller's [B][256] layout
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(hg + static_cast<long long>(brow) * kU + u + j) = *reinterpret_cast<float4*>(&pr[j]);
             }
         };
         // re-stage h (global, fp32) into the SWIZZLE_128B TF32 operand tiles; loads are issued
         // 16 at a time before their first use
-        auto restage_h = [&]() {
-            const int q = tid & 7, rb = tid >> 3;
+        auto restage_h = [&](int step) {
+            // lanes run over rows (coalesced 512-byte reads of the row-tiled exchange buffer); quad uq of the 64 is
+            // K-sub-tile uq/8, 16-byte column uq%8 of the swizzled operand row
+            const float* src = hx0 + (step & 1) * hx_stride;
+            const int r = tid & 127, uq0 = tid >> 7;
+            const bool ok = b0 + r < a.B;
 #pragma unroll
-            for (int kc0 = 0; kc0 < 8; kc0 += 4) {
+            for (int i0 = 0; i0 < 32; i0 += 16) {
                 float4 v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int kc = kc0 + (j >> 2), r = rb + 32 * (j & 3);
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b0 + r < a.B) v[j] = __ldcg(reinterpret_cast<const float4*>(hg + static_cast<long long>(b0 + r) * kU + 32 * kc + 4 * q));
+                    const int uq = uq0 + 2 * (i0 + j);
+                    v[j] = __ldcg(reinterpret_cast<const float4*>(src + uq * 512 + r * 4));
+                    if (!ok) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int kc = kc0 + (j >> 2), r = rb + 32 * (j & 3);
+                    const int uq = uq0 + 2 * (i0 + j);
+                    const int kc = uq >> 3, q = uq & 7;
                     *reinterpret_cast<uint4*>(&s.H[kc][0] + r * 128 + ((q ^ (r & 7)) << 4)) =
                         make_uint4(tf32_round(v[j].x), tf32_round(v[j].y), tf32_round(v[j].z), tf32_round(v[j].w));
                 }
@@ -286,35 +315,38 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
         // pull the xp rows of time step t into L2 one step ahead (they stream from HBM otherwise):
         // 128 rows x 4 KB = 4096 lines, 16 per thread
         auto prefetch_xp = [&](int t) {
-#pragma unroll 4
-            for (int i = tid; i < kRows * 32; i += kEpiThreads) {
-                const int r = i >> 5, line = i & 31;
-                if (((line >> 2) & 1) != half) continue;               // this half's 128 units of every gate
-                if (b0 + r < a.B) {
-                    const float* ptr = xp + (static_cast<long long>(b0 + r) * T + t) * 1024 + line * 32;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-                }
+            // this half's 128 units of every gate: 4 runs of 32 quads x 2 KB = 512 lines each, 8 lines per thread
+            const float* base = xp + (tile * T + t) * (256LL * 512);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int line = tid + i * kEpiThreads;               // 0..2047
+                const int g = line >> 9, l = line & 511;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (64 * g + 32 * half) * 512 + l * 32));
             }
         };
 
         for (int step = 0; step < T; ++step) {
             const int t = dir == 0 ? step : T - 1 - step;
+            if (tid == 0) stamp(step, 0);
             if (step + 1 < T) prefetch_xp(dir == 0 ? t + 1 : t - 1);
+            if (tid == 0) stamp(step, 1);
             if (step == 0) {
                 for (int pass = 0; pass < kPasses; ++pass)             // h0 = c0 = 0: z is the input projection alone
-                    for (int uo = 0; uo < 32; uo += 16) cell16(t, 64 * (kPasses * half + pass) + usub + uo, 0u, true);
+                    for (int uo = 0; uo < 32; uo += 16) cell16(step, t, 64 * (kPasses * half + pass) + usub + uo, 0u, true);
             } else {
                 for (int pass = 0; pass < kPasses; ++pass) {
                     const long long P = static_cast<long long>(step - 1) * kPasses + pass;
                     const int buf = static_cast<int>(P & 1);
                     wait_or_trap(&s.tfull[buf], static_cast<uint32_t>((P >> 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (tid == 0) stamp(step, 2 + 2 * pass);
                     // pass columns: [0,64) i, [64,128) f, [128,192) c~, [192,256) o
                     for (int uo = 0; uo < 32; uo += 16)
-                        cell16(t, 64 * (kPasses * half + pass) + usub + uo, static_cast<uint32_t>(buf * 256 + usub + uo), false);
+                        cell16(step, t, 64 * (kPasses * half + pass) + usub + uo, static_cast<uint32_t>(buf * 256 + usub + uo), false);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s.tempty[buf]);        // this warp has drained the pass
+                    if (tid == 0) stamp(step, 3 + 2 * pass);
                 }
             }
             if (step + 1 < T) {
@@ -340,9 +372,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                     if (!ok) asm volatile("trap;");
                 }
                 epi_bar_sync();
-                restage_h();
+                if (tid == 0) stamp(step, 6);
+                restage_h(step);
                 epi_bar_sync();
                 if (tid == 0) mbar_arrive(&s.hready);
+                if (tid == 0) stamp(step, 7);
             }
         }
     }
@@ -380,8 +414,20 @@ void mmla_lstm_arrange_weights(const float* U, float* out) {
             }
 }
 
+static long long* g_lstm_stamps = nullptr;
+static int g_lstm_stamp_cta = 0;
+extern "C" __attribute__((visibility("default"))) void mmla_debug_lstm_stamps(long long* dev_stamps, int32_t cta) {
+    g_lstm_stamps = dev_stamps;
+    g_lstm_stamp_cta = cta;
+}
+
+// Scratch floats per direction for the row-tiled cell state (1x) and the h exchange (2x): 3 x this.
+long long mmla_lstm_tile_floats(long long B) { return ((B + kRows - 1) / kRows) * 64LL * 512; }
+
+// xp_*: row-tiled input projections (xproj_fused.cu); h_*: [B][256] final hidden state (output);
+// scratch_*: 3 * mmla_lstm_tile_floats(B) floats each.
 int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
-                           float* h_b, float* c_f, float* c_b, long long B, int T, cudaStream_t st) {
+                           float* h_b, float* scratch_f, float* scratch_b, long long B, int T, cudaStream_t st) {
     MMLA_REQUIRE(B > 0 && B < (1LL << 22) && T >= 1, MMLA_EINVAL, "lstm_fused: bad batch/T");
     static bool attr_set = false;
     const int smem = static_cast<int>(sizeof(LstmSmem) + 1024);
@@ -391,8 +437,11 @@ int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr
     }
     LstmArgs a;
     a.xp[0] = xp_f; a.xp[1] = xp_b; a.wr[0] = wr_f; a.wr[1] = wr_b;
-    a.h[0] = h_f; a.h[1] = h_b; a.c[0] = c_f; a.c[1] = c_b;
+    a.h[0] = h_f; a.h[1] = h_b;
+    a.c[0] = scratch_f; a.c[1] = scratch_b;
+    a.hx[0] = scratch_f + mmla_lstm_tile_floats(B); a.hx[1] = scratch_b + mmla_lstm_tile_floats(B);
     a.B = static_cast<int>(B); a.T = T;
+    a.stamps = g_lstm_stamps; a.stamp_cta = g_lstm_stamp_cta;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2u * static_cast<unsigned>((B + kRows - 1) / kRows), 2, 1);   // two CTAs (unit halves) per 128-clip tile

@@ -395,11 +395,11 @@ int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int 
 long long mmla_xproj_arranged_floats();
 void mmla_xproj_arrange_weights(const float* W, float* out);
 int mmla_launch_xproj_fused(const float* seq, const float* w_f, const float* w_b, const float* b_f, const float* b_b,
-                            float* xp_f, float* xp_b, long long rows, cudaStream_t st);
+                            float* xp_f, float* xp_b, long long B, int T, cudaStream_t st);
 long long mmla_lstm_arranged_floats();
 void mmla_lstm_arrange_weights(const float* U, float* out);
 int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
-                           float* h_b, float* c_f, float* c_b, long long B, int T, cudaStream_t st);
+                           float* h_b, float* scratch_f, float* scratch_b, long long B, int T, cudaStream_t st);
 
 namespace {
 
@@ -615,7 +615,8 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
     // workspace plan (floats per clip): three rotating activation buffers + LSTM scratch
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const long long T = net->seq_len;
-    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 4 * 256 + (ov ? 0 : 256 * 40);
+    // (the LSTM buffers of the tensor-core path are laid out in whole 128-clip tiles: mmla_net_workspace_bytes rounds up)
+    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 2 * 256 + 6 * 256 + (ov ? 0 : 256 * 40);
     net->micro = ov ? 512 : 4096;         // measured on B200: larger micro-batches win (overlap, 512 clips: 24.8 ms at 128, 21.4 ms at 512)
     if (const char* e = getenv("MMLA_NET_MICRO")) {
         const int v = atoi(e);
@@ -635,7 +636,8 @@ EXPORT void mmla_net_destroy(MmlaNet* net) {
 EXPORT int64_t mmla_net_workspace_bytes(const MmlaNet* net, int64_t batch) {
     if (!net || batch < 0) return -1;
     const long long mb = batch < net->micro ? batch : net->micro;
-    return (mb < 1 ? 1 : mb) * net->per_clip_floats * static_cast<long long>(sizeof(float)) + 256;
+    const long long mbp = ((mb < 1 ? 1 : mb) + 127) / 128 * 128;
+    return mbp * net->per_clip_floats * static_cast<long long>(sizeof(float)) + 256;
 }
 
 static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t cep_frames, int64_t cep_clip_stride, int64_t batch,
@@ -683,11 +685,12 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         float* ws = static_cast<float*>(workspace);
         float* buf[3] = {ws, ws + B * act, ws + 2 * B * act};
         float* seq = ws + 3 * B * act;                    // [B,T,128]
-        float* xp[2] = {seq + B * T * 128, seq + B * T * 128 + B * T * 1024};   // [B,T,1024] per direction
-        float* z = xp[1] + B * T * 1024;                  // [B,1024] gate pre-activations
+        const long long Bp = (B + 127) / 128 * 128;       // the tensor-core LSTM path works in whole 128-clip tiles
+        float* xp[2] = {seq + B * T * 128, seq + B * T * 128 + Bp * T * 1024};  // per direction: [B,T,1024], or row-tiled
+        float* z = xp[1] + Bp * T * 1024;                 // [B,1024] gate pre-activations
         float* hdir[2] = {z + B * 1024, z + B * 1024 + B * 256};   // final h of the fwd / bwd layer
-        float* cst = hdir[1] + B * 256;                   // [B,256] cell state (x2 for the fused kernel)
-        float* xpad = cst + 2 * B * 256;                  // speaker: [B,256,40] channel-padded input
+        float* cst = hdir[1] + B * 256;                   // [B,256] cell state; fused kernel: 2 x 3 row-tiled [Bp,256] blocks
+        float* xpad = cst + 6 * Bp * 256;                 // speaker: [B,256,40] channel-padded input
 
         const void* xin = x_is_u8 ? static_cast<const void*>(static_cast<const unsigned char*>(x) + b0 * in_elems)
                                   : static_cast<const void*>(static_cast<const float*>(x) + b0 * in_elems);
@@ -797,22 +800,24 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         }
         MMLA_CUDA_CHECK(cudaGetLastError());
         // BiLSTM(256): input projections for all steps, then the recurrence
-        if (tc && net->lstm_in_fused[0] && net->lstm_in_fused[1]) {
+        // tensor-core mode: xproj_fused.cu -> lstm_fused.cu, which share the row-tiled xp layout
+        const bool fused_lstm = tc && net->lstm_in_fused[0] && net->lstm_in_fused[1] && net->lstm_rec_fused[0] && net->lstm_rec_fused[1];
+        if (fused_lstm) {
             // both directions in one launch (xproj_fused.cu)
             if ((rc = mmla_launch_xproj_fused(seq, net->lstm_in_fused[0], net->lstm_in_fused[1], net->lstm_in[0].b,
-                                              net->lstm_in[1].b, xp[0], xp[1], B * T, st)))
+                                              net->lstm_in[1].b, xp[0], xp[1], B, T, st)))
                 return rc;
         } else {
             for (int d = 0; d < 2; ++d)
                 if ((rc = launch_conv(net->lstm_in[d], seq, 0, B * T, 1, 1, nullptr, ACT_NONE, nullptr, 0, xp[d], st, tc))) return rc;
         }
-        if (tc) {
+        if (fused_lstm) {
             // one persistent launch: both directions, all time steps (lstm_fused.cu)
             if ((rc = mmla_launch_lstm_fused(xp[0], xp[1], net->lstm_rec_fused[0], net->lstm_rec_fused[1], hdir[0], hdir[1],
-                                             cst, cst + B * 256, B, T, st)))
+                                             cst, cst + 3 * Bp * 256, B, T, st)))
                 return rc;
         }
-        for (int d = 0; d < 2 && !tc; ++d) {
+        for (int d = 0; d < 2 && !fused_lstm; ++d) {
             float* h = hdir[d];                            // updated in place: the recurrent GEMM of a
             for (int s = 0; s < T; ++s) {                  // step finishes before its gate kernel writes h
                 const int t = d == 0 ? s : T - 1 - s;     // backward layer walks t = T-1 .. 0

@@ -3,14 +3,19 @@
 // SpeakerIdentification/scripts/speaker_identification.py:213) — the [B*T, 128] x [128, 1024] products whose
 // result `lstm_fused_kernel` adds to the recurrent pre-activations at every step.
 //
-// One CTA = (128-row tile of seq, direction):
+// Output layout ("row-tiled", shared with lstm_fused.cu): xp[d][clip tile bt][t][column quad cq][row r][4], clip
+// b = 128 bt + r, column = 4 cq + e in Keras order i|f|c|o.  Both kernels hold one clip per thread (TMEM lane = row),
+// so with this layout a warp's 128-bit access covers 32 consecutive rows = 512 contiguous bytes, whereas in the
+// natural [b][t][1024] layout the 32 lanes touch 32 different lines (the LSTM's gate epilogue spent 17k of its 60k
+// cycles per step in exactly those loads).  The buffer is sized for whole 128-clip tiles.
+//
+// One CTA = (128 clips x one time step of seq, direction):
 //   * the A tile [128 x 128] is read once (coalesced), rounded to TF32 and kept in shared memory for the whole
 //     CTA as four 128 x 32 SWIZZLE_128B sub-tiles (the same operand form lstm_fused.cu uses for h);
 //   * W_in streams from L2 through a 4-stage TMA ring of 16 KB chunks (host pre-arranged, TF32 pre-rounded):
 //     four passes of 256 output columns, 16 tcgen05.mma (M=128, N=256, K=8) each, accumulating in TMEM; the two
 //     256-column TMEM halves ping-pong so the MMAs of pass p+1 overlap the epilogue of pass p;
-//   * the epilogue adds the bias and writes through a 64-column staging tile so global stores are whole
-//     256-byte row segments.
+//   * the epilogue adds the bias and stores straight from registers (coalesced by construction, see above).
 // The generic implicit-GEMM kernel (conv_tc.cu, built for gathered conv operands) needed 0.075 ms per direction
 // for 4096 clips; this path is bound by the 134 MB it writes.
 #include <string.h>
@@ -29,12 +34,10 @@ constexpr int kPasses = kN / 256;             // 4
 constexpr int kStages = 4;
 constexpr int kEpi = 256;
 constexpr int kThreads = kEpi + 64;           // warp 8: TMA producer, warp 9: MMA issuer
-constexpr int kStgStride = 64 + 4;
 
 struct XpSmem {
     alignas(1024) unsigned char A[4][kSub];
     alignas(128) unsigned char ring[kStages][kChunkBytes];
-    alignas(16) float stg[128 * kStgStride];
     alignas(16) float bias[kN];
     alignas(8) uint64_t full[kStages], empty[kStages], tfull[2], tempty[2], aready;
     uint32_t tmem_base;
@@ -67,11 +70,12 @@ __device__ __forceinline__ void xp_commit(uint64_t* bar) {
 }
 
 struct XpArgs {
-    const float* seq;       // [rows][128]
+    const float* seq;       // [B][T][128]
     const float* w[2];      // arranged chunk streams, kPasses * kChunksPerPass chunks each
     const float* b[2];      // [1024]
-    float* xp[2];           // [rows][1024]
-    long long rows;
+    float* xp[2];           // row-tiled, ceil(B/128) x T x 256 x 128 x 4 floats
+    long long B;
+    int T;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) xproj_fused_kernel(const XpArgs a) {
@@ -79,7 +83,9 @@ __global__ void __launch_bounds__(kThreads, 1) xproj_fused_kernel(const XpArgs a
     XpSmem& s = *reinterpret_cast<XpSmem*>(smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
-    const long long r0 = static_cast<long long>(blockIdx.x) * 128;
+    const long long bt = blockIdx.x / a.T;                        // clip tile
+    const int t = static_cast<int>(blockIdx.x - bt * a.T);        // time step
+    const long long b0 = bt * 128;
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // f32 += tf32 x tf32, M=128, N=256
 
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) xproj_fused_kernel(const XpArgs a
         for (int j = 0; j < 16; ++j) {
             const int kc = j >> 2, r = rb + 32 * (j & 3);
             v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r0 + r < a.rows) v[j] = *reinterpret_cast<const float4*>(a.seq + (r0 + r) * kK + 32 * kc + 4 * q);
+            if (b0 + r < a.B) v[j] = *reinterpret_cast<const float4*>(a.seq + ((b0 + r) * a.T + t) * kK + 32 * kc + 4 * q);
         }
         for (int i = tid; i < kN; i += kEpi) s.bias[i] = a.b[dir][i];
     }
@@ -178,47 +184,43 @@ __global__ void __launch_bounds__(kThreads, 1) xproj_fused_kernel(const XpArgs a
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 0) xp_arrive(&s.aready);
 
-        const int quarter = warp & 3, chalf = warp >> 2;          // TMEM lanes 32*quarter..; 32-column half of a 64-column group
+        const int quarter = warp & 3, chalf = warp >> 2;          // TMEM lanes 32*quarter..; 128-column half of a pass
         const int row = 32 * quarter + lane;
-        float* out = a.xp[dir];
+        const bool row_ok = b0 + row < a.B;
+        float* out = a.xp[dir] + (bt * a.T + t) * (256LL * 512) + row * 4;
         for (int pass = 0; pass < kPasses; ++pass) {
             const int buf = pass & 1;
             xp_wait(&s.tfull[buf], static_cast<uint32_t>((pass >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int grp = 0; grp < 4; ++grp) {                   // 64 columns at a time through the staging tile
-                const int c0 = 64 * grp + 32 * chalf;             // column of the pass this thread reads
+#pragma unroll 1
+            for (int grp = 0; grp < 4; ++grp) {                   // 32 columns at a time: two loads in flight, one wait
+                const int c0 = 128 * chalf + 32 * grp;            // column of the pass this thread reads
+                uint32_t r[32];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t r[16];
+                for (int hh = 0; hh < 2; ++hh)
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "=r"(r[16 * hh + 0]), "=r"(r[16 * hh + 1]), "=r"(r[16 * hh + 2]), "=r"(r[16 * hh + 3]), "=r"(r[16 * hh + 4]),
+                          "=r"(r[16 * hh + 5]), "=r"(r[16 * hh + 6]), "=r"(r[16 * hh + 7]), "=r"(r[16 * hh + 8]), "=r"(r[16 * hh + 9]),
+                          "=r"(r[16 * hh + 10]), "=r"(r[16 * hh + 11]), "=r"(r[16 * hh + 12]), "=r"(r[16 * hh + 13]),
+                          "=r"(r[16 * hh + 14]), "=r"(r[16 * hh + 15])
                         : "r"(tmem + (static_cast<uint32_t>(32 * quarter) << 16) + static_cast<uint32_t>(buf * 256 + c0 + 16 * hh)));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 bv = *reinterpret_cast<const float4*>(&s.bias[256 * pass + c0 + 16 * hh + j]);
-                        *reinterpret_cast<float4*>(&s.stg[row * kStgStride + 32 * chalf + 16 * hh + j]) =
-                            make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
-                                        __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
-                    }
-                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (grp == 3) {                                   // this warp has drained the pass: MMAs of pass+2 may start
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) xp_arrive(&s.tempty[buf]);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (row_ok) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {                     // 128 rows x 16 float4, coalesced 256-byte row segments
-                    const int idx = tid + i * kEpi;
-                    const int rr = idx >> 4, q4 = idx & 15;
-                    if (r0 + rr < a.rows)
-                        *reinterpret_cast<float4*>(out + (r0 + rr) * kN + 256 * pass + 64 * grp + 4 * q4) =
-                            *reinterpret_cast<const float4*>(&s.stg[rr * kStgStride + 4 * q4]);
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = 256 * pass + c0 + j;
+                        const float4 bv = *reinterpret_cast<const float4*>(&s.bias[col]);
+                        *reinterpret_cast<float4*>(out + (col >> 2) * 512) =
+                            make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                                        __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                    }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
@@ -251,9 +253,11 @@ void mmla_xproj_arrange_weights(const float* W, float* out) {
             }
 }
 
+// seq: [B][T][128]; xp_f / xp_b: row-tiled outputs (see the top of this file), mmla_xproj_tiled_floats(B, T) floats each.
+long long mmla_xproj_tiled_floats(long long B, int T) { return ((B + 127) / 128) * T * 256LL * 512; }
 int mmla_launch_xproj_fused(const float* seq, const float* w_f, const float* w_b, const float* b_f, const float* b_b,
-                            float* xp_f, float* xp_b, long long rows, cudaStream_t st) {
-    MMLA_REQUIRE(rows > 0 && rows < (1LL << 30), MMLA_EINVAL, "xproj_fused: bad row count");
+                            float* xp_f, float* xp_b, long long B, int T, cudaStream_t st) {
+    MMLA_REQUIRE(B > 0 && T > 0 && B * T < (1LL << 30), MMLA_EINVAL, "xproj_fused: bad geometry");
     static bool attr_set = false;
     const int smem = static_cast<int>(sizeof(XpSmem) + 1024);
     if (!attr_set) {
@@ -265,8 +269,8 @@ int mmla_launch_xproj_fused(const float* seq, const float* w_f, const float* w_b
     a.w[0] = w_f; a.w[1] = w_b;
     a.b[0] = b_f; a.b[1] = b_b;
     a.xp[0] = xp_f; a.xp[1] = xp_b;
-    a.rows = rows;
-    const dim3 grid(static_cast<unsigned>((rows + 127) / 128), 2);
+    a.B = B; a.T = T;
+    const dim3 grid(static_cast<unsigned>(((B + 127) / 128) * T), 2);
     xproj_fused_kernel<<<grid, kThreads, smem, st>>>(a);
     mmla_count_launch("xproj_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
