@@ -48,7 +48,8 @@ constexpr int kBChunkBytes = kBChunkFloats * 4;   // 16 KB
 constexpr int kChunksPerStep = 64;          // 4 passes x 8 K-sub-tiles x 2 halves
 constexpr int kStages = 4;
 constexpr int kEpiThreads = 256;            // warps 0..7: gate epilogue + h re-staging
-constexpr int kThreads = kEpiThreads + 64;  // warp 8: TMA producer, warp 9: MMA issuer
+constexpr int kProducers = 2;               // TMA producer warps (see the producer loop)
+constexpr int kThreads = kEpiThreads + 32 + 32 * kProducers;  // warp 8: MMA issuer, warps 9..: TMA producers
 
 struct LstmSmem {
     alignas(1024) unsigned char H[8][kSubTile];              // h_{t-1}, SWIZZLE_128B K-major
@@ -166,10 +167,14 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     const int n_rec = T > 1 ? T - 1 : 0;                          // recurrent steps
     const long long total_chunks = static_cast<long long>(n_rec) * kChunksCta;
 
-    if (warp == 8) {
-        // ================= TMA producer: the periodic weight stream =================
+    if (warp > 8) {
+        // ================= TMA producers: the periodic weight stream =================
+        // Two producer WARPS, alternate chunks: a thread gets one cp.async.bulk through every ~420 cycles whatever its
+        // size (scripts/microbench/tma_stream.cu), so ONE producer moves 16 KB chunks at 39 B/clk while the MMAs of a
+        // chunk (2 x N=256) need it in 256 cycles = 64 B/clk.  (Several lanes of one warp do not help: their spin
+        // waits serialise.)
         if (lane == 0) {
-            for (long long g = 0; g < total_chunks; ++g) {
+            for (long long g = warp - 9; g < total_chunks; g += kProducers) {
                 const int stg = static_cast<int>(g % kStages);
                 const long long use = g / kStages;
                 if (use > 0) wait_or_trap(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
@@ -179,44 +184,53 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 8) {
         // ================= MMA issuer (warp-uniform loop, one elected lane issues; see resunit_fused.cu) =================
         {
-            long long g = 0;                                      // chunk counter
+            // Ring position as counters, descriptors advanced by adds, two chunks (4 MMAs) per trip: what sits between
+            // the last MMA of a trip and the first of the next is a bubble once the tensor pipe's short queue (~4
+            // MMAs) has drained — with one chunk (2 MMAs, 256 cycles) per trip a pass took 7.7k cycles instead of 4.1k.
+            static_assert(kStages == 4, "chunk pairs use stages {0,1} and {2,3}");
+            int stg = 0;
+            uint32_t par = 0;
             const uint64_t dB0 = desc_noswz(smem_u32(&s.Bst[0][0]), 256 * 16, 128);
+            const uint64_t dA0 = desc_sw128(smem_u32(&s.H[0][0]));
             constexpr uint32_t kStageUnits = kBChunkBytes / 16;
+            int P = 0;                                            // this CTA's pass counter
             for (int rs = 0; rs < n_rec; ++rs) {
                 wait_or_trap(&s.hready, static_cast<uint32_t>(rs & 1));        // h_{t-1} staged in smem
                 if (lane == 0) stamp(rs + 1, 8);
-                for (int pass = 0; pass < kPasses; ++pass) {
-                    const long long P = static_cast<long long>(rs) * kPasses + pass; // this CTA's pass counter
-                    const int buf = static_cast<int>(P & 1);
+                for (int pass = 0; pass < kPasses; ++pass, ++P) {
+                    const int buf = P & 1;
                     if (P >= 2) wait_or_trap(&s.tempty[buf], static_cast<uint32_t>(((P >> 1) - 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int kc = 0; kc < 8; ++kc) {
-                        const uint64_t dA = desc_sw128(smem_u32(&s.H[kc][0]));
-                        for (int kh = 0; kh < 2; ++kh, ++g) {
-                            const int stg = static_cast<int>(g % kStages);
-                            wait_or_trap(&s.full[stg], static_cast<uint32_t>((g / kStages) & 1));
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint64_t bd0 = dB0 + static_cast<uint64_t>(stg * kStageUnits);
-                            if (lstm_elect_one()) {
+                    const uint32_t dcol = tmem + static_cast<uint32_t>(buf * 256);
+                    uint64_t dA = dA0;
+                    for (int kc = 0; kc < 8; ++kc, dA += static_cast<uint64_t>(kSubTile / 16)) {
+                        // K-sub-tile kc: chunk 2kc covers its K columns 0..15, chunk 2kc+1 columns 16..31 (+64 B inside
+                        // the swizzled row = 4 descriptor units); 32 B per K=8 MMA
+                        const uint64_t bd0 = dB0 + static_cast<uint64_t>(stg * kStageUnits);
+                        wait_or_trap(&s.full[stg], par);
+                        wait_or_trap(&s.full[stg + 1], par);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (lstm_elect_one()) {
 #pragma unroll
-                                for (int m = 0; m < 2; ++m) {
-                                    const uint64_t ad = dA + static_cast<uint64_t>((2 * kh) * 2 + m * 2);   // 32 B per K=8 step
-                                    const uint64_t bd = bd0 + static_cast<uint64_t>(m * 2 * 256);
-                                    const uint32_t acc = (kc | kh | m) != 0 ? 1u : 0u;
-                                    asm volatile(
-                                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + buf * 256),
-                                        "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
-                                        : "memory");
-                                }
-                                umma_commit_to(&s.empty[stg]);
-                                if (kc == 7 && kh == 1) umma_commit_to(&s.tfull[buf]);
+                            for (int m = 0; m < 4; ++m) {
+                                const uint64_t ad = dA + static_cast<uint64_t>(m * 2);
+                                const uint64_t bd = bd0 + static_cast<uint64_t>((m >> 1) * kStageUnits + (m & 1) * 2 * 256);
+                                const uint32_t acc = (kc | m) != 0 ? 1u : 0u;
+                                asm volatile(
+                                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol),
+                                    "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                                    : "memory");
                             }
-                            __syncwarp();
+                            umma_commit_to(&s.empty[stg]);
+                            umma_commit_to(&s.empty[stg + 1]);
+                            if (kc == 7) umma_commit_to(&s.tfull[buf]);
                         }
+                        stg ^= 2;
+                        if (stg == 0) par ^= 1u;
                     }
                     if (lane == 0) stamp(rs + 1, 9 + pass);
                 }

@@ -33,7 +33,8 @@ constexpr int kChunksPerPass = kK / 16;       // 8
 constexpr int kPasses = kN / 256;             // 4
 constexpr int kStages = 4;
 constexpr int kEpi = 256;
-constexpr int kThreads = kEpi + 64;           // warp 8: TMA producer, warp 9: MMA issuer
+constexpr int kProducers = 2;                 // TMA producer warps, alternate chunks (see lstm_fused.cu)
+constexpr int kThreads = kEpi + 32 + 32 * kProducers;   // warp 8: MMA issuer, warps 9..: TMA producers
 
 struct XpSmem {
     alignas(1024) unsigned char A[4][kSub];
@@ -123,9 +124,11 @@ __global__ void __launch_bounds__(kThreads, 1) xproj_fused_kernel(const XpArgs a
     const uint32_t tmem = s.tmem_base;
     constexpr int kTotalChunks = kPasses * kChunksPerPass;
 
-    if (warp == 8) {
+    if (warp > 8) {
+        // two producer warps, alternate chunks (a single thread gets one bulk copy through per ~420 cycles: 39 B/clk
+        // at 16 KB, and the MMAs want 64 B/clk; see lstm_fused.cu / scripts/microbench/tma_stream.cu)
         if (lane == 0) {
-            for (int g = 0; g < kTotalChunks; ++g) {
+            for (int g = warp - 9; g < kTotalChunks; g += kProducers) {
                 const int stg = g % kStages, use = g / kStages;
                 if (use > 0) xp_wait(&s.empty[stg], static_cast<uint32_t>((use - 1) & 1));
                 mbar_arrive_expect_tx(&s.full[stg], kChunkBytes);
@@ -133,40 +136,45 @@ __global__ void __launch_bounds__(kThreads, 1) xproj_fused_kernel(const XpArgs a
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
+    } else if (warp == 8) {
         // whole warp converged, one elected lane issues (uniform-register descriptors)
         const uint64_t dB0 = xp_desc_noswz(smem_u32(&s.ring[0][0]), 256 * 16, 128);
         constexpr uint32_t kStageUnits = kChunkBytes / 16;
         xp_wait(&s.aready, 0u);
-        int g = 0;
+        // two chunks (4 MMAs) per trip, ring position as counters: see the MMA loop of lstm_fused.cu
+        static_assert(kStages == 4, "chunk pairs use stages {0,1} and {2,3}");
+        const uint64_t dA0 = xp_desc_sw128(smem_u32(&s.A[0][0]));
+        int stg = 0;
+        uint32_t par = 0;
         for (int pass = 0; pass < kPasses; ++pass) {
             const int buf = pass & 1;
             if (pass >= 2) xp_wait(&s.tempty[buf], static_cast<uint32_t>(((pass >> 1) - 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kc = 0; kc < 4; ++kc) {
-                const uint64_t dA = xp_desc_sw128(smem_u32(&s.A[kc][0]));
-                for (int kh = 0; kh < 2; ++kh, ++g) {
-                    const int stg = g % kStages;
-                    xp_wait(&s.full[stg], static_cast<uint32_t>((g / kStages) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t bd0 = dB0 + static_cast<uint64_t>(stg * kStageUnits);
-                    if (xp_elect_one()) {
+            const uint32_t dcol = tmem + static_cast<uint32_t>(buf * 256);
+            uint64_t dA = dA0;
+            for (int kc = 0; kc < 4; ++kc, dA += static_cast<uint64_t>(kSub / 16)) {
+                const uint64_t bd0 = dB0 + static_cast<uint64_t>(stg * kStageUnits);
+                xp_wait(&s.full[stg], par);
+                xp_wait(&s.full[stg + 1], par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (xp_elect_one()) {
 #pragma unroll
-                        for (int m = 0; m < 2; ++m) {
-                            const uint64_t ad = dA + static_cast<uint64_t>((2 * kh) * 2 + m * 2);   // 32 B per K=8 step
-                            const uint64_t bd = bd0 + static_cast<uint64_t>(m * 2 * 256);
-                            const uint32_t acc = (kc | kh | m) != 0 ? 1u : 0u;
-                            asm volatile(
-                                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + buf * 256),
-                                "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
-                                : "memory");
-                        }
-                        xp_commit(&s.empty[stg]);
-                        if (kc == 3 && kh == 1) xp_commit(&s.tfull[buf]);
+                    for (int m = 0; m < 4; ++m) {
+                        const uint64_t ad = dA + static_cast<uint64_t>(m * 2);                       // 32 B per K=8 step
+                        const uint64_t bd = bd0 + static_cast<uint64_t>((m >> 1) * kStageUnits + (m & 1) * 2 * 256);
+                        const uint32_t acc = (kc | m) != 0 ? 1u : 0u;
+                        asm volatile(
+                            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol),
+                            "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                            : "memory");
                     }
-                    __syncwarp();
+                    xp_commit(&s.empty[stg]);
+                    xp_commit(&s.empty[stg + 1]);
+                    if (kc == 3) xp_commit(&s.tfull[buf]);
                 }
+                stg ^= 2;
+                if (stg == 0) par ^= 1u;
             }
         }
     } else {
