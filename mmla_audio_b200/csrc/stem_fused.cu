@@ -28,13 +28,15 @@ constexpr int kQuads = kCin / 4;                 // 10 channel quads
 constexpr int kRows = 137;                       // 128 + 3 halo rows, padded to == 1 mod 8 (bank-friendly slab stride)
 constexpr int kWBytes = 4 * kCin * kCout * 4;    // 20480: 40 K-slabs x [32][4] floats
 constexpr int kThreadsStem = 256 + 32;           // warps 0..7 load / epilogue, warp 8 issues TMA + MMA
+constexpr int kCepStride = 145;                  // 139 staged rows; 4*145 = 4 mod 32 spreads the transposing stores
 
 struct StemSmem {
     alignas(128) unsigned char ab[kQuads * kRows * 16];     // operand slabs; later the output staging tile
     alignas(128) unsigned char w[kWBytes];
     alignas(16) float bias[kCout];
-    float cep[139][13];                                       // FROM_CEP: cepstra of times t0-5 .. t0+133 (clamped)
-    float dlt[135][13];                                       // FROM_CEP: delta   of times t0-3 .. t0+131 (clamped)
+    // FROM_CEP, channel-major so that lanes = consecutive time rows read / write consecutive words:
+    float cep[13][kCepStride];                                // cepstra of times t0-5 .. t0+133 (clamped into the clip)
+    float dlt[13][kCepStride];                                // delta   of times t0-3 .. t0+131 (those inside the clip)
     alignas(8) uint64_t wfull, aready, done;
     uint32_t tmem_base;
 };
@@ -156,6 +158,9 @@ __global__ void __launch_bounds__(kThreadsStem, 4) stem_fused_kernel(const float
                         make_uint4(st_tf32(v[i].x), st_tf32(v[i].y), st_tf32(v[i].z), st_tf32(v[i].w));
             }
         } else {
+            // (An earlier version looped over (row, channel) ELEMENTS with a division, five clamps and a three-way channel
+            //  test each: 61 instructions per feature element, the kernel was issue-bound at 0.129 ms.  Here a thread owns
+            //  a time row, clamps its neighbour indices once and walks the 13 channels with compile-time indices.)
             const int Tm1 = n_frames - 1;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -165,54 +170,73 @@ __global__ void __launch_bounds__(kThreadsStem, 4) stem_fused_kernel(const float
                     const float vv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (4 * q4 + u < 13) s.cep[rr][4 * q4 + u] = vv[u];
+                        if (4 * q4 + u < 13) s.cep[4 * q4 + u][rr] = vv[u];
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // delta of times t0-3 .. t0+131 that lie inside the clip: row dd <-> time t0 - 3 + dd; cep row of time t is
-            // t - (t0 - 5).  Every index below is a time already clamped into [0, T-1], and |clamped - requested| <= 2
-            // per level, so it stays inside the staged windows.
-            for (int i = tid; i < 135 * 13; i += 256) {
-                const int dd = i / 13, c = i - dd * 13;
+            // delta of times t0-3 .. t0+131 that lie inside the clip: row dd <-> time td = t0 - 3 + dd; the cep row of
+            // time t is t - (t0 - 5).  Neighbour times are clamped into [0, T-1] (the reference's edge replication) and
+            // |clamped - requested| <= 2, so they stay inside the staged window.  Work item = (row, channel half).
+            for (int it = tid; it < 2 * 135; it += 256) {
+                const int hi = it >= 135 ? 1 : 0;
+                const int dd = it - 135 * hi;
                 const int td = t0 - 3 + dd;
                 if (td < 0 || td > Tm1) continue;         // never read: consumers index by times clamped into [0, T-1]
-                float acc = 0.f;
+                const int base = 5 - t0;                  // cep row of time t = t + base
+                const int m2 = max(td - 2, 0) + base, m1 = max(td - 1, 0) + base;
+                const int p1 = min(td + 1, Tm1) + base, p2 = min(td + 2, Tm1) + base;
 #pragma unroll
-                for (int k = -2; k <= 2; ++k) {
-                    int tt = td + k;
-                    tt = tt < 0 ? 0 : (tt > Tm1 ? Tm1 : tt);
-                    acc = fmaf(static_cast<float>(k), s.cep[tt - (t0 - 5)][c], acc);
+                for (int cc = 0; cc < 7; ++cc) {
+                    const int c = cc + 7 * hi;            // channels [0,7) or [7,13)
+                    if (c < 13) {
+                        float acc = -2.f * s.cep[c][m2];
+                        acc = fmaf(-1.f, s.cep[c][m1], acc);
+                        acc = fmaf(1.f, s.cep[c][p1], acc);
+                        acc = fmaf(2.f, s.cep[c][p2], acc);
+                        s.dlt[c][dd] = acc * 0.1f;
+                    }
                 }
-                s.dlt[dd][c] = acc * 0.1f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // feature rows of times t0-1 .. t0+129 -> TF32 slabs; rows outside [0, T) are the zero padding
-            for (int idx = tid; idx < 131 * kQuads; idx += 256) {
-                const int r = idx / kQuads, q = idx - r * kQuads;
+            // feature rows of times t0-1 .. t0+129 -> TF32 slabs; rows outside [0, T) are the zero padding.
+            // Work item = (row r, channel third): MFCC | delta | delta-delta, 13 channels each; a third's channels are
+            // gathered into the 40-wide row with compile-time positions and stored as 16-byte slab entries.
+            for (int it = tid; it < 3 * 131; it += 256) {
+                const int third = it / 131;
+                const int r = it - 131 * third;
                 const int t = t0 - 1 + r;
-                float f[4] = {0.f, 0.f, 0.f, 0.f};
+                float f[13];
+#pragma unroll
+                for (int c = 0; c < 13; ++c) f[c] = 0.f;
                 if (t >= 0 && t <= Tm1) {
+                    if (third == 0) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ch = 4 * q + u;
-                        if (ch < 13) {
-                            f[u] = s.cep[t - (t0 - 5)][ch];
-                        } else if (ch < 26) {
-                            f[u] = s.dlt[t - (t0 - 3)][ch - 13];
-                        } else if (ch < 39) {
-                            float acc = 0.f;
+                        for (int c = 0; c < 13; ++c) f[c] = s.cep[c][t + 5 - t0];
+                    } else if (third == 1) {
 #pragma unroll
-                            for (int k = -2; k <= 2; ++k) {
-                                int tt = t + k;
-                                tt = tt < 0 ? 0 : (tt > Tm1 ? Tm1 : tt);
-                                acc = fmaf(static_cast<float>(k), s.dlt[tt - (t0 - 3)][ch - 26], acc);
-                            }
-                            f[u] = acc * 0.1f;
+                        for (int c = 0; c < 13; ++c) f[c] = s.dlt[c][t + 3 - t0];
+                    } else {
+                        const int base = 3 - t0;              // dlt row of time t = t + base
+                        const int m2 = max(t - 2, 0) + base, m1 = max(t - 1, 0) + base;
+                        const int p1 = min(t + 1, Tm1) + base, p2 = min(t + 2, Tm1) + base;
+#pragma unroll
+                        for (int c = 0; c < 13; ++c) {
+                            float acc = -2.f * s.dlt[c][m2];
+                            acc = fmaf(-1.f, s.dlt[c][m1], acc);
+                            acc = fmaf(1.f, s.dlt[c][p1], acc);
+                            acc = fmaf(2.f, s.dlt[c][p2], acc);
+                            f[c] = acc * 0.1f;
                         }
                     }
                 }
-                *reinterpret_cast<uint4*>(&s.ab[0] + (q * kRows + r) * 16) =
-                    make_uint4(st_tf32(f[0]), st_tf32(f[1]), st_tf32(f[2]), st_tf32(f[3]));
+                // channel ch = 13*third + c lives in slab quad ch/4, element ch%4: scalar 4-byte stores (lanes = rows,
+                // 16 B apart: 4-way conflicts at worst, 39 stores per row instead of 10 gathers of mixed origin)
+#pragma unroll
+                for (int c = 0; c < 13; ++c) {
+                    const int ch = 13 * third + c;        // third is warp-uniform except at the two seams
+                    *reinterpret_cast<uint32_t*>(&s.ab[0] + ((ch >> 2) * kRows + r) * 16 + (ch & 3) * 4) = st_tf32(f[c]);
+                }
+                if (third == 2) *reinterpret_cast<uint32_t*>(&s.ab[0] + (9 * kRows + r) * 16 + 12) = 0u;   // channel 39
             }
         }
         fence_proxy_async_smem();
