@@ -303,6 +303,25 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ hf,
         __syncwarp();
         float* pr = prob + b * n_classes;
         float vmax = -INFINITY;
+        if (n_classes <= 32) {
+            // few classes (the transferred speaker heads, the 2-way overlap head): the 32 lanes split K instead of
+            // 10 lanes walking 512 dependent FMAs each; lane n ends up with logit n
+            float zr[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) zr[k] = z[lane + 32 * k];
+            float mine = 0.f;
+            for (int n = 0; n < n_classes; ++n) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc = fmaf(zr[k], __ldg(wk + static_cast<long long>(lane + 32 * k) * n_classes + n), acc);
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == n) mine = acc + wb[n];
+            }
+            if (lane < n_classes) {
+                pr[lane] = mine;                                    // logits for now
+                vmax = mine;
+            }
+        } else
         for (int n = lane; n < n_classes; n += 32) {
             float acc = 0.f;
             for (int i = 0; i < 512; ++i) acc = fmaf(z[i], wk[static_cast<long long>(i) * n_classes + n], acc);

@@ -56,6 +56,9 @@ struct StageArgs {
     const float* fin_scale; const float* fin_shift;
     float* pooled;
     int B, T, G;                           // T = OUTPUT time steps
+    // tile -> CTA map: CTAs [0, n_full) own kTiles tiles each (whole waves); the rest own tail_tiles (<= kTiles) each,
+    // so the last wave is not a wave of full-size CTAs on a fraction of the SMs
+    int n_full, tail_tiles, n_tiles;
     long long* stamps;                     // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
     int stamp_cta;
 };
@@ -157,7 +160,10 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
     Smem& s = *reinterpret_cast<Smem*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = a.G, T = a.T;
-    const int clip_base = blockIdx.x * kTiles * G;               // tile j holds clips [clip_base + j*G, +G)
+    const int bx = static_cast<int>(blockIdx.x);
+    const int tile0 = bx < a.n_full ? bx * kTiles : a.n_full * kTiles + (bx - a.n_full) * a.tail_tiles;
+    const int nt = bx < a.n_full ? kTiles : min(a.tail_tiles, a.n_tiles - tile0);   // this CTA's tiles (warp-uniform)
+    const int clip_base = tile0 * G;                             // tile j holds clips [clip_base + j*G, +G)
 
     if (tid == 0) {
         for (int i = 0; i < kStagesTot; ++i) {
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         if (lane == 0) {
             if (Cfg::kTmaX) {
                 const int clip_floats = 2 * T * CIN;
-                for (int j = 0; j < kTiles; ++j) {
+                for (int j = 0; j < nt; ++j) {
                     const int clip0 = clip_base + j * G;
                     const int valid = a.B - clip0 < G ? (a.B - clip0 < 0 ? 0 : a.B - clip0) : G;
                     if (valid > 0) {
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         // ---- shortcut: raw x[2t] x Ws initialises the running-y accumulator of each tile as its operand arrives;
         //      the Ws chunks (ring slots 0..kChunksS-1) are released after the last tile has used them ----
 #pragma unroll 1
-        for (int j = 0; j < kTiles; ++j) {
+        for (int j = 0; j < nt; ++j) {
             rs_wait(&s.a0_ready, static_cast<uint32_t>(j & 1));
             if (j == 0)
                 for (int c = 0; c < kChunksS; ++c) rs_wait(&s.full[c], 0u);
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                     }
                 }
                 rs_commit(&s.a0_free);
-                if (j == kTiles - 1) {
+                if (j == nt - 1) {
                     for (int c = 0; c < kChunksS; ++c) rs_commit(&s.empty[c]);
                     rs_commit(&s.short_done);
                 }
@@ -280,6 +286,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
             if (rs_elect_one()) {
 #pragma unroll
                 for (int j = 0; j < kTiles; ++j) {
+                    if (j >= nt) break;
 #pragma unroll
                     for (int kk = 0; kk < kChunkK / 8; ++kk) {
                         const uint64_t ad = ad0 + static_cast<uint64_t>(j * kTileUnits + 2 * kk * kRtotS);
@@ -410,11 +417,12 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
             }
         };
         if (!Cfg::kTmaX)
-            for (int j = 0; j < kTiles; ++j) zero_halo(j);
+            for (int j = 0; j < nt; ++j) zero_halo(j);
         // ---- per tile: raw x[2t] -> shortcut operand; ReLU(BN1(max(x[2t], x[2t+1]))) -> conv1 operand ----
         unsigned char* a0 = &s.ring[kStages * kChunkBytes];
 #pragma unroll
         for (int j = 0; j < kTiles; ++j) {
+            if (j >= nt) break;
             if (Cfg::kTmaX) {
                 rs_wait(&s.x_full[j], 0u);
                 RS_READ_TILE(j)
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                     make_uint4(rs_tf32(fmaxf(fmaf(p.x, sc1.x, sh1.x), 0.f)), rs_tf32(fmaxf(fmaf(p.y, sc1.y, sh1.y), 0.f)),
                                rs_tf32(fmaxf(fmaf(p.z, sc1.z, sh1.z), 0.f)), rs_tf32(fmaxf(fmaf(p.w, sc1.w, sh1.w), 0.f)));
             }
-            if (!Cfg::kTmaX && j + 1 < kTiles) RS_LOAD_TILE(j + 1)  // latency overlaps the barrier round trip below
+            if (!Cfg::kTmaX && j + 1 < nt) RS_LOAD_TILE(j + 1)  // latency overlaps the barrier round trip below
             fence_proxy_async_smem();
             rs_epi_sync();
             if (tid == 0) rs_arrive(&s.a0_ready);
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         // accumulator block `dcol` of every tile -> * scale + shift -> ReLU -> TF32 -> that tile's operand buffer
         auto to_operand = [&](uint32_t dcol, const float* scale, const float* shift) {
 #pragma unroll 1
-            for (int j = 0; j < kTiles; ++j) {
+            for (int j = 0; j < nt; ++j) {
                 uint32_t z[kColsPerWarp];
                 ld_cols(trow + dcol + static_cast<uint32_t>(j * 2 * C + cbase), z);
 #pragma unroll
@@ -508,7 +516,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         // ---- last epilogue: y_2 -> staging (operand buffers are dead) -> coalesced 128-bit stores ----
         constexpr int kStride = C + 4;                            // floats per staged row (conflict-free STS/LDS.128)
 #pragma unroll 1
-        for (int j = 0; j < kTiles; ++j) {
+        for (int j = 0; j < nt; ++j) {
             float* stg = reinterpret_cast<float*>(&s.ab[j][0]);
             uint32_t z[kColsPerWarp];
             ld_cols(trow + static_cast<uint32_t>(j * 2 * C + C + cbase), z);
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
             const float4 fsh = *reinterpret_cast<const float4*>(a.fin_shift + 4 * q);
             const int To = T / 4;
 #pragma unroll 1
-            for (int idx = tid; idx < kTiles * 32 * kQuads; idx += kEpiS) {
+            for (int idx = tid; idx < nt * 32 * kQuads; idx += kEpiS) {
                 const int j = idx / (32 * kQuads), pr = (idx / kQuads) % 32;
                 const int to = pr / G, gg = pr - to * G;
                 const int clip = clip_base + j * G + gg;
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
             const int j = idx >> 7, r = idx & 127;
             const int t = r / G, gg = r - t * G;
             const int clip = clip_base + j * G + gg;
-            if (clip < a.B) {
+            if (j < nt && clip < a.B) {
                 float* dst = a.y + (static_cast<long long>(clip) * T + t) * C;
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                              "r"(smem_u32(&s.ab[j][0] + r * kStride * 4)), "r"(static_cast<uint32_t>(C * 4))
@@ -591,9 +599,16 @@ int launch_stage(const StageArgs& a, cudaStream_t st) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(resstage_fused_kernel<CIN, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const long long tiles = (a.B + a.G - 1) / a.G;
-    const unsigned grid = static_cast<unsigned>((tiles + StageCfg<CIN, C>::kTiles - 1) / StageCfg<CIN, C>::kTiles);
-    resstage_fused_kernel<CIN, C><<<grid, kThreadsS, smem, st>>>(a);
+    constexpr int kTilesCta = StageCfg<CIN, C>::kTiles;
+    StageArgs b = a;
+    const int tiles = (a.B + a.G - 1) / a.G;
+    const int slots = mmla_num_sms() * StageCfg<CIN, C>::kMinCtas;             // CTAs resident at once
+    b.n_tiles = tiles;
+    b.n_full = (tiles / (slots * kTilesCta)) * slots;                          // whole waves of full-size CTAs
+    const int rest = tiles - b.n_full * kTilesCta;
+    b.tail_tiles = rest > 0 ? (rest + slots - 1) / slots : 1;                   // <= kTilesCta
+    const unsigned grid = static_cast<unsigned>(b.n_full + (rest + b.tail_tiles - 1) / b.tail_tiles);
+    resstage_fused_kernel<CIN, C><<<grid, kThreadsS, smem, st>>>(b);
     mmla_count_launch("resstage_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
