@@ -65,10 +65,10 @@ struct StageArgs {
 
 template <int CIN, int C>
 struct StageCfg {
-    static constexpr int kTiles = C == 64 ? 4 : 2;             // 128-row tiles per CTA
+    static constexpr int kTiles = 2;                           // 128-row tiles per CTA
     static constexpr int kChunkK = 32;                         // K per ring chunk
-    static constexpr int kStages = C == 32 ? 4 : (C == 64 ? 8 : 3);
-    static constexpr int kMinCtas = C == 32 ? 3 : 1;
+    static constexpr int kStages = C == 32 ? 4 : (C == 64 ? 2 : 3);
+    static constexpr int kMinCtas = C == 32 ? 3 : (C == 64 ? 2 : 1);
     static constexpr int kChunkBytes = kChunkK * C * 4;
     // raw x[2t] of ONE tile (shortcut GEMM operand): slabs of 129 rows — with 128, the loader's lanes (which run over
     // channel quads for coalesced global loads) would all hit the same banks (16-way conflict, measured 4k cycles/tile)
@@ -81,7 +81,7 @@ struct StageCfg {
     static constexpr int kTileBytes = ((kSlabBytes > kStageTileBytes ? kSlabBytes : kStageTileBytes) + 127) / 128 * 128;
     // With one CTA per SM the raw x tile ([G clips][2T rows][CIN] fp32, contiguous in HBM) is fetched by ONE bulk copy
     // per tile into that tile's (still empty) operand buffer, all tiles in flight from the first cycle of the CTA.
-    static constexpr bool kTmaX = kMinCtas == 1;
+    static constexpr bool kTmaX = C >= 64;
     static constexpr int kRawTileBytes = 256 * CIN * 4;
     static_assert(!kTmaX || kRawTileBytes <= kTileBytes, "raw x tile is staged in the operand buffer");
 };
