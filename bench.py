@@ -224,8 +224,9 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     # classifier convolutions: 2 FLOP per multiply-add, Keras 'same' output sizes
     h, w_ = H0, T0
     res = 0.0
+    res_first_stage = 0.0                        # the first three residual units (the stage the stem is folded into)
     stem = 2.0 * h * w_ * spec.stem.kh * spec.stem.kw * spec.stem.cin * spec.stem.cout
-    for blk in spec.blocks:
+    for bi, blk in enumerate(spec.blocks):
         if blk.pool:
             h2, w2 = (-(-h // 2) if spec.ndim == 2 else h), -(-w_ // 2)
         else:
@@ -239,6 +240,8 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         if blk.shortcut is not None:
             res += 2.0 * h2 * w2 * blk.shortcut.cin * blk.shortcut.cout
         h, w_ = h2, w2
+        if bi == 2:
+            res_first_stage = res
     t_lstm = w_ if spec.ndim == 2 else w_ // 4                       # mean over H (overlap) / AvgPool1D(4) (speaker)
     feat = spec.blocks[-1].conv2.cout
     xproj = 2.0 * 2 * t_lstm * feat * 1024
@@ -249,8 +252,11 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     conv_flop = B * (stem + res + xproj)
     if spec.ndim == 1:
         work["resunit_fused_kernel"] = {"bound": "tensor", "per_step": B * res, "what": "the 9 residual units (18 convs + 3 shortcuts)"}
-        work["resstage_fused_kernel"] = {"bound": "tensor", "per_step": B * res,
-                                         "what": "the 3 ResNet stages = 9 residual units (18 convs + 3 shortcuts), TF32"}
+        work["resstage_fused_kernel"] = {"bound": "tensor", "per_step": B * (res - res_first_stage),
+                                         "what": "ResNet stages 2 and 3 = 6 residual units (12 convs + 2 shortcuts), TF32"}
+        work["stem_resstage_fused_kernel"] = {"bound": "tensor", "per_step": B * (stem + res_first_stage),
+                                              "what": "stem Conv1D(32,4) + ResNet stage 1 (3 residual units), features built "
+                                                      "from the MFCC-13 rows, TF32"}
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * xproj, "what": "both LSTM input projections"}
 
         work["stem_fused_kernel"] = {"bound": "hbm", "per_step": B * 256 * (40 + 32) * 4,

@@ -392,6 +392,7 @@ struct MmlaNet {
     long long per_clip_floats = 0;        // workspace floats per clip
     int micro = 0;                        // clips per micro-batch
     bool fuse_stages = true;              // speaker, TF32: one launch per ResNet stage (MMLA_NET_FUSE_STAGES=0: per unit)
+    bool fuse_stem = true;                // ... and the stem inside the first stage when the input is MFCC-13 rows (MMLA_NET_FUSE_STEM=0: own launch)
 };
 
 // conv_tc.cu
@@ -406,6 +407,9 @@ int mmla_launch_stem_from_cepstra(const float* cep, long long cep_clip_stride, i
 int mmla_launch_resstage_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* const (*p)[8],
                                const float* ws, const float* bs, const float* fin_scale, const float* fin_shift,
                                float* pooled, cudaStream_t st);
+int mmla_launch_resstage_stem_fused(const float* cepstra, long long cep_clip_stride, int n_frames, const float* stem_w,
+                                    const float* stem_b, float* y, long long B, const float* const (*p)[8], const float* ws,
+                                    const float* bs, cudaStream_t st);
 int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int Cin, int C, const float* bn1_scale,
                               const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                               const float* bn2_shift, const float* w2, const float* b2, const float* ws, const float* bs,
@@ -642,6 +646,7 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
         if (v > 0) net->micro = v;
     }
     if (const char* e = getenv("MMLA_NET_FUSE_STAGES")) net->fuse_stages = atoi(e) != 0;
+    if (const char* e = getenv("MMLA_NET_FUSE_STEM")) net->fuse_stem = atoi(e) != 0;
     *out_net = net;
     return MMLA_OK;
 }
@@ -717,7 +722,16 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         int cur = 0;
         int rc;
         bool seq_done = false;
-        if (from_cep) {
+        // label pipeline: the stem runs inside the first stage's kernel (resstage_fused.cu, STEM variant)
+        auto unit_tc = [&](const BlockW& k) { return k.conv1.k_tc && k.conv2.k_tc && (!k.pool || k.shortcut.k_tc); };
+        const bool stem_in_stage = from_cep && tc && !ov && net->fuse_stages && net->fuse_stem && net->stem_pad.k_tc &&
+                                   net->blocks.size() >= 3 && net->blocks[0].pool && !net->blocks[1].pool && !net->blocks[2].pool &&
+                                   unit_tc(net->blocks[0]) && unit_tc(net->blocks[1]) && unit_tc(net->blocks[2]) &&
+                                   net->blocks[0].conv1.cin == 32 && net->blocks[0].conv1.cout == 32 &&
+                                   net->blocks[1].conv1.cin == 32 && net->blocks[2].conv1.cin == 32 && W == 256;
+        if (stem_in_stage) {
+            rc = 0;
+        } else if (from_cep) {
             rc = mmla_launch_stem_from_cepstra(static_cast<const float*>(xin), cep_clip_stride, cep_frames, net->stem_pad.k_tc,
                                                net->stem_pad.b, buf[cur], B, st);                     // stem_fused.cu
         } else if (tc && !ov && net->stem_pad.k_tc) {
@@ -750,6 +764,7 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 // a whole ResNet stage (pooled unit + two plain units) in ONE launch: the activations between the
                 // units stay in shared memory (resunit_fused.cu, stage mode)
                 const int Wo = same_out(W, 2);
+                const bool with_stem = stem_in_stage && bi == 0;
                 const float* prm[3][8];
                 for (int u = 0; u < 3; ++u) {
                     const BlockW& k = net->blocks[bi + u];
@@ -758,10 +773,15 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 }
                 // the last stage also applies the net's tail (BN -> ReLU -> AveragePooling1D(4)) and writes `seq` directly
                 const bool tail = bi + 3 == net->blocks.size() && Wo % 4 == 0 && blk.conv1.cout == 128;
-                if ((rc = mmla_launch_resstage_fused(X, A, B, Wo, blk.conv1.cin, blk.conv1.cout, prm, blk.shortcut.k_tc,
-                                                     blk.shortcut.b, tail ? net->final_bn.scale : nullptr,
-                                                     tail ? net->final_bn.shift : nullptr, tail ? seq : nullptr, st)))
-                    return rc;
+                if (with_stem)
+                    rc = mmla_launch_resstage_stem_fused(static_cast<const float*>(xin), cep_clip_stride, cep_frames,
+                                                         net->stem_pad.k_tc, net->stem_pad.b, A, B, prm, blk.shortcut.k_tc,
+                                                         blk.shortcut.b, st);
+                else
+                    rc = mmla_launch_resstage_fused(X, A, B, Wo, blk.conv1.cin, blk.conv1.cout, prm, blk.shortcut.k_tc,
+                                                    blk.shortcut.b, tail ? net->final_bn.scale : nullptr,
+                                                    tail ? net->final_bn.shift : nullptr, tail ? seq : nullptr, st);
+                if (rc) return rc;
                 seq_done = tail;
                 W = Wo;
                 cur = (cur + 1) % 3;

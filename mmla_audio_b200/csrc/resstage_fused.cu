@@ -61,14 +61,30 @@ struct StageArgs {
     int n_full, tail_tiles, n_tiles;
     long long* stamps;                     // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
     int stamp_cta;
+    // STEM variant (first stage, label pipeline): x is not read; the stem Conv1D(32, 4) runs in here from the MFCC-13 rows
+    const float* cep;                      // [B][>= n_frames rows][16] fp32
+    long long cep_clip_stride;             // floats
+    int n_frames;                          // T of the clip's features (<= 256); rows beyond are the zero padding
+    const float* stem_w;                   // conv_tc-arranged [4 taps x 10 quads][32][4] TF32
+    const float* stem_b;                   // [32]
 };
 
-template <int CIN, int C>
+// Stem region of the STEM variant, laid over [ab | ring | stem_extra] (all dead once the stem MMAs have retired):
+constexpr int kStemFRows = 137;                                // feature slab rows: pooled time t = -1 .. 128 (+ bank padding)
+constexpr int kStemFBytes = (10 * kStemFRows * 16 + 127) / 128 * 128;   // one parity's slab [10 quads][rows][16 B]
+constexpr int kStemWBytes = 4 * 40 * 32 * 4;                   // 20480
+constexpr int kStemCepStride = 264;                            // >= 256 frames
+constexpr int kStemCepBytes = (13 * kStemCepStride * 4 + 127) / 128 * 128;
+constexpr int kStemOffFe = 0, kStemOffFo = kStemFBytes, kStemOffW = 2 * kStemFBytes, kStemOffCep = kStemOffW + kStemWBytes,
+              kStemOffDlt = kStemOffCep + kStemCepBytes, kStemBytes = kStemOffDlt + kStemCepBytes;
+
+template <int CIN, int C, bool STEM = false>
 struct StageCfg {
+    static_assert(!STEM || (CIN == 32 && C == 32), "the stem feeds the first stage");
     static constexpr int kTiles = 2;                           // 128-row tiles per CTA
     static constexpr int kChunkK = 32;                         // K per ring chunk
     static constexpr int kStages = C == 32 ? 4 : (C == 64 ? 2 : 3);
-    static constexpr int kMinCtas = C == 32 ? 3 : (C == 64 ? 2 : 1);
+    static constexpr int kMinCtas = STEM ? 2 : (C == 32 ? 3 : (C == 64 ? 2 : 1));
     static constexpr int kChunkBytes = kChunkK * C * 4;
     // raw x[2t] of ONE tile (shortcut GEMM operand): slabs of 129 rows — with 128, the loader's lanes (which run over
     // channel quads for coalesced global loads) would all hit the same banks (16-way conflict, measured 4k cycles/tile)
@@ -86,13 +102,17 @@ struct StageCfg {
     static_assert(!kTmaX || kRawTileBytes <= kTileBytes, "raw x tile is staged in the operand buffer");
 };
 
-template <int CIN, int C>
+template <int CIN, int C, bool STEM = false>
 struct StageSmem {
-    using Cfg = StageCfg<CIN, C>;
+    using Cfg = StageCfg<CIN, C, STEM>;
     alignas(128) unsigned char ab[Cfg::kTiles][Cfg::kTileBytes];   // per tile: the current MMA A operand / output staging
     // weight ring; its last kExtra stages double as `a0`, the shortcut GEMM's operand (raw x[2t] of one tile), and
     // join the ring when the last shortcut MMA has retired (short_done)
     alignas(128) unsigned char ring[Cfg::kStages * Cfg::kChunkBytes + Cfg::kA0Bytes];
+    static constexpr int kMainBytes = Cfg::kTiles * Cfg::kTileBytes + Cfg::kStages * Cfg::kChunkBytes + Cfg::kA0Bytes;
+    static_assert(kMainBytes % 128 == 0, "ab | ring | stem_extra are contiguous");
+    alignas(128) unsigned char stem_extra[STEM ? (kStemBytes > kMainBytes ? kStemBytes - kMainBytes : 128) : 128];
+    alignas(16) float prm0[3][C];          // STEM: stem bias, BN1 scale, BN1 shift of unit 0
     // per unit: [0] BN2 scale, [1] BN2 shift + b1*scale  (epilogue 1: ReLU(BN2(acc1 + b1)) = ReLU(acc1*[0] + [1]));
     //           [2] next BN1 scale, [3] next BN1 shift + run_u*scale, run_u = bs + b2_0 + .. + b2_u  (epilogue 2);
     //           [4] run_u  (y_u = acc2 + run_u, used by the final store)
@@ -104,6 +124,7 @@ struct StageSmem {
     alignas(8) uint64_t x_full[Cfg::kTiles];   // raw x tile landed (kTmaX)
     alignas(8) uint64_t a_ready[2];        // operand buffers written   (epilogue -> MMA): conv1, conv2
     alignas(8) uint64_t tfull[2];          // accumulators complete     (MMA -> epilogue): conv1, conv2
+    alignas(8) uint64_t stem_wfull, f_ready, f_free, stem_done;   // STEM: weights landed / feature slabs built / consumed / all done
     uint32_t tmem_base;
 };
 
@@ -136,10 +157,10 @@ __device__ __forceinline__ void rs_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int CIN, int C>
-__global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstage_fused_kernel(const __grid_constant__ StageArgs a) {
-    using Cfg = StageCfg<CIN, C>;
-    using Smem = StageSmem<CIN, C>;
+template <int CIN, int C, bool STEM>
+__global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C, STEM>::kMinCtas) resstage_fused_kernel(const __grid_constant__ StageArgs a) {
+    using Cfg = StageCfg<CIN, C, STEM>;
+    using Smem = StageSmem<CIN, C, STEM>;
     constexpr int kTiles = Cfg::kTiles;
     constexpr int kQuads = C / 4;
     constexpr int kQuadsIn = CIN / 4;
@@ -178,6 +199,10 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         }
         mbar_init(&s.a0_ready, 1);
         mbar_init(&s.a0_free, 1);
+        mbar_init(&s.stem_wfull, 1);
+        mbar_init(&s.f_ready, 1);
+        mbar_init(&s.f_free, 1);
+        mbar_init(&s.stem_done, 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -198,6 +223,12 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
     if (warp == 8) {
         // ================= TMA producer: shortcut, then per unit conv1 and conv2 weight chunks =================
         if (lane == 0) {
+            if (STEM) {
+                // stem weights first; the ring shares their bytes and starts when the last stem MMA has retired
+                mbar_arrive_expect_tx(&s.stem_wfull, kStemWBytes);
+                tma_bulk_g2s(&s.ab[0][0] + kStemOffW, a.stem_w, kStemWBytes, &s.stem_wfull);
+                rs_wait(&s.stem_done, 0u);
+            }
             if (Cfg::kTmaX) {
                 const int clip_floats = 2 * T * CIN;
                 for (int j = 0; j < nt; ++j) {
@@ -240,6 +271,51 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         const uint64_t dB0 = rs_desc(smem_u32(&s.ring[0]), C * 16, 128);
         constexpr uint32_t kStageUnits = Cfg::kChunkBytes / 16;      // descriptor address units per ring stage
         constexpr uint32_t kTileUnits = Cfg::kTileBytes / 16;        // ... per tile operand buffer
+        if (STEM) {
+            // ---- stem: Conv1D(32, 4, 'same') of the clip's [256, 40] feature rows, split by output-row parity so that
+            //      both x[2t] (-> TMEM columns of acc1) and x[2t+1] (-> acc2) come out with TMEM lane = pooled time t:
+            //        x[2t]   = W0 f[2t-1] + W1 f[2t]   + W2 f[2t+1] + W3 f[2t+2]
+            //        x[2t+1] = W0 f[2t]   + W1 f[2t+1] + W2 f[2t+2] + W3 f[2t+3]
+            //      with the features de-interleaved into Fe[t] = f[2t], Fo[t] = f[2t+1] (slab row = t + 1) every tap is a
+            //      whole-slab row shift again.  The max-pool and the shortcut operand then need no cross-lane traffic.
+            const uint64_t dFe = rs_desc(smem_u32(&s.ab[0][0] + kStemOffFe), kStemFRows * 16, 128);
+            const uint64_t dFo = rs_desc(smem_u32(&s.ab[0][0] + kStemOffFo), kStemFRows * 16, 128);
+            const uint64_t dW = rs_desc(smem_u32(&s.ab[0][0] + kStemOffW), C * 16, 128);
+            rs_wait(&s.stem_wfull, 0u);
+#pragma unroll 1
+            for (int j = 0; j < nt; ++j) {
+                rs_wait(&s.f_ready, static_cast<uint32_t>(j & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (rs_elect_one()) {
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {            // output row parity: 0 -> acc1 columns, 1 -> acc2 columns
+                        const uint32_t dcol = tmem + static_cast<uint32_t>(j * 2 * C + par * C);
+#pragma unroll
+                        for (int tap = 0; tap < 4; ++tap) {
+                            // feature index 2t + par + tap - 1 = 2 (t + sh) + odd  ->  slab Fo/Fe, start row t + sh + 1
+                            const int e = par + tap - 1;           // -1 .. 3
+                            const int odd = e & 1;
+                            const int sh = (e - odd) / 2;          // -1, 0, 1
+                            const uint64_t dF = odd ? dFo : dFe;
+#pragma unroll
+                            for (int kq = 0; kq < 5; ++kq) {
+                                const uint64_t ad = dF + static_cast<uint64_t>(2 * kq * kStemFRows + sh + 1);
+                                const uint64_t bd = dW + static_cast<uint64_t>((tap * 10 + 2 * kq) * C);
+                                const uint32_t acc = (tap | kq) != 0 ? 1u : 0u;
+                                asm volatile(
+                                    "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol),
+                                    "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                                    : "memory");
+                            }
+                        }
+                    }
+                    rs_commit(&s.f_free);
+                    if (j == nt - 1) rs_commit(&s.stem_done);
+                }
+                __syncwarp();
+            }
+        }
         // ---- shortcut: raw x[2t] x Ws initialises the running-y accumulator of each tile as its operand arrives;
         //      the Ws chunks (ring slots 0..kChunksS-1) are released after the last tile has used them ----
 #pragma unroll 1
@@ -380,7 +456,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
         }                                                                                                                \
     }
         if (tid == 0) stamp(16);
-        if (!Cfg::kTmaX) RS_LOAD_TILE(0)
+        if (!STEM && !Cfg::kTmaX) RS_LOAD_TILE(0)
         const float4 sc1 = *reinterpret_cast<const float4*>(a.u[0].bn1_scale + 4 * qd);
         const float4 sh1 = *reinterpret_cast<const float4*>(a.u[0].bn1_shift + 4 * qd);
         // Parameters: all global loads first, then the shared stores.  (Interleaved, every load has to wait for the
@@ -394,6 +470,11 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                 pb1[u] = __ldg(a.u[u].b1 + i); pb2[u] = __ldg(a.u[u].b2 + i);
                 ps1[u] = __ldg(a.u[u].bn1_scale + i); ph1[u] = __ldg(a.u[u].bn1_shift + i);
                 ps2[u] = __ldg(a.u[u].bn2_scale + i); ph2[u] = __ldg(a.u[u].bn2_shift + i);
+            }
+            if (STEM) {
+                s.prm0[0][i] = __ldg(a.stem_b + i);
+                s.prm0[1][i] = ps1[0];
+                s.prm0[2][i] = ph1[0];
             }
             float run = pbs;
 #pragma unroll
@@ -416,10 +497,177 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                 *reinterpret_cast<uint4*>(&s.ab[j][0] + (q * kRtotS + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
             }
         };
-        if (!Cfg::kTmaX)
+        if (!STEM && !Cfg::kTmaX)
             for (int j = 0; j < nt; ++j) zero_halo(j);
-        // ---- per tile: raw x[2t] -> shortcut operand; ReLU(BN1(max(x[2t], x[2t+1]))) -> conv1 operand ----
         unsigned char* a0 = &s.ring[kStages * kChunkBytes];
+        if (STEM) {
+            // ================= stem, phase A: per clip, MFCC-13 rows -> delta, delta-delta -> parity-split feature slabs ======
+            // (G = 1: a tile is one clip.)  Same arithmetic as stem_fused.cu's FROM_CEP path — `delta(feat, 2)` of
+            // speaker_identification.py:141-151 with edge replication inside the clip's T frames, zero rows from T to 256.
+            unsigned char* R = &s.ab[0][0];
+            float (*cep)[kStemCepStride] = reinterpret_cast<float (*)[kStemCepStride]>(R + kStemOffCep);
+            float (*dlt)[kStemCepStride] = reinterpret_cast<float (*)[kStemCepStride]>(R + kStemOffDlt);
+            const int Tn = a.n_frames, Tm1 = Tn - 1;
+            // rows 0 (t = -1) and 129 (t = 128) of both slabs are the conv's zero padding; nothing below rewrites them
+            for (int i = tid; i < 2 * 2 * 10; i += kEpiS) {
+                const int par = i / 20, rem = i - 20 * par;
+                const int q = rem >> 1, row = (rem & 1) ? 129 : 0;
+                *reinterpret_cast<uint4*>(R + (par ? kStemOffFo : kStemOffFe) + (q * kStemFRows + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            // cepstra rows of BOTH clips are fetched up front (<= 256 rows x 4 float4 = 4 per thread and clip): one exposed
+            // HBM latency per CTA
+            float4 cv[kTiles][4];
+#pragma unroll
+            for (int j = 0; j < kTiles; ++j) {
+                const int clip = clip_base + j;
+                const float* cc = a.cep + static_cast<long long>(j < nt && clip < a.B ? clip : 0) * a.cep_clip_stride;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int idx = tid + i * kEpiS;
+                    cv[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < nt && idx < Tn * 4) cv[j][i] = *reinterpret_cast<const float4*>(cc + static_cast<long long>(idx >> 2) * 16 + 4 * (idx & 3));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kTiles; ++j) {
+                if (j >= nt) break;
+                const int clip = clip_base + j;
+                const bool live = clip < a.B;
+                // cepstra rows 0 .. T-1 (16-float rows, 13 used), channel-major so that lanes = consecutive frames
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int idx = tid + i * kEpiS;
+                    const int rr = idx >> 2, q4 = idx & 3;
+                    if (idx < Tn * 4) {
+                        const float e[4] = {cv[j][i].x, cv[j][i].y, cv[j][i].z, cv[j][i].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (4 * q4 + u < 13) cep[4 * q4 + u][rr] = e[u];
+                    }
+                }
+                rs_epi_sync();
+                {   // delta: one thread per frame
+                    const int td = tid;
+                    if (td < Tn) {
+                        const int m2 = max(td - 2, 0), m1 = max(td - 1, 0), p1 = min(td + 1, Tm1), p2 = min(td + 2, Tm1);
+#pragma unroll
+                        for (int c = 0; c < 13; ++c) {
+                            float acc = -2.f * cep[c][m2];
+                            acc = fmaf(-1.f, cep[c][m1], acc);
+                            acc = fmaf(1.f, cep[c][p1], acc);
+                            acc = fmaf(2.f, cep[c][p2], acc);
+                            dlt[c][td] = acc * 0.1f;
+                        }
+                    }
+                }
+                rs_epi_sync();
+                if (j > 0) rs_wait(&s.f_free, static_cast<uint32_t>((j - 1) & 1));   // stem MMAs of clip j-1 retired
+                // feature rows 0 .. T-1 of the clip's [256, 40] tensor -> slab of the row's parity, slab row sI/2 + 1.  Work
+                // item = (row, third of the channels: MFCC | delta | delta-delta): 3T items over 256 threads, so the longest
+                // thread does 2 items instead of 39 channels.  Rows T .. 255 (zero padding) are written once: the slabs
+                // are reused by the CTA's next clip and n_frames is the same for all clips.
+                if (j == 0) {
+                    for (int i = tid; i < (256 - Tn) * 10; i += kEpiS) {
+                        const int q = i % 10, sI = Tn + i / 10;
+                        *reinterpret_cast<uint4*>(R + ((sI & 1) ? kStemOffFo : kStemOffFe) + (q * kStemFRows + (sI >> 1) + 1) * 16) =
+                            make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                for (int it = tid; it < 3 * Tn; it += kEpiS) {
+                    const int third = (it >= Tn ? 1 : 0) + (it >= 2 * Tn ? 1 : 0);
+                    const int sI = it - third * Tn;
+                    unsigned char* F = R + ((sI & 1) ? kStemOffFo : kStemOffFe) + ((sI >> 1) + 1) * 16;
+                    float f[13];
+                    if (!live) {
+#pragma unroll
+                        for (int c = 0; c < 13; ++c) f[c] = 0.f;
+                    } else if (third == 0) {
+#pragma unroll
+                        for (int c = 0; c < 13; ++c) f[c] = cep[c][sI];
+                    } else if (third == 1) {
+#pragma unroll
+                        for (int c = 0; c < 13; ++c) f[c] = dlt[c][sI];
+                    } else {
+                        const int m2 = max(sI - 2, 0), m1 = max(sI - 1, 0), p1 = min(sI + 1, Tm1), p2 = min(sI + 2, Tm1);
+#pragma unroll
+                        for (int c = 0; c < 13; ++c) {
+                            float acc = -2.f * dlt[c][m2];
+                            acc = fmaf(-1.f, dlt[c][m1], acc);
+                            acc = fmaf(1.f, dlt[c][p1], acc);
+                            acc = fmaf(2.f, dlt[c][p2], acc);
+                            f[c] = acc * 0.1f;
+                        }
+                    }
+                    // channel ch = 13 third + c -> quad ch/4, element ch%4 (compile-time per branch)
+                    if (third == 0) {
+#pragma unroll
+                        for (int c = 0; c < 13; ++c)
+                            *reinterpret_cast<uint32_t*>(F + (c >> 2) * (kStemFRows * 16) + (c & 3) * 4) = rs_tf32(f[c]);
+                    } else if (third == 1) {
+#pragma unroll
+                        for (int c = 0; c < 13; ++c)
+                            *reinterpret_cast<uint32_t*>(F + ((13 + c) >> 2) * (kStemFRows * 16) + ((13 + c) & 3) * 4) = rs_tf32(f[c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 13; ++c)
+                            *reinterpret_cast<uint32_t*>(F + ((26 + c) >> 2) * (kStemFRows * 16) + ((26 + c) & 3) * 4) = rs_tf32(f[c]);
+                        *reinterpret_cast<uint32_t*>(F + 9 * (kStemFRows * 16) + 12) = 0u;     // channel 39
+                    }
+                }
+                fence_proxy_async_smem();
+                rs_epi_sync();
+                if (tid == 0) rs_arrive(&s.f_ready);
+                if (tid == 0) stamp(40 + j);
+            }
+            // ================= stem, phase B: x[2t] | x[2t+1] (TMEM, lane = t) -> shortcut operand, conv1 operand ==========
+            rs_wait(&s.stem_done, 0u);                            // every stem MMA retired: the stem region is dead
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) stamp(44);
+            const int brow = 32 * (warp & 3) + lane;              // TMEM lane = pooled time t
+            const int bcol = 16 * (warp >> 2);                    // this warp's 16 of the 32 channels
+#pragma unroll 1
+            for (int j = 0; j < nt; ++j) {
+                zero_halo(j);
+                uint32_t xe[16], xo[16];
+                const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(j * 2 * C + bcol);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15}, [%16];\n"
+                    : "=r"(xe[0]), "=r"(xe[1]), "=r"(xe[2]), "=r"(xe[3]), "=r"(xe[4]), "=r"(xe[5]), "=r"(xe[6]), "=r"(xe[7]),
+                      "=r"(xe[8]), "=r"(xe[9]), "=r"(xe[10]), "=r"(xe[11]), "=r"(xe[12]), "=r"(xe[13]), "=r"(xe[14]), "=r"(xe[15])
+                    : "r"(taddr));
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15}, [%16];\n"
+                    : "=r"(xo[0]), "=r"(xo[1]), "=r"(xo[2]), "=r"(xo[3]), "=r"(xo[4]), "=r"(xo[5]), "=r"(xo[6]), "=r"(xo[7]),
+                      "=r"(xo[8]), "=r"(xo[9]), "=r"(xo[10]), "=r"(xo[11]), "=r"(xo[12]), "=r"(xo[13]), "=r"(xo[14]), "=r"(xo[15])
+                    : "r"(taddr + static_cast<uint32_t>(C)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (j > 0) rs_wait(&s.a0_free, static_cast<uint32_t>((j - 1) & 1));   // shortcut MMAs of tile j-1 retired
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    const int col = bcol + k;
+                    const float4 bv = *reinterpret_cast<const float4*>(&s.prm0[0][col]);
+                    const float4 sc = *reinterpret_cast<const float4*>(&s.prm0[1][col]);
+                    const float4 sh = *reinterpret_cast<const float4*>(&s.prm0[2][col]);
+                    const float e0 = __uint_as_float(xe[k]) + bv.x, e1 = __uint_as_float(xe[k + 1]) + bv.y;
+                    const float e2 = __uint_as_float(xe[k + 2]) + bv.z, e3 = __uint_as_float(xe[k + 3]) + bv.w;
+                    const float o0 = __uint_as_float(xo[k]) + bv.x, o1 = __uint_as_float(xo[k + 1]) + bv.y;
+                    const float o2 = __uint_as_float(xo[k + 2]) + bv.z, o3 = __uint_as_float(xo[k + 3]) + bv.w;
+                    *reinterpret_cast<uint4*>(a0 + ((col >> 2) * Cfg::kA0Rows + brow) * 16) =
+                        make_uint4(rs_tf32(e0), rs_tf32(e1), rs_tf32(e2), rs_tf32(e3));
+                    *reinterpret_cast<uint4*>(&s.ab[j][0] + ((col >> 2) * kRtotS + G + brow) * 16) =
+                        make_uint4(rs_relu_tf32(fmaf(fmaxf(e0, o0), sc.x, sh.x)), rs_relu_tf32(fmaf(fmaxf(e1, o1), sc.y, sh.y)),
+                                   rs_relu_tf32(fmaf(fmaxf(e2, o2), sc.z, sh.z)), rs_relu_tf32(fmaf(fmaxf(e3, o3), sc.w, sh.w)));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                fence_proxy_async_smem();
+                rs_epi_sync();
+                if (tid == 0) rs_arrive(&s.a0_ready);
+                if (tid == 0) stamp(32 + j);
+            }
+        } else {
+        // ---- per tile: raw x[2t] -> shortcut operand; ReLU(BN1(max(x[2t], x[2t+1]))) -> conv1 operand ----
 #pragma unroll
         for (int j = 0; j < kTiles; ++j) {
             if (j >= nt) break;
@@ -448,6 +696,7 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
             rs_epi_sync();
             if (tid == 0) rs_arrive(&s.a0_ready);
             if (tid == 0) stamp(32 + j);
+        }
         }
         if (tid == 0) rs_arrive(&s.a_ready[0]);
 
@@ -589,27 +838,27 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C>::kMinCtas) resstag
                      : "memory");
 }
 
-template <int CIN, int C>
+template <int CIN, int C, bool STEM = false>
 int launch_stage(const StageArgs& a, cudaStream_t st) {
     static bool attr_set = false;
-    const int smem = static_cast<int>(sizeof(StageSmem<CIN, C>) + 128);
-    static_assert(sizeof(StageSmem<CIN, C>) + 128 <= 227 * 1024, "stage kernel shared memory");
-    static_assert(StageCfg<CIN, C>::kExtra >= 1, "the shortcut operand buffer becomes at least one ring stage");
+    const int smem = static_cast<int>(sizeof(StageSmem<CIN, C, STEM>) + 128);
+    static_assert(sizeof(StageSmem<CIN, C, STEM>) + 128 <= 227 * 1024, "stage kernel shared memory");
+    static_assert(StageCfg<CIN, C, STEM>::kExtra >= 1, "the shortcut operand buffer becomes at least one ring stage");
     if (!attr_set) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resstage_fused_kernel<CIN, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resstage_fused_kernel<CIN, C, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    constexpr int kTilesCta = StageCfg<CIN, C>::kTiles;
+    constexpr int kTilesCta = StageCfg<CIN, C, STEM>::kTiles;
     StageArgs b = a;
     const int tiles = (a.B + a.G - 1) / a.G;
-    const int slots = mmla_num_sms() * StageCfg<CIN, C>::kMinCtas;             // CTAs resident at once
+    const int slots = mmla_num_sms() * StageCfg<CIN, C, STEM>::kMinCtas;       // CTAs resident at once
     b.n_tiles = tiles;
     b.n_full = (tiles / (slots * kTilesCta)) * slots;                          // whole waves of full-size CTAs
     const int rest = tiles - b.n_full * kTilesCta;
     b.tail_tiles = rest > 0 ? (rest + slots - 1) / slots : 1;                   // <= kTilesCta
     const unsigned grid = static_cast<unsigned>(b.n_full + (rest + b.tail_tiles - 1) / b.tail_tiles);
-    resstage_fused_kernel<CIN, C><<<grid, kThreadsS, smem, st>>>(b);
-    mmla_count_launch("resstage_fused_kernel", st);
+    resstage_fused_kernel<CIN, C, STEM><<<grid, kThreadsS, smem, st>>>(b);
+    mmla_count_launch(STEM ? "stem_resstage_fused_kernel" : "resstage_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }
@@ -655,4 +904,32 @@ int mmla_launch_resstage_fused(const float* x, float* y, long long B, int T, int
     if (Cin == 64 && C == 128) return launch_stage<64, 128>(a, st);
     mmla_set_error("resstage_fused: Cin=%d C=%d unsupported", Cin, C);
     return MMLA_EUNSUP;
+}
+
+// First stage with the stem folded in (label pipeline): cepstra [B][rows >= n_frames][16] fp32 (cep_clip_stride floats per
+// clip) -> Conv1D(32, 4, 'same') of the [256, 39] feature rows built on the fly (delta, delta-delta, zero rows from
+// n_frames to 256) -> the stage's three residual units -> y [B][128][32].  stem_w: the stem's conv_tc-arranged weights
+// with 40 input channels (channel 39 = 0), stem_b: [32].  Same results as stem_fused.cu (FROM_CEP) + the plain stage.
+int mmla_launch_resstage_stem_fused(const float* cepstra, long long cep_clip_stride, int n_frames, const float* stem_w,
+                                    const float* stem_b, float* y, long long B, const float* const (*p)[8], const float* ws,
+                                    const float* bs, cudaStream_t st) {
+    MMLA_REQUIRE(B > 0 && B < (1LL << 24), MMLA_EINVAL, "resstage_stem_fused: bad batch");
+    MMLA_REQUIRE(cepstra && stem_w && stem_b && y && ws && bs, MMLA_EINVAL, "resstage_stem_fused: null argument");
+    MMLA_REQUIRE(n_frames >= 1 && n_frames <= 256 && cep_clip_stride >= static_cast<long long>(n_frames) * 16, MMLA_EINVAL,
+                 "resstage_stem_fused: bad cepstra geometry");
+    StageArgs a;
+    memset(&a, 0, sizeof(a));
+    a.y = y;
+    for (int u = 0; u < kUnitsS; ++u) {
+        a.u[u].bn1_scale = p[u][0]; a.u[u].bn1_shift = p[u][1]; a.u[u].w1 = p[u][2]; a.u[u].b1 = p[u][3];
+        a.u[u].bn2_scale = p[u][4]; a.u[u].bn2_shift = p[u][5]; a.u[u].w2 = p[u][6]; a.u[u].b2 = p[u][7];
+    }
+    a.ws = ws; a.bs = bs;
+    a.B = static_cast<int>(B); a.T = 128; a.G = 1;
+    a.cep = cepstra; a.cep_clip_stride = cep_clip_stride; a.n_frames = n_frames; a.stem_w = stem_w; a.stem_b = stem_b;
+    if (g_stage_stamps) {
+        a.stamps = g_stage_stamps;
+        a.stamp_cta = g_stage_stamp_cta;
+    }
+    return launch_stage<32, 32, true>(a, st);
 }

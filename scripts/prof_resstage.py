@@ -31,6 +31,8 @@ for u in range(3):
     names[21 + 4 * u] = f"u{u} epi2 done"
 for j in range(4):
     names[32 + j] = f"tile{j} operands written"
+    names[40 + j] = f"stem: clip{j} features built"
+names[44] = "stem: all MMAs retired (seen by epilogue)"
 for st in range(3):
     row = P[st]
     t0 = row[row > 0].min()

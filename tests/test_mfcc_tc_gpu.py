@@ -205,7 +205,8 @@ def test_classifier_from_cepstra_equals_classifier_from_features(cuda, clip_len)
     cep = si.mfcc_batch(pcm, row_stride=16)
     assert cep.shape == (5, psf.num_frames(clip_len), 16) and not cep[:, :, 13:].any()
     names = _launch_names(lambda: model.predict_device_cepstra(cep))
-    assert names[0] == "stem_delta_fused_kernel" and "mfcc_finish_kernel" not in names
+    # the stem runs either in its own launch or inside the first ResNet stage's kernel; never a separate feature pass
+    assert names[0] in ("stem_delta_fused_kernel", "stem_resstage_fused_kernel") and "mfcc_finish_kernel" not in names
     p_cep, l_cep = model.predict_device_cepstra(cep)
     p_feat, l_feat = model.predict_device(si.speaker_features_batch(pcm))
     assert torch.allclose(p_cep, p_feat, rtol=0, atol=2e-6), float((p_cep - p_feat).abs().max())
@@ -213,3 +214,27 @@ def test_classifier_from_cepstra_equals_classifier_from_features(cuda, clip_len)
     ref_feat = np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(5)]).astype(np.float32)
     ref = onets.speaker_forward(ref_feat, w, spec)
     assert np.abs(p_cep.cpu().numpy() - ref).max() <= 5e-3
+
+
+def test_stem_inside_first_stage_matches_separate_stem(cuda, monkeypatch):
+    """Label pipeline from MFCC-13 rows: the stem computed inside the first ResNet stage's kernel (features split by row
+    parity, max-pool and shortcut operand straight from TMEM) vs the stand-alone stem kernel followed by the plain stage
+    kernel.  Same MMAs in the same order on the same TF32 operands: probabilities must agree to fp32 round-off, labels
+    exactly; clip lengths cover T < 128, T = 150, T = 250 and the full 256 frames, batches cover partial tile groups."""
+    import torch
+    from mmla_audio_b200 import models, speaker_identification as si, weights as W
+    spec = W.speaker_spec(10, "sigmoid")
+    w = W.synthetic_weights(spec, 4321)
+    monkeypatch.setenv("MMLA_NET_FUSE_STEM", "0")
+    separate = models.Model(spec, w, precision="tf32")
+    monkeypatch.setenv("MMLA_NET_FUSE_STEM", "1")
+    fused = models.Model(spec, w, precision="tf32")
+    for n, clip_len in ((1, 24000), (5, 8800), (37, 40000), (300, 24000), (9, 40960)):
+        cep = si.mfcc_batch(synth.synth_clips(11, n, clip_len), row_stride=16)
+        assert "stem_resstage_fused_kernel" in _launch_names(lambda: fused.predict_device_cepstra(cep))
+        assert "stem_delta_fused_kernel" in _launch_names(lambda: separate.predict_device_cepstra(cep))
+        pf, lf = fused.predict_device_cepstra(cep)
+        ps, ls = separate.predict_device_cepstra(cep)
+        d = float((pf - ps).abs().max())
+        print(f"stem in stage vs separate, {n} clips x {clip_len}: max |dprob| {d:.2e}")
+        assert d <= 2e-6 and torch.equal(lf, ls)
