@@ -304,7 +304,7 @@ def main():
     from mmla_audio_b200 import _lib, models, synth, tally, weights as W
     from mmla_audio_b200 import speaker_identification as si
     from mmla_audio_b200.pipeline import OverlapPipeline, SpeakerPipeline
-    from mmla_audio_b200.sharding import allreduce_counts, bind_host_thread_to_gpu, gather_labels, shard_range
+    from mmla_audio_b200.sharding import bind_host_thread_to_gpu, exchange_labels_and_counts, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -346,8 +346,7 @@ def main():
         labels, _ = pipe.run_device(x)
         counts = tally.device_counts(labels, n_classes)
         if world > 1:
-            labels = gather_labels(labels, n_total, rank, world)
-            counts = allreduce_counts(counts, world)
+            labels, counts = exchange_labels_and_counts(labels, counts, n_total, rank, world)
         return labels, counts
 
     def barrier():
@@ -385,7 +384,7 @@ def main():
         return pending.result()                                  # host numpy: the step's (gathered) labels + tallies
 
     def e2e_reduce(labels_dev, counts_dev):                      # device side, on the compute stream, before the read-back
-        return gather_labels(labels_dev, n_total, rank, world), allreduce_counts(counts_dev, world)
+        return exchange_labels_and_counts(labels_dev, counts_dev, n_total, rank, world)
 
     def e2e_run(steps):
         """`steps` passes through the public host API.  Every pass uploads its own PCM from pinned

@@ -124,7 +124,7 @@ class SpeakerPipeline:
 
         ``reduce(labels_dev, counts_dev) -> (labels_all, counts_all)``: optional device-side step run
         on the compute stream before the read-back — the multi-GPU label all_gather / tally
-        all_reduce (``sharding.gather_labels`` / ``allreduce_counts``); its outputs are what is
+        all_reduce, one collective (``sharding.exchange_labels_and_counts``); its outputs are what is
         copied to the host."""
         torch = _lib.require_cuda()
         B, L = pcm_host.shape

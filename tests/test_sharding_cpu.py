@@ -4,6 +4,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -33,18 +34,26 @@ def _worker(rank, world, port, n_total, n_classes, q):
     counts = torch.bincount(torch.where(local < 0, torch.tensor(n_classes), local.long()), minlength=n_classes + 1)
     counts = allreduce_counts(counts, world)
     ref = torch.bincount(torch.where(full < 0, torch.tensor(n_classes), full.long()), minlength=n_classes + 1)
-    q.put((rank, bool(torch.equal(gathered, full)), bool(torch.equal(counts, ref))))
+    # the same exchange as ONE collective (what bench.py and the pipelines use), twice to exercise the cached buffers
+    from mmla_audio_b200.sharding import exchange_labels_and_counts
+    ok_x = True
+    for _ in range(2):
+        local_counts = torch.bincount(torch.where(local < 0, torch.tensor(n_classes), local.long()), minlength=n_classes + 1)
+        g2, c2 = exchange_labels_and_counts(local, local_counts, n_total, rank, world)
+        ok_x = ok_x and bool(torch.equal(g2, full)) and bool(torch.equal(c2, ref)) and c2.dtype == torch.int64
+    q.put((rank, bool(torch.equal(gathered, full)) and ok_x, bool(torch.equal(counts, ref))))
     dist.destroy_process_group()
 
 
-def test_gather_and_allreduce_world2():
+@pytest.mark.parametrize("n_total", [1001, 4096])        # ragged and equal shards
+def test_gather_and_allreduce_world2(n_total):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1001, 10, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, 10, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
