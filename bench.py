@@ -224,6 +224,7 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     # classifier convolutions: 2 FLOP per multiply-add, Keras 'same' output sizes
     h, w_ = H0, T0
     res = 0.0
+    slab = 0.0                                   # overlap: the stride-1 3x3 / 4x1 convs (conv_slab_kernel)
     res_first_stage = 0.0                        # the first three residual units (the stage the stem is folded into)
     stem = 2.0 * h * w_ * spec.stem.kh * spec.stem.kw * spec.stem.cin * spec.stem.cout
     for bi, blk in enumerate(spec.blocks):
@@ -234,6 +235,8 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         if spec.ndim == 2:                       # overlap: both convs at full size, then MaxPool; shortcut strided
             res += 2.0 * h * w_ * blk.conv1.kh * blk.conv1.kw * blk.conv1.cin * blk.conv1.cout
             res += 2.0 * h * w_ * blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout
+            slab += 2.0 * h * w_ * (blk.conv1.kh * blk.conv1.kw * blk.conv1.cin * blk.conv1.cout +
+                                    blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout)
         else:                                    # speaker: MaxPool first, both convs at the pooled length
             res += 2.0 * h2 * w2 * blk.conv1.kh * blk.conv1.kw * blk.conv1.cin * blk.conv1.cout
             res += 2.0 * h2 * w2 * blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout
@@ -265,8 +268,11 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
                                            "what": "[T,13] cepstra in + [256,32] activations out (delta, delta-delta, padding, Conv1D k=4)"}
         work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
     else:
-        for k in ("conv_tc_kernel", "conv_igemm_kernel"):
-            work[k] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
+        work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
+        work["conv_slab_kernel"] = {"bound": "tensor", "per_step": B * slab,
+                                    "what": "the 18 stride-1 3x3 / 4x1 convolutions of the residual blocks (TF32, tap-shifted slabs)"}
+        work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (stem + res - slab),
+                                  "what": "1x1 stem conv + the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
     return work
 
 

@@ -64,6 +64,21 @@ void mmla_debug_resstage_stamps(long long* dev_stamps, int32_t cta);
 /* Same for the fused BiLSTM kernel: dev_stamps (DEVICE pointer, T x 16 int64, NULL = off) receives, per time step,
  * the clock64 timeline of CTA `cta` of the forward direction. */
 void mmla_debug_lstm_stamps(long long* dev_stamps, int32_t cta);
+/* Same for conv_slab_kernel: dev_stamps (DEVICE pointer, 64 x 16 int64, NULL = off) receives, for each of the next 64
+ * launches (row = launch ordinal), the clock64 timeline of a mid-image CTA of image `image`:
+ * 0 start, 1 set-up done, 2 slab written, 3 slab barrier, 4 first weight chunk landed, 5 MMAs issued, 6 accumulators
+ * complete, 7 epilogue done (warp 2), 8 all warps done. */
+void mmla_debug_conv_slab_stamps(long long* dev_stamps, int32_t image);
+/* One stride-1 'same' Conv2D layer of the classifiers, for layer-level parity tests of the convolution kernels:
+ *   y[B,H,W,N] = conv(act(x * pre_scale + pre_shift)) + bias (+ res), x [B,H,W,Cin] float32 NHWC (DEVICE),
+ *   w_host [kh*kw*Cin][N] (HOST, Keras HWIO flattened), bias / pre_scale / pre_shift / res / y DEVICE pointers
+ *   (pre_scale = NULL: no BN / activation prologue; res = NULL: no residual), pre_act 0 none / 1 ReLU / 2 ELU.
+ *   kernel: 0 = conv_igemm_kernel (fp32 CUDA cores), 1 = conv_tc_kernel (tcgen05, im2col gather),
+ *           2 = conv_slab_kernel (tcgen05, tap-shifted slab; MMLA_EUNSUP if the layer is not eligible).
+ * Synchronous on `stream`. */
+int mmla_debug_conv2d(const float* x, const float* w_host, const float* bias, const float* pre_scale, const float* pre_shift,
+                      int32_t pre_act, const float* res, float* y, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t N,
+                      int32_t kh, int32_t kw, int32_t kernel, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Speaker-ID features.

@@ -1,0 +1,434 @@
+// tcgen05 stride-1 convolution without an im2col gather: the "slab" kernel of the overlap classifier
+// (Conv2D 3x3 and 4x1 of `res_block`, overlap_detector_temp.py:253-280) and of any other stride-1
+// k > 1 conv whose Cin is 16 / 32 / 64 / 128.
+//
+// conv_tc_kernel builds every 128 x 32 im2col chunk with a gather: for a 3x3 conv each input element is
+// loaded, batch-normalised, ELU'd (expm1f) and rounded nine times, and the index arithmetic of the gather
+// (IMAD / ISETP / LOP3 = 40 % of its instructions, tensor pipe 2.5 % active) is what the kernel spends its
+// time on.  Here one CTA owns up to four consecutive 128-pixel tiles of ONE image and loads the pixels
+// they need ONCE:
+//
+//   * The image is addressed by a flat index over a ZERO-PADDED copy whose fast axis has Fp = F + kf - 1
+//     entries: p = sp * Fp + fp.  With that numbering output pixel q (same flat index, computed on the
+//     unpadded origin) reads padded input pixel q + ks_i * Fp + kf_j for tap (ks_i, kf_j): every filter tap is a
+//     UNIFORM row shift.  Outputs with fp >= F are junk rows (kf - 1 of every Fp, 1-2 %) and are not stored.
+//     3x3 convs take the image width as the fast axis (contiguous NHWC reads); the 4x1 convs take the
+//     HEIGHT, so their four taps are shifts of 0..3 rows and the halo is 3 rows instead of 3 * W.
+//   * BN + ELU/ReLU + TF32 rounding are applied once per element while the slab
+//     [channel quad][row][16 B] (the UMMA canonical K-major no-swizzle layout: 8-row x 16-byte core
+//     matrices, SBO = 128 B, LBO = slab stride) is written; padding rows are written as zeros AFTER the
+//     activation, which is what Keras' 'same' padding of the activated tensor means.
+//   * A tap's A operand is the slab's descriptor with its start address moved by `shift` rows (16 B each;
+//     the no-swizzle address map is linear in the row, so any row is a legal start — the speaker net's
+//     resunit_fused_kernel uses the same trick in 1-D).
+//   * Weights: the host-arranged [32 x N] K-chunks of conv_tc.cu come through a TMA ring
+//     (cp.async.bulk + mbarrier); every chunk feeds the MMAs of all the CTA's tiles (one TMEM accumulator
+//     of N columns per tile), so weight traffic per output pixel drops by the tile count.
+//   * Epilogue: tcgen05.ld, + bias (+ residual), 64-byte runs per thread straight to the NHWC output.
+#include <stdlib.h>
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int kSlabThreads = 256;
+constexpr int kSlabBK = 32;                 // K per ring chunk (matches mmla_tc_arrange_weights)
+constexpr int kSlabMaxTiles = 4;
+
+struct SlabArgs {
+    const float* x;
+    const float* wg;          // arranged weights (conv_tc.cu layout, one N tile)
+    const float* bias;
+    const float* pre_scale;
+    const float* pre_shift;
+    const float* res;
+    float* y;
+    long long res_row_stride;
+    long long img_pixels;     // H * W
+    int pre_act;
+    int F, S, Fp;             // fast / slow axis lengths, padded fast length
+    unsigned fp_magic;        // floor(2^32 / Fp) + 1: p / Fp == umulhi(p, fp_magic) for the p < 2^20 used here
+    int padF, padS;           // zero entries before the image on each axis
+    int pixF, pixS;           // pixel-index strides of the two axes (NHWC: w -> 1, h -> W)
+    int Cin, lq;              // lq = log2(Cin / 4)
+    int K, nk;
+    int kw;                   // filter width (tap index = ki * kw + kj)
+    int shift_h, shift_w;     // row shift per filter row / column
+    int tiles, T, cpi;        // 128-row tiles per image, tiles per CTA, CTAs per image
+    int Rs;                   // slab stride in rows
+    int stages;
+    unsigned ring_off, bar_off;
+    long long* stamps;        // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
+    int stamp_cta;
+};
+
+__device__ __forceinline__ uint32_t sl_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void sl_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+__device__ __forceinline__ uint64_t sl_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ bool sl_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void sl_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabArgs a) {
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
+    constexpr uint32_t kChunkBytes = 8 * NT * 16;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    unsigned char* slab = base;
+    unsigned char* ring = base + a.ring_off;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + a.bar_off);      // [stages]
+    uint64_t* empty = full + 4;                                          // [stages]
+    uint64_t* accum = full + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 9);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool stamping = a.stamps != nullptr && static_cast<int>(blockIdx.x) == a.stamp_cta;
+    auto stamp = [&](int slot) {
+        if (stamping) a.stamps[slot] = clock64();
+    };
+    if (tid == 0) stamp(0);
+    const int img = blockIdx.x / a.cpi;
+    const int tile0 = (blockIdx.x - img * a.cpi) * a.T;
+    const int Tc = min(a.T, a.tiles - tile0);
+    const int q0 = tile0 * 128;
+    const uint32_t cols = (Tc * NT <= 32) ? 32u : (Tc * NT <= 64) ? 64u : (Tc * NT <= 128) ? 128u : (Tc * NT <= 256) ? 256u : 512u;
+
+    if (tid == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(accum, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) stamp(1);
+
+    // ---- weight ring: the first `stages` chunks need no free slot, so they are requested before the fill ----
+    if (warp == 1 && lane == 0) {
+        const int pre = a.nk < a.stages ? a.nk : a.stages;
+        for (int kc = 0; kc < pre; ++kc) {
+            mbar_arrive_expect_tx(&full[kc], kChunkBytes);
+            tma_bulk_g2s(ring + kc * kChunkBytes, a.wg + static_cast<long long>(kc) * (NT * kSlabBK), kChunkBytes, &full[kc]);
+        }
+    }
+
+    // ---- slab fill: rows [0, rows) <-> padded flat indices q0 + row; BN + activation + TF32 once per element ----
+    const int kh_taps = (a.K / a.Cin) / a.kw;
+    const int rows = Tc * 128 + (kh_taps - 1) * a.shift_h + (a.kw - 1) * a.shift_w;
+    {
+        const int qc = 1 << a.lq;
+        const int c4 = tid & (qc - 1);
+        const int rpp = kSlabThreads >> a.lq;                 // rows per pass of the whole CTA
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool bn = a.pre_scale != nullptr;
+        if (bn) {
+            sc = __ldg(reinterpret_cast<const float4*>(a.pre_scale) + c4);
+            sh = __ldg(reinterpret_cast<const float4*>(a.pre_shift) + c4);
+        }
+        const float* ximg = a.x + static_cast<long long>(img) * a.img_pixels * a.Cin + 4 * c4;
+        unsigned char* dst0 = slab + static_cast<size_t>(c4) * a.Rs * 16;
+        // two batches of four 16-byte loads in flight per thread: batch i + 1 is requested before batch i is
+        // activated and stored
+        auto issue = [&](int r0, float4 (&v)[4], unsigned& ok) {
+            ok = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * rpp;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows) {
+                    const int p = q0 + r;
+                    const int sp = static_cast<int>(__umulhi(static_cast<unsigned>(p), a.fp_magic));
+                    const int s = sp - a.padS, f = p - sp * a.Fp - a.padF;
+                    if (s >= 0 && s < a.S && f >= 0 && f < a.F) {
+                        ok |= 1u << u;
+                        v[u] = __ldg(reinterpret_cast<const float4*>(ximg + static_cast<long long>(s * a.pixS + f * a.pixF) * a.Cin));
+                    }
+                }
+            }
+        };
+        auto finish = [&](int r0, const float4 (&v)[4], unsigned ok) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * rpp;
+                if (r < rows) {
+                    float4 w = v[u];
+                    if (((ok >> u) & 1u) && bn) {
+                        w.x = apply_act_tc(fmaf(w.x, sc.x, sh.x), a.pre_act);
+                        w.y = apply_act_tc(fmaf(w.y, sc.y, sh.y), a.pre_act);
+                        w.z = apply_act_tc(fmaf(w.z, sc.z, sh.z), a.pre_act);
+                        w.w = apply_act_tc(fmaf(w.w, sc.w, sh.w), a.pre_act);
+                    }
+                    *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(r) * 16) =
+                        make_uint4(sl_tf32(w.x), sl_tf32(w.y), sl_tf32(w.z), sl_tf32(w.w));
+                }
+            }
+        };
+        const int step = 4 * rpp;
+        float4 va[4], vb[4];
+        unsigned oka, okb;
+        int r0 = tid >> a.lq;
+        issue(r0, va, oka);
+        for (; r0 < rows; r0 += 2 * step) {
+            issue(r0 + step, vb, okb);
+            finish(r0, va, oka);
+            issue(r0 + 2 * step, va, oka);
+            finish(r0 + step, vb, okb);
+        }
+    }
+    if (tid == 0) stamp(2);
+    fence_proxy_async_smem();                // generic-proxy slab writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) stamp(3);
+
+    if (warp == 1) {
+        // ================= weight producer: remaining chunks =================
+        for (int kc = a.stages; kc < a.nk; ++kc) {
+            const int stg = kc % a.stages;
+            sl_wait(&empty[stg], static_cast<uint32_t>((kc / a.stages - 1) & 1));
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[stg], kChunkBytes);
+                tma_bulk_g2s(ring + stg * kChunkBytes, a.wg + static_cast<long long>(kc) * (NT * kSlabBK), kChunkBytes, &full[stg]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 0) {
+        // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dA = sl_desc(smem_u32(slab), static_cast<uint32_t>(a.Rs) * 16u, 128u);
+        const uint64_t dB = sl_desc(smem_u32(ring), NT * 16, 128);
+        const int lc = a.lq + 2;                               // log2(Cin)
+        for (int kc = 0; kc < a.nk; ++kc) {
+            const int stg = kc % a.stages;
+            sl_wait(&full[stg], static_cast<uint32_t>((kc / a.stages) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (kc == 0 && lane == 0) stamp(4);
+            const uint64_t bd0 = dB + static_cast<uint64_t>(stg * (kChunkBytes / 16));
+            // per-MMA operand offsets of this chunk (16-byte units): channel-quad slab + tap row shift
+            uint32_t aoff[4];
+            int nmma = 0;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = kc * kSlabBK + kk * 8;
+                aoff[kk] = 0;
+                if (k < a.K) {
+                    const int tap = k >> lc, c0 = k & (a.Cin - 1);
+                    const int ki = tap / a.kw, kj = tap - ki * a.kw;
+                    aoff[kk] = static_cast<uint32_t>((c0 >> 2) * a.Rs + ki * a.shift_h + kj * a.shift_w);
+                    nmma = kk + 1;
+                }
+            }
+            if (sl_elect_one()) {
+                for (int t = 0; t < Tc; ++t) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        if (kk < nmma) {
+                            const uint64_t ad = dA + static_cast<uint64_t>(aoff[kk] + static_cast<uint32_t>(t * 128));
+                            const uint64_t bd = bd0 + static_cast<uint64_t>(kk * 2 * NT);
+                            const uint32_t acc = (kc | kk) != 0 ? 1u : 0u;
+                            asm volatile(
+                                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
+                                "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                                : "memory");
+                        }
+                    }
+                }
+                sl_commit(&empty[stg]);
+                if (kc == a.nk - 1) sl_commit(accum);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) stamp(5);
+    }
+
+    // ---- epilogue: every warp owns 32 accumulator lanes (warp % 4) and one half of the columns (warp / 4) ----
+    {
+        const int quarter = warp & 3, chalf = warp >> 2;
+        constexpr int kColsPerWarp = NT / 2;
+        sl_wait(accum, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) stamp(6);
+        const long long out_pixels = static_cast<long long>(a.S) * a.Fp;
+        for (int t = 0; t < Tc; ++t) {
+            const int q = q0 + t * 128 + quarter * 32 + lane;
+            const int so = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), fo = q - so * a.Fp;
+            const bool valid = q < out_pixels && fo < a.F;
+            const long long pix = static_cast<long long>(img) * a.img_pixels + (valid ? so * a.pixS + fo * a.pixF : 0);
+#pragma unroll
+            for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
+                const int col = chalf * kColsPerWarp + c0;
+                uint32_t r[16];
+                const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * NT + col);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                    "%13, %14, %15}, [%16];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (valid) {
+                    const float4* bias = reinterpret_cast<const float4*>(a.bias + col);
+                    float4* dst = reinterpret_cast<float4*>(a.y + pix * NT + col);
+                    const float4* rs = a.res ? reinterpret_cast<const float4*>(a.res + pix * a.res_row_stride + col) : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bv = __ldg(bias + j);
+                        float4 o = make_float4(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
+                                               __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
+                        if (rs) {
+                            const float4 rr = rs[j];
+                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                        }
+                        dst[j] = o;
+                    }
+                }
+            }
+        }
+    }
+    if (tid == 64) stamp(7);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) stamp(8);
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+    }
+}
+
+int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+bool slab_enabled() {
+    const char* e = getenv("MMLA_CONV_SLAB");     // read per launch: tests flip it between calls
+    return !(e && e[0] == '0');
+}
+
+long long* g_slab_stamps = nullptr;       // mmla_debug_conv_slab_stamps: 64 rows (launch ordinal) x 16 slots
+int g_slab_stamp_cta = 0, g_slab_stamp_row = 0;
+
+template <int NT>
+int launch_slab(const SlabArgs& s, long long images, size_t smem, cudaStream_t st) {
+    static size_t attr = 0;
+    if (smem > attr) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(conv_slab_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr = smem;
+    }
+    conv_slab_kernel<NT><<<static_cast<unsigned>(images * s.cpi), kSlabThreads, smem, st>>>(s);
+    mmla_count_launch("conv_slab_kernel", st);
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
+}  // namespace
+
+// Whether conv_slab_kernel takes this layer (otherwise conv_tc_kernel's gather does).
+bool mmla_conv_slab_eligible(const ConvArgs& a) {
+    if (!slab_enabled()) return false;
+    if (a.stride != 1 || a.x_is_u8 || a.kh * a.kw <= 1) return false;
+    if (a.Cin != 16 && a.Cin != 32 && a.Cin != 64 && a.Cin != 128) return false;
+    if (a.N != 32 && a.N != 64 && a.N != 128) return false;
+    if (a.Ho != a.H || a.Wo != a.W || a.K != a.kh * a.kw * a.Cin) return false;
+    if (a.H <= 1) return false;                    // the 1-D speaker net has its own fused kernels
+    if (a.res && (a.res_row_stride % 4) != 0) return false;
+    return true;
+}
+
+int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
+    SlabArgs s;
+    memset(&s, 0, sizeof(s));
+    s.x = static_cast<const float*>(a.x); s.wg = wg; s.bias = a.bias;
+    s.pre_scale = a.pre_scale; s.pre_shift = a.pre_shift; s.pre_act = a.pre_act;
+    s.res = a.res; s.res_row_stride = a.res_row_stride; s.y = a.y;
+    s.img_pixels = static_cast<long long>(a.H) * a.W;
+    const long long images = a.M / s.img_pixels;
+    const bool fast_h = a.kw == 1;                 // k x 1 filters: the taps run along the fast axis
+    if (fast_h) {
+        s.F = a.H; s.S = a.W; s.Fp = a.H + a.kh - 1; s.padF = a.pad_t; s.padS = 0;
+        s.pixF = a.W; s.pixS = 1; s.shift_h = 1; s.shift_w = 0;
+    } else {
+        s.F = a.W; s.S = a.H; s.Fp = a.W + a.kw - 1; s.padF = a.pad_l; s.padS = a.pad_t;
+        s.pixF = 1; s.pixS = a.W; s.shift_h = s.Fp; s.shift_w = 1;
+    }
+    s.fp_magic = static_cast<unsigned>((1ULL << 32) / static_cast<unsigned>(s.Fp)) + 1u;
+    s.Cin = a.Cin; s.lq = ilog2(a.Cin / 4);
+    s.K = a.K; s.nk = (a.K + kSlabBK - 1) / kSlabBK; s.kw = a.kw;
+    const int halo = (a.kh - 1) * s.shift_h + (a.kw - 1) * s.shift_w;
+    s.tiles = static_cast<int>((static_cast<long long>(s.S) * s.Fp + 127) / 128);
+    s.stages = a.N <= 64 ? 3 : 2;
+    if (s.stages > s.nk) s.stages = s.nk;
+    const size_t ring = static_cast<size_t>(s.stages) * 8 * a.N * 16;
+    auto slab_rows = [&](int T) {
+        int r = T * 128 + halo;
+        if (a.Cin == 16) { while ((r & 7) != 2) ++r; } else if ((r & 1) == 0) ++r;     // conflict-free fill stores
+        return r;
+    };
+    auto bytes = [&](int T) { return static_cast<size_t>(a.Cin / 4) * slab_rows(T) * 16 + ring + 128 + 128; };
+    int tmax = kSlabMaxTiles;
+    if (tmax > 512 / a.N) tmax = 512 / a.N;
+    if (tmax > s.tiles) tmax = s.tiles;
+    int T = 0;
+    size_t budget = 113 * 1024;                        // two CTAs per SM
+    if (const char* e = getenv("MMLA_CONV_SLAB_KB")) {
+        const int v = atoi(e);
+        if (v >= 16 && v <= 226) budget = static_cast<size_t>(v) * 1024;
+    }
+    for (int t = tmax; t >= 1 && !T; --t)
+        if (bytes(t) <= budget) T = t;
+    for (int t = tmax; t >= 1 && !T; --t)
+        if (bytes(t) <= 226 * 1024) T = t;
+    MMLA_REQUIRE(T > 0, MMLA_EUNSUP, "conv_slab: layer does not fit in shared memory (Cin %d, halo %d rows)", a.Cin, halo);
+    if (const char* e = getenv("MMLA_CONV_SLAB_TILES")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= tmax && bytes(v) <= 226 * 1024) T = v;
+    }
+    s.T = T;
+    s.cpi = (s.tiles + T - 1) / T;
+    s.Rs = slab_rows(T);
+    s.ring_off = static_cast<unsigned>((static_cast<size_t>(a.Cin / 4) * s.Rs * 16 + 127) / 128 * 128);
+    s.bar_off = s.ring_off + static_cast<unsigned>(ring);
+    const size_t smem = s.bar_off + 128 + 128;
+    if (g_slab_stamps && g_slab_stamp_row < 64) {
+        s.stamps = g_slab_stamps + 16 * g_slab_stamp_row++;
+        s.stamp_cta = static_cast<int>((static_cast<long long>(g_slab_stamp_cta) % images) * s.cpi + s.cpi / 2);   // a mid-image CTA
+    }
+    MMLA_REQUIRE(static_cast<long long>(s.tiles) * 128 + halo < (1LL << 20), MMLA_EUNSUP, "conv_slab: image too large");
+    MMLA_REQUIRE(images * s.cpi < (1LL << 31) && images * s.img_pixels * (a.Cin > a.N ? a.Cin : a.N) < (1LL << 40), MMLA_EUNSUP,
+                 "conv_slab: batch too large");
+    switch (a.N) {
+        case 32: return launch_slab<32>(s, images, smem, st);
+        case 64: return launch_slab<64>(s, images, smem, st);
+        default: return launch_slab<128>(s, images, smem, st);
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) void mmla_debug_conv_slab_stamps(long long* dev_stamps, int32_t image) {
+    g_slab_stamps = dev_stamps;
+    g_slab_stamp_cta = image;
+    g_slab_stamp_row = 0;
+}

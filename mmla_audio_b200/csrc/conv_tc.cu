@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                             if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
                                 const int idx = xb[i] + (hi * a.W + wi) * a.Cin + c;
                                 v = a.x_is_u8 ? static_cast<float>(xu[idx]) : xf[idx];
-                                if (a.pre_scale) v = apply_act(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
+                                if (a.pre_scale) v = apply_act_tc(fmaf(v, a.pre_scale[c], a.pre_shift[c]), a.pre_act);
                             }
                         }
                     }
@@ -232,10 +232,10 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
                 if (__float_as_uint(v.x) == 0x7fc00000u) {
                     v = make_float4(0.f, 0.f, 0.f, 0.f);                     // padding pixel
                 } else if (bn) {
-                    v.x = apply_act(fmaf(v.x, sc.x, sh.x), a.pre_act);
-                    v.y = apply_act(fmaf(v.y, sc.y, sh.y), a.pre_act);
-                    v.z = apply_act(fmaf(v.z, sc.z, sh.z), a.pre_act);
-                    v.w = apply_act(fmaf(v.w, sc.w, sh.w), a.pre_act);
+                    v.x = apply_act_tc(fmaf(v.x, sc.x, sh.x), a.pre_act);
+                    v.y = apply_act_tc(fmaf(v.y, sc.y, sh.y), a.pre_act);
+                    v.z = apply_act_tc(fmaf(v.z, sc.z, sh.z), a.pre_act);
+                    v.w = apply_act_tc(fmaf(v.w, sc.w, sh.w), a.pre_act);
                 }
             }
             const int r = rb + 32 * i;
@@ -403,7 +403,12 @@ void mmla_tc_arrange_weights(const float* w, int K, int N, float* out) {
                     }
 }
 
+// conv_slab.cu: stride-1 k > 1 convs without the im2col gather
+bool mmla_conv_slab_eligible(const ConvArgs& a);
+int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st);
+
 int mmla_launch_conv_tc(const ConvArgs& a, const float* wg, cudaStream_t st) {
+    if (mmla_conv_slab_eligible(a)) return mmla_launch_conv_slab(a, wg, st);
     MMLA_REQUIRE(a.M < (1LL << 31) - 256 && (a.M / (a.Ho * a.Wo) + 1) * a.H * a.W * a.Cin < (1LL << 31), MMLA_EUNSUP,
                  "conv_tc: tensor too large for 32-bit indexing (reduce the micro-batch)");
     switch (mmla_tc_ntile(a.N)) {

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -884,6 +885,63 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         MMLA_CUDA_CHECK(cudaGetLastError());
     }
     return MMLA_OK;
+}
+
+// conv_slab.cu
+bool mmla_conv_slab_eligible(const ConvArgs& a);
+int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st);
+
+EXPORT int mmla_debug_conv2d(const float* x, const float* w_host, const float* bias, const float* pre_scale, const float* pre_shift,
+                             int32_t pre_act, const float* res, float* y, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t N,
+                             int32_t kh, int32_t kw, int32_t kernel, void* stream) {
+    MMLA_REQUIRE(x && w_host && bias && y && B >= 0 && H > 0 && W > 0 && Cin > 0 && N > 0 && kh > 0 && kw > 0, MMLA_EINVAL,
+                 "debug_conv2d: bad argument");
+    MMLA_REQUIRE(kernel >= 0 && kernel <= 2, MMLA_EINVAL, "debug_conv2d: unknown kernel %d", kernel);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K = kh * kw * Cin;
+    const bool tc = kernel != 0;
+    MMLA_REQUIRE(!tc || mmla_tc_ntile(N) != 0, MMLA_EUNSUP, "debug_conv2d: N=%d is not eligible for the tensor-core kernels", N);
+    std::vector<float> host(tc ? mmla_tc_arranged_floats(K, N) : static_cast<long long>(K) * N);
+    if (tc) mmla_tc_arrange_weights(w_host, K, N, host.data());
+    else memcpy(host.data(), w_host, host.size() * sizeof(float));
+    float* wdev = nullptr;
+    MMLA_CUDA_CHECK(cudaMalloc(&wdev, host.size() * sizeof(float)));
+    int rc = MMLA_OK;
+    if (cudaMemcpyAsync(wdev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MMLA_ECUDA;
+    if (rc == MMLA_OK) {
+        ConvW c;
+        c.kh = kh; c.kw = kw; c.cin = Cin; c.cout = N; c.stride = 1;
+        c.k = tc ? nullptr : wdev; c.b = bias; c.k_tc = tc ? wdev : nullptr;
+        BnW bn;
+        bn.scale = pre_scale; bn.shift = pre_shift;
+        if (kernel == 2) {
+            ConvArgs a;
+            memset(&a, 0, sizeof(a));
+            a.x = x; a.bias = bias; a.pre_scale = pre_scale; a.pre_shift = pre_shift; a.pre_act = pre_act;
+            a.res = res; a.res_row_stride = N; a.y = y; a.H = H; a.W = W; a.Cin = Cin; a.Ho = H; a.Wo = W; a.N = N; a.K = K;
+            a.kh = kh; a.kw = kw; a.stride = 1; a.pad_t = same_pad_before(H, kh, 1); a.pad_l = same_pad_before(W, kw, 1);
+            a.M = B * H * W;
+            if (!mmla_conv_slab_eligible(a)) {
+                mmla_set_error("debug_conv2d: layer is not eligible for conv_slab_kernel");
+                rc = MMLA_EUNSUP;
+            } else if (a.M > 0) {
+                rc = mmla_launch_conv_slab(a, wdev, st);
+            }
+        } else {
+            // kernel 1 must be the gather kernel even where the slab kernel is eligible
+            const char* old = getenv("MMLA_CONV_SLAB");
+            const std::string keep = old ? old : "";
+            if (kernel == 1) setenv("MMLA_CONV_SLAB", "0", 1);
+            rc = launch_conv(c, x, 0, B, H, W, pre_scale ? &bn : nullptr, pre_act, res, N, y, st, tc);
+            if (kernel == 1) { if (old) setenv("MMLA_CONV_SLAB", keep.c_str(), 1); else unsetenv("MMLA_CONV_SLAB"); }
+        }
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == MMLA_OK) {
+        mmla_set_error("debug_conv2d: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MMLA_ECUDA;
+    }
+    cudaFree(wdev);
+    return rc;
 }
 
 EXPORT int mmla_net_set_precision(MmlaNet* net, int32_t mode) {
