@@ -31,10 +31,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 // TF32 operand paths (conv_tc.cu, conv_slab.cu): the result is rounded to 10 mantissa bits right after, so ELU's
 // negative branch is ex2.approx(v * log2 e) - 1 (absolute error ~1e-7) instead of expm1f — expm1f was 60-70 % of
-// conv_slab_kernel's executed instructions (profiles/r01/conv_slab_v1_ncu_summary.txt).
+// conv_slab_kernel's executed instructions (profiles/r01/conv_slab_v1_ncu_summary.txt).  Branch-free on purpose: written
+// as `v > 0 ? v : __expf(v) - 1` the compiler emitted a divergent branch per element around the MUFU.
 __device__ __forceinline__ float apply_act_tc(float v, int act) {
-    if (act == ACT_RELU) return fmaxf(v, 0.f);
-    if (act == ACT_ELU) return v > 0.f ? v : __expf(v) - 1.f;
-    return v;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+    const float neg = act == ACT_ELU ? e - 1.f : (act == ACT_RELU ? 0.f : v);      // the value for v <= 0
+    return v > 0.f ? v : neg;
 }
 

@@ -35,6 +35,8 @@ namespace {
 constexpr int kSlabThreads = 256;
 constexpr int kSlabBK = 32;                 // K per ring chunk (matches mmla_tc_arrange_weights)
 constexpr int kSlabMaxTiles = 4;
+constexpr int kSlabMaxStages = 40;
+constexpr int kSlabMaxChunks = 64;         // K <= 2048
 
 struct SlabArgs {
     const float* x;
@@ -59,6 +61,9 @@ struct SlabArgs {
     int Rs;                   // slab stride in rows
     int stages;
     unsigned ring_off, bar_off;
+    int staged;               // epilogue through warp-private staging tiles (whole-line stores)
+    int nmma_last;            // MMAs (K = 8 each) in the last chunk; every other chunk has four
+    unsigned aoff[kSlabMaxChunks * 4];   // per MMA: A-operand offset in 16-byte units = channel-quad slab + tap row shift
     long long* stamps;        // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
     int stamp_cta;
 };
@@ -92,9 +97,9 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
     unsigned char* slab = base;
     unsigned char* ring = base + a.ring_off;
     uint64_t* full = reinterpret_cast<uint64_t*>(base + a.bar_off);      // [stages]
-    uint64_t* empty = full + 4;                                          // [stages]
-    uint64_t* accum = full + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 9);
+    uint64_t* empty = full + kSlabMaxStages;                             // [stages]
+    uint64_t* accum = full + 2 * kSlabMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kSlabMaxStages + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool stamping = a.stamps != nullptr && static_cast<int>(blockIdx.x) == a.stamp_cta;
@@ -128,9 +133,9 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
     if (tid == 0) stamp(1);
 
     // ---- weight ring: the first `stages` chunks need no free slot, so they are requested before the fill ----
-    if (warp == 1 && lane == 0) {
+    if (lane == 0) {                          // one chunk per warp at a time: bulk copies of one thread serialise
         const int pre = a.nk < a.stages ? a.nk : a.stages;
-        for (int kc = 0; kc < pre; ++kc) {
+        for (int kc = warp; kc < pre; kc += kSlabThreads / 32) {
             mbar_arrive_expect_tx(&full[kc], kChunkBytes);
             tma_bulk_g2s(ring + kc * kChunkBytes, a.wg + static_cast<long long>(kc) * (NT * kSlabBK), kChunkBytes, &full[kc]);
         }
@@ -151,52 +156,57 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
         }
         const float* ximg = a.x + static_cast<long long>(img) * a.img_pixels * a.Cin + 4 * c4;
         unsigned char* dst0 = slab + static_cast<size_t>(c4) * a.Rs * 16;
-        // two batches of four 16-byte loads in flight per thread: batch i + 1 is requested before batch i is
-        // activated and stored
-        auto issue = [&](int r0, float4 (&v)[4], unsigned& ok) {
-            ok = 0u;
+        // Pass 1: every element goes global -> slab by a 16-byte cp.async (no register staging: all of the thread's
+        // loads are in flight at once — the register-staged version paid one memory round trip per batch of four,
+        // 12-20 k cycles per CTA); padding rows are written as zeros.  Pass 2, after cp.async.wait_all: the same
+        // thread activates and rounds its own elements in place.
+        // (both loops are unrolled by four independent rows: with 2-4 warps per scheduler the fill is bound by the
+        //  dependent-issue latency of each warp's instruction chain, not by memory — clock64 stamps: 1 k cycles of
+        //  cp.async wait against 10-30 k cycles of address arithmetic and activation at one row per iteration)
+        unsigned long long okmask = 0ull;                     // bit i: row r0 + i * rpp holds image data
+        const int r0 = tid >> a.lq;
+        for (int it = 0; r0 + it * rpp < rows; it += 4) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int r = r0 + u * rpp;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < rows) {
+                const int r = r0 + (it + u) * rpp;
+                if (r < rows) {                               // (predication, no divergent paths: padding = zero-fill copy)
                     const int p = q0 + r;
                     const int sp = static_cast<int>(__umulhi(static_cast<unsigned>(p), a.fp_magic));
-                    const int s = sp - a.padS, f = p - sp * a.Fp - a.padF;
-                    if (s >= 0 && s < a.S && f >= 0 && f < a.F) {
-                        ok |= 1u << u;
-                        v[u] = __ldg(reinterpret_cast<const float4*>(ximg + static_cast<long long>(s * a.pixS + f * a.pixF) * a.Cin));
-                    }
+                    const int sI = sp - a.padS, f = p - sp * a.Fp - a.padF;
+                    const bool ok = sI >= 0 && sI < a.S && f >= 0 && f < a.F;
+                    okmask |= static_cast<unsigned long long>(ok) << (it + u);
+                    const float* src = ximg + (ok ? static_cast<long long>(sI * a.pixS + f * a.pixF) * a.Cin : 0ll);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst0 + static_cast<size_t>(r) * 16)),
+                                 "l"(src), "r"(ok ? 16 : 0)
+                                 : "memory");
                 }
             }
-        };
-        auto finish = [&](int r0, const float4 (&v)[4], unsigned ok) {
+        }
+        if (tid == 0) stamp(9);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (tid == 0) stamp(10);
+        for (int it = 0; r0 + it * rpp < rows; it += 4) {
+            uint4 raw[4];
+            const unsigned m4 = static_cast<unsigned>(okmask >> it) & 15u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + (it + u) * rpp < rows) raw[u] = *reinterpret_cast<const uint4*>(dst0 + static_cast<size_t>(r0 + (it + u) * rpp) * 16);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int r = r0 + u * rpp;
-                if (r < rows) {
-                    float4 w = v[u];
-                    if (((ok >> u) & 1u) && bn) {
+                if (r0 + (it + u) * rpp < rows) {
+                    float4 w = make_float4(__uint_as_float(raw[u].x), __uint_as_float(raw[u].y), __uint_as_float(raw[u].z),
+                                           __uint_as_float(raw[u].w));
+                    if (bn) {
                         w.x = apply_act_tc(fmaf(w.x, sc.x, sh.x), a.pre_act);
                         w.y = apply_act_tc(fmaf(w.y, sc.y, sh.y), a.pre_act);
                         w.z = apply_act_tc(fmaf(w.z, sc.z, sh.z), a.pre_act);
                         w.w = apply_act_tc(fmaf(w.w, sc.w, sh.w), a.pre_act);
                     }
-                    *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(r) * 16) =
-                        make_uint4(sl_tf32(w.x), sl_tf32(w.y), sl_tf32(w.z), sl_tf32(w.w));
+                    const uint32_t keep = ((m4 >> u) & 1u) ? 0xFFFFFFFFu : 0u;         // padding rows stay zero
+                    *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(r0 + (it + u) * rpp) * 16) =
+                        make_uint4(sl_tf32(w.x) & keep, sl_tf32(w.y) & keep, sl_tf32(w.z) & keep, sl_tf32(w.w) & keep);
                 }
             }
-        };
-        const int step = 4 * rpp;
-        float4 va[4], vb[4];
-        unsigned oka, okb;
-        int r0 = tid >> a.lq;
-        issue(r0, va, oka);
-        for (; r0 < rows; r0 += 2 * step) {
-            issue(r0 + step, vb, okb);
-            finish(r0, va, oka);
-            issue(r0 + 2 * step, va, oka);
-            finish(r0 + step, vb, okb);
         }
     }
     if (tid == 0) stamp(2);
@@ -206,67 +216,130 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
 
     if (warp == 1) {
         // ================= weight producer: remaining chunks =================
+        int stg = 0;
+        uint32_t ph = 0u;                     // ring position kept in counters (a runtime % and / per chunk are ~50 instructions)
         for (int kc = a.stages; kc < a.nk; ++kc) {
-            const int stg = kc % a.stages;
-            sl_wait(&empty[stg], static_cast<uint32_t>((kc / a.stages - 1) & 1));
+            sl_wait(&empty[stg], ph);
             if (lane == 0) {
                 mbar_arrive_expect_tx(&full[stg], kChunkBytes);
                 tma_bulk_g2s(ring + stg * kChunkBytes, a.wg + static_cast<long long>(kc) * (NT * kSlabBK), kChunkBytes, &full[stg]);
             }
             __syncwarp();
+            if (++stg == a.stages) { stg = 0; ph ^= 1u; }
         }
     } else if (warp == 0) {
         // ================= MMA issuer: warp-uniform loop, one elected lane issues =================
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dA = sl_desc(smem_u32(slab), static_cast<uint32_t>(a.Rs) * 16u, 128u);
         const uint64_t dB = sl_desc(smem_u32(ring), NT * 16, 128);
-        const int lc = a.lq + 2;                               // log2(Cin)
+        int stg = 0;
+        uint32_t ph = 0u;
         for (int kc = 0; kc < a.nk; ++kc) {
-            const int stg = kc % a.stages;
-            sl_wait(&full[stg], static_cast<uint32_t>((kc / a.stages) & 1));
+            sl_wait(&full[stg], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (kc == 0 && lane == 0) stamp(4);
             const uint64_t bd0 = dB + static_cast<uint64_t>(stg * (kChunkBytes / 16));
-            // per-MMA operand offsets of this chunk (16-byte units): channel-quad slab + tap row shift
-            uint32_t aoff[4];
-            int nmma = 0;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = kc * kSlabBK + kk * 8;
-                aoff[kk] = 0;
-                if (k < a.K) {
-                    const int tap = k >> lc, c0 = k & (a.Cin - 1);
-                    const int ki = tap / a.kw, kj = tap - ki * a.kw;
-                    aoff[kk] = static_cast<uint32_t>((c0 >> 2) * a.Rs + ki * a.shift_h + kj * a.shift_w);
-                    nmma = kk + 1;
-                }
-            }
-            if (sl_elect_one()) {
-                for (int t = 0; t < Tc; ++t) {
+            // per-MMA operand offsets come from the kernel parameters (host-computed table, constant bank -> uniform
+            // registers): computing tap = k / Cin / kw here cost ~2 k cycles of dependent scalar code per chunk, which
+            // — not the MMAs — set the pace of the issue loop
+            const uint32_t aoff[4] = {a.aoff[kc * 4], a.aoff[kc * 4 + 1], a.aoff[kc * 4 + 2], a.aoff[kc * 4 + 3]};
+            const int nmma = kc == a.nk - 1 ? a.nmma_last : 4;
+            // descriptor arithmetic stays in warp-uniform code OUTSIDE the elected region (uniform registers feed
+            // UTCHMMA directly); computed inside it, every MMA paid an R2UR waterfall: 130-400 cycles instead of 45-64
+            for (int t = 0; t < Tc; ++t) {
+                const uint64_t at = dA + static_cast<uint64_t>(static_cast<uint32_t>(t * 128));
+                const uint64_t ad[4] = {at + aoff[0], at + aoff[1], at + aoff[2], at + aoff[3]};
+                const uint32_t dt = tmem + static_cast<uint32_t>(t * NT);
+                if (sl_elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         if (kk < nmma) {
-                            const uint64_t ad = dA + static_cast<uint64_t>(aoff[kk] + static_cast<uint32_t>(t * 128));
-                            const uint64_t bd = bd0 + static_cast<uint64_t>(kk * 2 * NT);
                             const uint32_t acc = (kc | kk) != 0 ? 1u : 0u;
                             asm volatile(
                                 "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
-                                "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(dt),
+                                "l"(ad[kk]), "l"(bd0 + static_cast<uint64_t>(kk * 2 * NT)), "r"(kIdesc), "r"(acc)
                                 : "memory");
                         }
                     }
                 }
+                __syncwarp();
+            }
+            if (sl_elect_one()) {
                 sl_commit(&empty[stg]);
                 if (kc == a.nk - 1) sl_commit(accum);
             }
+            if (++stg == a.stages) { stg = 0; ph ^= 1u; }
             __syncwarp();
         }
         if (lane == 0) stamp(5);
     }
 
-    // ---- epilogue: every warp owns 32 accumulator lanes (warp % 4) and one half of the columns (warp / 4) ----
-    {
+    // ---- epilogue ----
+    if (a.staged) {
+        // Every warp owns 32 accumulator lanes (warp % 4) and every second (tile, 32-column chunk) unit (warp / 4).
+        // A unit goes TMEM -> registers -> a warp-private [32 rows][32 + 4 floats] staging tile in the dead slab ->
+        // global memory with eight lanes per row: each store instruction writes four whole 128-byte lines (the
+        // direct path below writes 16 bytes into each of 32 lines), the residual is read the same way.
+        constexpr int kChunks = NT / 32;
+        const int quarter = warp & 3, half = warp >> 2;
+        float* stg = reinterpret_cast<float*>(slab) + warp * (32 * 36);
+        const int seg = lane & 7, rsub = lane >> 3;
+        const int out_pixels = a.S * a.Fp;
+        // per unit and lane: the eight output rows (4i + rsub), their pixel offsets and residual values; the residual
+        // of a unit is requested before its accumulator is touched (for the first unit: before the MMAs are even
+        // waited for), so its memory round trip overlaps the tensor work instead of serialising row by row
+        long long pixoff[8];
+        float4 rr[8];
+        auto prefetch = [&](int u) {
+            const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
+            const int qb = q0 + t * 128 + quarter * 32 + rsub;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = qb + 4 * i;
+                const int so = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), fo = q - so * a.Fp;
+                const bool valid = q < out_pixels && fo < a.F;
+                pixoff[i] = valid ? static_cast<long long>(img) * a.img_pixels + (so * a.pixS + fo * a.pixF) : -1;
+                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && a.res) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res + pixoff[i] * a.res_row_stride + col0) + seg);
+            }
+        };
+        const int nunits = Tc * kChunks;
+        if (half < nunits) prefetch(half);
+        sl_wait(accum, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) stamp(6);
+        for (int u = half; u < nunits; u += 2) {
+            const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
+            uint32_t r[32];
+            const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * NT + col0);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j)       // lane = row; row stride 144 B: a quarter-warp's STS.128 covers 8 distinct 16-byte slots
+                *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            __syncwarp();
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + col0) + seg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {     // rows 4i .. 4i+3 of the warp's 32, eight lanes (128 B) per row
+                if (pixoff[i] >= 0) {
+                    const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * seg);
+                    *(reinterpret_cast<float4*>(a.y + pixoff[i] * NT + col0) + seg) =
+                        make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w);
+                }
+            }
+            __syncwarp();                     // the staging tile is rewritten by the next unit
+            if (u + 2 < nunits) prefetch(u + 2);
+        }
+    } else {
+        // direct: every warp owns 32 accumulator lanes (warp % 4) and one half of the columns (warp / 4)
         const int quarter = warp & 3, chalf = warp >> 2;
         constexpr int kColsPerWarp = NT / 2;
         sl_wait(accum, 0u);
@@ -378,41 +451,85 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
     s.fp_magic = static_cast<unsigned>((1ULL << 32) / static_cast<unsigned>(s.Fp)) + 1u;
     s.Cin = a.Cin; s.lq = ilog2(a.Cin / 4);
     s.K = a.K; s.nk = (a.K + kSlabBK - 1) / kSlabBK; s.kw = a.kw;
+    MMLA_REQUIRE(s.nk <= kSlabMaxChunks, MMLA_EUNSUP, "conv_slab: K = %d is too large", a.K);
     const int halo = (a.kh - 1) * s.shift_h + (a.kw - 1) * s.shift_w;
     s.tiles = static_cast<int>((static_cast<long long>(s.S) * s.Fp + 127) / 128);
-    s.stages = a.N <= 64 ? 3 : 2;
-    if (s.stages > s.nk) s.stages = s.nk;
-    const size_t ring = static_cast<size_t>(s.stages) * 8 * a.N * 16;
+    const size_t chunk = static_cast<size_t>(8) * a.N * 16;      // one [32 x N] K-chunk of weights
     auto slab_rows = [&](int T) {
         int r = T * 128 + halo;
         if (a.Cin == 16) { while ((r & 7) != 2) ++r; } else if ((r & 1) == 0) ++r;     // conflict-free fill stores
         return r;
     };
-    auto bytes = [&](int T) { return static_cast<size_t>(a.Cin / 4) * slab_rows(T) * 16 + ring + 128 + 128; };
+    constexpr size_t kStagingBytes = 8 * 32 * 36 * 4;           // epilogue staging tiles live in the dead slab
+    constexpr size_t kBarBytes = 1024 + 128;                    // mbarriers + alignment slack
+    auto slab_bytes = [&](int T) {
+        const size_t b = static_cast<size_t>(a.Cin / 4) * slab_rows(T) * 16;
+        return b < kStagingBytes ? kStagingBytes : b;
+    };
+    // Tiles per CTA, ring depth and CTAs per SM come from a small cost model fitted to the clock64 timelines of
+    // scripts/prof_conv_slab.py: a weight-ring refill takes ~3000 cycles from the commit that frees the slot (with 2-3
+    // slots the issue loop waited on weights for 2/3 of its time), a chunk holds T * 4 MMAs of max(N / 2, 45) cycles,
+    // fill and epilogue pay a memory round trip each, and co-resident CTAs overlap each other's phases.
+    auto bytes = [&](int T, int stages) { return slab_bytes(T) + stages * chunk + kBarBytes; };
     int tmax = kSlabMaxTiles;
     if (tmax > 512 / a.N) tmax = 512 / a.N;
     if (tmax > s.tiles) tmax = s.tiles;
+    int force_t = 0, force_kb = 0, force_stages = 0;
+    if (const char* e = getenv("MMLA_CONV_SLAB_TILES")) force_t = atoi(e);
+    if (const char* e = getenv("MMLA_CONV_SLAB_KB")) force_kb = atoi(e);
+    if (const char* e = getenv("MMLA_CONV_SLAB_STAGES")) force_stages = atoi(e);
+    const int min2 = s.nk < 2 ? s.nk : 2;
     int T = 0;
-    size_t budget = 113 * 1024;                        // two CTAs per SM
-    if (const char* e = getenv("MMLA_CONV_SLAB_KB")) {
-        const int v = atoi(e);
-        if (v >= 16 && v <= 226) budget = static_cast<size_t>(v) * 1024;
+    double best = 0.0;
+    const int budgets_kb[2] = {113, 226};              // two CTAs or one CTA per SM (~105 registers: no third)
+    const double overlap[2] = {1.7, 1.0};
+    for (int bi = 0; bi < 2; ++bi) {
+        const size_t budget = static_cast<size_t>(force_kb >= 16 && force_kb <= 226 ? force_kb : budgets_kb[bi]) * 1024;
+        for (int t = 1; t <= tmax; ++t) {
+            if (force_t >= 1 && force_t <= tmax && t != force_t) continue;
+            if (bytes(t, min2) > budget) continue;
+            int stages = static_cast<int>((budget - slab_bytes(t) - kBarBytes) / chunk);
+            if (stages > s.nk) stages = s.nk;
+            if (stages > kSlabMaxStages) stages = kSlabMaxStages;
+            if (force_stages >= 1 && force_stages <= stages) stages = force_stages;
+            const double per_chunk = t * 4.0 * (a.N / 2 > 45 ? a.N / 2 : 45);
+            const double refill = (3000.0 + per_chunk) / stages;
+            const double mma = s.nk * (per_chunk > refill ? per_chunk : refill);
+            const double fill = 5000.0 + slab_rows(t) * (a.Cin / 4) / 256.0 * 40.0;
+            const double epi = 3000.0 + 700.0 * t * (a.N / 32);
+            // useful tiles: the last CTA of an image may be partly empty
+            const int cpi = (s.tiles + t - 1) / t;
+            const double cost = (fill + mma + epi) * cpi / overlap[bi] / s.tiles;
+            if (!T || cost < best) {
+                T = t; best = cost; s.stages = stages;
+            }
+        }
     }
-    for (int t = tmax; t >= 1 && !T; --t)
-        if (bytes(t) <= budget) T = t;
-    for (int t = tmax; t >= 1 && !T; --t)
-        if (bytes(t) <= 226 * 1024) T = t;
     MMLA_REQUIRE(T > 0, MMLA_EUNSUP, "conv_slab: layer does not fit in shared memory (Cin %d, halo %d rows)", a.Cin, halo);
-    if (const char* e = getenv("MMLA_CONV_SLAB_TILES")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= tmax && bytes(v) <= 226 * 1024) T = v;
-    }
+    const size_t ring = s.stages * chunk;
     s.T = T;
+    s.nmma_last = 0;
+    for (int kc = 0; kc < s.nk; ++kc)
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = kc * kSlabBK + kk * 8;
+            s.aoff[kc * 4 + kk] = 0;
+            if (k < a.K) {
+                const int tap = k / a.Cin, c0 = k % a.Cin;
+                const int ki = tap / a.kw, kj = tap % a.kw;
+                s.aoff[kc * 4 + kk] = static_cast<unsigned>((c0 >> 2) * slab_rows(T) + ki * s.shift_h + kj * s.shift_w);
+                if (kc == s.nk - 1) s.nmma_last = kk + 1;
+            }
+        }
     s.cpi = (s.tiles + T - 1) / T;
     s.Rs = slab_rows(T);
-    s.ring_off = static_cast<unsigned>((static_cast<size_t>(a.Cin / 4) * s.Rs * 16 + 127) / 128 * 128);
+    s.ring_off = static_cast<unsigned>((slab_bytes(T) + 127) / 128 * 128);
+    s.staged = 1;
+    if (const char* e = getenv("MMLA_CONV_SLAB_EPI")) s.staged = e[0] != '0';
     s.bar_off = s.ring_off + static_cast<unsigned>(ring);
-    const size_t smem = s.bar_off + 128 + 128;
+    const size_t smem = s.bar_off + kBarBytes;
+    if (getenv("MMLA_CONV_SLAB_VERBOSE"))
+        fprintf(stderr, "conv_slab: %dx%d Cin %d N %d k %dx%d: %d tiles/image, T %d, %d CTAs/image, ring %d of %d chunks, %zu KB smem\n",
+                a.H, a.W, a.Cin, a.N, a.kh, a.kw, s.tiles, s.T, s.cpi, s.stages, s.nk, smem / 1024);
     if (g_slab_stamps && g_slab_stamp_row < 64) {
         s.stamps = g_slab_stamps + 16 * g_slab_stamp_row++;
         s.stamp_cta = static_cast<int>((static_cast<long long>(g_slab_stamp_cta) % images) * s.cpi + s.cpi / 2);   // a mid-image CTA

@@ -17,9 +17,9 @@ pipe.run_device(pcm)
 torch.cuda.synchronize()
 lib.mmla_debug_conv_slab_stamps(None, 0)
 P = stamps.cpu().numpy().reshape(64, 16)
-print("launch:  setup   fill  fsync  w-wait  issue  mma-tail  epilogue  exit   total   (cycles)")
+print("launch:  setup  (f.issue f.wait f.xform) fill  fsync  w-wait  issue  mma-tail  epilogue  exit   total   (cycles)")
 for i, r in enumerate(P):
     if r[0] == 0:
         continue
     d = lambda x, y: int(r[x] - r[y])
-    print(f"{i:5d}: {d(1,0):7d}{d(2,1):7d}{d(3,2):7d}{d(4,3):8d}{d(5,4):7d}{d(6,5):10d}{d(7,6):10d}{d(8,7):6d}{d(8,0):8d}")
+    print(f"{i:5d}: {d(1,0):7d}  ({d(9,1):6d}{d(10,9):7d}{d(2,10):8d}){d(2,1):6d}{d(3,2):7d}{d(4,3):8d}{d(5,4):7d}{d(6,5):10d}{d(7,6):10d}{d(8,7):6d}{d(8,0):8d}")
