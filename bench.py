@@ -271,8 +271,10 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
         work["conv_slab_kernel"] = {"bound": "tensor", "per_step": B * slab,
                                     "what": "the 18 stride-1 3x3 / 4x1 convolutions of the residual blocks (TF32, tap-shifted slabs)"}
-        work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (stem + res - slab),
-                                  "what": "1x1 stem conv + the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
+        work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (res - slab),
+                                  "what": "the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
+        work["stem1x1_kernel"] = {"bound": "hbm", "per_step": B * H0 * T0 * (3 + 16 * 4),
+                                  "what": "uint8 [128,151,3] image in + float32 [128,151,16] stem activations out"}
     return work
 
 

@@ -32,7 +32,6 @@
 
 namespace {
 
-constexpr int kSlabThreads = 256;
 constexpr int kSlabBK = 32;                 // K per ring chunk (matches mmla_tc_arrange_weights)
 constexpr int kSlabMaxTiles = 4;
 constexpr int kSlabMaxStages = 40;
@@ -61,7 +60,6 @@ struct SlabArgs {
     int Rs;                   // slab stride in rows
     int stages;
     unsigned ring_off, bar_off;
-    int staged;               // epilogue through warp-private staging tiles (whole-line stores)
     int nmma_last;            // MMAs (K = 8 each) in the last chunk; every other chunk has four
     unsigned aoff[kSlabMaxChunks * 4];   // per MMA: A-operand offset in 16-byte units = channel-quad slab + tap row shift
     long long* stamps;        // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
@@ -87,8 +85,13 @@ __device__ __forceinline__ void sl_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabArgs a) {
+// RES = residual added in the epilogue.  Layers without one run 512 threads at one or two CTAs per SM (the fill and
+// the epilogue want warps; <= 64 registers keep two CTAs per SM) or 256 threads at three CTAs per SM (the full-resolution
+// layers, which are HBM-heavy and gain most from co-resident CTAs in different phases); layers with a residual keep 256
+// threads at two per SM because the residual prefetch holds 40 more registers.
+template <int NT, bool RES, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_slab_kernel(const SlabArgs a) {
+    constexpr int kSlabThreads = THREADS;
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
     constexpr uint32_t kChunkBytes = 8 * NT * 16;
@@ -145,9 +148,13 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
     const int kh_taps = (a.K / a.Cin) / a.kw;
     const int rows = Tc * 128 + (kh_taps - 1) * a.shift_h + (a.kw - 1) * a.shift_w;
     {
-        const int qc = 1 << a.lq;
-        const int c4 = tid & (qc - 1);
-        const int rpp = kSlabThreads >> a.lq;                 // rows per pass of the whole CTA
+        // A warp instruction covers 8 consecutive rows x 4 channel quads: in the slab that is four contiguous 128-byte
+        // runs (one per quad), in global memory 64 contiguous bytes of 8 pixels.  (With lanes running over the channel
+        // quads of one or two pixels, every 16-byte piece of a cp.async landed in a different slab row: 32 shared-memory
+        // wavefronts per instruction, 34 cycles each measured.)  A warp keeps its quad group, so BN parameters load once.
+        const int lqg = a.lq - 2;                             // log2(quad groups of 4)
+        const int c4 = ((warp & ((1 << lqg) - 1)) << 2) + (lane >> 3);
+        const int rpp = ((kSlabThreads / 32) >> lqg) * 8;     // rows per pass of the whole CTA
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool bn = a.pre_scale != nullptr;
         if (bn) {
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
         //  dependent-issue latency of each warp's instruction chain, not by memory — clock64 stamps: 1 k cycles of
         //  cp.async wait against 10-30 k cycles of address arithmetic and activation at one row per iteration)
         unsigned long long okmask = 0ull;                     // bit i: row r0 + i * rpp holds image data
-        const int r0 = tid >> a.lq;
+        const int r0 = (warp >> lqg) * 8 + (lane & 7);
         for (int it = 0; r0 + it * rpp < rows; it += 4) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -244,28 +251,30 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
             // — not the MMAs — set the pace of the issue loop
             const uint32_t aoff[4] = {a.aoff[kc * 4], a.aoff[kc * 4 + 1], a.aoff[kc * 4 + 2], a.aoff[kc * 4 + 3]};
             const int nmma = kc == a.nk - 1 ? a.nmma_last : 4;
-            // descriptor arithmetic stays in warp-uniform code OUTSIDE the elected region (uniform registers feed
-            // UTCHMMA directly); computed inside it, every MMA paid an R2UR waterfall: 130-400 cycles instead of 45-64
-            for (int t = 0; t < Tc; ++t) {
-                const uint64_t at = dA + static_cast<uint64_t>(static_cast<uint32_t>(t * 128));
-                const uint64_t ad[4] = {at + aoff[0], at + aoff[1], at + aoff[2], at + aoff[3]};
-                const uint32_t dt = tmem + static_cast<uint32_t>(t * NT);
-                if (sl_elect_one()) {
+            // descriptor arithmetic stays in warp-uniform code (uniform registers feed UTCHMMA directly; computed per
+            // lane inside the elected region every MMA paid an R2UR waterfall) and the whole chunk — up to 16 MMAs —
+            // goes out from ONE elected region: the tensor pipe queues only ~4 MMAs, so whatever the issuing warp
+            // does between two MMAs is a bubble
+            // (only the low word of a descriptor moves: start address in 16-byte units; LBO / SBO / version stay)
+            const uint32_t alo = static_cast<uint32_t>(dA), ahi = static_cast<uint32_t>(dA >> 32);
+            const uint32_t blo = static_cast<uint32_t>(bd0), bhi = static_cast<uint32_t>(bd0 >> 32);
+            if (sl_elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        if (kk < nmma) {
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int t = 0; t < kSlabMaxTiles; ++t) {
+                        if (kk < nmma && t < Tc) {
                             const uint32_t acc = (kc | kk) != 0 ? 1u : 0u;
                             asm volatile(
-                                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(dt),
-                                "l"(ad[kk]), "l"(bd0 + static_cast<uint64_t>(kk * 2 * NT)), "r"(kIdesc), "r"(acc)
+                                "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+                                "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
+                                "r"(alo + aoff[kk] + static_cast<uint32_t>(t * 128)), "r"(ahi), "r"(blo + static_cast<uint32_t>(kk * 2 * NT)),
+                                "r"(bhi), "r"(kIdesc), "r"(acc)
                                 : "memory");
                         }
                     }
                 }
-                __syncwarp();
-            }
-            if (sl_elect_one()) {
                 sl_commit(&empty[stg]);
                 if (kc == a.nk - 1) sl_commit(accum);
             }
@@ -276,12 +285,13 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
     }
 
     // ---- epilogue ----
-    if (a.staged) {
-        // Every warp owns 32 accumulator lanes (warp % 4) and every second (tile, 32-column chunk) unit (warp / 4).
+    {
+        // Every warp owns 32 accumulator lanes (warp % 4) and every kGroups-th (tile, 32-column chunk) unit (warp / 4).
         // A unit goes TMEM -> registers -> a warp-private [32 rows][32 + 4 floats] staging tile in the dead slab ->
         // global memory with eight lanes per row: each store instruction writes four whole 128-byte lines (the
         // direct path below writes 16 bytes into each of 32 lines), the residual is read the same way.
         constexpr int kChunks = NT / 32;
+        constexpr int kGroups = kSlabThreads / 128;
         const int quarter = warp & 3, half = warp >> 2;
         float* stg = reinterpret_cast<float*>(slab) + warp * (32 * 36);
         const int seg = lane & 7, rsub = lane >> 3;
@@ -289,8 +299,9 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
         // per unit and lane: the eight output rows (4i + rsub), their pixel offsets and residual values; the residual
         // of a unit is requested before its accumulator is touched (for the first unit: before the MMAs are even
         // waited for), so its memory round trip overlaps the tensor work instead of serialising row by row
-        long long pixoff[8];
-        float4 rr[8];
+        int pixoff[8];                          // pixel index inside the image, -1: junk row
+        const long long imgbase = static_cast<long long>(img) * a.img_pixels;
+        float4 rr[RES ? 8 : 1];
         auto prefetch = [&](int u) {
             const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
             const int qb = q0 + t * 128 + quarter * 32 + rsub;
@@ -299,9 +310,9 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
                 const int q = qb + 4 * i;
                 const int so = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), fo = q - so * a.Fp;
                 const bool valid = q < out_pixels && fo < a.F;
-                pixoff[i] = valid ? static_cast<long long>(img) * a.img_pixels + (so * a.pixS + fo * a.pixF) : -1;
-                rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid && a.res) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res + pixoff[i] * a.res_row_stride + col0) + seg);
+                pixoff[i] = valid ? so * a.pixS + fo * a.pixF : -1;
+                if (RES) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (RES && valid) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res + (imgbase + pixoff[i]) * a.res_row_stride + col0) + seg);
             }
         };
         const int nunits = Tc * kChunks;
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
         sl_wait(accum, 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 64) stamp(6);
-        for (int u = half; u < nunits; u += 2) {
+        for (int u = half; u < nunits; u += kGroups) {
             const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
             uint32_t r[32];
             const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * NT + col0);
@@ -331,55 +342,13 @@ __global__ void __launch_bounds__(kSlabThreads, 2) conv_slab_kernel(const SlabAr
             for (int i = 0; i < 8; ++i) {     // rows 4i .. 4i+3 of the warp's 32, eight lanes (128 B) per row
                 if (pixoff[i] >= 0) {
                     const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * seg);
-                    *(reinterpret_cast<float4*>(a.y + pixoff[i] * NT + col0) + seg) =
-                        make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w);
+                    *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) =
+                        RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
+                            : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
                 }
             }
             __syncwarp();                     // the staging tile is rewritten by the next unit
-            if (u + 2 < nunits) prefetch(u + 2);
-        }
-    } else {
-        // direct: every warp owns 32 accumulator lanes (warp % 4) and one half of the columns (warp / 4)
-        const int quarter = warp & 3, chalf = warp >> 2;
-        constexpr int kColsPerWarp = NT / 2;
-        sl_wait(accum, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tid == 64) stamp(6);
-        const long long out_pixels = static_cast<long long>(a.S) * a.Fp;
-        for (int t = 0; t < Tc; ++t) {
-            const int q = q0 + t * 128 + quarter * 32 + lane;
-            const int so = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), fo = q - so * a.Fp;
-            const bool valid = q < out_pixels && fo < a.F;
-            const long long pix = static_cast<long long>(img) * a.img_pixels + (valid ? so * a.pixS + fo * a.pixF : 0);
-#pragma unroll
-            for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
-                const int col = chalf * kColsPerWarp + c0;
-                uint32_t r[16];
-                const uint32_t taddr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * NT + col);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
-                    "%13, %14, %15}, [%16];\n"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (valid) {
-                    const float4* bias = reinterpret_cast<const float4*>(a.bias + col);
-                    float4* dst = reinterpret_cast<float4*>(a.y + pix * NT + col);
-                    const float4* rs = a.res ? reinterpret_cast<const float4*>(a.res + pix * a.res_row_stride + col) : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 bv = __ldg(bias + j);
-                        float4 o = make_float4(__uint_as_float(r[4 * j]) + bv.x, __uint_as_float(r[4 * j + 1]) + bv.y,
-                                               __uint_as_float(r[4 * j + 2]) + bv.z, __uint_as_float(r[4 * j + 3]) + bv.w);
-                        if (rs) {
-                            const float4 rr = rs[j];
-                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                        }
-                        dst[j] = o;
-                    }
-                }
-            }
+            if (u + kGroups < nunits) prefetch(u + kGroups);
         }
     }
     if (tid == 64) stamp(7);
@@ -405,14 +374,15 @@ bool slab_enabled() {
 long long* g_slab_stamps = nullptr;       // mmla_debug_conv_slab_stamps: 64 rows (launch ordinal) x 16 slots
 int g_slab_stamp_cta = 0, g_slab_stamp_row = 0;
 
-template <int NT>
+template <int NT, bool RES, int THREADS>
 int launch_slab(const SlabArgs& s, long long images, size_t smem, cudaStream_t st) {
     static size_t attr = 0;
     if (smem > attr) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(conv_slab_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(conv_slab_kernel<NT, RES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)));
         attr = smem;
     }
-    conv_slab_kernel<NT><<<static_cast<unsigned>(images * s.cpi), kSlabThreads, smem, st>>>(s);
+    conv_slab_kernel<NT, RES, THREADS><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
     mmla_count_launch("conv_slab_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
@@ -460,7 +430,8 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
         if (a.Cin == 16) { while ((r & 7) != 2) ++r; } else if ((r & 1) == 0) ++r;     // conflict-free fill stores
         return r;
     };
-    constexpr size_t kStagingBytes = 8 * 32 * 36 * 4;           // epilogue staging tiles live in the dead slab
+    int threads = a.res ? 256 : 512;
+    size_t kStagingBytes = static_cast<size_t>(threads / 32) * 32 * 36 * 4;   // epilogue staging tiles (one per warp) live in the dead slab
     constexpr size_t kBarBytes = 1024 + 128;                    // mbarriers + alignment slack
     auto slab_bytes = [&](int T) {
         const size_t b = static_cast<size_t>(a.Cin / 4) * slab_rows(T) * 16;
@@ -481,9 +452,15 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
     const int min2 = s.nk < 2 ? s.nk : 2;
     int T = 0;
     double best = 0.0;
-    const int budgets_kb[2] = {113, 226};              // two CTAs or one CTA per SM (~105 registers: no third)
-    const double overlap[2] = {1.7, 1.0};
-    for (int bi = 0; bi < 2; ++bi) {
+    // three (256 threads, no residual), two or one CTA per SM
+    const int budgets_kb[3] = {75, 113, 226};
+    double overlap[3] = {4.5, 3.2, 1.0};             // measured: co-resident CTAs in different phases are what pays (sweep_conv_slab_v9)
+    if (const char* e = getenv("MMLA_CONV_SLAB_OVL3")) overlap[0] = atof(e);
+    if (const char* e = getenv("MMLA_CONV_SLAB_OVL2")) overlap[1] = atof(e);
+    int best_bi = 1;
+    for (int bi = a.res ? 1 : 0; bi < 3; ++bi) {
+        const int nthr = a.res || bi == 0 ? 256 : 512;
+        kStagingBytes = static_cast<size_t>(nthr / 32) * 32 * 36 * 4;
         const size_t budget = static_cast<size_t>(force_kb >= 16 && force_kb <= 226 ? force_kb : budgets_kb[bi]) * 1024;
         for (int t = 1; t <= tmax; ++t) {
             if (force_t >= 1 && force_t <= tmax && t != force_t) continue;
@@ -495,17 +472,19 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
             const double per_chunk = t * 4.0 * (a.N / 2 > 45 ? a.N / 2 : 45);
             const double refill = (3000.0 + per_chunk) / stages;
             const double mma = s.nk * (per_chunk > refill ? per_chunk : refill);
-            const double fill = 5000.0 + slab_rows(t) * (a.Cin / 4) / 256.0 * 40.0;
+            const double fill = 5000.0 + slab_rows(t) * (a.Cin / 4) / static_cast<double>(nthr) * 40.0;
             const double epi = 3000.0 + 700.0 * t * (a.N / 32);
             // useful tiles: the last CTA of an image may be partly empty
             const int cpi = (s.tiles + t - 1) / t;
             const double cost = (fill + mma + epi) * cpi / overlap[bi] / s.tiles;
             if (!T || cost < best) {
-                T = t; best = cost; s.stages = stages;
+                T = t; best = cost; s.stages = stages; best_bi = bi;
             }
         }
     }
     MMLA_REQUIRE(T > 0, MMLA_EUNSUP, "conv_slab: layer does not fit in shared memory (Cin %d, halo %d rows)", a.Cin, halo);
+    threads = a.res || best_bi == 0 ? 256 : 512;
+    kStagingBytes = static_cast<size_t>(threads / 32) * 32 * 36 * 4;
     const size_t ring = s.stages * chunk;
     s.T = T;
     s.nmma_last = 0;
@@ -523,13 +502,11 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
     s.cpi = (s.tiles + T - 1) / T;
     s.Rs = slab_rows(T);
     s.ring_off = static_cast<unsigned>((slab_bytes(T) + 127) / 128 * 128);
-    s.staged = 1;
-    if (const char* e = getenv("MMLA_CONV_SLAB_EPI")) s.staged = e[0] != '0';
     s.bar_off = s.ring_off + static_cast<unsigned>(ring);
     const size_t smem = s.bar_off + kBarBytes;
     if (getenv("MMLA_CONV_SLAB_VERBOSE"))
-        fprintf(stderr, "conv_slab: %dx%d Cin %d N %d k %dx%d: %d tiles/image, T %d, %d CTAs/image, ring %d of %d chunks, %zu KB smem\n",
-                a.H, a.W, a.Cin, a.N, a.kh, a.kw, s.tiles, s.T, s.cpi, s.stages, s.nk, smem / 1024);
+        fprintf(stderr, "conv_slab: %dx%d Cin %d N %d k %dx%d: %d tiles/image, T %d, %d CTAs/image, ring %d of %d chunks, %zu KB smem, %d threads\n",
+                a.H, a.W, a.Cin, a.N, a.kh, a.kw, s.tiles, s.T, s.cpi, s.stages, s.nk, smem / 1024, threads);
     if (g_slab_stamps && g_slab_stamp_row < 64) {
         s.stamps = g_slab_stamps + 16 * g_slab_stamp_row++;
         s.stamp_cta = static_cast<int>((static_cast<long long>(g_slab_stamp_cta) % images) * s.cpi + s.cpi / 2);   // a mid-image CTA
@@ -537,10 +514,24 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
     MMLA_REQUIRE(static_cast<long long>(s.tiles) * 128 + halo < (1LL << 20), MMLA_EUNSUP, "conv_slab: image too large");
     MMLA_REQUIRE(images * s.cpi < (1LL << 31) && images * s.img_pixels * (a.Cin > a.N ? a.Cin : a.N) < (1LL << 40), MMLA_EUNSUP,
                  "conv_slab: batch too large");
+    if (a.res) {
+        switch (a.N) {
+            case 32: return launch_slab<32, true, 256>(s, images, smem, st);
+            case 64: return launch_slab<64, true, 256>(s, images, smem, st);
+            default: return launch_slab<128, true, 256>(s, images, smem, st);
+        }
+    }
+    if (threads == 256) {
+        switch (a.N) {
+            case 32: return launch_slab<32, false, 256>(s, images, smem, st);
+            case 64: return launch_slab<64, false, 256>(s, images, smem, st);
+            default: return launch_slab<128, false, 256>(s, images, smem, st);
+        }
+    }
     switch (a.N) {
-        case 32: return launch_slab<32>(s, images, smem, st);
-        case 64: return launch_slab<64>(s, images, smem, st);
-        default: return launch_slab<128>(s, images, smem, st);
+        case 32: return launch_slab<32, false, 512>(s, images, smem, st);
+        case 64: return launch_slab<64, false, 512>(s, images, smem, st);
+        default: return launch_slab<128, false, 512>(s, images, smem, st);
     }
 }
 

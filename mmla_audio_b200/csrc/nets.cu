@@ -231,6 +231,36 @@ __global__ void __launch_bounds__(256) pad_channels_kernel(const float* __restri
 }
 
 // overlap: Lambda(mean over axis 1 = H): [B,H,W,C] -> [B,W,C]
+// Overlap-net stem Conv2D(16, 1x1) on the 3-channel classifier input (overlap_detector_temp.py:283): a per-pixel
+// 3 -> 16 affine map, i.e. a streaming kernel (3 bytes in, 64 bytes out per pixel).  Four lanes share a pixel and
+// write one float4 each, so a warp store covers 512 contiguous bytes.  (Through the im2col tensor-core kernel the
+// layer padded K = 3 to 32 and took 0.81 ms per 512 clips; this is bound by the 633 MB it writes.)
+__global__ void __launch_bounds__(256) stem1x1_kernel(const void* __restrict__ x, int x_is_u8, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ y, long long pixels) {
+    const int quad = threadIdx.x & 3;
+    const float4 w0 = *reinterpret_cast<const float4*>(w + 4 * quad);          // w[k][16], k = 0..2
+    const float4 w1 = *reinterpret_cast<const float4*>(w + 16 + 4 * quad);
+    const float4 w2 = *reinterpret_cast<const float4*>(w + 32 + 4 * quad);
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * quad);
+    const long long stride = static_cast<long long>(gridDim.x) * (blockDim.x >> 2);
+    for (long long p = static_cast<long long>(blockIdx.x) * (blockDim.x >> 2) + (threadIdx.x >> 2); p < pixels; p += stride) {
+        float c0, c1, c2;
+        if (x_is_u8) {
+            const unsigned char* px = static_cast<const unsigned char*>(x) + 3 * p;
+            c0 = static_cast<float>(px[0]); c1 = static_cast<float>(px[1]); c2 = static_cast<float>(px[2]);
+        } else {
+            const float* px = static_cast<const float*>(x) + 3 * p;
+            c0 = px[0]; c1 = px[1]; c2 = px[2];
+        }
+        float4 o;
+        o.x = fmaf(c2, w2.x, fmaf(c1, w1.x, fmaf(c0, w0.x, b.x)));
+        o.y = fmaf(c2, w2.y, fmaf(c1, w1.y, fmaf(c0, w0.y, b.y)));
+        o.z = fmaf(c2, w2.z, fmaf(c1, w1.z, fmaf(c0, w0.z, b.z)));
+        o.w = fmaf(c2, w2.w, fmaf(c1, w1.w, fmaf(c0, w0.w, b.w)));
+        *reinterpret_cast<float4*>(y + p * 16 + 4 * quad) = o;
+    }
+}
+
 __global__ void __launch_bounds__(256) mean_h_kernel(const float* __restrict__ x, float* __restrict__ y, long long B,
                                                      int H, int W, int C) {
     const long long total = B * W * C;
@@ -747,6 +777,14 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         } else if (pad40) {
             mmla_set_error("net_forward: 40-channel input needs the TF32 tensor-core mode");
             return MMLA_EUNSUP;
+        } else if (ov && tc && net->stem.kh == 1 && net->stem.kw == 1 && net->stem.cin == 3 && net->stem.cout == 16) {
+            const long long pixels = B * H * W;
+            if (pixels > 0) {
+                stem1x1_kernel<<<ew_grid(pixels * 4), 256, 0, st>>>(xin, x_is_u8, net->stem.k, net->stem.b, buf[cur], pixels);
+                mmla_count_launch("stem1x1_kernel", st);
+                MMLA_CUDA_CHECK(cudaGetLastError());
+            }
+            rc = 0;
         } else {
             rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
         }
