@@ -225,6 +225,7 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     h, w_ = H0, T0
     res = 0.0
     slab = 0.0                                   # overlap: the stride-1 3x3 / 4x1 convs (conv_slab_kernel)
+    pool_bytes = 0.0                             # overlap: pool_shortcut_kernel's compulsory traffic
     res_first_stage = 0.0                        # the first three residual units (the stage the stem is folded into)
     stem = 2.0 * h * w_ * spec.stem.kh * spec.stem.kw * spec.stem.cin * spec.stem.cout
     for bi, blk in enumerate(spec.blocks):
@@ -242,6 +243,7 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
             res += 2.0 * h2 * w2 * blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout
         if blk.shortcut is not None:
             res += 2.0 * h2 * w2 * blk.shortcut.cin * blk.shortcut.cout
+            pool_bytes += 4.0 * (h * w_ * blk.conv2.cout + h2 * w2 * blk.shortcut.cin + h2 * w2 * blk.shortcut.cout)
         h, w_ = h2, w2
         if bi == 2:
             res_first_stage = res
@@ -273,6 +275,9 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
                                     "what": "the 18 stride-1 3x3 / 4x1 convolutions of the residual blocks (TF32, tap-shifted slabs)"}
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (res - slab),
                                   "what": "the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
+        work["pool_shortcut_kernel"] = {"bound": "hbm", "per_step": B * pool_bytes,
+                                        "what": "per pooled block: full-resolution conv output in + every other block-input pixel in "
+                                                "+ pooled output out (MaxPool2x2 + stride-2 1x1 shortcut + add)"}
         work["stem1x1_kernel"] = {"bound": "hbm", "per_step": B * H0 * T0 * (3 + 16 * 4),
                                   "what": "uint8 [128,151,3] image in + float32 [128,151,16] stem activations out"}
     return work

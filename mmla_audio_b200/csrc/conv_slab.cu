@@ -471,7 +471,9 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
             if (force_stages >= 1 && force_stages <= stages) stages = force_stages;
             const double per_chunk = t * 4.0 * (a.N / 2 > 45 ? a.N / 2 : 45);
             const double refill = (3000.0 + per_chunk) / stages;
-            const double mma = s.nk * (per_chunk > refill ? per_chunk : refill);
+            const double stream = chunk / 28.0;       // one producer lane streams ~28 B/clk of weights from L2 (T = 1, N = 128: 25-27 k cycles for 590 KB)
+            double mma = per_chunk > refill ? per_chunk : refill;
+            mma = s.nk * (mma > stream ? mma : stream);
             const double fill = 5000.0 + slab_rows(t) * (a.Cin / 4) / static_cast<double>(nthr) * 40.0;
             const double epi = 3000.0 + 700.0 * t * (a.N / 32);
             // useful tiles: the last CTA of an image may be partly empty

@@ -231,6 +231,55 @@ __global__ void __launch_bounds__(256) pad_channels_kernel(const float* __restri
 }
 
 // overlap: Lambda(mean over axis 1 = H): [B,H,W,C] -> [B,W,C]
+// Tail of a pooled res_block of the overlap net (overlap_detector_temp.py:262-270) in one pass:
+//   y = MaxPool2x2/2 'same'(z) + Conv2D(N, 1x1, stride 2)(x) + bias
+// z = the block's second conv at full resolution [B,H,W,N], x = the block input [B,H,W,Cin].  One thread owns four output
+// channels of one pooled pixel; the [Cin][N] shortcut weights sit in shared memory; the products are exact fp32 FMAs
+// (K = Cin <= 64 is too short for the tensor-core path to pay: the separate maxpool_kernel + im2col conv_tc_kernel pair
+// took 0.88 ms per 512 clips, this is bound by reading z once).
+__global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restrict__ x, const float* __restrict__ z,
+                                                            const float* __restrict__ ws, const float* __restrict__ bs,
+                                                            float* __restrict__ y, long long B, int H, int W, int Cin, int N) {
+    extern __shared__ float4 wsm4[];                  // [Cin][N / 4]
+    for (int i = threadIdx.x; i < Cin * N / 4; i += blockDim.x) wsm4[i] = reinterpret_cast<const float4*>(ws)[i];
+    __syncthreads();
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, Q = N / 4;
+    const long long total = B * Ho * Wo * Q;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int q = static_cast<int>(idx % Q);
+        const long long p = idx / Q;
+        const int wo = static_cast<int>(p % Wo);
+        const long long t = p / Wo;
+        const int ho = static_cast<int>(t % Ho);
+        const long long b = t / Ho;
+        const int h0 = 2 * ho, w0 = 2 * wo;
+        const long long pin = (b * H + h0) * W + w0;
+        const float* zb = z + pin * N + 4 * q;
+        float4 m = *reinterpret_cast<const float4*>(zb);
+        auto mx = [&](const float* ptr) {
+            const float4 v = *reinterpret_cast<const float4*>(ptr);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        };
+        if (w0 + 1 < W) mx(zb + N);                    // 'same' pooling: the missing right / bottom neighbours are -inf
+        if (h0 + 1 < H) {
+            mx(zb + static_cast<long long>(W) * N);
+            if (w0 + 1 < W) mx(zb + static_cast<long long>(W) * N + N);
+        }
+        const float* xb = x + pin * Cin;
+        float4 acc = *reinterpret_cast<const float4*>(bs + 4 * q);
+        for (int c = 0; c < Cin; c += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(xb + c);
+            const float4 w0v = wsm4[(c + 0) * Q + q], w1v = wsm4[(c + 1) * Q + q], w2v = wsm4[(c + 2) * Q + q], w3v = wsm4[(c + 3) * Q + q];
+            acc.x = fmaf(xv.x, w0v.x, acc.x); acc.y = fmaf(xv.x, w0v.y, acc.y); acc.z = fmaf(xv.x, w0v.z, acc.z); acc.w = fmaf(xv.x, w0v.w, acc.w);
+            acc.x = fmaf(xv.y, w1v.x, acc.x); acc.y = fmaf(xv.y, w1v.y, acc.y); acc.z = fmaf(xv.y, w1v.z, acc.z); acc.w = fmaf(xv.y, w1v.w, acc.w);
+            acc.x = fmaf(xv.z, w2v.x, acc.x); acc.y = fmaf(xv.z, w2v.y, acc.y); acc.z = fmaf(xv.z, w2v.z, acc.z); acc.w = fmaf(xv.z, w2v.w, acc.w);
+            acc.x = fmaf(xv.w, w3v.x, acc.x); acc.y = fmaf(xv.w, w3v.y, acc.y); acc.z = fmaf(xv.w, w3v.z, acc.z); acc.w = fmaf(xv.w, w3v.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(y + p * N + 4 * q) = make_float4(m.x + acc.x, m.y + acc.y, m.z + acc.z, m.w + acc.w);
+    }
+}
+
 // Overlap-net stem Conv2D(16, 1x1) on the 3-channel classifier input (overlap_detector_temp.py:283): a per-pixel
 // 3 -> 16 affine map, i.e. a streaming kernel (3 bytes in, 64 bytes out per pixel).  Four lanes share a pixel and
 // write one float4 each, so a warp store covers 512 contiguous bytes.  (Through the im2col tensor-core kernel the
@@ -846,6 +895,19 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
                 if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st, tc))) return rc;
                 const int Ho = same_out(H, 2), Wo = same_out(W, 2), C = blk.conv2.cout;
+                const char* fp = getenv("MMLA_NET_FUSE_POOL");
+                const size_t wbytes = static_cast<size_t>(blk.shortcut.cin) * C * sizeof(float);
+                if (tc && !(fp && fp[0] == '0') && blk.shortcut.kh == 1 && blk.shortcut.kw == 1 && blk.shortcut.stride == 2 &&
+                    blk.shortcut.cin % 4 == 0 && C % 4 == 0 && wbytes <= 48 * 1024) {
+                    // MaxPool + stride-2 shortcut + add in one pass (reads X and Bf, writes A)
+                    pool_shortcut_kernel<<<ew_grid(B * Ho * Wo * C / 4), 256, wbytes, st>>>(X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W,
+                                                                                          blk.shortcut.cin, C);
+                    mmla_count_launch("pool_shortcut_kernel", st);
+                    MMLA_CUDA_CHECK(cudaGetLastError());
+                    H = Ho; W = Wo;
+                    cur = (cur + 1) % 3;
+                    continue;
+                }
                 maxpool_kernel<<<ew_grid(B * Ho * Wo * C / 4), 256, 0, st>>>(Bf, A, static_cast<int>(B), H, W, C, 2, 2, Ho, Wo);
                 mmla_count_launch("maxpool_kernel", st);
                 MMLA_CUDA_CHECK(cudaGetLastError());
