@@ -33,7 +33,7 @@
 namespace {
 
 constexpr int kSlabBK = 32;                 // K per ring chunk (matches mmla_tc_arrange_weights)
-constexpr int kSlabMaxTiles = 4;
+constexpr int kSlabMaxTiles = 4;             // (8 was tried: the 32-MMA elected region issues slower, every layer lost 5-10 %)
 constexpr int kSlabMaxStages = 40;
 constexpr int kSlabMaxChunks = 64;         // K <= 2048
 
@@ -452,35 +452,36 @@ int mmla_launch_conv_slab(const ConvArgs& a, const float* wg, cudaStream_t st) {
     const int min2 = s.nk < 2 ? s.nk : 2;
     int T = 0;
     double best = 0.0;
-    // three (256 threads, no residual), two or one CTA per SM
-    const int budgets_kb[3] = {75, 113, 226};
-    double overlap[3] = {4.5, 3.2, 1.0};             // measured: co-resident CTAs in different phases are what pays (sweep_conv_slab_v9)
-    if (const char* e = getenv("MMLA_CONV_SLAB_OVL3")) overlap[0] = atof(e);
-    if (const char* e = getenv("MMLA_CONV_SLAB_OVL2")) overlap[1] = atof(e);
     int best_bi = 1;
-    for (int bi = a.res ? 1 : 0; bi < 3; ++bi) {
-        const int nthr = a.res || bi == 0 ? 256 : 512;
-        kStagingBytes = static_cast<size_t>(nthr / 32) * 32 * 36 * 4;
-        const size_t budget = static_cast<size_t>(force_kb >= 16 && force_kb <= 226 ? force_kb : budgets_kb[bi]) * 1024;
-        for (int t = 1; t <= tmax; ++t) {
-            if (force_t >= 1 && force_t <= tmax && t != force_t) continue;
-            if (bytes(t, min2) > budget) continue;
-            int stages = static_cast<int>((budget - slab_bytes(t) - kBarBytes) / chunk);
-            if (stages > s.nk) stages = s.nk;
-            if (stages > kSlabMaxStages) stages = kSlabMaxStages;
-            if (force_stages >= 1 && force_stages <= stages) stages = force_stages;
-            const double per_chunk = t * 4.0 * (a.N / 2 > 45 ? a.N / 2 : 45);
-            const double refill = (3000.0 + per_chunk) / stages;
-            const double stream = chunk / 28.0;       // one producer lane streams ~28 B/clk of weights from L2 (T = 1, N = 128: 25-27 k cycles for 590 KB)
-            double mma = per_chunk > refill ? per_chunk : refill;
-            mma = s.nk * (mma > stream ? mma : stream);
-            const double fill = 5000.0 + slab_rows(t) * (a.Cin / 4) / static_cast<double>(nthr) * 40.0;
-            const double epi = 3000.0 + 700.0 * t * (a.N / 32);
-            // useful tiles: the last CTA of an image may be partly empty
-            const int cpi = (s.tiles + t - 1) / t;
-            const double cost = (fill + mma + epi) * cpi / overlap[bi] / s.tiles;
-            if (!T || cost < best) {
-                T = t; best = cost; s.stages = stages; best_bi = bi;
+    for (int pass = 0; pass < 2 && !T; ++pass) {       // pass 1: a forced tile count / budget that fits nowhere is ignored
+        if (pass == 1) force_t = force_kb = 0;
+        // three (256 threads, no residual), two or one CTA per SM
+        const int budgets_kb[3] = {75, 113, 226};
+        double overlap[3] = {4.5, 3.2, 1.0};             // measured: co-resident CTAs in different phases are what pays (sweep_conv_slab_v9)
+        if (const char* e = getenv("MMLA_CONV_SLAB_OVL3")) overlap[0] = atof(e);
+        if (const char* e = getenv("MMLA_CONV_SLAB_OVL2")) overlap[1] = atof(e);
+        for (int bi = a.res ? 1 : 0; bi < 3; ++bi) {
+            const int nthr = a.res || bi == 0 ? 256 : 512;
+            kStagingBytes = static_cast<size_t>(nthr / 32) * 32 * 36 * 4;
+            const size_t budget = static_cast<size_t>(force_kb >= 16 && force_kb <= 226 ? force_kb : budgets_kb[bi]) * 1024;
+            for (int t = 1; t <= tmax; ++t) {
+                if (force_t >= 1 && force_t <= tmax && t != force_t) continue;
+                if (bytes(t, min2) > budget) continue;
+                int stages = static_cast<int>((budget - slab_bytes(t) - kBarBytes) / chunk);
+                if (stages > s.nk) stages = s.nk;
+                if (stages > kSlabMaxStages) stages = kSlabMaxStages;
+                if (force_stages >= 1 && force_stages <= stages) stages = force_stages;
+                const double per_chunk = t * 4.0 * (a.N / 2 > 45 ? a.N / 2 : 45);
+                const double refill = (3000.0 + per_chunk) / stages;
+                const double mma = s.nk * (per_chunk > refill ? per_chunk : refill);
+                const double fill = 5000.0 + slab_rows(t) * (a.Cin / 4) / static_cast<double>(nthr) * 40.0;
+                const double epi = 3000.0 + 700.0 * t * (a.N / 32);
+                // useful tiles: the last CTA of an image may be partly empty
+                const int cpi = (s.tiles + t - 1) / t;
+                const double cost = (fill + mma + epi) * cpi / overlap[bi] / s.tiles;
+                if (!T || cost < best) {
+                    T = t; best = cost; s.stages = stages; best_bi = bi;
+                }
             }
         }
     }
