@@ -174,3 +174,27 @@ def test_fused_stages_match_per_unit_kernels(cuda, monkeypatch):
         print(f"stage-fused vs per-unit, {n} clips: max |dprob| {d:.2e}")
         assert d <= 5e-4
         assert (lu == ls).float().mean().item() >= 0.99
+
+
+def test_overlap_tf32_batch_invariance_and_fp32_agreement(cuda):
+    """Overlap net on the tensor-core path (conv_slab_kernel / stem1x1_kernel / pool_shortcut_kernel / fused LSTM):
+    a clip's probabilities do not depend on the batch it is in (bit-exact: every image is tiled on its own), and on a
+    bench-like batch the TF32 labels agree with the fp32 CUDA-core path (>= 95 %, |dprob| <= 5e-3)."""
+    from mmla_audio_b200 import models, weights as W
+    torch = cuda
+    spec = W.OVERLAP
+    w = W.synthetic_weights(spec, 1234)
+    mtc = models.Model(spec, w, precision="tf32")
+    m32 = models.Model(spec, w, precision="fp32")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randint(0, 256, (70, 128, 151, 3), dtype=torch.uint8, device="cuda", generator=g)
+    p_all, l_all = mtc.predict_device(x)
+    p_one, l_one = mtc.predict_device(x[41:42].contiguous())
+    p_few, l_few = mtc.predict_device(x[63:].contiguous())
+    assert torch.equal(p_all[41:42], p_one) and torch.equal(l_all[41:42], l_one)
+    assert torch.equal(p_all[63:], p_few) and torch.equal(l_all[63:], l_few)
+    p32, l32 = m32.predict_device(x)
+    agree = (l32 == l_all).float().mean().item()
+    d = (p32 - p_all).abs().max().item()
+    print("overlap tf32 vs fp32 on 70 clips: label agreement", agree, "max |dprob|", d)
+    assert agree >= 0.95 and d <= 5e-3
