@@ -304,7 +304,10 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     a = ap.parse_args()
     wl = dict(WORKLOADS[a.workload])
-    if a.clips:
+    if a.clips and a.clips != wl["clips"]:
+        # keep the label honest: "..._x512" -> "..._x19200" when --clips overrides the workload's batch
+        wl["name"] = wl["name"].replace("_x%d" % wl["clips"], "_x%d" % a.clips) if ("_x%d" % wl["clips"]) in wl["name"] \
+            else "%s_x%d" % (wl["name"], a.clips)
         wl["clips"] = a.clips
     if a.impl == "reference":
         run_reference_arm(a, wl)
