@@ -151,3 +151,32 @@ def test_host_pipeline_sync_and_pipelined(cuda):
     for i in (1, 2, 3):
         lab, cnt = pending[i].result()
         assert np.array_equal(lab, want[i][0]) and np.array_equal(cnt, want[i][1])
+
+
+def test_config4_full_size_8h_overlap_session_properties(cuda):
+    """BASELINE configs[3] at full size: an 8 h recording (460.8 M samples) -> 19 200 windows of 1.5 s through the
+    tensor-core overlap pipeline.  Too large for the oracle, so the checks are size-independent properties:
+    the window count of the reference's index math, tallies that sum to the window count, a second pass that gives
+    identical labels (determinism), the same labels when the session is processed in two halves with another chunk
+    size (batch independence across micro-batch boundaries), and agreement with the oracle-checked small-session path
+    on the first windows."""
+    from mmla_audio_b200 import models, synth as dsynth, weights as W
+    from mmla_audio_b200.pipeline import OverlapPipeline, segmentation_windows
+    torch = cuda
+    pipe = OverlapPipeline(models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234), precision="tf32"))
+    n_win, win = 19200, 24000
+    rec = dsynth.synth_clips(7000, n_win, win).reshape(-1)          # int16 CUDA, 8 h at 16 kHz
+    assert rec.numel() == 8 * 3600 * 16000
+    assert segmentation_windows(rec.numel(), win, win) == otally.num_windows(rec.numel(), win, win) == n_win
+    t0 = datetime(2021, 6, 1, 9, 0, 0, 123456)
+    labels, (counts, secs, total) = pipe.run_session(rec, t0=t0)
+    assert labels.numel() == n_win and sum(counts.values()) == n_win
+    assert abs(total - (n_win - 1) * 1.5) <= 1                      # t_last - t_first in whole seconds
+    labels2, (counts2, _, _) = pipe.run_session(rec, t0=t0)
+    assert torch.equal(labels, labels2) and counts == counts2
+    half = (n_win // 2) * win
+    la, _ = pipe.run_session(rec[:half], t0=t0, chunk=1000)
+    lb, _ = pipe.run_session(rec[half:], t0=t0, chunk=777)
+    assert torch.equal(labels, torch.cat([la, lb]))
+    small, _ = pipe.run_session(rec[: 40 * win], t0=t0)
+    assert torch.equal(labels[:40], small)
