@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
         //  cp.async wait against 10-30 k cycles of address arithmetic and activation at one row per iteration)
         unsigned long long okmask = 0ull;                     // bit i: row r0 + i * rpp holds image data
         const int r0 = (warp >> lqg) * 8 + (lane & 7);
-        for (int it = 0; r0 + it * rpp < rows; it += 4) {
+        auto copy_batch = [&](int it) {                       // rows r0 + (it .. it+3) * rpp: one cp.async group
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int r = r0 + (it + u) * rpp;
@@ -188,11 +188,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
                                  : "memory");
                 }
             }
-        }
-        if (tid == 0) stamp(9);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        if (tid == 0) stamp(10);
-        for (int it = 0; r0 + it * rpp < rows; it += 4) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto xform_batch = [&](int it) {
             uint4 raw[4];
             const unsigned m4 = static_cast<unsigned>(okmask >> it) & 15u;
 #pragma unroll
@@ -214,7 +212,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
                         make_uint4(sl_tf32(w.x) & keep, sl_tf32(w.y) & keep, sl_tf32(w.z) & keep, sl_tf32(w.w) & keep);
                 }
             }
+        };
+        // Software pipeline over batches of four rows: batch i is activated while batches i+1 .. i+kAhead are still
+        // landing, so a warp that the memory system holds back in its copies leaves the issue slots to warps that are
+        // activating (copy-everything-then-activate-everything had every warp in the same phase at the same time).
+        constexpr int kAhead = 3;
+        int it = 0;
+        for (; r0 + it * rpp < rows; it += 4) {
+            copy_batch(it);
+            if (it >= 4 * kAhead) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");
+                xform_batch(it - 4 * kAhead);
+            }
         }
+        if (tid == 0) stamp(9);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (tid == 0) stamp(10);
+        for (int jt = it >= 4 * kAhead ? it - 4 * kAhead : 0; jt < it; jt += 4) xform_batch(jt);
     }
     if (tid == 0) stamp(2);
     fence_proxy_async_smem();                // generic-proxy slab writes -> visible to the tensor core
