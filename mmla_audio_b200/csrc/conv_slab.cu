@@ -72,6 +72,43 @@ __device__ __forceinline__ void sl_wait(uint64_t* bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return;
     asm volatile("trap;");
 }
+// Wait of the epilogue warps for the accumulators: they have nothing to do for the whole MMA phase, so every poll asks
+// the hardware to suspend the thread for up to ~10 us (suspend-time hint) instead of re-issuing try_wait + branch every
+// few hundred cycles from 7-15 warps (a third of the kernel's executed instructions were such polls).
+__device__ __forceinline__ void sl_wait_long(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 21); ++i) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(10000u)
+            : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+}
+// BN + activation + TF32 rounding of one element with the activation as a COMPILE-TIME constant: with a run-time
+// `act` the compiler wrapped every element's MUFU in its own (uniform) branch — 16 branches per four rows.
+// ACT < 0: no BN / activation prologue at all (just the rounding).
+template <int V>
+struct SlInt {
+    static constexpr int value = V;
+};
+template <int ACT>
+__device__ __forceinline__ uint32_t sl_bn_act_tf32(uint32_t raw, float sc, float sh) {
+    float v = __uint_as_float(raw);
+    if (ACT >= 0) {
+        v = fmaf(v, sc, sh);
+        if (ACT == ACT_RELU) {
+            v = fmaxf(v, 0.f);
+        } else if (ACT == ACT_ELU) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+            v = v > 0.f ? v : e - 1.f;
+        }
+    }
+    return sl_tf32(v);
+}
 __device__ __forceinline__ uint64_t sl_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
            (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
@@ -190,7 +227,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        auto xform_batch = [&](int it) {
+        auto xform_batch = [&](int it, auto act_c) {
+            constexpr int ACT = decltype(act_c)::value;
             uint4 raw[4];
             const unsigned m4 = static_cast<unsigned>(okmask >> it) & 15u;
 #pragma unroll
@@ -199,17 +237,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (r0 + (it + u) * rpp < rows) {
-                    float4 w = make_float4(__uint_as_float(raw[u].x), __uint_as_float(raw[u].y), __uint_as_float(raw[u].z),
-                                           __uint_as_float(raw[u].w));
-                    if (bn) {
-                        w.x = apply_act_tc(fmaf(w.x, sc.x, sh.x), a.pre_act);
-                        w.y = apply_act_tc(fmaf(w.y, sc.y, sh.y), a.pre_act);
-                        w.z = apply_act_tc(fmaf(w.z, sc.z, sh.z), a.pre_act);
-                        w.w = apply_act_tc(fmaf(w.w, sc.w, sh.w), a.pre_act);
-                    }
                     const uint32_t keep = ((m4 >> u) & 1u) ? 0xFFFFFFFFu : 0u;         // padding rows stay zero
                     *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(r0 + (it + u) * rpp) * 16) =
-                        make_uint4(sl_tf32(w.x) & keep, sl_tf32(w.y) & keep, sl_tf32(w.z) & keep, sl_tf32(w.w) & keep);
+                        make_uint4(sl_bn_act_tf32<ACT>(raw[u].x, sc.x, sh.x) & keep, sl_bn_act_tf32<ACT>(raw[u].y, sc.y, sh.y) & keep,
+                                   sl_bn_act_tf32<ACT>(raw[u].z, sc.z, sh.z) & keep, sl_bn_act_tf32<ACT>(raw[u].w, sc.w, sh.w) & keep);
                 }
             }
         };
@@ -217,18 +248,24 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
         // landing, so a warp that the memory system holds back in its copies leaves the issue slots to warps that are
         // activating (copy-everything-then-activate-everything had every warp in the same phase at the same time).
         constexpr int kAhead = 3;
-        int it = 0;
-        for (; r0 + it * rpp < rows; it += 4) {
-            copy_batch(it);
-            if (it >= 4 * kAhead) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");
-                xform_batch(it - 4 * kAhead);
+        auto fill = [&](auto act_c) {
+            int it = 0;
+            for (; r0 + it * rpp < rows; it += 4) {
+                copy_batch(it);
+                if (it >= 4 * kAhead) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");
+                    xform_batch(it - 4 * kAhead, act_c);
+                }
             }
-        }
-        if (tid == 0) stamp(9);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        if (tid == 0) stamp(10);
-        for (int jt = it >= 4 * kAhead ? it - 4 * kAhead : 0; jt < it; jt += 4) xform_batch(jt);
+            if (tid == 0) stamp(9);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            if (tid == 0) stamp(10);
+            for (int jt = it >= 4 * kAhead ? it - 4 * kAhead : 0; jt < it; jt += 4) xform_batch(jt, act_c);
+        };
+        if (!bn) fill(SlInt<-1>{});
+        else if (a.pre_act == ACT_ELU) fill(SlInt<ACT_ELU>{});
+        else if (a.pre_act == ACT_RELU) fill(SlInt<ACT_RELU>{});
+        else fill(SlInt<ACT_NONE>{});
     }
     if (tid == 0) stamp(2);
     fence_proxy_async_smem();                // generic-proxy slab writes -> visible to the tensor core
@@ -331,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
         };
         const int nunits = Tc * kChunks;
         if (half < nunits) prefetch(half);
-        sl_wait(accum, 0u);
+        sl_wait_long(accum, 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 64) stamp(6);
         for (int u = half; u < nunits; u += kGroups) {
