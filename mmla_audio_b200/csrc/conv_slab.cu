@@ -72,21 +72,6 @@ __device__ __forceinline__ void sl_wait(uint64_t* bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return;
     asm volatile("trap;");
 }
-// Wait of the epilogue warps for the accumulators: they have nothing to do for the whole MMA phase, so every poll asks
-// the hardware to suspend the thread for up to ~10 us (suspend-time hint) instead of re-issuing try_wait + branch every
-// few hundred cycles from 7-15 warps (a third of the kernel's executed instructions were such polls).
-__device__ __forceinline__ void sl_wait_long(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 21); ++i) {
-        uint32_t ok;
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(10000u)
-            : "memory");
-        if (ok) return;
-    }
-    asm volatile("trap;");
-}
 // BN + activation + TF32 rounding of one element with the activation as a COMPILE-TIME constant: with a run-time
 // `act` the compiler wrapped every element's MUFU in its own (uniform) branch — 16 branches per four rows.
 // ACT < 0: no BN / activation prologue at all (just the rounding).
@@ -368,7 +353,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) conv_
         };
         const int nunits = Tc * kChunks;
         if (half < nunits) prefetch(half);
-        sl_wait_long(accum, 0u);
+        // ONE warp polls the accumulator mbarrier; everybody else sleeps in a hardware barrier.  (With every warp
+        // polling, try_wait + nanosleep + branch were a quarter of the kernel's executed instructions —
+        // profiles/r01/conv_slab_v15_fullres_ncu_summary.txt — taken from the issue slots of co-resident CTAs.)
+        if (warp == 0) sl_wait(accum, 0u);
+        asm volatile("bar.sync 1, %0;" ::"n"(kSlabThreads) : "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 64) stamp(6);
         for (int u = half; u < nunits; u += kGroups) {
