@@ -139,6 +139,15 @@ int mmla_psf_mfcc_rows(const int16_t* pcm, int64_t pcm_total_samples,
  * feat/out float32 [n_frames][dim]; out[t] = sum_{k=-N..N} k*feat[clamp(t+k)] / (2*sum k^2). */
 int mmla_delta(const float* feat, int64_t n_frames, int32_t dim, int32_t N, float* out, void* stream);
 
+/* Cepstral mean (variance = 0) or mean-and-variance (variance = 1) normalisation over the frames of each clip, in place:
+ * column c of clip i becomes (x - mean_t x) [/ std_t x] over rows [0, n_rows(i)) (population std; a constant column is
+ * only centred).  BASELINE.json north_star (3) lists CMVN; the reference applies none (its features are the raw
+ * MFCC + delta + delta-delta of speaker_identification.py:386-389), so this is an option, off by default.
+ * feat float32, clip i at feat + i*clip_stride floats, rows row_stride floats apart, columns [0, dim) are normalised
+ * (dim <= 64); n_rows_dev: DEVICE int32 [n_clips] real rows per clip, or NULL for the uniform n_rows. */
+int mmla_cmvn(float* feat, int64_t n_clips, int64_t clip_stride, int32_t row_stride, int32_t dim,
+              int32_t n_rows, const int32_t* n_rows_dev, int32_t variance, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Overlap-detection features.
  * Replaces OverlapFeaturesGenerator.generate_mels / generate_zcr / generate_zcr_image +

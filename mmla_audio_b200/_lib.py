@@ -11,10 +11,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmmla_b200.so")
 
-# every symbol include/mmla_b200.h declares (checked by tests/test_abi.py)
+# every symbol include/mmla_b200.h declares (checked by tests/test_host_cpu.py::test_library_exports_every_declared_symbol)
 SYMBOLS = (
     "mmla_last_error", "mmla_abi_version", "mmla_launch_count", "mmla_crc32c_host",
-    "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_psf_mfcc_rows", "mmla_delta", "mmla_overlap_features",
+    "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_psf_mfcc_rows", "mmla_delta", "mmla_cmvn", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
     "mmla_net_forward", "mmla_net_forward_cepstra",
     "mmla_tally", "mmla_synth_pcm", "mmla_debug_mfcc_tc_dump", "mmla_debug_resstage_stamps", "mmla_debug_lstm_stamps", "mmla_debug_conv2d", "mmla_debug_conv_slab_stamps", "mmla_trace_begin", "mmla_trace_end",
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
         "mmla_psf_mfcc": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, mp, vp, i64, vp]),
         "mmla_psf_mfcc_rows": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, mp, vp, i64, i32, vp]),
         "mmla_delta": (C.c_int, [vp, i64, i32, i32, vp, vp]),
+        "mmla_cmvn": (C.c_int, [vp, i64, i64, i32, i32, i32, vp, i32, vp]),
         "mmla_overlap_features": (C.c_int, [vp, i64, vp, vp, i64, i32, i64, i32, vp, vp, vp, vp, vp]),
         "mmla_net_create": (C.c_int, [i32, i32, i32, vp, i64, C.POINTER(vp)]),
         "mmla_net_destroy": (None, [vp]),

@@ -29,7 +29,21 @@ void mmla_set_error(const char* fmt, ...);
 // Called right after every kernel launch: bumps the counter mmla_launch_count() reports and, while a launch
 // trace is open (mmla_trace_begin), records a CUDA event on `st` so the kernel's device time can be read back.
 void mmla_count_launch(const char* kernel_name, cudaStream_t st);
-int mmla_num_sms();   // SM count of the current device (cached), <0 on error
+int mmla_num_sms();   // SM count of the current device (cached per device), <0 on error
+
+// `static MmlaPerDeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)`: function attributes such as
+// MaxDynamicSharedMemorySize are per DEVICE, so a per-process flag would leave a second GPU used from the same
+// process with the 48 KB default.
+struct MmlaPerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + TMA bulk copy (cp.async.bulk → SASS UBLKCP)

@@ -416,11 +416,14 @@ int g_slab_stamp_cta = 0, g_slab_stamp_row = 0;
 
 template <int NT, bool RES, int THREADS>
 int launch_slab(const SlabArgs& s, long long images, size_t smem, cudaStream_t st) {
-    static size_t attr = 0;
-    if (smem > attr) {
+    static size_t attr[64] = {};                                  // per device: function attributes are per device
+    int dev = 0;
+    MMLA_CUDA_CHECK(cudaGetDevice(&dev));
+    MMLA_REQUIRE(dev >= 0 && dev < 64, MMLA_EUNSUP, "conv_slab: device ordinal %d out of range", dev);
+    if (smem > attr[dev]) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(conv_slab_kernel<NT, RES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
-        attr = smem;
+        attr[dev] = smem;
     }
     conv_slab_kernel<NT, RES, THREADS><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
     mmla_count_launch("conv_slab_kernel", st);

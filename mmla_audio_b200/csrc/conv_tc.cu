@@ -355,11 +355,11 @@ __global__ void __launch_bounds__(256) conv_tc_kernel(const ConvArgs a, const fl
 
 template <int NT>
 int launch_nt(const ConvArgs& a, const float* wg, cudaStream_t st) {
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(TcSmem<NT>) + 1024)));
-        attr_set = true;
     }
     const dim3 grid(static_cast<unsigned>((a.M + 127) / 128), static_cast<unsigned>(a.N / NT));
     conv_tc_kernel<NT><<<grid, 256, sizeof(TcSmem<NT>) + 1024, st>>>(a, wg);

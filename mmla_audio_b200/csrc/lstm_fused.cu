@@ -443,11 +443,11 @@ long long mmla_lstm_tile_floats(long long B) { return ((B + kRows - 1) / kRows) 
 int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
                            float* h_b, float* scratch_f, float* scratch_b, long long B, int T, cudaStream_t st) {
     MMLA_REQUIRE(B > 0 && B < (1LL << 22) && T >= 1, MMLA_EINVAL, "lstm_fused: bad batch/T");
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(LstmSmem) + 1024);
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     LstmArgs a;
     a.xp[0] = xp_f; a.xp[1] = xp_b; a.wr[0] = wr_f; a.wr[1] = wr_b;

@@ -767,11 +767,11 @@ extern "C" __attribute__((visibility("default"))) int mmla_psf_mfcc_rows(const i
 
     const int sms = mmla_num_sms();
     MMLA_REQUIRE(sms > 0, MMLA_ECUDA, "mfcc: no CUDA device");
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(Smem))));
-        attr_set = true;
     }
     long long grid = 2LL * sms;
     if (grid > kp.n_units) grid = kp.n_units;

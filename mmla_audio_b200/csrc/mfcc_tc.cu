@@ -911,11 +911,11 @@ int get_consts(int nfilt, const unsigned char** out) {
 
 template <int NF, bool DBG>
 int launch_tc(const TcParams& kp, long long grid, cudaStream_t st) {
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(TcSmem));
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(mfcc_tc_kernel<NF, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     mfcc_tc_kernel<NF, DBG><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(kp);
     mmla_count_launch("mfcc_tc_kernel", st);

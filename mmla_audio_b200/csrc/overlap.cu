@@ -471,11 +471,11 @@ extern "C" __attribute__((visibility("default"))) int mmla_overlap_features(
     }
     const int sms = mmla_num_sms();
     MMLA_REQUIRE(sms > 0, MMLA_ECUDA, "overlap: no CUDA device");
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(overlap_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(sizeof(Smem))));
-        attr_set = true;
     }
     long long grid = sms;
     if (grid > n_clips) grid = n_clips;

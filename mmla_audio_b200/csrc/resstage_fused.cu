@@ -840,13 +840,13 @@ __global__ void __launch_bounds__(kThreadsS, StageCfg<CIN, C, STEM>::kMinCtas) r
 
 template <int CIN, int C, bool STEM = false>
 int launch_stage(const StageArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(StageSmem<CIN, C, STEM>) + 128);
     static_assert(sizeof(StageSmem<CIN, C, STEM>) + 128 <= 227 * 1024, "stage kernel shared memory");
     static_assert(StageCfg<CIN, C, STEM>::kExtra >= 1, "the shortcut operand buffer becomes at least one ring stage");
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(resstage_fused_kernel<CIN, C, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     constexpr int kTilesCta = StageCfg<CIN, C, STEM>::kTiles;
     StageArgs b = a;

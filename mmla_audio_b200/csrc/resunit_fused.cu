@@ -366,11 +366,11 @@ __global__ void __launch_bounds__(kThreadsRU, (C == 32 ? 4 : (C == 64 ? 3 : 2)))
 
 template <int CIN, int C, bool POOL>
 int launch_ru(const ResUnitArgs& a, cudaStream_t st) {
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(RuSmem<CIN, C, POOL>) + 128);
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(resunit_fused_kernel<CIN, C, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     const unsigned grid = static_cast<unsigned>((a.B + a.G - 1) / a.G);
     resunit_fused_kernel<CIN, C, POOL><<<grid, kThreadsRU, smem, st>>>(a);

@@ -286,11 +286,11 @@ __global__ void __launch_bounds__(kThreadsStem, 4) stem_fused_kernel(const float
 // bias: [32], y: [B][256][32].
 int mmla_launch_stem_fused(const float* x, const float* wg, const float* bias, float* y, long long B, cudaStream_t st) {
     MMLA_REQUIRE(B > 0 && B < (1LL << 22), MMLA_EINVAL, "stem_fused: bad batch");
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(StemSmem) + 128);
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(stem_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     stem_fused_kernel<false><<<static_cast<unsigned>(2 * B), kThreadsStem, smem, st>>>(x, wg, bias, y, static_cast<int>(B), kT, 0);
     mmla_count_launch("stem_fused_kernel", st);
@@ -306,11 +306,11 @@ int mmla_launch_stem_from_cepstra(const float* cep, long long cep_clip_stride, i
     MMLA_REQUIRE(n_frames >= 1 && n_frames <= kT, MMLA_EINVAL, "stem_fused: n_frames=%d must be in [1,256]", n_frames);
     MMLA_REQUIRE((cep_clip_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(cep) & 15) == 0, MMLA_EINVAL,
                  "stem_fused: cepstra rows must be 16-byte aligned");
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(StemSmem) + 128);
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(stem_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     stem_fused_kernel<true><<<static_cast<unsigned>(2 * B), kThreadsStem, smem, st>>>(cep, wg, bias, y, static_cast<int>(B), n_frames,
                                                                                         cep_clip_stride);

@@ -266,11 +266,11 @@ long long mmla_xproj_tiled_floats(long long B, int T) { return ((B + 127) / 128)
 int mmla_launch_xproj_fused(const float* seq, const float* w_f, const float* w_b, const float* b_f, const float* b_b,
                             float* xp_f, float* xp_b, long long B, int T, cudaStream_t st) {
     MMLA_REQUIRE(B > 0 && T > 0 && B * T < (1LL << 30), MMLA_EINVAL, "xproj_fused: bad geometry");
-    static bool attr_set = false;
+    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
+    const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(XpSmem) + 1024);
     if (!attr_set) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(xproj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
     }
     XpArgs a;
     a.seq = seq;

@@ -204,5 +204,5 @@ def load_model(model_dir: str, kind: Optional[str] = None, n_classes: Optional[i
 def save_synthetic_model(model_dir: str, spec: NetSpec, seed: int = 1234) -> Dict[str, np.ndarray]:
     """Write seeded synthetic weights as a TF tensor bundle under ``model_dir/variables/``."""
     w = synthetic_weights(spec, seed)
-    tf_bundle.write_bundle(os.path.join(model_dir, "variables", "variables"), w, with_crc=False)
+    tf_bundle.write_bundle(os.path.join(model_dir, "variables", "variables"), w, with_crc=True)
     return w

@@ -33,15 +33,40 @@ def window_view(pcm_1d, win: int, step: int):
 
 
 class PendingResult:
-    """Handle of one in-flight :meth:`SpeakerPipeline.submit_host` batch."""
+    """Handle of one in-flight :meth:`SpeakerPipeline.submit_host` batch.
 
-    def __init__(self, slot, done):
+    The caller's ``pcm_host`` buffer is read by asynchronous copies: it must stay untouched until
+    :meth:`wait_uploaded` returns (or ``uploaded.query()`` is true).  A handle is valid until its
+    result slot is recycled, i.e. for ``depth`` further submissions; after that :meth:`result`
+    raises instead of returning another batch's labels."""
+
+    def __init__(self, slot, done, uploaded, generation):
         self._slot, self._done = slot, done
-        self.labels_dev = slot["labels"]       # int32 CUDA [B]; valid until `depth` more submissions
+        self.uploaded = uploaded                # CUDA event: the last host->device slice of this batch has landed
+        self._generation = generation
+
+    def _check(self):
+        if self._slot["generation"] != self._generation:
+            raise RuntimeError("this PendingResult's slot was recycled by a later submit_host(); "
+                               "fetch results within `depth` submissions or raise `depth`")
+
+    @property
+    def labels_dev(self):
+        """int32 CUDA [B]; valid until ``depth`` more submissions."""
+        self._check()
+        return self._slot["labels"]
+
+    def wait_uploaded(self):
+        """Block until every slice of the caller's ``pcm_host`` has been copied to the device; the
+        host buffer may then be refilled with the next batch."""
+        self.uploaded.synchronize()
 
     def result(self):
         """Block until this batch's labels and tallies are on the host; returns numpy copies."""
+        self._check()
         self._done.synchronize()
+        self._check()
+        self._slot["fetched"] = True
         return self._slot["labels_h"].numpy().copy(), self._slot["counts_h"].numpy().copy()
 
 
@@ -121,6 +146,7 @@ class SpeakerPipeline:
         the call returns a :class:`PendingResult`; up to ``depth`` submissions may be in flight, so
         the upload of batch k+1 overlaps the compute of batch k (the recording loop of the
         reference scripts, pipelined).  ``PendingResult.result()`` waits for that batch only.
+        ``pcm_host`` is read asynchronously: do not modify it before ``PendingResult.wait_uploaded()``.
 
         ``reduce(labels_dev, counts_dev) -> (labels_all, counts_all)``: optional device-side step run
         on the compute stream before the read-back — the multi-GPU label all_gather / tally
@@ -141,14 +167,17 @@ class SpeakerPipeline:
             self._slots = [dict(labels=torch.empty((B,), dtype=torch.int32, device="cuda"),
                                 labels_h=torch.empty((B,), dtype=torch.int32).pin_memory(),
                                 counts_h=torch.empty((n_classes + 1,), dtype=torch.int64).pin_memory(),
-                                done=None) for _ in range(depth)]
+                                done=None, generation=0, fetched=True) for _ in range(depth)]
             self._slot_next = 0
             self._stage_key = key
         slot = self._slots[self._slot_next]
         self._slot_next = (self._slot_next + 1) % len(self._slots)
         if slot["done"] is not None:
-            slot["done"].synchronize()                  # the slot's previous batch must be read out
+            slot["done"].synchronize()                  # the slot's previous batch must have finished
+        slot["generation"] += 1                         # handles of the slot's previous batch now raise
+        slot["fetched"] = False
         compute = torch.cuda.current_stream()
+        uploaded = None
         labels = slot["labels"]
         for i in range(n_chunks):
             lo, hi = bounds[i], bounds[i + 1]
@@ -161,6 +190,7 @@ class SpeakerPipeline:
                     self._copy_stream.wait_event(self._stage_free[k])
                 buf.copy_(pcm_host[lo:hi], non_blocking=True)
                 copied.record(self._copy_stream)
+            uploaded = copied
             compute.wait_event(copied)
             lab, _ = self.run_device(buf)
             labels[lo:hi] = lab
@@ -176,7 +206,7 @@ class SpeakerPipeline:
         done = torch.cuda.Event()
         done.record(compute)
         slot["done"] = done
-        return PendingResult(slot, done)
+        return PendingResult(slot, done, uploaded, slot["generation"])
 
     def run_host(self, pcm_host, n_classes: int, n_chunks: int = 2):
         """Synchronous form of :meth:`submit_host`: returns (labels int32 numpy [B], counts int64
@@ -189,6 +219,7 @@ class SpeakerPipeline:
         rows every 2.56 s (speaker_identification_post_processing.py:253-312).  With ``log_path`` the
         TSV log the reference appends row by row (:278-312) is written for ``visualization()``."""
         torch = _lib.require_cuda()
+        speaker_names = tally.normalize_names(speaker_names)     # make_feature_experiment's dict has str keys
         chunks = whole_file_chunks(pcm_long, self.cfg)
         prob, labels = self.model.predict_device(chunks)
         if len(silent_index):

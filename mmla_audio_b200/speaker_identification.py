@@ -61,10 +61,12 @@ def _to_device_pcm(torch, pcm):
 
 
 def mfcc_batch(pcm, cfg: MfccConfig = MfccConfig(), with_deltas: bool = False, pad_frames: int = 0,
-               out=None, row_stride: int = 0):
+               out=None, row_stride: int = 0, cmvn=False):
     """Batched device path.  ``pcm``: int16 [B, L] (numpy or torch; CUDA tensors are used in
     place).  Returns a float32 CUDA tensor [B, rows, dim] with rows = pad_frames or T(L).
-    ``row_stride`` > dim widens the rows (zero filled): [B, rows, row_stride]."""
+    ``row_stride`` > dim widens the rows (zero filled): [B, rows, row_stride].
+    ``cmvn``: False (the reference: none), ``"mean"`` or True (mean and variance) — per clip and column
+    over the clip's real frames (BASELINE north_star option; applied to all ``dim`` columns)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     x = _to_device_pcm(torch, pcm)
@@ -87,6 +89,11 @@ def mfcc_batch(pcm, cfg: MfccConfig = MfccConfig(), with_deltas: bool = False, p
     stride0 = x.stride(0) if B > 1 else L
     _lib.check(lib.mmla_psf_mfcc_rows(x.data_ptr(), (B - 1) * stride0 + L, None, None, B, L, stride0, C.byref(p),
                                       out.data_ptr(), rows * width, width, _lib.stream_ptr(torch)), "mmla_psf_mfcc_rows")
+    if cmvn:
+        if cmvn not in (True, "mean", "mvn"):
+            raise ValueError("cmvn must be False, True / 'mvn' or 'mean'")
+        _lib.check(lib.mmla_cmvn(out.data_ptr(), B, rows * width, width, dim, min(T, rows), None,
+                                 0 if cmvn == "mean" else 1, _lib.stream_ptr(torch)), "mmla_cmvn")
     return out
 
 

@@ -18,6 +18,11 @@ OVERLAP_DEGREE_DICT = {"0": "non-overlapped", "1": "overlapped"}   # record_on_p
 SILENT = -1                                                          # label id of the 'silent' sentinel
 
 
+def normalize_names(id_to_name) -> Dict[int, str]:
+    """{int id: name} from a dict keyed by ints or by the reference's ``str(idx)`` keys."""
+    return {int(k): v for k, v in (id_to_name or {}).items()}
+
+
 def device_counts(labels, n_classes: int):
     """int64 CUDA tensor [n_classes+1]; the last bin collects out-of-range ids (e.g. SILENT)."""
     torch = _lib.require_cuda()
@@ -68,10 +73,12 @@ def tally_session(labels, id_to_name: Dict[int, str], t0: datetime, dt_seconds: 
     total_seconds) with dict order as the reference builds it: ``initial_order`` first (overlap
     script) or order of first appearance (speaker script)."""
     torch = _lib.require_cuda()
-    n_classes = max(id_to_name) + 1 if id_to_name else 1
+    # the reference's own dicts are keyed by str(idx) (speaker_identification.py:360-369 `speaker_id`,
+    # record_on_pc.py:34 `overlap_degree_dict`): accept those as well as int keys
+    names = normalize_names(id_to_name)
+    n_classes = max(names) + 1 if names else 1
     counts = device_counts(labels, n_classes).cpu().tolist()
     host = labels.cpu().tolist()
-    names = dict(id_to_name)
     order: List[str] = list(initial_order) if initial_order else []
     seen = set(order)
     for l in host:                       # order of first appearance, as the speaker script does
@@ -82,7 +89,8 @@ def tally_session(labels, id_to_name: Dict[int, str], t0: datetime, dt_seconds: 
     by_name = {nm: 0 for nm in order}
     for cid, c in enumerate(counts[:-1]):
         if c:
-            by_name[names[cid]] = by_name.get(names[cid], 0) + c
+            nm = names.get(cid, "silent")          # an id nobody registered is logged like the sentinel
+            by_name[nm] = by_name.get(nm, 0) + c
     if counts[-1]:
         by_name["silent"] = by_name.get("silent", 0) + counts[-1]
     n = len(host)

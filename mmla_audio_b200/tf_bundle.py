@@ -221,11 +221,48 @@ def _make_crc_table() -> np.ndarray:
 _CRC_TABLE = _make_crc_table()
 
 
+def _make_slice8_tables():
+    t = [[int(v) for v in _CRC_TABLE]]
+    for k in range(1, 8):
+        prev = t[k - 1]
+        t.append([(prev[i] >> 8) ^ t[0][prev[i] & 0xFF] for i in range(256)])
+    return t
+
+
+_CRC_T8 = _make_slice8_tables()
+_crc_native = None
+
+
+def _native_crc():
+    """``mmla_crc32c_host`` from libmmla_b200.so (host code, no GPU needed) when the library is built."""
+    global _crc_native
+    if _crc_native is None:
+        try:
+            from . import _lib
+            _crc_native = _lib.load().mmla_crc32c_host
+        except Exception:
+            _crc_native = False
+    return _crc_native
+
+
 def crc32c(data: bytes) -> int:
-    tab = _CRC_TABLE
+    """CRC-32C (Castagnoli).  Weight shards are megabytes: the library's C routine is used when
+    libmmla_b200.so is present, otherwise a slice-by-8 loop (8 bytes per Python iteration)."""
+    fn = _native_crc()
+    if fn and len(data) >= 64:
+        buf = bytes(data)
+        return int(fn(buf, len(buf))) & 0xFFFFFFFF
+    t0, t1, t2, t3, t4, t5, t6, t7 = _CRC_T8
     c = 0xFFFFFFFF
-    for b in data:
-        c = int(tab[(c ^ b) & 0xFF]) ^ (c >> 8)
+    n8 = len(data) // 8
+    if n8:
+        words = struct.unpack_from("<%dQ" % n8, data)
+        for w in words:
+            w ^= c
+            c = (t7[w & 0xFF] ^ t6[(w >> 8) & 0xFF] ^ t5[(w >> 16) & 0xFF] ^ t4[(w >> 24) & 0xFF] ^
+                 t3[(w >> 32) & 0xFF] ^ t2[(w >> 40) & 0xFF] ^ t1[(w >> 48) & 0xFF] ^ t0[w >> 56])
+    for b in data[n8 * 8:]:
+        c = t0[(c ^ b) & 0xFF] ^ (c >> 8)
     return c ^ 0xFFFFFFFF
 
 

@@ -151,3 +151,65 @@ def test_seconds_from_counts_is_the_reference_expression():
     norm, secs = seconds_from_counts([1, 2, 4], 1000.0)
     assert norm == [round(1 / 7, 4), round(2 / 7, 4), round(4 / 7, 4)]
     assert secs == [int(n * 1000.0) for n in norm]
+
+
+def test_log_rows_literal_reference_strings():
+    """a16: the TSV rows, transcribed by hand from the reference's write statements —
+    overlap_detection_post_processing.py:213-224 (`'segment' + '\\t' + 'overlapped degree' + '\\t' +
+    'timestamp'`; row 0 carries `time` as is, every later row first does `time = time +
+    timedelta(seconds=1.5)`) and speaker_identification_post_processing.py:278-312 (`time = time +
+    timedelta(seconds=2.56)` BEFORE every row, the first included; header 'speaker').  `str(datetime)`
+    drops the fraction when microsecond == 0, which is what the `[:-7]` parsing trips over."""
+    from datetime import datetime
+    from mmla_audio_b200.tally import log_rows
+    t0 = datetime(2021, 6, 1, 12, 0, 0, 654321)
+    assert log_rows(["non-overlapped", "overlapped", "silent"], t0, 1.5, "overlapped degree", add_before_first=False) == [
+        "segment\toverlapped degree\ttimestamp",
+        "0\tnon-overlapped\t2021-06-01 12:00:00.654321",
+        "1\toverlapped\t2021-06-01 12:00:02.154321",
+        "2\tsilent\t2021-06-01 12:00:03.654321",
+    ]
+    assert log_rows(["alice", "silent", "bob"], t0, 2.56, "speaker", add_before_first=True) == [
+        "segment\tspeaker\ttimestamp",
+        "0\talice\t2021-06-01 12:00:03.214321",
+        "1\tsilent\t2021-06-01 12:00:05.774321",
+        "2\tbob\t2021-06-01 12:00:08.334321",
+    ]
+    whole = datetime(2021, 12, 31, 23, 59, 59)                   # microsecond == 0: no ".000000" in str()
+    assert log_rows(["overlapped", "overlapped"], whole, 1.5, "overlapped degree", add_before_first=False) == [
+        "segment\toverlapped degree\ttimestamp",
+        "0\toverlapped\t2021-12-31 23:59:59",
+        "1\toverlapped\t2022-01-01 00:00:00.500000",
+    ]
+
+
+def test_normalize_names_accepts_reference_str_keys():
+    """make_feature_experiment / speaker_id_dict are keyed by str(idx) (speaker_identification.py:360-369)."""
+    from mmla_audio_b200 import speaker_identification as si
+    from mmla_audio_b200.tally import normalize_names
+    yy = si.binarizer(["bob", "bob", "alice"], dim=2)
+    speaker_id = {str(int(np.argmax(yy[i]))): n for i, n in enumerate(["bob", "bob", "alice"])}
+    assert speaker_id == {"0": "bob", "1": "alice"}
+    assert normalize_names(speaker_id) == {0: "bob", 1: "alice"}
+    assert normalize_names({0: "x"}) == {0: "x"} and normalize_names(None) == {}
+
+
+def test_synthetic_bundle_carries_real_crcs(tmp_path):
+    """save_synthetic_model writes masked crc32c values TensorFlow's BundleReader would accept."""
+    w = {"a/.ATTRIBUTES/VARIABLE_VALUE": np.arange(70000, dtype=np.float32),
+         "b/.ATTRIBUTES/VARIABLE_VALUE": np.ones((3, 5), np.float32)}
+    prefix = str(tmp_path / "variables" / "variables")
+    tf_bundle.write_bundle(prefix, w)
+    _, entries = tf_bundle.read_index(prefix + ".index")
+    assert all(e.crc32c != 0 for e in entries)
+    back = tf_bundle.read_bundle(prefix, verify_crc=True)
+    for k in w:
+        np.testing.assert_array_equal(back[k], w[k])
+    # the slice-by-8 python loop and the library routine agree
+    blob = w["a/.ATTRIBUTES/VARIABLE_VALUE"].tobytes()
+    native = tf_bundle.crc32c(blob)
+    saved, tf_bundle._crc_native = tf_bundle._crc_native, False
+    try:
+        assert tf_bundle.crc32c(blob) == native
+    finally:
+        tf_bundle._crc_native = saved

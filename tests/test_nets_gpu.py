@@ -41,7 +41,7 @@ def test_speaker_base_630_softmax(cuda):
     from mmla_audio_b200 import models, weights as W
     spec = W.SPEAKER_BASE
     w = W.synthetic_weights(spec, 99)
-    model = models.Model(spec, w)
+    model = models.Model(spec, w, precision="fp32")
     pcm = synth.synth_clips(300, 8, 40960)
     x = np.concatenate([psf.input_feature_gen(pcm[i]) for i in range(8)]).astype(np.float32)
     got = model.predict(x)
@@ -72,7 +72,7 @@ def test_micro_batching_consistent(cuda):
     from mmla_audio_b200 import models, weights as W
     torch = cuda
     spec = W.OVERLAP
-    model = models.Model(spec, W.synthetic_weights(spec, 7))
+    model = models.Model(spec, W.synthetic_weights(spec, 7), precision="fp32")
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randint(0, 256, (40, 128, 151, 3), dtype=torch.uint8, device="cuda", generator=g)
     p_all, l_all = model.predict_device(x)
@@ -88,7 +88,7 @@ def test_bad_weight_blob_fails_loudly(cuda):
     w = W.synthetic_weights(spec, 1)
     w.pop(next(iter(w)))
     with pytest.raises(KeyError):
-        models.Model(spec, w)
+        models.Model(spec, w, precision="fp32")
 
 
 # ---------------------------------------------------------------------------------------------

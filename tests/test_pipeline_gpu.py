@@ -20,7 +20,7 @@ def test_config1_overlap_single_clip(cuda):
     from mmla_audio_b200 import models, weights as W
     from mmla_audio_b200.pipeline import OverlapPipeline
     w = W.synthetic_weights(W.OVERLAP, 1234)
-    pipe = OverlapPipeline(models.Model(W.OVERLAP, w))
+    pipe = OverlapPipeline(models.Model(W.OVERLAP, w, precision="fp32"))
     sig = synth.synth_clips(77, 1, 40000)
     labels, prob = pipe.run_device(cuda.from_numpy(sig).cuda())
     ref = onets.overlap_forward(lm.classifier_input(sig[0])[None], w, W.OVERLAP)
@@ -37,7 +37,7 @@ def test_config4_long_session_overlap(cuda, tmp_path):
     from mmla_audio_b200 import models, tally, weights as W
     from mmla_audio_b200.pipeline import OverlapPipeline, segmentation_windows
     w = W.synthetic_weights(W.OVERLAP, 1234)
-    pipe = OverlapPipeline(models.Model(W.OVERLAP, w))
+    pipe = OverlapPipeline(models.Model(W.OVERLAP, w, precision="fp32"))
     rec = synth.synth_clips(500, 40, 24000).reshape(-1)[: 40 * 24000 - 5000]   # ragged tail is dropped
     n = segmentation_windows(len(rec), 24000, 24000)
     assert n == otally.num_windows(len(rec), 24000, 24000) == 39
@@ -69,7 +69,7 @@ def test_config4_long_session_speaker(cuda, tmp_path):
     from mmla_audio_b200.pipeline import SpeakerPipeline
     spec = W.speaker_spec(10, "sigmoid")
     w = W.synthetic_weights(spec, 4321)
-    pipe = SpeakerPipeline(models.Model(spec, w))
+    pipe = SpeakerPipeline(models.Model(spec, w, precision="fp32"))
     rec = synth.synth_clips(700, 30, 40960).reshape(-1)           # 76.8 s -> 30 chunks
     names = {i: f"spk{i}" for i in range(10)}
     t0 = datetime(2022, 3, 3, 8, 30, 0, 111111)
