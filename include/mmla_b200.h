@@ -218,6 +218,32 @@ int mmla_net_forward_cepstra(MmlaNet* net, const float* cepstra, int64_t cep_cli
                              void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Silence removal: WebRTC VAD, aggressiveness 3, 16 kHz, 30 ms frames + vad_collector.
+ * Replaces  vad = webrtcvad.Vad(3); vad.is_speech(frame.bytes, sample_rate)
+ *           frame_generator(30, audio, sample_rate); vad_collector(sample_rate, 30, 300, vad, frames)
+ *           and the rewrite of the clip from the yielded segments in save_wave_file(..., silence_remove=True)
+ *   OverlapDetection/scripts/record_on_pc.py:33,214-226,229-295 (same code in SpeakerIdentification/scripts/
+ *   record_on_pc.py:207-273 and both *_post_processing.py files), whose consequence `len(sig) < 4000 => 'silent'`
+ *   (record_on_pc.py:142; speaker_identification.py:375) is applied per clip by the pipelines.
+ * pcm            int16 [n_clips][clip_stride] (DEVICE), clips starting on 8-byte boundaries.
+ * clip_len_dev   DEVICE int32 [n_clips] samples per clip, or NULL for the uniform clip_len.
+ * clips_per_stream  the detector adapts from frame to frame and, in the reference (one module-global Vad object), from
+ *                clip to clip: every run of this many consecutive clips is one sequential stream starting from a fresh
+ *                detector.  1 = independent clips (batch mode, one thread per clip); n_clips = one session in order.
+ * Outputs (DEVICE; each may be NULL, pcm_out needs keep):
+ *   speech       uint8 [n_clips][max_frames]  is_speech of frame f (0 past the clip's frame count)
+ *   keep         uint8 [n_clips][max_frames]  1 where vad_collector yields the frame
+ *   voiced_len   int32 [n_clips]              480 * kept frames = the rewritten clip's length in samples
+ *   pcm_out      int16 [n_clips][out_stride]  kept frames, concatenated in order (samples past voiced_len untouched)
+ * mmla_vad_num_frames: frames frame_generator yields for n samples (`while offset + n < len(audio)`, byte offsets).
+ * ---------------------------------------------------------------------------------------- */
+int32_t mmla_vad_num_frames(int32_t n_samples);
+int mmla_vad_trim(const int16_t* pcm, int64_t n_clips, int32_t clip_len, int64_t clip_stride,
+                  const int32_t* clip_len_dev, int64_t clips_per_stream,
+                  uint8_t* speech, uint8_t* keep, int32_t max_frames, int32_t* voiced_len,
+                  int16_t* pcm_out, int64_t out_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Label tallies.  Replaces the counting loops of
  *   OverlapDetection/scripts/overlap_degree_distribution.py:49-61
  *   SpeakerIdentification/scripts/speaker_time_distribution.py:52-80

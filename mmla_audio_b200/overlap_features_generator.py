@@ -32,10 +32,12 @@ class OverlapFeaturesGenerator:
         return self.window_length, self.hop_length, self.sr
 
     # ------------------------------------------------------------------ batched device path
-    def features_batch(self, pcm, n_mels=128, want=("image",)):
+    def features_batch(self, pcm, n_mels=128, want=("image",), lengths_host=None):
         """pcm: int16 [B, L] (numpy / torch).  Returns a dict of CUDA tensors for the names in
         ``want``: 's_db', 's_db_norm' float32 [B,n_mels,151]; 'zcr' float32 [B,151];
-        'image' uint8 [B,n_mels,151,3] (rows flipped, trunc(v*255) — what the classifier eats)."""
+        'image' uint8 [B,n_mels,151,3] (rows flipped, trunc(v*255) — what the classifier eats).
+        ``lengths_host``: optional per-clip sample counts (ragged clips, e.g. after silence removal): clip i is
+        ``pcm[i, :lengths_host[i]]``, zero-padded / truncated to 24000 like every clip (…generator.py:73-80)."""
         from .speaker_identification import _to_device_pcm
         torch = _lib.require_cuda()
         lib = _lib.load()
@@ -55,7 +57,14 @@ class OverlapFeaturesGenerator:
             out["image"] = torch.empty((B, n_mels, OVERLAP_FRAMES, 3), dtype=torch.uint8, device=dev)
         ptr = lambda k: out[k].data_ptr() if k in out else None
         stride0 = x.stride(0) if B > 1 else L
-        _lib.check(lib.mmla_overlap_features(x.data_ptr(), (B - 1) * stride0 + L, None, None, B, L, stride0,
+        off_p = len_p = None
+        if lengths_host is not None:
+            ln = np.ascontiguousarray(lengths_host, dtype=np.int32)
+            if ln.shape != (B,) or (ln > L).any() or (ln < 0).any():
+                raise ValueError("lengths_host must hold one length in [0, L] per clip")
+            off = np.arange(B, dtype=np.int64) * stride0
+            off_p, len_p = off.ctypes.data, ln.ctypes.data
+        _lib.check(lib.mmla_overlap_features(x.data_ptr(), (B - 1) * stride0 + L, off_p, len_p, B, L, stride0,
                                              n_mels, ptr("s_db"), ptr("s_db_norm"), ptr("zcr"), ptr("image"),
                                              _lib.stream_ptr(torch)), "mmla_overlap_features")
         return out
@@ -107,7 +116,7 @@ class OverlapFeaturesGenerator:
         Image.fromarray(rgba, "RGBA").save(out_dir + out_name, format="PNG")
         return None
 
-    def classifier_input_batch(self, pcm):
+    def classifier_input_batch(self, pcm, lengths_host=None):
         """uint8 CUDA ``[B,128,151,3]`` — the tensor ``decode_png(.,3)`` yields in the reference
         (record_on_pc.py:156-158), without the PNG round trip."""
-        return self.features_batch(pcm, want=("image",))["image"]
+        return self.features_batch(pcm, want=("image",), lengths_host=lengths_host)["image"]

@@ -18,7 +18,8 @@ from . import _lib, tally
 from .models import Model
 from .overlap_features_generator import OverlapFeaturesGenerator
 from .params import (MfccConfig, OVERLAP_CLIP_SAMPLES, SILENT_MIN_SAMPLES, SPEAKER_FRAMES)
-from .speaker_identification import mfcc_batch, speaker_features_batch, whole_file_chunks, _to_device_pcm
+from .speaker_identification import (mfcc_batch, mfcc_ragged, speaker_features_batch, whole_file_chunks,
+                                     _to_device_pcm)
 
 
 def segmentation_windows(n_samples: int, win: int, step: int) -> int:
@@ -107,10 +108,23 @@ class SpeakerPipeline:
         prob, labels = self.model.predict_device(feat)
         return labels, prob
 
-    def run_device(self, pcm_dev):
-        """pcm_dev: int16 CUDA [B, L] (L >= 4000).  → (labels int32 [B], prob [B,n])."""
+    def run_device(self, pcm_dev, lengths=None, silence_removed: bool = False, vad_clips_per_stream: int = 1):
+        """pcm_dev: int16 CUDA [B, L].  → (labels int32 [B], prob [B,n]).
+
+        ``lengths`` (int32 [B], host or device): ragged clips, clip i = ``pcm_dev[i, :lengths[i]]``.
+        ``silence_removed=True``: every clip first goes through the WebRTC VAD + ``vad_collector``
+        (``save_wave_file(.., silence_remove=True)``, SI record_on_pc.py:117 → :185-204) and the features are
+        taken from the rewritten (voiced-only) clip.  Either way the reference's rule ``len(sig) < 4000 =>
+        'silent'`` (speaker_identification.py:375) is applied PER CLIP: such clips get label -1 and skip the
+        classifier; their ``prob`` rows are zero."""
         torch = _lib.require_cuda()
         B = pcm_dev.shape[0]
+        if silence_removed:
+            from .vad import vad_trim
+            res = vad_trim(pcm_dev, lengths, clips_per_stream=vad_clips_per_stream)
+            pcm_dev, lengths = res.pcm, res.voiced_len
+        if lengths is not None:
+            return self._run_ragged(torch, pcm_dev, lengths)
         if pcm_dev.shape[1] < SILENT_MIN_SAMPLES:          # every clip is 'silent'
             return (torch.full((B,), tally.SILENT, dtype=torch.int32, device=pcm_dev.device), None)
         n = self.n_streams if B >= self.split_min_clips else 1
@@ -136,6 +150,29 @@ class SpeakerPipeline:
         for o in outs[1:]:                                    # tensors allocated on side streams, consumed on `main`
             o[0].record_stream(main)
             o[1].record_stream(main)
+        return labels, prob
+
+    def _run_ragged(self, torch, pcm_dev, lengths):
+        """Per-clip lengths: clips shorter than 4000 samples are 'silent' (-1); the others go through the ragged
+        feature entry (``mmla_psf_mfcc`` with per-clip offsets / lengths → [n,256,39]) and the classifier."""
+        B, L = pcm_dev.shape
+        ln = torch.as_tensor(lengths).to(torch.int32).cpu().numpy()          # one small read-back: the rule is a host decision
+        if ln.shape != (B,):
+            raise ValueError("lengths must have one entry per clip")
+        ln = np.minimum(ln, L)
+        live = np.nonzero(ln >= SILENT_MIN_SAMPLES)[0]
+        labels = torch.full((B,), tally.SILENT, dtype=torch.int32, device=pcm_dev.device)
+        prob = torch.zeros((B, self.model.spec.n_classes), dtype=torch.float32, device=pcm_dev.device)
+        if len(live) == 0:
+            return labels, prob
+        stride0 = pcm_dev.stride(0) if B > 1 else L
+        flat = pcm_dev.as_strided(((B - 1) * stride0 + L,), (1,))
+        feat, _rows = mfcc_ragged(flat, live.astype(np.int64) * stride0, ln[live], self.cfg, with_deltas=True,
+                                  pad_frames=SPEAKER_FRAMES)
+        p_live, l_live = self.model.predict_device(feat)
+        idx = torch.from_numpy(live).to(pcm_dev.device)
+        labels[idx] = l_live
+        prob[idx] = p_live
         return labels, prob
 
     def submit_host(self, pcm_host, n_classes: int, n_chunks: int = 2, depth: int = 3, reduce=None):
@@ -240,12 +277,39 @@ class OverlapPipeline:
         self.model = model
         self.ofg = OverlapFeaturesGenerator(wl=25, hl=10)
 
-    def run_device(self, pcm_dev):
-        """pcm_dev: int16 CUDA [B, L].  → (labels int32 [B], prob [B,2]); label -1 = 'silent'
-        when L < 4000 (record_on_pc.py:141-154)."""
+    def run_device(self, pcm_dev, lengths=None, silence_removed: bool = False, vad_clips_per_stream: int = 1):
+        """pcm_dev: int16 CUDA [B, L].  → (labels int32 [B], prob [B,2]); label -1 = 'silent' for every clip
+        with fewer than 4000 samples (record_on_pc.py:141-154), decided PER CLIP when ``lengths`` are given or
+        ``silence_removed=True`` runs the WebRTC VAD + ``vad_collector`` first (``save_wave_file(..,
+        silence_remove=True)``, record_on_pc.py:133 → :214-226).  The features of a trimmed clip are taken from
+        its first 24000 voiced samples, zero-padded (overlap_features_generator.py:73-80)."""
         torch = _lib.require_cuda()
-        B = pcm_dev.shape[0]
-        if pcm_dev.shape[1] < SILENT_MIN_SAMPLES:
+        B, L = pcm_dev.shape
+        if silence_removed:
+            from .vad import vad_trim
+            res = vad_trim(pcm_dev, lengths, clips_per_stream=vad_clips_per_stream)
+            pcm_dev, lengths = res.pcm, res.voiced_len
+            L = pcm_dev.shape[1]
+        if lengths is not None:
+            ln = np.minimum(torch.as_tensor(lengths).to(torch.int32).cpu().numpy(), L)
+            if ln.shape != (B,):
+                raise ValueError("lengths must have one entry per clip")
+            live = np.nonzero(ln >= SILENT_MIN_SAMPLES)[0]
+            labels = torch.full((B,), tally.SILENT, dtype=torch.int32, device=pcm_dev.device)
+            prob = torch.zeros((B, 2), dtype=torch.float32, device=pcm_dev.device)
+            if len(live):
+                if len(live) == B:
+                    img = self.ofg.classifier_input_batch(pcm_dev, lengths_host=ln)
+                else:
+                    idx = torch.from_numpy(live).to(pcm_dev.device)
+                    img = self.ofg.classifier_input_batch(pcm_dev.index_select(0, idx), lengths_host=ln[live])
+                p_live, l_live = self.model.predict_device(img)
+                if len(live) == B:
+                    return l_live, p_live
+                labels[idx] = l_live
+                prob[idx] = p_live
+            return labels, prob
+        if L < SILENT_MIN_SAMPLES:
             return (torch.full((B,), tally.SILENT, dtype=torch.int32, device=pcm_dev.device), None)
         img = self.ofg.classifier_input_batch(pcm_dev)
         prob, labels = self.model.predict_device(img)
