@@ -218,6 +218,21 @@ int mmla_net_forward_cepstra(MmlaNet* net, const float* cepstra, int64_t cep_cli
                              void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Stationary spectral-gating noise reduction.
+ * Replaces  nr.reduce_noise(y_noise=noise, y=y, sr=sr, stationary=True) + sf.write(filepath, ., 16000)
+ *   OverlapDetection/scripts/record_on_pc.py:208-212; overlap_detection_post_processing.py:128-133 (and the
+ *   SpeakerIdentification copies) with noisereduce's defaults: n_fft 1024, hop 256, n_std_thresh_stationary 1.5,
+ *   prop_decrease 1, 500 Hz / 50 ms mask smoothing, 30000-sample chunk padding; output = PCM_16 as libsndfile writes it.
+ * mmla_noise_profile: noise int16 [n_samples] (the ambient-noise recording, first 600000 samples used) ->
+ *   thresh_out float32 [513] (DEVICE) = per-bin mean + n_std_thresh * std of the noise spectrogram in dB.
+ * mmla_noise_gate: pcm int16 [n_clips][clip_stride], clip_len_dev DEVICE int32 [n_clips] or NULL (uniform clip_len,
+ *   <= 600000) -> out int16 [n_clips][out_stride], samples [0, len) of every clip (the rest untouched).
+ * ---------------------------------------------------------------------------------------- */
+int mmla_noise_profile(const int16_t* noise, int64_t n_samples, float n_std_thresh, float* thresh_out, void* stream);
+int mmla_noise_gate(const int16_t* pcm, int64_t n_clips, int32_t clip_len, int64_t clip_stride,
+                    const int32_t* clip_len_dev, const float* thresh, int16_t* out, int64_t out_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Silence removal: WebRTC VAD, aggressiveness 3, 16 kHz, 30 ms frames + vad_collector.
  * Replaces  vad = webrtcvad.Vad(3); vad.is_speech(frame.bytes, sample_rate)
  *           frame_generator(30, audio, sample_rate); vad_collector(sample_rate, 30, 300, vad, frames)

@@ -54,7 +54,10 @@ def _to_device_pcm(torch, pcm):
         a = np.asarray(pcm)
         if a.dtype != np.int16:
             raise TypeError(f"PCM must be int16 (as scipy.io.wavfile.read returns it), got {a.dtype}")
-        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        a = np.ascontiguousarray(a)
+        if not a.flags.writeable:                      # e.g. np.frombuffer views: torch wants a writable source
+            a = a.copy()
+        t = torch.from_numpy(a).cuda()
     if t.dim() == 0 or t.stride(-1) != 1 or t.data_ptr() % 16:
         t = t.contiguous().clone()
     return t
