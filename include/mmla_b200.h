@@ -218,6 +218,26 @@ int mmla_net_forward_cepstra(MmlaNet* net, const float* cepstra, int64_t cep_cli
                              void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Enrollment: the frozen trunk's 512-d output and the fit of the transfer head.
+ * Replaces the first phase of transfer_learning, SpeakerIdentification/scripts/speaker_identification.py:401-432:
+ *   sliced_base_model = Model(base_model.input, base_model.layers[-2].output)          -> mmla_net_embed
+ *   Dense(dim, activation='sigmoid', name='customized_dense'); compile(loss="categorical_crossentropy",
+ *   optimizer=RMSprop(lr=0.0001)); fit(batch_size=16, epochs=500)                        -> mmla_head_fit
+ * mmla_net_embed: like mmla_net_forward (same x / x_is_u8 / workspace), writes embed float32 [batch][512] =
+ *   [forward h | backward h] of the Bidirectional LSTM (the input of the Dense head).
+ * mmla_head_fit: embed [n_samples][512], y_onehot float32 [n_samples][n_classes] (n_classes <= 64), order int32
+ *   [epochs][n_samples] = the sample visiting order of every epoch (Keras reshuffles per epoch; supplied by the caller so
+ *   a fit is reproducible), batch_size <= 32; kernel [512][n_classes] and bias [n_classes] (DEVICE) hold the initial
+ *   weights on entry and the fitted ones on return; loss_out [epochs] (DEVICE, may be NULL) the mean training loss per
+ *   epoch.  Loss and optimiser as Keras defines them (see csrc/head_fit.cu).  All pointers DEVICE.
+ * ---------------------------------------------------------------------------------------- */
+int mmla_net_embed(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch, void* workspace, int64_t workspace_bytes,
+                   float* embed, void* stream);
+int mmla_head_fit(const float* embed, const float* y_onehot, int64_t n_samples, int32_t n_classes, const int32_t* order,
+                  int32_t epochs, int32_t batch_size, float lr, float rho, float eps, float* kernel, float* bias,
+                  float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stationary spectral-gating noise reduction.
  * Replaces  nr.reduce_noise(y_noise=noise, y=y, sr=sr, stationary=True) + sf.write(filepath, ., 16000)
  *   OverlapDetection/scripts/record_on_pc.py:208-212; overlap_detection_post_processing.py:128-133 (and the

@@ -16,7 +16,7 @@ SYMBOLS = (
     "mmla_last_error", "mmla_abi_version", "mmla_launch_count", "mmla_crc32c_host",
     "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_psf_mfcc_rows", "mmla_delta", "mmla_cmvn", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
-    "mmla_net_forward", "mmla_net_forward_cepstra",
+    "mmla_net_forward", "mmla_net_forward_cepstra", "mmla_net_embed", "mmla_head_fit",
     "mmla_tally", "mmla_synth_pcm", "mmla_vad_num_frames", "mmla_vad_trim", "mmla_noise_profile", "mmla_noise_gate", "mmla_debug_mfcc_tc_dump", "mmla_debug_resstage_stamps", "mmla_debug_lstm_stamps", "mmla_debug_conv2d", "mmla_debug_conv_slab_stamps", "mmla_trace_begin", "mmla_trace_end",
 )
 
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
         "mmla_net_workspace_bytes": (i64, [vp, i64]),
         "mmla_net_forward": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, vp, vp]),
         "mmla_net_forward_cepstra": (C.c_int, [vp, vp, i64, i32, i64, vp, i64, vp, vp, vp]),
+        "mmla_net_embed": (C.c_int, [vp, vp, i32, i64, vp, i64, vp, vp]),
+        "mmla_head_fit": (C.c_int, [vp, vp, i64, i32, vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]),
         "mmla_tally": (C.c_int, [vp, i64, i32, vp, vp]),
         "mmla_noise_profile": (C.c_int, [vp, i64, C.c_float, vp, vp]),
         "mmla_noise_gate": (C.c_int, [vp, i64, i32, i64, vp, vp, vp, i64, vp]),

@@ -366,6 +366,18 @@ __global__ void __launch_bounds__(256) lstm_gates_kernel(const float* __restrict
     }
 }
 
+// [B,256] forward h | [B,256] backward h -> [B,512], the Bidirectional layer's concatenated output
+__global__ void __launch_bounds__(256) embed_concat_kernel(const float* __restrict__ hf, const float* __restrict__ hb, long long B,
+                                                           float* __restrict__ out) {
+    const long long total = B * 512;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = e >> 9;
+        const int i = static_cast<int>(e & 511);
+        out[e] = i < 256 ? hf[b * 256 + i] : hb[b * 256 + i - 256];
+    }
+}
+
 // head: z [B,512] (fwd|bwd) -> optional LeakyReLU -> Dense -> softmax|sigmoid -> prob, argmax
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ hf, const float* __restrict__ hb,
                                                    const float* __restrict__ wk, const float* __restrict__ wb,
@@ -745,7 +757,8 @@ EXPORT int64_t mmla_net_workspace_bytes(const MmlaNet* net, int64_t batch) {
 }
 
 static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t cep_frames, int64_t cep_clip_stride, int64_t batch,
-                        void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream);
+                        void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream,
+                        float* embed = nullptr);
 
 EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch, void* workspace,
                             int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
@@ -762,9 +775,15 @@ EXPORT int mmla_net_forward_cepstra(MmlaNet* net, const float* cepstra, int64_t 
     return forward_impl(net, cepstra, 3, n_frames, cep_clip_stride, batch, workspace, workspace_bytes, prob, labels, stream);
 }
 
+EXPORT int mmla_net_embed(MmlaNet* net, const void* x, int32_t x_is_u8, int64_t batch, void* workspace, int64_t workspace_bytes,
+                          float* embed, void* stream) {
+    MMLA_REQUIRE(embed != nullptr, MMLA_EINVAL, "net_embed: null output");
+    return forward_impl(net, x, x_is_u8, 0, 0, batch, workspace, workspace_bytes, nullptr, nullptr, stream, embed);
+}
+
 static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t cep_frames, int64_t cep_clip_stride, int64_t batch,
-                        void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
-    MMLA_REQUIRE(net && x && prob && workspace, MMLA_EINVAL, "net_forward: null argument");
+                        void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream, float* embed) {
+    MMLA_REQUIRE(net && x && (prob || embed) && workspace, MMLA_EINVAL, "net_forward: null argument");
     MMLA_REQUIRE(batch >= 0, MMLA_EINVAL, "net_forward: negative batch");
     const bool from_cep = x_is_u8 == 3;       // MFCC-13 rows; delta / delta-delta / padding happen inside the stem kernel
     if (from_cep) x_is_u8 = 0;
@@ -974,6 +993,13 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 }
                 MMLA_CUDA_CHECK(cudaGetLastError());
             }
+        }
+        if (embed) {
+            // the trunk's output = layers[-2] of the Keras model: [fwd h | bwd h] (speaker_identification.py:403)
+            embed_concat_kernel<<<ew_grid(B * 512), 256, 0, st>>>(hdir[0], hdir[1], B, embed + b0 * 512);
+            mmla_count_launch("embed_concat_kernel", st);
+            MMLA_CUDA_CHECK(cudaGetLastError());
+            if (!prob) continue;
         }
         const int warps = 8;
         long long hgrid = (B + warps - 1) / warps;

@@ -133,6 +133,30 @@ class Model:
                                         labels.data_ptr(), _lib.stream_ptr(torch)), "mmla_net_forward")
         return prob, labels
 
+    def embed_device(self, x):
+        """The frozen trunk's output — ``Model(base.input, base.layers[-2].output)`` of ``transfer_learning``
+        (speaker_identification.py:402-406): float32 CUDA [B, 512] = [forward h | backward h] of the BiLSTM, the
+        tensor the Dense head reads.  ``x`` as for :meth:`predict_device`."""
+        torch, lib = self._torch, self._lib
+        if tuple(x.shape[1:]) != self.input_shape:
+            raise ValueError(f"expected input [B, {self.input_shape}], got {tuple(x.shape)}")
+        is_u8 = x.dtype == torch.uint8 and self.spec.ndim == 2
+        if not is_u8 and x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        B = x.shape[0]
+        need = lib.mmla_net_workspace_bytes(self._handle, B)
+        key = int(torch.cuda.current_stream().cuda_stream)
+        if self._ws is None:
+            self._ws = {}
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need or ws.device != x.device:
+            ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=x.device)
+        out = torch.empty((B, 512), dtype=torch.float32, device=x.device)
+        _lib.check(lib.mmla_net_embed(self._handle, x.data_ptr(), 1 if is_u8 else 0, B, ws.data_ptr(), ws.numel(),
+                                      out.data_ptr(), _lib.stream_ptr(torch)), "mmla_net_embed")
+        return out
+
     def predict_device_cepstra(self, cep):
         """Speaker net, TF32 mode: ``cep`` float32 CUDA [B, T, 16] — the MFCC-13 rows of
         ``mfcc_batch(pcm, row_stride=16)`` (T = psf frame count <= 256).  Delta, delta-delta and the

@@ -135,8 +135,9 @@ def overlap_forward(x_nhwc: np.ndarray, w: Dict[str, np.ndarray], spec: NetSpec,
 
 @torch.no_grad()
 def speaker_forward(x_btf: np.ndarray, w: Dict[str, np.ndarray], spec: NetSpec,
-                    return_logits: bool = False) -> np.ndarray:
-    """x float [B,256,39] → prob float32 [B,n_classes] (softmax base / sigmoid transfer head)."""
+                    return_logits: bool = False, return_embedding: bool = False) -> np.ndarray:
+    """x float [B,256,39] → prob float32 [B,n_classes] (softmax base / sigmoid transfer head).
+    ``return_embedding``: the 512-d output of ``layers[-2]`` instead (speaker_identification.py:403)."""
     x = torch.from_numpy(np.ascontiguousarray(x_btf, dtype=np.float32)).permute(0, 2, 1)
     net = _conv(x, w, spec, spec.stem)
     for b in spec.blocks:
@@ -154,6 +155,8 @@ def speaker_forward(x_btf: np.ndarray, w: Dict[str, np.ndarray], spec: NetSpec,
     net = F.avg_pool1d(net, 4)
     seq = net.permute(0, 2, 1).contiguous()                  # [B, 8, 128]
     z = _bilstm(seq, w, spec)
+    if return_embedding:
+        return z.numpy()
     if return_logits:
         kk, bk = dense_keys(spec)
         return (z @ _t(w, kk) + _t(w, bk)).numpy()
