@@ -270,6 +270,53 @@ class SpeakerPipeline:
         return labels, tally.tally_session(labels, speaker_names, t0, 2.56, add_before_first=True)
 
 
+    def session_chunks_sharded(self, pcm_long, rank: int, world: int):
+        """This rank's share of ``whole_file_chunks(pcm_long)``: float32 CUDA [chunk_hi - chunk_lo, 256, 39], identical
+        to rows [chunk_lo, chunk_hi) of the single-GPU result.  The rank reads its chunk range plus a halo (5 frames
+        before, 4 frames + one window after — ``sharding.session_slice``) from the shared recording; nothing is exchanged."""
+        from .sharding import session_slice
+        torch = _lib.require_cuda()
+        x = _to_device_pcm(torch, pcm_long).reshape(-1)
+        sl = session_slice(x.numel(), rank, world, self.cfg.frame_len, self.cfg.frame_step, SPEAKER_FRAMES)
+        n_own = sl["chunk_hi"] - sl["chunk_lo"]
+        width = 3 * self.cfg.numcep
+        if n_own <= 0:
+            return torch.empty((0, SPEAKER_FRAMES, width), dtype=torch.float32, device=x.device), sl
+        piece = x[sl["sample_lo"]:sl["sample_hi"]]
+        feat = mfcc_batch(piece.reshape(1, -1), self.cfg, with_deltas=True)[0]          # [frames of the slice, 39]
+        rows = feat[sl["skip_rows"]:sl["skip_rows"] + n_own * SPEAKER_FRAMES]
+        if sl["chunk_hi"] < sl["n_chunks_total"]:
+            rows = rows[: n_own * SPEAKER_FRAMES]                                        # the tail rows are halo
+        else:                                                                            # last chunk of the file: zero rows
+            real = sl["n_frames_total"] - sl["chunk_lo"] * SPEAKER_FRAMES
+            rows = rows[:real]
+        out = torch.zeros((n_own * SPEAKER_FRAMES, width), dtype=torch.float32, device=x.device)
+        out[: rows.shape[0]] = rows
+        return out.view(n_own, SPEAKER_FRAMES, width), sl
+
+    def run_session_sharded(self, pcm_long, speaker_names: Dict[int, str], rank: int, world: int,
+                            t0: Optional[datetime] = None, silent_index=()):
+        """:meth:`run_session` with the recording's chunks split across ``world`` ranks (one process per GPU): every
+        rank labels its chunk range, one all_gather (``sharding.exchange_labels_and_counts``) gives every rank all
+        labels, and the tallies are computed from the gathered labels — identical on every rank and to the
+        single-GPU session."""
+        from .sharding import exchange_labels_and_counts
+        torch = _lib.require_cuda()
+        speaker_names = tally.normalize_names(speaker_names)
+        chunks, sl = self.session_chunks_sharded(pcm_long, rank, world)
+        n_classes = self.model.spec.n_classes
+        if chunks.shape[0]:
+            _prob, labels = self.model.predict_device(chunks)
+        else:
+            labels = torch.empty((0,), dtype=torch.int32, device="cuda")
+        counts = tally.device_counts(labels, n_classes)
+        labels, _counts = exchange_labels_and_counts(labels, counts, sl["n_chunks_total"], rank, world)
+        labels = labels.clone()
+        if len(silent_index):
+            labels[torch.as_tensor(list(silent_index), dtype=torch.long, device=labels.device)] = tally.SILENT
+        return labels, tally.tally_session(labels, speaker_names, t0 or datetime.today(), 2.56, add_before_first=True)
+
+
 class OverlapPipeline:
     def __init__(self, model: Model):
         if model.spec.ndim != 2:

@@ -17,6 +17,35 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return (n_items * rank) // world, (n_items * (rank + 1)) // world
 
 
+# Whole-file speaker features (speaker_identification_post_processing.py:255-269) are NOT independent per chunk: the
+# frame grid, the pre-emphasis sample and the delta / delta-delta context (+-4 frames, edge-replicated only at the FILE's
+# ends) run across the 256-frame chunk borders.  A rank therefore reads its chunk range plus a read-only halo from the
+# shared recording and throws the halo rows away — no exchange is needed.
+HALO_FRAMES_BEFORE = 5      # frame 0 of a slice has no predecessor sample for its pre-emphasis (1) + delta-delta context (4)
+HALO_FRAMES_AFTER = 4       # delta-delta context
+
+
+def session_slice(n_samples: int, rank: int, world: int, frame_len: int = 400, frame_step: int = 160,
+                  chunk_frames: int = 256):
+    """Split of one long recording's 256-frame chunks across ranks.  Returns a dict:
+    ``chunk_lo, chunk_hi``  this rank's chunks [lo, hi) of the ceil(T/256) chunks of the file,
+    ``sample_lo, sample_hi``  the samples it must read (its frames plus the halo),
+    ``skip_rows``  feature rows of the slice to drop before the first owned chunk,
+    ``n_chunks_total, n_frames_total``.
+    The halo is 5 frames before (= 800 samples) and 4 frames + one window after (= 4*160 + 240 = 880 samples)."""
+    T = 1 if n_samples <= frame_len else 1 + -(-(n_samples - frame_len) // frame_step)
+    n_chunks = max(1, -(-T // chunk_frames))
+    c_lo, c_hi = shard_range(n_chunks, rank, world)
+    f_lo = max(0, c_lo * chunk_frames - HALO_FRAMES_BEFORE)
+    f_hi = min(T, c_hi * chunk_frames + HALO_FRAMES_AFTER)          # exclusive
+    s_lo = f_lo * frame_step
+    s_hi = n_samples if f_hi >= T else (f_hi - 1) * frame_step + frame_len
+    if c_hi <= c_lo:
+        s_lo = s_hi = 0
+    return {"chunk_lo": c_lo, "chunk_hi": c_hi, "sample_lo": s_lo, "sample_hi": s_hi,
+            "skip_rows": c_lo * chunk_frames - f_lo, "n_chunks_total": n_chunks, "n_frames_total": T}
+
+
 def gather_labels(labels_local, n_total: int, rank: int, world: int):
     """all_gather of int32 labels sharded with shard_range → full [n_total] tensor on every rank."""
     import torch

@@ -180,3 +180,24 @@ def test_config4_full_size_8h_overlap_session_properties(cuda):
     assert torch.equal(labels, torch.cat([la, lb]))
     small, _ = pipe.run_session(rec[: 40 * win], t0=t0)
     assert torch.equal(labels[:40], small)
+
+
+def test_long_session_halo_sharding_equals_single_gpu(cuda):
+    """SURVEY §8e, long single recording: the chunks each of R ranks computes from its sample range + halo are
+    bit-identical to the same chunks of the single-GPU whole-file pass (emulated ranks on one device: the sharding is
+    pure index math, nothing is exchanged on the data path)."""
+    from mmla_audio_b200 import models, weights as W
+    from mmla_audio_b200 import speaker_identification as si
+    from mmla_audio_b200.pipeline import SpeakerPipeline
+    torch = cuda
+    spec = W.speaker_spec(10, "sigmoid")
+    pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321), precision="tf32"))
+    for n_samples in (40960 * 9 + 777, 40960 * 4, 46000):
+        rec = synth.synth_clips(1200, -(-n_samples // 40960), 40960).reshape(-1)[:n_samples]
+        rec_dev = torch.from_numpy(rec).cuda()
+        whole = si.whole_file_chunks(rec_dev)
+        for world in (2, 3, 8):
+            parts = [pipe.session_chunks_sharded(rec_dev, r, world)[0] for r in range(world)]
+            got = torch.cat(parts)
+            assert got.shape == whole.shape
+            assert torch.equal(got, whole), (n_samples, world, (got - whole).abs().max().item())
