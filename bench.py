@@ -680,6 +680,33 @@ def main():
         summary["bulk_1M_hbm_frac_per_gpu"] = round(nb / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)
         del pb, ob
         torch.cuda.empty_cache()
+
+        # (3) BASELINE configs[3], speaker half: ONE 8 h recording (460.8 M samples -> 2 879 999 frames -> 11 250 chunks of
+        #     256 frames), whole-file MFCC + delta + delta-delta, chunks split across the ranks with a read-only halo
+        #     (sharding.session_slice: no exchange on the data path), classifier, label all_gather, tallies
+        from datetime import datetime as _dt
+        n8h = 11250 * 40960
+        rec = synth.synth_clips(30_000_000, 11250, 40960).reshape(-1)          # every rank holds the shared recording
+        spk_names = {i: "spk%d" % i for i in range(10)}
+        spipe = SpeakerPipeline(models.Model(W.speaker_spec(10, "sigmoid"), W.synthetic_weights(W.speaker_spec(10, "sigmoid"), 4321),
+                                             precision="tf32"))
+        t_fix = _dt(2021, 6, 1, 9, 0, 0, 123456)
+
+        def session():
+            return spipe.run_session_sharded(rec, spk_names, rank, world, t0=t_fix)
+
+        for _ in range(2):
+            session()
+        ms_s = timed(session, 5)
+        lab_s, (cnt_s, sec_s, tot_s) = session()
+        extra["speaker_8h_session"] = {"audio_hours": 8.0, "chunks": int(lab_s.numel()), "ms_per_session": ms_s,
+                                       "audio_s_per_s": n8h / SR / (ms_s * 1e-3), "total_seconds": tot_s,
+                                       "sharding": "256-frame chunk ranges + 800 / 880-sample halo per rank, labels all_gather",
+                                       "scaling": "strong (one recording)"}
+        summary["speaker_8h_session_ms"] = round(ms_s, 3)
+        summary["speaker_8h_session_audio_s_per_s"] = round(n8h / SR / (ms_s * 1e-3), 1)
+        del rec, spipe
+        torch.cuda.empty_cache()
     sampler.stop()
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) and label agreement against the oracle -------

@@ -190,3 +190,88 @@ def test_tally_oracle_matches_reference_expressions():
     assert counts == {"non-overlapped": 1, "overlapped": 3, "silent": 1}
     assert total == 6.0 and secs == {"non-overlapped": int(0.2 * 6), "overlapped": int(0.6 * 6), "silent": int(0.2 * 6)}
     assert otally.num_windows(460800000, 24000, 24000) == 19200 and otally.num_windows(40000, 24000, 24000) == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# END-TO-END cross-checks of the two feature chains against independent implementations.
+# They cannot turn "parity unpinned" into pinned — the independent code is not the reference's own library either —
+# but they catch a wrong window, pad mode, mel scale, normalisation or log convention in the restatement as a whole.
+# ---------------------------------------------------------------------------------------------
+def test_librosa_chain_vs_torchaudio_end_to_end():
+    """oracle: librosa.load -> melspectrogram(n_fft=400, hop=160, 128 mel) -> power_to_db(ref=max)  versus
+    torchaudio MelSpectrogram(norm='slaney', mel_scale='slaney', pad_mode='reflect', power=2) + 10 log10, top_db 80.
+    Residuals (recorded): mel power <= 2e-5 relative to the clip maximum (float32 STFT in torchaudio vs float64 FFT
+    stored as complex64 in the oracle); dB map <= 2e-3 dB wherever the value is above the -80 dB floor."""
+    import torchaudio.transforms as T
+    mel = T.MelSpectrogram(sample_rate=16000, n_fft=400, win_length=400, hop_length=160, n_mels=128, f_min=0.0, f_max=8000.0,
+                           window_fn=torch.hann_window, power=2.0, center=True, pad_mode="reflect", norm="slaney",
+                           mel_scale="slaney")
+    worst_p, worst_db = 0.0, 0.0
+    for clip in (3, 4, 5):
+        sig = synth.synth_clips(clip, 1, 24000)[0]
+        y = lm.pad_or_truncate(lm.load_pcm(sig))
+        ref = mel(torch.from_numpy(y)[None]).numpy()[0]                      # [128, 151]
+        got = lm.melspectrogram(y)
+        assert got.shape == ref.shape == (128, 151)
+        worst_p = max(worst_p, float(np.abs(got - ref).max() / ref.max()))
+        db_ref = 10.0 * np.log10(np.maximum(ref, 1e-10)) - 10.0 * np.log10(max(ref.max(), 1e-10))
+        db_ref = np.maximum(db_ref, db_ref.max() - 80.0)
+        db_got = lm.power_to_db_refmax(got)
+        live = db_ref > -79.0
+        worst_db = max(worst_db, float(np.abs(db_got - db_ref)[live].max()))
+        assert db_got.min() >= -80.0 - 1e-4 and abs(float(db_got.max())) <= 1e-5
+    print("librosa chain vs torchaudio: mel power rel", worst_p, "dB", worst_db)
+    assert worst_p <= 2e-5 and worst_db <= 2e-3
+
+
+def test_psf_chain_vs_independent_scipy_pipeline_end_to_end():
+    """oracle psf.mfcc versus a pipeline written a different way with scipy primitives only: scipy.signal.lfilter
+    pre-emphasis, stride-trick framing, scipy.fft.rfft, a filterbank built from the closed-form triangle expression
+    (not the per-bin loops), scipy.fftpack.dct(type=2, norm='ortho'), sinusoidal lifter, log-energy in c0.
+    Residual (recorded): <= 1e-9 absolute on cepstra of magnitude up to ~40 (float64 on both sides)."""
+    import scipy.signal
+    worst = 0.0
+    for clip, n, nfilt in ((6, 24000, 26), (7, 40960, 26), (8, 40000, 40), (9, 4321, 26)):
+        sig = synth.synth_clips(clip, 1, n)[0].astype(np.float64)
+        emph = scipy.signal.lfilter([1.0, -0.97], [1.0], sig)
+        emph[0] = sig[0]
+        T_ = 1 if n <= 400 else 1 + int(math.ceil((n - 400) / 160.0))
+        padded = np.concatenate([emph, np.zeros((T_ - 1) * 160 + 400 - n)])
+        frames = np.lib.stride_tricks.sliding_window_view(padded, 400)[::160][:T_]
+        pspec = np.abs(scipy.fft.rfft(frames, 512, axis=1)) ** 2 / 512.0
+        energy = pspec.sum(1)
+        energy[energy == 0] = np.finfo(float).eps
+        mel_pts = np.linspace(0.0, 2595 * np.log10(1 + 8000 / 700.0), nfilt + 2)
+        bins = np.floor(513 * (700 * (10 ** (mel_pts / 2595.0) - 1)) / 16000.0)
+        k = np.arange(257)[None, :]
+        lo, ce, hi = bins[:-2, None], bins[1:-1, None], bins[2:, None]
+        fb = np.where((k >= lo) & (k < ce), (k - lo) / (ce - lo), 0.0) + np.where((k >= ce) & (k < hi), (hi - k) / (hi - ce), 0.0)
+        fe = pspec @ fb.T
+        fe[fe == 0] = np.finfo(float).eps
+        cep = scipy.fftpack.dct(np.log(fe), type=2, axis=1, norm="ortho")[:, :13]
+        cep *= 1 + 11.0 * np.sin(np.pi * np.arange(13) / 22.0)
+        cep[:, 0] = np.log(energy)
+        got = psf.mfcc(synth.synth_clips(clip, 1, n)[0], 16000, winlen=0.025, winstep=0.01, nfft=512, nfilt=nfilt)
+        assert got.shape == cep.shape == (T_, 13)
+        worst = max(worst, float(np.abs(got - cep).max()))
+    print("psf chain vs independent scipy pipeline: max |d|", worst)
+    assert worst <= 1e-9
+
+
+def test_noisereduce_oracle_against_hand_rolled_stft():
+    """The spectral-gate oracle leans on scipy.signal.stft / istft; check the conventions it assumes about them (periodic
+    Hann, boundary zeros, 1/sum(w) scaling, perfect reconstruction with an all-ones mask)."""
+    from oracle import noisereduce_stationary as onr
+    from scipy.signal import stft, istft
+    x = synth.synth_clips(2, 1, 8192)[0].astype(np.float64) / 32768
+    _, _, Z = stft(x, nfft=1024, noverlap=768, nperseg=1024, padded=False)
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(1024) / 1024)
+    xp = np.concatenate([np.zeros(512), x, np.zeros(512)])
+    m = 7
+    mine = np.fft.rfft(w * xp[256 * m: 256 * m + 1024]) / w.sum()
+    np.testing.assert_allclose(Z[:, m], mine, atol=1e-12)
+    assert Z.shape == (513, (len(x) + 256) // 256)
+    _, back = istft(Z, nfft=1024, noverlap=768, nperseg=1024)
+    np.testing.assert_allclose(back[: len(x)], x, atol=1e-12)
+    f = onr._smoothing_filter(16, 3)
+    assert f.shape == (33, 7) and abs(f.sum() - 1) < 1e-12 and np.isclose(f[16, 3] * 68, 1.0)
