@@ -16,7 +16,9 @@
 // n_fft = 400 = 2^4*5^2 is not a power of two; the folded dense DFT costs 24 MFLOP/clip, ~1 %
 // of the overlap classifier's 1.84 GFLOP/clip, so a mixed-radix FFT is not worth its
 // complexity here.
+#include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -73,6 +75,7 @@ struct Params {
     const long long* clip_off;
     const int* clip_len_arr;
     const OverlapTables* tab;
+    const unsigned char* dft_b;      // tensor-core path: [13 K steps][cos hi | cos lo | sin hi | sin lo][6656 B], UMMA K-major
     long long n_clips, clip_stride;
     int clip_len, n_mels;
     float* s_db;
@@ -88,7 +91,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ float block_reduce(Smem& s, float v, bool is_max) {
+template <int NT, class SmemT>
+__device__ __forceinline__ float block_reduce(SmemT& s, float v, bool is_max) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -100,8 +104,72 @@ __device__ __forceinline__ float block_reduce(Smem& s, float v, bool is_max) {
     __syncthreads();
     float r = s.red[0];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w) r = is_max ? fmaxf(r, s.red[w]) : fminf(r, s.red[w]);
+    for (int w = 1; w < NT / 32; ++w) r = is_max ? fmaxf(r, s.red[w]) : fminf(r, s.red[w]);
     return r;
+}
+
+// power_to_db(ref=max, amin=1e-10, top_db=80) + normalize_matrix + the three outputs, from the clip's mel tile s.M
+// (overlap_features_generator.py:82-83,103-117,142-151); every thread of the CTA takes part.
+template <int NT, class SmemT>
+__device__ __forceinline__ void finish_clip(SmemT& s, const Params& p, long long clip, int n_mels, int tid) {
+    const int total = n_mels * kFrames;
+    float vmax = 0.f;
+    for (int e = tid; e < total; e += NT) vmax = fmaxf(vmax, s.M[e / kFrames][e % kFrames]);
+    vmax = block_reduce<NT>(s, vmax, true);
+    // numpy-1.21 semantics: the reference term is evaluated in float64, then applied in float32
+    const float ref_db = static_cast<float>(10.0 * log10(fmax(1e-10, static_cast<double>(vmax))));
+    const float max_db = 10.0f * log10f(fmaxf(1e-10f, vmax)) - ref_db;
+    const float floor_db = max_db - 80.0f;
+    float vmin = max_db;
+    for (int e = tid; e < total; e += NT) {
+        float* q = &s.M[e / kFrames][e % kFrames];
+        float db = 10.0f * log10f(fmaxf(1e-10f, *q)) - ref_db;
+        db = fmaxf(db, floor_db);
+        *q = db;
+        vmin = fminf(vmin, db);
+    }
+    vmin = block_reduce<NT>(s, vmin, false);
+    const float diff = max_db - vmin;
+    __syncthreads();
+    if (p.s_db) {
+        float* dst = p.s_db + clip * static_cast<long long>(total);
+        for (int e = tid; e < total; e += NT) dst[e] = s.M[e / kFrames][e % kFrames];
+    }
+    if (p.s_db_norm) {
+        float* dst = p.s_db_norm + clip * static_cast<long long>(total);
+        for (int e = tid; e < total; e += NT) dst[e] = (s.M[e / kFrames][e % kFrames] - vmin) / diff;
+    }
+    if (p.image) {
+        // uint8 [n_mels][151][3], row r = mel (n_mels-1-r); value trunc(float64(v) * 255)
+        uint32_t* dst = reinterpret_cast<uint32_t*>(p.image + clip * static_cast<long long>(total) * 3);
+        const int words = total * 3 / 4;
+        for (int wd = tid; wd < words; wd += NT) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int byte = 4 * wd + b;
+                const int pix = byte / 3, c = byte - 3 * pix;
+                const int r = pix / kFrames, t = pix - r * kFrames;
+                uint32_t q = 0u;                                      // (x*255).astype(uint8): truncation
+                if (c == 0) {
+                    const double v255 = s.zcr255[t];
+                    q = (v255 >= 0.0) ? static_cast<uint32_t>(static_cast<int>(v255)) & 0xFFu : 0u;
+                } else {
+                    // trunc(float64(v) * 255) for the float32 v = 1 - nrm in [0, 1] in integer arithmetic: the 24-bit
+                    // significand times 255 fits 32 bits, so the result is exact (FP64 multiplies are slow on this part).
+                    // NaN (constant clip), negatives and values below 2^-8 map to 0 exactly as the float64 path did.
+                    const float nrm = (s.M[n_mels - 1 - r][t] - vmin) / diff;
+                    const uint32_t bits = __float_as_uint(1.0f - nrm);
+                    const int ex = static_cast<int>((bits >> 23) & 0xFFu);
+                    if (!(bits >> 31) && ex != 0xFF && ex >= 119)
+                        q = ex >= 127 ? 255u : ((((bits & 0x7FFFFFu) | 0x800000u) * 255u) >> (150 - ex));
+                }
+                packed |= (q & 0xFFu) << (8 * b);
+            }
+            dst[wd] = packed;
+        }
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kThreads, 1) overlap_features_kernel(const __grid_constant__ Params p) {
@@ -268,61 +336,360 @@ __global__ void __launch_bounds__(kThreads, 1) overlap_features_kernel(const __g
         }
         __syncthreads();
 
-        // ---- power_to_db(ref=max, amin=1e-10, top_db=80) + normalize_matrix ---------------------
-        const int total = n_mels * kFrames;
-        float vmax = 0.f;
-        for (int e = tid; e < total; e += kThreads) vmax = fmaxf(vmax, s.M[e / kFrames][e % kFrames]);
-        vmax = block_reduce(s, vmax, true);
-        // numpy-1.21 semantics: the reference term is evaluated in float64, then applied in float32
-        const float ref_db = static_cast<float>(10.0 * log10(fmax(1e-10, static_cast<double>(vmax))));
-        const float max_db = 10.0f * log10f(fmaxf(1e-10f, vmax)) - ref_db;
-        const float floor_db = max_db - 80.0f;
-        float vmin = max_db;
-        for (int e = tid; e < total; e += kThreads) {
-            float* q = &s.M[e / kFrames][e % kFrames];
-            float db = 10.0f * log10f(fmaxf(1e-10f, *q)) - ref_db;
-            db = fmaxf(db, floor_db);
-            *q = db;
-            vmin = fminf(vmin, db);
-        }
-        vmin = block_reduce(s, vmin, false);
-        const float diff = max_db - vmin;
-        __syncthreads();
-        if (p.s_db) {
-            float* dst = p.s_db + clip * static_cast<long long>(total);
-            for (int e = tid; e < total; e += kThreads) dst[e] = s.M[e / kFrames][e % kFrames];
-        }
-        if (p.s_db_norm) {
-            float* dst = p.s_db_norm + clip * static_cast<long long>(total);
-            for (int e = tid; e < total; e += kThreads) dst[e] = (s.M[e / kFrames][e % kFrames] - vmin) / diff;
-        }
-        if (p.image) {
-            // uint8 [n_mels][151][3], row r = mel (n_mels-1-r); value trunc(float64(v) * 255)
-            uint32_t* dst = reinterpret_cast<uint32_t*>(p.image + clip * static_cast<long long>(total) * 3);
-            const int words = total * 3 / 4;
-            for (int wd = tid; wd < words; wd += kThreads) {
-                uint32_t packed = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int byte = 4 * wd + b;
-                    const int pix = byte / 3, c = byte - 3 * pix;
-                    const int r = pix / kFrames, t = pix - r * kFrames;
-                    double v255;
-                    if (c == 0) {
-                        v255 = s.zcr255[t];
-                    } else {
-                        const float nrm = (s.M[n_mels - 1 - r][t] - vmin) / diff;
-                        v255 = static_cast<double>(1.0f - nrm) * 255.0;
-                    }
-                    // (x*255).astype(uint8): truncation; NaN (constant clip) maps to 0 here
-                    const uint32_t q = (v255 >= 0.0) ? static_cast<uint32_t>(static_cast<int>(v255)) & 0xFFu : 0u;
-                    packed |= q << (8 * b);
-                }
-                dst[wd] = packed;
-            }
-        }
-        __syncthreads();
+        finish_clip<kThreads>(s, p, clip, n_mels, tid);
     }
+}
+
+// =================================================================================================
+// Tensor-core variant: the folded 400-point DFT as a [frames x 208] x [208 x 208] product pair on tcgen05
+// =================================================================================================
+// X[k] = sum_{n<=200} e[n] cos(2 pi k n / 400) - i sum_{n<200} o[n] sin(2 pi k n / 400), e / o the even / odd folds of the
+// Hann-windowed, reflect-padded frame.  Rows of the A operands are FRAMES (M = 128: frames 0..127 of the clip, then
+// 128..150), K is the folded sample index in 13 steps of 16, N = 208 bins (201 used).  fp32-grade accuracy comes from the
+// same fp16 hi + lo split as csrc/mfcc_tc.cu: D += A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation in TMEM (D_cos in
+// columns [0, 208), D_sin in [208, 416)).  Samples enter at int16 scale x 0.5, so e <= 32768 and the lo halves stay in the
+// fp16 normal range; the power is scaled back by 2^-28.
+//   warps 0-3   epilogue: zero-crossing counts while the first product runs, then tcgen05.ld of their 32 frames' spectrum
+//               (thread = frame), |X|^2 into a per-thread scratch (local memory: lane-interleaved, so a warp's access is
+//               one line), sparse slaney mel rows -> the clip's mel tile in shared memory
+//   warps 4-11  A producers: per K step 128 frames x 16 folded samples; a lane owns one pair of samples of one frame
+//               (eight lanes per frame read 32 contiguous bytes), window, fold, hi / lo split, 4-byte stores into the
+//               UMMA K-major no-swizzle layout (K-group stride 2112 B: conflict-free)
+//   warp 12     TMA: the step's four B tiles (cos hi | cos lo | sin hi | sin lo, host-arranged, 26 KB) by one bulk copy
+//   warp 13     MMA issue: six N = 208 products per step (104 cycles each by the N/2 law: the tensor pipe is busy)
+// after which all 448 threads run the clip-level dB / min-max / image pass (finish_clip).
+constexpr int kTcThreads = 448;
+constexpr int kKSteps = 13;                            // 208 folded samples / 16
+constexpr int kALbo = 2112;                            // K-group stride of an A tile (2048 + 64: shifts banks by 16)
+constexpr int kATile = 2 * kALbo;                      // one operand (e|o, hi|lo) of one K step: 128 rows x 16 halves
+constexpr int kBLbo = 26 * 128;                        // K-group stride of a B tile: 26 row groups of 8 bins
+constexpr int kBTile = 2 * kBLbo;                      // 6656 B: 208 bins x 16 halves
+constexpr int kStageA = 4 * kATile;                    // e_hi, e_lo, o_hi, o_lo
+constexpr int kStageB = 4 * kBTile;                    // cos_hi, cos_lo, sin_hi, sin_lo
+constexpr int kStages = 2;
+constexpr float kAScale = 0.5f;                        // int16 scale x 0.5 = librosa's float x 2^14
+constexpr float kPowScale = 1.0f / (16384.0f * 16384.0f);
+
+struct SmemTc {
+    alignas(128) unsigned char a[kStages][kStageA];
+    alignas(128) unsigned char b[kStages][kStageB];
+    alignas(16) int16_t pcm[kClip + 16];
+    float M[kMaxMels][kMStride];
+    float zcr[kFrames + 1];
+    double zcr255[kFrames + 1];
+    float red[kTcThreads / 32];
+    int mel_start[kMaxMels], mel_len[kMaxMels], mel_off[kMaxMels];
+    float mel_w[kMaxMelNnz];
+    float window[kNfft];
+    alignas(8) uint64_t bar_pcm, full[kStages], empty[kStages], d_full;
+    uint32_t tmem_base;
+};
+static_assert(sizeof(SmemTc) <= 227 * 1024, "SmemTc exceeds the 227 KB a CTA can own");
+
+__device__ __forceinline__ bool elect_one_tc() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc_k_major(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16_tc(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+                 "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_tc(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tc(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: traps instead of hanging the GPU on a protocol error
+__device__ __noinline__ void wait_tc(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << 26); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void tmem_ld16_tc(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_tc() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void split2_tc(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) overlap_features_tc_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    SmemTc& s = *reinterpret_cast<SmemTc*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const OverlapTables& T = *p.tab;
+    for (int i = tid; i < kMaxMels; i += kTcThreads) {
+        s.mel_start[i] = T.mel_start[i];
+        s.mel_len[i] = T.mel_len[i];
+        s.mel_off[i] = T.mel_off[i];
+    }
+    for (int i = tid; i < kMaxMelNnz; i += kTcThreads) s.mel_w[i] = T.mel_w[i];
+    for (int i = tid; i < kNfft; i += kTcThreads) s.window[i] = T.window[i];
+    {   // A tiles: finite everywhere
+        uint4* z = reinterpret_cast<uint4*>(&s.a[0][0]);
+        for (int i = tid; i < kStages * kStageA / 16; i += kTcThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        mbar_init(&s.bar_pcm, 1);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&s.full[i], 9);                   // 8 producer warps + the TMA warp's expect_tx arrive
+            mbar_init(&s.empty[i], 1);
+        }
+        mbar_init(&s.d_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s.tmem_base;
+    const int n_mels = p.n_mels;
+    uint32_t pcm_phase = 0;
+    uint32_t step = 0;                                  // K steps so far (ring position); the same count in every role
+    uint32_t tiles_done = 0;                            // M tiles so far (d_full phase)
+    float* S = reinterpret_cast<float*>(&s.b[0][0]);    // [208 bins][64 frames] power tile, overlaid on the idle B ring
+    static_assert(kStages * kStageB >= kBinsPad * 64 * 4, "power tile does not fit the B ring");
+
+    for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+        const long long off = p.clip_off ? p.clip_off[clip] : clip * p.clip_stride;
+        const int len = p.clip_len_arr ? p.clip_len_arr[clip] : p.clip_len;
+        const int nvalid = min(len, kClip);
+        const long long a0 = off & ~7LL;
+        const int shift = static_cast<int>(off - a0);
+        if (tid == 0) {
+            uint32_t bytes = static_cast<uint32_t>(((off + nvalid + 7) & ~7LL) - a0) * 2u;
+            if (bytes == 0) bytes = 16;
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(&s.bar_pcm, bytes);
+            tma_bulk_g2s(&s.pcm[0], p.pcm + a0, bytes, &s.bar_pcm);
+        }
+        mbar_wait(&s.bar_pcm, pcm_phase);
+        pcm_phase ^= 1u;
+        unsigned short* px = reinterpret_cast<unsigned short*>(&s.pcm[0]) + shift;
+        for (int i = nvalid + tid; i < kClip; i += kTcThreads) px[i] = 0;       // zero padding to 24000: no bounds tests later
+        __syncthreads();
+
+        // ---- zero-crossing rate: edge padding adds no crossings, so a frame's count is a difference of the running
+        //      count C(i) = #{1 <= j <= i : sign(y[j]) != sign(y[j-1])} at its clamped ends (block scan over 54-sample runs)
+        {
+            constexpr int kSeg = 54;                                            // 448 x 54 >= 24000
+            int* zc = reinterpret_cast<int*>(&s.a[0][0]);                       // scratch: [448] run totals, [302] end counts
+            const int i0 = tid * kSeg, i1 = min(i0 + kSeg, kClip);
+            int cnt = 0;
+            if (i0 < kClip) {
+                int prev = i0 > 0 ? px[i0 - 1] >> 15 : px[0] >> 15;
+                for (int i = i0; i < i1; ++i) {
+                    const int cur = px[i] >> 15;
+                    cnt += cur != prev;
+                    prev = cur;
+                }
+            }
+            int incl = cnt;                                                     // inclusive scan: warp, then across warps
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int* wsum = zc + 800;
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            int base_w = 0;
+            for (int w = 0; w < warp; ++w) base_w += wsum[w];
+            zc[tid] = base_w + incl - cnt;                                      // exclusive prefix: crossings before run `tid`
+            __syncthreads();
+            if (tid < 2 * kFrames) {
+                const int t = tid >> 1;
+                const int b = t * kHop - kNfft / 2;
+                const int i = (tid & 1) ? min(b + kNfft - 1, kClip - 1) : max(b, 0);
+                const int r = i / kSeg;
+                int c = zc[r];
+                int prev = r * kSeg > 0 ? px[r * kSeg - 1] >> 15 : px[0] >> 15;
+                for (int j = r * kSeg; j <= i; ++j) {
+                    const int cur = px[j] >> 15;
+                    c += cur != prev;
+                    prev = cur;
+                }
+                zc[448 + tid] = c;                                              // C(i)
+            }
+            __syncthreads();
+            if (tid < kFrames) {
+                const double z = static_cast<double>(zc[448 + 2 * tid + 1] - zc[448 + 2 * tid]) / 400.0;
+                s.zcr[tid] = static_cast<float>(z);
+                s.zcr255[tid] = z * 255.0;
+                if (p.zcr) p.zcr[clip * kFrames + tid] = static_cast<float>(z);
+            }
+            __syncthreads();
+            for (int i = tid; i < 1024; i += kTcThreads) zc[i] = 0;             // the A tile's rows must stay finite
+            __syncthreads();
+        }
+
+        for (int mt = 0; mt < 2; ++mt) {
+            if (warp == 12) {
+                // ================= TMA: the four B tiles of every K step =================
+                if (lane == 0) {
+                    fence_proxy_async_smem();                                   // the ring held the power tile
+                    for (int ks = 0; ks < kKSteps; ++ks) {
+                        const uint32_t st = (step + ks) % kStages, use = (step + ks) / kStages;
+                        if (use >= 1) wait_tc(&s.empty[st], (use - 1) & 1);
+                        mbar_arrive_expect_tx(&s.full[st], kStageB);
+                        tma_bulk_g2s(&s.b[st][0], p.dft_b + static_cast<size_t>(ks) * kStageB, kStageB, &s.full[st]);
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 13) {
+                // ================= MMA issue =================
+                constexpr uint32_t kIdesc = (1u << 4) | (static_cast<uint32_t>(kBinsPad >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+                const uint64_t dA = desc_k_major(smem_u32(&s.a[0][0]), kALbo, 128);
+                const uint64_t dB = desc_k_major(smem_u32(&s.b[0][0]), kBLbo, 128);
+                for (int ks = 0; ks < kKSteps; ++ks) {
+                    const uint32_t st = (step + ks) % kStages, use = (step + ks) / kStages;
+                    wait_tc(&s.full[st], use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one_tc()) {
+                        const uint64_t a = dA + static_cast<uint64_t>((st * kStageA) >> 4);
+                        const uint64_t b = dB + static_cast<uint64_t>((st * kStageB) >> 4);
+                        const uint32_t acc = ks != 0 ? 1u : 0u;
+                        // cos part: e_hi Bc_hi + e_lo Bc_hi + e_hi Bc_lo ; sin part: o_hi Bs_hi + o_lo Bs_hi + o_hi Bs_lo
+                        umma_f16_tc(tmem, a, b, kIdesc, acc);
+                        umma_f16_tc(tmem, a + (kATile >> 4), b, kIdesc, 1u);
+                        umma_f16_tc(tmem, a, b + (kBTile >> 4), kIdesc, 1u);
+                        umma_f16_tc(tmem + kBinsPad, a + ((2 * kATile) >> 4), b + ((2 * kBTile) >> 4), kIdesc, acc);
+                        umma_f16_tc(tmem + kBinsPad, a + ((3 * kATile) >> 4), b + ((2 * kBTile) >> 4), kIdesc, 1u);
+                        umma_f16_tc(tmem + kBinsPad, a + ((2 * kATile) >> 4), b + ((3 * kBTile) >> 4), kIdesc, 1u);
+                        umma_commit_tc(&s.empty[st]);
+                        if (ks == kKSteps - 1) umma_commit_tc(&s.d_full);
+                    }
+                    __syncwarp();
+                }
+            } else if (warp >= 4) {
+                // ================= A producers =================
+                const int pt = tid - 128;                                    // 0..255
+                const int fs = pt >> 3, ps = pt & 7;                         // frame slot 0..31, sample pair 0..7
+                const int rows = mt == 0 ? 128 : kFrames - 128;              // frames of this tile
+                for (int ks = 0; ks < kKSteps; ++ks) {
+                    const uint32_t st = (step + ks) % kStages, use = (step + ks) / kStages;
+                    if (use >= 1) wait_tc(&s.empty[st], (use - 1) & 1);
+                    unsigned char* at = &s.a[st][0];
+                    const int n = 16 * ks + 2 * ps;                      // folded sample indices n, n + 1
+                    const float w0 = n <= 200 ? s.window[n] * kAScale : 0.f;
+                    const float w1 = n + 1 <= 200 ? s.window[n + 1] * kAScale : 0.f;
+                    const bool m0 = n >= 1 && n <= 199, m1 = n + 1 <= 199;   // samples with a mirror partner
+                    const uint32_t koff = (ps >> 2) * kALbo + (ps & 3) * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int f = fs + 32 * q;                       // row of the tile
+                        if (mt == 1 && f >= 32 && f >= rows) break;      // tile 1 has 23 frames: rows 32.. keep tile 0's (finite,
+                                                                         // unused) values, rows are independent in the product
+                        const int t = 128 * mt + f;                      // frame of the clip
+                        float e0 = 0.f, e1 = 0.f, o0 = 0.f, o1 = 0.f;
+                        if (t < kFrames) {
+                            const int base = t * kHop - kNfft / 2;
+                            float a_0, a_1, b_0, b_1;
+                            if (t >= 2 && t <= 148) {                    // interior frame: no reflection
+                                a_0 = s16_bits_to_float(px[base + n]);
+                                a_1 = s16_bits_to_float(px[base + n + 1]);
+                                b_0 = s16_bits_to_float(px[base + kNfft - n]);
+                                b_1 = s16_bits_to_float(px[base + kNfft - n - 1]);
+                            } else {
+                                auto smp = [&](int i) -> float {         // librosa centre padding: reflect
+                                    i = i < 0 ? -i : (i >= kClip ? 2 * (kClip - 1) - i : i);
+                                    return s16_bits_to_float(px[i]);
+                                };
+                                a_0 = smp(base + n);
+                                a_1 = smp(base + n + 1);
+                                b_0 = smp(base + kNfft - n);
+                                b_1 = smp(base + kNfft - n - 1);
+                            }
+                            if (!m0) b_0 = 0.f;
+                            if (!m1) b_1 = 0.f;
+                            e0 = w0 * (a_0 + b_0);
+                            e1 = w1 * (a_1 + b_1);
+                            o0 = m0 ? w0 * (a_0 - b_0) : 0.f;
+                            o1 = m1 ? w1 * (a_1 - b_1) : 0.f;
+                        }
+                        uint32_t ehi, elo, ohi, olo;
+                        split2_tc(e0, e1, ehi, elo);
+                        split2_tc(o0, o1, ohi, olo);
+                        const uint32_t roff = koff + (f >> 3) * 128 + (f & 7) * 16;
+                        *reinterpret_cast<uint32_t*>(at + roff) = ehi;
+                        *reinterpret_cast<uint32_t*>(at + kATile + roff) = elo;
+                        *reinterpret_cast<uint32_t*>(at + 2 * kATile + roff) = ohi;
+                        *reinterpret_cast<uint32_t*>(at + 3 * kATile + roff) = olo;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_tc(&s.full[st]);
+                }
+            }
+            step += kKSteps;
+            // ---- spectrum -> power -> mel, 64 frames at a time; the power tile S[bin][frame] overlays the B ring, which
+            //      is idle once the tile's last product has completed (d_full) ----
+            const int n_halves = mt == 0 ? 2 : 1;
+            for (int h = 0; h < n_halves; ++h) {
+                if (h == 0) {                                                   // every product of the tile has completed:
+                    wait_tc(&s.d_full, tiles_done & 1);                         // accumulators readable, B ring idle
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                if (warp < 4 && (warp >> 1) == h) {
+                    const uint32_t trow = tmem + (static_cast<uint32_t>(32 * warp) << 16);
+                    const int fh = 32 * (warp & 1) + lane;
+#pragma unroll 1
+                    for (int c = 0; c < kBinsPad / 16; ++c) {
+                        uint32_t re[16], im[16];
+                        tmem_ld16_tc(trow + 16 * c, re);
+                        tmem_ld16_tc(trow + kBinsPad + 16 * c, im);
+                        tmem_wait_tc();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
+                            S[(16 * c + j) * 64 + fh] = fmaf(a, a, b * b) * kPowScale;
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                }
+                __syncthreads();
+                const int t0 = 128 * mt + 64 * h;
+                for (int e = tid; e < n_mels * 64; e += kTcThreads) {
+                    const int m = e >> 6, fh = e & 63;
+                    const int t = t0 + fh;
+                    if (t < kFrames) {
+                        const float* w = &s.mel_w[s.mel_off[m]];
+                        const float* x = &S[s.mel_start[m] * 64 + fh];
+                        const int ln = s.mel_len[m];
+                        float acc = 0.f;
+                        for (int i = 0; i < ln; ++i) acc = fmaf(w[i], x[i * 64], acc);
+                        s.M[m][t] = acc;
+                    }
+                }
+                __syncthreads();
+            }
+            ++tiles_done;
+        }
+        finish_clip<kTcThreads>(s, p, clip, n_mels, tid);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -392,6 +759,51 @@ int build_tables(int n_mels, OverlapTables& t) {
 
 std::mutex g_mu;
 std::map<std::pair<int, int>, OverlapTables*> g_cache;   // (device, n_mels)
+std::map<int, unsigned char*> g_dft_b;                   // device -> tensor-core DFT operand table
+
+// B operands of the tensor-core DFT: per K step the tiles cos hi | cos lo | sin hi | sin lo, each [208 bins x 16 folded
+// samples] fp16 in the UMMA K-major no-swizzle layout (core matrix = 8 bins x 16 B; K-group stride 26 x 128 B).
+int get_dft_b(const unsigned char** out) {
+    int dev = 0;
+    MMLA_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_dft_b.find(dev);
+    if (it != g_dft_b.end()) {
+        *out = it->second;
+        return MMLA_OK;
+    }
+    std::vector<unsigned char> host(static_cast<size_t>(kKSteps) * kStageB, 0);
+    const double PI = 3.14159265358979323846;
+    auto put = [&](unsigned char* hi, unsigned char* lo, int col, int kk, double v) {
+        const size_t off = static_cast<size_t>(kk / 8) * kBLbo + static_cast<size_t>(col / 8) * 128 + (col % 8) * 16 + (kk % 8) * 2;
+        const __half h = __float2half_rn(static_cast<float>(v));
+        const __half l = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
+        memcpy(hi + off, &h, 2);
+        memcpy(lo + off, &l, 2);
+    };
+    for (int ks = 0; ks < kKSteps; ++ks) {
+        unsigned char* base = host.data() + static_cast<size_t>(ks) * kStageB;
+        for (int kk = 0; kk < 16; ++kk) {
+            const int n = 16 * ks + kk;
+            for (int k = 0; k < kBins; ++k) {
+                if (n > 200) continue;
+                const int r = (n * k) % kNfft;                               // exact argument reduction
+                put(base, base + kBTile, k, kk, cos(2.0 * PI * r / kNfft));
+                if (n >= 1 && n <= 199) put(base + 2 * kBTile, base + 3 * kBTile, k, kk, sin(2.0 * PI * r / kNfft));
+            }
+        }
+    }
+    unsigned char* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, host.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        mmla_set_error("overlap: DFT operand upload failed: %s", cudaGetErrorString(e));
+        return MMLA_ECUDA;
+    }
+    g_dft_b[dev] = d;
+    *out = d;
+    return MMLA_OK;
+}
 
 int get_tables(int n_mels, const OverlapTables** out) {
     int dev = 0;
@@ -471,16 +883,27 @@ extern "C" __attribute__((visibility("default"))) int mmla_overlap_features(
     }
     const int sms = mmla_num_sms();
     MMLA_REQUIRE(sms > 0, MMLA_ECUDA, "overlap: no CUDA device");
-    static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
-    const bool attr_set = !attr_once.first();
-    if (!attr_set) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(overlap_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(sizeof(Smem))));
-    }
     long long grid = sms;
     if (grid > n_clips) grid = n_clips;
-    overlap_features_kernel<<<static_cast<unsigned>(grid), kThreads, sizeof(Smem), st>>>(kp);
-    mmla_count_launch("overlap_features_kernel", st);
+    const char* force = getenv("MMLA_OVERLAP_KERNEL");
+    if (force && strcmp(force, "fp32") == 0) {
+        // the CUDA-core contraction (r01 kernel): kept as the cross-check of the tensor-core path
+        static MmlaPerDeviceOnce attr_once;                      // cudaFuncSetAttribute is per device
+        if (attr_once.first())
+            MMLA_CUDA_CHECK(cudaFuncSetAttribute(overlap_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(sizeof(Smem))));
+        overlap_features_kernel<<<static_cast<unsigned>(grid), kThreads, sizeof(Smem), st>>>(kp);
+        mmla_count_launch("overlap_features_kernel", st);
+    } else {
+        rc = get_dft_b(&kp.dft_b);
+        if (rc != MMLA_OK) return rc;
+        static MmlaPerDeviceOnce attr_once_tc;
+        if (attr_once_tc.first())
+            MMLA_CUDA_CHECK(cudaFuncSetAttribute(overlap_features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(sizeof(SmemTc))));
+        overlap_features_tc_kernel<<<static_cast<unsigned>(grid), kTcThreads, sizeof(SmemTc), st>>>(kp);
+        mmla_count_launch("overlap_features_tc_kernel", st);
+    }
     MMLA_CUDA_CHECK(cudaGetLastError());
     if (dev_tmp) MMLA_CUDA_CHECK(cudaFreeAsync(dev_tmp, st));
     return MMLA_OK;

@@ -89,3 +89,37 @@ def test_overlap_reference_signatures(cuda, tmp_path):
     m = np.arange(12, dtype=np.float32).reshape(3, 4)
     np.testing.assert_allclose(ofg.normalize_matrix(m), lm.normalize_matrix(m), rtol=1e-6)
     assert np.isnan(ofg.normalize_matrix(np.ones((2, 2), np.float32))).all()
+
+
+def test_tensor_core_dft_matches_cuda_core_kernel_and_oracle(cuda, monkeypatch):
+    """r02: the folded 400-point DFT runs on tcgen05 (fp16 hi + lo split, three products, fp32 accumulation in TMEM) in
+    `overlap_features_tc_kernel`; `MMLA_OVERLAP_KERNEL=fp32` selects the r01 CUDA-core contraction.  Both against the oracle
+    (same tolerances), exact ZCR on both, and against each other on a ragged batch incl. quiet and all-zero clips."""
+    from mmla_audio_b200 import _lib
+    from mmla_audio_b200.overlap_features_generator import OverlapFeaturesGenerator
+    ofg = OverlapFeaturesGenerator(wl=25, hl=10)
+    lib = _lib.load()
+    pcm = synth.synth_clips(60, 40, 24000)
+    pcm[3] = pcm[3] // 300                                # quiet clip: ~100 LSB peak (lo halves near the fp16 subnormals)
+    pcm[4] = 0
+    pcm[5, 5000:] = 0
+    names0 = []
+    feats = {}
+    for mode in ("tc", "fp32"):
+        if mode == "fp32":
+            monkeypatch.setenv("MMLA_OVERLAP_KERNEL", "fp32")
+        else:
+            monkeypatch.delenv("MMLA_OVERLAP_KERNEL", raising=False)
+        tr = _lib.trace_launches(lambda: feats.__setitem__(mode, ofg.features_batch(pcm, want=("s_db", "s_db_norm", "zcr", "image"))), cuda)
+        names0.append([n for n, _ in tr])
+    assert names0[0] == ["overlap_features_tc_kernel"] and names0[1] == ["overlap_features_kernel"]
+    for i in list(range(8)) + [39]:
+        if i == 4:
+            continue                                      # constant clip: 0/0 in normalize_matrix (the caller discards it)
+        _check_clip(pcm[i], feats["tc"], i, f"tc clip{i}")
+    assert cuda.equal(feats["tc"]["zcr"], feats["fp32"]["zcr"])
+    live = [i for i in range(40) if i != 4]
+    d_db = (feats["tc"]["s_db"][live] - feats["fp32"]["s_db"][live]).abs().max().item()
+    d_img = (feats["tc"]["image"][live].int() - feats["fp32"]["image"][live].int()).abs()
+    print("tensor-core vs CUDA-core DFT: max |d s_db|", d_db, "pixels differing", (d_img > 0).float().mean().item())
+    assert d_db <= 0.02 and d_img.max().item() <= 1 and (d_img > 0).float().mean().item() <= 0.01
