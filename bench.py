@@ -247,8 +247,9 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
             work[k] = {"bound": "hbm", "per_step": nb, "what": "int16 PCM in + float32 [T,13] cepstra out"}
         return work
     if workload == "overlap":
-        work["overlap_features_kernel"] = {"bound": "hbm", "per_step": B * (24000 * 2 + 128 * 151 * 3),
-                                           "what": "int16 PCM (24000 samples) in + uint8 [128,151,3] image out"}
+        for k in ("overlap_features_tc_kernel", "overlap_features_kernel"):
+            work[k] = {"bound": "hbm", "per_step": B * (24000 * 2 + 128 * 151 * 3),
+                       "what": "int16 PCM (24000 samples) in + uint8 [128,151,3] image out"}
         spec, T0, H0 = pipe.model.spec, 151, 128
     else:
         rows = min(T, 256)
@@ -311,6 +312,9 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
         work["conv_slab_kernel"] = {"bound": "tensor", "per_step": B * slab,
                                     "what": "the 18 stride-1 3x3 / 4x1 convolutions of the residual blocks (TF32, tap-shifted slabs)"}
+        work["resblock2d_fused_kernel"] = {"bound": "tensor", "per_step": B * slab,
+                                           "what": "the 9 residual blocks' conv pairs (3x3 then 4x1, TF32, tap-shifted slabs, the "
+                                                   "intermediate stays in shared memory): 18 convolutions in 9 launches"}
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (res - slab),
                                   "what": "the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
         work["pool_shortcut_kernel"] = {"bound": "hbm", "per_step": B * pool_bytes,
@@ -640,7 +644,8 @@ def main():
         summary["overlap_x512_audio_s_per_s"] = round(world * Bo * Lo / SR / (ms_o * 1e-3), 1)
         summary["overlap_x512_e2e_audio_s_per_s"] = round(world * Bo * Lo / SR / (ms_oe * 1e-3), 1)
         for row in ok:
-            if row["kernel"] in ("conv_slab_kernel", "overlap_features_kernel") and "frac" in row:
+            if row["kernel"] in ("conv_slab_kernel", "resblock2d_fused_kernel", "overlap_features_kernel",
+                                 "overlap_features_tc_kernel") and "frac" in row:
                 summary["overlap_%s_frac" % row["kernel"]] = round(row["frac"], 4)
         del po, po_dev, po_host, opipe
 

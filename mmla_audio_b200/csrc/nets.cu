@@ -506,6 +506,12 @@ int mmla_launch_resunit_fused(const float* x, float* y, long long B, int T, int 
                               const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                               const float* bn2_shift, const float* w2, const float* b2, const float* ws, const float* bs,
                               cudaStream_t st);
+// resblock2d_fused.cu (overlap net: both convolutions of a res_block in one launch)
+bool mmla_resblock2d_eligible(int H, int W, int Cin, int C, int kh1, int kw1, int kh2, int kw2, int act);
+int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, int W, int Cin, int C, const float* bn1_scale,
+                                 const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
+                                 const float* bn2_shift, const float* w2, const float* b2, const float* res,
+                                 long long res_row_stride, cudaStream_t st);
 // lstm_fused.cu
 long long mmla_xproj_arranged_floats();
 void mmla_xproj_arrange_weights(const float* W, float* out);
@@ -864,6 +870,11 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
             float* A = buf[(cur + 1) % 3];
             float* Bf = buf[(cur + 2) % 3];
             auto fusable = [&](const BlockW& k) { return k.conv1.k_tc && k.conv2.k_tc && (!k.pool || k.shortcut.k_tc); };
+            auto pair_fusable = [&](const BlockW& k, int h, int w) {
+                return k.conv1.k_tc && k.conv2.k_tc && k.conv1.stride == 1 && k.conv2.stride == 1 && k.conv2.cin == k.conv1.cout &&
+                       k.conv2.cout == k.conv1.cout && k.bn1.scale && k.bn2.scale &&
+                       mmla_resblock2d_eligible(h, w, k.conv1.cin, k.conv1.cout, k.conv1.kh, k.conv1.kw, k.conv2.kh, k.conv2.kw, act_kind);
+            };
             if (tc && !ov && net->fuse_stages && blk.pool && bi + 2 < net->blocks.size() && fusable(blk) &&
                 fusable(net->blocks[bi + 1]) && fusable(net->blocks[bi + 2]) && !net->blocks[bi + 1].pool &&
                 !net->blocks[bi + 2].pool && net->blocks[bi + 1].conv1.cin == blk.conv1.cout &&
@@ -906,13 +917,28 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 cur = (cur + 1) % 3;
             } else if (!blk.pool) {
                 // out = conv2(act(bn2(conv1(act(bn1(x)))))) + x
-                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
-                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, X, blk.conv2.cout, Bf, st, tc))) return rc;
+                if (ov && tc && pair_fusable(blk, H, W)) {
+                    // both convolutions in one launch, the intermediate stays in shared memory (resblock2d_fused.cu)
+                    if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
+                                                           blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
+                                                           blk.conv2.b, X, blk.conv2.cout, st)))
+                        return rc;
+                } else {
+                    if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
+                    if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, X, blk.conv2.cout, Bf, st, tc))) return rc;
+                }
                 cur = (cur + 2) % 3;
             } else if (ov) {
                 // full-resolution convs, MaxPool2x2 'same', then shortcut conv (stride 2) + pooled
-                if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
-                if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st, tc))) return rc;
+                if (tc && pair_fusable(blk, H, W)) {
+                    if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
+                                                           blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
+                                                           blk.conv2.b, nullptr, 0, st)))
+                        return rc;
+                } else {
+                    if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
+                    if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st, tc))) return rc;
+                }
                 const int Ho = same_out(H, 2), Wo = same_out(W, 2), C = blk.conv2.cout;
                 const char* fp = getenv("MMLA_NET_FUSE_POOL");
                 const size_t wbytes = static_cast<size_t>(blk.shortcut.cin) * C * sizeof(float);
@@ -1064,6 +1090,34 @@ EXPORT int mmla_debug_conv2d(const float* x, const float* w_host, const float* b
     }
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == MMLA_OK) {
         mmla_set_error("debug_conv2d: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = MMLA_ECUDA;
+    }
+    cudaFree(wdev);
+    return rc;
+}
+
+EXPORT int mmla_debug_resblock2d(const float* x, const float* w1_host, const float* b1, const float* bn1_scale, const float* bn1_shift,
+                                 const float* w2_host, const float* b2, const float* bn2_scale, const float* bn2_shift, const float* res,
+                                 float* y, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t C, void* stream) {
+    MMLA_REQUIRE(x && w1_host && b1 && bn1_scale && bn1_shift && w2_host && b2 && bn2_scale && bn2_shift && y && B >= 0 && H > 0 &&
+                     W > 0 && Cin > 0 && C > 0,
+                 MMLA_EINVAL, "debug_resblock2d: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MMLA_REQUIRE(mmla_resblock2d_eligible(H, W, Cin, C, 3, 3, 4, 1, ACT_ELU), MMLA_EUNSUP,
+                 "debug_resblock2d: block is not eligible for resblock2d_fused_kernel");
+    const int K1 = 9 * Cin, K2 = 4 * C;
+    const long long n1 = mmla_tc_arranged_floats(K1, C), n2 = mmla_tc_arranged_floats(K2, C);
+    std::vector<float> host(n1 + n2);
+    mmla_tc_arrange_weights(w1_host, K1, C, host.data());
+    mmla_tc_arrange_weights(w2_host, K2, C, host.data() + n1);
+    float* wdev = nullptr;
+    MMLA_CUDA_CHECK(cudaMalloc(&wdev, host.size() * sizeof(float)));
+    int rc = MMLA_OK;
+    if (cudaMemcpyAsync(wdev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MMLA_ECUDA;
+    if (rc == MMLA_OK)
+        rc = mmla_launch_resblock2d_fused(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, wdev, b1, bn2_scale, bn2_shift, wdev + n1, b2, res, C, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == MMLA_OK) {
+        mmla_set_error("debug_resblock2d: %s", cudaGetErrorString(cudaGetLastError()));
         rc = MMLA_ECUDA;
     }
     cudaFree(wdev);

@@ -1,0 +1,589 @@
+// One launch per `res_block` conv pair of the overlap classifier (overlap_detector_temp.py:253-280):
+//
+//     u = Conv2D(C, 3, 'same')(ELU(BN1(x)))          v = Conv2D(C, (4, 1), 'same')(ELU(BN2(u)))  (+ x for a plain block)
+//
+// conv_slab_kernel ran the two convolutions as two launches with u (fp32, up to 1.27 GB per 512 clips) written to HBM by
+// the first and gathered + activated again by the second: 6.7 GB of the net's 12.6 GB of DRAM traffic per 512 clips was u.
+// Here u never leaves the SM.  Both convolutions use the same flat pixel numbering with the image HEIGHT as the fast axis
+// and Fp = H + 3 entries per column (Keras 'same' for k = 4: one row before, two after; the 3x3 needs 1 + 1 <= 3):
+//
+//     q = w * Fp + h                                  flat index of an output pixel (h >= H: junk rows, 2 %, never stored)
+//     conv1:  u(j) = b1 + sum_{dh,dw} W1[dh][dw] . xpad[j + dw * Fp + dh]       xpad[(w + 1) * Fp + h + 1] = ELU(BN1(x[h, w]))
+//     conv2:  v(q) = b2 + sum_{dh}    W2[dh]     . upad[q + dh]                 upad[j + 1] = valid(j) ? ELU(BN2(u(j))) : 0
+//
+// i.e. every filter tap of either convolution is a UNIFORM row shift of one operand slab (csrc/conv_slab.cu), and conv1's
+// accumulator row j is exactly conv2's padded operand row j + 1 with the junk rows replaced by the zero padding.  A CTA owns
+// S = 128 T - 3 consecutive outputs q of one image (T <= 4 tiles of 128 rows):
+//   fill      x rows [Q - 1, Q - 1 + 128 T + 2 Fp + 2) by 16-byte cp.async, BN1 + ELU + TF32 rounding in place (as conv_slab)
+//   conv1     T accumulators of C columns in TMEM, weights through a TMA ring ([32 x C] K-chunks, conv_tc.cu arrangement)
+//   epilogue1 tcgen05.ld -> + b1 -> BN2 -> ELU -> TF32 -> the u slab [channel quad][row][16 B], which OVERLAYS the dead x slab
+//   conv2     the same TMEM columns and the same weight ring (its chunks follow conv1's; they are prefetched into the slots
+//             conv1 frees while epilogue 1 runs)
+//   epilogue2 tcgen05.ld -> staging tiles in the dead slab -> + b2 (+ residual) -> whole-line NHWC stores
+// Arithmetic per element is the same sequence of operations as the two conv_slab launches (same TF32 operands, same K order,
+// same fp32 epilogue expressions), so the results are bit-identical to them (tests/test_resblock2d_gpu.py).
+#include <stdlib.h>
+#include <string.h>
+
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int kRbBK = 32;                   // K per ring chunk (mmla_tc_arrange_weights)
+constexpr int kRbMaxTiles = 4;
+constexpr int kRbMaxStages = 40;
+constexpr int kRbMaxChunks = 64;           // conv1 + conv2 chunks
+
+struct RbArgs {
+    const float* x;
+    const float* w1;          // arranged weights (conv_tc.cu layout, one N tile) of the 3x3
+    const float* w2;          // ... of the 4x1
+    const float* b1;
+    const float* b2;
+    const float* bn1_scale;
+    const float* bn1_shift;
+    const float* bn2_scale;
+    const float* bn2_shift;
+    const float* res;
+    float* y;
+    long long res_row_stride;
+    long long img_pixels;     // H * W
+    int H, W, Fp;
+    unsigned fp_magic;        // floor(2^32 / Fp) + 1
+    int total_q;              // W * Fp
+    int Cin, lq;              // lq = log2(Cin / 4)
+    int nk1, nk;              // ring chunks of conv1 / of both convolutions
+    int nmma1_last, nmma2_last;
+    int T, S, cpi;            // tiles per CTA, outputs per CTA (128 T - 3), CTAs per image
+    int RsX, RsU;             // slab strides in rows
+    int stages;
+    unsigned ring_off, par_off, bar_off;
+    unsigned aoff[kRbMaxChunks * 4];   // per MMA: channel-quad slab + tap row shift, in 16-byte units
+    long long* stamps;        // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
+    int stamp_cta;
+};
+
+__device__ __forceinline__ uint32_t rb_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void rb_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 24); ++i)
+        if (mbar_try_wait(bar, parity)) return;
+    asm volatile("trap;");
+}
+// BN + ELU + TF32 rounding of one element: the expression of conv_slab.cu's fill (bit-identical results).
+__device__ __forceinline__ uint32_t rb_bn_elu_tf32(float v, float sc, float sh) {
+    v = fmaf(v, sc, sh);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+    v = v > 0.f ? v : e - 1.f;
+    return rb_tf32(v);
+}
+__device__ __forceinline__ uint64_t rb_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ bool rb_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void rb_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void rb_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int NT, bool RES, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resblock2d_fused_kernel(const RbArgs a) {
+    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
+    constexpr uint32_t kChunkBytes = 8 * NT * 16;
+    constexpr int kWarps = THREADS / 32;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    unsigned char* slab = base;
+    unsigned char* ring = base + a.ring_off;
+    float* par = reinterpret_cast<float*>(base + a.par_off);              // b1 | bn2 scale | bn2 shift, NT floats each
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + a.bar_off);      // [stages]
+    uint64_t* empty = full + kRbMaxStages;                               // [stages]
+    uint64_t* accum = full + 2 * kRbMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kRbMaxStages + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool stamping = a.stamps != nullptr && static_cast<int>(blockIdx.x) == a.stamp_cta;
+    auto stamp = [&](int slot) {
+        if (stamping) a.stamps[slot] = clock64();
+    };
+    if (tid == 0) stamp(0);
+    const int img = blockIdx.x / a.cpi;
+    const int Qc = (blockIdx.x - img * a.cpi) * a.S;                      // first output of this CTA
+    const int nq = min(a.S, a.total_q - Qc);                              // outputs of this CTA
+    const int Tc = (nq + 3 + 127) >> 7;                                   // tiles of either convolution
+    const uint32_t cols = (Tc * NT <= 32) ? 32u : (Tc * NT <= 64) ? 64u : (Tc * NT <= 128) ? 128u : (Tc * NT <= 256) ? 256u : 512u;
+
+    if (tid == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(accum, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 3 * NT; i += THREADS) {
+        const int c = i % NT, which = i / NT;
+        par[i] = __ldg((which == 0 ? a.b1 : which == 1 ? a.bn2_scale : a.bn2_shift) + c);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) stamp(1);
+
+    auto wsrc = [&](int kc) {
+        return kc < a.nk1 ? a.w1 + static_cast<long long>(kc) * (NT * kRbBK) : a.w2 + static_cast<long long>(kc - a.nk1) * (NT * kRbBK);
+    };
+    // ---- weight ring: the first `stages` chunks need no free slot, so they are requested before the fill ----
+    if (lane == 0) {                          // one chunk per warp at a time: bulk copies of one thread serialise
+        const int pre = a.nk < a.stages ? a.nk : a.stages;
+        for (int kc = warp; kc < pre; kc += kWarps) {
+            mbar_arrive_expect_tx(&full[kc], kChunkBytes);
+            tma_bulk_g2s(ring + kc * kChunkBytes, wsrc(kc), kChunkBytes, &full[kc]);
+        }
+    }
+
+    // ---- x slab fill: row r <-> padded flat index Qc - 1 + r; BN1 + ELU + TF32 once per element (conv_slab.cu's fill) ----
+    {
+        const int rows = Tc * 128 + 2 * a.Fp + 2;
+        const int lqg = a.lq - 2;                             // log2(quad groups of 4)
+        const int c4 = ((warp & ((1 << lqg) - 1)) << 2) + (lane >> 3);
+        const int rpp = (kWarps >> lqg) * 8;                  // rows per pass of the whole CTA
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bn1_scale) + c4);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.bn1_shift) + c4);
+        const float* ximg = a.x + static_cast<long long>(img) * a.img_pixels * a.Cin + 4 * c4;
+        unsigned char* dst0 = slab + static_cast<size_t>(c4) * a.RsX * 16;
+        unsigned long long okmask = 0ull;                     // bit i: row r0 + i * rpp holds image data
+        const int r0 = (warp >> lqg) * 8 + (lane & 7);
+        auto copy_batch = [&](int it) {                       // rows r0 + (it .. it+3) * rpp: one cp.async group
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + (it + u) * rpp;
+                if (r < rows) {
+                    const int p = Qc - 1 + r;
+                    const int wp = static_cast<int>(__umulhi(static_cast<unsigned>(p < 0 ? 0 : p), a.fp_magic));
+                    const int w = wp - 1, h = p - wp * a.Fp - 1;
+                    const bool ok = p >= 0 && w >= 0 && w < a.W && h >= 0 && h < a.H;
+                    okmask |= static_cast<unsigned long long>(ok) << (it + u);
+                    const float* src = ximg + (ok ? static_cast<long long>(h * a.W + w) * a.Cin : 0ll);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst0 + static_cast<size_t>(r) * 16)),
+                                 "l"(src), "r"(ok ? 16 : 0)
+                                 : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto xform_batch = [&](int it) {
+            uint4 raw[4];
+            const unsigned m4 = static_cast<unsigned>(okmask >> it) & 15u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + (it + u) * rpp < rows) raw[u] = *reinterpret_cast<const uint4*>(dst0 + static_cast<size_t>(r0 + (it + u) * rpp) * 16);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (r0 + (it + u) * rpp < rows) {
+                    const uint32_t keep = ((m4 >> u) & 1u) ? 0xFFFFFFFFu : 0u;         // padding rows stay zero
+                    *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(r0 + (it + u) * rpp) * 16) = make_uint4(
+                        rb_bn_elu_tf32(__uint_as_float(raw[u].x), sc.x, sh.x) & keep, rb_bn_elu_tf32(__uint_as_float(raw[u].y), sc.y, sh.y) & keep,
+                        rb_bn_elu_tf32(__uint_as_float(raw[u].z), sc.z, sh.z) & keep, rb_bn_elu_tf32(__uint_as_float(raw[u].w), sc.w, sh.w) & keep);
+                }
+            }
+        };
+        constexpr int kAhead = 3;
+        int it = 0;
+        for (; r0 + it * rpp < rows; it += 4) {
+            copy_batch(it);
+            if (it >= 4 * kAhead) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");
+                xform_batch(it - 4 * kAhead);
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        for (int jt = it >= 4 * kAhead ? it - 4 * kAhead : 0; jt < it; jt += 4) xform_batch(jt);
+    }
+    if (tid == 0) stamp(2);
+    fence_proxy_async_smem();                // generic-proxy slab writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) stamp(3);
+
+    // Ring state of the two single-warp roles; both convolutions run through the same loop bodies.
+    int p_stg = 0, p_kc = a.stages;           // producer (warp 1): next chunk to request
+    uint32_t p_ph = 0u;
+    int m_stg = 0;                            // MMA issuer (warp 0)
+    uint32_t m_ph = 0u;
+    auto produce = [&](int kc_end) {          // chunks [p_kc, kc_end)
+        for (; p_kc < kc_end; ++p_kc) {
+            rb_wait(&empty[p_stg], p_ph);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[p_stg], kChunkBytes);
+                tma_bulk_g2s(ring + p_stg * kChunkBytes, wsrc(p_kc), kChunkBytes, &full[p_stg]);
+            }
+            __syncwarp();
+            if (++p_stg == a.stages) { p_stg = 0; p_ph ^= 1u; }
+        }
+    };
+    auto issue = [&](int kc0, int kc1, int nmma_last, uint32_t rs16) {   // chunks [kc0, kc1) of one convolution
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dA = rb_desc(smem_u32(slab), rs16, 128u);
+        const uint64_t dB = rb_desc(smem_u32(ring), NT * 16, 128);
+        for (int kc = kc0; kc < kc1; ++kc) {
+            rb_wait(&full[m_stg], m_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t bd0 = dB + static_cast<uint64_t>(m_stg * (kChunkBytes / 16));
+            const uint32_t aoff[4] = {a.aoff[kc * 4], a.aoff[kc * 4 + 1], a.aoff[kc * 4 + 2], a.aoff[kc * 4 + 3]};
+            const int nmma = kc == kc1 - 1 ? nmma_last : 4;
+            const uint32_t alo = static_cast<uint32_t>(dA), ahi = static_cast<uint32_t>(dA >> 32);
+            const uint32_t blo = static_cast<uint32_t>(bd0), bhi = static_cast<uint32_t>(bd0 >> 32);
+            if (rb_elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int t = 0; t < kRbMaxTiles; ++t) {
+                        if (kk < nmma && t < Tc) {
+                            const uint32_t acc = (kc != kc0 || kk != 0) ? 1u : 0u;
+                            asm volatile(
+                                "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+                                "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
+                                "r"(alo + aoff[kk] + static_cast<uint32_t>(t * 128)), "r"(ahi), "r"(blo + static_cast<uint32_t>(kk * 2 * NT)),
+                                "r"(bhi), "r"(kIdesc), "r"(acc)
+                                : "memory");
+                        }
+                    }
+                }
+                rb_commit(&empty[m_stg]);
+                if (kc == kc1 - 1) rb_commit(accum);
+            }
+            if (++m_stg == a.stages) { m_stg = 0; m_ph ^= 1u; }
+            __syncwarp();
+        }
+    };
+
+    // ================= conv1 =================
+    if (warp == 1) {
+        // conv2's chunks go into the slots conv1's MMAs free; the rest waits for conv2 (after epilogue 1: this warp takes part)
+        const int lim = a.nk1 + a.stages;
+        produce(a.nk < lim ? a.nk : lim);
+    } else if (warp == 0) {
+        issue(0, a.nk1, a.nmma1_last, static_cast<uint32_t>(a.RsX) * 16u);
+        if (lane == 0) stamp(4);
+    }
+
+    constexpr int kChunks = NT / 32;
+    constexpr int kGroups = THREADS / 128;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int nunits = Tc * kChunks;
+
+    // ================= epilogue 1: accumulator -> + b1 -> BN2 -> ELU -> TF32 -> u slab (over the dead x slab) =================
+    {
+        if (warp == 0) rb_wait(accum, 0u);    // one polling warp, everybody else sleeps in the hardware barrier
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) stamp(5);
+        const float4* par4 = reinterpret_cast<const float4*>(par);
+        for (int u = half; u < nunits; u += kGroups) {
+            const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
+            const int i = t * 128 + quarter * 32 + lane;      // u slab row = padded index Qc + i; conv1's flat output j = Qc - 1 + i
+            const int j = Qc - 1 + i;
+            bool valid = j >= 0 && j < a.total_q;
+            if (valid) {
+                const int wj = static_cast<int>(__umulhi(static_cast<unsigned>(j), a.fp_magic));
+                valid = j - wj * a.Fp < a.H;
+            }
+            const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;   // junk rows ARE conv2's zero padding
+            uint32_t r[32];
+            rb_tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * NT + col0), r);
+            unsigned char* dst = slab + (static_cast<size_t>(col0 >> 2) * a.RsU + i) * 16;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 bb = par4[(col0 >> 2) + g], sc = par4[(NT >> 2) + (col0 >> 2) + g], sh = par4[(NT >> 1) + (col0 >> 2) + g];
+                *reinterpret_cast<uint4*>(dst + static_cast<size_t>(g) * a.RsU * 16) =
+                    make_uint4(rb_bn_elu_tf32(__uint_as_float(r[4 * g]) + bb.x, sc.x, sh.x) & keep,
+                               rb_bn_elu_tf32(__uint_as_float(r[4 * g + 1]) + bb.y, sc.y, sh.y) & keep,
+                               rb_bn_elu_tf32(__uint_as_float(r[4 * g + 2]) + bb.z, sc.z, sh.z) & keep,
+                               rb_bn_elu_tf32(__uint_as_float(r[4 * g + 3]) + bb.w, sc.w, sh.w) & keep);
+            }
+        }
+        // rows 128 Tc .. + 2 only feed outputs that are never stored, but they must be finite
+        for (int i = tid; i < 3 * (NT / 4); i += THREADS)
+            *reinterpret_cast<uint4*>(slab + (static_cast<size_t>(i / 3) * a.RsU + Tc * 128 + i % 3) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        fence_proxy_async_smem();
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) stamp(6);
+    }
+
+    // ================= conv2 =================
+    if (warp == 1) {
+        produce(a.nk);
+    } else if (warp == 0) {
+        issue(a.nk1, a.nk, a.nmma2_last, static_cast<uint32_t>(a.RsU) * 16u);
+        if (lane == 0) stamp(7);
+    }
+
+    // ================= epilogue 2: + b2 (+ residual) -> NHWC (conv_slab.cu's staged epilogue) =================
+    {
+        float* stg = reinterpret_cast<float*>(slab) + warp * (32 * 36);
+        const int seg = lane & 7, rsub = lane >> 3;
+        int pixoff[8];                          // pixel index inside the image, -1: junk row
+        const long long imgbase = static_cast<long long>(img) * a.img_pixels;
+        float4 rr[RES ? 8 : 1];
+        auto prefetch = [&](int u) {
+            const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
+            const int rb = t * 128 + quarter * 32 + rsub;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = rb + 4 * i, q = Qc + row;
+                const int wq = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), hq = q - wq * a.Fp;
+                const bool valid = row < nq && hq < a.H;
+                pixoff[i] = valid ? hq * a.W + wq : -1;
+                if (RES) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (RES && valid) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res + (imgbase + pixoff[i]) * a.res_row_stride + col0) + seg);
+            }
+        };
+        if (half < nunits) prefetch(half);
+        if (warp == 0) rb_wait(accum, 1u);
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 64) stamp(8);
+        for (int u = half; u < nunits; u += kGroups) {
+            const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
+            uint32_t r[32];
+            rb_tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * NT + col0), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)       // lane = row; row stride 144 B: a quarter-warp's STS.128 covers 8 distinct 16-byte slots
+                *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            __syncwarp();
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.b2 + col0) + seg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {     // rows 4i .. 4i+3 of the warp's 32, eight lanes (128 B) per row
+                if (pixoff[i] >= 0) {
+                    const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * seg);
+                    *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) =
+                        RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
+                            : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                }
+            }
+            __syncwarp();                     // the staging tile is rewritten by the next unit
+            if (u + kGroups < nunits) prefetch(u + kGroups);
+        }
+    }
+    if (tid == 64) stamp(9);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) stamp(10);
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+    }
+}
+
+int rb_ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+long long* g_rb_stamps = nullptr;         // mmla_debug_resblock2d_stamps: 16 rows (launch ordinal) x 16 slots
+int g_rb_stamp_cta = 0, g_rb_stamp_row = 0;
+
+template <int NT, bool RES, int THREADS>
+int launch_rb(const RbArgs& s, long long images, size_t smem, cudaStream_t st) {
+    static size_t attr[64] = {};                                  // per device: function attributes are per device
+    int dev = 0;
+    MMLA_CUDA_CHECK(cudaGetDevice(&dev));
+    MMLA_REQUIRE(dev >= 0 && dev < 64, MMLA_EUNSUP, "resblock2d: device ordinal %d out of range", dev);
+    if (smem > attr[dev]) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resblock2d_fused_kernel<NT, RES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)));
+        attr[dev] = smem;
+    }
+    resblock2d_fused_kernel<NT, RES, THREADS><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
+    mmla_count_launch("resblock2d_fused_kernel", st);
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
+}  // namespace
+
+// Whether resblock2d_fused_kernel takes a res_block's conv pair: 3x3 'same' (Cin 16 / 32 / 64 / 128 -> C) then (4, 1) 'same'
+// (C -> C), both stride 1, ELU prologues.  MMLA_NET_FUSE_BLOCKS=0 keeps the two conv_slab launches.
+bool mmla_resblock2d_eligible(int H, int W, int Cin, int C, int kh1, int kw1, int kh2, int kw2, int act) {
+    const char* e = getenv("MMLA_NET_FUSE_BLOCKS");     // read per launch: tests flip it between calls
+    if (e && e[0] == '0') return false;
+    if (kh1 != 3 || kw1 != 3 || kh2 != 4 || kw2 != 1 || act != ACT_ELU) return false;
+    if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
+    if (C != 32 && C != 64 && C != 128) return false;
+    if (H < 2 || W < 1) return false;
+    if (static_cast<long long>(W + 2) * (H + 3) + 512 + 8 >= (1LL << 20)) return false;
+    return true;
+}
+
+int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, int W, int Cin, int C, const float* bn1_scale,
+                                 const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
+                                 const float* bn2_shift, const float* w2, const float* b2, const float* res,
+                                 long long res_row_stride, cudaStream_t st) {
+    if (B <= 0) return MMLA_OK;
+    MMLA_REQUIRE(!res || res_row_stride % 4 == 0, MMLA_EUNSUP, "resblock2d: residual row stride must be a multiple of 4 floats");
+    RbArgs s;
+    memset(&s, 0, sizeof(s));
+    s.x = x; s.y = y; s.w1 = w1; s.w2 = w2; s.b1 = b1; s.b2 = b2;
+    s.bn1_scale = bn1_scale; s.bn1_shift = bn1_shift; s.bn2_scale = bn2_scale; s.bn2_shift = bn2_shift;
+    s.res = res; s.res_row_stride = res_row_stride;
+    s.img_pixels = static_cast<long long>(H) * W;
+    s.H = H; s.W = W; s.Fp = H + 3;
+    s.fp_magic = static_cast<unsigned>((1ULL << 32) / static_cast<unsigned>(s.Fp)) + 1u;
+    s.total_q = W * s.Fp;
+    s.Cin = Cin; s.lq = rb_ilog2(Cin / 4);
+    const int K1 = 9 * Cin, K2 = 4 * C;
+    s.nk1 = (K1 + kRbBK - 1) / kRbBK;
+    s.nk = s.nk1 + K2 / kRbBK;
+    MMLA_REQUIRE(s.nk <= kRbMaxChunks, MMLA_EUNSUP, "resblock2d: K = %d + %d is too large", K1, K2);
+    const size_t chunk = static_cast<size_t>(8) * C * 16;        // one [32 x C] K-chunk of weights
+    constexpr size_t kBarBytes = 1024 + 128;                    // mbarriers + alignment slack
+    const size_t par_bytes = static_cast<size_t>(3) * C * 4;
+    auto rows_x = [&](int T) {
+        int r = T * 128 + 2 * s.Fp + 2;
+        if (Cin == 16) { while ((r & 7) != 2) ++r; } else if ((r & 1) == 0) ++r;     // conflict-free fill stores (conv_slab.cu)
+        return r;
+    };
+    auto rows_u = [&](int T) { return (T * 128 + 3) | 1; };
+    auto slab_bytes = [&](int T, int nthr) {
+        const size_t bx = static_cast<size_t>(Cin / 4) * rows_x(T) * 16, bu = static_cast<size_t>(C / 4) * rows_u(T) * 16;
+        const size_t stg = static_cast<size_t>(nthr / 32) * 32 * 36 * 4;               // epilogue-2 staging tiles, one per warp
+        size_t b = bx > bu ? bx : bu;
+        return b > stg ? b : stg;
+    };
+    // Tiles per CTA, ring depth and CTAs per SM: the cost model of conv_slab.cu (fitted to its clock64 timelines) with both
+    // convolutions' phases in one CTA; co-resident CTAs in different phases are what hides the fill and the epilogues.
+    int force_t = 0, force_kb = 0, force_stages = 0;
+    if (const char* e = getenv("MMLA_RB_TILES")) force_t = atoi(e);
+    if (const char* e = getenv("MMLA_RB_KB")) force_kb = atoi(e);
+    if (const char* e = getenv("MMLA_RB_STAGES")) force_stages = atoi(e);
+    int tmax = kRbMaxTiles;
+    if (tmax > 512 / C) tmax = 512 / C;
+    {
+        const int need = (s.total_q + 3 + 127) / 128;             // a whole image in one CTA
+        if (tmax > need) tmax = need;
+    }
+    int T = 0, best_thr = 256;
+    double best = 0.0;
+    for (int pass = 0; pass < 2 && !T; ++pass) {       // pass 1: a forced tile count / budget that fits nowhere is ignored
+        if (pass == 1) force_t = force_kb = 0;
+        const int budgets_kb[3] = {75, 113, 226};
+        const double overlap[3] = {4.5, 3.2, 1.0};
+        for (int bi = res ? 1 : 0; bi < 3; ++bi) {
+            const int nthr = res || bi == 0 ? 256 : 512;
+            const int ctas = 3 - bi;
+            const size_t budget = static_cast<size_t>(force_kb >= 16 && force_kb <= 226 ? force_kb : budgets_kb[bi]) * 1024;
+            for (int t = 1; t <= tmax; ++t) {
+                if (force_t >= 1 && force_t <= tmax && t != force_t) continue;
+                int cols = 32;
+                while (cols < t * C) cols *= 2;
+                if (cols * ctas > 512) continue;                  // the CTAs of an SM share 512 TMEM columns
+                const size_t fixed = slab_bytes(t, nthr) + par_bytes + kBarBytes + 256;
+                if (fixed + 2 * chunk > budget) continue;
+                int stages = static_cast<int>((budget - fixed) / chunk);
+                if (stages > s.nk) stages = s.nk;
+                if (stages > kRbMaxStages) stages = kRbMaxStages;
+                if (force_stages >= 1 && force_stages <= stages) stages = force_stages;
+                const double per_chunk = t * 4.0 * (C / 2 > 45 ? C / 2 : 45);
+                const double refill = (3000.0 + per_chunk) / stages;
+                const double mma = s.nk * (per_chunk > refill ? per_chunk : refill);
+                const double fill = 5000.0 + rows_x(t) * (Cin / 4) / static_cast<double>(nthr) * 40.0;
+                const double epi = 2.0 * (3000.0 + 700.0 * t * (C / 32));
+                const int outs = t * 128 - 3;
+                const int cpi = (s.total_q + outs - 1) / outs;
+                const double cost = (fill + mma + epi) * cpi / overlap[bi] / s.total_q;
+                if (!T || cost < best) {
+                    T = t; best = cost; s.stages = stages; best_thr = nthr;
+                }
+            }
+        }
+    }
+    MMLA_REQUIRE(T > 0, MMLA_EUNSUP, "resblock2d: block does not fit in shared memory (Cin %d, C %d, H %d)", Cin, C, H);
+    s.T = T;
+    s.S = T * 128 - 3;
+    s.cpi = (s.total_q + s.S - 1) / s.S;
+    s.RsX = rows_x(T);
+    s.RsU = rows_u(T);
+    s.nmma1_last = s.nmma2_last = 0;
+    for (int kc = 0; kc < s.nk; ++kc)
+        for (int kk = 0; kk < 4; ++kk) {
+            s.aoff[kc * 4 + kk] = 0;
+            if (kc < s.nk1) {
+                const int k = kc * kRbBK + kk * 8;
+                if (k < K1) {
+                    const int tap = k / Cin, c0 = k % Cin;
+                    const int dh = tap / 3, dw = tap % 3;         // Keras HWIO: tap = kernel row * 3 + kernel column
+                    s.aoff[kc * 4 + kk] = static_cast<unsigned>((c0 >> 2) * s.RsX + dw * s.Fp + dh);
+                    if (kc == s.nk1 - 1) s.nmma1_last = kk + 1;
+                }
+            } else {
+                const int k = (kc - s.nk1) * kRbBK + kk * 8;
+                const int dh = k / C, c0 = k % C;
+                s.aoff[kc * 4 + kk] = static_cast<unsigned>((c0 >> 2) * s.RsU + dh);
+                if (kc == s.nk - 1) s.nmma2_last = kk + 1;
+            }
+        }
+    const size_t sb = slab_bytes(T, best_thr);
+    s.ring_off = static_cast<unsigned>((sb + 127) / 128 * 128);
+    s.par_off = s.ring_off + static_cast<unsigned>(s.stages * chunk);
+    s.bar_off = static_cast<unsigned>((s.par_off + par_bytes + 127) / 128 * 128);
+    const size_t smem = s.bar_off + kBarBytes;
+    if (getenv("MMLA_RB_VERBOSE"))
+        fprintf(stderr, "resblock2d: %dx%d Cin %d C %d: %d outputs/image, T %d, %d CTAs/image, ring %d of %d chunks, %zu KB smem, %d threads\n",
+                H, W, Cin, C, s.total_q, s.T, s.cpi, s.stages, s.nk, smem / 1024, best_thr);
+    if (g_rb_stamps && g_rb_stamp_row < 16) {
+        s.stamps = g_rb_stamps + 16 * g_rb_stamp_row++;
+        s.stamp_cta = static_cast<int>((static_cast<long long>(g_rb_stamp_cta) % B) * s.cpi + s.cpi / 2);   // a mid-image CTA
+    }
+    MMLA_REQUIRE(B * s.cpi < (1LL << 31) && B * s.img_pixels * (Cin > C ? Cin : C) < (1LL << 40), MMLA_EUNSUP,
+                 "resblock2d: batch too large");
+    if (res) {
+        switch (C) {
+            case 32: return launch_rb<32, true, 256>(s, B, smem, st);
+            case 64: return launch_rb<64, true, 256>(s, B, smem, st);
+            default: return launch_rb<128, true, 256>(s, B, smem, st);
+        }
+    }
+    if (best_thr == 256) {
+        switch (C) {
+            case 32: return launch_rb<32, false, 256>(s, B, smem, st);
+            case 64: return launch_rb<64, false, 256>(s, B, smem, st);
+            default: return launch_rb<128, false, 256>(s, B, smem, st);
+        }
+    }
+    switch (C) {
+        case 32: return launch_rb<32, false, 512>(s, B, smem, st);
+        case 64: return launch_rb<64, false, 512>(s, B, smem, st);
+        default: return launch_rb<128, false, 512>(s, B, smem, st);
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) void mmla_debug_resblock2d_stamps(long long* dev_stamps, int32_t image) {
+    g_rb_stamps = dev_stamps;
+    g_rb_stamp_cta = image;
+    g_rb_stamp_row = 0;
+}

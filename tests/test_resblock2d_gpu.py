@@ -1,0 +1,125 @@
+"""GPU parity of resblock2d_fused_kernel (csrc/resblock2d_fused.cu): both convolutions of a `res_block`
+(overlap_detector_temp.py:253-280: BN -> ELU -> Conv2D(C, 3) -> BN -> ELU -> Conv2D(C, (4, 1)) [+ x]) in ONE launch with the
+intermediate in shared memory, through the C-ABI's mmla_debug_resblock2d, against
+  * the two conv_slab_kernel launches it replaces (mmla_debug_conv2d, kernel 2): same TF32 operands, same K order, same fp32
+    epilogue expressions => BIT-IDENTICAL, and
+  * a torch float64 pair of convolutions with explicit Keras 'same' padding (k = 4: one row before, two after): TF32 operands
+    twice, so the bar is 5e-3 of the block's largest output.
+Every block shape of the overlap classifier plus ragged geometries (an image smaller than one tile, one column, H = 2).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ELU = 2
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _slab_conv(torch, lib, x, w, bias, bn, res):
+    B, H, W, Cin = x.shape
+    kh, kw, _, N = w.shape
+    y = torch.empty(B, H, W, N, device="cuda", dtype=torch.float32)
+    wh = np.ascontiguousarray(w.reshape(kh * kw * Cin, N), dtype=np.float32)
+    rc = lib.mmla_debug_conv2d(_ptr(x), wh.ctypes.data_as(C.c_void_p), _ptr(bias), _ptr(bn[0]), _ptr(bn[1]), ELU, _ptr(res), _ptr(y),
+                               B, H, W, Cin, N, kh, kw, 2, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.mmla_last_error().decode()
+    return y
+
+
+def _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res):
+    B, H, W, Cin = x.shape
+    Cc = w1.shape[3]
+    y = torch.full((B, H, W, Cc), float("nan"), device="cuda", dtype=torch.float32)
+    w1h = np.ascontiguousarray(w1.reshape(9 * Cin, Cc), dtype=np.float32)
+    w2h = np.ascontiguousarray(w2.reshape(4 * Cc, Cc), dtype=np.float32)
+    rc = lib.mmla_debug_resblock2d(_ptr(x), w1h.ctypes.data_as(C.c_void_p), _ptr(b1), _ptr(bn1[0]), _ptr(bn1[1]),
+                                   w2h.ctypes.data_as(C.c_void_p), _ptr(b2), _ptr(bn2[0]), _ptr(bn2[1]), _ptr(res), _ptr(y),
+                                   B, H, W, Cin, Cc, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.mmla_last_error().decode()
+    return y
+
+
+def _torch_ref(torch, x, w1, b1, bn1, w2, b2, bn2, res):
+    F = torch.nn.functional
+
+    def conv(a, w, bias, bn):
+        kh, kw = w.shape[0], w.shape[1]
+        a = a * bn[0].double() + bn[1].double()
+        a = torch.where(a > 0, a, torch.expm1(a)).permute(0, 3, 1, 2)
+        pt, pl = (kh - 1) // 2, (kw - 1) // 2
+        a = F.pad(a, (pl, kw - 1 - pl, pt, kh - 1 - pt))
+        y = F.conv2d(a, torch.as_tensor(w, device=a.device).double().permute(3, 2, 0, 1)) + bias.double()[None, :, None, None]
+        return y.permute(0, 2, 3, 1)
+
+    y = conv(conv(x.double(), w1, b1, bn1), w2, b2, bn2)
+    if res is not None:
+        y = y + res.double()
+    return y.float()
+
+
+BLOCKS = [  # (H, W, Cin, C, residual, B)
+    (128, 151, 16, 32, False, 2),      # block 1 (pooled: no residual here, MaxPool + shortcut follow)
+    (64, 76, 32, 32, True, 3),         # blocks 2, 3
+    (64, 76, 32, 64, False, 2),        # block 4
+    (32, 38, 64, 64, True, 5),         # blocks 5, 6
+    (32, 38, 64, 128, False, 3),       # block 7
+    (16, 19, 128, 128, True, 7),       # blocks 8, 9
+    (5, 7, 32, 32, True, 3),           # less than one tile per image
+    (9, 130, 16, 64, False, 2),
+    (37, 1, 64, 32, True, 4),          # one column
+    (2, 3, 128, 128, True, 1),
+    (128, 151, 16, 32, True, 1),       # Cin != C with a residual of C channels (generic entry)
+]
+
+
+@pytest.mark.parametrize("H,W,Cin,Cc,with_res,B", BLOCKS)
+def test_fused_block_matches_two_slab_convs_bitwise(cuda, H, W, Cin, Cc, with_res, B):
+    torch = cuda
+    from mmla_audio_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(H * 1000 + W * 10 + Cin + Cc)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    w1 = (torch.randn(3, 3, Cin, Cc, generator=g) * (2.0 / (9 * Cin)) ** 0.5).numpy()
+    w2 = (torch.randn(4, 1, Cc, Cc, generator=g) * (2.0 / (4 * Cc)) ** 0.5).numpy()
+    b1 = (torch.randn(Cc, generator=g) * 0.1).cuda()
+    b2 = (torch.randn(Cc, generator=g) * 0.1).cuda()
+    bn1 = ((torch.rand(Cin, generator=g) + 0.5).cuda(), (torch.randn(Cin, generator=g) * 0.3).cuda())
+    bn2 = ((torch.rand(Cc, generator=g) + 0.5).cuda(), (torch.randn(Cc, generator=g) * 0.3).cuda())
+    res = torch.randn(B, H, W, Cc, generator=g).cuda() if with_res else None
+    fused = _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res)
+    u = _slab_conv(torch, lib, x, w1, b1, bn1, None)
+    two = _slab_conv(torch, lib, u, w2, b2, bn2, res)
+    ref = _torch_ref(torch, x, w1, b1, bn1, w2, b2, bn2, res)
+    assert not torch.isnan(fused).any(), "an output pixel was never written"
+    scale = ref.abs().max().item()
+    d_ref = (fused - ref).abs().max().item()
+    n_diff = int((fused != two).sum().item())
+    print(f"fused vs fp64 convs {d_ref / scale:.2e} of max |y| = {scale:.2f}; elements differing from the two slab launches: {n_diff}")
+    assert n_diff == 0
+    assert d_ref <= 5e-3 * scale
+
+
+def test_block_fusion_switch_keeps_overlap_net_output_bitwise(cuda, monkeypatch):
+    """Whole overlap net, TF32 mode: MMLA_NET_FUSE_BLOCKS=0 (two conv_slab launches per block) vs the default (one
+    resblock2d_fused_kernel launch per block): identical probabilities, and the launch trace shows the fused kernel."""
+    from mmla_audio_b200 import _lib, models, weights as W
+    torch = cuda
+    spec = W.OVERLAP
+    model = models.Model(spec, W.synthetic_weights(spec, 1234), precision="tf32")
+    x = torch.randint(0, 256, (5, 128, 151, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
+    monkeypatch.setenv("MMLA_NET_FUSE_BLOCKS", "0")
+    out = {}
+    tr0 = _lib.trace_launches(lambda: out.__setitem__("two", model.predict_device(x)), torch)
+    monkeypatch.delenv("MMLA_NET_FUSE_BLOCKS")
+    tr1 = _lib.trace_launches(lambda: out.__setitem__("one", model.predict_device(x)), torch)
+    n0 = [n for n, _ in tr0]
+    n1 = [n for n, _ in tr1]
+    assert n0.count("conv_slab_kernel") == 18 and "resblock2d_fused_kernel" not in n0
+    assert n1.count("resblock2d_fused_kernel") == 9 and "conv_slab_kernel" not in n1
+    assert torch.equal(out["two"][0], out["one"][0]) and torch.equal(out["two"][1], out["one"][1])
