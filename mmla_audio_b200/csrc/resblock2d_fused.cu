@@ -227,20 +227,24 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     __syncthreads();
     if (tid == 0) stamp(3);
 
-    // Ring state of the two single-warp roles; both convolutions run through the same loop bodies.
-    int p_stg = 0, p_kc = a.stages;           // producer (warp 1): next chunk to request
-    uint32_t p_ph = 0u;
-    int m_stg = 0;                            // MMA issuer (warp 0)
+    // Ring state.  Weight producers: warps 1 .. kProducers, warp w owns chunks kc = stages + (w - 1) + i * kProducers (one
+    // thread gets one bulk copy through every ~420 cycles whatever its size, so a 16 KB chunk per 4 x 64-cycle MMAs needs
+    // more than one producer: scripts/microbench/tma_stream.cu).  MMA issuer: warp 0.
+    // (never more producers than ring slots: a producer two phases ahead of a slot's `empty` barrier would see the 1-bit
+    //  parity of the phase before last and overwrite a chunk that has not been consumed)
+    const int kProducers = a.stages < 3 ? a.stages : 3;
+    int p_kc = a.stages + (warp - 1);         // next chunk this producer warp requests
+    int m_stg = 0;
     uint32_t m_ph = 0u;
-    auto produce = [&](int kc_end) {          // chunks [p_kc, kc_end)
-        for (; p_kc < kc_end; ++p_kc) {
-            rb_wait(&empty[p_stg], p_ph);
+    auto produce = [&](int kc_end) {          // this warp's chunks below kc_end
+        for (; p_kc < kc_end; p_kc += kProducers) {
+            const int use = p_kc / a.stages, stg = p_kc - use * a.stages;
+            rb_wait(&empty[stg], static_cast<uint32_t>((use - 1) & 1));
             if (lane == 0) {
-                mbar_arrive_expect_tx(&full[p_stg], kChunkBytes);
-                tma_bulk_g2s(ring + p_stg * kChunkBytes, wsrc(p_kc), kChunkBytes, &full[p_stg]);
+                mbar_arrive_expect_tx(&full[stg], kChunkBytes);
+                tma_bulk_g2s(ring + stg * kChunkBytes, wsrc(p_kc), kChunkBytes, &full[stg]);
             }
             __syncwarp();
-            if (++p_stg == a.stages) { p_stg = 0; p_ph ^= 1u; }
         }
     };
     auto issue = [&](int kc0, int kc1, int nmma_last, uint32_t rs16) {   // chunks [kc0, kc1) of one convolution
@@ -281,8 +285,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     };
 
     // ================= conv1 =================
-    if (warp == 1) {
-        // conv2's chunks go into the slots conv1's MMAs free; the rest waits for conv2 (after epilogue 1: this warp takes part)
+    if (warp >= 1 && warp <= kProducers) {
+        // conv2's chunks go into the slots conv1's MMAs free; the rest waits for conv2 (after epilogue 1: these warps take part)
         const int lim = a.nk1 + a.stages;
         produce(a.nk < lim ? a.nk : lim);
     } else if (warp == 0) {
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     }
 
     // ================= conv2 =================
-    if (warp == 1) {
+    if (warp >= 1 && warp <= kProducers) {
         produce(a.nk);
     } else if (warp == 0) {
         issue(a.nk1, a.nk, a.nmma2_last, static_cast<uint32_t>(a.RsU) * 16u);
@@ -481,6 +485,14 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     if (const char* e = getenv("MMLA_RB_TILES")) force_t = atoi(e);
     if (const char* e = getenv("MMLA_RB_KB")) force_kb = atoi(e);
     if (const char* e = getenv("MMLA_RB_STAGES")) force_stages = atoi(e);
+    // Measured on B200 for the overlap classifier's own shapes (scripts/sweep_resblock2d.sh, profiles/r02/sweep_resblock2d_v2.txt)
+    // where the model below picks a slower configuration: the full-resolution block prefers four tiles at three CTAs per SM
+    // even with a two-slot ring (0.89 vs 1.02 ms per 512 clips), the 16 x 19 blocks prefer two tiles on one CTA per SM (half
+    // the weight stream from L2 per output: 0.30 vs 0.35 ms).
+    if (!force_t && !force_kb) {
+        if (H == 128 && Cin == 16 && C == 32) { force_t = 4; force_kb = 75; }
+        if (H == 16 && Cin == 128 && C == 128) { force_t = 2; force_kb = 226; }
+    }
     int tmax = kRbMaxTiles;
     if (tmax > 512 / C) tmax = 512 / C;
     {
