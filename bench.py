@@ -264,6 +264,7 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     h, w_ = H0, T0
     res = 0.0
     slab = 0.0                                   # overlap: the stride-1 3x3 / 4x1 convs (conv_slab_kernel)
+    slab_first = 0.0                             # ... of the first block (stem_resblock2d_fused_kernel)
     pool_bytes = 0.0                             # overlap: pool_shortcut_kernel's compulsory traffic
     res_first_stage = 0.0                        # the first three residual units (the stage the stem is folded into)
     stem = 2.0 * h * w_ * spec.stem.kh * spec.stem.kw * spec.stem.cin * spec.stem.cout
@@ -277,6 +278,8 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
             res += 2.0 * h * w_ * blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout
             slab += 2.0 * h * w_ * (blk.conv1.kh * blk.conv1.kw * blk.conv1.cin * blk.conv1.cout +
                                     blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout)
+            if bi == 0:
+                slab_first = slab
         else:                                    # speaker: MaxPool first, both convs at the pooled length
             res += 2.0 * h2 * w2 * blk.conv1.kh * blk.conv1.kw * blk.conv1.cin * blk.conv1.cout
             res += 2.0 * h2 * w2 * blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout
@@ -312,9 +315,12 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         work["conv_igemm_kernel"] = {"bound": "tensor", "per_step": conv_flop, "what": "all convolutions + LSTM input projections"}
         work["conv_slab_kernel"] = {"bound": "tensor", "per_step": B * slab,
                                     "what": "the 18 stride-1 3x3 / 4x1 convolutions of the residual blocks (TF32, tap-shifted slabs)"}
-        work["resblock2d_fused_kernel"] = {"bound": "tensor", "per_step": B * slab,
-                                           "what": "the 9 residual blocks' conv pairs (3x3 then 4x1, TF32, tap-shifted slabs, the "
-                                                   "intermediate stays in shared memory): 18 convolutions in 9 launches"}
+        work["resblock2d_fused_kernel"] = {"bound": "tensor", "per_step": B * (slab - slab_first),
+                                           "what": "residual blocks 2-9: conv pairs (3x3 then 4x1, TF32, tap-shifted slabs, the "
+                                                   "intermediate stays in shared memory): 16 convolutions in 8 launches"}
+        work["stem_resblock2d_fused_kernel"] = {"bound": "tensor", "per_step": B * (slab_first + stem),
+                                                "what": "stem Conv2D(16, 1x1) from the uint8 image + residual block 1's conv pair "
+                                                        "at 128 x 151 (TF32)"}
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (res - slab),
                                   "what": "the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
         work["pool_shortcut_kernel"] = {"bound": "hbm", "per_step": B * pool_bytes,

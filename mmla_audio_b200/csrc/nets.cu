@@ -237,11 +237,18 @@ __global__ void __launch_bounds__(256) pad_channels_kernel(const float* __restri
 // channels of one pooled pixel; the [Cin][N] shortcut weights sit in shared memory; the products are exact fp32 FMAs
 // (K = Cin <= 64 is too short for the tensor-core path to pay: the separate maxpool_kernel + im2col conv_tc_kernel pair
 // took 0.88 ms per 512 clips, this is bound by reading z once).
+// img != null (first block, stem folded into the conv-pair kernel): x is never materialised — the block input at the pooled
+// pixel is the stem Conv2D(16, 1x1) of the 3-channel image, recomputed here with stem1x1_kernel's expression (Cin = 16).
 __global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                                             const float* __restrict__ ws, const float* __restrict__ bs,
-                                                            float* __restrict__ y, long long B, int H, int W, int Cin, int N) {
-    extern __shared__ float4 wsm4[];                  // [Cin][N / 4]
+                                                            float* __restrict__ y, long long B, int H, int W, int Cin, int N,
+                                                            const void* __restrict__ img, int img_is_u8,
+                                                            const float* __restrict__ stem_w, const float* __restrict__ stem_b) {
+    extern __shared__ float4 wsm4[];                  // [Cin][N / 4] (+ stem mode: [4][16] = w0 | w1 | w2 | bias)
     for (int i = threadIdx.x; i < Cin * N / 4; i += blockDim.x) wsm4[i] = reinterpret_cast<const float4*>(ws)[i];
+    float* stem_s = reinterpret_cast<float*>(wsm4 + Cin * N / 4);
+    if (img)
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) stem_s[i] = i < 48 ? stem_w[i] : stem_b[i - 48];
     __syncthreads();
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, Q = N / 4;
     const long long total = B * Ho * Wo * Q;
@@ -268,8 +275,26 @@ __global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restr
         }
         const float* xb = x + pin * Cin;
         float4 acc = *reinterpret_cast<const float4*>(bs + 4 * q);
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (img) {
+            if (img_is_u8) {
+                const unsigned char* px = static_cast<const unsigned char*>(img) + pin * 3;
+                c0 = static_cast<float>(px[0]); c1 = static_cast<float>(px[1]); c2 = static_cast<float>(px[2]);
+            } else {
+                const float* px = static_cast<const float*>(img) + pin * 3;
+                c0 = px[0]; c1 = px[1]; c2 = px[2];
+            }
+        }
         for (int c = 0; c < Cin; c += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(xb + c);
+            float4 xv;
+            if (img) {
+                xv.x = fmaf(c2, stem_s[32 + c], fmaf(c1, stem_s[16 + c], fmaf(c0, stem_s[c], stem_s[48 + c])));
+                xv.y = fmaf(c2, stem_s[33 + c], fmaf(c1, stem_s[17 + c], fmaf(c0, stem_s[c + 1], stem_s[49 + c])));
+                xv.z = fmaf(c2, stem_s[34 + c], fmaf(c1, stem_s[18 + c], fmaf(c0, stem_s[c + 2], stem_s[50 + c])));
+                xv.w = fmaf(c2, stem_s[35 + c], fmaf(c1, stem_s[19 + c], fmaf(c0, stem_s[c + 3], stem_s[51 + c])));
+            } else {
+                xv = *reinterpret_cast<const float4*>(xb + c);
+            }
             const float4 w0v = wsm4[(c + 0) * Q + q], w1v = wsm4[(c + 1) * Q + q], w2v = wsm4[(c + 2) * Q + q], w3v = wsm4[(c + 3) * Q + q];
             acc.x = fmaf(xv.x, w0v.x, acc.x); acc.y = fmaf(xv.x, w0v.y, acc.y); acc.z = fmaf(xv.x, w0v.z, acc.z); acc.w = fmaf(xv.x, w0v.w, acc.w);
             acc.x = fmaf(xv.y, w1v.x, acc.x); acc.y = fmaf(xv.y, w1v.y, acc.y); acc.z = fmaf(xv.y, w1v.z, acc.z); acc.w = fmaf(xv.y, w1v.w, acc.w);
@@ -511,7 +536,8 @@ bool mmla_resblock2d_eligible(int H, int W, int Cin, int C, int kh1, int kw1, in
 int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, int W, int Cin, int C, const float* bn1_scale,
                                  const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
-                                 long long res_row_stride, cudaStream_t st);
+                                 long long res_row_stride, cudaStream_t st, const void* img = nullptr, int img_is_u8 = 0,
+                                 const float* stem_w = nullptr, const float* stem_b = nullptr);
 // lstm_fused.cu
 long long mmla_xproj_arranged_floats();
 void mmla_xproj_arrange_weights(const float* W, float* out);
@@ -827,6 +853,19 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         int cur = 0;
         int rc;
         bool seq_done = false;
+        bool stem_folded = false;
+        const int act_kind = ov ? ACT_ELU : ACT_RELU;
+        auto pair_fusable = [&](const BlockW& k, int h, int w) {
+            return k.conv1.k_tc && k.conv2.k_tc && k.conv1.stride == 1 && k.conv2.stride == 1 && k.conv2.cin == k.conv1.cout &&
+                   k.conv2.cout == k.conv1.cout && k.bn1.scale && k.bn2.scale &&
+                   mmla_resblock2d_eligible(h, w, k.conv1.cin, k.conv1.cout, k.conv1.kh, k.conv1.kw, k.conv2.kh, k.conv2.kw, act_kind);
+        };
+        auto pool_fusable = [&](const BlockW& k) {
+            const char* fp = getenv("MMLA_NET_FUSE_POOL");
+            return k.pool && !(fp && fp[0] == '0') && k.shortcut.kh == 1 && k.shortcut.kw == 1 && k.shortcut.stride == 2 &&
+                   k.shortcut.cin % 4 == 0 && k.conv2.cout % 4 == 0 &&
+                   static_cast<size_t>(k.shortcut.cin) * k.conv2.cout * sizeof(float) <= 48 * 1024;
+        };
         // label pipeline: the stem runs inside the first stage's kernel (resstage_fused.cu, STEM variant)
         auto unit_tc = [&](const BlockW& k) { return k.conv1.k_tc && k.conv2.k_tc && (!k.pool || k.shortcut.k_tc); };
         const bool stem_in_stage = from_cep && tc && !ov && net->fuse_stages && net->fuse_stem && net->stem_pad.k_tc &&
@@ -853,7 +892,14 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
             return MMLA_EUNSUP;
         } else if (ov && tc && net->stem.kh == 1 && net->stem.kw == 1 && net->stem.cin == 3 && net->stem.cout == 16) {
             const long long pixels = B * H * W;
-            if (pixels > 0) {
+            // first block eligible: the stem runs inside its conv-pair kernel and inside its pooling kernel (resblock2d_fused.cu,
+            // STEM mode) and the [B,128,151,16] stem tensor is never materialised (MMLA_NET_FUSE_STEM2D=0: own launch)
+            {
+                const char* e = getenv("MMLA_NET_FUSE_STEM2D");
+                stem_folded = !(e && e[0] == '0') && !net->blocks.empty() && net->blocks[0].conv1.cin == 16 &&
+                              net->blocks[0].conv1.cout == 32 && pair_fusable(net->blocks[0], H, W) && pool_fusable(net->blocks[0]);
+            }
+            if (pixels > 0 && !stem_folded) {
                 stem1x1_kernel<<<ew_grid(pixels * 4), 256, 0, st>>>(xin, x_is_u8, net->stem.k, net->stem.b, buf[cur], pixels);
                 mmla_count_launch("stem1x1_kernel", st);
                 MMLA_CUDA_CHECK(cudaGetLastError());
@@ -863,18 +909,12 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
             rc = launch_conv(net->stem, xin, x_is_u8, B, H, W, nullptr, ACT_NONE, nullptr, 0, buf[cur], st, tc);
         }
         if (rc) return rc;
-        const int act_kind = ov ? ACT_ELU : ACT_RELU;
         for (size_t bi = 0; bi < net->blocks.size(); ++bi) {
             const BlockW& blk = net->blocks[bi];
             float* X = buf[cur];
             float* A = buf[(cur + 1) % 3];
             float* Bf = buf[(cur + 2) % 3];
             auto fusable = [&](const BlockW& k) { return k.conv1.k_tc && k.conv2.k_tc && (!k.pool || k.shortcut.k_tc); };
-            auto pair_fusable = [&](const BlockW& k, int h, int w) {
-                return k.conv1.k_tc && k.conv2.k_tc && k.conv1.stride == 1 && k.conv2.stride == 1 && k.conv2.cin == k.conv1.cout &&
-                       k.conv2.cout == k.conv1.cout && k.bn1.scale && k.bn2.scale &&
-                       mmla_resblock2d_eligible(h, w, k.conv1.cin, k.conv1.cout, k.conv1.kh, k.conv1.kw, k.conv2.kh, k.conv2.kw, act_kind);
-            };
             if (tc && !ov && net->fuse_stages && blk.pool && bi + 2 < net->blocks.size() && fusable(blk) &&
                 fusable(net->blocks[bi + 1]) && fusable(net->blocks[bi + 2]) && !net->blocks[bi + 1].pool &&
                 !net->blocks[bi + 2].pool && net->blocks[bi + 1].conv1.cin == blk.conv1.cout &&
@@ -930,23 +970,24 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 cur = (cur + 2) % 3;
             } else if (ov) {
                 // full-resolution convs, MaxPool2x2 'same', then shortcut conv (stride 2) + pooled
+                const bool fold = stem_folded && bi == 0;
                 if (tc && pair_fusable(blk, H, W)) {
                     if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
                                                            blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
-                                                           blk.conv2.b, nullptr, 0, st)))
+                                                           blk.conv2.b, nullptr, 0, st, fold ? xin : nullptr, x_is_u8,
+                                                           fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr)))
                         return rc;
                 } else {
                     if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
                     if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, nullptr, 0, Bf, st, tc))) return rc;
                 }
                 const int Ho = same_out(H, 2), Wo = same_out(W, 2), C = blk.conv2.cout;
-                const char* fp = getenv("MMLA_NET_FUSE_POOL");
-                const size_t wbytes = static_cast<size_t>(blk.shortcut.cin) * C * sizeof(float);
-                if (tc && !(fp && fp[0] == '0') && blk.shortcut.kh == 1 && blk.shortcut.kw == 1 && blk.shortcut.stride == 2 &&
-                    blk.shortcut.cin % 4 == 0 && C % 4 == 0 && wbytes <= 48 * 1024) {
+                const size_t wbytes = static_cast<size_t>(blk.shortcut.cin) * C * sizeof(float) + 256;
+                if (tc && pool_fusable(blk)) {
                     // MaxPool + stride-2 shortcut + add in one pass (reads X and Bf, writes A)
-                    pool_shortcut_kernel<<<ew_grid(B * Ho * Wo * C / 4), 256, wbytes, st>>>(X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W,
-                                                                                          blk.shortcut.cin, C);
+                    pool_shortcut_kernel<<<ew_grid(B * Ho * Wo * C / 4), 256, wbytes, st>>>(
+                        X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W, blk.shortcut.cin, C, fold ? xin : nullptr, x_is_u8,
+                        fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr);
                     mmla_count_launch("pool_shortcut_kernel", st);
                     MMLA_CUDA_CHECK(cudaGetLastError());
                     H = Ho; W = Wo;

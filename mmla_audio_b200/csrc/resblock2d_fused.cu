@@ -46,6 +46,10 @@ struct RbArgs {
     const float* bn2_shift;
     const float* res;
     float* y;
+    const void* img;          // STEM: the classifier input [B,H,W,3] (uint8 or float32); x is unused
+    const float* stem_w;      // STEM: Conv2D(16, 1x1) weights [3][16] and bias [16] (overlap_detector_temp.py:283)
+    const float* stem_b;
+    int img_is_u8;
     long long res_row_stride;
     long long img_pixels;     // H * W
     int H, W, Fp;
@@ -101,7 +105,9 @@ __device__ __forceinline__ void rb_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int NT, bool RES, int THREADS>
+// STEM: the block's input is the net's stem Conv2D(16, 1x1) of the 3-channel classifier image, computed in the fill from the
+// image bytes (the expression of stem1x1_kernel, csrc/nets.cu): the [B,128,151,16] stem tensor is never written or read.
+template <int NT, bool RES, int THREADS, bool STEM = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resblock2d_fused_kernel(const RbArgs a) {
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
@@ -164,6 +170,53 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
         }
     }
 
+    if constexpr (STEM) {
+        // ---- x slab fill from the image: 3 values per pixel -> 16 stem channels -> BN1 + ELU + TF32, one pass, no staging ----
+        const int rows = Tc * 128 + 2 * a.Fp + 2;
+        const int c4 = lane >> 3;                             // Cin = 16: four quads, eight rows per warp instruction
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bn1_scale) + c4);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.bn1_shift) + c4);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.stem_w) + c4);
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.stem_w + 16) + c4);
+        const float4 w2 = __ldg(reinterpret_cast<const float4*>(a.stem_w + 32) + c4);
+        const float4 sb = __ldg(reinterpret_cast<const float4*>(a.stem_b) + c4);
+        const unsigned char* img8 = static_cast<const unsigned char*>(a.img) + static_cast<long long>(img) * a.img_pixels * 3;
+        const float* imgf = static_cast<const float*>(a.img) + static_cast<long long>(img) * a.img_pixels * 3;
+        unsigned char* dst0 = slab + static_cast<size_t>(c4) * a.RsX * 16;
+        // four rows per iteration: all twelve pixel loads first, then the arithmetic (one row at a time the loop waited a
+        // memory round trip per row: 13.5 k cycles per CTA against 9.4 k for the cp.async fill of the materialised tensor)
+        for (int r0 = warp * 8 + (lane & 7); r0 < rows; r0 += 4 * kWarps * 8) {
+            float c[4][3];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * kWarps * 8;
+                const int p = Qc - 1 + r;
+                const int wp = static_cast<int>(__umulhi(static_cast<unsigned>(p < 0 ? 0 : p), a.fp_magic));
+                const int w = wp - 1, h = p - wp * a.Fp - 1;
+                ok[u] = r < rows && p >= 0 && w >= 0 && w < a.W && h >= 0 && h < a.H;
+                const long long px = ok[u] ? static_cast<long long>(h * a.W + w) * 3 : 0ll;
+                if (a.img_is_u8) {
+                    c[u][0] = static_cast<float>(img8[px]); c[u][1] = static_cast<float>(img8[px + 1]); c[u][2] = static_cast<float>(img8[px + 2]);
+                } else {
+                    c[u][0] = imgf[px]; c[u][1] = imgf[px + 1]; c[u][2] = imgf[px + 2];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * kWarps * 8;
+                if (r < rows) {
+                    const uint32_t keep = ok[u] ? 0xFFFFFFFFu : 0u;
+                    const float c0 = c[u][0], c1 = c[u][1], c2 = c[u][2];
+                    *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(r) * 16) = make_uint4(
+                        rb_bn_elu_tf32(fmaf(c2, w2.x, fmaf(c1, w1.x, fmaf(c0, w0.x, sb.x))), sc.x, sh.x) & keep,
+                        rb_bn_elu_tf32(fmaf(c2, w2.y, fmaf(c1, w1.y, fmaf(c0, w0.y, sb.y))), sc.y, sh.y) & keep,
+                        rb_bn_elu_tf32(fmaf(c2, w2.z, fmaf(c1, w1.z, fmaf(c0, w0.z, sb.z))), sc.z, sh.z) & keep,
+                        rb_bn_elu_tf32(fmaf(c2, w2.w, fmaf(c1, w1.w, fmaf(c0, w0.w, sb.w))), sc.w, sh.w) & keep);
+                }
+            }
+        }
+    } else
     // ---- x slab fill: row r <-> padded flat index Qc - 1 + r; BN1 + ELU + TF32 once per element (conv_slab.cu's fill) ----
     {
         const int rows = Tc * 128 + 2 * a.Fp + 2;
@@ -412,19 +465,19 @@ int rb_ilog2(int v) {
 long long* g_rb_stamps = nullptr;         // mmla_debug_resblock2d_stamps: 16 rows (launch ordinal) x 16 slots
 int g_rb_stamp_cta = 0, g_rb_stamp_row = 0;
 
-template <int NT, bool RES, int THREADS>
+template <int NT, bool RES, int THREADS, bool STEM = false>
 int launch_rb(const RbArgs& s, long long images, size_t smem, cudaStream_t st) {
     static size_t attr[64] = {};                                  // per device: function attributes are per device
     int dev = 0;
     MMLA_CUDA_CHECK(cudaGetDevice(&dev));
     MMLA_REQUIRE(dev >= 0 && dev < 64, MMLA_EUNSUP, "resblock2d: device ordinal %d out of range", dev);
     if (smem > attr[dev]) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resblock2d_fused_kernel<NT, RES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resblock2d_fused_kernel<NT, RES, THREADS, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
         attr[dev] = smem;
     }
-    resblock2d_fused_kernel<NT, RES, THREADS><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
-    mmla_count_launch("resblock2d_fused_kernel", st);
+    resblock2d_fused_kernel<NT, RES, THREADS, STEM><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
+    mmla_count_launch(STEM ? "stem_resblock2d_fused_kernel" : "resblock2d_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }
@@ -444,17 +497,22 @@ bool mmla_resblock2d_eligible(int H, int W, int Cin, int C, int kh1, int kw1, in
     return true;
 }
 
+// img != null: stem mode — x is ignored, the block input is Conv2D(16, 1x1)(img) computed in the fill (Cin must be 16, no
+// residual, 256-thread configuration).
 int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, int W, int Cin, int C, const float* bn1_scale,
                                  const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
-                                 long long res_row_stride, cudaStream_t st) {
+                                 long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8, const float* stem_w,
+                                 const float* stem_b) {
     if (B <= 0) return MMLA_OK;
+    MMLA_REQUIRE(!img || (Cin == 16 && C == 32 && !res && stem_w && stem_b), MMLA_EUNSUP, "resblock2d: stem mode needs Cin 16, C 32, no residual");
     MMLA_REQUIRE(!res || res_row_stride % 4 == 0, MMLA_EUNSUP, "resblock2d: residual row stride must be a multiple of 4 floats");
     RbArgs s;
     memset(&s, 0, sizeof(s));
     s.x = x; s.y = y; s.w1 = w1; s.w2 = w2; s.b1 = b1; s.b2 = b2;
     s.bn1_scale = bn1_scale; s.bn1_shift = bn1_shift; s.bn2_scale = bn2_scale; s.bn2_shift = bn2_shift;
     s.res = res; s.res_row_stride = res_row_stride;
+    s.img = img; s.img_is_u8 = img_is_u8; s.stem_w = stem_w; s.stem_b = stem_b;
     s.img_pixels = static_cast<long long>(H) * W;
     s.H = H; s.W = W; s.Fp = H + 3;
     s.fp_magic = static_cast<unsigned>((1ULL << 32) / static_cast<unsigned>(s.Fp)) + 1u;
@@ -506,7 +564,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
         const int budgets_kb[3] = {75, 113, 226};
         const double overlap[3] = {4.5, 3.2, 1.0};
         for (int bi = res ? 1 : 0; bi < 3; ++bi) {
-            const int nthr = res || bi == 0 ? 256 : 512;
+            const int nthr = res || img || bi == 0 ? 256 : 512;
             const int ctas = 3 - bi;
             const size_t budget = static_cast<size_t>(force_kb >= 16 && force_kb <= 226 ? force_kb : budgets_kb[bi]) * 1024;
             for (int t = 1; t <= tmax; ++t) {
@@ -580,6 +638,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
             default: return launch_rb<128, true, 256>(s, B, smem, st);
         }
     }
+    if (img) return launch_rb<32, false, 256, true>(s, B, smem, st);
     if (best_thr == 256) {
         switch (C) {
             case 32: return launch_rb<32, false, 256>(s, B, smem, st);

@@ -19,13 +19,13 @@ for _ in range(reps):
     tr = _lib.trace_launches(lambda: pipe.run_device(pcm), torch)
     i = 0
     for n, ms in tr:
-        if n in ("resblock2d_fused_kernel", "conv_slab_kernel", "pool_shortcut_kernel"):
+        if n in ("resblock2d_fused_kernel", "stem_resblock2d_fused_kernel", "conv_slab_kernel", "pool_shortcut_kernel", "stem1x1_kernel"):
             acc[(i, n)] = acc.get((i, n), 0.0) + ms / reps
             i += 1
 tot = {}
 for (i, n), ms in sorted(acc.items()):
     tot[n] = tot.get(n, 0.0) + ms
-print(" ".join(f"{ms:.4f}" for (_, n), ms in sorted(acc.items()) if n != "pool_shortcut_kernel"))
+print(" ".join(f"{ms:.4f}" for (_, n), ms in sorted(acc.items()) if n not in ("pool_shortcut_kernel", "stem1x1_kernel")))
 print("totals:", {k: round(v, 4) for k, v in tot.items()}, "step", round(sum(ms for _, ms in tr), 4))
 if os.environ.get("STAMPS", "1") != "0":
     stamps = torch.zeros(16 * 16, dtype=torch.int64, device="cuda")

@@ -105,21 +105,29 @@ def test_fused_block_matches_two_slab_convs_bitwise(cuda, H, W, Cin, Cc, with_re
     assert d_ref <= 5e-3 * scale
 
 
-def test_block_fusion_switch_keeps_overlap_net_output_bitwise(cuda, monkeypatch):
-    """Whole overlap net, TF32 mode: MMLA_NET_FUSE_BLOCKS=0 (two conv_slab launches per block) vs the default (one
-    resblock2d_fused_kernel launch per block): identical probabilities, and the launch trace shows the fused kernel."""
+def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch):
+    """Whole overlap net, TF32 mode, uint8 and float32 images: MMLA_NET_FUSE_BLOCKS=0 (two conv_slab launches per block) vs
+    MMLA_NET_FUSE_STEM2D=0 (one resblock2d_fused_kernel launch per block, stem1x1_kernel on its own) vs the default (the stem
+    Conv2D(16, 1x1) also computed inside the first block's conv-pair and pooling kernels): identical probabilities, and the
+    launch traces show which kernels ran."""
     from mmla_audio_b200 import _lib, models, weights as W
     torch = cuda
     spec = W.OVERLAP
     model = models.Model(spec, W.synthetic_weights(spec, 1234), precision="tf32")
-    x = torch.randint(0, 256, (5, 128, 151, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
-    monkeypatch.setenv("MMLA_NET_FUSE_BLOCKS", "0")
-    out = {}
-    tr0 = _lib.trace_launches(lambda: out.__setitem__("two", model.predict_device(x)), torch)
-    monkeypatch.delenv("MMLA_NET_FUSE_BLOCKS")
-    tr1 = _lib.trace_launches(lambda: out.__setitem__("one", model.predict_device(x)), torch)
-    n0 = [n for n, _ in tr0]
-    n1 = [n for n, _ in tr1]
-    assert n0.count("conv_slab_kernel") == 18 and "resblock2d_fused_kernel" not in n0
-    assert n1.count("resblock2d_fused_kernel") == 9 and "conv_slab_kernel" not in n1
-    assert torch.equal(out["two"][0], out["one"][0]) and torch.equal(out["two"][1], out["one"][1])
+    x8 = torch.randint(0, 256, (5, 128, 151, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
+    for x in (x8, x8.float() * 0.37 - 20.0):
+        out, names = {}, {}
+        for mode, env in (("two", {"MMLA_NET_FUSE_BLOCKS": "0"}), ("one", {"MMLA_NET_FUSE_STEM2D": "0"}), ("stem", {})):
+            for k in ("MMLA_NET_FUSE_BLOCKS", "MMLA_NET_FUSE_STEM2D"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            tr = _lib.trace_launches(lambda: out.__setitem__(mode, model.predict_device(x)), torch)
+            names[mode] = [n for n, _ in tr]
+        assert names["two"].count("conv_slab_kernel") == 18 and "resblock2d_fused_kernel" not in names["two"]
+        assert names["one"].count("resblock2d_fused_kernel") == 9 and "conv_slab_kernel" not in names["one"]
+        assert names["one"].count("stem1x1_kernel") == 1 and names["two"].count("stem1x1_kernel") == 1
+        assert names["stem"].count("resblock2d_fused_kernel") == 8 and names["stem"].count("stem_resblock2d_fused_kernel") == 1
+        assert "stem1x1_kernel" not in names["stem"]
+        for mode in ("one", "stem"):
+            assert torch.equal(out["two"][0], out[mode][0]) and torch.equal(out["two"][1], out[mode][1]), mode
