@@ -143,19 +143,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
         mbar_init(accum, 1);
         mbar_fence_init();
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    // The barrier initialisation is all the weight prefetch and the fill need; the TMEM allocation (which can wait for a
+    // co-resident CTA's columns) and the epilogue parameters land behind the fill, before the barrier that ends it.
+    float pv[(3 * NT + THREADS - 1) / THREADS];
+#pragma unroll
+    for (int i = 0; i < (3 * NT + THREADS - 1) / THREADS; ++i) {
+        const int e = tid + i * THREADS;
+        pv[i] = 0.f;
+        if (e < 3 * NT) pv[i] = __ldg((e < NT ? a.b1 : e < 2 * NT ? a.bn2_scale : a.bn2_shift) + (e % NT));
     }
-    for (int i = tid; i < 3 * NT; i += THREADS) {
-        const int c = i % NT, which = i / NT;
-        par[i] = __ldg((which == 0 ? a.b1 : which == 1 ? a.bn2_scale : a.bn2_shift) + c);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *tmem_slot;
     if (tid == 0) stamp(1);
 
     auto wsrc = [&](int kc) {
@@ -276,8 +273,19 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
         for (int jt = it >= 4 * kAhead ? it - 4 * kAhead : 0; jt < it; jt += 4) xform_batch(jt);
     }
     if (tid == 0) stamp(2);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < (3 * NT + THREADS - 1) / THREADS; ++i)
+        if (tid + i * THREADS < 3 * NT) par[tid + i * THREADS] = pv[i];
     fence_proxy_async_smem();                // generic-proxy slab writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
     if (tid == 0) stamp(3);
 
     // Ring state.  Weight producers: warps 1 .. kProducers, warp w owns chunks kc = stages + (w - 1) + i * kProducers (one
