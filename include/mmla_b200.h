@@ -82,10 +82,12 @@ int mmla_debug_conv2d(const float* x, const float* w_host, const float* bias, co
 /* One res_block conv pair of the overlap classifier (overlap_detector_temp.py:253-280) through resblock2d_fused_kernel:
  *   y[B,H,W,C] = Conv2D(C,(4,1),'same')(ELU(BN2(Conv2D(C,3,'same')(ELU(BN1(x)))))) (+ res), x [B,H,W,Cin] float32 NHWC (DEVICE),
  *   w1_host [9*Cin][C], w2_host [4*C][C] (HOST, Keras HWIO flattened), b1 / b2 / folded BN scale+shift / res / y DEVICE pointers
- *   (res = NULL: no residual; rows of C floats otherwise).  MMLA_EUNSUP if the block is not eligible.  Synchronous on `stream`. */
+ *   (res = NULL: no residual; rows of C floats otherwise).  hpool = 1 (pooled blocks: even H, no residual): y is [B,H/2,W,C],
+ *   the maximum over the row pairs (2i, 2i+1) of the block output, taken in the kernel's epilogue.
+ *   MMLA_EUNSUP if the block is not eligible.  Synchronous on `stream`. */
 int mmla_debug_resblock2d(const float* x, const float* w1_host, const float* b1, const float* bn1_scale, const float* bn1_shift,
                           const float* w2_host, const float* b2, const float* bn2_scale, const float* bn2_shift, const float* res,
-                          float* y, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t C, void* stream);
+                          float* y, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t C, int32_t hpool, void* stream);
 /* clock64 timeline of resblock2d_fused_kernel: dev_stamps (DEVICE pointer, 16 x 16 int64, NULL = off) receives, for each of the
  * next 16 launches, the stamps of a mid-image CTA of image `image`: 0 start, 1 set-up done, 2 x slab written, 3 slab barrier,
  * 4 conv1 issued, 5 conv1 accumulators complete, 6 u slab written, 7 conv2 issued, 8 conv2 accumulators complete,

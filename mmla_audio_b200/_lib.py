@@ -81,7 +81,7 @@ def load() -> C.CDLL:
         "mmla_debug_lstm_stamps": (None, [vp, i32]),
         "mmla_debug_conv_slab_stamps": (None, [vp, i32]),
         "mmla_debug_conv2d": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
-        "mmla_debug_resblock2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "mmla_debug_resblock2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
         "mmla_debug_resblock2d_stamps": (None, [vp, i32]),
         "mmla_trace_begin": (C.c_int, [vp]),
         "mmla_trace_end": (C.c_int, [vp, i64, vp, i32]),

@@ -243,65 +243,90 @@ __global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restr
                                                             const float* __restrict__ ws, const float* __restrict__ bs,
                                                             float* __restrict__ y, long long B, int H, int W, int Cin, int N,
                                                             const void* __restrict__ img, int img_is_u8,
-                                                            const float* __restrict__ stem_w, const float* __restrict__ stem_b) {
+                                                            const float* __restrict__ stem_w, const float* __restrict__ stem_b,
+                                                            int z_half) {
     extern __shared__ float4 wsm4[];                  // [Cin][N / 4] (+ stem mode: [4][16] = w0 | w1 | w2 | bias)
     for (int i = threadIdx.x; i < Cin * N / 4; i += blockDim.x) wsm4[i] = reinterpret_cast<const float4*>(ws)[i];
     float* stem_s = reinterpret_cast<float*>(wsm4 + Cin * N / 4);
     if (img)
         for (int i = threadIdx.x; i < 64; i += blockDim.x) stem_s[i] = i < 48 ? stem_w[i] : stem_b[i - 48];
     __syncthreads();
-    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, Q = N / 4;
-    const long long total = B * Ho * Wo * Q;
+    // One thread owns four output channels of kPix consecutive pooled pixels of a row: every shortcut weight read from shared
+    // memory feeds kPix FMAs (with one pixel per thread the kernel was bound by its LDS.128 stream, one per four FMAs:
+    // ~0.14 ms of each launch's 0.22-0.37 ms per 512 clips).  The FMA order per output is unchanged (c ascending).
+    constexpr int kPix = 4;
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, Q = N / 4, G = (Wo + kPix - 1) / kPix;
+    const long long total = B * Ho * G * Q;
     for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int q = static_cast<int>(idx % Q);
-        const long long p = idx / Q;
-        const int wo = static_cast<int>(p % Wo);
-        const long long t = p / Wo;
+        const long long pg = idx / Q;
+        const int g = static_cast<int>(pg % G);
+        const long long t = pg / G;
         const int ho = static_cast<int>(t % Ho);
         const long long b = t / Ho;
-        const int h0 = 2 * ho, w0 = 2 * wo;
-        const long long pin = (b * H + h0) * W + w0;
-        const float* zb = z + pin * N + 4 * q;
-        float4 m = *reinterpret_cast<const float4*>(zb);
-        auto mx = [&](const float* ptr) {
-            const float4 v = *reinterpret_cast<const float4*>(ptr);
-            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-        };
-        if (w0 + 1 < W) mx(zb + N);                    // 'same' pooling: the missing right / bottom neighbours are -inf
-        if (h0 + 1 < H) {
-            mx(zb + static_cast<long long>(W) * N);
-            if (w0 + 1 < W) mx(zb + static_cast<long long>(W) * N + N);
-        }
-        const float* xb = x + pin * Cin;
-        float4 acc = *reinterpret_cast<const float4*>(bs + 4 * q);
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        if (img) {
-            if (img_is_u8) {
-                const unsigned char* px = static_cast<const unsigned char*>(img) + pin * 3;
-                c0 = static_cast<float>(px[0]); c1 = static_cast<float>(px[1]); c2 = static_cast<float>(px[2]);
-            } else {
-                const float* px = static_cast<const float*>(img) + pin * 3;
-                c0 = px[0]; c1 = px[1]; c2 = px[2];
+        const int h0 = 2 * ho;
+        float4 m[kPix], acc[kPix];
+        float c0[kPix], c1[kPix], c2[kPix];
+        const float* xb[kPix];
+        const float4 bias = *reinterpret_cast<const float4*>(bs + 4 * q);
+#pragma unroll
+        for (int u = 0; u < kPix; ++u) {
+            const int wo = min(kPix * g + u, Wo - 1);  // the tail group recomputes the row's last pixel (not stored)
+            const int w0 = 2 * wo;
+            const long long pin = (b * H + h0) * W + w0;
+            // z_half: z = [B, H/2, W, N] already holds the maximum over each window's two rows (resblock2d_fused.cu, HPOOL)
+            const float* zb = z + (z_half ? ((b * Ho + ho) * W + w0) : pin) * N + 4 * q;
+            m[u] = *reinterpret_cast<const float4*>(zb);
+            auto mx = [&](const float* ptr) {
+                const float4 v = *reinterpret_cast<const float4*>(ptr);
+                m[u].x = fmaxf(m[u].x, v.x); m[u].y = fmaxf(m[u].y, v.y); m[u].z = fmaxf(m[u].z, v.z); m[u].w = fmaxf(m[u].w, v.w);
+            };
+            if (w0 + 1 < W) mx(zb + N);                // 'same' pooling: the missing right / bottom neighbours are -inf
+            if (!z_half && h0 + 1 < H) {
+                mx(zb + static_cast<long long>(W) * N);
+                if (w0 + 1 < W) mx(zb + static_cast<long long>(W) * N + N);
+            }
+            xb[u] = x + pin * Cin;
+            acc[u] = bias;
+            c0[u] = c1[u] = c2[u] = 0.f;
+            if (img) {
+                if (img_is_u8) {
+                    const unsigned char* px = static_cast<const unsigned char*>(img) + pin * 3;
+                    c0[u] = static_cast<float>(px[0]); c1[u] = static_cast<float>(px[1]); c2[u] = static_cast<float>(px[2]);
+                } else {
+                    const float* px = static_cast<const float*>(img) + pin * 3;
+                    c0[u] = px[0]; c1[u] = px[1]; c2[u] = px[2];
+                }
             }
         }
         for (int c = 0; c < Cin; c += 4) {
-            float4 xv;
-            if (img) {
-                xv.x = fmaf(c2, stem_s[32 + c], fmaf(c1, stem_s[16 + c], fmaf(c0, stem_s[c], stem_s[48 + c])));
-                xv.y = fmaf(c2, stem_s[33 + c], fmaf(c1, stem_s[17 + c], fmaf(c0, stem_s[c + 1], stem_s[49 + c])));
-                xv.z = fmaf(c2, stem_s[34 + c], fmaf(c1, stem_s[18 + c], fmaf(c0, stem_s[c + 2], stem_s[50 + c])));
-                xv.w = fmaf(c2, stem_s[35 + c], fmaf(c1, stem_s[19 + c], fmaf(c0, stem_s[c + 3], stem_s[51 + c])));
-            } else {
-                xv = *reinterpret_cast<const float4*>(xb + c);
-            }
             const float4 w0v = wsm4[(c + 0) * Q + q], w1v = wsm4[(c + 1) * Q + q], w2v = wsm4[(c + 2) * Q + q], w3v = wsm4[(c + 3) * Q + q];
-            acc.x = fmaf(xv.x, w0v.x, acc.x); acc.y = fmaf(xv.x, w0v.y, acc.y); acc.z = fmaf(xv.x, w0v.z, acc.z); acc.w = fmaf(xv.x, w0v.w, acc.w);
-            acc.x = fmaf(xv.y, w1v.x, acc.x); acc.y = fmaf(xv.y, w1v.y, acc.y); acc.z = fmaf(xv.y, w1v.z, acc.z); acc.w = fmaf(xv.y, w1v.w, acc.w);
-            acc.x = fmaf(xv.z, w2v.x, acc.x); acc.y = fmaf(xv.z, w2v.y, acc.y); acc.z = fmaf(xv.z, w2v.z, acc.z); acc.w = fmaf(xv.z, w2v.w, acc.w);
-            acc.x = fmaf(xv.w, w3v.x, acc.x); acc.y = fmaf(xv.w, w3v.y, acc.y); acc.z = fmaf(xv.w, w3v.z, acc.z); acc.w = fmaf(xv.w, w3v.w, acc.w);
+#pragma unroll
+            for (int u = 0; u < kPix; ++u) {
+                float4 xv;
+                if (img) {
+                    xv.x = fmaf(c2[u], stem_s[32 + c], fmaf(c1[u], stem_s[16 + c], fmaf(c0[u], stem_s[c], stem_s[48 + c])));
+                    xv.y = fmaf(c2[u], stem_s[33 + c], fmaf(c1[u], stem_s[17 + c], fmaf(c0[u], stem_s[c + 1], stem_s[49 + c])));
+                    xv.z = fmaf(c2[u], stem_s[34 + c], fmaf(c1[u], stem_s[18 + c], fmaf(c0[u], stem_s[c + 2], stem_s[50 + c])));
+                    xv.w = fmaf(c2[u], stem_s[35 + c], fmaf(c1[u], stem_s[19 + c], fmaf(c0[u], stem_s[c + 3], stem_s[51 + c])));
+                } else {
+                    xv = *reinterpret_cast<const float4*>(xb[u] + c);
+                }
+                float4& a = acc[u];
+                a.x = fmaf(xv.x, w0v.x, a.x); a.y = fmaf(xv.x, w0v.y, a.y); a.z = fmaf(xv.x, w0v.z, a.z); a.w = fmaf(xv.x, w0v.w, a.w);
+                a.x = fmaf(xv.y, w1v.x, a.x); a.y = fmaf(xv.y, w1v.y, a.y); a.z = fmaf(xv.y, w1v.z, a.z); a.w = fmaf(xv.y, w1v.w, a.w);
+                a.x = fmaf(xv.z, w2v.x, a.x); a.y = fmaf(xv.z, w2v.y, a.y); a.z = fmaf(xv.z, w2v.z, a.z); a.w = fmaf(xv.z, w2v.w, a.w);
+                a.x = fmaf(xv.w, w3v.x, a.x); a.y = fmaf(xv.w, w3v.y, a.y); a.z = fmaf(xv.w, w3v.z, a.z); a.w = fmaf(xv.w, w3v.w, a.w);
+            }
         }
-        *reinterpret_cast<float4*>(y + p * N + 4 * q) = make_float4(m.x + acc.x, m.y + acc.y, m.z + acc.z, m.w + acc.w);
+#pragma unroll
+        for (int u = 0; u < kPix; ++u) {
+            const int wo = kPix * g + u;
+            if (wo < Wo)
+                *reinterpret_cast<float4*>(y + ((b * Ho + ho) * Wo + wo) * N + 4 * q) =
+                    make_float4(m[u].x + acc[u].x, m[u].y + acc[u].y, m[u].z + acc[u].z, m[u].w + acc[u].w);
+        }
     }
 }
 
@@ -537,7 +562,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                  long long res_row_stride, cudaStream_t st, const void* img = nullptr, int img_is_u8 = 0,
-                                 const float* stem_w = nullptr, const float* stem_b = nullptr);
+                                 const float* stem_w = nullptr, const float* stem_b = nullptr, int hpool = 0);
 // lstm_fused.cu
 long long mmla_xproj_arranged_floats();
 void mmla_xproj_arrange_weights(const float* W, float* out);
@@ -971,11 +996,18 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
             } else if (ov) {
                 // full-resolution convs, MaxPool2x2 'same', then shortcut conv (stride 2) + pooled
                 const bool fold = stem_folded && bi == 0;
+                // the maximum over each pooling window's two rows is taken in the conv-pair kernel's epilogue (HPOOL): Bf is then
+                // [B, H/2, W, C] and the pooling kernel reads half as much (MMLA_NET_FUSE_HPOOL=0: full-resolution Bf)
+                bool hpool = false;
+                if (tc && pair_fusable(blk, H, W) && pool_fusable(blk) && H % 2 == 0) {
+                    const char* e = getenv("MMLA_NET_FUSE_HPOOL");
+                    hpool = !(e && e[0] == '0');
+                }
                 if (tc && pair_fusable(blk, H, W)) {
                     if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
                                                            blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
                                                            blk.conv2.b, nullptr, 0, st, fold ? xin : nullptr, x_is_u8,
-                                                           fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr)))
+                                                           fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0)))
                         return rc;
                 } else {
                     if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
@@ -985,9 +1017,9 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 const size_t wbytes = static_cast<size_t>(blk.shortcut.cin) * C * sizeof(float) + 256;
                 if (tc && pool_fusable(blk)) {
                     // MaxPool + stride-2 shortcut + add in one pass (reads X and Bf, writes A)
-                    pool_shortcut_kernel<<<ew_grid(B * Ho * Wo * C / 4), 256, wbytes, st>>>(
+                    pool_shortcut_kernel<<<ew_grid(B * Ho * ((Wo + 3) / 4) * C / 4), 256, wbytes, st>>>(
                         X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W, blk.shortcut.cin, C, fold ? xin : nullptr, x_is_u8,
-                        fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr);
+                        fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0);
                     mmla_count_launch("pool_shortcut_kernel", st);
                     MMLA_CUDA_CHECK(cudaGetLastError());
                     H = Ho; W = Wo;
@@ -1139,7 +1171,7 @@ EXPORT int mmla_debug_conv2d(const float* x, const float* w_host, const float* b
 
 EXPORT int mmla_debug_resblock2d(const float* x, const float* w1_host, const float* b1, const float* bn1_scale, const float* bn1_shift,
                                  const float* w2_host, const float* b2, const float* bn2_scale, const float* bn2_shift, const float* res,
-                                 float* y, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t C, void* stream) {
+                                 float* y, int64_t B, int32_t H, int32_t W, int32_t Cin, int32_t C, int32_t hpool, void* stream) {
     MMLA_REQUIRE(x && w1_host && b1 && bn1_scale && bn1_shift && w2_host && b2 && bn2_scale && bn2_shift && y && B >= 0 && H > 0 &&
                      W > 0 && Cin > 0 && C > 0,
                  MMLA_EINVAL, "debug_resblock2d: bad argument");
@@ -1156,7 +1188,8 @@ EXPORT int mmla_debug_resblock2d(const float* x, const float* w1_host, const flo
     int rc = MMLA_OK;
     if (cudaMemcpyAsync(wdev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MMLA_ECUDA;
     if (rc == MMLA_OK)
-        rc = mmla_launch_resblock2d_fused(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, wdev, b1, bn2_scale, bn2_shift, wdev + n1, b2, res, C, st);
+        rc = mmla_launch_resblock2d_fused(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, wdev, b1, bn2_scale, bn2_shift, wdev + n1, b2, res, C, st,
+                                          nullptr, 0, nullptr, nullptr, hpool);
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == MMLA_OK) {
         mmla_set_error("debug_resblock2d: %s", cudaGetErrorString(cudaGetLastError()));
         rc = MMLA_ECUDA;

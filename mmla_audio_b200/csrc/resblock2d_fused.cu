@@ -50,6 +50,7 @@ struct RbArgs {
     const float* stem_w;      // STEM: Conv2D(16, 1x1) weights [3][16] and bias [16] (overlap_detector_temp.py:283)
     const float* stem_b;
     int img_is_u8;
+    int hpool;                // HPOOL: Fp = H + 4, S = 128 T - 4, y = [B, H/2, W, C] = max over row pairs (2i, 2i+1) of the block output
     long long res_row_stride;
     long long img_pixels;     // H * W
     int H, W, Fp;
@@ -107,7 +108,10 @@ __device__ __forceinline__ void rb_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
 
 // STEM: the block's input is the net's stem Conv2D(16, 1x1) of the 3-channel classifier image, computed in the fill from the
 // image bytes (the expression of stem1x1_kernel, csrc/nets.cu): the [B,128,151,16] stem tensor is never written or read.
-template <int NT, bool RES, int THREADS, bool STEM = false>
+// HPOOL (pooled blocks): the MaxPool2D(2)'s maximum over the two ROWS of each window is taken in epilogue 2 — with an even
+// column pitch (Fp = H + 4) and an even chunk length the partners are adjacent accumulator rows of one warp's staging tile —
+// so the kernel writes [B, H/2, W, C], half of the block output, and pool_shortcut_kernel reads half as much.
+template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resblock2d_fused_kernel(const RbArgs a) {
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
@@ -412,20 +416,31 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     {
         float* stg = reinterpret_cast<float*>(slab) + warp * (32 * 36);
         const int seg = lane & 7, rsub = lane >> 3;
-        int pixoff[8];                          // pixel index inside the image, -1: junk row
-        const long long imgbase = static_cast<long long>(img) * a.img_pixels;
+        constexpr int kRowsPerLane = HPOOL ? 4 : 8;
+        int pixoff[kRowsPerLane];               // pixel index inside the (half-pooled) image, -1: junk row
+        const long long imgbase = static_cast<long long>(img) * (HPOOL ? a.img_pixels / 2 : a.img_pixels);
         float4 rr[RES ? 8 : 1];
         auto prefetch = [&](int u) {
             const int t = u / kChunks, col0 = (u - t * kChunks) * 32;
-            const int rb = t * 128 + quarter * 32 + rsub;
+            if constexpr (HPOOL) {
+                const int rb = t * 128 + quarter * 32 + 2 * rsub;     // rows (rb + 8 i, rb + 8 i + 1): even chunk start, even pitch
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = rb + 4 * i, q = Qc + row;
-                const int wq = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), hq = q - wq * a.Fp;
-                const bool valid = row < nq && hq < a.H;
-                pixoff[i] = valid ? hq * a.W + wq : -1;
-                if (RES) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (RES && valid) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res + (imgbase + pixoff[i]) * a.res_row_stride + col0) + seg);
+                for (int i = 0; i < 4; ++i) {
+                    const int row = rb + 8 * i, q = Qc + row;
+                    const int wq = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), hq = q - wq * a.Fp;
+                    pixoff[i] = (row < nq && hq < a.H) ? (hq >> 1) * a.W + wq : -1;
+                }
+            } else {
+                const int rb = t * 128 + quarter * 32 + rsub;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = rb + 4 * i, q = Qc + row;
+                    const int wq = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), hq = q - wq * a.Fp;
+                    const bool valid = row < nq && hq < a.H;
+                    pixoff[i] = valid ? hq * a.W + wq : -1;
+                    if (RES) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (RES && valid) rr[i] = __ldg(reinterpret_cast<const float4*>(a.res + (imgbase + pixoff[i]) * a.res_row_stride + col0) + seg);
+                }
             }
         };
         if (half < nunits) prefetch(half);
@@ -442,13 +457,26 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
                 *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             __syncwarp();
             const float4 bv = __ldg(reinterpret_cast<const float4*>(a.b2 + col0) + seg);
+            if constexpr (HPOOL) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {     // rows 4i .. 4i+3 of the warp's 32, eight lanes (128 B) per row
-                if (pixoff[i] >= 0) {
-                    const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * seg);
-                    *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) =
-                        RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
-                            : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                for (int i = 0; i < 4; ++i) { // row pairs (8i + 2 rsub, + 1) of the warp's 32, eight lanes (128 B) per pooled row
+                    if (pixoff[i] >= 0) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(stg + (8 * i + 2 * rsub) * 36 + 4 * seg);
+                        const float4 v1 = *reinterpret_cast<const float4*>(stg + (8 * i + 2 * rsub + 1) * 36 + 4 * seg);
+                        *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) =
+                            make_float4(fmaxf(v0.x + bv.x, v1.x + bv.x), fmaxf(v0.y + bv.y, v1.y + bv.y),
+                                        fmaxf(v0.z + bv.z, v1.z + bv.z), fmaxf(v0.w + bv.w, v1.w + bv.w));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { // rows 4i .. 4i+3 of the warp's 32, eight lanes (128 B) per row
+                    if (pixoff[i] >= 0) {
+                        const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * seg);
+                        *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) =
+                            RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
+                                : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                    }
                 }
             }
             __syncwarp();                     // the staging tile is rewritten by the next unit
@@ -473,18 +501,18 @@ int rb_ilog2(int v) {
 long long* g_rb_stamps = nullptr;         // mmla_debug_resblock2d_stamps: 16 rows (launch ordinal) x 16 slots
 int g_rb_stamp_cta = 0, g_rb_stamp_row = 0;
 
-template <int NT, bool RES, int THREADS, bool STEM = false>
+template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false>
 int launch_rb(const RbArgs& s, long long images, size_t smem, cudaStream_t st) {
     static size_t attr[64] = {};                                  // per device: function attributes are per device
     int dev = 0;
     MMLA_CUDA_CHECK(cudaGetDevice(&dev));
     MMLA_REQUIRE(dev >= 0 && dev < 64, MMLA_EUNSUP, "resblock2d: device ordinal %d out of range", dev);
     if (smem > attr[dev]) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resblock2d_fused_kernel<NT, RES, THREADS, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resblock2d_fused_kernel<NT, RES, THREADS, STEM, HPOOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem)));
         attr[dev] = smem;
     }
-    resblock2d_fused_kernel<NT, RES, THREADS, STEM><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
+    resblock2d_fused_kernel<NT, RES, THREADS, STEM, HPOOL><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
     mmla_count_launch(STEM ? "stem_resblock2d_fused_kernel" : "resblock2d_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
@@ -501,7 +529,7 @@ bool mmla_resblock2d_eligible(int H, int W, int Cin, int C, int kh1, int kw1, in
     if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return false;
     if (C != 32 && C != 64 && C != 128) return false;
     if (H < 2 || W < 1) return false;
-    if (static_cast<long long>(W + 2) * (H + 3) + 512 + 8 >= (1LL << 20)) return false;
+    if (static_cast<long long>(W + 2) * (H + 4) + 512 + 8 >= (1LL << 20)) return false;
     return true;
 }
 
@@ -511,8 +539,9 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                  long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8, const float* stem_w,
-                                 const float* stem_b) {
+                                 const float* stem_b, int hpool) {
     if (B <= 0) return MMLA_OK;
+    MMLA_REQUIRE(!hpool || (!res && H % 2 == 0), MMLA_EUNSUP, "resblock2d: row-pooled output needs an even height and no residual");
     MMLA_REQUIRE(!img || (Cin == 16 && C == 32 && !res && stem_w && stem_b), MMLA_EUNSUP, "resblock2d: stem mode needs Cin 16, C 32, no residual");
     MMLA_REQUIRE(!res || res_row_stride % 4 == 0, MMLA_EUNSUP, "resblock2d: residual row stride must be a multiple of 4 floats");
     RbArgs s;
@@ -522,7 +551,9 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     s.res = res; s.res_row_stride = res_row_stride;
     s.img = img; s.img_is_u8 = img_is_u8; s.stem_w = stem_w; s.stem_b = stem_b;
     s.img_pixels = static_cast<long long>(H) * W;
-    s.H = H; s.W = W; s.Fp = H + 3;
+    s.hpool = hpool;
+    const int drop = hpool ? 4 : 3;                              // outputs a CTA gives up to the 4x1 halo (even for HPOOL)
+    s.H = H; s.W = W; s.Fp = H + drop;
     s.fp_magic = static_cast<unsigned>((1ULL << 32) / static_cast<unsigned>(s.Fp)) + 1u;
     s.total_q = W * s.Fp;
     s.Cin = Cin; s.lq = rb_ilog2(Cin / 4);
@@ -591,7 +622,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                 const double mma = s.nk * (per_chunk > refill ? per_chunk : refill);
                 const double fill = 5000.0 + rows_x(t) * (Cin / 4) / static_cast<double>(nthr) * 40.0;
                 const double epi = 2.0 * (3000.0 + 700.0 * t * (C / 32));
-                const int outs = t * 128 - 3;
+                const int outs = t * 128 - drop;
                 const int cpi = (s.total_q + outs - 1) / outs;
                 const double cost = (fill + mma + epi) * cpi / overlap[bi] / s.total_q;
                 if (!T || cost < best) {
@@ -602,7 +633,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     }
     MMLA_REQUIRE(T > 0, MMLA_EUNSUP, "resblock2d: block does not fit in shared memory (Cin %d, C %d, H %d)", Cin, C, H);
     s.T = T;
-    s.S = T * 128 - 3;
+    s.S = T * 128 - drop;
     s.cpi = (s.total_q + s.S - 1) / s.S;
     s.RsX = rows_x(T);
     s.RsU = rows_u(T);
@@ -646,7 +677,21 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
             default: return launch_rb<128, true, 256>(s, B, smem, st);
         }
     }
-    if (img) return launch_rb<32, false, 256, true>(s, B, smem, st);
+    if (img) return hpool ? launch_rb<32, false, 256, true, true>(s, B, smem, st) : launch_rb<32, false, 256, true>(s, B, smem, st);
+    if (hpool) {
+        if (best_thr == 256) {
+            switch (C) {
+                case 32: return launch_rb<32, false, 256, false, true>(s, B, smem, st);
+                case 64: return launch_rb<64, false, 256, false, true>(s, B, smem, st);
+                default: return launch_rb<128, false, 256, false, true>(s, B, smem, st);
+            }
+        }
+        switch (C) {
+            case 32: return launch_rb<32, false, 512, false, true>(s, B, smem, st);
+            case 64: return launch_rb<64, false, 512, false, true>(s, B, smem, st);
+            default: return launch_rb<128, false, 512, false, true>(s, B, smem, st);
+        }
+    }
     if (best_thr == 256) {
         switch (C) {
             case 32: return launch_rb<32, false, 256>(s, B, smem, st);

@@ -32,15 +32,15 @@ def _slab_conv(torch, lib, x, w, bias, bn, res):
     return y
 
 
-def _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res):
+def _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res, hpool=0):
     B, H, W, Cin = x.shape
     Cc = w1.shape[3]
-    y = torch.full((B, H, W, Cc), float("nan"), device="cuda", dtype=torch.float32)
+    y = torch.full((B, H // 2 if hpool else H, W, Cc), float("nan"), device="cuda", dtype=torch.float32)
     w1h = np.ascontiguousarray(w1.reshape(9 * Cin, Cc), dtype=np.float32)
     w2h = np.ascontiguousarray(w2.reshape(4 * Cc, Cc), dtype=np.float32)
     rc = lib.mmla_debug_resblock2d(_ptr(x), w1h.ctypes.data_as(C.c_void_p), _ptr(b1), _ptr(bn1[0]), _ptr(bn1[1]),
                                    w2h.ctypes.data_as(C.c_void_p), _ptr(b2), _ptr(bn2[0]), _ptr(bn2[1]), _ptr(res), _ptr(y),
-                                   B, H, W, Cin, Cc, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                   B, H, W, Cin, Cc, hpool, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.mmla_last_error().decode()
     return y
 
@@ -103,13 +103,19 @@ def test_fused_block_matches_two_slab_convs_bitwise(cuda, H, W, Cin, Cc, with_re
     print(f"fused vs fp64 convs {d_ref / scale:.2e} of max |y| = {scale:.2f}; elements differing from the two slab launches: {n_diff}")
     assert n_diff == 0
     assert d_ref <= 5e-3 * scale
+    if not with_res and H % 2 == 0:
+        # pooled blocks: the maximum over the row pairs (2i, 2i + 1) taken in the kernel's epilogue (HPOOL: column pitch H + 4,
+        # 128 T - 4 outputs per CTA) against the same maximum of the full-resolution output
+        hp = _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, None, hpool=1)
+        assert torch.equal(hp, torch.maximum(fused[:, 0::2], fused[:, 1::2]))
 
 
 def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch):
     """Whole overlap net, TF32 mode, uint8 and float32 images: MMLA_NET_FUSE_BLOCKS=0 (two conv_slab launches per block) vs
     MMLA_NET_FUSE_STEM2D=0 (one resblock2d_fused_kernel launch per block, stem1x1_kernel on its own) vs the default (the stem
     Conv2D(16, 1x1) also computed inside the first block's conv-pair and pooling kernels): identical probabilities, and the
-    launch traces show which kernels ran."""
+    launch traces show which kernels ran; MMLA_NET_FUSE_HPOOL=0 keeps the pooled blocks' conv output at full resolution
+    (default: the row half of the MaxPool is taken in the conv-pair kernel's epilogue)."""
     from mmla_audio_b200 import _lib, models, weights as W
     torch = cuda
     spec = W.OVERLAP
@@ -117,8 +123,9 @@ def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch
     x8 = torch.randint(0, 256, (5, 128, 151, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
     for x in (x8, x8.float() * 0.37 - 20.0):
         out, names = {}, {}
-        for mode, env in (("two", {"MMLA_NET_FUSE_BLOCKS": "0"}), ("one", {"MMLA_NET_FUSE_STEM2D": "0"}), ("stem", {})):
-            for k in ("MMLA_NET_FUSE_BLOCKS", "MMLA_NET_FUSE_STEM2D"):
+        for mode, env in (("two", {"MMLA_NET_FUSE_BLOCKS": "0"}), ("one", {"MMLA_NET_FUSE_STEM2D": "0", "MMLA_NET_FUSE_HPOOL": "0"}),
+                          ("nohp", {"MMLA_NET_FUSE_HPOOL": "0"}), ("stem", {})):
+            for k in ("MMLA_NET_FUSE_BLOCKS", "MMLA_NET_FUSE_STEM2D", "MMLA_NET_FUSE_HPOOL"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
@@ -129,5 +136,5 @@ def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch
         assert names["one"].count("stem1x1_kernel") == 1 and names["two"].count("stem1x1_kernel") == 1
         assert names["stem"].count("resblock2d_fused_kernel") == 8 and names["stem"].count("stem_resblock2d_fused_kernel") == 1
         assert "stem1x1_kernel" not in names["stem"]
-        for mode in ("one", "stem"):
+        for mode in ("one", "nohp", "stem"):
             assert torch.equal(out["two"][0], out[mode][0]) and torch.equal(out["two"][1], out[mode][1]), mode
