@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ hf,
 struct ConvW {
     const float* k = nullptr;
     const float* k_tc = nullptr;          // same weights arranged + TF32-rounded for conv_tc.cu (or null)
+    const float* k_tc2 = nullptr;         // ... in the CTA-pair arrangement of resblock2d_fused.cu (overlap net, cout >= 64)
     const float* b = nullptr;
     int kh = 1, kw = 1, cin = 0, cout = 0, stride = 1;
 };
@@ -562,7 +563,10 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                  long long res_row_stride, cudaStream_t st, const void* img = nullptr, int img_is_u8 = 0,
-                                 const float* stem_w = nullptr, const float* stem_b = nullptr, int hpool = 0);
+                                 const float* stem_w = nullptr, const float* stem_b = nullptr, int hpool = 0,
+                                 const float* w1_pair = nullptr, const float* w2_pair = nullptr);
+void mmla_rb_arrange_weights_pair(const float* w, int K, int N, float* out);
+bool mmla_rb_pair_wanted(int Cin, int C);
 // lstm_fused.cu
 long long mmla_xproj_arranged_floats();
 void mmla_xproj_arrange_weights(const float* W, float* out);
@@ -670,6 +674,12 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
         stage.resize(stage.size() + mmla_tc_arranged_floats(K, c.cout));
         mmla_tc_arrange_weights(wsrc, K, c.cout, stage.data() + off);
         fixes.push_back({&c.k_tc, off});
+        if (ov && c.cout >= 64 && c.cout <= 128 && K % 32 == 0 && c.kh * c.kw > 1) {
+            const long long off2 = static_cast<long long>(stage.size());
+            stage.resize(stage.size() + mmla_tc_arranged_floats(K, c.cout));
+            mmla_rb_arrange_weights_pair(wsrc, K, c.cout, stage.data() + off2);
+            fixes.push_back({&c.k_tc2, off2});
+        }
     };
     auto take_conv = [&](ConvW& c, int kh, int kw, int cin, int cout, int stride) {
         c.kh = kh; c.kw = kw; c.cin = cin; c.cout = cout; c.stride = stride;
@@ -986,7 +996,8 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                     // both convolutions in one launch, the intermediate stays in shared memory (resblock2d_fused.cu)
                     if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
                                                            blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
-                                                           blk.conv2.b, X, blk.conv2.cout, st)))
+                                                           blk.conv2.b, X, blk.conv2.cout, st, nullptr, 0, nullptr, nullptr, 0,
+                                                           blk.conv1.k_tc2, blk.conv2.k_tc2)))
                         return rc;
                 } else {
                     if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
@@ -1007,7 +1018,8 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                     if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
                                                            blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
                                                            blk.conv2.b, nullptr, 0, st, fold ? xin : nullptr, x_is_u8,
-                                                           fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0)))
+                                                           fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0,
+                                                           blk.conv1.k_tc2, blk.conv2.k_tc2)))
                         return rc;
                 } else {
                     if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
@@ -1180,16 +1192,22 @@ EXPORT int mmla_debug_resblock2d(const float* x, const float* w1_host, const flo
                  "debug_resblock2d: block is not eligible for resblock2d_fused_kernel");
     const int K1 = 9 * Cin, K2 = 4 * C;
     const long long n1 = mmla_tc_arranged_floats(K1, C), n2 = mmla_tc_arranged_floats(K2, C);
-    std::vector<float> host(n1 + n2);
+    const bool pair = mmla_rb_pair_wanted(Cin, C);
+    std::vector<float> host((n1 + n2) * (pair ? 2 : 1));
     mmla_tc_arrange_weights(w1_host, K1, C, host.data());
     mmla_tc_arrange_weights(w2_host, K2, C, host.data() + n1);
+    if (pair) {
+        mmla_rb_arrange_weights_pair(w1_host, K1, C, host.data() + n1 + n2);
+        mmla_rb_arrange_weights_pair(w2_host, K2, C, host.data() + 2 * n1 + n2);
+    }
     float* wdev = nullptr;
     MMLA_CUDA_CHECK(cudaMalloc(&wdev, host.size() * sizeof(float)));
     int rc = MMLA_OK;
     if (cudaMemcpyAsync(wdev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MMLA_ECUDA;
     if (rc == MMLA_OK)
         rc = mmla_launch_resblock2d_fused(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, wdev, b1, bn2_scale, bn2_shift, wdev + n1, b2, res, C, st,
-                                          nullptr, 0, nullptr, nullptr, hpool);
+                                          nullptr, 0, nullptr, nullptr, hpool, pair ? wdev + n1 + n2 : nullptr,
+                                          pair ? wdev + 2 * n1 + n2 : nullptr);
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == MMLA_OK) {
         mmla_set_error("debug_resblock2d: %s", cudaGetErrorString(cudaGetLastError()));
         rc = MMLA_ECUDA;

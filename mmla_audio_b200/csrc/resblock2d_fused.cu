@@ -50,6 +50,7 @@ struct RbArgs {
     const float* stem_w;      // STEM: Conv2D(16, 1x1) weights [3][16] and bias [16] (overlap_detector_temp.py:283)
     const float* stem_b;
     int img_is_u8;
+    int n_ctas;               // PAIR: real CTAs (the grid is rounded up to whole pairs)
     int hpool;                // HPOOL: Fp = H + 4, S = 128 T - 4, y = [B, H/2, W, C] = max over row pairs (2i, 2i+1) of the block output
     long long res_row_stride;
     long long img_pixels;     // H * W
@@ -94,6 +95,20 @@ __device__ __forceinline__ bool rb_elect_one() {
 __device__ __forceinline__ void rb_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// PAIR (cta_group::2): the leader's commit arrives on the barrier at the same offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void rb_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+__device__ __forceinline__ void rb_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t rb_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void rb_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -111,11 +126,18 @@ __device__ __forceinline__ void rb_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
 // HPOOL (pooled blocks): the MaxPool2D(2)'s maximum over the two ROWS of each window is taken in epilogue 2 — with an even
 // column pitch (Fp = H + 4) and an even chunk length the partners are adjacent accumulator rows of one warp's staging tile —
 // so the kernel writes [B, H/2, W, C], half of the block output, and pool_shortcut_kernel reads half as much.
-template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false>
+// PAIR (C >= 64): two CTAs of a cluster run every MMA together (`tcgen05.mma.cta_group::2`, M = 256: 128 rows of each CTA's
+// slab) and each holds HALF of every weight chunk (N / 2 columns), so the same ring bytes keep twice as many chunks in flight
+// and the weight stream out of L2 halves — the C >= 64 blocks wait on exactly that (a ring slot is re-requested when its
+// MMAs complete and lands ~3 000 cycles later).  OPT-IN, see mmla_rb_pair_wanted: it measured slower.  The leader (rank 0) issues; the peer's warp 0 relays "my half has landed" to
+// the leader's `pfull` barriers; `empty` / `accum` are arrived in both CTAs by multicast commits; cluster barriers replace the
+// CTA barriers where the leader's MMAs read the peer's slab.
+template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resblock2d_fused_kernel(const RbArgs a) {
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
-                                (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M=128
-    constexpr uint32_t kChunkBytes = 8 * NT * 16;
+                                (static_cast<uint32_t>((PAIR ? 256 : 128) >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M
+    constexpr uint32_t kChunkBytes = 8 * NT * 16 / (PAIR ? 2 : 1);
+    constexpr int kNB = PAIR ? NT / 2 : NT;                               // weight columns this CTA holds
     constexpr int kWarps = THREADS / 32;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
@@ -124,8 +146,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     float* par = reinterpret_cast<float*>(base + a.par_off);              // b1 | bn2 scale | bn2 shift, NT floats each
     uint64_t* full = reinterpret_cast<uint64_t*>(base + a.bar_off);      // [stages]
     uint64_t* empty = full + kRbMaxStages;                               // [stages]
-    uint64_t* accum = full + 2 * kRbMaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kRbMaxStages + 1);
+    uint64_t* pfull = full + 2 * kRbMaxStages;                           // [stages] PAIR, leader: the peer's half has landed
+    uint64_t* accum = full + 3 * kRbMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 3 * kRbMaxStages + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool stamping = a.stamps != nullptr && static_cast<int>(blockIdx.x) == a.stamp_cta;
@@ -133,16 +156,20 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
         if (stamping) a.stamps[slot] = clock64();
     };
     if (tid == 0) stamp(0);
-    const int img = blockIdx.x / a.cpi;
-    const int Qc = (blockIdx.x - img * a.cpi) * a.S;                      // first output of this CTA
-    const int nq = min(a.S, a.total_q - Qc);                              // outputs of this CTA
-    const int Tc = (nq + 3 + 127) >> 7;                                   // tiles of either convolution
-    const uint32_t cols = (Tc * NT <= 32) ? 32u : (Tc * NT <= 64) ? 64u : (Tc * NT <= 128) ? 128u : (Tc * NT <= 256) ? 256u : 512u;
+    const uint32_t rank = PAIR ? rb_cluster_rank() : 0u;
+    const bool dummy = PAIR && static_cast<int>(blockIdx.x) >= a.n_ctas;  // pads the grid to whole pairs: runs the protocol, no data
+    const int img = dummy ? 0 : blockIdx.x / a.cpi;
+    const int Qc = dummy ? 0 : (blockIdx.x - img * a.cpi) * a.S;          // first output of this CTA
+    const int nq = dummy ? 0 : min(a.S, a.total_q - Qc);                  // outputs of this CTA
+    const int Tc = dummy ? 0 : (nq + 3 + 127) >> 7;                       // tiles of either convolution
+    const int Tm = PAIR ? a.T : Tc;                                       // tiles the MMAs run over (a pair: the same in both CTAs)
+    const uint32_t cols = (Tm * NT <= 32) ? 32u : (Tm * NT <= 64) ? 64u : (Tm * NT <= 128) ? 128u : (Tm * NT <= 256) ? 256u : 512u;
 
     if (tid == 0) {
         for (int i = 0; i < a.stages; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
+            if (PAIR) mbar_init(&pfull[i], 1);
         }
         mbar_init(accum, 1);
         mbar_fence_init();
@@ -159,8 +186,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     __syncthreads();
     if (tid == 0) stamp(1);
 
-    auto wsrc = [&](int kc) {
-        return kc < a.nk1 ? a.w1 + static_cast<long long>(kc) * (NT * kRbBK) : a.w2 + static_cast<long long>(kc - a.nk1) * (NT * kRbBK);
+    auto wsrc = [&](int kc) {                 // PAIR: the pair arrangement keeps this CTA's half of a chunk contiguous
+        return (kc < a.nk1 ? a.w1 + static_cast<long long>(kc) * (NT * kRbBK) : a.w2 + static_cast<long long>(kc - a.nk1) * (NT * kRbBK)) +
+               rank * (kNB * kRbBK);
     };
     // ---- weight ring: the first `stages` chunks need no free slot, so they are requested before the fill ----
     if (lane == 0) {                          // one chunk per warp at a time: bulk copies of one thread serialise
@@ -173,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
 
     if constexpr (STEM) {
         // ---- x slab fill from the image: 3 values per pixel -> 16 stem channels -> BN1 + ELU + TF32, one pass, no staging ----
-        const int rows = Tc * 128 + 2 * a.Fp + 2;
+        const int rows = dummy ? 0 : Tc * 128 + 2 * a.Fp + 2;
         const int c4 = lane >> 3;                             // Cin = 16: four quads, eight rows per warp instruction
         const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bn1_scale) + c4);
         const float4 sh = __ldg(reinterpret_cast<const float4*>(a.bn1_shift) + c4);
@@ -220,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     } else
     // ---- x slab fill: row r <-> padded flat index Qc - 1 + r; BN1 + ELU + TF32 once per element (conv_slab.cu's fill) ----
     {
-        const int rows = Tc * 128 + 2 * a.Fp + 2;
+        const int rows = dummy ? 0 : Tc * 128 + 2 * a.Fp + 2;
         const int lqg = a.lq - 2;                             // log2(quad groups of 4)
         const int c4 = ((warp & ((1 << lqg) - 1)) << 2) + (lane >> 3);
         const int rpp = (kWarps >> lqg) * 8;                  // rows per pass of the whole CTA
@@ -278,16 +306,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     }
     if (tid == 0) stamp(2);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
 #pragma unroll
     for (int i = 0; i < (3 * NT + THREADS - 1) / THREADS; ++i)
         if (tid + i * THREADS < 3 * NT) par[tid + i * THREADS] = pv[i];
     fence_proxy_async_smem();                // generic-proxy slab writes -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if constexpr (PAIR) rb_cluster_sync();   // the leader's MMAs read both slabs; both CTAs' barriers are initialised
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     if (tid == 0) stamp(3);
@@ -315,9 +350,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     auto issue = [&](int kc0, int kc1, int nmma_last, uint32_t rs16) {   // chunks [kc0, kc1) of one convolution
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dA = rb_desc(smem_u32(slab), rs16, 128u);
-        const uint64_t dB = rb_desc(smem_u32(ring), NT * 16, 128);
+        const uint64_t dB = rb_desc(smem_u32(ring), kNB * 16, 128);
         for (int kc = kc0; kc < kc1; ++kc) {
             rb_wait(&full[m_stg], m_ph);
+            if constexpr (PAIR) rb_wait(&pfull[m_stg], m_ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t bd0 = dB + static_cast<uint64_t>(m_stg * (kChunkBytes / 16));
             const uint32_t aoff[4] = {a.aoff[kc * 4], a.aoff[kc * 4 + 1], a.aoff[kc * 4 + 2], a.aoff[kc * 4 + 3]};
@@ -329,21 +365,48 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
                 for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
                     for (int t = 0; t < kRbMaxTiles; ++t) {
-                        if (kk < nmma && t < Tc) {
+                        if (kk < nmma && t < Tm) {
                             const uint32_t acc = (kc != kc0 || kk != 0) ? 1u : 0u;
-                            asm volatile(
-                                "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
-                                "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
-                                "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
-                                "r"(alo + aoff[kk] + static_cast<uint32_t>(t * 128)), "r"(ahi), "r"(blo + static_cast<uint32_t>(kk * 2 * NT)),
-                                "r"(bhi), "r"(kIdesc), "r"(acc)
-                                : "memory");
+                            if constexpr (PAIR) {
+                                asm volatile(
+                                    "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+                                    "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                                    "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
+                                    "r"(alo + aoff[kk] + static_cast<uint32_t>(t * 128)), "r"(ahi), "r"(blo + static_cast<uint32_t>(kk * 2 * kNB)),
+                                    "r"(bhi), "r"(kIdesc), "r"(acc)
+                                    : "memory");
+                            } else {
+                                asm volatile(
+                                    "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+                                    "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
+                                    "r"(alo + aoff[kk] + static_cast<uint32_t>(t * 128)), "r"(ahi), "r"(blo + static_cast<uint32_t>(kk * 2 * kNB)),
+                                    "r"(bhi), "r"(kIdesc), "r"(acc)
+                                    : "memory");
+                            }
                         }
                     }
                 }
-                rb_commit(&empty[m_stg]);
-                if (kc == kc1 - 1) rb_commit(accum);
+                if constexpr (PAIR) {
+                    rb_commit_pair(&empty[m_stg]);
+                    if (kc == kc1 - 1) rb_commit_pair(accum);
+                } else {
+                    rb_commit(&empty[m_stg]);
+                    if (kc == kc1 - 1) rb_commit(accum);
+                }
             }
+            if (++m_stg == a.stages) { m_stg = 0; m_ph ^= 1u; }
+            __syncwarp();
+        }
+    };
+    // PAIR, peer CTA: warp 0 tells the leader when this CTA's half of a chunk has landed
+    auto relay = [&](int kc0, int kc1) {
+        uint32_t remote0;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote0) : "r"(smem_u32(pfull)), "r"(0));
+        for (int kc = kc0; kc < kc1; ++kc) {
+            rb_wait(&full[m_stg], m_ph);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote0 + 8u * m_stg) : "memory");
             if (++m_stg == a.stages) { m_stg = 0; m_ph ^= 1u; }
             __syncwarp();
         }
@@ -355,7 +418,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
         const int lim = a.nk1 + a.stages;
         produce(a.nk < lim ? a.nk : lim);
     } else if (warp == 0) {
-        issue(0, a.nk1, a.nmma1_last, static_cast<uint32_t>(a.RsX) * 16u);
+        if (rank == 0) issue(0, a.nk1, a.nmma1_last, static_cast<uint32_t>(a.RsX) * 16u);
+        else relay(0, a.nk1);
         if (lane == 0) stamp(4);
     }
 
@@ -399,7 +463,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
             *reinterpret_cast<uint4*>(slab + (static_cast<size_t>(i / 3) * a.RsU + Tc * 128 + i % 3) * 16) = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         fence_proxy_async_smem();
-        __syncthreads();
+        if constexpr (PAIR) rb_cluster_sync();   // conv2's MMAs read both CTAs' u slabs and overwrite both accumulators
+        else __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 0) stamp(6);
     }
@@ -408,7 +473,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     if (warp >= 1 && warp <= kProducers) {
         produce(a.nk);
     } else if (warp == 0) {
-        issue(a.nk1, a.nk, a.nmma2_last, static_cast<uint32_t>(a.RsU) * 16u);
+        if (rank == 0) issue(a.nk1, a.nk, a.nmma2_last, static_cast<uint32_t>(a.RsU) * 16u);
+        else relay(a.nk1, a.nk);
         if (lane == 0) stamp(7);
     }
 
@@ -485,10 +551,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resbl
     }
     if (tid == 64) stamp(9);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if constexpr (PAIR) rb_cluster_sync();       // neither CTA leaves while the pair's MMAs / commits / relays could still target it
+    else __syncthreads();
     if (tid == 0) stamp(10);
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
     }
 }
 
@@ -501,18 +569,36 @@ int rb_ilog2(int v) {
 long long* g_rb_stamps = nullptr;         // mmla_debug_resblock2d_stamps: 16 rows (launch ordinal) x 16 slots
 int g_rb_stamp_cta = 0, g_rb_stamp_row = 0;
 
-template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false>
+template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false, bool PAIR = false>
 int launch_rb(const RbArgs& s, long long images, size_t smem, cudaStream_t st) {
     static size_t attr[64] = {};                                  // per device: function attributes are per device
     int dev = 0;
     MMLA_CUDA_CHECK(cudaGetDevice(&dev));
     MMLA_REQUIRE(dev >= 0 && dev < 64, MMLA_EUNSUP, "resblock2d: device ordinal %d out of range", dev);
+    auto kern = resblock2d_fused_kernel<NT, RES, THREADS, STEM, HPOOL, PAIR>;
     if (smem > attr[dev]) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(resblock2d_fused_kernel<NT, RES, THREADS, STEM, HPOOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr[dev] = smem;
     }
-    resblock2d_fused_kernel<NT, RES, THREADS, STEM, HPOOL><<<static_cast<unsigned>(images * s.cpi), THREADS, smem, st>>>(s);
+    const long long ctas = images * s.cpi;
+    if constexpr (PAIR) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(static_cast<unsigned>((ctas + 1) / 2 * 2), 1, 1);   // whole pairs; the odd one out runs the protocol only
+        cfg.blockDim = dim3(THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, s));
+    } else {
+        kern<<<static_cast<unsigned>(ctas), THREADS, smem, st>>>(s);
+    }
     mmla_count_launch(STEM ? "stem_resblock2d_fused_kernel" : "resblock2d_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
@@ -533,14 +619,45 @@ bool mmla_resblock2d_eligible(int H, int W, int Cin, int C, int kh1, int kw1, in
     return true;
 }
 
+// Weight arrangement of the PAIR mode: per [32 x N] K-chunk the two column halves one after the other, each in conv_tc.cu's
+// layout for N / 2 columns — out[kchunk][half][slab 0..7][n 0..N/2-1][4] = tf32(W[kchunk*32 + slab*4 + j][half*N/2 + n]) — so
+// that a CTA's half of a chunk is one contiguous bulk copy.  Same size as mmla_tc_arrange_weights' output; K % 32 == 0.
+void mmla_rb_arrange_weights_pair(const float* w, int K, int N, float* out) {
+    const int nk = K / kRbBK, nh = N / 2;
+    for (int kc = 0; kc < nk; ++kc)
+        for (int h = 0; h < 2; ++h)
+            for (int slab = 0; slab < 8; ++slab)
+                for (int n = 0; n < nh; ++n)
+                    for (int j = 0; j < 4; ++j) {
+                        float v = w[static_cast<long long>(kc * kRbBK + slab * 4 + j) * N + h * nh + n];
+                        uint32_t u;
+                        memcpy(&u, &v, 4);
+                        if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & ~0x1FFFu;
+                        memcpy(&v, &u, 4);
+                        out[((((static_cast<long long>(kc) * 2 + h) * 8 + slab) * nh + n) * 4) + j] = v;
+                    }
+}
+bool mmla_rb_pair_wanted(int Cin, int C) {
+    // Opt-in (MMLA_RB_PAIR=1): measured SLOWER than one CTA per MMA on every C >= 64 block of the overlap net (0.68 -> 0.78,
+    // 0.29 -> 0.35, 0.56 -> 0.70, 0.29 -> 0.34 ms per 512 clips, profiles/r02/experiment_notes.txt): the N <= 128, K = 8 MMAs are
+    // too small to amortise the pair's per-instruction hand-shake (162 vs 110 cycles per MMA at N = 64) and the three cluster
+    // barriers keep the two CTAs in lock-step.  Kept as a tested alternative (bit-identical results).
+    const char* e = getenv("MMLA_RB_PAIR");
+    return e && e[0] == '1' && C >= 64 && (9 * Cin) % kRbBK == 0;
+}
+
 // img != null: stem mode — x is ignored, the block input is Conv2D(16, 1x1)(img) computed in the fill (Cin must be 16, no
 // residual, 256-thread configuration).
 int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, int W, int Cin, int C, const float* bn1_scale,
                                  const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                  long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8, const float* stem_w,
-                                 const float* stem_b, int hpool) {
+                                 const float* stem_b, int hpool, const float* w1_pair, const float* w2_pair) {
     if (B <= 0) return MMLA_OK;
+    // w1_pair / w2_pair: the same weights in the PAIR arrangement (mmla_rb_arrange_weights_pair); when given (and wanted) the
+    // block runs on CTA pairs
+    const bool pair = w1_pair && w2_pair && !img && mmla_rb_pair_wanted(Cin, C);
+    if (pair) { w1 = w1_pair; w2 = w2_pair; }
     MMLA_REQUIRE(!hpool || (!res && H % 2 == 0), MMLA_EUNSUP, "resblock2d: row-pooled output needs an even height and no residual");
     MMLA_REQUIRE(!img || (Cin == 16 && C == 32 && !res && stem_w && stem_b), MMLA_EUNSUP, "resblock2d: stem mode needs Cin 16, C 32, no residual");
     MMLA_REQUIRE(!res || res_row_stride % 4 == 0, MMLA_EUNSUP, "resblock2d: residual row stride must be a multiple of 4 floats");
@@ -561,7 +678,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     s.nk1 = (K1 + kRbBK - 1) / kRbBK;
     s.nk = s.nk1 + K2 / kRbBK;
     MMLA_REQUIRE(s.nk <= kRbMaxChunks, MMLA_EUNSUP, "resblock2d: K = %d + %d is too large", K1, K2);
-    const size_t chunk = static_cast<size_t>(8) * C * 16;        // one [32 x C] K-chunk of weights
+    const size_t chunk = static_cast<size_t>(8) * C * 16 / (pair ? 2 : 1);   // one [32 x C] K-chunk of weights (PAIR: this CTA's half)
     constexpr size_t kBarBytes = 1024 + 128;                    // mbarriers + alignment slack
     const size_t par_bytes = static_cast<size_t>(3) * C * 4;
     auto rows_x = [&](int T) {
@@ -662,14 +779,31 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     s.bar_off = static_cast<unsigned>((s.par_off + par_bytes + 127) / 128 * 128);
     const size_t smem = s.bar_off + kBarBytes;
     if (getenv("MMLA_RB_VERBOSE"))
-        fprintf(stderr, "resblock2d: %dx%d Cin %d C %d: %d outputs/image, T %d, %d CTAs/image, ring %d of %d chunks, %zu KB smem, %d threads\n",
-                H, W, Cin, C, s.total_q, s.T, s.cpi, s.stages, s.nk, smem / 1024, best_thr);
+        fprintf(stderr, "resblock2d: %dx%d Cin %d C %d: %d outputs/image, T %d, %d CTAs/image, ring %d of %d chunks, %zu KB smem, %d threads%s\n",
+                H, W, Cin, C, s.total_q, s.T, s.cpi, s.stages, s.nk, smem / 1024, best_thr, pair ? ", CTA pairs" : "");
     if (g_rb_stamps && g_rb_stamp_row < 16) {
         s.stamps = g_rb_stamps + 16 * g_rb_stamp_row++;
         s.stamp_cta = static_cast<int>((static_cast<long long>(g_rb_stamp_cta) % B) * s.cpi + s.cpi / 2);   // a mid-image CTA
     }
-    MMLA_REQUIRE(B * s.cpi < (1LL << 31) && B * s.img_pixels * (Cin > C ? Cin : C) < (1LL << 40), MMLA_EUNSUP,
+    MMLA_REQUIRE(B * s.cpi < (1LL << 31) - 2 && B * s.img_pixels * (Cin > C ? Cin : C) < (1LL << 40), MMLA_EUNSUP,
                  "resblock2d: batch too large");
+    s.n_ctas = static_cast<int>(B * s.cpi);
+    if (pair) {
+        if (res) return C == 64 ? launch_rb<64, true, 256, false, false, true>(s, B, smem, st)
+                                : launch_rb<128, true, 256, false, false, true>(s, B, smem, st);
+        if (hpool) {
+            if (best_thr == 256)
+                return C == 64 ? launch_rb<64, false, 256, false, true, true>(s, B, smem, st)
+                               : launch_rb<128, false, 256, false, true, true>(s, B, smem, st);
+            return C == 64 ? launch_rb<64, false, 512, false, true, true>(s, B, smem, st)
+                           : launch_rb<128, false, 512, false, true, true>(s, B, smem, st);
+        }
+        if (best_thr == 256)
+            return C == 64 ? launch_rb<64, false, 256, false, false, true>(s, B, smem, st)
+                           : launch_rb<128, false, 256, false, false, true>(s, B, smem, st);
+        return C == 64 ? launch_rb<64, false, 512, false, false, true>(s, B, smem, st)
+                       : launch_rb<128, false, 512, false, false, true>(s, B, smem, st);
+    }
     if (res) {
         switch (C) {
             case 32: return launch_rb<32, true, 256>(s, B, smem, st);

@@ -138,3 +138,30 @@ def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch
         assert "stem1x1_kernel" not in names["stem"]
         for mode in ("one", "nohp", "stem"):
             assert torch.equal(out["two"][0], out[mode][0]) and torch.equal(out["two"][1], out[mode][1]), mode
+
+
+@pytest.mark.parametrize("H,W,Cin,Cc,with_res,B", [(64, 76, 32, 64, False, 3), (32, 38, 64, 64, True, 5), (16, 19, 128, 128, True, 7),
+                                                   (32, 38, 64, 128, False, 2)])
+def test_cta_pair_mode_is_bit_identical(cuda, monkeypatch, H, W, Cin, Cc, with_res, B):
+    """MMLA_RB_PAIR=1 (opt-in): `tcgen05.mma.cta_group::2` — two CTAs of a cluster run every MMA together (M = 256), each
+    holding half of every weight chunk; an odd CTA count pads the grid with a protocol-only CTA (B odd here).  Same operands,
+    same K order => the same bits as one CTA per MMA, with and without the row-pooled epilogue."""
+    torch = cuda
+    from mmla_audio_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(7 + H + Cin + Cc)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    w1 = (torch.randn(3, 3, Cin, Cc, generator=g) * (2.0 / (9 * Cin)) ** 0.5).numpy()
+    w2 = (torch.randn(4, 1, Cc, Cc, generator=g) * (2.0 / (4 * Cc)) ** 0.5).numpy()
+    b1 = (torch.randn(Cc, generator=g) * 0.1).cuda()
+    b2 = (torch.randn(Cc, generator=g) * 0.1).cuda()
+    bn1 = ((torch.rand(Cin, generator=g) + 0.5).cuda(), (torch.randn(Cin, generator=g) * 0.3).cuda())
+    bn2 = ((torch.rand(Cc, generator=g) + 0.5).cuda(), (torch.randn(Cc, generator=g) * 0.3).cuda())
+    res = torch.randn(B, H, W, Cc, generator=g).cuda() if with_res else None
+    modes = [0] if with_res else [0, 1]
+    monkeypatch.delenv("MMLA_RB_PAIR", raising=False)
+    one = [_fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res, hpool=hp) for hp in modes]
+    monkeypatch.setenv("MMLA_RB_PAIR", "1")
+    two = [_fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res, hpool=hp) for hp in modes]
+    for a, b in zip(one, two):
+        assert not torch.isnan(b).any() and torch.equal(a, b)
