@@ -265,6 +265,7 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
     res = 0.0
     slab = 0.0                                   # overlap: the stride-1 3x3 / 4x1 convs (conv_slab_kernel)
     slab_first = 0.0                             # ... of the first block (stem_resblock2d_fused_kernel)
+    slab_23 = 0.0                                # ... of blocks 2 and 3 (resblock2d_persist_kernel)
     pool_bytes = 0.0                             # overlap: pool_shortcut_kernel's compulsory traffic
     res_first_stage = 0.0                        # the first three residual units (the stage the stem is folded into)
     stem = 2.0 * h * w_ * spec.stem.kh * spec.stem.kw * spec.stem.cin * spec.stem.cout
@@ -280,6 +281,8 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
                                     blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout)
             if bi == 0:
                 slab_first = slab
+            if bi == 2:
+                slab_23 = slab - slab_first
         else:                                    # speaker: MaxPool first, both convs at the pooled length
             res += 2.0 * h2 * w2 * blk.conv1.kh * blk.conv1.kw * blk.conv1.cin * blk.conv1.cout
             res += 2.0 * h2 * w2 * blk.conv2.kh * blk.conv2.kw * blk.conv2.cin * blk.conv2.cout
@@ -321,6 +324,15 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         work["stem_resblock2d_fused_kernel"] = {"bound": "tensor", "per_step": B * (slab_first + stem),
                                                 "what": "stem Conv2D(16, 1x1) from the uint8 image + residual block 1's conv pair "
                                                         "at 128 x 151 (TF32)"}
+        work["resblock2d_persist_kernel"] = {"bound": "tensor", "per_step": B * slab_23,
+                                             "what": "residual blocks 2-3 (64 x 76 x 32): conv pairs on the persistent, "
+                                                     "warp-specialised kernel (TF32, weights resident in shared memory)"}
+        work["stem_resblock2d_persist_kernel"] = {"bound": "tensor", "per_step": B * (slab_first + stem),
+                                                  "what": "stem Conv2D(16, 1x1) from the uint8 image + residual block 1's conv pair "
+                                                          "at 128 x 151 (TF32), persistent warp-specialised kernel"}
+        work["resblock2d_fused_kernel"]["per_step"] = B * (slab - slab_first - slab_23)
+        work["resblock2d_fused_kernel"]["what"] = ("residual blocks 4-9 (C >= 64): conv pairs (3x3 then 4x1, TF32, tap-shifted "
+                                                   "slabs, the intermediate stays in shared memory)")
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (res - slab),
                                   "what": "the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
         work["pool_shortcut_kernel"] = {"bound": "hbm", "per_step": B * pool_bytes,
@@ -650,7 +662,8 @@ def main():
         summary["overlap_x512_audio_s_per_s"] = round(world * Bo * Lo / SR / (ms_o * 1e-3), 1)
         summary["overlap_x512_e2e_audio_s_per_s"] = round(world * Bo * Lo / SR / (ms_oe * 1e-3), 1)
         for row in ok:
-            if row["kernel"] in ("conv_slab_kernel", "resblock2d_fused_kernel", "overlap_features_kernel",
+            if row["kernel"] in ("conv_slab_kernel", "resblock2d_fused_kernel", "resblock2d_persist_kernel",
+                                 "stem_resblock2d_persist_kernel", "overlap_features_kernel",
                                  "overlap_features_tc_kernel") and "frac" in row:
                 summary["overlap_%s_frac" % row["kernel"]] = round(row["frac"], 4)
         del po, po_dev, po_host, opipe

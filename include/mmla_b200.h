@@ -93,6 +93,10 @@ int mmla_debug_resblock2d(const float* x, const float* w1_host, const float* b1,
  * 4 conv1 issued, 5 conv1 accumulators complete, 6 u slab written, 7 conv2 issued, 8 conv2 accumulators complete,
  * 9 epilogue done (warp 2), 10 all warps done. */
 void mmla_debug_resblock2d_stamps(long long* dev_stamps, int32_t image);
+/* Same for resblock2d_persist_kernel: dev_stamps (DEVICE pointer, 4 x 4 x 16 int64, NULL = off) receives, for each of the next
+ * four launches, the stamps of work items 4..7 of a mid-grid CTA (16 slots per item): 0/1 fill start / end, 2/3 conv1 issue,
+ * 4/5 conv2 issue, 6/7/8 epilogue 1 (accumulator ready, slab free, done), 9/10/11 epilogue 2 (accumulator ready, drained, stored). */
+void mmla_debug_resblock2d_persist_stamps(long long* dev_stamps);
 
 /* ------------------------------------------------------------------------------------------
  * Speaker-ID features.

@@ -17,7 +17,7 @@ SYMBOLS = (
     "mmla_psf_num_frames", "mmla_psf_mfcc", "mmla_psf_mfcc_rows", "mmla_delta", "mmla_cmvn", "mmla_overlap_features",
     "mmla_net_create", "mmla_net_destroy", "mmla_net_set_precision", "mmla_net_workspace_bytes",
     "mmla_net_forward", "mmla_net_forward_cepstra", "mmla_net_embed", "mmla_head_fit",
-    "mmla_tally", "mmla_synth_pcm", "mmla_vad_num_frames", "mmla_vad_trim", "mmla_noise_profile", "mmla_noise_gate", "mmla_debug_mfcc_tc_dump", "mmla_debug_resstage_stamps", "mmla_debug_lstm_stamps", "mmla_debug_conv2d", "mmla_debug_resblock2d", "mmla_debug_resblock2d_stamps", "mmla_debug_conv_slab_stamps", "mmla_trace_begin", "mmla_trace_end",
+    "mmla_tally", "mmla_synth_pcm", "mmla_vad_num_frames", "mmla_vad_trim", "mmla_noise_profile", "mmla_noise_gate", "mmla_debug_mfcc_tc_dump", "mmla_debug_resstage_stamps", "mmla_debug_lstm_stamps", "mmla_debug_conv2d", "mmla_debug_resblock2d", "mmla_debug_resblock2d_stamps", "mmla_debug_resblock2d_persist_stamps", "mmla_debug_conv_slab_stamps", "mmla_trace_begin", "mmla_trace_end",
 )
 
 
@@ -83,6 +83,7 @@ def load() -> C.CDLL:
         "mmla_debug_conv2d": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
         "mmla_debug_resblock2d": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
         "mmla_debug_resblock2d_stamps": (None, [vp, i32]),
+        "mmla_debug_resblock2d_persist_stamps": (None, [vp]),
         "mmla_trace_begin": (C.c_int, [vp]),
         "mmla_trace_end": (C.c_int, [vp, i64, vp, i32]),
     }

@@ -25,101 +25,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "conv_common.cuh"
+#include "resblock2d_common.cuh"
 
 namespace {
-
-constexpr int kRbBK = 32;                   // K per ring chunk (mmla_tc_arrange_weights)
-constexpr int kRbMaxTiles = 4;
-constexpr int kRbMaxStages = 40;
-constexpr int kRbMaxChunks = 64;           // conv1 + conv2 chunks
-
-struct RbArgs {
-    const float* x;
-    const float* w1;          // arranged weights (conv_tc.cu layout, one N tile) of the 3x3
-    const float* w2;          // ... of the 4x1
-    const float* b1;
-    const float* b2;
-    const float* bn1_scale;
-    const float* bn1_shift;
-    const float* bn2_scale;
-    const float* bn2_shift;
-    const float* res;
-    float* y;
-    const void* img;          // STEM: the classifier input [B,H,W,3] (uint8 or float32); x is unused
-    const float* stem_w;      // STEM: Conv2D(16, 1x1) weights [3][16] and bias [16] (overlap_detector_temp.py:283)
-    const float* stem_b;
-    int img_is_u8;
-    int n_ctas;               // PAIR: real CTAs (the grid is rounded up to whole pairs)
-    int hpool;                // HPOOL: Fp = H + 4, S = 128 T - 4, y = [B, H/2, W, C] = max over row pairs (2i, 2i+1) of the block output
-    long long res_row_stride;
-    long long img_pixels;     // H * W
-    int H, W, Fp;
-    unsigned fp_magic;        // floor(2^32 / Fp) + 1
-    int total_q;              // W * Fp
-    int Cin, lq;              // lq = log2(Cin / 4)
-    int nk1, nk;              // ring chunks of conv1 / of both convolutions
-    int nmma1_last, nmma2_last;
-    int T, S, cpi;            // tiles per CTA, outputs per CTA (128 T - 3), CTAs per image
-    int RsX, RsU;             // slab strides in rows
-    int stages;
-    unsigned ring_off, par_off, bar_off;
-    unsigned aoff[kRbMaxChunks * 4];   // per MMA: channel-quad slab + tap row shift, in 16-byte units
-    long long* stamps;        // diagnostics: clock64 timeline of CTA `stamp_cta` (null = off)
-    int stamp_cta;
-};
-
-__device__ __forceinline__ uint32_t rb_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
-__device__ __forceinline__ void rb_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 24); ++i)
-        if (mbar_try_wait(bar, parity)) return;
-    asm volatile("trap;");
-}
-// BN + ELU + TF32 rounding of one element: the expression of conv_slab.cu's fill (bit-identical results).
-__device__ __forceinline__ uint32_t rb_bn_elu_tf32(float v, float sc, float sh) {
-    v = fmaf(v, sc, sh);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
-    v = v > 0.f ? v : e - 1.f;
-    return rb_tf32(v);
-}
-__device__ __forceinline__ uint64_t rb_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
-           (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ bool rb_elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void rb_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// PAIR (cta_group::2): the leader's commit arrives on the barrier at the same offset in BOTH CTAs of the pair.
-__device__ __forceinline__ void rb_commit_pair(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(static_cast<uint16_t>(3))
-                 : "memory");
-}
-__device__ __forceinline__ void rb_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t rb_cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void rb_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // STEM: the block's input is the net's stem Conv2D(16, 1x1) of the 3-channel classifier image, computed in the fill from the
 // image bytes (the expression of stem1x1_kernel, csrc/nets.cu): the [B,128,151,16] stem tensor is never written or read.
@@ -646,6 +554,13 @@ bool mmla_rb_pair_wanted(int Cin, int C) {
     return e && e[0] == '1' && C >= 64 && (9 * Cin) % kRbBK == 0;
 }
 
+// resblock2d_persist.cu
+int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, int H, int W, int Cin, int C, const float* bn1_scale,
+                                       const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
+                                       const float* bn2_shift, const float* w2, const float* b2, const float* res,
+                                       long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8,
+                                       const float* stem_w, const float* stem_b, int hpool);
+
 // img != null: stem mode — x is ignored, the block input is Conv2D(16, 1x1)(img) computed in the fill (Cin must be 16, no
 // residual, 256-thread configuration).
 int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, int W, int Cin, int C, const float* bn1_scale,
@@ -654,6 +569,12 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8, const float* stem_w,
                                  const float* stem_b, int hpool, const float* w1_pair, const float* w2_pair) {
     if (B <= 0) return MMLA_OK;
+    {   // the C = 32 blocks run on the persistent, warp-specialised kernel where their slabs fit (resblock2d_persist.cu)
+        const int pr = mmla_try_launch_resblock2d_persist(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, w1, b1, bn2_scale, bn2_shift, w2, b2,
+                                                          res, res_row_stride, st, img, img_is_u8, stem_w, stem_b, hpool);
+        if (pr < 0) return -pr;
+        if (pr > 0) return MMLA_OK;
+    }
     // w1_pair / w2_pair: the same weights in the PAIR arrangement (mmla_rb_arrange_weights_pair); when given (and wanted) the
     // block runs on CTA pairs
     const bool pair = w1_pair && w2_pair && !img && mmla_rb_pair_wanted(Cin, C);

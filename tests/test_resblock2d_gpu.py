@@ -79,8 +79,9 @@ BLOCKS = [  # (H, W, Cin, C, residual, B)
 
 
 @pytest.mark.parametrize("H,W,Cin,Cc,with_res,B", BLOCKS)
-def test_fused_block_matches_two_slab_convs_bitwise(cuda, H, W, Cin, Cc, with_res, B):
+def test_fused_block_matches_two_slab_convs_bitwise(cuda, monkeypatch, H, W, Cin, Cc, with_res, B):
     torch = cuda
+    monkeypatch.setenv("MMLA_NET_PERSIST", "0")          # resblock2d_fused_kernel; the persistent kernel is compared below
     from mmla_audio_b200 import _lib
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(H * 1000 + W * 10 + Cin + Cc)
@@ -103,11 +104,24 @@ def test_fused_block_matches_two_slab_convs_bitwise(cuda, H, W, Cin, Cc, with_re
     print(f"fused vs fp64 convs {d_ref / scale:.2e} of max |y| = {scale:.2f}; elements differing from the two slab launches: {n_diff}")
     assert n_diff == 0
     assert d_ref <= 5e-3 * scale
+    hp = None
     if not with_res and H % 2 == 0:
         # pooled blocks: the maximum over the row pairs (2i, 2i + 1) taken in the kernel's epilogue (HPOOL: column pitch H + 4,
         # 128 T - 4 outputs per CTA) against the same maximum of the full-resolution output
         hp = _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, None, hpool=1)
         assert torch.equal(hp, torch.maximum(fused[:, 0::2], fused[:, 1::2]))
+    if Cc == 32 and Cin in (16, 32):
+        # resblock2d_persist_kernel (persistent, warp-specialised, weights resident): the same bits, also with a forced
+        # one-tile configuration (more work items per CTA, every buffer parity exercised)
+        monkeypatch.setenv("MMLA_NET_PERSIST", "2")
+        for tiles in (None, "1"):
+            if tiles:
+                monkeypatch.setenv("MMLA_RB_TILES", tiles)
+            ps = _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res)
+            assert torch.equal(ps, fused), f"persistent kernel differs (tiles {tiles})"
+            if hp is not None:
+                assert torch.equal(_fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, None, hpool=1), hp)
+        monkeypatch.delenv("MMLA_RB_TILES", raising=False)
 
 
 def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch):
@@ -115,7 +129,9 @@ def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch
     MMLA_NET_FUSE_STEM2D=0 (one resblock2d_fused_kernel launch per block, stem1x1_kernel on its own) vs the default (the stem
     Conv2D(16, 1x1) also computed inside the first block's conv-pair and pooling kernels): identical probabilities, and the
     launch traces show which kernels ran; MMLA_NET_FUSE_HPOOL=0 keeps the pooled blocks' conv output at full resolution
-    (default: the row half of the MaxPool is taken in the conv-pair kernel's epilogue)."""
+    (default: the row half of the MaxPool is taken in the conv-pair kernel's epilogue); MMLA_NET_PERSIST=0 keeps the C = 32
+    blocks on the one-CTA-per-item kernel (default: block 1 on resblock2d_persist_kernel, csrc/resblock2d_persist.cu; 2: blocks
+    2 and 3 as well)."""
     from mmla_audio_b200 import _lib, models, weights as W
     torch = cuda
     spec = W.OVERLAP
@@ -123,20 +139,27 @@ def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch
     x8 = torch.randint(0, 256, (5, 128, 151, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
     for x in (x8, x8.float() * 0.37 - 20.0):
         out, names = {}, {}
+        sw = ("MMLA_NET_FUSE_BLOCKS", "MMLA_NET_FUSE_STEM2D", "MMLA_NET_FUSE_HPOOL", "MMLA_NET_PERSIST")
         for mode, env in (("two", {"MMLA_NET_FUSE_BLOCKS": "0"}), ("one", {"MMLA_NET_FUSE_STEM2D": "0", "MMLA_NET_FUSE_HPOOL": "0"}),
-                          ("nohp", {"MMLA_NET_FUSE_HPOOL": "0"}), ("stem", {})):
-            for k in ("MMLA_NET_FUSE_BLOCKS", "MMLA_NET_FUSE_STEM2D", "MMLA_NET_FUSE_HPOOL"):
+                          ("nohp", {"MMLA_NET_FUSE_HPOOL": "0"}), ("nopersist", {"MMLA_NET_PERSIST": "0"}),
+                          ("persist3", {"MMLA_NET_PERSIST": "2"}), ("stem", {})):
+            for k in sw:
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             tr = _lib.trace_launches(lambda: out.__setitem__(mode, model.predict_device(x)), torch)
             names[mode] = [n for n, _ in tr]
-        assert names["two"].count("conv_slab_kernel") == 18 and "resblock2d_fused_kernel" not in names["two"]
-        assert names["one"].count("resblock2d_fused_kernel") == 9 and "conv_slab_kernel" not in names["one"]
+        pairs = lambda n: n.count("resblock2d_fused_kernel") + n.count("resblock2d_persist_kernel")
+        stems = lambda n: n.count("stem_resblock2d_fused_kernel") + n.count("stem_resblock2d_persist_kernel")
+        assert names["two"].count("conv_slab_kernel") == 18 and pairs(names["two"]) + stems(names["two"]) == 0
+        assert pairs(names["one"]) == 9 and "conv_slab_kernel" not in names["one"]
         assert names["one"].count("stem1x1_kernel") == 1 and names["two"].count("stem1x1_kernel") == 1
-        assert names["stem"].count("resblock2d_fused_kernel") == 8 and names["stem"].count("stem_resblock2d_fused_kernel") == 1
-        assert "stem1x1_kernel" not in names["stem"]
-        for mode in ("one", "nohp", "stem"):
+        assert pairs(names["stem"]) == 8 and stems(names["stem"]) == 1 and "stem1x1_kernel" not in names["stem"]
+        # block 1 runs on the persistent, warp-specialised kernel (MMLA_NET_PERSIST=0: never, 2: blocks 2 and 3 as well)
+        assert names["stem"].count("stem_resblock2d_persist_kernel") == 1 and names["stem"].count("resblock2d_persist_kernel") == 0
+        assert names["persist3"].count("stem_resblock2d_persist_kernel") == 1 and names["persist3"].count("resblock2d_persist_kernel") == 2
+        assert not any("persist" in n for n in names["nopersist"]) and names["nopersist"].count("resblock2d_fused_kernel") == 8
+        for mode in ("one", "nohp", "nopersist", "persist3", "stem"):
             assert torch.equal(out["two"][0], out[mode][0]) and torch.equal(out["two"][1], out[mode][1]), mode
 
 
