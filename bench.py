@@ -330,9 +330,10 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         work["stem_resblock2d_persist_kernel"] = {"bound": "tensor", "per_step": B * (slab_first + stem),
                                                   "what": "stem Conv2D(16, 1x1) from the uint8 image + residual block 1's conv pair "
                                                           "at 128 x 151 (TF32), persistent warp-specialised kernel"}
-        work["resblock2d_fused_kernel"]["per_step"] = B * (slab - slab_first - slab_23)
-        work["resblock2d_fused_kernel"]["what"] = ("residual blocks 4-9 (C >= 64): conv pairs (3x3 then 4x1, TF32, tap-shifted "
-                                                   "slabs, the intermediate stays in shared memory)")
+        if os.environ.get("MMLA_NET_PERSIST") == "2":        # blocks 2-3 on the persistent kernel as well
+            work["resblock2d_fused_kernel"]["per_step"] = B * (slab - slab_first - slab_23)
+            work["resblock2d_fused_kernel"]["what"] = ("residual blocks 4-9 (C >= 64): conv pairs (3x3 then 4x1, TF32, tap-shifted "
+                                                       "slabs, the intermediate stays in shared memory)")
         work["conv_tc_kernel"] = {"bound": "tensor", "per_step": B * (res - slab),
                                   "what": "the three stride-2 1x1 shortcut convs (TF32, im2col gather)"}
         work["pool_shortcut_kernel"] = {"bound": "hbm", "per_step": B * pool_bytes,
