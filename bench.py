@@ -467,11 +467,12 @@ def main():
         """`steps` passes through the public host API.  Every pass uploads its own PCM from pinned
         host memory and reads its own labels + tallies back; up to `--e2e-depth` passes are in
         flight so the upload of pass k+1 overlaps the compute of pass k."""
-        if a.workload == "speaker_id":
+        if a.workload in ("speaker_id", "overlap"):
             from collections import deque
             pend = deque()
+            chunks = a.e2e_chunks if a.workload == "speaker_id" else 1      # overlap is compute-bound: whole batches
             for _ in range(steps):
-                pend.append(pipe.submit_host(pcm_host, n_classes, n_chunks=a.e2e_chunks, depth=a.e2e_depth + 1,
+                pend.append(pipe.submit_host(pcm_host, n_classes, n_chunks=chunks, depth=a.e2e_depth + 1,
                                              reduce=e2e_reduce if world > 1 else None))
                 if len(pend) >= a.e2e_depth:
                     e2e_finish(pend.popleft())
@@ -642,17 +643,28 @@ def main():
                 lab, cnt = exchange_labels_and_counts(lab, cnt, Bo * world, rank, world)
             return lab, cnt
 
-        def ostep_e2e():
-            po_dev.copy_(po_host, non_blocking=True)
-            lab, cnt = ostep(po_dev)
-            lab.cpu(), cnt.cpu()
+        def o_reduce(labels_dev, counts_dev):
+            return exchange_labels_and_counts(labels_dev, counts_dev, Bo * world, rank, world)
+
+        def ostep_e2e(n=1):
+            # the public host API, as for the speaker workload: every pass uploads its own PCM from pinned host memory and
+            # reads its own labels + tallies back; two passes in flight, one slice per pass (the path is compute-bound)
+            from collections import deque
+            pend = deque()
+            for _ in range(n):
+                pend.append(opipe.submit_host(po_host, 2, n_chunks=1, depth=3, reduce=o_reduce if world > 1 else None))
+                if len(pend) >= 2:
+                    pend.popleft().result()
+            while pend:
+                pend.popleft().result()
 
         for _ in range(3):
             ostep(po)
         n_o = max(5, a.steps // 2)
         ms_o = timed(lambda: ostep(po), n_o)
-        ostep_e2e()
-        ms_oe = timed(ostep_e2e, max(3, n_o // 2))
+        ostep_e2e(2)
+        n_oe = max(4, n_o // 2)
+        ms_oe = timed(lambda: ostep_e2e(n_oe), 1) / n_oe
         tr = _lib.trace_launches(lambda: [ostep(po) for _ in range(3)], torch)
         barrier()
         ok = kernel_rooflines(tr, 3, ms_o, kernel_work("overlap", Bo, Lo, opipe, 0))

@@ -71,7 +71,86 @@ class PendingResult:
         return self._slot["labels_h"].numpy().copy(), self._slot["counts_h"].numpy().copy()
 
 
-class SpeakerPipeline:
+class _HostApi:
+    """Host-buffer entry points shared by both pipelines (they only need ``self.run_device``)."""
+
+    def submit_host(self, pcm_host, n_classes: int, n_chunks: int = 2, depth: int = 3, reduce=None):
+        """Asynchronous end-to-end pass from HOST memory: ``pcm_host`` int16 [B, L] (pinned for
+        full speed).  The batch is cut into ``n_chunks`` slices; a copy stream uploads slice i+1
+        while slice i runs features + classifier on the compute stream, and the labels + tallies
+        are read back into pinned host buffers behind the last slice.  Nothing blocks the host:
+        the call returns a :class:`PendingResult`; up to ``depth`` submissions may be in flight, so
+        the upload of batch k+1 overlaps the compute of batch k (the recording loop of the
+        reference scripts, pipelined).  ``PendingResult.result()`` waits for that batch only.
+        ``pcm_host`` is read asynchronously: do not modify it before ``PendingResult.wait_uploaded()``.
+
+        ``reduce(labels_dev, counts_dev) -> (labels_all, counts_all)``: optional device-side step run
+        on the compute stream before the read-back — the multi-GPU label all_gather / tally
+        all_reduce, one collective (``sharding.exchange_labels_and_counts``); its outputs are what is
+        copied to the host."""
+        torch = _lib.require_cuda()
+        B, L = pcm_host.shape
+        n_chunks = max(1, min(n_chunks, B))
+        bounds = [(B * i) // n_chunks for i in range(n_chunks + 1)]
+        cmax = max(bounds[i + 1] - bounds[i] for i in range(n_chunks))
+        key = (B, cmax, L, n_classes, depth)
+        if getattr(self, "_stage_key", None) != key:
+            nbuf = 3
+            self._stage = [torch.empty((cmax, L), dtype=torch.int16, device="cuda") for _ in range(nbuf)]
+            self._stage_free = [None] * nbuf            # event: last consumer of the buffer is done
+            self._stage_next = 0
+            self._copy_stream = torch.cuda.Stream()
+            self._slots = [dict(labels=torch.empty((B,), dtype=torch.int32, device="cuda"),
+                                labels_h=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                                counts_h=torch.empty((n_classes + 1,), dtype=torch.int64).pin_memory(),
+                                done=None, generation=0, fetched=True) for _ in range(depth)]
+            self._slot_next = 0
+            self._stage_key = key
+        slot = self._slots[self._slot_next]
+        self._slot_next = (self._slot_next + 1) % len(self._slots)
+        if slot["done"] is not None:
+            slot["done"].synchronize()                  # the slot's previous batch must have finished
+        slot["generation"] += 1                         # handles of the slot's previous batch now raise
+        slot["fetched"] = False
+        compute = torch.cuda.current_stream()
+        uploaded = None
+        labels = slot["labels"]
+        for i in range(n_chunks):
+            lo, hi = bounds[i], bounds[i + 1]
+            k = self._stage_next
+            self._stage_next = (k + 1) % len(self._stage)
+            buf = self._stage[k][: hi - lo]
+            copied = torch.cuda.Event()
+            with torch.cuda.stream(self._copy_stream):
+                if self._stage_free[k] is not None:
+                    self._copy_stream.wait_event(self._stage_free[k])
+                buf.copy_(pcm_host[lo:hi], non_blocking=True)
+                copied.record(self._copy_stream)
+            uploaded = copied
+            compute.wait_event(copied)
+            lab, _ = self.run_device(buf)
+            labels[lo:hi] = lab
+            free = torch.cuda.Event()
+            free.record(compute)
+            self._stage_free[k] = free
+        counts = tally.device_counts(labels, n_classes)
+        labels_out, counts_out = (labels, counts) if reduce is None else reduce(labels, counts)
+        if slot["labels_h"].numel() != labels_out.numel():
+            slot["labels_h"] = torch.empty((labels_out.numel(),), dtype=torch.int32).pin_memory()
+        slot["labels_h"].copy_(labels_out.reshape(-1), non_blocking=True)
+        slot["counts_h"].copy_(counts_out, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        slot["done"] = done
+        return PendingResult(slot, done, uploaded, slot["generation"])
+
+    def run_host(self, pcm_host, n_classes: int, n_chunks: int = 2):
+        """Synchronous form of :meth:`submit_host`: returns (labels int32 numpy [B], counts int64
+        numpy [n_classes+1])."""
+        return self.submit_host(pcm_host, n_classes, n_chunks).result()
+
+
+class SpeakerPipeline(_HostApi):
     def __init__(self, model: Model, cfg: MfccConfig = MfccConfig(), n_streams: int = 1, split_min_clips: int = 1024):
         """``n_streams`` > 1: batches of at least ``split_min_clips`` clips are cut into that many slices that
         run on their own CUDA streams, so kernels that cannot fill the GPU on their own (the persistent
@@ -175,81 +254,6 @@ class SpeakerPipeline:
         prob[idx] = p_live
         return labels, prob
 
-    def submit_host(self, pcm_host, n_classes: int, n_chunks: int = 2, depth: int = 3, reduce=None):
-        """Asynchronous end-to-end pass from HOST memory: ``pcm_host`` int16 [B, L] (pinned for
-        full speed).  The batch is cut into ``n_chunks`` slices; a copy stream uploads slice i+1
-        while slice i runs features + classifier on the compute stream, and the labels + tallies
-        are read back into pinned host buffers behind the last slice.  Nothing blocks the host:
-        the call returns a :class:`PendingResult`; up to ``depth`` submissions may be in flight, so
-        the upload of batch k+1 overlaps the compute of batch k (the recording loop of the
-        reference scripts, pipelined).  ``PendingResult.result()`` waits for that batch only.
-        ``pcm_host`` is read asynchronously: do not modify it before ``PendingResult.wait_uploaded()``.
-
-        ``reduce(labels_dev, counts_dev) -> (labels_all, counts_all)``: optional device-side step run
-        on the compute stream before the read-back — the multi-GPU label all_gather / tally
-        all_reduce, one collective (``sharding.exchange_labels_and_counts``); its outputs are what is
-        copied to the host."""
-        torch = _lib.require_cuda()
-        B, L = pcm_host.shape
-        n_chunks = max(1, min(n_chunks, B))
-        bounds = [(B * i) // n_chunks for i in range(n_chunks + 1)]
-        cmax = max(bounds[i + 1] - bounds[i] for i in range(n_chunks))
-        key = (B, cmax, L, n_classes, depth)
-        if getattr(self, "_stage_key", None) != key:
-            nbuf = 3
-            self._stage = [torch.empty((cmax, L), dtype=torch.int16, device="cuda") for _ in range(nbuf)]
-            self._stage_free = [None] * nbuf            # event: last consumer of the buffer is done
-            self._stage_next = 0
-            self._copy_stream = torch.cuda.Stream()
-            self._slots = [dict(labels=torch.empty((B,), dtype=torch.int32, device="cuda"),
-                                labels_h=torch.empty((B,), dtype=torch.int32).pin_memory(),
-                                counts_h=torch.empty((n_classes + 1,), dtype=torch.int64).pin_memory(),
-                                done=None, generation=0, fetched=True) for _ in range(depth)]
-            self._slot_next = 0
-            self._stage_key = key
-        slot = self._slots[self._slot_next]
-        self._slot_next = (self._slot_next + 1) % len(self._slots)
-        if slot["done"] is not None:
-            slot["done"].synchronize()                  # the slot's previous batch must have finished
-        slot["generation"] += 1                         # handles of the slot's previous batch now raise
-        slot["fetched"] = False
-        compute = torch.cuda.current_stream()
-        uploaded = None
-        labels = slot["labels"]
-        for i in range(n_chunks):
-            lo, hi = bounds[i], bounds[i + 1]
-            k = self._stage_next
-            self._stage_next = (k + 1) % len(self._stage)
-            buf = self._stage[k][: hi - lo]
-            copied = torch.cuda.Event()
-            with torch.cuda.stream(self._copy_stream):
-                if self._stage_free[k] is not None:
-                    self._copy_stream.wait_event(self._stage_free[k])
-                buf.copy_(pcm_host[lo:hi], non_blocking=True)
-                copied.record(self._copy_stream)
-            uploaded = copied
-            compute.wait_event(copied)
-            lab, _ = self.run_device(buf)
-            labels[lo:hi] = lab
-            free = torch.cuda.Event()
-            free.record(compute)
-            self._stage_free[k] = free
-        counts = tally.device_counts(labels, n_classes)
-        labels_out, counts_out = (labels, counts) if reduce is None else reduce(labels, counts)
-        if slot["labels_h"].numel() != labels_out.numel():
-            slot["labels_h"] = torch.empty((labels_out.numel(),), dtype=torch.int32).pin_memory()
-        slot["labels_h"].copy_(labels_out.reshape(-1), non_blocking=True)
-        slot["counts_h"].copy_(counts_out, non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(compute)
-        slot["done"] = done
-        return PendingResult(slot, done, uploaded, slot["generation"])
-
-    def run_host(self, pcm_host, n_classes: int, n_chunks: int = 2):
-        """Synchronous form of :meth:`submit_host`: returns (labels int32 numpy [B], counts int64
-        numpy [n_classes+1])."""
-        return self.submit_host(pcm_host, n_classes, n_chunks).result()
-
     def run_session(self, pcm_long, speaker_names: Dict[int, str], t0: Optional[datetime] = None,
                     silent_index=(), log_path: Optional[str] = None):
         """Offline session: MFCC-39 over the whole recording, 256-frame chunks, one predict,
@@ -317,7 +321,7 @@ class SpeakerPipeline:
         return labels, tally.tally_session(labels, speaker_names, t0 or datetime.today(), 2.56, add_before_first=True)
 
 
-class OverlapPipeline:
+class OverlapPipeline(_HostApi):
     def __init__(self, model: Model):
         if model.spec.ndim != 2:
             raise ValueError("OverlapPipeline needs the overlap net")
