@@ -41,7 +41,7 @@ namespace {
 // the leader's `pfull` barriers; `empty` / `accum` are arrived in both CTAs by multicast commits; cluster barriers replace the
 // CTA barriers where the leader's MMAs read the peer's slab.
 template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false, bool PAIR = false>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : 2) resblock2d_fused_kernel(const RbArgs a) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS == 512 && RES ? 1 : 2)) resblock2d_fused_kernel(const RbArgs a) {
     constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                 (static_cast<uint32_t>((PAIR ? 256 : 128) >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M
     constexpr uint32_t kChunkBytes = 8 * NT * 16 / (PAIR ? 2 : 1);
@@ -641,8 +641,10 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
         const int budgets_kb[3] = {75, 113, 226};
         const double overlap[3] = {4.5, 3.2, 1.0};
         for (int bi = res ? 1 : 0; bi < 3; ++bi) {
-            const int nthr = res || img || bi == 0 ? 256 : 512;
+            // (a residual's prefetch holds 40 more registers: 256 threads at two CTAs per SM, 512 when the CTA has the SM alone)
+            const int nthr = img || bi == 0 || (res && bi == 1) ? 256 : 512;
             const int ctas = 3 - bi;
+            if (force_kb >= 16 && force_kb <= 226 && force_kb > budgets_kb[bi]) continue;   // a forced budget that large means fewer CTAs per SM
             const size_t budget = static_cast<size_t>(force_kb >= 16 && force_kb <= 226 ? force_kb : budgets_kb[bi]) * 1024;
             for (int t = 1; t <= tmax; ++t) {
                 if (force_t >= 1 && force_t <= tmax && t != force_t) continue;
@@ -726,6 +728,13 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                        : launch_rb<128, false, 512, false, false, true>(s, B, smem, st);
     }
     if (res) {
+        if (best_thr == 512) {
+            switch (C) {
+                case 32: return launch_rb<32, true, 512>(s, B, smem, st);
+                case 64: return launch_rb<64, true, 512>(s, B, smem, st);
+                default: return launch_rb<128, true, 512>(s, B, smem, st);
+            }
+        }
         switch (C) {
             case 32: return launch_rb<32, true, 256>(s, B, smem, st);
             case 64: return launch_rb<64, true, 256>(s, B, smem, st);
