@@ -61,7 +61,7 @@ struct Smem {
     alignas(16) float tabS[2][kChunk][kBinsPad];
     float M[kMaxMels][kMStride];
     float zcr[kFrames + 1];
-    double zcr255[kFrames + 1];
+    uint32_t zq[kFrames + 1];                      // image channel 0 per frame: (uint8) trunc(float64(zcr) * 255), computed once
     float red[kThreads / 32];
     float bcast[4];
     int mel_start[kMaxMels], mel_len[kMaxMels], mel_off[kMaxMels];
@@ -152,8 +152,7 @@ __device__ __forceinline__ void finish_clip(SmemT& s, const Params& p, long long
                 const int r = pix / kFrames, t = pix - r * kFrames;
                 uint32_t q = 0u;                                      // (x*255).astype(uint8): truncation
                 if (c == 0) {
-                    const double v255 = s.zcr255[t];
-                    q = (v255 >= 0.0) ? static_cast<uint32_t>(static_cast<int>(v255)) & 0xFFu : 0u;
+                    q = s.zq[t];                                      // (151 FP64 conversions per clip instead of 19 328)
                 } else {
                     // trunc(float64(v) * 255) for the float32 v = 1 - nrm in [0, 1] in integer arithmetic: the 24-bit
                     // significand times 255 fits 32 bits, so the result is exact (FP64 multiplies are slow on this part).
@@ -226,7 +225,10 @@ __global__ void __launch_bounds__(kThreads, 1) overlap_features_kernel(const __g
             }
             const double z = static_cast<double>(cnt) / 400.0;      // np.mean over 400 booleans
             s.zcr[tid] = static_cast<float>(z);
-            s.zcr255[tid] = z * 255.0;
+            {
+                const double v255 = z * 255.0;
+                s.zq[tid] = (v255 >= 0.0) ? static_cast<uint32_t>(static_cast<int>(v255)) & 0xFFu : 0u;
+            }
             if (p.zcr) p.zcr[clip * kFrames + tid] = static_cast<float>(z);
         }
 
@@ -376,7 +378,7 @@ struct SmemTc {
     alignas(16) int16_t pcm[kClip + 16];
     float M[kMaxMels][kMStride];
     float zcr[kFrames + 1];
-    double zcr255[kFrames + 1];
+    uint32_t zq[kFrames + 1];                      // image channel 0 per frame: (uint8) trunc(float64(zcr) * 255), computed once
     float red[kTcThreads / 32];
     int mel_start[kMaxMels], mel_len[kMaxMels], mel_off[kMaxMels];
     float mel_w[kMaxMelNnz];
@@ -535,7 +537,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) overlap_features_tc_kernel(cons
             if (tid < kFrames) {
                 const double z = static_cast<double>(zc[448 + 2 * tid + 1] - zc[448 + 2 * tid]) / 400.0;
                 s.zcr[tid] = static_cast<float>(z);
-                s.zcr255[tid] = z * 255.0;
+                {
+                    const double v255 = z * 255.0;
+                    s.zq[tid] = (v255 >= 0.0) ? static_cast<uint32_t>(static_cast<int>(v255)) & 0xFFu : 0u;
+                }
                 if (p.zcr) p.zcr[clip * kFrames + tid] = static_cast<float>(z);
             }
             __syncthreads();
