@@ -111,7 +111,8 @@ __device__ __forceinline__ float block_reduce(SmemT& s, float v, bool is_max) {
 // power_to_db(ref=max, amin=1e-10, top_db=80) + normalize_matrix + the three outputs, from the clip's mel tile s.M
 // (overlap_features_generator.py:82-83,103-117,142-151); every thread of the CTA takes part.
 template <int NT, class SmemT>
-__device__ __forceinline__ void finish_clip(SmemT& s, const Params& p, long long clip, int n_mels, int tid) {
+__device__ __forceinline__ void finish_clip(SmemT& s, const Params& p, long long clip, int n_mels, int tid, unsigned char* scratch,
+                                            int scratch_dirty_bytes) {
     const int total = n_mels * kFrames;
     float vmax = 0.f;
     for (int e = tid; e < total; e += NT) vmax = fmaxf(vmax, s.M[e / kFrames][e % kFrames]);
@@ -140,32 +141,52 @@ __device__ __forceinline__ void finish_clip(SmemT& s, const Params& p, long long
         for (int e = tid; e < total; e += NT) dst[e] = (s.M[e / kFrames][e % kFrames] - vmin) / diff;
     }
     if (p.image) {
-        // uint8 [n_mels][151][3], row r = mel (n_mels-1-r); value trunc(float64(v) * 255)
-        uint32_t* dst = reinterpret_cast<uint32_t*>(p.image + clip * static_cast<long long>(total) * 3);
-        const int words = total * 3 / 4;
-        for (int wd = tid; wd < words; wd += NT) {
-            uint32_t packed = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int byte = 4 * wd + b;
-                const int pix = byte / 3, c = byte - 3 * pix;
+        // uint8 [n_mels][151][3], row r = mel (n_mels-1-r); value trunc(float64(v) * 255).  Channels 1 and 2 carry the same
+        // value, channel 0 the frame's ZCR byte: one quantisation per PIXEL into a shared-memory copy of the image, then
+        // 16-byte stores (packing per 32-bit word of the row-major byte stream cost ~200 instructions per word: two
+        // divisions and a quantisation per byte — 45 % of the kernel's stall samples, profiles/r02/overlap_features_tc_v2_*).
+        auto quant = [&](int r, int t) -> uint32_t {
+            // trunc(float64(v) * 255) for the float32 v = 1 - nrm in [0, 1] in integer arithmetic: the 24-bit significand
+            // times 255 fits 32 bits, so the result is exact (FP64 multiplies are slow on this part).  NaN (constant
+            // clip), negatives and values below 2^-8 map to 0 exactly as the float64 path did.
+            const float nrm = (s.M[n_mels - 1 - r][t] - vmin) / diff;
+            const uint32_t bits = __float_as_uint(1.0f - nrm);
+            const int ex = static_cast<int>((bits >> 23) & 0xFFu);
+            uint32_t q = 0u;
+            if (!(bits >> 31) && ex != 0xFF && ex >= 119) q = ex >= 127 ? 255u : ((((bits & 0x7FFFFFu) | 0x800000u) * 255u) >> (150 - ex));
+            return q & 0xFFu;
+        };
+        uint8_t* gimg = p.image + clip * static_cast<long long>(total) * 3;
+        const int bytes = total * 3;
+        if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gimg) & 15) == 0) {
+            for (int pix = tid; pix < total; pix += NT) {
                 const int r = pix / kFrames, t = pix - r * kFrames;
-                uint32_t q = 0u;                                      // (x*255).astype(uint8): truncation
-                if (c == 0) {
-                    q = s.zq[t];                                      // (151 FP64 conversions per clip instead of 19 328)
-                } else {
-                    // trunc(float64(v) * 255) for the float32 v = 1 - nrm in [0, 1] in integer arithmetic: the 24-bit
-                    // significand times 255 fits 32 bits, so the result is exact (FP64 multiplies are slow on this part).
-                    // NaN (constant clip), negatives and values below 2^-8 map to 0 exactly as the float64 path did.
-                    const float nrm = (s.M[n_mels - 1 - r][t] - vmin) / diff;
-                    const uint32_t bits = __float_as_uint(1.0f - nrm);
-                    const int ex = static_cast<int>((bits >> 23) & 0xFFu);
-                    if (!(bits >> 31) && ex != 0xFF && ex >= 119)
-                        q = ex >= 127 ? 255u : ((((bits & 0x7FFFFFu) | 0x800000u) * 255u) >> (150 - ex));
-                }
-                packed |= (q & 0xFFu) << (8 * b);
+                const uint32_t g = quant(r, t);
+                scratch[3 * pix] = static_cast<uint8_t>(s.zq[t]);
+                scratch[3 * pix + 1] = static_cast<uint8_t>(g);
+                scratch[3 * pix + 2] = static_cast<uint8_t>(g);
             }
-            dst[wd] = packed;
+            __syncthreads();
+            const uint4* src = reinterpret_cast<const uint4*>(scratch);
+            uint4* dst = reinterpret_cast<uint4*>(gimg);
+            for (int i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
+            __syncthreads();
+            // the part of the scratch that doubles as a tensor-core operand ring must hold finite values again
+            for (int i = tid; i < scratch_dirty_bytes / 16; i += NT) reinterpret_cast<uint4*>(scratch)[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(gimg);   // odd sizes: per 32-bit word of the byte stream
+            const int words = bytes / 4;
+            for (int wd = tid; wd < words; wd += NT) {
+                uint32_t packed = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int byte = 4 * wd + b;
+                    const int pix = byte / 3, c = byte - 3 * pix;
+                    const int r = pix / kFrames, t = pix - r * kFrames;
+                    packed |= (c == 0 ? (s.zq[t] & 0xFFu) : quant(r, t)) << (8 * b);
+                }
+                dst[wd] = packed;
+            }
         }
     }
     __syncthreads();
@@ -338,7 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) overlap_features_kernel(const __g
         }
         __syncthreads();
 
-        finish_clip<kThreads>(s, p, clip, n_mels, tid);
+        // scratch: Ae | Ao | tabC | tabS are contiguous (78 KB >= the 58 KB image) and rewritten by the next tile before use
+        finish_clip<kThreads>(s, p, clip, n_mels, tid, reinterpret_cast<unsigned char*>(&s.Ae[0][0]), 0);
     }
 }
 
@@ -387,6 +409,8 @@ struct SmemTc {
     uint32_t tmem_base;
 };
 static_assert(sizeof(SmemTc) <= 227 * 1024, "SmemTc exceeds the 227 KB a CTA can own");
+static_assert(offsetof(SmemTc, b) == kStages * kStageA && kStages * (kStageA + kStageB) >= kMaxMels * kFrames * 3,
+              "the image scratch needs the A and B rings back to back");
 
 __device__ __forceinline__ bool elect_one_tc() {
     uint32_t pred;
@@ -690,7 +714,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) overlap_features_tc_kernel(cons
             }
             ++tiles_done;
         }
-        finish_clip<kTcThreads>(s, p, clip, n_mels, tid);
+        // scratch: the A and B operand rings are contiguous (87 KB >= the 58 KB image) and idle here
+        finish_clip<kTcThreads>(s, p, clip, n_mels, tid, &s.a[0][0], kStages * kStageA);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
