@@ -49,9 +49,17 @@ struct RbArgs {
 };
 
 __device__ __forceinline__ uint32_t rb_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+// try_wait with a suspend-time hint: the warp is parked in hardware instead of spinning through the issue slots of the
+// working warps (the persistent kernel has up to twenty warps waiting at a time); traps instead of hanging on a logic error.
 __device__ __forceinline__ void rb_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t i = 0; i < (1u << 24); ++i)
-        if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
+                     : "memory");
+        if (ok) return;
+    }
     asm volatile("trap;");
 }
 // BN + ELU + TF32 rounding of one element: the expression of conv_slab.cu's fill (bit-identical results).
