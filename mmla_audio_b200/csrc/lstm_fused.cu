@@ -46,7 +46,7 @@ constexpr int kSubTile = 128 * 128;         // bytes of one 128x32 TF32 sub-tile
 constexpr int kBChunkFloats = 4 * 256 * 4;  // one weight chunk = two MMAs: 4 K-slabs (K=16) x 256 columns x 4
 constexpr int kBChunkBytes = kBChunkFloats * 4;   // 16 KB
 constexpr int kChunksPerStep = 64;          // 4 passes x 8 K-sub-tiles x 2 halves
-constexpr int kStages = 4;
+constexpr int kStages = 6;                   // 96 KB in flight: the stream into a CTA is ring bytes / ~2 000 cycles of L2 latency
 constexpr int kEpiThreads = 256;            // warps 0..7: gate epilogue + h re-staging
 constexpr int kProducers = 2;               // TMA producer warps (see the producer loop)
 constexpr int kThreads = kEpiThreads + 32 + 32 * kProducers;  // warp 8: MMA issuer, warps 9..: TMA producers
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             // Ring position as counters, descriptors advanced by adds, two chunks (4 MMAs) per trip: what sits between
             // the last MMA of a trip and the first of the next is a bubble once the tensor pipe's short queue (~4
             // MMAs) has drained — with one chunk (2 MMAs, 256 cycles) per trip a pass took 7.7k cycles instead of 4.1k.
-            static_assert(kStages == 4, "chunk pairs use stages {0,1} and {2,3}");
+            static_assert(kStages % 2 == 0, "chunk pairs use stages {0,1}, {2,3}, ...");
             int stg = 0;
             uint32_t par = 0;
             const uint64_t dB0 = desc_noswz(smem_u32(&s.Bst[0][0]), 256 * 16, 128);
@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                             umma_commit_to(&s.empty[stg + 1]);
                             if (kc == 7) umma_commit_to(&s.tfull[buf]);
                         }
-                        stg ^= 2;
-                        if (stg == 0) par ^= 1u;
+                        stg += 2;
+                        if (stg == kStages) { stg = 0; par ^= 1u; }
                     }
                     if (lane == 0) stamp(rs + 1, 9 + pass);
                 }
