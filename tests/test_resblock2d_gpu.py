@@ -75,6 +75,9 @@ BLOCKS = [  # (H, W, Cin, C, residual, B)
     (37, 1, 64, 32, True, 4),          # one column
     (2, 3, 128, 128, True, 1),
     (128, 151, 16, 32, True, 1),       # Cin != C with a residual of C channels (generic entry)
+    (2, 3, 64, 64, False, 2),          # smallest pooled block (H = 2): row-pooled epilogue on a one-tile image
+    (6, 5, 16, 32, False, 3),          # tiny block-1 shape: persistent kernel with fewer work items than SMs
+    (33, 9, 32, 32, False, 2),         # odd height: no row pooling, 36-row columns
 ]
 
 
