@@ -70,6 +70,8 @@ __device__ __forceinline__ uint32_t rb_bn_elu_tf32(float v, float sc, float sh) 
     v = v > 0.f ? v : e - 1.f;
     return rb_tf32(v);
 }
+// uint8 -> float without the quarter-rate I2F pipe: 0x4B000000 | v is the float 2^23 + v; the subtraction is exact.
+__device__ __forceinline__ float rb_u8_to_float(unsigned char v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 __device__ __forceinline__ uint64_t rb_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return static_cast<uint64_t>((addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16) |
            (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);

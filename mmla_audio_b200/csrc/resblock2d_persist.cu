@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) resblock2d_persist_kernel(const
                         ok[u] = r < rows && p >= 0 && w >= 0 && w < a.W && h >= 0 && h < a.H;
                         const long long px = ok[u] ? static_cast<long long>(h * a.W + w) * 3 : 0ll;
                         if (a.img_is_u8) {
-                            c[u][0] = static_cast<float>(img8[px]); c[u][1] = static_cast<float>(img8[px + 1]); c[u][2] = static_cast<float>(img8[px + 2]);
+                            c[u][0] = rb_u8_to_float(img8[px]); c[u][1] = rb_u8_to_float(img8[px + 1]); c[u][2] = rb_u8_to_float(img8[px + 2]);
                         } else {
                             c[u][0] = imgf[px]; c[u][1] = imgf[px + 1]; c[u][2] = imgf[px + 2];
                         }
