@@ -330,6 +330,12 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         work["stem_resblock2d_persist_kernel"] = {"bound": "tensor", "per_step": B * (slab_first + stem),
                                                   "what": "stem Conv2D(16, 1x1) from the uint8 image + residual block 1's conv pair "
                                                           "at 128 x 151 (TF32), persistent warp-specialised kernel"}
+        work["resblock2d_f16_kernel"] = {"bound": "tensor", "per_step": B * (slab - slab_first),
+                                         "what": "residual blocks 2-9: conv pairs with fp16 operands / fp32 accumulation "
+                                                 "(precision fp16): 16 convolutions in 8 launches"}
+        work["stem_resblock2d_f16_kernel"] = {"bound": "tensor", "per_step": B * (slab_first + stem),
+                                              "what": "stem Conv2D(16, 1x1) from the uint8 image + residual block 1's conv pair "
+                                                      "at 128 x 151, fp16 operands / fp32 accumulation"}
         if os.environ.get("MMLA_NET_PERSIST") == "2":        # blocks 2-3 on the persistent kernel as well
             work["resblock2d_fused_kernel"]["per_step"] = B * (slab - slab_first - slab_23)
             work["resblock2d_fused_kernel"]["what"] = ("residual blocks 4-9 (C >= 64): conv pairs (3x3 then 4x1, TF32, tap-shifted "
@@ -355,7 +361,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="speaker_id", choices=sorted(WORKLOADS))
     ap.add_argument("--clips", type=int, default=0, help="clips per GPU (default: workload's)")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp16"],
                     help="classifier matmul arithmetic: tf32 = tcgen05 tensor cores, fp32 = CUDA cores")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="host pipeline: upload/compute overlap slices per pass")
     ap.add_argument("--e2e-depth", type=int, default=2, help="host pipeline: passes in flight (1 = synchronous)")
@@ -540,7 +546,9 @@ def main():
                     "algorithmic_flop_per_step": w["per_step"], "what": w["what"], "launch_ms": launch_ms,
                     "launches_per_step": dom["launches_per_step"], "share_of_step": dom["share_of_step"],
                     "peak_source": peaks["source"] + " cuBLAS bf16 sustained (the kernel computes in "
-                                   + ("tf32, nominal peak half of bf16)" if a.precision == "tf32" else "fp32 on CUDA cores)")}
+                                   + ("tf32, nominal peak half of bf16)" if a.precision == "tf32" else
+                                      "fp16 operands, fp32 accumulation: the same nominal peak as bf16)" if a.precision == "fp16" else
+                                      "fp32 on CUDA cores)")}
     # the HBM-bound feature kernel is the metric's second half ("HBM GB/s as % of peak"): always reported
     for k in kernels:
         wk = work.get(k["kernel"])
@@ -628,7 +636,8 @@ def main():
     # ---- secondary workloads in the same line, so the driver's BENCH / SCALE records carry them at every N ------
     if a.workload == "speaker_id" and not a.no_extra:
         del pcm_dev2
-        # (1) overlap path (BASELINE configs[0]/[3]): 512 clips of 1.5 s per GPU, TF32 classifier
+        # (1) overlap path (BASELINE configs[0]/[3]): 512 clips of 1.5 s per GPU; classifier in its "fp16" mode (conv pairs with
+        #     fp16 operands / fp32 accumulation, same parity bars as TF32: tests/test_r02_parity_gpu.py) and in "tf32"
         Bo, Lo = 512, 24000
         po = synth.synth_clips(20_000_000 + rank * Bo, Bo, Lo)
         po_host = torch.empty((Bo, Lo), dtype=torch.int16).pin_memory()
@@ -658,27 +667,36 @@ def main():
             while pend:
                 pend.popleft().result()
 
-        for _ in range(3):
-            ostep(po)
-        n_o = max(5, a.steps // 2)
-        ms_o = timed(lambda: ostep(po), n_o)
-        ostep_e2e(2)
-        n_oe = max(4, n_o // 2)
-        ms_oe = timed(lambda: ostep_e2e(n_oe), 1) / n_oe
-        tr = _lib.trace_launches(lambda: [ostep(po) for _ in range(3)], torch)
-        barrier()
-        ok = kernel_rooflines(tr, 3, ms_o, kernel_work("overlap", Bo, Lo, opipe, 0))
-        extra["overlap_1.5s_x512"] = {
-            "clips_per_gpu": Bo, "ms_per_step": ms_o, "audio_s_per_s": world * Bo * Lo / SR / (ms_o * 1e-3),
-            "e2e_audio_s_per_s": world * Bo * Lo / SR / (ms_oe * 1e-3), "e2e_ms_per_step": ms_oe,
-            "classifier_precision": "tf32", "kernels": ok[:6]}
-        summary["overlap_x512_audio_s_per_s"] = round(world * Bo * Lo / SR / (ms_o * 1e-3), 1)
-        summary["overlap_x512_e2e_audio_s_per_s"] = round(world * Bo * Lo / SR / (ms_oe * 1e-3), 1)
-        for row in ok:
-            if row["kernel"] in ("conv_slab_kernel", "resblock2d_fused_kernel", "resblock2d_persist_kernel",
-                                 "stem_resblock2d_persist_kernel", "overlap_features_kernel",
-                                 "overlap_features_tc_kernel") and "frac" in row:
-                summary["overlap_%s_frac" % row["kernel"]] = round(row["frac"], 4)
+        by_prec = {}
+        for prec in ("tf32", "fp16"):
+            opipe.model.set_precision(prec)
+            for _ in range(3):
+                ostep(po)
+            n_o = max(5, a.steps // 2)
+            ms_o = timed(lambda: ostep(po), n_o)
+            ostep_e2e(2)
+            n_oe = max(4, n_o // 2)
+            ms_oe = timed(lambda: ostep_e2e(n_oe), 1) / n_oe
+            tr = _lib.trace_launches(lambda: [ostep(po) for _ in range(3)], torch)
+            barrier()
+            ok = kernel_rooflines(tr, 3, ms_o, kernel_work("overlap", Bo, Lo, opipe, 0))
+            by_prec[prec] = {
+                "clips_per_gpu": Bo, "ms_per_step": ms_o, "audio_s_per_s": world * Bo * Lo / SR / (ms_o * 1e-3),
+                "e2e_audio_s_per_s": world * Bo * Lo / SR / (ms_oe * 1e-3), "e2e_ms_per_step": ms_oe,
+                "classifier_precision": prec, "kernels": ok[:6]}
+        # headline of the overlap path = the fp16-operand mode; the TF32 mode's line rides along
+        extra["overlap_1.5s_x512"] = dict(by_prec["fp16"], tf32=by_prec["tf32"])
+        summary["overlap_x512_audio_s_per_s"] = round(by_prec["fp16"]["audio_s_per_s"], 1)
+        summary["overlap_x512_e2e_audio_s_per_s"] = round(by_prec["fp16"]["e2e_audio_s_per_s"], 1)
+        summary["overlap_x512_classifier_precision"] = "fp16 operands / fp32 accumulation in the conv pairs, tf32 elsewhere"
+        summary["overlap_x512_tf32_audio_s_per_s"] = round(by_prec["tf32"]["audio_s_per_s"], 1)
+        summary["overlap_x512_tf32_e2e_audio_s_per_s"] = round(by_prec["tf32"]["e2e_audio_s_per_s"], 1)
+        for prec in ("tf32", "fp16"):
+            for row in by_prec[prec]["kernels"]:
+                if row["kernel"] in ("conv_slab_kernel", "resblock2d_fused_kernel", "resblock2d_persist_kernel",
+                                     "stem_resblock2d_persist_kernel", "resblock2d_f16_kernel", "stem_resblock2d_f16_kernel",
+                                     "overlap_features_kernel", "overlap_features_tc_kernel") and "frac" in row:
+                    summary["overlap_%s_frac" % row["kernel"]] = round(row["frac"], 4)
         del po, po_dev, po_host, opipe
 
         # (2) BASELINE configs[2] at its stated size: 1 M clips of 2.5 s GLOBAL (nfilt 40, 13 cepstra), sharded over
@@ -778,7 +796,7 @@ def main():
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if (pipe is None or a.precision == "fp32") else "tf32", "data": "synthetic",
+            "dtype": "f32" if (pipe is None or a.precision == "fp32") else ("f16" if a.precision == "fp16" else "tf32"), "data": "synthetic",
             "config": {"workload": wl["name"], "classifier_precision": a.precision if pipe is not None else None,
                        "clips_per_gpu": B, "clip_seconds": L / SR, "global_clips": n_total,
                        "stream_slices": getattr(pipe, "n_streams", 1) if pipe is not None else 1,

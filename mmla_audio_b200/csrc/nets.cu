@@ -233,6 +233,18 @@ __global__ void __launch_bounds__(256) pad_channels_kernel(const float* __restri
 // overlap: Lambda(mean over axis 1 = H): [B,H,W,C] -> [B,W,C]
 // Tail of a pooled res_block of the overlap net (overlap_detector_temp.py:262-270) in one pass:
 //   y = MaxPool2x2/2 'same'(z) + Conv2D(N, 1x1, stride 2)(x) + bias
+// fp16-operand mode: the expressions of resblock2d_common.cuh's rb_bn_elu / rb_pack_h2 (BN + ELU in fp32, saturating half2 pack)
+__device__ __forceinline__ float act_bn_elu(float v, float sc, float sh) {
+    v = fmaf(v, sc, sh);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+    return v > 0.f ? v : e - 1.f;
+}
+__device__ __forceinline__ uint32_t act_pack_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // F2FP.SATFINITE: +-65504 instead of inf
+    return r;
+}
 // z = the block's second conv at full resolution [B,H,W,N], x = the block input [B,H,W,Cin].  One thread owns four output
 // channels of one pooled pixel; the [Cin][N] shortcut weights sit in shared memory; the products are exact fp32 FMAs
 // (K = Cin <= 64 is too short for the tensor-core path to pay: the separate maxpool_kernel + im2col conv_tc_kernel pair
@@ -244,7 +256,11 @@ __global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restr
                                                             float* __restrict__ y, long long B, int H, int W, int Cin, int N,
                                                             const void* __restrict__ img, int img_is_u8,
                                                             const float* __restrict__ stem_w, const float* __restrict__ stem_b,
-                                                            int z_half) {
+                                                            int z_half, unsigned short* __restrict__ ya = nullptr,
+                                                            const float* __restrict__ ya_scale = nullptr,
+                                                            const float* __restrict__ ya_shift = nullptr) {
+    // ya != null (fp16-operand mode): also writes ELU(BN(y)) as fp16 [B,Ho,Wo,N] with the NEXT block's BN1 (ya_scale / ya_shift),
+    // i.e. the next conv-pair kernel's operand, so that its fill is a plain asynchronous copy (resblock2d_fused.cu)
     extern __shared__ float4 wsm4[];                  // [Cin][N / 4] (+ stem mode: [4][16] = w0 | w1 | w2 | bias)
     for (int i = threadIdx.x; i < Cin * N / 4; i += blockDim.x) wsm4[i] = reinterpret_cast<const float4*>(ws)[i];
     float* stem_s = reinterpret_cast<float*>(wsm4 + Cin * N / 4);
@@ -320,12 +336,22 @@ __global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restr
                 a.x = fmaf(xv.w, w3v.x, a.x); a.y = fmaf(xv.w, w3v.y, a.y); a.z = fmaf(xv.w, w3v.z, a.z); a.w = fmaf(xv.w, w3v.w, a.w);
             }
         }
+        float4 ysc = make_float4(0.f, 0.f, 0.f, 0.f), ysh = ysc;
+        if (ya) {
+            ysc = *reinterpret_cast<const float4*>(ya_scale + 4 * q);
+            ysh = *reinterpret_cast<const float4*>(ya_shift + 4 * q);
+        }
 #pragma unroll
         for (int u = 0; u < kPix; ++u) {
             const int wo = kPix * g + u;
-            if (wo < Wo)
-                *reinterpret_cast<float4*>(y + ((b * Ho + ho) * Wo + wo) * N + 4 * q) =
-                    make_float4(m[u].x + acc[u].x, m[u].y + acc[u].y, m[u].z + acc[u].z, m[u].w + acc[u].w);
+            if (wo < Wo) {
+                const float4 o = make_float4(m[u].x + acc[u].x, m[u].y + acc[u].y, m[u].z + acc[u].z, m[u].w + acc[u].w);
+                *reinterpret_cast<float4*>(y + ((b * Ho + ho) * Wo + wo) * N + 4 * q) = o;
+                if (ya)
+                    *reinterpret_cast<uint2*>(ya + ((b * Ho + ho) * Wo + wo) * N + 4 * q) =
+                        make_uint2(act_pack_h2(act_bn_elu(o.x, ysc.x, ysh.x), act_bn_elu(o.y, ysc.y, ysh.y)),
+                                   act_pack_h2(act_bn_elu(o.z, ysc.z, ysh.z), act_bn_elu(o.w, ysc.w, ysh.w)));
+            }
         }
     }
 }
@@ -500,10 +526,12 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ hf,
 // ---------------------------------------------------------------------------------------------
 // network description + executor
 // ---------------------------------------------------------------------------------------------
+constexpr long long kOvHalfFloats = 64LL * 76 * 32 / 2;   // floats holding one fp16 [64,76,32] activation (the largest conv-pair operand after block 1)
 struct ConvW {
     const float* k = nullptr;
     const float* k_tc = nullptr;          // same weights arranged + TF32-rounded for conv_tc.cu (or null)
     const float* k_tc2 = nullptr;         // ... in the CTA-pair arrangement of resblock2d_fused.cu (overlap net, cout >= 64)
+    const float* k_h = nullptr;           // ... as fp16 chunks for resblock2d_fused.cu's fp16-operand mode (overlap net's conv pairs)
     const float* b = nullptr;
     int kh = 1, kw = 1, cin = 0, cout = 0, stride = 1;
 };
@@ -512,6 +540,7 @@ struct BnW {
     const float* shift = nullptr;
 };
 struct BlockW {
+    typedef const BnW* BnPtr;
     BnW bn1, bn2;
     ConvW conv1, conv2, shortcut;
     bool pool = false;
@@ -564,8 +593,12 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                  long long res_row_stride, cudaStream_t st, const void* img = nullptr, int img_is_u8 = 0,
                                  const float* stem_w = nullptr, const float* stem_b = nullptr, int hpool = 0,
-                                 const float* w1_pair = nullptr, const float* w2_pair = nullptr);
+                                 const float* w1_pair = nullptr, const float* w2_pair = nullptr, const void* w1_h = nullptr,
+                                 const void* w2_h = nullptr, const void* xa = nullptr, void* ya = nullptr,
+                                 const float* ya_scale = nullptr, const float* ya_shift = nullptr);
 void mmla_rb_arrange_weights_pair(const float* w, int K, int N, float* out);
+long long mmla_rb_f16_arranged_halves(int K, int N);
+void mmla_rb_arrange_weights_f16(const float* w, int K, int N, uint16_t* out);
 bool mmla_rb_pair_wanted(int Cin, int C);
 // lstm_fused.cu
 long long mmla_xproj_arranged_floats();
@@ -679,6 +712,17 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
             stage.resize(stage.size() + mmla_tc_arranged_floats(K, c.cout));
             mmla_rb_arrange_weights_pair(wsrc, K, c.cout, stage.data() + off2);
             fixes.push_back({&c.k_tc2, off2});
+        }
+        if (ov && c.cout >= 32 && c.cout <= 128 && c.cin % 16 == 0 && c.kh * c.kw > 1) {
+            // fp16 chunks of the conv pairs (MMLA_PRECISION_F16): the halves ride in the float blob, two per element
+            const long long halves = mmla_rb_f16_arranged_halves(K, c.cout);
+            std::vector<uint16_t> hbuf(static_cast<size_t>(halves));
+            mmla_rb_arrange_weights_f16(wsrc, K, c.cout, hbuf.data());
+            while (stage.size() % 4) stage.push_back(0.f);
+            const long long off3 = static_cast<long long>(stage.size());
+            stage.resize(stage.size() + static_cast<size_t>((halves + 1) / 2));
+            memcpy(stage.data() + off3, hbuf.data(), static_cast<size_t>(halves) * 2);
+            fixes.push_back({&c.k_h, off3});
         }
     };
     auto take_conv = [&](ConvW& c, int kh, int kw, int cin, int cout, int stride) {
@@ -798,7 +842,8 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const long long T = net->seq_len;
     // (the LSTM buffers of the tensor-core path are laid out in whole 128-clip tiles: mmla_net_workspace_bytes rounds up)
-    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 2 * 256 + 6 * 256 + (ov ? 0 : 256 * 40);
+    // (overlap: + two fp16 [64,76,32] buffers = the conv pairs' activated operands of the fp16-operand mode)
+    net->per_clip_floats = 3 * act + T * 128 + 2 * T * 1024 + 1024 + 2 * 256 + 6 * 256 + (ov ? 2 * kOvHalfFloats : 256 * 40);
     net->micro = ov ? 512 : 4096;         // measured on B200: larger micro-batches win (overlap, 512 clips: 24.8 ms at 128, 21.4 ms at 512)
     if (const char* e = getenv("MMLA_NET_MICRO")) {
         const int v = atoi(e);
@@ -865,7 +910,8 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
     MMLA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, MMLA_EINVAL, "net_forward: workspace must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ov = net->kind == MMLA_NET_OVERLAP;
-    const bool tc = net->precision == MMLA_PRECISION_TF32;
+    const bool tc = net->precision == MMLA_PRECISION_TF32 || net->precision == MMLA_PRECISION_F16;
+    const bool f16 = net->precision == MMLA_PRECISION_F16;     // overlap net: the conv pairs take fp16 operands, the rest is TF32
     const long long in_elems = from_cep ? cep_clip_stride : static_cast<long long>(net->in_h) * net->in_w * (pad40 ? 40 : net->in_c);
     const long long act = ov ? 128LL * 151 * 32 : 256LL * 32;
     const int T = net->seq_len;
@@ -881,6 +927,10 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         float* hdir[2] = {z + B * 1024, z + B * 1024 + B * 256};   // final h of the fwd / bwd layer
         float* cst = hdir[1] + B * 256;                   // [B,256] cell state; fused kernel: 2 x 3 row-tiled [Bp,256] blocks
         float* xpad = cst + 6 * Bp * 256;                 // speaker: [B,256,40] channel-padded input
+        // overlap, fp16-operand mode: ELU(BN1(x)) of the current block input as fp16 (written by the kernel that produced x)
+        unsigned short* hact[2] = {reinterpret_cast<unsigned short*>(xpad), reinterpret_cast<unsigned short*>(xpad + Bp * kOvHalfFloats)};
+        int hcur = 0;
+        bool have_xa = false;                             // hact[hcur] holds the activated copy of buf[cur]
 
         const void* xin = x_is_u8 ? static_cast<const void*>(static_cast<const unsigned char*>(x) + b0 * in_elems)
                                   : static_cast<const void*>(static_cast<const float*>(x) + b0 * in_elems);
@@ -894,6 +944,16 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
             return k.conv1.k_tc && k.conv2.k_tc && k.conv1.stride == 1 && k.conv2.stride == 1 && k.conv2.cin == k.conv1.cout &&
                    k.conv2.cout == k.conv1.cout && k.bn1.scale && k.bn2.scale &&
                    mmla_resblock2d_eligible(h, w, k.conv1.cin, k.conv1.cout, k.conv1.kh, k.conv1.kw, k.conv2.kh, k.conv2.kw, act_kind);
+        };
+        // fp16-operand mode: the BN1 of block bi + 1 when that block will run on the fp16 conv-pair kernel from a [h,w,c] input
+        // that fits the fp16 buffers (its producer then also writes the activated fp16 operand), else null
+        auto next_bn = [&](size_t bi, int c, int h, int w) -> const BlockW::BnPtr {
+            const char* e = getenv("MMLA_NET_F16_ACT");       // "0": every fill converts from the fp32 tensor
+            if (!f16 || (e && e[0] == '0') || bi + 1 >= net->blocks.size()) return nullptr;
+            const BlockW& k = net->blocks[bi + 1];
+            if (!k.conv1.k_h || !k.conv2.k_h || k.conv1.cin != c || !pair_fusable(k, h, w)) return nullptr;
+            if (static_cast<long long>(h) * w * c > 2 * kOvHalfFloats) return nullptr;
+            return &k.bn1;
         };
         auto pool_fusable = [&](const BlockW& k) {
             const char* fp = getenv("MMLA_NET_FUSE_POOL");
@@ -949,6 +1009,8 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
             float* X = buf[cur];
             float* A = buf[(cur + 1) % 3];
             float* Bf = buf[(cur + 2) % 3];
+            const bool xa_in = have_xa;                   // hact[hcur] = the activated fp16 copy of X (fp16-operand mode)
+            have_xa = false;                              // set again by the kernel that produces the next block's input
             auto fusable = [&](const BlockW& k) { return k.conv1.k_tc && k.conv2.k_tc && (!k.pool || k.shortcut.k_tc); };
             if (tc && !ov && net->fuse_stages && blk.pool && bi + 2 < net->blocks.size() && fusable(blk) &&
                 fusable(net->blocks[bi + 1]) && fusable(net->blocks[bi + 2]) && !net->blocks[bi + 1].pool &&
@@ -994,11 +1056,18 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 // out = conv2(act(bn2(conv1(act(bn1(x)))))) + x
                 if (ov && tc && pair_fusable(blk, H, W)) {
                     // both convolutions in one launch, the intermediate stays in shared memory (resblock2d_fused.cu)
+                    const bool h16 = f16 && blk.conv1.k_h && blk.conv2.k_h;
+                    const BnW* nbn = next_bn(bi, blk.conv2.cout, H, W);      // fp16 mode: this block also writes the next one's operand
                     if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
                                                            blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
                                                            blk.conv2.b, X, blk.conv2.cout, st, nullptr, 0, nullptr, nullptr, 0,
-                                                           blk.conv1.k_tc2, blk.conv2.k_tc2)))
+                                                           blk.conv1.k_tc2, blk.conv2.k_tc2, h16 ? blk.conv1.k_h : nullptr,
+                                                           h16 ? blk.conv2.k_h : nullptr, h16 && xa_in ? hact[hcur] : nullptr,
+                                                           h16 && nbn ? hact[hcur ^ 1] : nullptr, nbn ? nbn->scale : nullptr,
+                                                           nbn ? nbn->shift : nullptr)))
                         return rc;
+                    have_xa = h16 && nbn;
+                    hcur ^= 1;
                 } else {
                     if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
                     if ((rc = launch_conv(blk.conv2, A, 0, B, H, W, &blk.bn2, act_kind, X, blk.conv2.cout, Bf, st, tc))) return rc;
@@ -1015,11 +1084,13 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                     hpool = !(e && e[0] == '0');
                 }
                 if (tc && pair_fusable(blk, H, W)) {
+                    const bool h16 = f16 && blk.conv1.k_h && blk.conv2.k_h;
                     if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
                                                            blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
                                                            blk.conv2.b, nullptr, 0, st, fold ? xin : nullptr, x_is_u8,
                                                            fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0,
-                                                           blk.conv1.k_tc2, blk.conv2.k_tc2)))
+                                                           blk.conv1.k_tc2, blk.conv2.k_tc2, h16 ? blk.conv1.k_h : nullptr,
+                                                           h16 ? blk.conv2.k_h : nullptr, h16 && xa_in ? hact[hcur] : nullptr)))
                         return rc;
                 } else {
                     if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
@@ -1029,11 +1100,15 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 const size_t wbytes = static_cast<size_t>(blk.shortcut.cin) * C * sizeof(float) + 256;
                 if (tc && pool_fusable(blk)) {
                     // MaxPool + stride-2 shortcut + add in one pass (reads X and Bf, writes A)
+                    const BnW* nbn = f16 ? next_bn(bi, C, Ho, Wo) : nullptr;
                     pool_shortcut_kernel<<<ew_grid(B * Ho * ((Wo + 3) / 4) * C / 4), 256, wbytes, st>>>(
                         X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W, blk.shortcut.cin, C, fold ? xin : nullptr, x_is_u8,
-                        fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0);
+                        fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0, nbn ? hact[hcur ^ 1] : nullptr,
+                        nbn ? nbn->scale : nullptr, nbn ? nbn->shift : nullptr);
                     mmla_count_launch("pool_shortcut_kernel", st);
                     MMLA_CUDA_CHECK(cudaGetLastError());
+                    have_xa = nbn != nullptr;
+                    hcur ^= 1;
                     H = Ho; W = Wo;
                     cur = (cur + 1) % 3;
                     continue;
@@ -1193,12 +1268,23 @@ EXPORT int mmla_debug_resblock2d(const float* x, const float* w1_host, const flo
     const int K1 = 9 * Cin, K2 = 4 * C;
     const long long n1 = mmla_tc_arranged_floats(K1, C), n2 = mmla_tc_arranged_floats(K2, C);
     const bool pair = mmla_rb_pair_wanted(Cin, C);
-    std::vector<float> host((n1 + n2) * (pair ? 2 : 1));
+    const char* e16 = getenv("MMLA_RB_F16");                    // "1": the fp16-operand form of the kernel (MMLA_PRECISION_F16)
+    const bool f16 = e16 && e16[0] == '1';
+    const long long h1 = mmla_rb_f16_arranged_halves(K1, C), h2 = mmla_rb_f16_arranged_halves(K2, C);
+    const long long f16_floats = f16 ? (h1 + h2 + 1) / 2 + 8 : 0;
+    std::vector<float> host((n1 + n2) * (pair ? 2 : 1) + f16_floats);
     mmla_tc_arrange_weights(w1_host, K1, C, host.data());
     mmla_tc_arrange_weights(w2_host, K2, C, host.data() + n1);
     if (pair) {
         mmla_rb_arrange_weights_pair(w1_host, K1, C, host.data() + n1 + n2);
         mmla_rb_arrange_weights_pair(w2_host, K2, C, host.data() + 2 * n1 + n2);
+    }
+    long long hoff = ((n1 + n2) * (pair ? 2 : 1) + 3) / 4 * 4;   // 16-byte aligned start of the fp16 chunks (in floats)
+    if (f16) {
+        MMLA_REQUIRE(h1 % 8 == 0, MMLA_EUNSUP, "debug_resblock2d: odd fp16 chunk size");
+        uint16_t* hp = reinterpret_cast<uint16_t*>(host.data() + hoff);
+        mmla_rb_arrange_weights_f16(w1_host, K1, C, hp);
+        mmla_rb_arrange_weights_f16(w2_host, K2, C, hp + h1);
     }
     float* wdev = nullptr;
     MMLA_CUDA_CHECK(cudaMalloc(&wdev, host.size() * sizeof(float)));
@@ -1207,7 +1293,9 @@ EXPORT int mmla_debug_resblock2d(const float* x, const float* w1_host, const flo
     if (rc == MMLA_OK)
         rc = mmla_launch_resblock2d_fused(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, wdev, b1, bn2_scale, bn2_shift, wdev + n1, b2, res, C, st,
                                           nullptr, 0, nullptr, nullptr, hpool, pair ? wdev + n1 + n2 : nullptr,
-                                          pair ? wdev + 2 * n1 + n2 : nullptr);
+                                          pair ? wdev + 2 * n1 + n2 : nullptr,
+                                          f16 ? static_cast<const void*>(reinterpret_cast<const uint16_t*>(wdev + hoff)) : nullptr,
+                                          f16 ? static_cast<const void*>(reinterpret_cast<const uint16_t*>(wdev + hoff) + h1) : nullptr);
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == MMLA_OK) {
         mmla_set_error("debug_resblock2d: %s", cudaGetErrorString(cudaGetLastError()));
         rc = MMLA_ECUDA;
@@ -1218,8 +1306,10 @@ EXPORT int mmla_debug_resblock2d(const float* x, const float* w1_host, const flo
 
 EXPORT int mmla_net_set_precision(MmlaNet* net, int32_t mode) {
     MMLA_REQUIRE(net != nullptr, MMLA_EINVAL, "net_set_precision: null net");
-    MMLA_REQUIRE(mode == MMLA_PRECISION_FP32 || mode == MMLA_PRECISION_TF32, MMLA_EINVAL,
+    MMLA_REQUIRE(mode == MMLA_PRECISION_FP32 || mode == MMLA_PRECISION_TF32 || mode == MMLA_PRECISION_F16, MMLA_EINVAL,
                  "net_set_precision: unknown mode %d", mode);
+    MMLA_REQUIRE(mode != MMLA_PRECISION_F16 || net->kind == MMLA_NET_OVERLAP, MMLA_EUNSUP,
+                 "net_set_precision: the fp16-operand mode exists for the overlap net's conv pairs only");
     net->precision = mode;
     return MMLA_OK;
 }

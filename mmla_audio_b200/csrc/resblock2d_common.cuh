@@ -8,6 +8,7 @@
 namespace {
 
 constexpr int kRbBK = 32;                   // K per ring chunk (mmla_tc_arrange_weights)
+constexpr int kRbBKh = 64;                  // ... of the fp16-operand mode (mmla_rb_arrange_weights_f16): same bytes per chunk
 constexpr int kRbMaxTiles = 4;
 constexpr int kRbMaxStages = 40;
 constexpr int kRbMaxChunks = 64;           // conv1 + conv2 chunks
@@ -24,6 +25,10 @@ struct RbArgs {
     const float* bn2_shift;
     const float* res;
     float* y;
+    const void* xa;           // F16: ELU(BN1(x)) already as fp16 [B,H,W,Cin] (written by the producer of x), or null: the fill converts x
+    void* ya;                 // F16: ELU(BN(y)) as fp16 [B,H,W,C] for the NEXT block (its BN1 = ya_scale / ya_shift), or null
+    const float* ya_scale;
+    const float* ya_shift;
     const void* img;          // STEM: the classifier input [B,H,W,3] (uint8 or float32); x is unused
     const float* stem_w;      // STEM: Conv2D(16, 1x1) weights [3][16] and bias [16] (overlap_detector_temp.py:283)
     const float* stem_b;
@@ -69,6 +74,20 @@ __device__ __forceinline__ uint32_t rb_bn_elu_tf32(float v, float sc, float sh) 
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
     v = v > 0.f ? v : e - 1.f;
     return rb_tf32(v);
+}
+// fp16-operand mode: BN + ELU in fp32 (same expression), then two elements per F2FP into one half2 word.  Operands keep the
+// 11 significant bits TF32 keeps; what changes is the exponent range, so the conversion saturates (ELU output is >= -1: only
+// the upper bound can be hit) instead of producing infinities, and values below 6e-5 go subnormal (absolute error <= 3e-8).
+__device__ __forceinline__ float rb_bn_elu(float v, float sc, float sh) {
+    v = fmaf(v, sc, sh);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v, 0.f) * 1.4426950408889634f));
+    return v > 0.f ? v : e - 1.f;
+}
+__device__ __forceinline__ uint32_t rb_pack_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // F2FP.SATFINITE: +-65504 instead of inf
+    return r;
 }
 // uint8 -> float without the quarter-rate I2F pipe: 0x4B000000 | v is the float 2^23 + v; the subtraction is exact.
 __device__ __forceinline__ float rb_u8_to_float(unsigned char v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }

@@ -22,6 +22,7 @@
 //   epilogue2 tcgen05.ld -> staging tiles in the dead slab -> + b2 (+ residual) -> whole-line NHWC stores
 // Arithmetic per element is the same sequence of operations as the two conv_slab launches (same TF32 operands, same K order,
 // same fp32 epilogue expressions), so the results are bit-identical to them (tests/test_resblock2d_gpu.py).
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -40,10 +41,17 @@ namespace {
 // MMAs complete and lands ~3 000 cycles later).  OPT-IN, see mmla_rb_pair_wanted: it measured slower.  The leader (rank 0) issues; the peer's warp 0 relays "my half has landed" to
 // the leader's `pfull` barriers; `empty` / `accum` are arrived in both CTAs by multicast commits; cluster barriers replace the
 // CTA barriers where the leader's MMAs read the peer's slab.
-template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false, bool PAIR = false>
+// F16 (precision mode "fp16" of the overlap net): both convolutions' operands are fp16 (activations converted in the fill /
+// in epilogue 1, weights arranged by mmla_rb_arrange_weights_f16), accumulation stays fp32 in TMEM (`kind::f16`).  An operand
+// slab row is then 8 channels per 16 bytes ([channel octet][row][16 B]) and one MMA covers K = 16: half the operand bytes
+// through shared memory, half the MMAs and half the ring chunks per output of the TF32 form, which is what bounds these
+// kernels.  Same 11 significant bits per operand as TF32; NOT bit-identical to it (round-to-nearest-even
+// instead of round-half-up, K = 16 summation groups).
+template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false, bool PAIR = false, bool F16 = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS == 512 && RES ? 1 : 2)) resblock2d_fused_kernel(const RbArgs a) {
-    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
-                                (static_cast<uint32_t>((PAIR ? 256 : 128) >> 4) << 24);   // D=f32, A=B=tf32, K-major, N, M
+    static_assert(!(PAIR && F16), "the CTA-pair mode exists for TF32 operands only");
+    constexpr uint32_t kIdesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (static_cast<uint32_t>(NT >> 3) << 17) |
+                                (static_cast<uint32_t>((PAIR ? 256 : 128) >> 4) << 24);   // D=f32, A=B=tf32 (or f16), K-major, N, M
     constexpr uint32_t kChunkBytes = 8 * NT * 16 / (PAIR ? 2 : 1);
     constexpr int kNB = PAIR ? NT / 2 : NT;                               // weight columns this CTA holds
     constexpr int kWarps = THREADS / 32;
@@ -122,7 +130,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
         unsigned char* dst0 = slab + static_cast<size_t>(c4) * a.RsX * 16;
         // four rows per iteration: all twelve pixel loads first, then the arithmetic (one row at a time the loop waited a
         // memory round trip per row: 13.5 k cycles per CTA against 9.4 k for the cp.async fill of the materialised tensor)
-        for (int r0 = warp * 8 + (lane & 7); r0 < rows; r0 += 4 * kWarps * 8) {
+        for (int rb = warp * 8; rb < rows; rb += 4 * kWarps * 8) {      // warp-uniform trip count (the F16 form shuffles)
+            const int r0 = rb + (lane & 7);
             float c[4][3];
             bool ok[4];
 #pragma unroll
@@ -139,6 +148,32 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
                     c[u][0] = imgf[px]; c[u][1] = imgf[px + 1]; c[u][2] = imgf[px + 2];
                 }
             }
+            if constexpr (F16) {
+                // this lane's four channels of four rows as half2 pairs; lanes l and l ^ 8 hold the two quads of one octet:
+                // the even quad's lane assembles rows u = 0, 2, the odd quad's lane rows u = 1, 3 (one shuffle pair per row)
+                uint32_t pk[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t keep = ok[u] ? 0xFFFFFFFFu : 0u;
+                    const float c0 = c[u][0], c1 = c[u][1], c2 = c[u][2];
+                    pk[u][0] = rb_pack_h2(rb_bn_elu(fmaf(c2, w2.x, fmaf(c1, w1.x, fmaf(c0, w0.x, sb.x))), sc.x, sh.x),
+                                          rb_bn_elu(fmaf(c2, w2.y, fmaf(c1, w1.y, fmaf(c0, w0.y, sb.y))), sc.y, sh.y)) & keep;
+                    pk[u][1] = rb_pack_h2(rb_bn_elu(fmaf(c2, w2.z, fmaf(c1, w1.z, fmaf(c0, w0.z, sb.z))), sc.z, sh.z),
+                                          rb_bn_elu(fmaf(c2, w2.w, fmaf(c1, w1.w, fmaf(c0, w0.w, sb.w))), sc.w, sh.w)) & keep;
+                }
+                const bool odd = (c4 & 1) != 0;
+                unsigned char* dsth = slab + static_cast<size_t>(c4 >> 1) * a.RsX * 16;
+#pragma unroll
+                for (int u = 0; u < 4; u += 2) {
+                    const uint32_t g0 = __shfl_xor_sync(0xffffffffu, odd ? pk[u][0] : pk[u + 1][0], 8);
+                    const uint32_t g1 = __shfl_xor_sync(0xffffffffu, odd ? pk[u][1] : pk[u + 1][1], 8);
+                    const int r = r0 + (u + (odd ? 1 : 0)) * kWarps * 8;
+                    if (r < rows)
+                        *reinterpret_cast<uint4*>(dsth + static_cast<size_t>(r) * 16) =
+                            odd ? make_uint4(g0, g1, pk[u + 1][0], pk[u + 1][1]) : make_uint4(pk[u][0], pk[u][1], g0, g1);
+                }
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int r = r0 + u * kWarps * 8;
@@ -151,6 +186,75 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
                         rb_bn_elu_tf32(fmaf(c2, w2.z, fmaf(c1, w1.z, fmaf(c0, w0.z, sb.z))), sc.z, sh.z) & keep,
                         rb_bn_elu_tf32(fmaf(c2, w2.w, fmaf(c1, w1.w, fmaf(c0, w0.w, sb.w))), sc.w, sh.w) & keep);
                 }
+            }
+        }
+    } else if (F16 && a.xa != nullptr) {
+        // ---- x slab fill, fp16 operands, the producer of x has already written ELU(BN1(x)) as fp16: the fill is a plain
+        // asynchronous gather, 16 bytes = one channel octet of one row per copy (zero-fill form for the padding rows), every
+        // copy of the CTA in flight at once and nothing to transform ----
+        const int rows = Tc * 128 + 2 * a.Fp + 2;
+        const int no = a.Cin >> 3;                            // channel octets per row: 2, 4, 8, 16
+        const int osh = no >= 4 ? 2 : 1;                      // a warp instruction covers 4 octets x 8 rows (2 x 16 for Cin = 16)
+        const int rpi = 32 >> osh, ngrp = no >> osh;
+        const int c8 = ((warp % ngrp) << osh) + (lane >> (5 - osh));
+        const int rpp = (kWarps / ngrp) * rpi;
+        const uint16_t* ximg = static_cast<const uint16_t*>(a.xa) + static_cast<long long>(img) * a.img_pixels * a.Cin + 8 * c8;
+        unsigned char* dsth = slab + static_cast<size_t>(c8) * a.RsX * 16;
+        for (int r = (warp / ngrp) * rpi + (lane & (rpi - 1)); r < rows; r += rpp) {
+            const int p = Qc - 1 + r;
+            const int wp = static_cast<int>(__umulhi(static_cast<unsigned>(p < 0 ? 0 : p), a.fp_magic));
+            const int w = wp - 1, h = p - wp * a.Fp - 1;
+            const bool ok = p >= 0 && w >= 0 && w < a.W && h >= 0 && h < a.H;
+            const uint16_t* src = ximg + (ok ? static_cast<long long>(h * a.W + w) * a.Cin : 0ll);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dsth + static_cast<size_t>(r) * 16)), "l"(src),
+                         "r"(ok ? 16 : 0)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if constexpr (F16) {
+        // ---- x slab fill, fp16 operands: 16-byte loads of one channel quad per lane (the cp.async form's lane map: 8 rows x 4
+        // quads per warp instruction), eight rows in flight per lane, BN1 + ELU in fp32, half2 packing, and the two quads of an
+        // octet joined by one shuffle pair per row (lanes l, l ^ 8) before the 16-byte store ----
+        const int rows = Tc * 128 + 2 * a.Fp + 2;
+        const int lqg = a.lq - 2;
+        const int c4 = ((warp & ((1 << lqg) - 1)) << 2) + (lane >> 3);
+        const int rpp = (kWarps >> lqg) * 8;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(a.bn1_scale) + c4);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(a.bn1_shift) + c4);
+        const float* ximg = a.x + static_cast<long long>(img) * a.img_pixels * a.Cin + 4 * c4;
+        unsigned char* dsth = slab + static_cast<size_t>(c4 >> 1) * a.RsX * 16;
+        const bool odd = (c4 & 1) != 0;
+        for (int rb = (warp >> lqg) * 8; rb < rows; rb += 8 * rpp) {    // warp-uniform trip count
+            const int r0 = rb + (lane & 7);
+            float4 raw[8];
+            unsigned okm = 0u;                                          // bit u: row u holds image data (padding rows stay zero)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u * rpp;
+                const int p = Qc - 1 + r;
+                const int wp = static_cast<int>(__umulhi(static_cast<unsigned>(p < 0 ? 0 : p), a.fp_magic));
+                const int w = wp - 1, h = p - wp * a.Fp - 1;
+                const bool ok = r < rows && p >= 0 && w >= 0 && w < a.W && h >= 0 && h < a.H;
+                raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) raw[u] = __ldg(reinterpret_cast<const float4*>(ximg + static_cast<long long>(h * a.W + w) * a.Cin));
+                okm |= static_cast<unsigned>(ok) << u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                uint32_t pk[2][2];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const uint32_t keep = ((okm >> (u + v)) & 1u) ? 0xFFFFFFFFu : 0u;
+                    pk[v][0] = rb_pack_h2(rb_bn_elu(raw[u + v].x, sc.x, sh.x), rb_bn_elu(raw[u + v].y, sc.y, sh.y)) & keep;
+                    pk[v][1] = rb_pack_h2(rb_bn_elu(raw[u + v].z, sc.z, sh.z), rb_bn_elu(raw[u + v].w, sc.w, sh.w)) & keep;
+                }
+                const uint32_t g0 = __shfl_xor_sync(0xffffffffu, odd ? pk[0][0] : pk[1][0], 8);
+                const uint32_t g1 = __shfl_xor_sync(0xffffffffu, odd ? pk[0][1] : pk[1][1], 8);
+                const int r = r0 + (u + (odd ? 1 : 0)) * rpp;
+                if (r < rows)
+                    *reinterpret_cast<uint4*>(dsth + static_cast<size_t>(r) * 16) =
+                        odd ? make_uint4(g0, g1, pk[1][0], pk[1][1]) : make_uint4(pk[0][0], pk[0][1], g0, g1);
             }
         }
     } else
@@ -283,6 +387,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
                                     "r"(alo + aoff[kk] + static_cast<uint32_t>(t * 128)), "r"(ahi), "r"(blo + static_cast<uint32_t>(kk * 2 * kNB)),
                                     "r"(bhi), "r"(kIdesc), "r"(acc)
                                     : "memory");
+                            } else if constexpr (F16) {
+                                asm volatile(
+                                    "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
+                                    "mov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+                                    "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem + static_cast<uint32_t>(t * NT)),
+                                    "r"(alo + aoff[kk] + static_cast<uint32_t>(t * 128)), "r"(ahi), "r"(blo + static_cast<uint32_t>(kk * 2 * kNB)),
+                                    "r"(bhi), "r"(kIdesc), "r"(acc)
+                                    : "memory");
                             } else {
                                 asm volatile(
                                     "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\n"
@@ -355,6 +467,24 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
             const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;   // junk rows ARE conv2's zero padding
             uint32_t r[32];
             rb_tmem_ld32(tmem + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(t * NT + col0), r);
+            if constexpr (F16) {
+                unsigned char* dsth = slab + (static_cast<size_t>(col0 >> 3) * a.RsU + i) * 16;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {                 // one channel octet per 16-byte store
+                    uint32_t h[4];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float4 bb = par4[(col0 >> 2) + 2 * g + e], sc = par4[(NT >> 2) + (col0 >> 2) + 2 * g + e],
+                                     sh = par4[(NT >> 1) + (col0 >> 2) + 2 * g + e];
+                        h[2 * e] = rb_pack_h2(rb_bn_elu(__uint_as_float(r[8 * g + 4 * e]) + bb.x, sc.x, sh.x),
+                                              rb_bn_elu(__uint_as_float(r[8 * g + 4 * e + 1]) + bb.y, sc.y, sh.y)) & keep;
+                        h[2 * e + 1] = rb_pack_h2(rb_bn_elu(__uint_as_float(r[8 * g + 4 * e + 2]) + bb.z, sc.z, sh.z),
+                                                  rb_bn_elu(__uint_as_float(r[8 * g + 4 * e + 3]) + bb.w, sc.w, sh.w)) & keep;
+                    }
+                    *reinterpret_cast<uint4*>(dsth + static_cast<size_t>(g) * a.RsU * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                }
+                continue;
+            }
             unsigned char* dst = slab + (static_cast<size_t>(col0 >> 2) * a.RsU + i) * 16;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -367,7 +497,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
             }
         }
         // rows 128 Tc .. + 2 only feed outputs that are never stored, but they must be finite
-        for (int i = tid; i < 3 * (NT / 4); i += THREADS)
+        for (int i = tid; i < 3 * (NT / (F16 ? 8 : 4)); i += THREADS)
             *reinterpret_cast<uint4*>(slab + (static_cast<size_t>(i / 3) * a.RsU + Tc * 128 + i % 3) * 16) = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         fence_proxy_async_smem();
@@ -431,6 +561,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
                 *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             __syncwarp();
             const float4 bv = __ldg(reinterpret_cast<const float4*>(a.b2 + col0) + seg);
+            float4 ysc = make_float4(0.f, 0.f, 0.f, 0.f), ysh = ysc;
+            if (F16 && !HPOOL && a.ya) {
+                ysc = __ldg(reinterpret_cast<const float4*>(a.ya_scale + col0) + seg);
+                ysh = __ldg(reinterpret_cast<const float4*>(a.ya_shift + col0) + seg);
+            }
             if constexpr (HPOOL) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { // row pairs (8i + 2 rsub, + 1) of the warp's 32, eight lanes (128 B) per pooled row
@@ -447,9 +582,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
                 for (int i = 0; i < 8; ++i) { // rows 4i .. 4i+3 of the warp's 32, eight lanes (128 B) per row
                     if (pixoff[i] >= 0) {
                         const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * seg);
-                        *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) =
-                            RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
-                                : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                        const float4 o = RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
+                                             : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                        *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) = o;
+                        if (F16 && a.ya)          // the next block's operand: its BN1 + ELU applied here, once per element, as fp16
+                            *(reinterpret_cast<uint2*>(static_cast<uint16_t*>(a.ya) + (imgbase + pixoff[i]) * NT + col0) + seg) =
+                                make_uint2(rb_pack_h2(rb_bn_elu(o.x, ysc.x, ysh.x), rb_bn_elu(o.y, ysc.y, ysh.y)),
+                                           rb_pack_h2(rb_bn_elu(o.z, ysc.z, ysh.z), rb_bn_elu(o.w, ysc.w, ysh.w)));
                     }
                 }
             }
@@ -477,13 +616,13 @@ int rb_ilog2(int v) {
 long long* g_rb_stamps = nullptr;         // mmla_debug_resblock2d_stamps: 16 rows (launch ordinal) x 16 slots
 int g_rb_stamp_cta = 0, g_rb_stamp_row = 0;
 
-template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false, bool PAIR = false>
+template <int NT, bool RES, int THREADS, bool STEM = false, bool HPOOL = false, bool PAIR = false, bool F16 = false>
 int launch_rb(const RbArgs& s, long long images, size_t smem, cudaStream_t st) {
     static size_t attr[64] = {};                                  // per device: function attributes are per device
     int dev = 0;
     MMLA_CUDA_CHECK(cudaGetDevice(&dev));
     MMLA_REQUIRE(dev >= 0 && dev < 64, MMLA_EUNSUP, "resblock2d: device ordinal %d out of range", dev);
-    auto kern = resblock2d_fused_kernel<NT, RES, THREADS, STEM, HPOOL, PAIR>;
+    auto kern = resblock2d_fused_kernel<NT, RES, THREADS, STEM, HPOOL, PAIR, F16>;
     if (smem > attr[dev]) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr[dev] = smem;
@@ -507,9 +646,57 @@ int launch_rb(const RbArgs& s, long long images, size_t smem, cudaStream_t st) {
     } else {
         kern<<<static_cast<unsigned>(ctas), THREADS, smem, st>>>(s);
     }
-    mmla_count_launch(STEM ? "stem_resblock2d_fused_kernel" : "resblock2d_fused_kernel", st);
+    mmla_count_launch(F16 ? (STEM ? "stem_resblock2d_f16_kernel" : "resblock2d_f16_kernel")
+                          : (STEM ? "stem_resblock2d_fused_kernel" : "resblock2d_fused_kernel"), st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
+}
+
+// one CTA per MMA (no pairs): residual / stem / row-pooled / plain variants at 256 or 512 threads
+template <bool F16>
+int dispatch_rb(const RbArgs& s, long long B, size_t smem, cudaStream_t st, int C, bool res, bool img, bool hpool, int thr) {
+    if (res) {
+        if (thr == 512) {
+            switch (C) {
+                case 32: return launch_rb<32, true, 512, false, false, false, F16>(s, B, smem, st);
+                case 64: return launch_rb<64, true, 512, false, false, false, F16>(s, B, smem, st);
+                default: return launch_rb<128, true, 512, false, false, false, F16>(s, B, smem, st);
+            }
+        }
+        switch (C) {
+            case 32: return launch_rb<32, true, 256, false, false, false, F16>(s, B, smem, st);
+            case 64: return launch_rb<64, true, 256, false, false, false, F16>(s, B, smem, st);
+            default: return launch_rb<128, true, 256, false, false, false, F16>(s, B, smem, st);
+        }
+    }
+    if (img) return hpool ? launch_rb<32, false, 256, true, true, false, F16>(s, B, smem, st)
+                          : launch_rb<32, false, 256, true, false, false, F16>(s, B, smem, st);
+    if (hpool) {
+        if (thr == 256) {
+            switch (C) {
+                case 32: return launch_rb<32, false, 256, false, true, false, F16>(s, B, smem, st);
+                case 64: return launch_rb<64, false, 256, false, true, false, F16>(s, B, smem, st);
+                default: return launch_rb<128, false, 256, false, true, false, F16>(s, B, smem, st);
+            }
+        }
+        switch (C) {
+            case 32: return launch_rb<32, false, 512, false, true, false, F16>(s, B, smem, st);
+            case 64: return launch_rb<64, false, 512, false, true, false, F16>(s, B, smem, st);
+            default: return launch_rb<128, false, 512, false, true, false, F16>(s, B, smem, st);
+        }
+    }
+    if (thr == 256) {
+        switch (C) {
+            case 32: return launch_rb<32, false, 256, false, false, false, F16>(s, B, smem, st);
+            case 64: return launch_rb<64, false, 256, false, false, false, F16>(s, B, smem, st);
+            default: return launch_rb<128, false, 256, false, false, false, F16>(s, B, smem, st);
+        }
+    }
+    switch (C) {
+        case 32: return launch_rb<32, false, 512, false, false, false, F16>(s, B, smem, st);
+        case 64: return launch_rb<64, false, 512, false, false, false, F16>(s, B, smem, st);
+        default: return launch_rb<128, false, 512, false, false, false, F16>(s, B, smem, st);
+    }
 }
 
 }  // namespace
@@ -545,6 +732,30 @@ void mmla_rb_arrange_weights_pair(const float* w, int K, int N, float* out) {
                         out[((((static_cast<long long>(kc) * 2 + h) * 8 + slab) * nh + n) * 4) + j] = v;
                     }
 }
+// Weight arrangement of the fp16-operand mode: [64 x N] K-chunks, each [k octet 0..7][n 0..N-1][8 halves] =
+// half(W[kchunk*64 + octet*8 + j][n]) (UMMA K-major no-swizzle core matrices, the fp16 twin of mmla_tc_arrange_weights'
+// [k quad][n][4 tf32]); rows k >= K are zero.  Round-to-nearest-even, saturating at the largest finite half.  `out` holds
+// ceil(K / 64) * 64 * N halves = as many BYTES per chunk as the TF32 arrangement.
+long long mmla_rb_f16_arranged_halves(int K, int N) { return static_cast<long long>((K + kRbBKh - 1) / kRbBKh) * kRbBKh * N; }
+static uint16_t rb_float_to_half_rn(float f) {
+    if (f > 65504.f) f = 65504.f;
+    if (f < -65504.f) f = -65504.f;
+    const __half h = __float2half_rn(f);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+void mmla_rb_arrange_weights_f16(const float* w, int K, int N, uint16_t* out) {
+    const int nk = (K + kRbBKh - 1) / kRbBKh;
+    for (int kc = 0; kc < nk; ++kc)
+        for (int oct = 0; oct < 8; ++oct)
+            for (int n = 0; n < N; ++n)
+                for (int j = 0; j < 8; ++j) {
+                    const int k = kc * kRbBKh + oct * 8 + j;
+                    out[((static_cast<long long>(kc) * 8 + oct) * N + n) * 8 + j] =
+                        k < K ? rb_float_to_half_rn(w[static_cast<long long>(k) * N + n]) : static_cast<uint16_t>(0);
+                }
+}
 bool mmla_rb_pair_wanted(int Cin, int C) {
     // Opt-in (MMLA_RB_PAIR=1): measured SLOWER than one CTA per MMA on every C >= 64 block of the overlap net (0.68 -> 0.78,
     // 0.29 -> 0.35, 0.56 -> 0.70, 0.29 -> 0.34 ms per 512 clips, profiles/r02/experiment_notes.txt): the N <= 128, K = 8 MMAs are
@@ -567,8 +778,15 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                  long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8, const float* stem_w,
-                                 const float* stem_b, int hpool, const float* w1_pair, const float* w2_pair) {
+                                 const float* stem_b, int hpool, const float* w1_pair, const float* w2_pair, const void* w1_h,
+                                 const void* w2_h, const void* xa, void* ya, const float* ya_scale, const float* ya_shift) {
     if (B <= 0) return MMLA_OK;
+    // w1_h / w2_h: the same weights as fp16 chunks (mmla_rb_arrange_weights_f16); when given the block runs with fp16 operands
+    const bool f16 = w1_h && w2_h;
+    if (f16) {
+        w1 = static_cast<const float*>(w1_h);      // chunk c starts c * 128 * C bytes in, in either arrangement
+        w2 = static_cast<const float*>(w2_h);
+    } else
     {   // the C = 32 blocks run on the persistent, warp-specialised kernel where their slabs fit (resblock2d_persist.cu)
         const int pr = mmla_try_launch_resblock2d_persist(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, w1, b1, bn2_scale, bn2_shift, w2, b2,
                                                           res, res_row_stride, st, img, img_is_u8, stem_w, stem_b, hpool);
@@ -577,7 +795,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     }
     // w1_pair / w2_pair: the same weights in the PAIR arrangement (mmla_rb_arrange_weights_pair); when given (and wanted) the
     // block runs on CTA pairs
-    const bool pair = w1_pair && w2_pair && !img && mmla_rb_pair_wanted(Cin, C);
+    const bool pair = !f16 && w1_pair && w2_pair && !img && mmla_rb_pair_wanted(Cin, C);
     if (pair) { w1 = w1_pair; w2 = w2_pair; }
     MMLA_REQUIRE(!hpool || (!res && H % 2 == 0), MMLA_EUNSUP, "resblock2d: row-pooled output needs an even height and no residual");
     MMLA_REQUIRE(!img || (Cin == 16 && C == 32 && !res && stem_w && stem_b), MMLA_EUNSUP, "resblock2d: stem mode needs Cin 16, C 32, no residual");
@@ -588,6 +806,9 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     s.bn1_scale = bn1_scale; s.bn1_shift = bn1_shift; s.bn2_scale = bn2_scale; s.bn2_shift = bn2_shift;
     s.res = res; s.res_row_stride = res_row_stride;
     s.img = img; s.img_is_u8 = img_is_u8; s.stem_w = stem_w; s.stem_b = stem_b;
+    MMLA_REQUIRE(f16 || (!xa && !ya), MMLA_EINVAL, "resblock2d: fp16 activations need the fp16-operand mode");
+    MMLA_REQUIRE(!ya || (!hpool && ya_scale && ya_shift), MMLA_EINVAL, "resblock2d: fp16 output needs the next block's BN and a full-resolution output");
+    s.xa = img ? nullptr : xa; s.ya = ya; s.ya_scale = ya_scale; s.ya_shift = ya_shift;
     s.img_pixels = static_cast<long long>(H) * W;
     s.hpool = hpool;
     const int drop = hpool ? 4 : 3;                              // outputs a CTA gives up to the 4x1 halo (even for HPOOL)
@@ -596,20 +817,23 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     s.total_q = W * s.Fp;
     s.Cin = Cin; s.lq = rb_ilog2(Cin / 4);
     const int K1 = 9 * Cin, K2 = 4 * C;
-    s.nk1 = (K1 + kRbBK - 1) / kRbBK;
-    s.nk = s.nk1 + K2 / kRbBK;
+    const int BK = f16 ? kRbBKh : kRbBK;                         // K per ring chunk (four MMAs), channels per 16-byte slab row
+    const int cpr = f16 ? 8 : 4;
+    s.nk1 = (K1 + BK - 1) / BK;
+    s.nk = s.nk1 + K2 / BK;
     MMLA_REQUIRE(s.nk <= kRbMaxChunks, MMLA_EUNSUP, "resblock2d: K = %d + %d is too large", K1, K2);
     const size_t chunk = static_cast<size_t>(8) * C * 16 / (pair ? 2 : 1);   // one [32 x C] K-chunk of weights (PAIR: this CTA's half)
     constexpr size_t kBarBytes = 1024 + 128;                    // mbarriers + alignment slack
     const size_t par_bytes = static_cast<size_t>(3) * C * 4;
     auto rows_x = [&](int T) {
         int r = T * 128 + 2 * s.Fp + 2;
+        if (f16) return r | 1;
         if (Cin == 16) { while ((r & 7) != 2) ++r; } else if ((r & 1) == 0) ++r;     // conflict-free fill stores (conv_slab.cu)
         return r;
     };
     auto rows_u = [&](int T) { return (T * 128 + 3) | 1; };
     auto slab_bytes = [&](int T, int nthr) {
-        const size_t bx = static_cast<size_t>(Cin / 4) * rows_x(T) * 16, bu = static_cast<size_t>(C / 4) * rows_u(T) * 16;
+        const size_t bx = static_cast<size_t>(Cin / cpr) * rows_x(T) * 16, bu = static_cast<size_t>(C / cpr) * rows_u(T) * 16;
         const size_t stg = static_cast<size_t>(nthr / 32) * 32 * 36 * 4;               // epilogue-2 staging tiles, one per warp
         size_t b = bx > bu ? bx : bu;
         return b > stg ? b : stg;
@@ -624,9 +848,11 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     // where the model below picks a slower configuration: the full-resolution block prefers four tiles at three CTAs per SM
     // even with a two-slot ring (0.89 vs 1.02 ms per 512 clips), the 16 x 19 blocks prefer two tiles on one CTA per SM (half
     // the weight stream from L2 per output: 0.30 vs 0.35 ms).
+    // fp16 operands (profiles/r02/sweep_resblock2d_f16_v2.txt): the slabs are half as large, so the full-resolution block keeps
+    // three CTAs per SM at 56 KB (0.74 vs 0.76 ms) and the 16 x 19 blocks run two CTAs per SM (0.143 / 0.135 vs 0.182 / 0.172 ms).
     if (!force_t && !force_kb) {
-        if (H == 128 && Cin == 16 && C == 32) { force_t = 4; force_kb = 75; }
-        if (H == 16 && Cin == 128 && C == 128) { force_t = 2; force_kb = 226; }
+        if (H == 128 && Cin == 16 && C == 32) { force_t = 4; force_kb = f16 ? 56 : 75; }
+        if (H == 16 && Cin == 128 && C == 128) { force_t = 2; force_kb = f16 ? 113 : 226; }
     }
     int tmax = kRbMaxTiles;
     if (tmax > 512 / C) tmax = 512 / C;
@@ -682,17 +908,17 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
         for (int kk = 0; kk < 4; ++kk) {
             s.aoff[kc * 4 + kk] = 0;
             if (kc < s.nk1) {
-                const int k = kc * kRbBK + kk * 8;
+                const int k = kc * BK + kk * (BK / 4);
                 if (k < K1) {
                     const int tap = k / Cin, c0 = k % Cin;
                     const int dh = tap / 3, dw = tap % 3;         // Keras HWIO: tap = kernel row * 3 + kernel column
-                    s.aoff[kc * 4 + kk] = static_cast<unsigned>((c0 >> 2) * s.RsX + dw * s.Fp + dh);
+                    s.aoff[kc * 4 + kk] = static_cast<unsigned>((c0 / cpr) * s.RsX + dw * s.Fp + dh);
                     if (kc == s.nk1 - 1) s.nmma1_last = kk + 1;
                 }
             } else {
-                const int k = (kc - s.nk1) * kRbBK + kk * 8;
+                const int k = (kc - s.nk1) * BK + kk * (BK / 4);
                 const int dh = k / C, c0 = k % C;
-                s.aoff[kc * 4 + kk] = static_cast<unsigned>((c0 >> 2) * s.RsU + dh);
+                s.aoff[kc * 4 + kk] = static_cast<unsigned>((c0 / cpr) * s.RsU + dh);
                 if (kc == s.nk - 1) s.nmma2_last = kk + 1;
             }
         }
@@ -703,7 +929,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     const size_t smem = s.bar_off + kBarBytes;
     if (getenv("MMLA_RB_VERBOSE"))
         fprintf(stderr, "resblock2d: %dx%d Cin %d C %d: %d outputs/image, T %d, %d CTAs/image, ring %d of %d chunks, %zu KB smem, %d threads%s\n",
-                H, W, Cin, C, s.total_q, s.T, s.cpi, s.stages, s.nk, smem / 1024, best_thr, pair ? ", CTA pairs" : "");
+                H, W, Cin, C, s.total_q, s.T, s.cpi, s.stages, s.nk, smem / 1024, best_thr, pair ? ", CTA pairs" : f16 ? ", fp16 operands" : "");
     if (g_rb_stamps && g_rb_stamp_row < 16) {
         s.stamps = g_rb_stamps + 16 * g_rb_stamp_row++;
         s.stamp_cta = static_cast<int>((static_cast<long long>(g_rb_stamp_cta) % B) * s.cpi + s.cpi / 2);   // a mid-image CTA
@@ -727,47 +953,8 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
         return C == 64 ? launch_rb<64, false, 512, false, false, true>(s, B, smem, st)
                        : launch_rb<128, false, 512, false, false, true>(s, B, smem, st);
     }
-    if (res) {
-        if (best_thr == 512) {
-            switch (C) {
-                case 32: return launch_rb<32, true, 512>(s, B, smem, st);
-                case 64: return launch_rb<64, true, 512>(s, B, smem, st);
-                default: return launch_rb<128, true, 512>(s, B, smem, st);
-            }
-        }
-        switch (C) {
-            case 32: return launch_rb<32, true, 256>(s, B, smem, st);
-            case 64: return launch_rb<64, true, 256>(s, B, smem, st);
-            default: return launch_rb<128, true, 256>(s, B, smem, st);
-        }
-    }
-    if (img) return hpool ? launch_rb<32, false, 256, true, true>(s, B, smem, st) : launch_rb<32, false, 256, true>(s, B, smem, st);
-    if (hpool) {
-        if (best_thr == 256) {
-            switch (C) {
-                case 32: return launch_rb<32, false, 256, false, true>(s, B, smem, st);
-                case 64: return launch_rb<64, false, 256, false, true>(s, B, smem, st);
-                default: return launch_rb<128, false, 256, false, true>(s, B, smem, st);
-            }
-        }
-        switch (C) {
-            case 32: return launch_rb<32, false, 512, false, true>(s, B, smem, st);
-            case 64: return launch_rb<64, false, 512, false, true>(s, B, smem, st);
-            default: return launch_rb<128, false, 512, false, true>(s, B, smem, st);
-        }
-    }
-    if (best_thr == 256) {
-        switch (C) {
-            case 32: return launch_rb<32, false, 256>(s, B, smem, st);
-            case 64: return launch_rb<64, false, 256>(s, B, smem, st);
-            default: return launch_rb<128, false, 256>(s, B, smem, st);
-        }
-    }
-    switch (C) {
-        case 32: return launch_rb<32, false, 512>(s, B, smem, st);
-        case 64: return launch_rb<64, false, 512>(s, B, smem, st);
-        default: return launch_rb<128, false, 512>(s, B, smem, st);
-    }
+    return f16 ? dispatch_rb<true>(s, B, smem, st, C, res != nullptr, img != nullptr, hpool != 0, best_thr)
+               : dispatch_rb<false>(s, B, smem, st, C, res != nullptr, img != nullptr, hpool != 0, best_thr);
 }
 
 extern "C" __attribute__((visibility("default"))) void mmla_debug_resblock2d_stamps(long long* dev_stamps, int32_t image) {

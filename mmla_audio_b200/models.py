@@ -24,7 +24,7 @@ from .weights import (NetSpec, OVERLAP, SPEAKER_BASE, speaker_spec, weight_shape
 
 KIND_OVERLAP, KIND_SPEAKER = 0, 1
 HEAD_IDS = {"softmax": 0, "sigmoid": 1}
-PRECISION_IDS = {"fp32": 0, "tf32": 1}
+PRECISION_IDS = {"fp32": 0, "tf32": 1, "fp16": 2}
 
 
 def pack_weights(spec: NetSpec, w: Dict[str, np.ndarray]) -> np.ndarray:
@@ -85,7 +85,7 @@ class Model:
 
     def set_precision(self, precision: str) -> None:
         if precision not in PRECISION_IDS:
-            raise ValueError("precision must be 'fp32' or 'tf32'")
+            raise ValueError("precision must be 'fp32', 'tf32' or 'fp16' (overlap net only)")
         _lib.check(self._lib.mmla_net_set_precision(self._handle, PRECISION_IDS[precision]),
                    "mmla_net_set_precision")
         self.precision = precision

@@ -8,7 +8,7 @@ from mmla_audio_b200 import _lib, models, synth, weights as W
 from mmla_audio_b200.pipeline import OverlapPipeline
 
 lib = _lib.load()
-pipe = OverlapPipeline(models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234), precision="tf32"))
+pipe = OverlapPipeline(models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234), precision=os.environ.get("PRECISION", "tf32")))
 pcm = synth.synth_clips(0, int(os.environ.get("CLIPS", "512")), 24000)
 for _ in range(2):
     pipe.run_device(pcm)
@@ -19,7 +19,7 @@ for _ in range(reps):
     tr = _lib.trace_launches(lambda: pipe.run_device(pcm), torch)
     i = 0
     for n, ms in tr:
-        if n in ("resblock2d_fused_kernel", "stem_resblock2d_fused_kernel", "resblock2d_persist_kernel", "stem_resblock2d_persist_kernel", "conv_slab_kernel", "pool_shortcut_kernel", "stem1x1_kernel"):
+        if n in ("resblock2d_f16_kernel", "stem_resblock2d_f16_kernel", "resblock2d_fused_kernel", "stem_resblock2d_fused_kernel", "resblock2d_persist_kernel", "stem_resblock2d_persist_kernel", "conv_slab_kernel", "pool_shortcut_kernel", "stem1x1_kernel"):
             acc[(i, n)] = acc.get((i, n), 0.0) + ms / reps
             i += 1
 tot = {}

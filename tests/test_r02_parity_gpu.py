@@ -56,14 +56,16 @@ def test_bench_batch_tf32_labels_vs_oracle(cuda):
     assert agree >= 0.95
 
 
-def test_overlap_256_clips_tf32_vs_oracle(cuda):
-    """256 overlap clips through OverlapPipeline on the tcgen05 path (overlap_features_kernel -> stem1x1 ->
-    conv_slab x18 -> pool_shortcut x3 -> fused BiLSTM -> head) against the oracle's librosa restatement + torch-CPU net."""
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_overlap_256_clips_tf32_vs_oracle(cuda, precision):
+    """256 overlap clips through OverlapPipeline on the tcgen05 path (overlap_features_tc_kernel -> conv-pair kernels x9 ->
+    pool_shortcut x3 -> fused BiLSTM -> head) against the oracle's librosa restatement + torch-CPU net; "fp16" = the conv
+    pairs with fp16 operands (MMLA_PRECISION_F16), same bars."""
     from mmla_audio_b200 import models, synth as dsynth, weights as W
     from mmla_audio_b200.pipeline import OverlapPipeline
     w = W.synthetic_weights(W.OVERLAP, 1234)
     n = 256
-    pipe = OverlapPipeline(models.Model(W.OVERLAP, w, precision="tf32"))
+    pipe = OverlapPipeline(models.Model(W.OVERLAP, w, precision=precision))
     labels, prob = pipe.run_device(dsynth.synth_clips(1000, n, 24000))
     host = synth.synth_clips(1000, n, 24000)
     x = np.stack([lm.classifier_input(host[i]) for i in range(n)])
@@ -72,7 +74,7 @@ def test_overlap_256_clips_tf32_vs_oracle(cuda):
     d = np.abs(got - ref).max()
     agree = float((lg == lr).mean())
     clear = _margin(ref) > 1e-2
-    print(f"overlap 256 clips tf32 vs ORACLE: label agreement {agree:.4f}, max |dprob| {d:.2e}")
+    print(f"overlap 256 clips {precision} vs ORACLE: label agreement {agree:.4f}, max |dprob| {d:.2e}")
     assert d <= 5e-3
     assert (lg[clear] == lr[clear]).all()
     assert agree >= 0.95

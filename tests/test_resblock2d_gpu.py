@@ -127,6 +127,84 @@ def test_fused_block_matches_two_slab_convs_bitwise(cuda, monkeypatch, H, W, Cin
         monkeypatch.delenv("MMLA_RB_TILES", raising=False)
 
 
+@pytest.mark.parametrize("H,W,Cin,Cc,with_res,B", BLOCKS)
+def test_fp16_operand_block_matches_fp64_convs(cuda, monkeypatch, H, W, Cin, Cc, with_res, B):
+    """The fp16-operand form of the kernel (MMLA_PRECISION_F16; here through MMLA_RB_F16=1 of the debug entry): fp16 keeps the 11
+    significant bits TF32 keeps, so the bar against the float64 pair of convolutions is the TF32 one (5e-3 of max |y|) and the
+    two tensor-core forms agree to 3e-3; the row-pooled variant must equal the maximum over row pairs of the full output."""
+    torch = cuda
+    from mmla_audio_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(H * 1000 + W * 10 + Cin + Cc + 7)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda()
+    w1 = (torch.randn(3, 3, Cin, Cc, generator=g) * (2.0 / (9 * Cin)) ** 0.5).numpy()
+    w2 = (torch.randn(4, 1, Cc, Cc, generator=g) * (2.0 / (4 * Cc)) ** 0.5).numpy()
+    b1 = (torch.randn(Cc, generator=g) * 0.1).cuda()
+    b2 = (torch.randn(Cc, generator=g) * 0.1).cuda()
+    bn1 = ((torch.rand(Cin, generator=g) + 0.5).cuda(), (torch.randn(Cin, generator=g) * 0.3).cuda())
+    bn2 = ((torch.rand(Cc, generator=g) + 0.5).cuda(), (torch.randn(Cc, generator=g) * 0.3).cuda())
+    res = torch.randn(B, H, W, Cc, generator=g).cuda() if with_res else None
+    monkeypatch.setenv("MMLA_NET_PERSIST", "0")
+    tf32 = _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res)
+    monkeypatch.setenv("MMLA_RB_F16", "1")
+    f16 = _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res)
+    ref = _torch_ref(torch, x, w1, b1, bn1, w2, b2, bn2, res)
+    assert not torch.isnan(f16).any(), "an output pixel was never written"
+    scale = ref.abs().max().item()
+    d_ref, d_tf = (f16 - ref).abs().max().item(), (f16 - tf32).abs().max().item()
+    print(f"fp16 operands vs fp64 convs {d_ref / scale:.2e}, vs the TF32 form {d_tf / scale:.2e} of max |y| = {scale:.2f}")
+    assert d_ref <= 5e-3 * scale and d_tf <= 3e-3 * scale
+    if not with_res and H % 2 == 0:
+        hp = _fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, None, hpool=1)
+        assert torch.equal(hp, torch.maximum(f16[:, 0::2], f16[:, 1::2]))
+    for tiles in ("1", "2"):                      # other tile counts per CTA: same arithmetic per element
+        monkeypatch.setenv("MMLA_RB_TILES", tiles)
+        assert torch.equal(_fused(torch, lib, x, w1, b1, bn1, w2, b2, bn2, res), f16), f"tiles {tiles}"
+
+
+def test_fp16_operands_saturate_instead_of_overflowing(cuda, monkeypatch):
+    """Activations beyond the fp16 range (> 65504 after BN + ELU) are clamped to the largest finite half: the output stays
+    finite (an unclamped conversion would give inf, and inf * 0-weight NaN)."""
+    torch = cuda
+    from mmla_audio_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, H, W, Cin, Cc = 1, 8, 8, 32, 32
+    x = torch.randn(B, H, W, Cin, generator=g).cuda() * 1e6
+    w1 = (torch.randn(3, 3, Cin, Cc, generator=g) * 1e-3).numpy()
+    w2 = (torch.randn(4, 1, Cc, Cc, generator=g) * 1e-3).numpy()
+    z = torch.zeros(Cc).cuda()
+    one_in, one = (torch.ones(Cin).cuda(), torch.zeros(Cin).cuda()), (torch.ones(Cc).cuda(), torch.zeros(Cc).cuda())
+    monkeypatch.setenv("MMLA_NET_PERSIST", "0")
+    monkeypatch.setenv("MMLA_RB_F16", "1")
+    y = _fused(torch, lib, x, w1, z, one_in, w2, z, one, None)
+    assert torch.isfinite(y).all()
+
+
+def test_fp16_mode_activated_operand_handoff_is_bitwise_neutral(cuda, monkeypatch):
+    """Whole overlap net, precision "fp16": by default the kernel that produces a block's input (pool_shortcut_kernel or the
+    previous conv-pair kernel's epilogue) also writes ELU(BN1(x)) as fp16, and the conv-pair kernel's fill is a plain
+    asynchronous copy; MMLA_NET_F16_ACT=0 makes every fill convert from the fp32 tensor instead.  Same expression, same rounding:
+    identical probabilities.  Against the TF32 mode the probabilities agree to 2e-3."""
+    from mmla_audio_b200 import _lib, models, weights as W
+    torch = cuda
+    model = models.Model(W.OVERLAP, W.synthetic_weights(W.OVERLAP, 1234), precision="fp16")
+    x8 = torch.randint(0, 256, (6, 128, 151, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).cuda()
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MMLA_NET_F16_ACT", mode)
+        tr = _lib.trace_launches(lambda: out.__setitem__(mode, model.predict_device(x8)[0].clone()), torch)
+        names = [n for n, _ in tr]
+        assert names.count("resblock2d_f16_kernel") == 8 and names.count("stem_resblock2d_f16_kernel") == 1, names
+    monkeypatch.delenv("MMLA_NET_F16_ACT")
+    assert torch.equal(out["0"], out["1"])
+    model.set_precision("tf32")
+    ref = model.predict_device(x8)[0]
+    d = (out["1"] - ref).abs().max().item()
+    print(f"fp16-operand mode vs TF32 mode: max |dprob| {d:.2e}")
+    assert d <= 2e-3
+
+
 def test_block_fusion_switches_keep_overlap_net_output_bitwise(cuda, monkeypatch):
     """Whole overlap net, TF32 mode, uint8 and float32 images: MMLA_NET_FUSE_BLOCKS=0 (two conv_slab launches per block) vs
     MMLA_NET_FUSE_STEM2D=0 (one resblock2d_fused_kernel launch per block, stem1x1_kernel on its own) vs the default (the stem
