@@ -34,6 +34,8 @@ struct RbArgs {
     const float* stem_b;
     int img_is_u8;
     int n_ctas;               // PAIR: real CTAs (the grid is rounded up to whole pairs)
+    int u_bufs;               // persistent kernel: u slabs (2 in the fp16-operand form: epilogue 1 (k+1) writes while conv2 (k) reads)
+    int mma_hi;               // persistent kernel: the MMA issuer is the CTA's highest-numbered warp (MMLA_PS_MMA_HI)
     int hpool;                // HPOOL: Fp = H + 4, S = 128 T - 4, y = [B, H/2, W, C] = max over row pairs (2i, 2i+1) of the block output
     long long res_row_stride;
     long long img_pixels;     // H * W

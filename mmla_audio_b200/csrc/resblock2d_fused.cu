@@ -770,7 +770,7 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
                                        const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                        const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                        long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8,
-                                       const float* stem_w, const float* stem_b, int hpool);
+                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h);
 
 // img != null: stem mode — x is ignored, the block input is Conv2D(16, 1x1)(img) computed in the fill (Cin must be 16, no
 // residual, 256-thread configuration).
@@ -783,15 +783,17 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     if (B <= 0) return MMLA_OK;
     // w1_h / w2_h: the same weights as fp16 chunks (mmla_rb_arrange_weights_f16); when given the block runs with fp16 operands
     const bool f16 = w1_h && w2_h;
+    {   // the C = 32 blocks run on the persistent, warp-specialised kernel where their slabs fit (resblock2d_persist.cu; fp16
+        // operands: the stem block only)
+        const int pr = mmla_try_launch_resblock2d_persist(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, w1, b1, bn2_scale, bn2_shift, w2, b2,
+                                                          res, res_row_stride, st, img, img_is_u8, stem_w, stem_b, hpool,
+                                                          f16 && !ya ? w1_h : nullptr, f16 && !ya ? w2_h : nullptr);
+        if (pr < 0) return -pr;
+        if (pr > 0) return MMLA_OK;
+    }
     if (f16) {
         w1 = static_cast<const float*>(w1_h);      // chunk c starts c * 128 * C bytes in, in either arrangement
         w2 = static_cast<const float*>(w2_h);
-    } else
-    {   // the C = 32 blocks run on the persistent, warp-specialised kernel where their slabs fit (resblock2d_persist.cu)
-        const int pr = mmla_try_launch_resblock2d_persist(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, w1, b1, bn2_scale, bn2_shift, w2, b2,
-                                                          res, res_row_stride, st, img, img_is_u8, stem_w, stem_b, hpool);
-        if (pr < 0) return -pr;
-        if (pr > 0) return MMLA_OK;
     }
     // w1_pair / w2_pair: the same weights in the PAIR arrangement (mmla_rb_arrange_weights_pair); when given (and wanted) the
     // block runs on CTA pairs

@@ -195,9 +195,15 @@ def test_fp16_mode_activated_operand_handoff_is_bitwise_neutral(cuda, monkeypatc
         monkeypatch.setenv("MMLA_NET_F16_ACT", mode)
         tr = _lib.trace_launches(lambda: out.__setitem__(mode, model.predict_device(x8)[0].clone()), torch)
         names = [n for n, _ in tr]
-        assert names.count("resblock2d_f16_kernel") == 8 and names.count("stem_resblock2d_f16_kernel") == 1, names
+        assert names.count("resblock2d_f16_kernel") == 8 and names.count("stem_resblock2d_persist_f16_kernel") == 1, names
     monkeypatch.delenv("MMLA_NET_F16_ACT")
     assert torch.equal(out["0"], out["1"])
+    # block 1 on the one-CTA-per-item kernel instead of the persistent one: the same bits
+    monkeypatch.setenv("MMLA_NET_PERSIST", "0")
+    tr = _lib.trace_launches(lambda: out.__setitem__("np", model.predict_device(x8)[0].clone()), torch)
+    assert [n for n, _ in tr].count("stem_resblock2d_f16_kernel") == 1
+    monkeypatch.delenv("MMLA_NET_PERSIST")
+    assert torch.equal(out["np"], out["1"])
     model.set_precision("tf32")
     ref = model.predict_device(x8)[0]
     d = (out["1"] - ref).abs().max().item()
