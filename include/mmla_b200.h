@@ -203,8 +203,9 @@ int mmla_overlap_features(const int16_t* pcm, int64_t pcm_total_samples,
  *   TF32: tcgen05 tensor cores, TF32 operands (10-bit mantissa), fp32 accumulation in TMEM. */
 #define MMLA_PRECISION_FP32 0
 #define MMLA_PRECISION_TF32 1
-/*   F16 (overlap net only): as TF32, except that the res_block conv pairs (99 % of the net's FLOP) take fp16 operands
- *        (`kind::f16`: the same 11 significant bits as TF32, half the bytes; conversion saturates at 65504), fp32 accumulation. */
+/*   F16: as TF32, except that the overlap net's res_block conv pairs (99 % of its FLOP) and both nets' LSTM recurrence take
+ *        fp16 operands (`kind::f16`: the same 11 significant bits as TF32, half the bytes; conversions saturate at 65504;
+ *        the LSTM's h lies in (-1, 1)), fp32 accumulation.  Every tensor in HBM stays fp32. */
 #define MMLA_PRECISION_F16 2
 
 typedef struct MmlaNet MmlaNet;   /* opaque */

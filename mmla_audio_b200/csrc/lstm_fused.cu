@@ -33,6 +33,7 @@
 // CTA never overwrites the h its peer may still be re-staging).  In the natural [b][..] layouts every lane touched
 // its own 128-byte line: 17k of the 60k cycles of a step went into those loads (scripts/prof_lstm.py).  Only the
 // final h is written in the caller's [B][256] layout.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 
@@ -45,7 +46,7 @@ constexpr int kRows = 128;                  // clips per CTA
 constexpr int kSubTile = 128 * 128;         // bytes of one 128x32 TF32 sub-tile
 constexpr int kBChunkFloats = 4 * 256 * 4;  // one weight chunk = two MMAs: 4 K-slabs (K=16) x 256 columns x 4
 constexpr int kBChunkBytes = kBChunkFloats * 4;   // 16 KB
-constexpr int kChunksPerStep = 64;          // 4 passes x 8 K-sub-tiles x 2 halves
+constexpr int kChunksPerStep = 64;          // 4 passes x 8 K-sub-tiles x 2 halves (fp16 operands: 4 x 4 x 2 = 32 chunks of K = 32)
 constexpr int kStages = 6;                   // 96 KB in flight: the stream into a CTA is ring bytes / ~2 000 cycles of L2 latency
 constexpr int kEpiThreads = 256;            // warps 0..7: gate epilogue + h re-staging
 constexpr int kProducers = 2;               // TMA producer warps (see the producer loop)
@@ -70,6 +71,7 @@ struct LstmArgs {
     float* c[2];            // row-tiled cell state, ceil(B/128) x 64 x 128 x 4 floats
     float* hx[2];           // row-tiled h exchange, 2 x the size of c
     int B, T;
+    int f16;                // fp16 operands (h in (-1, 1) and the recurrent weights as halves, fp32 accumulation): wr = fp16 chunk stream
     long long* stamps;      // diagnostics: clock64 timeline of CTA (stamp_cta, dir 0), 16 slots per step (null = off)
     int stamp_cta;
 };
@@ -113,6 +115,11 @@ __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
 // Warp-specialised: warp 8 streams the weights (TMA), warp 9 issues the MMAs, warps 0..7 run the
 // gate epilogue.  A step is four accumulator passes of 64 units ([i|f|c~|o] x 64 = 256 TMEM
 // columns); the two TMEM halves ping-pong so the MMAs of pass p+1 overlap the epilogue of pass p.
+// F16: h_{t-1} and U as fp16 (`kind::f16`, K = 16 per MMA).  h = o * tanh(c) lies in (-1, 1), so fp16 keeps exactly the 11
+// significant bits TF32 keeps and no range question arises; a 16 KB weight chunk then covers K = 32 instead of 16, i.e. the
+// stream a step pulls through the ring — what paces the recurrence, see kStages — is half as long.  The operand tiles become
+// four 128 x 64-half sub-tiles (the same 128-byte swizzled rows).
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs a) {
     extern __shared__ unsigned char smem_dyn[];
     // offset applied to the __shared__ array itself so accesses stay LDS/STS (an integer round-trip makes them generic)
@@ -122,7 +129,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     const int half = blockIdx.x & 1;                          // rank in the 2-CTA cluster = which 128 units
     const int b0 = (blockIdx.x >> 1) * kRows;
     constexpr int kPasses = 2;                                // 64-unit passes per CTA and step
-    constexpr int kChunksCta = kChunksPerStep / 2;            // weight chunks per CTA and step
+    constexpr int kChunksCta = kChunksPerStep / (F16 ? 4 : 2);   // weight chunks per CTA and step
+    constexpr int kSubTiles = F16 ? 4 : 8;                    // 128-byte-row K sub-tiles of the h operand
     const float* xp = a.xp[dir];
     const float* wr = a.wr[dir];
     float* hg = a.h[dir];
@@ -132,8 +140,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
     float* hx0 = a.hx[dir] + tile * tile_floats;                // buffer of even steps; odd steps: + hx_stride
     const long long hx_stride = ((a.B + kRows - 1) / kRows) * tile_floats;
     const int T = a.T;
-    constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
-                                (static_cast<uint32_t>(128 >> 4) << 24);   // f32 += tf32 x tf32, M=128, N=256
+    constexpr uint32_t kIdesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (static_cast<uint32_t>(256 >> 3) << 17) |
+                                (static_cast<uint32_t>(128 >> 4) << 24);   // f32 += tf32 x tf32 (or f16 x f16), M=128, N=256
 
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t dcol = tmem + static_cast<uint32_t>(buf * 256);
                     uint64_t dA = dA0;
-                    for (int kc = 0; kc < 8; ++kc, dA += static_cast<uint64_t>(kSubTile / 16)) {
+                    for (int kc = 0; kc < kSubTiles; ++kc, dA += static_cast<uint64_t>(kSubTile / 16)) {
                         // K-sub-tile kc: chunk 2kc covers its K columns 0..15, chunk 2kc+1 columns 16..31 (+64 B inside
                         // the swizzled row = 4 descriptor units); 32 B per K=8 MMA
                         const uint64_t bd0 = dB0 + static_cast<uint64_t>(stg * kStageUnits);
@@ -219,6 +227,13 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                                 const uint64_t ad = dA + static_cast<uint64_t>(m * 2);
                                 const uint64_t bd = bd0 + static_cast<uint64_t>((m >> 1) * kStageUnits + (m & 1) * 2 * 256);
                                 const uint32_t acc = (kc | m) != 0 ? 1u : 0u;
+                                if constexpr (F16)
+                                    asm volatile(
+                                        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol),
+                                        "l"(ad), "l"(bd), "r"(kIdesc), "r"(acc)
+                                        : "memory");
+                                else
                                 asm volatile(
                                     "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol),
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                             }
                             umma_commit_to(&s.empty[stg]);
                             umma_commit_to(&s.empty[stg + 1]);
-                            if (kc == 7) umma_commit_to(&s.tfull[buf]);
+                            if (kc == kSubTiles - 1) umma_commit_to(&s.tfull[buf]);
                         }
                         stg += 2;
                         if (stg == kStages) { stg = 0; par ^= 1u; }
@@ -319,6 +334,13 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int uq = uq0 + 2 * (i0 + j);
+                    if constexpr (F16) {
+                        // four units = 8 bytes: half of the 16-byte column (uq >> 1) & 7 of K sub-tile uq >> 4 (64 halves per row)
+                        const __half2 lo = __floats2half2_rn(v[j].x, v[j].y), hi = __floats2half2_rn(v[j].z, v[j].w);
+                        *reinterpret_cast<uint2*>(&s.H[uq >> 4][0] + r * 128 + ((((uq >> 1) & 7) ^ (r & 7)) << 4) + (uq & 1) * 8) =
+                            make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                        continue;
+                    }
                     const int kc = uq >> 3, q = uq & 7;
                     *reinterpret_cast<uint4*>(&s.H[kc][0] + r * 128 + ((q ^ (r & 7)) << 4)) =
                         make_uint4(tf32_round(v[j].x), tf32_round(v[j].y), tf32_round(v[j].z), tf32_round(v[j].w));
@@ -428,6 +450,28 @@ void mmla_lstm_arrange_weights(const float* U, float* out) {
             }
 }
 
+// fp16 form: chunk (pass, kc, kh) -> [4 octets][256 n][8 halves] with k = 64 kc + 32 kh + 8 octet + e (K = 32 per 16 KB chunk),
+// columns as above; round-to-nearest-even halves.  out: 32 chunks x 8192 halves (half the bytes of the TF32 stream).
+long long mmla_lstm_arranged_halves() { return 32LL * 8192; }
+void mmla_lstm_arrange_weights_f16(const float* U, uint16_t* out) {
+    for (int pass = 0; pass < 4; ++pass)
+        for (int kc = 0; kc < 4; ++kc)
+            for (int kh = 0; kh < 2; ++kh) {
+                uint16_t* chunk = out + (static_cast<long long>((pass * 4 + kc) * 2 + kh)) * 8192;
+                for (int oct = 0; oct < 4; ++oct)
+                    for (int n = 0; n < 256; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = kc * 64 + kh * 32 + oct * 8 + e;
+                            const int gate = n / 64;
+                            const int unit = 64 * pass + (n % 64);
+                            float v = U[static_cast<long long>(k) * 1024 + gate * 256 + unit];
+                            v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+                            const __half h = __float2half_rn(v);
+                            memcpy(&chunk[(oct * 256 + n) * 8 + e], &h, 2);
+                        }
+            }
+}
+
 static long long* g_lstm_stamps = nullptr;
 static int g_lstm_stamp_cta = 0;
 extern "C" __attribute__((visibility("default"))) void mmla_debug_lstm_stamps(long long* dev_stamps, int32_t cta) {
@@ -440,14 +484,16 @@ long long mmla_lstm_tile_floats(long long B) { return ((B + kRows - 1) / kRows) 
 
 // xp_*: row-tiled input projections (xproj_fused.cu); h_*: [B][256] final hidden state (output);
 // scratch_*: 3 * mmla_lstm_tile_floats(B) floats each.
+// f16 != 0: wr_f / wr_b point at the fp16 chunk streams (mmla_lstm_arrange_weights_f16)
 int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
-                           float* h_b, float* scratch_f, float* scratch_b, long long B, int T, cudaStream_t st) {
+                           float* h_b, float* scratch_f, float* scratch_b, long long B, int T, cudaStream_t st, int f16) {
     MMLA_REQUIRE(B > 0 && B < (1LL << 22) && T >= 1, MMLA_EINVAL, "lstm_fused: bad batch/T");
     static MmlaPerDeviceOnce attr_once;                          // cudaFuncSetAttribute is per device
     const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(LstmSmem) + 1024);
     if (!attr_set) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     LstmArgs a;
     a.xp[0] = xp_f; a.xp[1] = xp_b; a.wr[0] = wr_f; a.wr[1] = wr_b;
@@ -455,6 +501,7 @@ int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr
     a.c[0] = scratch_f; a.c[1] = scratch_b;
     a.hx[0] = scratch_f + mmla_lstm_tile_floats(B); a.hx[1] = scratch_b + mmla_lstm_tile_floats(B);
     a.B = static_cast<int>(B); a.T = T;
+    a.f16 = f16;
     a.stamps = g_lstm_stamps; a.stamp_cta = g_lstm_stamp_cta;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -469,8 +516,9 @@ int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel, a));
-    mmla_count_launch("lstm_fused_kernel", st);
+    if (f16) MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<true>, a));
+    else MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<false>, a));
+    mmla_count_launch(f16 ? "lstm_fused_f16_kernel" : "lstm_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }

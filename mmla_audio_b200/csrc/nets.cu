@@ -556,6 +556,7 @@ struct MmlaNet {
     ConvW lstm_in[2];                     // [feat,1024] projection (bias = LSTM bias)
     ConvW lstm_rec[2];                    // [256,1024] recurrent (bias = zeros)
     const float* lstm_rec_fused[2] = {nullptr, nullptr};   // chunk stream for lstm_fused_kernel
+    const float* lstm_rec_f16[2] = {nullptr, nullptr};     // ... as fp16 chunks (MMLA_PRECISION_F16)
     const float* lstm_in_fused[2] = {nullptr, nullptr};    // chunk stream for xproj_fused_kernel
     const float* dense_k = nullptr;
     const float* dense_b = nullptr;
@@ -607,8 +608,10 @@ int mmla_launch_xproj_fused(const float* seq, const float* w_f, const float* w_b
                             float* xp_f, float* xp_b, long long B, int T, cudaStream_t st);
 long long mmla_lstm_arranged_floats();
 void mmla_lstm_arrange_weights(const float* U, float* out);
+long long mmla_lstm_arranged_halves();
+void mmla_lstm_arrange_weights_f16(const float* U, uint16_t* out);
 int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr_f, const float* wr_b, float* h_f,
-                           float* h_b, float* scratch_f, float* scratch_b, long long B, int T, cudaStream_t st);
+                           float* h_b, float* scratch_f, float* scratch_b, long long B, int T, cudaStream_t st, int f16 = 0);
 
 namespace {
 
@@ -807,6 +810,15 @@ EXPORT int mmla_net_create(int32_t kind, int32_t n_classes, int32_t head, const 
             stage.resize(stage.size() + mmla_lstm_arranged_floats());
             mmla_lstm_arrange_weights(wr_src, stage.data() + off);
             fixes.push_back({&net->lstm_rec_fused[d], off});
+            {
+                const long long halves = mmla_lstm_arranged_halves();
+                std::vector<uint16_t> hbuf(static_cast<size_t>(halves));
+                mmla_lstm_arrange_weights_f16(wr_src, hbuf.data());
+                const long long off_h = static_cast<long long>(stage.size());       // still 16-byte aligned: the chunk stream above is
+                stage.resize(stage.size() + static_cast<size_t>(halves / 2));
+                memcpy(stage.data() + off_h, hbuf.data(), static_cast<size_t>(halves) * 2);
+                fixes.push_back({&net->lstm_rec_f16[d], off_h});
+            }
             const long long off_in = static_cast<long long>(stage.size());
             stage.resize(stage.size() + mmla_xproj_arranged_floats());
             mmla_xproj_arrange_weights(wi_src, stage.data() + off_in);
@@ -879,8 +891,9 @@ EXPORT int mmla_net_forward(MmlaNet* net, const void* x, int32_t x_is_u8, int64_
 
 EXPORT int mmla_net_forward_cepstra(MmlaNet* net, const float* cepstra, int64_t cep_clip_stride, int32_t n_frames, int64_t batch,
                                     void* workspace, int64_t workspace_bytes, float* prob, int32_t* labels, void* stream) {
-    MMLA_REQUIRE(net && net->kind == MMLA_NET_SPEAKER && net->precision == MMLA_PRECISION_TF32 && net->stem_pad.k_tc, MMLA_EUNSUP,
-                 "net_forward_cepstra: needs the speaker net in TF32 tensor-core mode");
+    MMLA_REQUIRE(net && net->kind == MMLA_NET_SPEAKER && (net->precision == MMLA_PRECISION_TF32 || net->precision == MMLA_PRECISION_F16) &&
+                     net->stem_pad.k_tc,
+                 MMLA_EUNSUP, "net_forward_cepstra: needs the speaker net in a tensor-core mode (TF32 / F16)");
     MMLA_REQUIRE(n_frames >= 1 && n_frames <= 256 && cep_clip_stride >= static_cast<int64_t>(n_frames) * 16, MMLA_EINVAL,
                  "net_forward_cepstra: bad cepstra geometry (n_frames %d, clip stride %lld)", n_frames,
                  static_cast<long long>(cep_clip_stride));
@@ -1158,8 +1171,10 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
         }
         if (fused_lstm) {
             // one persistent launch: both directions, all time steps (lstm_fused.cu)
-            if ((rc = mmla_launch_lstm_fused(xp[0], xp[1], net->lstm_rec_fused[0], net->lstm_rec_fused[1], hdir[0], hdir[1],
-                                             cst, cst + 3 * Bp * 256, B, T, st)))
+            const bool l16 = f16 && net->lstm_rec_f16[0] && net->lstm_rec_f16[1];     // fp16 mode: h and U as halves
+            if ((rc = mmla_launch_lstm_fused(xp[0], xp[1], l16 ? net->lstm_rec_f16[0] : net->lstm_rec_fused[0],
+                                             l16 ? net->lstm_rec_f16[1] : net->lstm_rec_fused[1], hdir[0], hdir[1], cst,
+                                             cst + 3 * Bp * 256, B, T, st, l16 ? 1 : 0)))
                 return rc;
         }
         for (int d = 0; d < 2 && !fused_lstm; ++d) {
@@ -1308,8 +1323,7 @@ EXPORT int mmla_net_set_precision(MmlaNet* net, int32_t mode) {
     MMLA_REQUIRE(net != nullptr, MMLA_EINVAL, "net_set_precision: null net");
     MMLA_REQUIRE(mode == MMLA_PRECISION_FP32 || mode == MMLA_PRECISION_TF32 || mode == MMLA_PRECISION_F16, MMLA_EINVAL,
                  "net_set_precision: unknown mode %d", mode);
-    MMLA_REQUIRE(mode != MMLA_PRECISION_F16 || net->kind == MMLA_NET_OVERLAP, MMLA_EUNSUP,
-                 "net_set_precision: the fp16-operand mode exists for the overlap net's conv pairs only");
+
     net->precision = mode;
     return MMLA_OK;
 }

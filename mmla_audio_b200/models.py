@@ -65,8 +65,9 @@ class Model:
     ``[B, n_classes]`` numpy out.  ``predict_device`` keeps everything on the GPU."""
 
     def __init__(self, spec: NetSpec, weights: Dict[str, np.ndarray], precision: str = "fp32"):
-        """precision: 'fp32' (CUDA-core implicit GEMM, bit-faithful layer semantics) or 'tf32'
-        (tcgen05 tensor cores, TF32 operands, fp32 accumulation)."""
+        """precision: 'fp32' (CUDA-core implicit GEMM, bit-faithful layer semantics), 'tf32' (tcgen05 tensor cores,
+        TF32 operands, fp32 accumulation) or 'fp16' (as 'tf32', with fp16 operands — the same 11 significant bits, half
+        the bytes — in the overlap net's conv pairs and in the LSTM recurrence of both nets)."""
         self.spec = spec
         self.weights = weights
         self._handle = None
@@ -85,7 +86,7 @@ class Model:
 
     def set_precision(self, precision: str) -> None:
         if precision not in PRECISION_IDS:
-            raise ValueError("precision must be 'fp32', 'tf32' or 'fp16' (overlap net only)")
+            raise ValueError("precision must be 'fp32', 'tf32' or 'fp16'")
         _lib.check(self._lib.mmla_net_set_precision(self._handle, PRECISION_IDS[precision]),
                    "mmla_net_set_precision")
         self.precision = precision
@@ -106,7 +107,7 @@ class Model:
         """x: CUDA tensor [B,128,151,3] uint8|float32 (overlap) or [B,256,39] float32 (speaker).
         Returns (prob float32 CUDA [B,n], labels int32 CUDA [B])."""
         torch, lib = self._torch, self._lib
-        pad40 = (self.spec.ndim == 1 and self.precision == "tf32" and tuple(x.shape[1:]) == (256, 40)
+        pad40 = (self.spec.ndim == 1 and self.precision in ("tf32", "fp16") and tuple(x.shape[1:]) == (256, 40)
                  and x.dtype == torch.float32)      # channel-padded features (speaker_features_batch(row_stride=40))
         if tuple(x.shape[1:]) != self.input_shape and not pad40:
             raise ValueError(f"expected input [B, {self.input_shape}], got {tuple(x.shape)}")

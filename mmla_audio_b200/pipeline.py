@@ -170,7 +170,7 @@ class SpeakerPipeline(_HostApi):
     def _run_slice(self, torch, pcm_dev, slot: int):
         B, L = pcm_dev.shape
         T = self.cfg.num_frames(L)
-        if self.model.precision == "tf32" and self.cfg.numcep == 13 and T <= SPEAKER_FRAMES:
+        if self.model.precision in ("tf32", "fp16") and self.cfg.numcep == 13 and T <= SPEAKER_FRAMES:
             # label pipeline: MFCC-13 rows only; delta / delta-delta / padding happen inside the classifier's stem
             # kernel, so the [B,256,39] feature tensor never exists in HBM
             cep = self._feat.get(slot)

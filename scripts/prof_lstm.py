@@ -7,7 +7,7 @@ from mmla_audio_b200.pipeline import SpeakerPipeline
 
 lib = _lib.load()
 spec = W.speaker_spec(10, "sigmoid")
-pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321), precision="tf32"))
+pipe = SpeakerPipeline(models.Model(spec, W.synthetic_weights(spec, 4321), precision=__import__("os").environ.get("PRECISION", "tf32")))
 pcm = synth.synth_clips(0, int(os.environ.get("CLIPS", "4096")), 24000)
 for _ in range(3):
     pipe.run_device(pcm)

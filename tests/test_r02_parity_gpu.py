@@ -42,18 +42,21 @@ def test_bench_batch_tf32_labels_vs_oracle(cuda):
     spec = W.speaker_spec(10, "sigmoid")
     w = W.synthetic_weights(spec, 4321)
     n = 4096
-    pipe = SpeakerPipeline(models.Model(spec, w, precision="tf32"))
-    labels, prob = pipe.run_device(dsynth.synth_clips(0, n, 24000))
     ref = oracle_speaker_probs(0, n, 24000, w, spec)
-    got, lg, lr = prob.cpu().numpy(), labels.cpu().numpy(), ref.argmax(1)
-    d = np.abs(got - ref).max()
-    agree = float((lg == lr).mean())
+    lr = ref.argmax(1)
     clear = _margin(ref) > 1e-2
-    print(f"bench batch (4096 clips) tf32 vs ORACLE: label agreement {agree:.4f}, max |dprob| {d:.2e}, "
-          f"clear-margin clips {int(clear.sum())}")
-    assert d <= 5e-3                                             # TF32 operand rounding (2^-11 relative)
-    assert (lg[clear] == lr[clear]).all()
-    assert agree >= 0.95
+    # "fp16" = the same pipeline with the LSTM recurrence on fp16 operands (h in (-1, 1): the 11 significant bits TF32 keeps)
+    for precision in ("tf32", "fp16"):
+        pipe = SpeakerPipeline(models.Model(spec, w, precision=precision))
+        labels, prob = pipe.run_device(dsynth.synth_clips(0, n, 24000))
+        got, lg = prob.cpu().numpy(), labels.cpu().numpy()
+        d = np.abs(got - ref).max()
+        agree = float((lg == lr).mean())
+        print(f"bench batch (4096 clips) {precision} vs ORACLE: label agreement {agree:.4f}, max |dprob| {d:.2e}, "
+              f"clear-margin clips {int(clear.sum())}")
+        assert d <= 5e-3                                         # operand rounding (2^-11 relative)
+        assert (lg[clear] == lr[clear]).all()
+        assert agree >= 0.95
 
 
 @pytest.mark.parametrize("precision", ["tf32", "fp16"])
