@@ -35,6 +35,7 @@
 // final h is written in the caller's [B][256] layout.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -119,22 +120,25 @@ __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
 // significant bits TF32 keeps and no range question arises; a 16 KB weight chunk then covers K = 32 instead of 16, i.e. the
 // stream a step pulls through the ring — what paces the recurrence, see kStages — is half as long.  The operand tiles become
 // four 128 x 64-half sub-tiles (the same 128-byte swizzled rows).
-template <bool F16>
+// NP: CTAs per 128-clip tile (the cluster size).  2: two 64-unit passes per CTA and step (4096 speaker clips = 128 CTAs); 4: one
+// pass each — chosen for small batches (the overlap net's 512 clips: 32 CTAs instead of 16), where a step is paced by the gate
+// epilogue's MUFU work of ONE SM and not by anything shared.
+template <bool F16, int NP>
 __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs a) {
     extern __shared__ unsigned char smem_dyn[];
     // offset applied to the __shared__ array itself so accesses stay LDS/STS (an integer round-trip makes them generic)
     LstmSmem& s = *reinterpret_cast<LstmSmem*>(smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
-    const int half = blockIdx.x & 1;                          // rank in the 2-CTA cluster = which 128 units
-    const int b0 = (blockIdx.x >> 1) * kRows;
-    constexpr int kPasses = 2;                                // 64-unit passes per CTA and step
-    constexpr int kChunksCta = kChunksPerStep / (F16 ? 4 : 2);   // weight chunks per CTA and step
+    const int half = blockIdx.x % NP;                         // rank in the cluster = which 256 / NP units
+    const int b0 = (blockIdx.x / NP) * kRows;
+    constexpr int kPasses = 4 / NP;                           // 64-unit passes per CTA and step
+    constexpr int kChunksCta = kChunksPerStep / (F16 ? 2 : 1) / NP;   // weight chunks per CTA and step
     constexpr int kSubTiles = F16 ? 4 : 8;                    // 128-byte-row K sub-tiles of the h operand
     const float* xp = a.xp[dir];
     const float* wr = a.wr[dir];
     float* hg = a.h[dir];
-    const long long tile = blockIdx.x >> 1;
+    const long long tile = blockIdx.x / NP;
     const long long tile_floats = 64LL * 512;                  // one row-tiled [64 quads][128 rows][4] block
     float* cg = a.c[dir] + tile * tile_floats;
     float* hx0 = a.hx[dir] + tile * tile_floats;                // buffer of even steps; odd steps: + hx_stride
@@ -153,8 +157,8 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
             mbar_init(&s.tempty[i], 8);           // one arrival per epilogue warp
         }
         mbar_init(&s.hready, 1);
-        mbar_init(&s.peer[0], 1);
-        mbar_init(&s.peer[1], 1);
+        mbar_init(&s.peer[0], NP - 1);           // one arrival per peer CTA
+        mbar_init(&s.peer[1], NP - 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -351,13 +355,14 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
         // pull the xp rows of time step t into L2 one step ahead (they stream from HBM otherwise):
         // 128 rows x 4 KB = 4096 lines, 16 per thread
         auto prefetch_xp = [&](int t) {
-            // this half's 128 units of every gate: 4 runs of 32 quads x 2 KB = 512 lines each, 8 lines per thread
+            // this CTA's 256 / NP units of every gate: 4 runs of 64 / NP quads x 2 KB (16 lines per quad), 16 / NP lines per thread
             const float* base = xp + (tile * T + t) * (256LL * 512);
+            constexpr int kQuads = 64 / NP, kLinesGate = kQuads * 16;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int line = tid + i * kEpiThreads;               // 0..2047
-                const int g = line >> 9, l = line & 511;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (64 * g + 32 * half) * 512 + l * 32));
+            for (int i = 0; i < 16 / NP; ++i) {
+                const int line = tid + i * kEpiThreads;               // 0 .. 4 kLinesGate - 1
+                const int g = line / kLinesGate, l = line % kLinesGate;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (64 * g + kQuads * half) * 512 + l * 32));
             }
         };
 
@@ -395,8 +400,11 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_fused_kernel(const LstmArgs 
                     // two barriers used alternately: a barrier can then never run two phases ahead of its waiter
                     // (the peer cannot pass step s+1's hand-over without this CTA's arrive for s+1)
                     uint64_t* pb = &s.peer[step & 1];
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(pb)), "r"(half ^ 1));
-                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#pragma unroll
+                    for (int pr = 1; pr < NP; ++pr) {                  // every peer's barrier expects NP - 1 arrivals
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(pb)), "r"((half + pr) % NP));
+                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+                    }
                     const uint32_t parity = static_cast<uint32_t>((step >> 1) & 1);
                     uint32_t ok = 0;
                     for (uint32_t i = 0; i < (1u << 24) && !ok; ++i)
@@ -492,8 +500,17 @@ int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr
     const bool attr_set = !attr_once.first();
     const int smem = static_cast<int>(sizeof(LstmSmem) + 1024);
     if (!attr_set) {
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(lstm_fused_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    // four CTAs per tile while they all fit on the chip at once (a second wave would double the recurrence's latency)
+    const long long tiles = (B + kRows - 1) / kRows;
+    int np = (2 * tiles * 4 <= mmla_num_sms()) ? 4 : 2;
+    if (const char* e = getenv("MMLA_LSTM_CLUSTER")) {
+        const int v = atoi(e);
+        if (v == 2 || v == 4) np = v;
     }
     LstmArgs a;
     a.xp[0] = xp_f; a.xp[1] = xp_b; a.wr[0] = wr_f; a.wr[1] = wr_b;
@@ -505,19 +522,21 @@ int mmla_launch_lstm_fused(const float* xp_f, const float* xp_b, const float* wr
     a.stamps = g_lstm_stamps; a.stamp_cta = g_lstm_stamp_cta;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2u * static_cast<unsigned>((B + kRows - 1) / kRows), 2, 1);   // two CTAs (unit halves) per 128-clip tile
+    cfg.gridDim = dim3(static_cast<unsigned>(np) * static_cast<unsigned>(tiles), 2, 1);   // np CTAs (unit ranges) per 128-clip tile
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = static_cast<size_t>(smem);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(np);
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (f16) MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<true>, a));
-    else MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<false>, a));
+    if (f16 && np == 4) MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<true, 4>, a));
+    else if (f16) MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<true, 2>, a));
+    else if (np == 4) MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<false, 4>, a));
+    else MMLA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lstm_fused_kernel<false, 2>, a));
     mmla_count_launch(f16 ? "lstm_fused_f16_kernel" : "lstm_fused_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
