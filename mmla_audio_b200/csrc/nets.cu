@@ -21,6 +21,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include <cuda_fp16.h>
+
 #include "conv_common.cuh"
 
 namespace {
@@ -251,6 +253,7 @@ __device__ __forceinline__ uint32_t act_pack_h2(float lo, float hi) {
 // took 0.88 ms per 512 clips, this is bound by reading z once).
 // img != null (first block, stem folded into the conv-pair kernel): x is never materialised — the block input at the pooled
 // pixel is the stem Conv2D(16, 1x1) of the 3-channel image, recomputed here with stem1x1_kernel's expression (Cin = 16).
+template <bool Z16>
 __global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                                             const float* __restrict__ ws, const float* __restrict__ bs,
                                                             float* __restrict__ y, long long B, int H, int W, int Cin, int N,
@@ -291,17 +294,27 @@ __global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restr
             const int wo = min(kPix * g + u, Wo - 1);  // the tail group recomputes the row's last pixel (not stored)
             const int w0 = 2 * wo;
             const long long pin = (b * H + h0) * W + w0;
-            // z_half: z = [B, H/2, W, N] already holds the maximum over each window's two rows (resblock2d_fused.cu, HPOOL)
-            const float* zb = z + (z_half ? ((b * Ho + ho) * W + w0) : pin) * N + 4 * q;
-            m[u] = *reinterpret_cast<const float4*>(zb);
-            auto mx = [&](const float* ptr) {
-                const float4 v = *reinterpret_cast<const float4*>(ptr);
+            // z_half: z = [B, H/2, W, N] already holds the maximum over each window's two rows (resblock2d_fused.cu, HPOOL);
+            // Z16: ... as fp16 (fp16-operand mode: the conv branch's output in half the bytes)
+            const long long zoff = (z_half ? ((b * Ho + ho) * W + w0) : pin) * N + 4 * q;
+            auto ldz = [&](long long d) {               // four channels at element offset d from this pixel
+                if constexpr (Z16) {
+                    const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(z) + zoff + d);
+                    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+                    return make_float4(lo.x, lo.y, hi.x, hi.y);
+                } else {
+                    return *reinterpret_cast<const float4*>(z + zoff + d);
+                }
+            };
+            m[u] = ldz(0);
+            auto mx = [&](long long d) {
+                const float4 v = ldz(d);
                 m[u].x = fmaxf(m[u].x, v.x); m[u].y = fmaxf(m[u].y, v.y); m[u].z = fmaxf(m[u].z, v.z); m[u].w = fmaxf(m[u].w, v.w);
             };
-            if (w0 + 1 < W) mx(zb + N);                // 'same' pooling: the missing right / bottom neighbours are -inf
+            if (w0 + 1 < W) mx(N);                     // 'same' pooling: the missing right / bottom neighbours are -inf
             if (!z_half && h0 + 1 < H) {
-                mx(zb + static_cast<long long>(W) * N);
-                if (w0 + 1 < W) mx(zb + static_cast<long long>(W) * N + N);
+                mx(static_cast<long long>(W) * N);
+                if (w0 + 1 < W) mx(static_cast<long long>(W) * N + N);
             }
             xb[u] = x + pin * Cin;
             acc[u] = bias;
@@ -596,7 +609,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  const float* stem_w = nullptr, const float* stem_b = nullptr, int hpool = 0,
                                  const float* w1_pair = nullptr, const float* w2_pair = nullptr, const void* w1_h = nullptr,
                                  const void* w2_h = nullptr, const void* xa = nullptr, void* ya = nullptr,
-                                 const float* ya_scale = nullptr, const float* ya_shift = nullptr);
+                                 const float* ya_scale = nullptr, const float* ya_shift = nullptr, int y_f16 = 0);
 void mmla_rb_arrange_weights_pair(const float* w, int K, int N, float* out);
 long long mmla_rb_f16_arranged_halves(int K, int N);
 void mmla_rb_arrange_weights_f16(const float* w, int K, int N, uint16_t* out);
@@ -1091,19 +1104,26 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 const bool fold = stem_folded && bi == 0;
                 // the maximum over each pooling window's two rows is taken in the conv-pair kernel's epilogue (HPOOL): Bf is then
                 // [B, H/2, W, C] and the pooling kernel reads half as much (MMLA_NET_FUSE_HPOOL=0: full-resolution Bf)
-                bool hpool = false;
+                bool hpool = false, z16 = false;
                 if (tc && pair_fusable(blk, H, W) && pool_fusable(blk) && H % 2 == 0) {
                     const char* e = getenv("MMLA_NET_FUSE_HPOOL");
                     hpool = !(e && e[0] == '0');
                 }
                 if (tc && pair_fusable(blk, H, W)) {
                     const bool h16 = f16 && blk.conv1.k_h && blk.conv2.k_h;
+                    {   // fp16 mode, OPT-IN (MMLA_NET_F16_Z=1): the row-pooled conv output goes to the pooling kernel as fp16.  Measured
+                        // 3.488 -> 3.470 ms per 512 clips only (pool_shortcut_kernel 0.645 -> 0.625 ms: it is not bound by reading z),
+                        // which does not pay for one more 11-bit rounding on the conv branch: off by default.
+                        const char* e = getenv("MMLA_NET_F16_Z");
+                        z16 = h16 && hpool && pool_fusable(blk) && e && e[0] == '1';
+                    }
                     if ((rc = mmla_launch_resblock2d_fused(X, Bf, B, H, W, blk.conv1.cin, blk.conv1.cout, blk.bn1.scale, blk.bn1.shift,
                                                            blk.conv1.k_tc, blk.conv1.b, blk.bn2.scale, blk.bn2.shift, blk.conv2.k_tc,
                                                            blk.conv2.b, nullptr, 0, st, fold ? xin : nullptr, x_is_u8,
                                                            fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0,
                                                            blk.conv1.k_tc2, blk.conv2.k_tc2, h16 ? blk.conv1.k_h : nullptr,
-                                                           h16 ? blk.conv2.k_h : nullptr, h16 && xa_in ? hact[hcur] : nullptr)))
+                                                           h16 ? blk.conv2.k_h : nullptr, h16 && xa_in ? hact[hcur] : nullptr, nullptr,
+                                                           nullptr, nullptr, z16 ? 1 : 0)))
                         return rc;
                 } else {
                     if ((rc = launch_conv(blk.conv1, X, 0, B, H, W, &blk.bn1, act_kind, nullptr, 0, A, st, tc))) return rc;
@@ -1114,10 +1134,16 @@ static int forward_impl(MmlaNet* net, const void* x, int32_t x_is_u8, int32_t ce
                 if (tc && pool_fusable(blk)) {
                     // MaxPool + stride-2 shortcut + add in one pass (reads X and Bf, writes A)
                     const BnW* nbn = f16 ? next_bn(bi, C, Ho, Wo) : nullptr;
-                    pool_shortcut_kernel<<<ew_grid(B * Ho * ((Wo + 3) / 4) * C / 4), 256, wbytes, st>>>(
-                        X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W, blk.shortcut.cin, C, fold ? xin : nullptr, x_is_u8,
-                        fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0, nbn ? hact[hcur ^ 1] : nullptr,
-                        nbn ? nbn->scale : nullptr, nbn ? nbn->shift : nullptr);
+                    if (z16)
+                        pool_shortcut_kernel<true><<<ew_grid(B * Ho * ((Wo + 3) / 4) * C / 4), 256, wbytes, st>>>(
+                            X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W, blk.shortcut.cin, C, fold ? xin : nullptr, x_is_u8,
+                            fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, 1, nbn ? hact[hcur ^ 1] : nullptr,
+                            nbn ? nbn->scale : nullptr, nbn ? nbn->shift : nullptr);
+                    else
+                        pool_shortcut_kernel<false><<<ew_grid(B * Ho * ((Wo + 3) / 4) * C / 4), 256, wbytes, st>>>(
+                            X, Bf, blk.shortcut.k, blk.shortcut.b, A, B, H, W, blk.shortcut.cin, C, fold ? xin : nullptr, x_is_u8,
+                            fold ? net->stem.k : nullptr, fold ? net->stem.b : nullptr, hpool ? 1 : 0, nbn ? hact[hcur ^ 1] : nullptr,
+                            nbn ? nbn->scale : nullptr, nbn ? nbn->shift : nullptr);
                     mmla_count_launch("pool_shortcut_kernel", st);
                     MMLA_CUDA_CHECK(cudaGetLastError());
                     have_xa = nbn != nullptr;

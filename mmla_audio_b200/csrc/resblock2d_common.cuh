@@ -29,6 +29,7 @@ struct RbArgs {
     void* ya;                 // F16: ELU(BN(y)) as fp16 [B,H,W,C] for the NEXT block (its BN1 = ya_scale / ya_shift), or null
     const float* ya_scale;
     const float* ya_shift;
+    int y_f16;                // F16 + HPOOL: the row-pooled conv output y = [B, H/2, W, C] is written as fp16 (pool_shortcut_kernel reads it)
     const void* img;          // STEM: the classifier input [B,H,W,3] (uint8 or float32); x is unused
     const float* stem_w;      // STEM: Conv2D(16, 1x1) weights [3][16] and bias [16] (overlap_detector_temp.py:283)
     const float* stem_b;

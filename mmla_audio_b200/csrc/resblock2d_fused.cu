@@ -572,9 +572,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 && !RES ? 3 : (THREADS
                     if (pixoff[i] >= 0) {
                         const float4 v0 = *reinterpret_cast<const float4*>(stg + (8 * i + 2 * rsub) * 36 + 4 * seg);
                         const float4 v1 = *reinterpret_cast<const float4*>(stg + (8 * i + 2 * rsub + 1) * 36 + 4 * seg);
-                        *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) =
-                            make_float4(fmaxf(v0.x + bv.x, v1.x + bv.x), fmaxf(v0.y + bv.y, v1.y + bv.y),
-                                        fmaxf(v0.z + bv.z, v1.z + bv.z), fmaxf(v0.w + bv.w, v1.w + bv.w));
+                        const float4 o = make_float4(fmaxf(v0.x + bv.x, v1.x + bv.x), fmaxf(v0.y + bv.y, v1.y + bv.y),
+                                                     fmaxf(v0.z + bv.z, v1.z + bv.z), fmaxf(v0.w + bv.w, v1.w + bv.w));
+                        if (F16 && a.y_f16)           // the conv branch's output, already 11-bit operands deep: half the bytes to the pooling kernel
+                            *(reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.y) + (imgbase + pixoff[i]) * NT + col0) + seg) =
+                                make_uint2(rb_pack_h2(o.x, o.y), rb_pack_h2(o.z, o.w));
+                        else
+                            *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT + col0) + seg) = o;
                     }
                 }
             } else {
@@ -770,7 +774,7 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
                                        const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                        const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                        long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8,
-                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h);
+                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h, int y_f16);
 
 // img != null: stem mode — x is ignored, the block input is Conv2D(16, 1x1)(img) computed in the fill (Cin must be 16, no
 // residual, 256-thread configuration).
@@ -779,7 +783,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
                                  const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                  long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8, const float* stem_w,
                                  const float* stem_b, int hpool, const float* w1_pair, const float* w2_pair, const void* w1_h,
-                                 const void* w2_h, const void* xa, void* ya, const float* ya_scale, const float* ya_shift) {
+                                 const void* w2_h, const void* xa, void* ya, const float* ya_scale, const float* ya_shift, int y_f16) {
     if (B <= 0) return MMLA_OK;
     // w1_h / w2_h: the same weights as fp16 chunks (mmla_rb_arrange_weights_f16); when given the block runs with fp16 operands
     const bool f16 = w1_h && w2_h;
@@ -787,7 +791,7 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
         // operands: the stem block only)
         const int pr = mmla_try_launch_resblock2d_persist(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, w1, b1, bn2_scale, bn2_shift, w2, b2,
                                                           res, res_row_stride, st, img, img_is_u8, stem_w, stem_b, hpool,
-                                                          f16 && !ya ? w1_h : nullptr, f16 && !ya ? w2_h : nullptr);
+                                                          f16 && !ya ? w1_h : nullptr, f16 && !ya ? w2_h : nullptr, y_f16);
         if (pr < 0) return -pr;
         if (pr > 0) return MMLA_OK;
     }
@@ -810,7 +814,8 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
     s.img = img; s.img_is_u8 = img_is_u8; s.stem_w = stem_w; s.stem_b = stem_b;
     MMLA_REQUIRE(f16 || (!xa && !ya), MMLA_EINVAL, "resblock2d: fp16 activations need the fp16-operand mode");
     MMLA_REQUIRE(!ya || (!hpool && ya_scale && ya_shift), MMLA_EINVAL, "resblock2d: fp16 output needs the next block's BN and a full-resolution output");
-    s.xa = img ? nullptr : xa; s.ya = ya; s.ya_scale = ya_scale; s.ya_shift = ya_shift;
+    MMLA_REQUIRE(!y_f16 || (f16 && hpool), MMLA_EINVAL, "resblock2d: an fp16 output exists for the row-pooled fp16-operand form only");
+    s.xa = img ? nullptr : xa; s.ya = ya; s.ya_scale = ya_scale; s.ya_shift = ya_shift; s.y_f16 = y_f16;
     s.img_pixels = static_cast<long long>(H) * W;
     s.hpool = hpool;
     const int drop = hpool ? 4 : 3;                              // outputs a CTA gives up to the 4x1 halo (even for HPOOL)

@@ -453,9 +453,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) resblock2d_persist_kernel(const
                         if (pixoff[i] >= 0) {
                             const float4 v0 = *reinterpret_cast<const float4*>(stg + (8 * i + 2 * rsub) * 36 + 4 * seg);
                             const float4 v1 = *reinterpret_cast<const float4*>(stg + (8 * i + 2 * rsub + 1) * 36 + 4 * seg);
-                            *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT) + seg) =
-                                make_float4(fmaxf(v0.x + bv.x, v1.x + bv.x), fmaxf(v0.y + bv.y, v1.y + bv.y),
-                                            fmaxf(v0.z + bv.z, v1.z + bv.z), fmaxf(v0.w + bv.w, v1.w + bv.w));
+                            const float4 o = make_float4(fmaxf(v0.x + bv.x, v1.x + bv.x), fmaxf(v0.y + bv.y, v1.y + bv.y),
+                                                         fmaxf(v0.z + bv.z, v1.z + bv.z), fmaxf(v0.w + bv.w, v1.w + bv.w));
+                            if (F16 && a.y_f16)
+                                *(reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.y) + (imgbase + pixoff[i]) * NT) + seg) =
+                                    make_uint2(rb_pack_h2(o.x, o.y), rb_pack_h2(o.z, o.w));
+                            else
+                                *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT) + seg) = o;
                         }
                     }
                 } else {
@@ -509,7 +513,7 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
                                        const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                        const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                        long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8,
-                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h) {
+                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h, int y_f16) {
     // w1_h / w2_h: fp16 weight chunks (mmla_rb_arrange_weights_f16) => the fp16-operand form, built for the stem block only
     const bool f16 = w1_h && w2_h;
     if (f16 && !img) return 0;
@@ -531,6 +535,8 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
     s.img = img; s.img_is_u8 = img_is_u8; s.stem_w = stem_w; s.stem_b = stem_b;
     s.img_pixels = static_cast<long long>(H) * W;
     s.hpool = hpool;
+    s.y_f16 = f16 && hpool ? y_f16 : 0;
+    if (y_f16 && !s.y_f16) return 0;
     const int drop = hpool ? 4 : 3;
     s.H = H; s.W = W; s.Fp = H + drop;
     s.fp_magic = static_cast<unsigned>((1ULL << 32) / static_cast<unsigned>(s.Fp)) + 1u;
