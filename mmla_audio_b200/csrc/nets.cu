@@ -253,8 +253,11 @@ __device__ __forceinline__ uint32_t act_pack_h2(float lo, float hi) {
 // took 0.88 ms per 512 clips, this is bound by reading z once).
 // img != null (first block, stem folded into the conv-pair kernel): x is never materialised — the block input at the pooled
 // pixel is the stem Conv2D(16, 1x1) of the 3-channel image, recomputed here with stem1x1_kernel's expression (Cin = 16).
+#ifndef MMLA_POOL_MIN_CTAS
+#define MMLA_POOL_MIN_CTAS 3
+#endif
 template <bool Z16>
-__global__ void __launch_bounds__(256) pool_shortcut_kernel(const float* __restrict__ x, const float* __restrict__ z,
+__global__ void __launch_bounds__(256, MMLA_POOL_MIN_CTAS) pool_shortcut_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                                             const float* __restrict__ ws, const float* __restrict__ bs,
                                                             float* __restrict__ y, long long B, int H, int W, int Cin, int N,
                                                             const void* __restrict__ img, int img_is_u8,
