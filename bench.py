@@ -336,8 +336,14 @@ def kernel_work(workload: str, B: int, L: int, pipe, bulk_frames: int):
         work["stem_resblock2d_f16_kernel"] = {"bound": "tensor", "per_step": B * (slab_first + stem),
                                               "what": "stem Conv2D(16, 1x1) from the uint8 image + residual block 1's conv pair "
                                                       "at 128 x 151, fp16 operands / fp32 accumulation"}
+        work["resblock2d_persist_f16_kernel"] = {"bound": "tensor", "per_step": B * slab_23,
+                                                 "what": "residual blocks 2-3 (64 x 76 x 32): conv pairs with fp16 operands on the "
+                                                         "persistent, warp-specialised kernel"}
         work["stem_resblock2d_persist_f16_kernel"] = dict(work["stem_resblock2d_f16_kernel"],
                                                           what=work["stem_resblock2d_f16_kernel"]["what"] + ", persistent warp-specialised kernel")
+        if os.environ.get("MMLA_NET_PERSIST") == "2":
+            work["resblock2d_f16_kernel"] = dict(work["resblock2d_f16_kernel"], per_step=B * (slab - slab_first - slab_23),
+                                                 what="residual blocks 4-9 (C >= 64): conv pairs with fp16 operands / fp32 accumulation")
         if os.environ.get("MMLA_NET_PERSIST") == "2":        # blocks 2-3 on the persistent kernel as well
             work["resblock2d_fused_kernel"]["per_step"] = B * (slab - slab_first - slab_23)
             work["resblock2d_fused_kernel"]["what"] = ("residual blocks 4-9 (C >= 64): conv pairs (3x3 then 4x1, TF32, tap-shifted "
@@ -697,7 +703,7 @@ def main():
             for row in by_prec[prec]["kernels"]:
                 if row["kernel"] in ("conv_slab_kernel", "resblock2d_fused_kernel", "resblock2d_persist_kernel",
                                      "stem_resblock2d_persist_kernel", "resblock2d_f16_kernel", "stem_resblock2d_f16_kernel",
-                                     "stem_resblock2d_persist_f16_kernel",
+                                     "stem_resblock2d_persist_f16_kernel", "resblock2d_persist_f16_kernel",
                                      "overlap_features_kernel", "overlap_features_tc_kernel") and "frac" in row:
                     summary["overlap_%s_frac" % row["kernel"]] = round(row["frac"], 4)
         del po, po_dev, po_host, opipe

@@ -774,7 +774,8 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
                                        const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                        const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                        long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8,
-                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h, int y_f16);
+                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h, int y_f16,
+                                       const void* xa, void* ya, const float* ya_scale, const float* ya_shift);
 
 // img != null: stem mode — x is ignored, the block input is Conv2D(16, 1x1)(img) computed in the fill (Cin must be 16, no
 // residual, 256-thread configuration).
@@ -791,7 +792,8 @@ int mmla_launch_resblock2d_fused(const float* x, float* y, long long B, int H, i
         // operands: the stem block only)
         const int pr = mmla_try_launch_resblock2d_persist(x, y, B, H, W, Cin, C, bn1_scale, bn1_shift, w1, b1, bn2_scale, bn2_shift, w2, b2,
                                                           res, res_row_stride, st, img, img_is_u8, stem_w, stem_b, hpool,
-                                                          f16 && !ya ? w1_h : nullptr, f16 && !ya ? w2_h : nullptr, y_f16);
+                                                          f16 ? w1_h : nullptr, f16 ? w2_h : nullptr, y_f16, f16 ? xa : nullptr,
+                                                          f16 ? ya : nullptr, ya_scale, ya_shift);
         if (pr < 0) return -pr;
         if (pr > 0) return MMLA_OK;
     }

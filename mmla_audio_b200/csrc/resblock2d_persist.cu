@@ -55,7 +55,7 @@ __device__ __forceinline__ void ps_arrive(uint64_t* bar) {
 // per MMA, fp16 weight chunks.
 template <bool RES, bool STEM, bool HPOOL, bool F16 = false>
 __global__ void __launch_bounds__(kPsThreads, 1) resblock2d_persist_kernel(const RbArgs a) {
-    static_assert(!F16 || STEM, "the fp16-operand form of the persistent kernel is built for the stem block");
+    // (fp16 operands: the stem block, or a block whose producer has written the activated fp16 operand `xa`)
     constexpr uint32_t kIdesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (static_cast<uint32_t>(NT >> 3) << 17) |
                                 (static_cast<uint32_t>(128 >> 4) << 24);   // D=f32, A=B=tf32 (or f16), K-major, N, M=128
     constexpr uint32_t kChunkBytes = 8 * NT * 16;
@@ -276,6 +276,28 @@ __global__ void __launch_bounds__(kPsThreads, 1) resblock2d_persist_kernel(const
                         }
                     }
                 }
+            } else if constexpr (F16) {
+                // the producer of x has written ELU(BN1(x)) as fp16: a plain asynchronous gather, one channel octet of one row per
+                // copy (zero-fill form for the padding rows), every copy of the item in flight at once (resblock2d_fused.cu)
+                const int no = a.Cin >> 3;                            // channel octets per row: 2, 4
+                const int osh = no >= 4 ? 2 : 1;
+                const int rpi = 32 >> osh, ngrp = no >> osh;
+                const int c8 = ((fw % ngrp) << osh) + (lane >> (5 - osh));
+                const int rpp = (kPsFillWarps / ngrp) * rpi;
+                const uint16_t* ximg = static_cast<const uint16_t*>(a.xa) + static_cast<long long>(it.img) * a.img_pixels * a.Cin + 8 * c8;
+                unsigned char* dsth = slab + static_cast<size_t>(c8) * a.RsX * 16;
+                for (int r = (fw / ngrp) * rpi + (lane & (rpi - 1)); r < rows; r += rpp) {
+                    const int p = Qc - 1 + r;
+                    const int wp = static_cast<int>(__umulhi(static_cast<unsigned>(p < 0 ? 0 : p), a.fp_magic));
+                    const int w = wp - 1, h = p - wp * a.Fp - 1;
+                    const bool ok = p >= 0 && w >= 0 && w < a.W && h >= 0 && h < a.H;
+                    const uint16_t* src = ximg + (ok ? static_cast<long long>(h * a.W + w) * a.Cin : 0ll);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dsth + static_cast<size_t>(r) * 16)), "l"(src),
+                                 "r"(ok ? 16 : 0)
+                                 : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_all;" ::: "memory");
             } else {
                 const int lqg = a.lq - 2;                             // log2(quad groups of 4)
                 const int c4 = ((fw & ((1 << lqg) - 1)) << 2) + (lane >> 3);
@@ -403,6 +425,11 @@ __global__ void __launch_bounds__(kPsThreads, 1) resblock2d_persist_kernel(const
         const int seg = lane & 7, rsub = lane >> 3;
         constexpr int kRowsPerLane = HPOOL ? 4 : 8;
         const float4 bv = __ldg(reinterpret_cast<const float4*>(a.b2) + seg);
+        float4 ysc = make_float4(0.f, 0.f, 0.f, 0.f), ysh = ysc;      // F16: the next block's BN1 (its activated fp16 operand is written here)
+        if (F16 && !HPOOL && a.ya) {
+            ysc = __ldg(reinterpret_cast<const float4*>(a.ya_scale) + seg);
+            ysh = __ldg(reinterpret_cast<const float4*>(a.ya_shift) + seg);
+        }
         for (int k = 0; k < my; ++k) {
             const PsItem it = ps_item(a, k);
             const long long imgbase = static_cast<long long>(it.img) * (HPOOL ? a.img_pixels / 2 : a.img_pixels);
@@ -430,6 +457,22 @@ __global__ void __launch_bounds__(kPsThreads, 1) resblock2d_persist_kernel(const
                     }
                 }
             };
+            if constexpr (RES) {
+                // pull the residual rows of the NEXT item into L2 now (the block input is larger than L2: from DRAM every tile's
+                // residual load cost the whole memory latency, four times per item, with nothing to hide it behind — e2 20 k cycles)
+                auto l2_prefetch = [&](int kk) {
+                    const PsItem nx = ps_item(a, kk);
+                    const long long nbase = static_cast<long long>(nx.img) * a.img_pixels;
+                    for (int r = (warp - kPsE2Warp0) * 32 + lane; r < nx.nq; r += 128) {
+                        const int q = nx.Qc + r;
+                        const int wq = static_cast<int>(__umulhi(static_cast<unsigned>(q), a.fp_magic)), hq = q - wq * a.Fp;
+                        if (hq < a.H)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (nbase + hq * a.W + wq) * a.res_row_stride));
+                    }
+                };
+                if (k == 0) l2_prefetch(0);
+                if (k + 1 < my) l2_prefetch(k + 1);
+            }
             prefetch(0);                            // the residual's round trip overlaps conv2
             rb_wait(&bar.a2full, static_cast<uint32_t>(k & 1));                      // conv2 (k) complete
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -467,9 +510,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) resblock2d_persist_kernel(const
                     for (int i = 0; i < 8; ++i) { // rows 4i .. 4i+3 of the warp's 32, eight lanes (128 B) per row
                         if (pixoff[i] >= 0) {
                             const float4 v = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * 36 + 4 * seg);
-                            *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT) + seg) =
-                                RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
-                                    : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                            const float4 o = RES ? make_float4(v.x + bv.x + rr[i].x, v.y + bv.y + rr[i].y, v.z + bv.z + rr[i].z, v.w + bv.w + rr[i].w)
+                                                 : make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+                            *(reinterpret_cast<float4*>(a.y + (imgbase + pixoff[i]) * NT) + seg) = o;
+                            if (F16 && a.ya)
+                                *(reinterpret_cast<uint2*>(static_cast<uint16_t*>(a.ya) + (imgbase + pixoff[i]) * NT) + seg) =
+                                    make_uint2(rb_pack_h2(rb_bn_elu(o.x, ysc.x, ysh.x), rb_bn_elu(o.y, ysc.y, ysh.y)),
+                                               rb_pack_h2(rb_bn_elu(o.z, ysc.z, ysh.z), rb_bn_elu(o.w, ysc.w, ysh.w)));
                         }
                     }
                 }
@@ -499,7 +546,8 @@ int launch_ps(const RbArgs& s, unsigned grid, size_t smem, cudaStream_t st) {
         attr[dev] = smem;
     }
     kern<<<grid, kPsThreads, smem, st>>>(s);
-    mmla_count_launch(F16 ? "stem_resblock2d_persist_f16_kernel" : STEM ? "stem_resblock2d_persist_kernel" : "resblock2d_persist_kernel", st);
+    mmla_count_launch(F16 ? (STEM ? "stem_resblock2d_persist_f16_kernel" : "resblock2d_persist_f16_kernel")
+                          : STEM ? "stem_resblock2d_persist_kernel" : "resblock2d_persist_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;
 }
@@ -513,17 +561,24 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
                                        const float* bn1_shift, const float* w1, const float* b1, const float* bn2_scale,
                                        const float* bn2_shift, const float* w2, const float* b2, const float* res,
                                        long long res_row_stride, cudaStream_t st, const void* img, int img_is_u8,
-                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h, int y_f16) {
-    // w1_h / w2_h: fp16 weight chunks (mmla_rb_arrange_weights_f16) => the fp16-operand form, built for the stem block only
+                                       const float* stem_w, const float* stem_b, int hpool, const void* w1_h, const void* w2_h, int y_f16,
+                                       const void* xa, void* ya, const float* ya_scale, const float* ya_shift) {
+    // w1_h / w2_h: fp16 weight chunks (mmla_rb_arrange_weights_f16) => the fp16-operand form: the stem block, or a block whose
+    // producer has written the activated fp16 operand xa (the fill is then a plain asynchronous copy)
     const bool f16 = w1_h && w2_h;
-    if (f16 && !img) return 0;
+    if (f16 && !img && !xa) return 0;
     if (f16) { w1 = static_cast<const float*>(w1_h); w2 = static_cast<const float*>(w2_h); }
+    if (!f16 && (xa || ya)) return 0;
     const char* e = getenv("MMLA_NET_PERSIST");             // 0: never, 2: every C = 32 block, default: Cin = 16 (block 1) only
     if (e && e[0] == '0') return 0;
     // Measured (512 clips): block 1 (128 x 151, 16 -> 32) 0.866 -> 0.757 ms; blocks 2, 3 (64 x 76, 32 -> 32) 0.412 -> 0.417 ms — with
     // every role running at once the N = 32 MMAs take 83 instead of 45 cycles there (the SM's shared-memory bandwidth is shared
     // by 520 KB of operand fetches and 250 KB of fill / epilogue traffic per item), which is what the co-resident CTAs of the
     // one-CTA-per-item kernel already reached.
+    // fp16 operands, blocks 2, 3 (MMLA_NET_PERSIST=2; needs the activated fp16 operand xa): 0.299 -> 0.477 ms — the four epilogue-2
+    // warps need 17.5 k cycles per item for the residual add + the next block's fp16 operand (3.5-4 k per tile and warp, latency-
+    // bound chains; the one-CTA-per-item kernel puts eight warps on it and hides the rest behind co-resident CTAs), and every other
+    // role waits for them (profiles/r02/experiment_notes.txt).
     if (Cin != 16 && !(e && e[0] == '2')) return 0;
     if (C != 32 || (Cin != 16 && Cin != 32) || (img && Cin != 16) || (hpool && (res || (H & 1))) || (img && res)) return 0;
     if (res && res_row_stride != C) return 0;
@@ -533,6 +588,8 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
     s.bn1_scale = bn1_scale; s.bn1_shift = bn1_shift; s.bn2_scale = bn2_scale; s.bn2_shift = bn2_shift;
     s.res = res; s.res_row_stride = res_row_stride;
     s.img = img; s.img_is_u8 = img_is_u8; s.stem_w = stem_w; s.stem_b = stem_b;
+    s.xa = img ? nullptr : xa; s.ya = ya; s.ya_scale = ya_scale; s.ya_shift = ya_shift;
+    if (ya && (hpool || !ya_scale || !ya_shift)) return 0;
     s.img_pixels = static_cast<long long>(H) * W;
     s.hpool = hpool;
     s.y_f16 = f16 && hpool ? y_f16 : 0;
@@ -626,6 +683,8 @@ int mmla_try_launch_resblock2d_persist(const float* x, float* y, long long B, in
     }
     int rc;
     if (img && f16) rc = hpool ? launch_ps<false, true, true, true>(s, grid, smem, st) : launch_ps<false, true, false, true>(s, grid, smem, st);
+    else if (f16 && res) rc = launch_ps<true, false, false, true>(s, grid, smem, st);
+    else if (f16) rc = hpool ? launch_ps<false, false, true, true>(s, grid, smem, st) : launch_ps<false, false, false, true>(s, grid, smem, st);
     else if (img) rc = hpool ? launch_ps<false, true, true>(s, grid, smem, st) : launch_ps<false, true, false>(s, grid, smem, st);
     else if (res) rc = launch_ps<true, false, false>(s, grid, smem, st);
     else rc = hpool ? launch_ps<false, false, true>(s, grid, smem, st) : launch_ps<false, false, false>(s, grid, smem, st);

@@ -19,7 +19,7 @@ for _ in range(reps):
     tr = _lib.trace_launches(lambda: pipe.run_device(pcm), torch)
     i = 0
     for n, ms in tr:
-        if n in ("stem_resblock2d_persist_f16_kernel", "resblock2d_f16_kernel", "stem_resblock2d_f16_kernel", "resblock2d_fused_kernel", "stem_resblock2d_fused_kernel", "resblock2d_persist_kernel", "stem_resblock2d_persist_kernel", "conv_slab_kernel", "pool_shortcut_kernel", "stem1x1_kernel"):
+        if n in ("resblock2d_persist_f16_kernel", "stem_resblock2d_persist_f16_kernel", "resblock2d_f16_kernel", "stem_resblock2d_f16_kernel", "resblock2d_fused_kernel", "stem_resblock2d_fused_kernel", "resblock2d_persist_kernel", "stem_resblock2d_persist_kernel", "conv_slab_kernel", "pool_shortcut_kernel", "stem1x1_kernel"):
             acc[(i, n)] = acc.get((i, n), 0.0) + ms / reps
             i += 1
 tot = {}

@@ -195,15 +195,19 @@ def test_fp16_mode_activated_operand_handoff_is_bitwise_neutral(cuda, monkeypatc
         monkeypatch.setenv("MMLA_NET_F16_ACT", mode)
         tr = _lib.trace_launches(lambda: out.__setitem__(mode, model.predict_device(x8)[0].clone()), torch)
         names = [n for n, _ in tr]
-        assert names.count("resblock2d_f16_kernel") == 8 and names.count("stem_resblock2d_persist_f16_kernel") == 1, names
+        assert names.count("stem_resblock2d_persist_f16_kernel") == 1 and names.count("resblock2d_f16_kernel") == 8, names
     monkeypatch.delenv("MMLA_NET_F16_ACT")
     assert torch.equal(out["0"], out["1"])
     # block 1 on the one-CTA-per-item kernel instead of the persistent one: the same bits
     monkeypatch.setenv("MMLA_NET_PERSIST", "0")
     tr = _lib.trace_launches(lambda: out.__setitem__("np", model.predict_device(x8)[0].clone()), torch)
-    assert [n for n, _ in tr].count("stem_resblock2d_f16_kernel") == 1
+    assert [n for n, _ in tr].count("stem_resblock2d_f16_kernel") == 1 and [n for n, _ in tr].count("resblock2d_f16_kernel") == 8
+    # ... and blocks 2, 3 on the persistent kernel's fp16 form (fill = the producer's fp16 operand, epilogue 2 writes the next one)
+    monkeypatch.setenv("MMLA_NET_PERSIST", "2")
+    tr = _lib.trace_launches(lambda: out.__setitem__("p2", model.predict_device(x8)[0].clone()), torch)
+    assert [n for n, _ in tr].count("resblock2d_persist_f16_kernel") == 2
     monkeypatch.delenv("MMLA_NET_PERSIST")
-    assert torch.equal(out["np"], out["1"])
+    assert torch.equal(out["np"], out["1"]) and torch.equal(out["p2"], out["1"])
     # opt-in MMLA_NET_F16_Z=1: the pooled blocks' row-pooled conv output travels to pool_shortcut_kernel as fp16: not bitwise
     # neutral — one more 11-bit rounding of a value that is already two 11-bit-operand convolutions deep — but small
     monkeypatch.setenv("MMLA_NET_F16_Z", "1")
