@@ -33,7 +33,7 @@ def sources():
 
 def _digest() -> str:
     h = hashlib.sha256()
-    files = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
+    files = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".inc"))]
     files.append(os.path.join(INCLUDE, "mmla_b200.h"))
     for f in files:
         h.update(f.encode())

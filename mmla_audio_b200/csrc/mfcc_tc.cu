@@ -743,6 +743,8 @@ __global__ void __launch_bounds__(kThreads, 1) mfcc_tc_kernel(const __grid_const
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+#include "mfcc_tc2.inc"
+
 // ---------------------------------------------------------------------------------------------
 // Finish pass: delta, delta-delta (reference `delta(feat, 2)` applied twice, edge replicated) and
 // zero rows up to pad_frames.  One CTA handles 128 rows of one clip.
@@ -923,6 +925,80 @@ int launch_tc(const TcParams& kp, long long grid, cudaStream_t st) {
     return MMLA_OK;
 }
 
+std::map<std::pair<int, int>, unsigned char*> g_consts2;     // per (device, nfilt), mfcc_tc2_kernel
+
+void put_split2(unsigned char* hi, unsigned char* lo, int n, int k, double v) {
+    // B[n][k], 64 x 64, UMMA K-major no-swizzle: core matrix (n/8, k/8) = 8 rows x 16 B, N-group stride 1024 B
+    const size_t off = static_cast<size_t>(n / 8) * 1024 + static_cast<size_t>(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+    const __half h = __float2half_rn(static_cast<float>(v));
+    const __half l = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
+    memcpy(hi + off, &h, 2);
+    memcpy(lo + off, &l, 2);
+}
+
+int get_consts2(int nfilt, const unsigned char** out) {
+    int dev = 0;
+    MMLA_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_consts2.find(std::make_pair(dev, nfilt));
+    if (it != g_consts2.end()) {
+        *out = it->second;
+        return MMLA_OK;
+    }
+    std::vector<unsigned char> host(k2ConstBytes, 0);
+    unsigned char* bh = host.data();
+    unsigned char* bl = bh + k2B1Bytes;
+    float2* tw = reinterpret_cast<float2*>(bl + k2B1Bytes);
+    float* dct = reinterpret_cast<float*>(tw + 8 * k2TwStride);
+    const double PI = 3.14159265358979323846;
+    // stage 1: column 0 = Re S[.][0], column 1 = Re S[.][32], columns 2j, 2j+1 = Re, Im of S[.][j]; rows n1 >= 50 are the
+    // frame's zero padding (8 * 50 = 400 samples)
+    for (int n1 = 0; n1 < 64; ++n1) {
+        const double live = n1 < 50 ? 1.0 : 0.0;
+        put_split2(bh, bl, 0, n1, live);
+        put_split2(bh, bl, 1, n1, live * ((n1 & 1) ? -1.0 : 1.0));
+        for (int j = 1; j < 32; ++j) {
+            const double th = 2.0 * PI * ((n1 * j) % 64) / 64.0;
+            put_split2(bh, bl, 2 * j, n1, live * cos(th));
+            put_split2(bh, bl, 2 * j + 1, n1, -live * sin(th));
+        }
+    }
+    for (int r = 0; r < 8; ++r)
+        for (int k1 = 0; k1 <= 32; ++k1) {
+            const double th = 2.0 * PI * ((r * k1) % 512) / 512.0;
+            tw[r * k2TwStride + k1] = make_float2(static_cast<float>(kS2 * cos(th)), static_cast<float>(-kS2 * sin(th)));
+        }
+    for (int c = 0; c < 13; ++c) {
+        const double scale = c == 0 ? sqrt(1.0 / nfilt) : sqrt(2.0 / nfilt);
+        const double lift = 1.0 + (22 / 2.0) * sin(PI * c / 22);
+        for (int m = 0; m < nfilt; ++m)
+            dct[m * 16 + (c < 7 ? c : c + 1)] = static_cast<float>(lift * scale * cos(PI * c * (2 * m + 1) / (2.0 * nfilt)));
+    }
+    unsigned char* devp = nullptr;
+    cudaError_t e = cudaMalloc(&devp, k2ConstBytes);
+    if (e == cudaSuccess) e = cudaMemcpy(devp, host.data(), k2ConstBytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        mmla_set_error("mfcc_tc2 constants upload failed: %s", cudaGetErrorString(e));
+        return MMLA_ECUDA;
+    }
+    g_consts2[std::make_pair(dev, nfilt)] = devp;
+    *out = devp;
+    return MMLA_OK;
+}
+
+template <int NF>
+int launch_tc2(const TcParams& kp, long long grid, cudaStream_t st) {
+    static MmlaPerDeviceOnce attr_once;
+    const int smem = static_cast<int>(sizeof(Tc2Smem));
+    if (attr_once.first()) {
+        MMLA_CUDA_CHECK(cudaFuncSetAttribute(mfcc_tc2_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    mfcc_tc2_kernel<NF><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(kp);
+    mmla_count_launch("mfcc_tc2_kernel", st);
+    MMLA_CUDA_CHECK(cudaGetLastError());
+    return MMLA_OK;
+}
+
 }  // namespace
 
 // Returns MMLA_OK and *handled = 1 when the tensor-core path ran; *handled = 0 when the
@@ -970,8 +1046,12 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     }
     if (n_groups == 0) return MMLA_OK;
 
+    // MMLA_MFCC_TC=2 selects the 64 x 8 formulation (mfcc_tc2_kernel); the debug dumps / clock stamps exist only in the
+    // 32 x 16 kernel
+    const char* form = getenv("MMLA_MFCC_TC");
+    const bool use_tc2 = form && strcmp(form, "2") == 0 && !dbg;
     const unsigned char* consts = nullptr;
-    int rc = get_consts(p.nfilt, &consts);
+    int rc = use_tc2 ? get_consts2(p.nfilt, &consts) : get_consts(p.nfilt, &consts);
     if (rc != MMLA_OK) return rc;
 
     TcParams kp;
@@ -1017,7 +1097,8 @@ int mmla_mfcc_tc_try(const int16_t* pcm, int64_t pcm_total, const int64_t* clip_
     MMLA_REQUIRE(sms > 0, MMLA_ECUDA, "mfcc_tc: no CUDA device");
     const long long n_tiles = (n_groups + kTileGroups - 1) / kTileGroups;
     const long long grid = n_tiles < sms ? n_tiles : sms;
-    if (dbg || prof) rc = p.nfilt == 26 ? launch_tc<26, true>(kp, grid, st) : launch_tc<40, true>(kp, grid, st);
+    if (use_tc2) rc = p.nfilt == 26 ? launch_tc2<26>(kp, grid, st) : launch_tc2<40>(kp, grid, st);
+    else if (dbg || prof) rc = p.nfilt == 26 ? launch_tc<26, true>(kp, grid, st) : launch_tc<40, true>(kp, grid, st);
     else rc = p.nfilt == 26 ? launch_tc<26, false>(kp, grid, st) : launch_tc<40, false>(kp, grid, st);
     if (rc != MMLA_OK) return rc;
 
