@@ -137,6 +137,11 @@ __device__ __forceinline__ Group decode_group(const TcParams& p, int G) {
     return g;
 }
 
+// One out-of-line copy of the group arithmetic for the roles of mfcc_tc2_kernel (code size: its roles share a small
+// instruction cache).  mfcc_tc_kernel keeps the inlined form: the out-of-line call, a compact signal loop and a rolled TMA
+// loop were measured on it and ran 3-6 % slower (profiles/r02/experiment_notes.txt).
+__device__ __noinline__ Group decode_group2(const TcParams& p, int G) { return decode_group(p, G); }
+
 // mbarrier wait that parks the warp in hardware (suspend-time hint) instead of polling, so waiting
 // roles do not steal issue slots from working ones; traps instead of hanging the GPU on a logic error.
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
@@ -972,7 +977,7 @@ int get_consts2(int nfilt, const unsigned char** out) {
         const double scale = c == 0 ? sqrt(1.0 / nfilt) : sqrt(2.0 / nfilt);
         const double lift = 1.0 + (22 / 2.0) * sin(PI * c / 22);
         for (int m = 0; m < nfilt; ++m)
-            dct[m * 16 + (c < 7 ? c : c + 1)] = static_cast<float>(lift * scale * cos(PI * c * (2 * m + 1) / (2.0 * nfilt)));
+            dct[m * 16 + c] = static_cast<float>(lift * scale * cos(PI * c * (2 * m + 1) / (2.0 * nfilt)));
     }
     unsigned char* devp = nullptr;
     cudaError_t e = cudaMalloc(&devp, k2ConstBytes);
@@ -993,7 +998,7 @@ int launch_tc2(const TcParams& kp, long long grid, cudaStream_t st) {
     if (attr_once.first()) {
         MMLA_CUDA_CHECK(cudaFuncSetAttribute(mfcc_tc2_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-    mfcc_tc2_kernel<NF><<<static_cast<unsigned>(grid), kThreads, smem, st>>>(kp);
+    mfcc_tc2_kernel<NF><<<static_cast<unsigned>(grid), k2Threads, smem, st>>>(kp);
     mmla_count_launch("mfcc_tc2_kernel", st);
     MMLA_CUDA_CHECK(cudaGetLastError());
     return MMLA_OK;

@@ -238,3 +238,82 @@ def test_stem_inside_first_stage_matches_separate_stem(cuda, monkeypatch):
         d = float((pf - ps).abs().max())
         print(f"stem in stage vs separate, {n} clips x {clip_len}: max |dprob| {d:.2e}")
         assert d <= 2e-6 and torch.equal(lf, ls)
+
+
+# ---------------------------------------------------------------------------------------------
+# mfcc_tc2_kernel: the 64 x 8 formulation (csrc/mfcc_tc2.inc), selected with MMLA_MFCC_TC=2
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nfilt", [26, 40])
+def test_tc2_formulation_matches_oracle_and_tc1(cuda, monkeypatch, nfilt):
+    """Same bar as the 32 x 16 kernel (1e-4 rel + 1e-4 of max |ref|), several clip lengths incl. partial last groups."""
+    from mmla_audio_b200 import speaker_identification as si
+    cfg = si.MfccConfig(nfilt=nfilt)
+    for clip_len in (40000, 24000, 40960, 4000, 8000):
+        pcm = synth.synth_clips(700 + clip_len % 97, 5, clip_len)
+        monkeypatch.delenv("MMLA_MFCC_TC", raising=False)
+        tc1 = si.mfcc_batch(pcm, cfg).cpu().numpy()
+        monkeypatch.setenv("MMLA_MFCC_TC", "2")
+        assert _launch_names(lambda: si.mfcc_batch(pcm, cfg)) == ["mfcc_tc2_kernel"]
+        tc2 = si.mfcc_batch(pcm, cfg).cpu().numpy()
+        for i in range(pcm.shape[0]):
+            ref = ref_mfcc(pcm[i], nfilt=nfilt)
+            assert_mfcc_close(tc2[i], ref)
+            assert_mfcc_close(tc2[i], tc1[i])
+
+
+def test_tc2_features_padding_ragged_edges_and_windows(cuda, monkeypatch):
+    """The callers of the kernel: MFCC-39 padded to 256 rows (finish pass), a ragged batch, the edge clips of
+    test_mfcc_gpu.py, overlapping windows as a strided view, 16-float rows with the zero tail written by the epilogue."""
+    import torch
+    from mmla_audio_b200 import speaker_identification as si
+    from mmla_audio_b200.pipeline import window_view
+    monkeypatch.setenv("MMLA_MFCC_TC", "2")
+    pcm = synth.synth_clips(720, 3, 24000)
+    assert _launch_names(lambda: si.speaker_features_batch(pcm)) == ["mfcc_tc2_kernel", "mfcc_finish_kernel"]
+    out = si.speaker_features_batch(pcm).cpu().numpy()
+    for i in range(3):
+        assert_mfcc_close(out[i], psf.input_feature_gen(pcm[i])[0])
+    # ragged
+    lens = [40000, 4001, 24000, 163, 33333]
+    clips = [synth.synth_clips(750 + i, 1, n)[0] for i, n in enumerate(lens)]
+    offs, pos = [], 0
+    for c in clips:
+        pos = (pos + 7) // 8 * 8
+        offs.append(pos)
+        pos += len(c)
+    buf = np.zeros(pos + 8, np.int16)
+    for o, c in zip(offs, clips):
+        buf[o:o + len(c)] = c
+    got, rows = si.mfcc_ragged(buf, offs, lens, with_deltas=True)
+    got = got.cpu().numpy()
+    for i, c in enumerate(clips):
+        assert_mfcc_close(got[i, :rows[i]], psf.mfcc39(c))
+    # edge clips
+    rng = np.random.default_rng(5)
+    cases = {
+        "zero": np.zeros(8000, np.int16),
+        "dc": np.full(8000, 1234, np.int16),
+        "square": (np.where((np.arange(8000) // 40) % 2 == 0, 32767, -32768)).astype(np.int16),
+        "short": rng.integers(-3000, 3000, 137).astype(np.int16),
+        "one_frame": rng.integers(-3000, 3000, 400).astype(np.int16),
+        "ragged": rng.integers(-20000, 20000, 12345).astype(np.int16),
+        "noise_fs": rng.integers(-32768, 32767, 16000).astype(np.int16),
+    }
+    for name, sig in cases.items():
+        g = si.mfcc_batch(sig)[0].cpu().numpy()
+        ref = ref_mfcc(sig)
+        assert g.shape == ref.shape, name
+        if name == "zero":
+            np.testing.assert_allclose(g, ref, rtol=1e-5, atol=1e-4, err_msg=name)
+        else:
+            assert_mfcc_close(g, ref)
+    # overlapping windows (clip_stride < clip_len) and 16-float rows
+    rec = synth.synth_clips(760, 4, 40000).reshape(-1)
+    wins = window_view(torch.from_numpy(rec).cuda(), 24000, 8000)
+    w = si.mfcc_batch(wins).cpu().numpy()
+    for j in (0, 1, wins.shape[0] - 1):
+        assert_mfcc_close(w[j], ref_mfcc(rec[j * 8000:j * 8000 + 24000]))
+    wide = si.mfcc_batch(pcm, row_stride=16).cpu().numpy()
+    assert wide.shape[-1] == 16 and not wide[..., 13:].any()
+    for i in range(3):
+        assert_mfcc_close(wide[i, :, :13], ref_mfcc(pcm[i]))
